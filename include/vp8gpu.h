@@ -1,0 +1,261 @@
+/* vp8gpu.h -- C ABI of the B200-native VP8 pixel pipeline.
+ *
+ * This is the drop-in boundary for the hot path of excamera/alfalfa's src/decoder
+ * (SURVEY.md section 8b).  Alfalfa has no FFI of its own: its boundary is the C++
+ * class API, so every entry point below names the reference interface it stands in for
+ * (paths relative to /root/reference/src).  Plain pointers and sizes only; no C++ or
+ * torch types cross this line.  The C++ mirror of the reference classes that sits on
+ * top of this ABI is alfalfa_b200/host/alfalfa_gpu.hh; INTEGRATION.md shows the
+ * reference-side binding.
+ *
+ * Layering (top to bottom):
+ *   vp8gpu_decoder_*   = Decoder           (decoder/decoder.hh:244-300)
+ *   vp8gpu_parse_*     = DecoderState::parse_and_apply (decoder/decoder_state.hh:73-167)
+ *   vp8gpu_decode_parsed = Frame::decode + Frame::loopfilter (decoder/frame.cc:139-250),
+ *                        the narrowest seam: parsed records in, pixels out
+ *   vp8gpu_frame_*     = RasterHandle / MutableRasterHandle (decoder/raster_handle.hh)
+ *
+ * Every function returns an int status (VP8GPU_OK or a negative VP8GPU_ERR_*), never
+ * throws, and never falls back to a CPU implementation: if the CUDA device or the
+ * kernels are unavailable the call fails with VP8GPU_ERR_CUDA.
+ */
+#ifndef VP8GPU_H
+#define VP8GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes: one per reference exception class (util/exception.hh:76-98) ---- */
+#define VP8GPU_OK                0
+#define VP8GPU_ERR_INVALID      -1 /* Invalid: malformed bitstream                     */
+#define VP8GPU_ERR_UNSUPPORTED  -2 /* Unsupported: legal VP8 the reference also rejects */
+#define VP8GPU_ERR_LOGIC        -3 /* LogicError / bad argument                        */
+#define VP8GPU_ERR_CUDA         -4 /* CUDA runtime failure (no device, launch error)   */
+#define VP8GPU_ERR_NOMEM        -5 /* pool exhausted / allocation failure              */
+
+/* ---- prediction modes: numbering of decoder/modemv_data.hh:41-50 ---- */
+enum {
+  VP8GPU_DC_PRED = 0, VP8GPU_V_PRED, VP8GPU_H_PRED, VP8GPU_TM_PRED, VP8GPU_B_PRED,
+  VP8GPU_NEARESTMV, VP8GPU_NEARMV, VP8GPU_ZEROMV, VP8GPU_NEWMV, VP8GPU_SPLITMV
+};
+enum {
+  VP8GPU_B_DC_PRED = 0, VP8GPU_B_TM_PRED, VP8GPU_B_VE_PRED, VP8GPU_B_HE_PRED, VP8GPU_B_LD_PRED,
+  VP8GPU_B_RD_PRED, VP8GPU_B_VR_PRED, VP8GPU_B_VL_PRED, VP8GPU_B_HD_PRED, VP8GPU_B_HU_PRED
+};
+/* reference_frame of decoder/modemv_data.hh:52 */
+enum { VP8GPU_REF_CURRENT = 0, VP8GPU_REF_LAST, VP8GPU_REF_GOLDEN, VP8GPU_REF_ALTREF };
+
+/* ---- the parsed-frame records that cross the seam (host -> HBM) ----
+ *
+ * One frame = one vp8gpu_frame_desc + mb_cols*mb_rows vp8gpu_mb records (raster order) +
+ * a token stream + the split-MV side array.  This is what the CPU entropy front end
+ * emits instead of the reference's TwoD<Macroblock>/Block object graph
+ * (decoder/frame.hh:56-61, block.hh:128-146).
+ */
+
+/* One non-zero quantised coefficient, exactly as decoded by tokens.cc:50-135 (NOT
+ * dequantised, NOT transformed; the GPU back end does that):
+ *   bits  0..15  value (int16, two's complement)
+ *   bits 16..19  coefficient position in raster order inside the 4x4 block
+ *                (= zigzag[index], tokens.hh:60)
+ *   bits 20..24  block: 0..15 Y (raster order), 16..19 U, 20..23 V, 24 Y2
+ */
+typedef uint32_t vp8gpu_token;
+#define VP8GPU_TOKEN(blk, pos, val) \
+  ((uint32_t)(uint16_t)(val) | ((uint32_t)(pos) << 16) | ((uint32_t)(blk) << 20))
+#define VP8GPU_BLK_U  16
+#define VP8GPU_BLK_V  20
+#define VP8GPU_BLK_Y2 24
+
+#define VP8GPU_MB_HAS_Y2 1u /* Y2Block::coded(): y_mode is neither B_PRED nor SPLITMV */
+
+/* 32 bytes per macroblock. */
+typedef struct vp8gpu_mb {
+  uint32_t tok_off;    /* first token of this MB in the frame's token stream          */
+  uint16_t tok_cnt;    /* number of tokens; 0 <=> Macroblock::has_nonzero_ == false    */
+  uint8_t  y_mode;     /* VP8GPU_DC_PRED .. VP8GPU_SPLITMV                             */
+  uint8_t  uv_mode;    /* VP8GPU_DC_PRED .. VP8GPU_TM_PRED (intra MBs)                 */
+  uint8_t  ref_frame;  /* VP8GPU_REF_*; CURRENT = intra-coded                          */
+  uint8_t  segment_id; /* 0..3, row of vp8gpu_frame_desc.quant                         */
+  uint8_t  lf_level;   /* loop-filter level after segment/ref/mode adjustment and the
+                          single clamp of loopfilter.cc:85 (0..63); 0 = MB not filtered */
+  uint8_t  flags;      /* VP8GPU_MB_*                                                  */
+  int16_t  mv_x, mv_y; /* base motion vector (Y_.at(3,3)), 1/8-pel units, luma even   */
+  uint32_t split_idx;  /* SPLITMV: entry in the split-MV side array                    */
+  uint32_t reserved;
+  uint64_t b_modes;    /* B_PRED: 16 x 4-bit VP8GPU_B_*; sub-block i in bits 4i..4i+3  */
+} vp8gpu_mb;
+
+/* 16 luma motion vectors of a SPLITMV macroblock, raster order, (x, y) pairs. */
+typedef struct vp8gpu_split_mvs { int16_t mv[16][2]; } vp8gpu_split_mvs;
+
+/* Dequantisation factors of one segment, already resolved from QuantIndices the way
+ * Quantizer::Quantizer does (decoder/quantization.cc:83-93). */
+typedef struct vp8gpu_quant {
+  uint16_t y_dc, y_ac, y2_dc, y2_ac, uv_dc, uv_ac;
+} vp8gpu_quant;
+
+typedef struct vp8gpu_frame_desc {
+  uint16_t width, height;       /* display size                                        */
+  uint16_t mb_cols, mb_rows;    /* ceil(width/16), ceil(height/16)                     */
+  uint8_t  key_frame;
+  uint8_t  show_frame;
+  uint8_t  loop_filter_level;   /* frame header value; 0 disables the whole pass
+                                   (frame.cc:144)                                      */
+  uint8_t  sharpness;           /* 0..7                                                */
+  uint8_t  pad0[4];
+  vp8gpu_quant quant[4];        /* per segment (all four equal when segmentation off)  */
+  uint32_t n_tokens;
+  uint32_t n_split;             /* entries in the split-MV side array                  */
+  /* reference-buffer update (frame.cc:272-307), applied by the host after decoding */
+  uint8_t  refresh_last, refresh_golden, refresh_alternate;
+  uint8_t  copy_to_golden;      /* 0 none, 1 last, 2 alternate                         */
+  uint8_t  copy_to_alternate;   /* 0 none, 1 last, 2 golden                            */
+  uint8_t  pad1[3];
+} vp8gpu_frame_desc;
+
+/* ---- context, device frames ---- */
+
+typedef struct vp8gpu_ctx vp8gpu_ctx;
+typedef int32_t vp8gpu_frame_id; /* handle of a ref-counted device raster, >= 0 */
+
+/* Create a context on CUDA device `device` for rasters of display size width x height.
+ * `max_frames` bounds the device frame pool (each frame is 1.5 * W16 * H16 bytes, planar
+ * Y/U/V, MB-aligned like VP8Raster, vp8_raster.hh:53 / prediction.cc:87-90); 0 = default.
+ * Unlike the reference's process-global pools (raster_handle.cc:74-83) a context is
+ * independent of every other context, so several frame sizes can coexist. */
+int vp8gpu_ctx_create(int device, int width, int height, int max_frames, vp8gpu_ctx** out);
+void vp8gpu_ctx_destroy(vp8gpu_ctx* ctx);
+const char* vp8gpu_last_error(const vp8gpu_ctx* ctx); /* text of the last failure */
+
+/* MutableRasterHandle(width,height) (raster_handle.cc:145): a writable frame, refcount 1.
+ * Contents are undefined until written by upload or decode. */
+int vp8gpu_frame_alloc(vp8gpu_ctx* ctx, vp8gpu_frame_id* out);
+/* RasterHandle copy / destruction (shared_ptr semantics, raster_handle.hh:95-123). */
+int vp8gpu_frame_retain(vp8gpu_ctx* ctx, vp8gpu_frame_id id);
+int vp8gpu_frame_release(vp8gpu_ctx* ctx, vp8gpu_frame_id id);
+/* Copy the MB-aligned planes host<->device. Strides in bytes; the planes are
+ * 16*mb_cols x 16*mb_rows (Y) and half that (U, V).  download blocks until done. */
+int vp8gpu_frame_upload(vp8gpu_ctx* ctx, vp8gpu_frame_id id, const uint8_t* y, size_t y_stride,
+                        const uint8_t* u, const uint8_t* v, size_t uv_stride);
+int vp8gpu_frame_download(vp8gpu_ctx* ctx, vp8gpu_frame_id id, uint8_t* y, size_t y_stride,
+                          uint8_t* u, uint8_t* v, size_t uv_stride);
+/* BaseRaster::dump (util/raster.cc:85-114): the display rectangle as packed planar
+ * Y, U, V into `dst` (size width*height + 2*ceil(w/2)*ceil(h/2)). Blocks until done. */
+int vp8gpu_frame_download_display(vp8gpu_ctx* ctx, vp8gpu_frame_id id, uint8_t* dst, size_t dst_size);
+/* Same copy, asynchronous: queued behind the frame's producer; `dst` should be pinned
+ * (vp8gpu_host_alloc).  vp8gpu_ctx_sync waits for everything queued so far. */
+int vp8gpu_frame_download_display_async(vp8gpu_ctx* ctx, vp8gpu_frame_id id, uint8_t* dst, size_t dst_size);
+int vp8gpu_ctx_sync(vp8gpu_ctx* ctx);
+int vp8gpu_host_alloc(void** out, size_t bytes); /* pinned host memory */
+void vp8gpu_host_free(void* p);
+
+/* ---- the seam: Frame::decode + Frame::loopfilter on parsed records ----
+ *
+ * Replaces the two calls at decoder/decoder.cc:109-111 (and encoder/encoder.cc:155-156).
+ * refs[] = {last, golden, alternative} as in References (decoder.hh:123-141); ignored
+ * for key frames.  `out` must be a frame from vp8gpu_frame_alloc that nobody else reads.
+ * The call is asynchronous with respect to the host (work is queued on `lane`, a small
+ * integer naming one of the context's CUDA streams; use one lane per decoder instance so
+ * independent decoders overlap on the device).  Host buffers are consumed before return.
+ */
+int vp8gpu_decode_parsed(vp8gpu_ctx* ctx, int lane, const vp8gpu_frame_desc* desc,
+                         const vp8gpu_mb* mbs, const vp8gpu_token* tokens,
+                         const vp8gpu_split_mvs* split, const vp8gpu_frame_id refs[3],
+                         vp8gpu_frame_id out);
+
+/* Batched form of the seam: n independent frames (different decoders / GOPs / streams)
+ * in one set of kernel launches.  All arrays have n entries. */
+typedef struct vp8gpu_job {
+  const vp8gpu_frame_desc* desc;
+  const vp8gpu_mb* mbs;
+  const vp8gpu_token* tokens;
+  const vp8gpu_split_mvs* split;
+  vp8gpu_frame_id refs[3];
+  vp8gpu_frame_id out;
+} vp8gpu_job;
+int vp8gpu_decode_batch(vp8gpu_ctx* ctx, int lane, const vp8gpu_job* jobs, int n);
+
+/* Device-resident batch: records are uploaded once, then the kernels can be run any
+ * number of times (used by bench.py for the HBM-resident `value` measurement and by
+ * profilers).  `kernel_ms`, if not NULL, receives the device time of this run measured
+ * with CUDA events on the launching stream. */
+typedef struct vp8gpu_resident_batch vp8gpu_resident_batch;
+int vp8gpu_batch_upload(vp8gpu_ctx* ctx, const vp8gpu_job* jobs, int n, vp8gpu_resident_batch** out);
+int vp8gpu_batch_run(vp8gpu_ctx* ctx, int lane, vp8gpu_resident_batch* b, float* kernel_ms);
+void vp8gpu_batch_free(vp8gpu_ctx* ctx, vp8gpu_resident_batch* b);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+uint64_t vp8gpu_launch_count(const vp8gpu_ctx* ctx);
+
+/* ---- CPU entropy front end: DecoderState::parse_and_apply ----
+ *
+ * vp8gpu_state is DecoderState (decoder.hh:190-225): probability tables, segmentation
+ * (incl. the persistent segment map) and loop-filter adjustments.  It is a plain value:
+ * clone is a deep copy, equal/hash follow DecoderState::operator== / hash.
+ */
+typedef struct vp8gpu_state vp8gpu_state;
+int vp8gpu_state_create(int width, int height, vp8gpu_state** out);
+int vp8gpu_state_clone(const vp8gpu_state* s, vp8gpu_state** out);
+void vp8gpu_state_destroy(vp8gpu_state* s);
+int vp8gpu_state_equal(const vp8gpu_state* a, const vp8gpu_state* b);
+uint64_t vp8gpu_state_hash(const vp8gpu_state* s);
+
+/* A parsed frame (KeyFrame / InterFrame, frame.hh:126-127) in flat form. The arrays are
+ * owned by the vp8gpu_parsed object and stay valid until it is destroyed or reused. */
+typedef struct vp8gpu_parsed vp8gpu_parsed;
+int vp8gpu_parsed_create(vp8gpu_parsed** out);
+void vp8gpu_parsed_destroy(vp8gpu_parsed* p);
+const vp8gpu_frame_desc* vp8gpu_parsed_desc(const vp8gpu_parsed* p);
+const vp8gpu_mb* vp8gpu_parsed_mbs(const vp8gpu_parsed* p);
+const vp8gpu_token* vp8gpu_parsed_tokens(const vp8gpu_parsed* p);
+const vp8gpu_split_mvs* vp8gpu_parsed_split(const vp8gpu_parsed* p);
+
+/* Decoder::decompress_frame + parse_frame<KeyFrame|InterFrame> (decoder.cc:83-98):
+ * parse one compressed VP8 frame, update `state` exactly as parse_and_apply does, and
+ * fill `out`.  Errors: INVALID (truncated / bad start code / bad partition sizes),
+ * UNSUPPORTED (version != 0, scaling, colour space / clamping bits, simple filter,
+ * size != state size), mirroring uncompressed_chunk.cc:34-130 and frame_header.hh:213-295.
+ * On error `state` is unchanged. */
+int vp8gpu_parse_frame(vp8gpu_state* state, const uint8_t* data, size_t len, vp8gpu_parsed* out);
+
+/* ---- Decoder (decoder.hh:244-300): DecoderState + References, explicit state passing ---- */
+typedef struct vp8gpu_decoder vp8gpu_decoder;
+/* Decoder(width,height): references start as one shared all-zero raster. */
+int vp8gpu_decoder_create(vp8gpu_ctx* ctx, vp8gpu_decoder** out);
+/* Decoder(DecoderState, References): takes a copy of `state` and a reference on each frame. */
+int vp8gpu_decoder_create_from(vp8gpu_ctx* ctx, const vp8gpu_state* state,
+                               const vp8gpu_frame_id refs[3], vp8gpu_decoder** out);
+/* Copy construction: O(1) in pixels, the clone shares the three reference rasters. */
+int vp8gpu_decoder_clone(const vp8gpu_decoder* d, vp8gpu_decoder** out);
+void vp8gpu_decoder_destroy(vp8gpu_decoder* d);
+/* Decoder::get_frame_output (decoder.cc:125-135): parse + decode one compressed frame.
+ * *shown = show_frame; *out = the decoded raster with one reference owned by the caller
+ * (release it with vp8gpu_frame_release).  Asynchronous on the decoder's lane. */
+int vp8gpu_decoder_decode(vp8gpu_decoder* d, const uint8_t* data, size_t len, int* shown,
+                          vp8gpu_frame_id* out);
+/* Decoder::decode_frame (decoder.cc:101-118) for an already parsed frame; `parsed` must
+ * have been produced by vp8gpu_parse_frame on this decoder's state (vp8gpu_decoder_state). */
+int vp8gpu_decoder_decode_parsed(vp8gpu_decoder* d, const vp8gpu_parsed* parsed, int* shown,
+                                 vp8gpu_frame_id* out);
+vp8gpu_state* vp8gpu_decoder_state(vp8gpu_decoder* d);            /* get_state (borrowed) */
+int vp8gpu_decoder_references(const vp8gpu_decoder* d, vp8gpu_frame_id refs[3]); /* borrowed */
+int vp8gpu_decoder_lane(const vp8gpu_decoder* d);
+/* Decoder::operator== (decoder.cc:153): state equal and the three rasters pixel-equal. */
+int vp8gpu_decoder_equal(vp8gpu_decoder* a, vp8gpu_decoder* b, int* equal);
+
+/* ---- whole-stream helper (decoder/player.cc:60-143, FilePlayer) ----
+ * Decode every frame of an in-memory IVF with `threads` host workers, one GOP (key frame
+ * to next key frame) per task, each worker driving its own Decoder on its own lane.  The
+ * display rectangles of the shown frames are written, in stream order, to `dst`
+ * (may be NULL to leave the frames on the device).  *n_shown / *n_decoded are outputs. */
+int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threads, uint8_t* dst,
+                      size_t dst_size, uint32_t* n_decoded, uint32_t* n_shown);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VP8GPU_H */
