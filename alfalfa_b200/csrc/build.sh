@@ -1,0 +1,15 @@
+#!/bin/sh
+# Build libvp8gpu.so (CUDA kernels for sm_100a + host library) in-tree.
+# usage: alfalfa_b200/csrc/build.sh   -> alfalfa_b200/libvp8gpu.so
+set -e
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+ARCH="-gencode arch=compute_100a,code=sm_100a"
+FLAGS="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wextra,-pthread"
+mkdir -p build
+$NVCC $ARCH $FLAGS -Xptxas -v -c kernels.cu -o build/kernels.o 2> build/ptxas_kernels.log || { cat build/ptxas_kernels.log; exit 1; }
+$NVCC $ARCH $FLAGS -c engine.cu -o build/engine.o
+$NVCC $FLAGS -x cu $ARCH -c capi.cc -o build/capi.o
+g++ -O3 -std=c++17 -fPIC -Wall -Wextra -c parser.cc -o build/parser.o
+$NVCC $ARCH -shared -o ../libvp8gpu.so build/kernels.o build/engine.o build/capi.o build/parser.o -Xcompiler -pthread
+echo "built $(cd .. && pwd)/libvp8gpu.so"

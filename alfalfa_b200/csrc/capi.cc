@@ -1,0 +1,499 @@
+// capi.cc -- the extern "C" surface declared in include/vp8gpu.h, on top of Engine (device
+// side) and parser (CPU entropy front end).  Also holds the Decoder object (state + three
+// reference rasters, explicit state passing as in decoder/decoder.hh:244-300) and the
+// GOP-parallel whole-stream helper.
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include <atomic>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/vp8gpu.h"
+#include "engine.hpp"
+#include "parser.h"
+
+using vp8::Engine;
+using vp8::HostJob;
+using vp8::ParsedFrame;
+using vp8::State;
+
+struct vp8gpu_ctx {
+  Engine* engine = nullptr;
+  std::string create_error;
+  std::atomic<int> next_lane{0};
+};
+struct vp8gpu_state {
+  State s;
+  vp8gpu_state(int w, int h) : s(w, h) {}
+  explicit vp8gpu_state(const State& o) : s(o) {}
+};
+struct vp8gpu_parsed {
+  ParsedFrame f;
+  uint32_t n_intra = 0, n_filtered = 0;
+  cudaEvent_t consumed = nullptr;  // set for pinned instances owned by a decoder
+  bool busy = false;
+  explicit vp8gpu_parsed(const vp8::Allocator& a) : f(a) {}
+};
+struct vp8gpu_resident_batch {
+  Engine::Resident* r = nullptr;
+};
+
+namespace {
+
+void* pinned_alloc(size_t n) {
+  void* p = nullptr;
+  return cudaHostAlloc(&p, n, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
+}
+void pinned_free(void* p) { cudaFreeHost(p); }
+const vp8::Allocator kPinned = {&pinned_alloc, &pinned_free};
+
+void count_mbs(vp8gpu_parsed* p) {
+  const vp8gpu_frame_desc& d = p->f.desc;
+  const size_t n = (size_t)d.mb_cols * d.mb_rows;
+  const vp8gpu_mb* m = p->f.mbs.data();
+  uint32_t ni = 0, nf = 0;
+  for (size_t i = 0; i < n; i++) {
+    ni += m[i].ref_frame == VP8GPU_REF_CURRENT;
+    nf += m[i].lf_level != 0;
+  }
+  p->n_intra = ni;
+  p->n_filtered = nf;
+}
+
+}  // namespace
+
+// =============================================================================================
+// context and frames
+// =============================================================================================
+extern "C" {
+
+int vp8gpu_ctx_create(int device, int width, int height, int max_frames, vp8gpu_ctx** out) {
+  if (!out) return VP8GPU_ERR_LOGIC;
+  *out = nullptr;
+  vp8gpu_ctx* c = new vp8gpu_ctx();
+  const int rc = Engine::create(device, width, height, max_frames, &c->engine, &c->create_error);
+  if (rc != VP8GPU_OK) {
+    delete c;
+    return rc;
+  }
+  *out = c;
+  return VP8GPU_OK;
+}
+void vp8gpu_ctx_destroy(vp8gpu_ctx* ctx) {
+  if (!ctx) return;
+  delete ctx->engine;
+  delete ctx;
+}
+const char* vp8gpu_last_error(const vp8gpu_ctx* ctx) { return ctx && ctx->engine ? ctx->engine->last_error() : ""; }
+
+int vp8gpu_frame_alloc(vp8gpu_ctx* ctx, vp8gpu_frame_id* out) { return ctx->engine->frame_alloc(out); }
+int vp8gpu_frame_retain(vp8gpu_ctx* ctx, vp8gpu_frame_id id) { return ctx->engine->frame_retain(id); }
+int vp8gpu_frame_release(vp8gpu_ctx* ctx, vp8gpu_frame_id id) { return ctx->engine->frame_release(id); }
+int vp8gpu_frame_upload(vp8gpu_ctx* ctx, vp8gpu_frame_id id, const uint8_t* y, size_t ys, const uint8_t* u,
+                        const uint8_t* v, size_t cs) {
+  return ctx->engine->frame_upload(id, y, ys, u, v, cs);
+}
+int vp8gpu_frame_download(vp8gpu_ctx* ctx, vp8gpu_frame_id id, uint8_t* y, size_t ys, uint8_t* u, uint8_t* v,
+                          size_t cs) {
+  return ctx->engine->frame_download(id, y, ys, u, v, cs);
+}
+int vp8gpu_frame_download_display(vp8gpu_ctx* ctx, vp8gpu_frame_id id, uint8_t* dst, size_t dst_size) {
+  return ctx->engine->frame_download_display(id, 0, dst, dst_size, true);
+}
+int vp8gpu_frame_download_display_async(vp8gpu_ctx* ctx, vp8gpu_frame_id id, uint8_t* dst, size_t dst_size) {
+  return ctx->engine->frame_download_display(id, 0, dst, dst_size, false);
+}
+int vp8gpu_ctx_sync(vp8gpu_ctx* ctx) { return ctx->engine->sync_all(); }
+int vp8gpu_host_alloc(void** out, size_t bytes) {
+  return cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess ? VP8GPU_OK : VP8GPU_ERR_NOMEM;
+}
+void vp8gpu_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+uint64_t vp8gpu_launch_count(const vp8gpu_ctx* ctx) { return ctx->engine->launches(); }
+
+// =============================================================================================
+// the seam
+// =============================================================================================
+static HostJob to_host_job(const vp8gpu_job& j) {
+  HostJob h;
+  h.desc = j.desc;
+  h.mbs = j.mbs;
+  h.tokens = j.tokens;
+  h.split = j.split;
+  memcpy(h.refs, j.refs, sizeof(h.refs));
+  h.out = j.out;
+  return h;
+}
+
+int vp8gpu_decode_batch(vp8gpu_ctx* ctx, int lane, const vp8gpu_job* jobs, int n) {
+  if (!ctx || !jobs || n < 0) return VP8GPU_ERR_LOGIC;
+  std::vector<HostJob> hj;
+  hj.reserve(n);
+  for (int i = 0; i < n; i++) {
+    if (!jobs[i].desc || !jobs[i].mbs) return ctx->engine->fail(VP8GPU_ERR_LOGIC, "decode_batch: null records");
+    if (jobs[i].desc->mb_cols != ctx->engine->geom().mb_cols || jobs[i].desc->mb_rows != ctx->engine->geom().mb_rows)
+      return ctx->engine->fail(VP8GPU_ERR_LOGIC, "decode_batch: frame size does not match the context");
+    hj.push_back(to_host_job(jobs[i]));
+  }
+  const int rc = ctx->engine->submit(lane, hj.data(), n, nullptr);
+  if (rc != VP8GPU_OK) return rc;
+  // the caller's arrays may be pageable or pinned; make "consumed before return" unconditional
+  cudaError_t e = cudaStreamSynchronize(ctx->engine->stream(lane));
+  return e == cudaSuccess ? VP8GPU_OK : ctx->engine->cuda_fail(e, "decode_batch sync");
+}
+
+int vp8gpu_decode_parsed(vp8gpu_ctx* ctx, int lane, const vp8gpu_frame_desc* desc, const vp8gpu_mb* mbs,
+                         const vp8gpu_token* tokens, const vp8gpu_split_mvs* split, const vp8gpu_frame_id refs[3],
+                         vp8gpu_frame_id out) {
+  vp8gpu_job j;
+  j.desc = desc;
+  j.mbs = mbs;
+  j.tokens = tokens;
+  j.split = split;
+  for (int i = 0; i < 3; i++) j.refs[i] = refs ? refs[i] : -1;
+  j.out = out;
+  return vp8gpu_decode_batch(ctx, lane, &j, 1);
+}
+
+int vp8gpu_batch_upload(vp8gpu_ctx* ctx, const vp8gpu_job* jobs, int n, vp8gpu_resident_batch** out) {
+  std::vector<HostJob> hj;
+  for (int i = 0; i < n; i++) hj.push_back(to_host_job(jobs[i]));
+  vp8gpu_resident_batch* b = new vp8gpu_resident_batch();
+  const int rc = ctx->engine->resident_upload(hj.data(), n, &b->r);
+  if (rc != VP8GPU_OK) {
+    delete b;
+    return rc;
+  }
+  *out = b;
+  return VP8GPU_OK;
+}
+int vp8gpu_batch_run(vp8gpu_ctx* ctx, int lane, vp8gpu_resident_batch* b, float* kernel_ms) {
+  return ctx->engine->resident_run(lane, b->r, kernel_ms);
+}
+void vp8gpu_batch_free(vp8gpu_ctx* ctx, vp8gpu_resident_batch* b) {
+  if (!b) return;
+  ctx->engine->resident_free(b->r);
+  delete b;
+}
+
+// =============================================================================================
+// CPU front end
+// =============================================================================================
+int vp8gpu_state_create(int width, int height, vp8gpu_state** out) {
+  if (!out || width <= 0 || height <= 0) return VP8GPU_ERR_LOGIC;
+  *out = new vp8gpu_state(width, height);
+  return VP8GPU_OK;
+}
+int vp8gpu_state_clone(const vp8gpu_state* s, vp8gpu_state** out) {
+  if (!s || !out) return VP8GPU_ERR_LOGIC;
+  *out = new vp8gpu_state(s->s);
+  return VP8GPU_OK;
+}
+void vp8gpu_state_destroy(vp8gpu_state* s) { delete s; }
+int vp8gpu_state_equal(const vp8gpu_state* a, const vp8gpu_state* b) { return a && b && a->s == b->s; }
+uint64_t vp8gpu_state_hash(const vp8gpu_state* s) { return s->s.hash(); }
+
+int vp8gpu_parsed_create(vp8gpu_parsed** out) {
+  if (!out) return VP8GPU_ERR_LOGIC;
+  *out = new vp8gpu_parsed(vp8::kMallocAllocator);
+  return VP8GPU_OK;
+}
+void vp8gpu_parsed_destroy(vp8gpu_parsed* p) {
+  if (!p) return;
+  if (p->consumed) cudaEventDestroy(p->consumed);
+  delete p;
+}
+const vp8gpu_frame_desc* vp8gpu_parsed_desc(const vp8gpu_parsed* p) { return &p->f.desc; }
+const vp8gpu_mb* vp8gpu_parsed_mbs(const vp8gpu_parsed* p) { return p->f.mbs.data(); }
+const vp8gpu_token* vp8gpu_parsed_tokens(const vp8gpu_parsed* p) { return p->f.tokens.data(); }
+const vp8gpu_split_mvs* vp8gpu_parsed_split(const vp8gpu_parsed* p) { return p->f.split.data(); }
+
+int vp8gpu_parse_frame(vp8gpu_state* state, const uint8_t* data, size_t len, vp8gpu_parsed* out) {
+  if (!state || !data || !out) return VP8GPU_ERR_LOGIC;
+  const int rc = vp8::parse_frame(state->s, data, len, out->f);
+  if (rc == VP8GPU_OK) count_mbs(out);
+  return rc;
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// Decoder
+// =============================================================================================
+struct vp8gpu_decoder {
+  vp8gpu_ctx* ctx = nullptr;
+  int lane = 0;
+  vp8gpu_state state;
+  int refs[3] = {-1, -1, -1};  // last, golden, alternative; each holds one reference count
+  // ring of pinned parsed-frame buffers so the host can parse frame N+1 while the DMA engine
+  // is still reading frame N's records
+  std::unique_ptr<vp8gpu_parsed> ring[vp8::kStagingDepth];
+  int ring_next = 0;
+  vp8gpu_decoder(vp8gpu_ctx* c, int w, int h) : ctx(c), state(w, h) {}
+  vp8gpu_decoder(vp8gpu_ctx* c, const State& s) : ctx(c), state(s) {}
+};
+
+namespace {
+
+void set_ref(Engine* e, int* slot, int id) {
+  // RasterHandle assignment: retain the new raster, release the old one
+  if (*slot == id) return;
+  e->frame_retain(id);
+  if (*slot >= 0) e->frame_release(*slot);
+  *slot = id;
+}
+
+vp8gpu_parsed* next_ring_slot(vp8gpu_decoder* d) {
+  std::unique_ptr<vp8gpu_parsed>& p = d->ring[d->ring_next];
+  d->ring_next = (d->ring_next + 1) % vp8::kStagingDepth;
+  if (!p) {
+    p.reset(new vp8gpu_parsed(kPinned));
+    cudaEventCreateWithFlags(&p->consumed, cudaEventDisableTiming);
+  }
+  if (p->busy) {
+    cudaEventSynchronize(p->consumed);
+    p->busy = false;
+  }
+  return p.get();
+}
+
+// Decoder::decode_frame (decoder.cc:101-118): decode + loopfilter into a fresh raster, then
+// Frame::copy_to (frame.cc:272-307) on the references.
+int decode_parsed_impl(vp8gpu_decoder* d, vp8gpu_parsed* p, bool pinned_ring, int* shown, int* out_id) {
+  Engine* e = d->ctx->engine;
+  const vp8gpu_frame_desc& desc = p->f.desc;
+  int out = -1;
+  int rc = e->frame_alloc(&out);
+  if (rc != VP8GPU_OK) return rc;
+  HostJob j;
+  j.desc = &desc;
+  j.mbs = p->f.mbs.data();
+  j.tokens = p->f.tokens.data();
+  j.split = p->f.split.data();
+  memcpy(j.refs, d->refs, sizeof(j.refs));
+  j.out = out;
+  j.n_intra = (int)p->n_intra;
+  j.n_filtered = (int)p->n_filtered;
+  rc = e->submit(d->lane, &j, 1, pinned_ring ? p->consumed : nullptr);
+  if (rc != VP8GPU_OK) {
+    e->frame_release(out);
+    return rc;
+  }
+  if (pinned_ring) p->busy = true;
+  else cudaStreamSynchronize(e->stream(d->lane));  // caller-owned (possibly pageable) records
+  if (desc.key_frame) {
+    set_ref(e, &d->refs[0], out);
+    set_ref(e, &d->refs[1], out);
+    set_ref(e, &d->refs[2], out);
+  } else {
+    if (desc.copy_to_alternate == 1) set_ref(e, &d->refs[2], d->refs[0]);
+    else if (desc.copy_to_alternate == 2) set_ref(e, &d->refs[2], d->refs[1]);
+    if (desc.copy_to_golden == 1) set_ref(e, &d->refs[1], d->refs[0]);
+    else if (desc.copy_to_golden == 2) set_ref(e, &d->refs[1], d->refs[2]);
+    if (desc.refresh_golden) set_ref(e, &d->refs[1], out);
+    if (desc.refresh_alternate) set_ref(e, &d->refs[2], out);
+    if (desc.refresh_last) set_ref(e, &d->refs[0], out);
+  }
+  if (shown) *shown = desc.show_frame;
+  if (out_id) *out_id = out;  // the allocation's reference goes to the caller
+  else e->frame_release(out);
+  return VP8GPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vp8gpu_decoder_create(vp8gpu_ctx* ctx, vp8gpu_decoder** out) {
+  if (!ctx || !out) return VP8GPU_ERR_LOGIC;
+  Engine* e = ctx->engine;
+  vp8gpu_decoder* d = new vp8gpu_decoder(ctx, e->width(), e->height());
+  d->lane = ctx->next_lane.fetch_add(1) % vp8::kMaxLanes;
+  int id = -1;
+  int rc = e->frame_alloc(&id);
+  if (rc == VP8GPU_OK) rc = e->frame_clear(id, d->lane);
+  if (rc != VP8GPU_OK) {
+    if (id >= 0) e->frame_release(id);
+    delete d;
+    return rc;
+  }
+  // References( MutableRasterHandle ): last, golden and alternative share one raster (decoder.cc:165-169)
+  d->refs[0] = d->refs[1] = d->refs[2] = id;
+  e->frame_retain(id);
+  e->frame_retain(id);
+  *out = d;
+  return VP8GPU_OK;
+}
+
+int vp8gpu_decoder_create_from(vp8gpu_ctx* ctx, const vp8gpu_state* state, const vp8gpu_frame_id refs[3],
+                               vp8gpu_decoder** out) {
+  if (!ctx || !state || !refs || !out) return VP8GPU_ERR_LOGIC;
+  Engine* e = ctx->engine;
+  if (state->s.width != e->width() || state->s.height != e->height())
+    return e->fail(VP8GPU_ERR_LOGIC, "decoder_create_from: state size does not match the context");
+  for (int i = 0; i < 3; i++)
+    if (e->frame_retain(refs[i]) != VP8GPU_OK) {
+      for (int k = 0; k < i; k++) e->frame_release(refs[k]);
+      return VP8GPU_ERR_LOGIC;
+    }
+  vp8gpu_decoder* d = new vp8gpu_decoder(ctx, state->s);
+  d->lane = ctx->next_lane.fetch_add(1) % vp8::kMaxLanes;
+  memcpy(d->refs, refs, sizeof(d->refs));
+  *out = d;
+  return VP8GPU_OK;
+}
+
+int vp8gpu_decoder_clone(const vp8gpu_decoder* src, vp8gpu_decoder** out) {
+  if (!src || !out) return VP8GPU_ERR_LOGIC;
+  const vp8gpu_state tmp(src->state.s);
+  return vp8gpu_decoder_create_from(src->ctx, &tmp, src->refs, out);
+}
+
+void vp8gpu_decoder_destroy(vp8gpu_decoder* d) {
+  if (!d) return;
+  Engine* e = d->ctx->engine;
+  for (auto& p : d->ring)
+    if (p && p->busy) cudaEventSynchronize(p->consumed);
+  for (int i = 0; i < 3; i++)
+    if (d->refs[i] >= 0) e->frame_release(d->refs[i]);
+  for (auto& p : d->ring)
+    if (p) {
+      if (p->consumed) cudaEventDestroy(p->consumed);
+      p->consumed = nullptr;
+    }
+  delete d;
+}
+
+int vp8gpu_decoder_decode(vp8gpu_decoder* d, const uint8_t* data, size_t len, int* shown, vp8gpu_frame_id* out) {
+  if (!d || !data) return VP8GPU_ERR_LOGIC;
+  cudaSetDevice(d->ctx->engine->device());
+  vp8gpu_parsed* p = next_ring_slot(d);
+  const int rc = vp8::parse_frame(d->state.s, data, len, p->f);
+  if (rc != VP8GPU_OK) return d->ctx->engine->fail(rc, "parse_frame failed");
+  count_mbs(p);
+  return decode_parsed_impl(d, p, true, shown, out);
+}
+
+int vp8gpu_decoder_decode_parsed(vp8gpu_decoder* d, const vp8gpu_parsed* parsed, int* shown, vp8gpu_frame_id* out) {
+  if (!d || !parsed) return VP8GPU_ERR_LOGIC;
+  cudaSetDevice(d->ctx->engine->device());
+  return decode_parsed_impl(d, const_cast<vp8gpu_parsed*>(parsed), false, shown, out);
+}
+
+vp8gpu_state* vp8gpu_decoder_state(vp8gpu_decoder* d) { return &d->state; }
+int vp8gpu_decoder_references(const vp8gpu_decoder* d, vp8gpu_frame_id refs[3]) {
+  memcpy(refs, d->refs, sizeof(d->refs));
+  return VP8GPU_OK;
+}
+int vp8gpu_decoder_lane(const vp8gpu_decoder* d) { return d->lane; }
+
+int vp8gpu_decoder_equal(vp8gpu_decoder* a, vp8gpu_decoder* b, int* equal) {
+  if (!a || !b || !equal || a->ctx != b->ctx) return VP8GPU_ERR_LOGIC;
+  *equal = 0;
+  if (!(a->state.s == b->state.s)) return VP8GPU_OK;
+  for (int i = 0; i < 3; i++) {
+    int eq = 0;
+    const int rc = a->ctx->engine->frames_equal(a->refs[i], b->refs[i], a->lane, &eq);
+    if (rc != VP8GPU_OK) return rc;
+    if (!eq) return VP8GPU_OK;
+  }
+  *equal = 1;
+  return VP8GPU_OK;
+}
+
+// =============================================================================================
+// whole-stream helper: FilePlayer semantics (player.cc:88-143) with GOP-level parallelism
+// =============================================================================================
+int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threads, uint8_t* dst, size_t dst_size,
+                      uint32_t* n_decoded, uint32_t* n_shown) {
+  if (!ctx || !ivf) return VP8GPU_ERR_LOGIC;
+  Engine* e = ctx->engine;
+  // IVF container (util/ivf.cc:36-82)
+  if (len < 32 || memcmp(ivf, "DKIF", 4) != 0) return e->fail(VP8GPU_ERR_INVALID, "missing IVF file header");
+  if ((ivf[4] | (ivf[5] << 8)) != 0) return e->fail(VP8GPU_ERR_UNSUPPORTED, "not an IVF version 0 file");
+  if ((ivf[6] | (ivf[7] << 8)) != 32) return e->fail(VP8GPU_ERR_UNSUPPORTED, "unsupported IVF header length");
+  if (memcmp(ivf + 8, "VP80", 4) != 0) return e->fail(VP8GPU_ERR_UNSUPPORTED, "not a VP8 file");
+  const int w = ivf[12] | (ivf[13] << 8), h = ivf[14] | (ivf[15] << 8);
+  if (w != e->width() || h != e->height()) return e->fail(VP8GPU_ERR_UNSUPPORTED, "IVF size does not match the context");
+  const uint32_t count = ivf[24] | (ivf[25] << 8) | (ivf[26] << 16) | ((uint32_t)ivf[27] << 24);
+  struct Item {
+    const uint8_t* p;
+    uint32_t n;
+    int64_t out_off;  // -1 = hidden
+  };
+  std::vector<Item> items;
+  std::vector<uint32_t> gop_start;
+  const size_t frame_bytes = (size_t)w * h + 2 * (size_t)((w + 1) / 2) * ((h + 1) / 2);
+  size_t pos = 32, out_off = 0;
+  uint32_t shown_total = 0;
+  for (uint32_t i = 0; i < count; i++) {
+    if (pos + 12 > len) return e->fail(VP8GPU_ERR_INVALID, "IVF file truncated");
+    const uint32_t n = ivf[pos] | (ivf[pos + 1] << 8) | (ivf[pos + 2] << 16) | ((uint32_t)ivf[pos + 3] << 24);
+    if (pos + 12 + n > len) return e->fail(VP8GPU_ERR_INVALID, "IVF file truncated");
+    const uint8_t* p = ivf + pos + 12;
+    pos += 12 + n;
+    const bool key = n > 0 && !(p[0] & 1);
+    if (items.empty() && !key) continue;  // FilePlayer starts at the first key frame
+    if (key) gop_start.push_back((uint32_t)items.size());
+    const bool shown = n > 0 && ((p[0] >> 4) & 1);
+    Item it = {p, n, shown ? (int64_t)out_off : -1};
+    if (shown) {
+      out_off += frame_bytes;
+      shown_total++;
+    }
+    items.push_back(it);
+  }
+  if (dst && dst_size < out_off) return e->fail(VP8GPU_ERR_LOGIC, "decode_ivf: destination too small");
+  gop_start.push_back((uint32_t)items.size());
+  const int n_gops = (int)gop_start.size() - 1;
+  if (threads < 1) threads = 1;
+  if (threads > vp8::kMaxLanes) threads = vp8::kMaxLanes;
+  if (threads > n_gops) threads = n_gops > 0 ? n_gops : 1;
+
+  std::atomic<int> next_gop{0};
+  std::atomic<int> first_error{VP8GPU_OK};
+  auto worker = [&](int tid) {
+    cudaSetDevice(e->device());
+    vp8gpu_decoder* d = nullptr;
+    int rc = vp8gpu_decoder_create(ctx, &d);
+    if (rc != VP8GPU_OK) {
+      int ok = VP8GPU_OK;
+      first_error.compare_exchange_strong(ok, rc);
+      return;
+    }
+    d->lane = tid;  // one lane per worker
+    for (;;) {
+      const int g = next_gop.fetch_add(1);
+      if (g >= n_gops || first_error.load() != VP8GPU_OK) break;
+      for (uint32_t i = gop_start[g]; i < gop_start[g + 1]; i++) {
+        int shown = 0, id = -1;
+        rc = vp8gpu_decoder_decode(d, items[i].p, items[i].n, &shown, &id);
+        if (rc != VP8GPU_OK) break;
+        if (dst && items[i].out_off >= 0)
+          rc = e->frame_download_display(id, d->lane, dst + items[i].out_off, frame_bytes, false);
+        e->frame_release(id);
+        if (rc != VP8GPU_OK) break;
+      }
+      if (rc != VP8GPU_OK) {
+        int ok = VP8GPU_OK;
+        first_error.compare_exchange_strong(ok, rc);
+        break;
+      }
+    }
+    e->sync_lane(d->lane);
+    vp8gpu_decoder_destroy(d);
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < threads; t++) pool.emplace_back(worker, t);
+  worker(0);
+  for (auto& t : pool) t.join();
+  if (n_decoded) *n_decoded = (uint32_t)items.size();
+  if (n_shown) *n_shown = shown_total;
+  return first_error.load();
+}
+
+}  // extern "C"

@@ -1,0 +1,547 @@
+// engine.cu -- see engine.hpp.
+//
+// Ownership model = the reference's RasterHandle (decoder/raster_handle.hh:95-123): device
+// rasters are reference counted, immutable once a decode has been queued into them, and return
+// to a per-context pool (not a process-global one, cf. raster_handle.cc:74-83).  Because work is
+// asynchronous and several decoders run on different CUDA streams ("lanes"), every raster
+// remembers which streams touched it (one event per stream slot); a stream that wants to read,
+// or to recycle and overwrite, a raster first waits for the other streams' events.
+#include "engine.hpp"
+
+#include <string.h>
+
+namespace vp8 {
+
+int launch_compare(const uint8_t* a, const uint8_t* b, const Geom& g, int* d_flag, void* stream);
+
+namespace {
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+constexpr int kSyncHeaderInts = 64;  // [0] = intra ticket, [32] = loop-filter ticket (own cache lines)
+}  // namespace
+
+int Engine::fail(int code, const std::string& what) {
+  err_ = what;
+  return code;
+}
+int Engine::cuda_fail(cudaError_t e, const char* what) {
+  err_ = std::string(what) + ": " + cudaGetErrorString(e);
+  return VP8GPU_ERR_CUDA;
+}
+#define CU(call)                                             \
+  do {                                                       \
+    cudaError_t e__ = (call);                                \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call);    \
+  } while (0)
+
+int Engine::create(int device, int width, int height, int max_frames, Engine** out, std::string* err) {
+  if (width <= 0 || height <= 0 || width > 16383 || height > 16383) {
+    if (err) *err = "bad frame size";
+    return VP8GPU_ERR_LOGIC;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || device < 0 || device >= ndev) {
+    if (err) *err = std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "bad index");
+    return VP8GPU_ERR_CUDA;
+  }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    if (err) *err = cudaGetErrorString(e);
+    return VP8GPU_ERR_CUDA;
+  }
+  Engine* en = new Engine();
+  en->device_ = device;
+  en->width_ = width;
+  en->height_ = height;
+  Geom& g = en->g_;
+  g.mb_cols = (width + 15) / 16;
+  g.mb_rows = (height + 15) / 16;
+  g.W = 16 * g.mb_cols;
+  g.H = 16 * g.mb_rows;
+  g.y_pitch = (int)align_up(g.W, 32);
+  g.c_pitch = g.y_pitch / 2;
+  g.u_off = (uint32_t)((size_t)g.y_pitch * g.H);
+  g.v_off = g.u_off + (uint32_t)((size_t)g.c_pitch * (g.H / 2));
+  g.frame_bytes = g.v_off + (uint32_t)((size_t)g.c_pitch * (g.H / 2));
+  if (max_frames <= 0) max_frames = 64;
+  en->frames_.resize(max_frames);
+  for (int i = max_frames - 1; i >= 0; i--) en->free_.push_back(i);
+  *out = en;
+  return VP8GPU_OK;
+}
+
+Engine::~Engine() {
+  cudaSetDevice(device_);
+  cudaDeviceSynchronize();
+  for (auto& f : frames_) {
+    if (f.dev) cudaFree(f.dev);
+    for (auto& ev : f.ev)
+      if (ev) cudaEventDestroy(ev);
+  }
+  for (int l = 0; l < kMaxLanes; l++)
+    for (auto& s : staging_[l]) {
+      if (s.dev) cudaFree(s.dev);
+      if (s.host) cudaFreeHost(s.host);
+      if (s.done) cudaEventDestroy(s.done);
+    }
+  for (auto& s : lanes_)
+    if (s) cudaStreamDestroy(s);
+  if (cmp_scratch_) cudaFree(cmp_scratch_);
+}
+
+int Engine::ensure_lane(int lane) {
+  if (lane < 0 || lane >= kMaxLanes) return fail(VP8GPU_ERR_LOGIC, "lane out of range");
+  std::lock_guard<std::mutex> lk(mu_);
+  CU(cudaSetDevice(device_));
+  if (!lanes_[lane]) {
+    CU(cudaStreamCreateWithFlags(&lanes_[lane], cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&lanes_[kMaxLanes + lane], cudaStreamNonBlocking));
+  }
+  return VP8GPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// frame pool
+// ---------------------------------------------------------------------------------------------
+int Engine::frame_alloc(int* id) {
+  std::lock_guard<std::mutex> lk(mu_);
+  if (free_.empty()) return fail(VP8GPU_ERR_NOMEM, "device frame pool exhausted");
+  const int i = free_.back();
+  Frame& f = frames_[i];
+  if (!f.dev) {
+    CU(cudaSetDevice(device_));
+    CU(cudaMalloc(&f.dev, g_.frame_bytes));
+  }
+  free_.pop_back();
+  f.refcnt = 1;
+  *id = i;
+  return VP8GPU_OK;
+}
+int Engine::frame_retain(int id) {
+  std::lock_guard<std::mutex> lk(mu_);
+  if (id < 0 || id >= (int)frames_.size() || frames_[id].refcnt <= 0) return fail(VP8GPU_ERR_LOGIC, "retain: bad frame id");
+  frames_[id].refcnt++;
+  return VP8GPU_OK;
+}
+int Engine::frame_release(int id) {
+  std::lock_guard<std::mutex> lk(mu_);
+  if (id < 0 || id >= (int)frames_.size() || frames_[id].refcnt <= 0) return fail(VP8GPU_ERR_LOGIC, "release: bad frame id");
+  if (--frames_[id].refcnt == 0) free_.push_back(id);  // `pending` keeps guarding the memory
+  return VP8GPU_OK;
+}
+
+// caller holds mu_
+int Engine::touch(Frame& f, int slot) {
+  if (!f.ev[slot]) CU(cudaEventCreateWithFlags(&f.ev[slot], cudaEventDisableTiming));
+  CU(cudaEventRecord(f.ev[slot], lanes_[slot]));
+  f.pending |= 1ull << slot;
+  return VP8GPU_OK;
+}
+int Engine::wait_for(Frame& f, int slot, cudaStream_t s) {
+  uint64_t m = f.pending & ~(1ull << slot);
+  while (m) {
+    const int t = __builtin_ctzll(m);
+    m &= m - 1;
+    CU(cudaStreamWaitEvent(s, f.ev[t], 0));
+  }
+  return VP8GPU_OK;
+}
+
+int Engine::frame_clear(int id, int lane) {
+  if (int rc = ensure_lane(lane)) return rc;
+  std::lock_guard<std::mutex> lk(mu_);
+  Frame& f = frames_[id];
+  if (int rc = wait_for(f, lane, lanes_[lane])) return rc;
+  CU(cudaMemsetAsync(f.dev, 0, g_.frame_bytes, lanes_[lane]));
+  f.pending = 0;
+  return touch(f, lane);
+}
+
+int Engine::frame_upload(int id, const uint8_t* y, size_t ys, const uint8_t* u, const uint8_t* v, size_t cs) {
+  if (int rc = ensure_lane(0)) return rc;
+  std::lock_guard<std::mutex> lk(mu_);
+  if (id < 0 || id >= (int)frames_.size() || frames_[id].refcnt <= 0) return fail(VP8GPU_ERR_LOGIC, "upload: bad frame id");
+  Frame& f = frames_[id];
+  cudaStream_t s = lanes_[0];
+  if (int rc = wait_for(f, 0, s)) return rc;
+  CU(cudaMemcpy2DAsync(f.dev, g_.y_pitch, y, ys, g_.W, g_.H, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpy2DAsync(f.dev + g_.u_off, g_.c_pitch, u, cs, g_.W / 2, g_.H / 2, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpy2DAsync(f.dev + g_.v_off, g_.c_pitch, v, cs, g_.W / 2, g_.H / 2, cudaMemcpyHostToDevice, s));
+  f.pending = 0;
+  if (int rc = touch(f, 0)) return rc;
+  CU(cudaStreamSynchronize(s));
+  return VP8GPU_OK;
+}
+
+int Engine::frame_download(int id, uint8_t* y, size_t ys, uint8_t* u, uint8_t* v, size_t cs) {
+  if (int rc = ensure_lane(0)) return rc;
+  cudaStream_t s;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (id < 0 || id >= (int)frames_.size() || frames_[id].refcnt <= 0) return fail(VP8GPU_ERR_LOGIC, "download: bad frame id");
+    Frame& f = frames_[id];
+    const int slot = kMaxLanes + 0;
+    s = lanes_[slot];
+    if (int rc = wait_for(f, slot, s)) return rc;
+    CU(cudaMemcpy2DAsync(y, ys, f.dev, g_.y_pitch, g_.W, g_.H, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpy2DAsync(u, cs, f.dev + g_.u_off, g_.c_pitch, g_.W / 2, g_.H / 2, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpy2DAsync(v, cs, f.dev + g_.v_off, g_.c_pitch, g_.W / 2, g_.H / 2, cudaMemcpyDeviceToHost, s));
+    if (int rc = touch(f, slot)) return rc;
+  }
+  CU(cudaStreamSynchronize(s));
+  return VP8GPU_OK;
+}
+
+int Engine::frame_download_display(int id, int lane, uint8_t* dst, size_t dst_size, bool wait) {
+  if (int rc = ensure_lane(lane)) return rc;
+  const int cw = (width_ + 1) / 2, ch = (height_ + 1) / 2;
+  const size_t need = (size_t)width_ * height_ + 2 * (size_t)cw * ch;
+  if (dst_size < need) return fail(VP8GPU_ERR_LOGIC, "download_display: destination too small");
+  cudaStream_t s;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (id < 0 || id >= (int)frames_.size() || frames_[id].refcnt <= 0) return fail(VP8GPU_ERR_LOGIC, "download: bad frame id");
+    Frame& f = frames_[id];
+    const int slot = kMaxLanes + lane;
+    s = lanes_[slot];
+    if (int rc = wait_for(f, slot, s)) return rc;
+    uint8_t* p = dst;
+    CU(cudaMemcpy2DAsync(p, width_, f.dev, g_.y_pitch, width_, height_, cudaMemcpyDeviceToHost, s));
+    p += (size_t)width_ * height_;
+    CU(cudaMemcpy2DAsync(p, cw, f.dev + g_.u_off, g_.c_pitch, cw, ch, cudaMemcpyDeviceToHost, s));
+    p += (size_t)cw * ch;
+    CU(cudaMemcpy2DAsync(p, cw, f.dev + g_.v_off, g_.c_pitch, cw, ch, cudaMemcpyDeviceToHost, s));
+    if (int rc = touch(f, slot)) return rc;
+  }
+  if (wait) CU(cudaStreamSynchronize(s));
+  return VP8GPU_OK;
+}
+
+int Engine::frames_equal(int a, int b, int lane, int* equal) {
+  if (int rc = ensure_lane(lane)) return rc;
+  if (a == b) {
+    *equal = 1;
+    return VP8GPU_OK;
+  }
+  int* flag;
+  cudaStream_t s = lanes_[lane];
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (!cmp_scratch_) CU(cudaMalloc(&cmp_scratch_, 256));
+    flag = reinterpret_cast<int*>(cmp_scratch_);
+    if (int rc = wait_for(frames_[a], lane, s)) return rc;
+    if (int rc = wait_for(frames_[b], lane, s)) return rc;
+    CU(cudaMemsetAsync(flag, 0, sizeof(int), s));
+    if (int e = launch_compare(frames_[a].dev, frames_[b].dev, g_, flag, s)) return cuda_fail((cudaError_t)e, "compare");
+    launches_++;
+    if (int rc = touch(frames_[a], lane)) return rc;
+    if (int rc = touch(frames_[b], lane)) return rc;
+  }
+  int h = 0;
+  CU(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  *equal = h == 0;
+  return VP8GPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// job submission
+// ---------------------------------------------------------------------------------------------
+int Engine::count_jobs(const HostJob& j, uint32_t* n_intra, uint32_t* n_inter, uint32_t* n_filtered) const {
+  const size_t n = (size_t)g_.mb_cols * g_.mb_rows;
+  uint32_t ni = 0, nf = 0;
+  if (j.n_intra >= 0 && j.n_filtered >= 0) {
+    ni = (uint32_t)j.n_intra;
+    nf = (uint32_t)j.n_filtered;
+  } else {
+    for (size_t i = 0; i < n; i++) {
+      ni += j.mbs[i].ref_frame == VP8GPU_REF_CURRENT;
+      nf += j.mbs[i].lf_level != 0;
+    }
+  }
+  *n_intra = ni;
+  *n_inter = (uint32_t)n - ni;
+  *n_filtered = j.desc->loop_filter_level ? nf : 0;
+  return VP8GPU_OK;
+}
+
+namespace {
+struct Layout {
+  size_t jobs_off, sync_off, sync_bytes, total;
+  std::vector<size_t> mbs_off, tok_off, split_off;
+};
+Layout plan(const Geom& g, const HostJob* jobs, int n) {
+  Layout L;
+  L.jobs_off = 0;
+  L.sync_off = align_up(sizeof(DevJob) * n, 256);
+  L.sync_bytes = sizeof(int) * (kSyncHeaderInts + (size_t)n * 2 * g.mb_rows);
+  size_t off = align_up(L.sync_off + L.sync_bytes, 256);
+  const size_t n_mbs = (size_t)g.mb_cols * g.mb_rows;
+  for (int i = 0; i < n; i++) {
+    L.mbs_off.push_back(off);
+    off = align_up(off + n_mbs * sizeof(vp8gpu_mb), 256);
+    L.tok_off.push_back(off);
+    off = align_up(off + (size_t)jobs[i].desc->n_tokens * sizeof(vp8gpu_token) + 4, 256);
+    L.split_off.push_back(off);
+    off = align_up(off + (size_t)jobs[i].desc->n_split * sizeof(vp8gpu_split_mvs) + 4, 256);
+  }
+  L.total = off;
+  return L;
+}
+}  // namespace
+
+int Engine::build_and_launch(int lane, const DevJob* d_jobs, int* d_sync, int n, bool any_inter, bool any_intra,
+                             bool any_lf) {
+  cudaStream_t s = lanes_[lane];
+  if (any_inter) {
+    if (int e = launch_inter(d_jobs, n, g_, s)) return cuda_fail((cudaError_t)e, "k_inter launch");
+    launches_++;
+  }
+  if (any_intra) {
+    if (int e = launch_intra(d_jobs, n, g_, d_sync + 0, s)) return cuda_fail((cudaError_t)e, "k_intra launch");
+    launches_++;
+  }
+  if (any_lf) {
+    if (int e = launch_loopfilter(d_jobs, n, g_, d_sync + 32, s)) return cuda_fail((cudaError_t)e, "k_loopfilter launch");
+    launches_++;
+  }
+  return VP8GPU_OK;
+}
+
+int Engine::submit(int lane, const HostJob* jobs, int n, cudaEvent_t consumed) {
+  if (n <= 0) return VP8GPU_OK;
+  if (int rc = ensure_lane(lane)) return rc;
+  CU(cudaSetDevice(device_));
+  cudaStream_t s = lanes_[lane];
+  const Layout L = plan(g_, jobs, n);
+  Staging& st = staging_[lane][staging_next_[lane]];
+  staging_next_[lane] = (staging_next_[lane] + 1) % kStagingDepth;
+  if (st.in_flight) {
+    CU(cudaEventSynchronize(st.done));
+    st.in_flight = false;
+  }
+  if (!st.done) CU(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+  const size_t hdr_bytes = align_up(L.sync_off + L.sync_bytes, 256);
+  if (st.host_cap < hdr_bytes) {
+    if (st.host) CU(cudaFreeHost(st.host));
+    st.host_cap = hdr_bytes * 2;
+    CU(cudaHostAlloc(&st.host, st.host_cap, cudaHostAllocDefault));
+  }
+  if (st.dev_cap < L.total) {
+    if (st.dev) CU(cudaFree(st.dev));
+    st.dev_cap = L.total + L.total / 2;
+    CU(cudaMalloc(&st.dev, st.dev_cap));
+  }
+  // header: device-side job descriptors + zeroed tickets / progress counters
+  memset(st.host, 0, hdr_bytes);
+  DevJob* hj = reinterpret_cast<DevJob*>(st.host);
+  int* d_sync = reinterpret_cast<int*>(st.dev + L.sync_off);
+  bool any_inter = false, any_intra = false, any_lf = false;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (int i = 0; i < n; i++) {
+      const HostJob& j = jobs[i];
+      if (j.out < 0 || j.out >= (int)frames_.size() || frames_[j.out].refcnt <= 0)
+        return fail(VP8GPU_ERR_LOGIC, "submit: bad output frame");
+      DevJob& d = hj[i];
+      d.mbs = reinterpret_cast<const vp8gpu_mb*>(st.dev + L.mbs_off[i]);
+      d.tokens = reinterpret_cast<const vp8gpu_token*>(st.dev + L.tok_off[i]);
+      d.split = reinterpret_cast<const vp8gpu_split_mvs*>(st.dev + L.split_off[i]);
+      d.out = frames_[j.out].dev;
+      for (int r = 0; r < 3; r++) {
+        d.ref[r] = nullptr;
+        if (!j.desc->key_frame) {
+          if (j.refs[r] < 0 || j.refs[r] >= (int)frames_.size() || frames_[j.refs[r]].refcnt <= 0)
+            return fail(VP8GPU_ERR_LOGIC, "submit: bad reference frame");
+          d.ref[r] = frames_[j.refs[r]].dev;
+        }
+      }
+      d.intra_progress = d_sync + kSyncHeaderInts + (size_t)(2 * i) * g_.mb_rows;
+      d.lf_progress = d_sync + kSyncHeaderInts + (size_t)(2 * i + 1) * g_.mb_rows;
+      memcpy(d.quant, j.desc->quant, sizeof(d.quant));
+      d.key_frame = j.desc->key_frame;
+      d.sharpness = j.desc->sharpness;
+      uint32_t n_filtered;
+      count_jobs(j, &d.n_intra, &d.n_inter, &n_filtered);
+      d.lf_enabled = n_filtered != 0;
+      any_inter |= d.n_inter != 0;
+      any_intra |= d.n_intra != 0;
+      any_lf |= d.lf_enabled != 0;
+    }
+    // stream ordering against other users of the rasters
+    for (int i = 0; i < n; i++) {
+      if (int rc = wait_for(frames_[jobs[i].out], lane, s)) return rc;
+      frames_[jobs[i].out].pending &= 1ull << lane;
+      if (!jobs[i].desc->key_frame)
+        for (int r = 0; r < 3; r++)
+          if (int rc = wait_for(frames_[jobs[i].refs[r]], lane, s)) return rc;
+    }
+  }
+  CU(cudaMemcpyAsync(st.dev, st.host, hdr_bytes, cudaMemcpyHostToDevice, s));
+  const size_t n_mbs = (size_t)g_.mb_cols * g_.mb_rows;
+  for (int i = 0; i < n; i++) {
+    const HostJob& j = jobs[i];
+    CU(cudaMemcpyAsync(st.dev + L.mbs_off[i], j.mbs, n_mbs * sizeof(vp8gpu_mb), cudaMemcpyHostToDevice, s));
+    if (j.desc->n_tokens)
+      CU(cudaMemcpyAsync(st.dev + L.tok_off[i], j.tokens, (size_t)j.desc->n_tokens * sizeof(vp8gpu_token),
+                         cudaMemcpyHostToDevice, s));
+    if (j.desc->n_split)
+      CU(cudaMemcpyAsync(st.dev + L.split_off[i], j.split, (size_t)j.desc->n_split * sizeof(vp8gpu_split_mvs),
+                         cudaMemcpyHostToDevice, s));
+  }
+  if (consumed) CU(cudaEventRecord(consumed, s));
+  if (int rc = build_and_launch(lane, reinterpret_cast<const DevJob*>(st.dev), d_sync, n, any_inter, any_intra, any_lf))
+    return rc;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (int i = 0; i < n; i++) {
+      if (int rc = touch(frames_[jobs[i].out], lane)) return rc;
+      if (!jobs[i].desc->key_frame)
+        for (int r = 0; r < 3; r++)
+          if (int rc = touch(frames_[jobs[i].refs[r]], lane)) return rc;
+    }
+  }
+  CU(cudaEventRecord(st.done, s));
+  st.in_flight = true;
+  return VP8GPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-resident batches (bench / profiling): records stay in HBM, kernels can be re-run
+// ---------------------------------------------------------------------------------------------
+struct Engine::Resident {
+  uint8_t* dev = nullptr;
+  size_t sync_off = 0, sync_bytes = 0;
+  int n = 0;
+  bool any_inter = false, any_intra = false, any_lf = false;
+  std::vector<int> outs, refs;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+};
+
+int Engine::resident_upload(const HostJob* jobs, int n, Resident** out) {
+  if (n <= 0) return fail(VP8GPU_ERR_LOGIC, "empty batch");
+  if (int rc = ensure_lane(0)) return rc;
+  CU(cudaSetDevice(device_));
+  const Layout L = plan(g_, jobs, n);
+  Resident* r = new Resident();
+  r->n = n;
+  r->sync_off = L.sync_off;
+  r->sync_bytes = L.sync_bytes;
+  cudaError_t e = cudaMalloc(&r->dev, L.total);
+  if (e != cudaSuccess) {
+    delete r;
+    return cuda_fail(e, "cudaMalloc(resident batch)");
+  }
+  std::vector<uint8_t> hdr(align_up(L.sync_off + L.sync_bytes, 256), 0);
+  DevJob* hj = reinterpret_cast<DevJob*>(hdr.data());
+  int* d_sync = reinterpret_cast<int*>(r->dev + L.sync_off);
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (int i = 0; i < n; i++) {
+      const HostJob& j = jobs[i];
+      DevJob& d = hj[i];
+      d.mbs = reinterpret_cast<const vp8gpu_mb*>(r->dev + L.mbs_off[i]);
+      d.tokens = reinterpret_cast<const vp8gpu_token*>(r->dev + L.tok_off[i]);
+      d.split = reinterpret_cast<const vp8gpu_split_mvs*>(r->dev + L.split_off[i]);
+      if (j.out < 0 || j.out >= (int)frames_.size() || frames_[j.out].refcnt <= 0) {
+        cudaFree(r->dev);
+        delete r;
+        return fail(VP8GPU_ERR_LOGIC, "resident: bad output frame");
+      }
+      d.out = frames_[j.out].dev;
+      r->outs.push_back(j.out);
+      for (int k = 0; k < 3; k++) {
+        d.ref[k] = nullptr;
+        if (!j.desc->key_frame) {
+          if (j.refs[k] < 0 || j.refs[k] >= (int)frames_.size() || frames_[j.refs[k]].refcnt <= 0) {
+            cudaFree(r->dev);
+            delete r;
+            return fail(VP8GPU_ERR_LOGIC, "resident: bad reference frame");
+          }
+          d.ref[k] = frames_[j.refs[k]].dev;
+          r->refs.push_back(j.refs[k]);
+        }
+      }
+      d.intra_progress = d_sync + kSyncHeaderInts + (size_t)(2 * i) * g_.mb_rows;
+      d.lf_progress = d_sync + kSyncHeaderInts + (size_t)(2 * i + 1) * g_.mb_rows;
+      memcpy(d.quant, j.desc->quant, sizeof(d.quant));
+      d.key_frame = j.desc->key_frame;
+      d.sharpness = j.desc->sharpness;
+      uint32_t n_filtered;
+      count_jobs(j, &d.n_intra, &d.n_inter, &n_filtered);
+      d.lf_enabled = n_filtered != 0;
+      r->any_inter |= d.n_inter != 0;
+      r->any_intra |= d.n_intra != 0;
+      r->any_lf |= d.lf_enabled != 0;
+    }
+  }
+  const size_t n_mbs = (size_t)g_.mb_cols * g_.mb_rows;
+  CU(cudaMemcpy(r->dev, hdr.data(), hdr.size(), cudaMemcpyHostToDevice));
+  for (int i = 0; i < n; i++) {
+    CU(cudaMemcpy(r->dev + L.mbs_off[i], jobs[i].mbs, n_mbs * sizeof(vp8gpu_mb), cudaMemcpyHostToDevice));
+    if (jobs[i].desc->n_tokens)
+      CU(cudaMemcpy(r->dev + L.tok_off[i], jobs[i].tokens, (size_t)jobs[i].desc->n_tokens * 4, cudaMemcpyHostToDevice));
+    if (jobs[i].desc->n_split)
+      CU(cudaMemcpy(r->dev + L.split_off[i], jobs[i].split, (size_t)jobs[i].desc->n_split * 64, cudaMemcpyHostToDevice));
+  }
+  CU(cudaEventCreate(&r->t0));
+  CU(cudaEventCreate(&r->t1));
+  *out = r;
+  return VP8GPU_OK;
+}
+
+int Engine::resident_run(int lane, Resident* r, float* ms) {
+  if (int rc = ensure_lane(lane)) return rc;
+  CU(cudaSetDevice(device_));
+  cudaStream_t s = lanes_[lane];
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (int id : r->outs) {
+      if (int rc = wait_for(frames_[id], lane, s)) return rc;
+    }
+    for (int id : r->refs)
+      if (int rc = wait_for(frames_[id], lane, s)) return rc;
+  }
+  CU(cudaMemsetAsync(r->dev + r->sync_off, 0, r->sync_bytes, s));
+  if (ms) CU(cudaEventRecord(r->t0, s));
+  if (int rc = build_and_launch(lane, reinterpret_cast<const DevJob*>(r->dev), reinterpret_cast<int*>(r->dev + r->sync_off),
+                                r->n, r->any_inter, r->any_intra, r->any_lf))
+    return rc;
+  if (ms) CU(cudaEventRecord(r->t1, s));
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (int id : r->outs)
+      if (int rc = touch(frames_[id], lane)) return rc;
+    for (int id : r->refs)
+      if (int rc = touch(frames_[id], lane)) return rc;
+  }
+  if (ms) {
+    CU(cudaEventSynchronize(r->t1));
+    CU(cudaEventElapsedTime(ms, r->t0, r->t1));
+  }
+  return VP8GPU_OK;
+}
+
+void Engine::resident_free(Resident* r) {
+  if (!r) return;
+  cudaSetDevice(device_);
+  cudaDeviceSynchronize();
+  if (r->dev) cudaFree(r->dev);
+  if (r->t0) cudaEventDestroy(r->t0);
+  if (r->t1) cudaEventDestroy(r->t1);
+  delete r;
+}
+
+int Engine::sync_all() {
+  CU(cudaSetDevice(device_));
+  CU(cudaDeviceSynchronize());
+  return VP8GPU_OK;
+}
+int Engine::sync_lane(int lane) {
+  if (int rc = ensure_lane(lane)) return rc;
+  CU(cudaStreamSynchronize(lanes_[lane]));
+  CU(cudaStreamSynchronize(lanes_[kMaxLanes + lane]));
+  return VP8GPU_OK;
+}
+
+}  // namespace vp8

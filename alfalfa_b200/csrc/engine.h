@@ -1,0 +1,44 @@
+// engine.h -- device-side job description shared by kernels.cu (device code) and
+// engine.cu (host orchestration).  Internal to the library; the public surface is
+// include/vp8gpu.h.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/vp8gpu.h"
+
+namespace vp8 {
+
+// Geometry of every raster of a context.  Planes live in one allocation:
+//   Y at 0 (y_pitch x H), U at u_off, V at v_off (c_pitch x H/2 each).
+// Pitches are multiples of 32 / 16 bytes so rows can be moved as 16-byte / 8-byte vectors.
+struct Geom {
+  int mb_cols, mb_rows;
+  int W, H;              // MB-aligned luma size (16*mb_cols, 16*mb_rows), VP8Raster dims
+  int y_pitch, c_pitch;  // bytes
+  uint32_t u_off, v_off; // byte offsets of the chroma planes
+  uint32_t frame_bytes;
+};
+
+// One frame's decode job as the kernels see it (an array of these lives in HBM).
+struct DevJob {
+  const vp8gpu_mb* mbs;
+  const vp8gpu_token* tokens;
+  const vp8gpu_split_mvs* split;
+  uint8_t* out;
+  const uint8_t* ref[3];   // last, golden, altref (ref_frame - 1)
+  int* intra_progress;     // [mb_rows] wavefront counters, zeroed before launch
+  int* lf_progress;        // [mb_rows]
+  vp8gpu_quant quant[4];
+  uint8_t key_frame, sharpness, lf_enabled, pad;
+  uint32_t n_intra;        // intra-coded macroblocks in the frame
+  uint32_t n_inter;
+  uint32_t pad2;
+};
+
+// Kernel launchers (kernels.cu).  `stream` is a cudaStream_t passed as void* so this header
+// stays free of CUDA includes.  Return 0 or a cudaError_t value.
+int launch_inter(const DevJob* jobs, int njobs, const Geom& g, void* stream);
+int launch_intra(const DevJob* jobs, int njobs, const Geom& g, int* ticket, void* stream);
+int launch_loopfilter(const DevJob* jobs, int njobs, const Geom& g, int* ticket, void* stream);
+
+}  // namespace vp8

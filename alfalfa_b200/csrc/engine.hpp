@@ -1,0 +1,106 @@
+// engine.hpp -- host orchestration of the device side: frame pool (RasterHandle semantics),
+// per-lane CUDA streams, staging of parsed records, kernel launches.  Internal header.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+#include "parser.h"
+
+namespace vp8 {
+
+constexpr int kMaxLanes = 32;       // compute lanes; lane i's copy stream is slot kMaxLanes + i
+constexpr int kStagingDepth = 3;    // device record buffers in flight per lane
+
+// a decode job with host-side record arrays
+struct HostJob {
+  const vp8gpu_frame_desc* desc;
+  const vp8gpu_mb* mbs;
+  const vp8gpu_token* tokens;
+  const vp8gpu_split_mvs* split;
+  int refs[3];
+  int out;
+  int n_intra = -1;    // -1: count them here
+  int n_filtered = -1;
+};
+
+class Engine {
+ public:
+  static int create(int device, int width, int height, int max_frames, Engine** out, std::string* err);
+  ~Engine();
+
+  const Geom& geom() const { return g_; }
+  int width() const { return width_; }
+  int height() const { return height_; }
+  int device() const { return device_; }
+
+  // frame pool
+  int frame_alloc(int* id);
+  int frame_retain(int id);
+  int frame_release(int id);
+  int frame_upload(int id, const uint8_t* y, size_t ys, const uint8_t* u, const uint8_t* v, size_t cs);
+  int frame_download(int id, uint8_t* y, size_t ys, uint8_t* u, uint8_t* v, size_t cs);
+  int frame_download_display(int id, int lane, uint8_t* dst, size_t dst_size, bool wait);
+  int frame_clear(int id, int lane);  // all-zero raster (initial References)
+  int frames_equal(int a, int b, int lane, int* equal);
+
+  // decode n frames in one set of launches on `lane`; host arrays must stay valid until the
+  // returned event (*consumed, optional) has fired (pinned) or are consumed on return (pageable)
+  int submit(int lane, const HostJob* jobs, int n, cudaEvent_t consumed);
+
+  // device-resident batches
+  struct Resident;
+  int resident_upload(const HostJob* jobs, int n, Resident** out);
+  int resident_run(int lane, Resident* r, float* ms);
+  void resident_free(Resident* r);
+
+  int sync_all();
+  int sync_lane(int lane);
+  cudaStream_t stream(int lane) const { return lanes_[lane]; }
+  uint64_t launches() const { return launches_.load(); }
+  const char* last_error() const { return err_.c_str(); }
+  int fail(int code, const std::string& what);
+  int cuda_fail(cudaError_t e, const char* what);
+
+ private:
+  Engine() = default;
+  struct Frame {
+    uint8_t* dev = nullptr;
+    int refcnt = 0;
+    uint64_t pending = 0;                  // stream slots that touched it since the last wait
+    cudaEvent_t ev[2 * kMaxLanes] = {};    // lazily created
+  };
+  struct Staging {
+    uint8_t* dev = nullptr;
+    size_t dev_cap = 0;
+    uint8_t* host = nullptr;  // pinned header: DevJob[n] + sync words
+    size_t host_cap = 0;
+    cudaEvent_t done = nullptr;
+    bool in_flight = false;
+  };
+  int ensure_lane(int lane);
+  int touch(Frame& f, int slot);                     // record "slot used this frame"
+  int wait_for(Frame& f, int slot, cudaStream_t s);  // make stream s wait for other users
+  int build_and_launch(int lane, const DevJob* d_jobs, int* d_sync, int n, bool any_inter, bool any_intra,
+                       bool any_lf);
+  int count_jobs(const HostJob& j, uint32_t* n_intra, uint32_t* n_inter, uint32_t* n_filtered) const;
+
+  int device_ = 0, width_ = 0, height_ = 0;
+  Geom g_{};
+  std::mutex mu_;
+  std::vector<Frame> frames_;
+  std::vector<int> free_;
+  cudaStream_t lanes_[2 * kMaxLanes] = {};
+  Staging staging_[kMaxLanes][kStagingDepth];
+  int staging_next_[kMaxLanes] = {};
+  uint8_t* cmp_scratch_ = nullptr;
+  std::atomic<uint64_t> launches_{0};
+  std::string err_;
+};
+
+}  // namespace vp8

@@ -1,0 +1,83 @@
+// parser.h -- CPU entropy front end of the B200 VP8 pipeline.
+//
+// Replaces, on the host, what the reference does in DecoderState::parse_and_apply
+// (decoder/decoder_state.hh:73-167): bool-decode the first partition (frame header, macroblock
+// modes, motion vectors) and the DCT partitions (coefficient tokens).  Instead of the
+// reference's per-frame object graph (TwoD<Macroblock>, 25 Block objects per macroblock,
+// decoder/frame.hh:56-61) it emits the flat records of include/vp8gpu.h directly into
+// (optionally pinned) staging memory that is copied to HBM as is: one 32-byte vp8gpu_mb per
+// macroblock, one 32-bit token per non-zero coefficient, one 64-byte entry per SPLITMV
+// macroblock.  Header and token parsing are fused into a single raster pass that only keeps
+// one row of neighbour context.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "../../include/vp8gpu.h"
+
+namespace vp8 {
+
+// DecoderState (decoder/decoder.hh:190-225) as a plain copyable value.
+struct State {
+  int width = 0, height = 0, mb_cols = 0, mb_rows = 0;
+  uint8_t coef_probs[1056];
+  uint8_t ymode_probs[4];
+  uint8_t uvmode_probs[3];
+  uint8_t mv_probs[2][19];
+  bool seg_enabled = false, seg_abs = false;  // Optional<Segmentation>
+  int8_t seg_quant[4] = {0, 0, 0, 0}, seg_lf[4] = {0, 0, 0, 0};
+  std::vector<uint8_t> seg_map;               // mb_cols * mb_rows
+  bool lf_adj_enabled = false;                // Optional<FilterAdjustments>
+  int8_t ref_adj[4] = {0, 0, 0, 0}, mode_adj[4] = {0, 0, 0, 0};
+
+  State(int w, int h);
+  void reset_probs();
+  bool operator==(const State& o) const;  // DecoderState::operator==, decoder.cc:257-264
+  uint64_t hash() const;
+};
+
+// Growable array whose storage comes from a pluggable allocator, so that the engine can
+// hand the parser pinned host memory (cudaHostAlloc) and DMA it without a staging copy.
+struct Allocator {
+  void* (*alloc)(size_t);
+  void (*free)(void*);
+};
+extern const Allocator kMallocAllocator;
+
+template <class T>
+class Buffer {
+ public:
+  explicit Buffer(const Allocator& a) : a_(a) {}
+  ~Buffer() { if (p_) a_.free(p_); }
+  Buffer(const Buffer&) = delete;
+  Buffer& operator=(const Buffer&) = delete;
+  T* data() { return p_; }
+  const T* data() const { return p_; }
+  size_t capacity() const { return cap_; }
+  // keeps the first `keep` elements
+  bool reserve(size_t n, size_t keep);
+ private:
+  Allocator a_;
+  T* p_ = nullptr;
+  size_t cap_ = 0;
+};
+
+// KeyFrame / InterFrame (decoder/frame.hh:126-127) in flat form.
+struct ParsedFrame {
+  explicit ParsedFrame(const Allocator& a = kMallocAllocator) : mbs(a), tokens(a), split(a) {}
+  vp8gpu_frame_desc desc{};
+  Buffer<vp8gpu_mb> mbs;
+  Buffer<vp8gpu_token> tokens;
+  Buffer<vp8gpu_split_mvs> split;
+};
+
+// Parse one compressed frame and apply it to `state`.  Returns VP8GPU_OK or VP8GPU_ERR_*;
+// on error `state` is left untouched.
+int parse_frame(State& state, const uint8_t* data, size_t len, ParsedFrame& out);
+
+// true if the frame tag says key frame (uncompressed_chunk.cc:53)
+inline bool is_key_frame(const uint8_t* data, size_t len) { return len > 0 && !(data[0] & 1); }
+
+}  // namespace vp8

@@ -1,0 +1,295 @@
+"""Host-side mirror of the reference's decoder interface (src/decoder/decoder.hh:244-300,
+player.hh:40-97) for Python callers (tests, bench).  Same names and meaning as the reference:
+
+    Decoder(ctx)                      Decoder(width, height)
+    Decoder.parse_frame(chunk)        Decoder::parse_frame<FrameType>  -> ParsedFrame
+    Decoder.decode_frame(parsed)      Decoder::decode_frame            -> (shown, RasterHandle)
+    Decoder.get_frame_output(chunk)   Decoder::get_frame_output        -> (shown, RasterHandle)
+    Decoder.parse_and_decode_frame    -> RasterHandle or None (hidden frame)
+    Decoder.get_state / get_references / copy() / ==
+    FilePlayer(ctx, ivf_bytes).advance() / eof()
+
+Errors are raised as Invalid / Unsupported / LogicError like the reference's exception classes.
+Every call goes through the C ABI in libvpx8gpu.so; nothing here computes pixels.
+"""
+import ctypes as C
+import struct
+
+import numpy as np
+
+from . import capi
+from .capi import check
+
+
+class Context:
+    """vp8gpu_ctx: one CUDA device + one frame size (per-context raster pool)."""
+
+    def __init__(self, width, height, device=0, max_frames=0):
+        self.L = capi.lib()
+        self.width, self.height = width, height
+        self.mb_cols, self.mb_rows = (width + 15) // 16, (height + 15) // 16
+        self.h = C.c_void_p()
+        check(self.L.vp8gpu_ctx_create(device, width, height, max_frames, C.byref(self.h)), None,
+              "vp8gpu_ctx_create (is a CUDA device present?)")
+
+    def close(self):
+        if self.h:
+            self.L.vp8gpu_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def display_bytes(self):
+        return self.width * self.height + 2 * ((self.width + 1) // 2) * ((self.height + 1) // 2)
+
+    def sync(self):
+        check(self.L.vp8gpu_ctx_sync(self.h), self.h, "sync")
+
+    def launch_count(self):
+        return int(self.L.vp8gpu_launch_count(self.h))
+
+    def alloc_frame(self):
+        fid = C.c_int32(-1)
+        check(self.L.vp8gpu_frame_alloc(self.h, C.byref(fid)), self.h, "frame_alloc")
+        return RasterHandle(self, fid.value)
+
+
+class RasterHandle:
+    """RasterHandle (decoder/raster_handle.hh:95-123): a ref-counted device raster."""
+
+    def __init__(self, ctx, fid):
+        self.ctx, self.id = ctx, fid
+
+    def release(self):
+        if self.id is not None and self.ctx.h:
+            self.ctx.L.vp8gpu_frame_release(self.ctx.h, self.id)
+        self.id = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def planes(self):
+        """MB-aligned planes (Y, U, V) as numpy arrays (blocks until the frame is decoded)."""
+        c = self.ctx
+        W, H = 16 * c.mb_cols, 16 * c.mb_rows
+        y = np.empty((H, W), np.uint8)
+        u = np.empty((H // 2, W // 2), np.uint8)
+        v = np.empty((H // 2, W // 2), np.uint8)
+        check(c.L.vp8gpu_frame_download(c.h, self.id, y.ctypes.data, W, u.ctypes.data, v.ctypes.data, W // 2), c.h,
+              "frame_download")
+        return y, u, v
+
+    def upload(self, y, u, v):
+        c = self.ctx
+        y, u, v = (np.ascontiguousarray(a, dtype=np.uint8) for a in (y, u, v))
+        check(c.L.vp8gpu_frame_upload(c.h, self.id, y.ctypes.data, y.shape[1], u.ctypes.data, v.ctypes.data,
+                                      u.shape[1]), c.h, "frame_upload")
+
+    def display_bytes(self):
+        """BaseRaster::dump (util/raster.cc:85-114)"""
+        c = self.ctx
+        buf = np.empty(c.display_bytes, np.uint8)
+        check(c.L.vp8gpu_frame_download_display(c.h, self.id, buf.ctypes.data, buf.size), c.h, "download_display")
+        return buf.tobytes()
+
+
+class DecoderState:
+    """DecoderState (decoder.hh:190-225) handle."""
+
+    def __init__(self, width=None, height=None, _h=None, _owned=True):
+        self.L = capi.lib()
+        self._owned = _owned
+        if _h is not None:
+            self.h = _h
+        else:
+            self.h = C.c_void_p()
+            check(self.L.vp8gpu_state_create(width, height, C.byref(self.h)))
+
+    def clone(self):
+        h = C.c_void_p()
+        check(self.L.vp8gpu_state_clone(self.h, C.byref(h)))
+        return DecoderState(_h=h)
+
+    def __eq__(self, other):
+        return bool(self.L.vp8gpu_state_equal(self.h, other.h))
+
+    def hash(self):
+        return int(self.L.vp8gpu_state_hash(self.h))
+
+    def __del__(self):
+        try:
+            if self._owned and self.h:
+                self.L.vp8gpu_state_destroy(self.h)
+        except Exception:
+            pass
+
+
+class ParsedFrame:
+    """KeyFrame / InterFrame (frame.hh:126-127) in the flat form of include/vp8gpu.h."""
+
+    def __init__(self):
+        self.L = capi.lib()
+        self.h = C.c_void_p()
+        check(self.L.vp8gpu_parsed_create(C.byref(self.h)))
+
+    def __del__(self):
+        try:
+            self.L.vp8gpu_parsed_destroy(self.h)
+        except Exception:
+            pass
+
+    @property
+    def desc(self):
+        return self.L.vp8gpu_parsed_desc(self.h).contents
+
+    def arrays(self):
+        """copies of (mbs, tokens, split)"""
+        d = self.desc
+        n = d.mb_cols * d.mb_rows
+        mbs = np.frombuffer(C.string_at(self.L.vp8gpu_parsed_mbs(self.h), n * 32), dtype=capi.MB_DTYPE).copy()
+        tok = (np.frombuffer(C.string_at(self.L.vp8gpu_parsed_tokens(self.h), d.n_tokens * 4), dtype="<u4").copy()
+               if d.n_tokens else np.zeros(0, "<u4"))
+        sp = (np.frombuffer(C.string_at(self.L.vp8gpu_parsed_split(self.h), d.n_split * 64), dtype="<i2").copy()
+              .reshape(-1, 16, 2) if d.n_split else np.zeros((0, 16, 2), "<i2"))
+        return mbs, tok, sp
+
+
+class Decoder:
+    """Decoder (decoder.hh:244-300): DecoderState + References with explicit state passing."""
+
+    def __init__(self, ctx, _h=None):
+        self.ctx, self.L = ctx, ctx.L
+        if _h is not None:
+            self.h = _h
+        else:
+            self.h = C.c_void_p()
+            check(self.L.vp8gpu_decoder_create(ctx.h, C.byref(self.h)), ctx.h, "decoder_create")
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.L.vp8gpu_decoder_destroy(self.h)
+        except Exception:
+            pass
+
+    def copy(self):
+        """copy construction: O(1) in pixels, shares the reference rasters"""
+        h = C.c_void_p()
+        check(self.L.vp8gpu_decoder_clone(self.h, C.byref(h)), self.ctx.h, "decoder_clone")
+        return Decoder(self.ctx, h)
+
+    def get_state(self):
+        return DecoderState(_h=C.c_void_p(self.L.vp8gpu_decoder_state(self.h)), _owned=False).clone()
+
+    def get_references(self):
+        """(last, golden, alternative) as new RasterHandles"""
+        ids = (C.c_int32 * 3)()
+        self.L.vp8gpu_decoder_references(self.h, ids)
+        out = []
+        for i in ids:
+            check(self.L.vp8gpu_frame_retain(self.ctx.h, i), self.ctx.h, "retain")
+            out.append(RasterHandle(self.ctx, i))
+        return tuple(out)
+
+    def parse_frame(self, chunk):
+        """Decoder::decompress_frame + parse_frame: updates the decoder's state"""
+        p = ParsedFrame()
+        st = C.c_void_p(self.L.vp8gpu_decoder_state(self.h))
+        check(self.L.vp8gpu_parse_frame(st, chunk, len(chunk), p.h), self.ctx.h, "parse_frame")
+        return p
+
+    def decode_frame(self, parsed):
+        shown, fid = C.c_int(0), C.c_int32(-1)
+        check(self.L.vp8gpu_decoder_decode_parsed(self.h, parsed.h, C.byref(shown), C.byref(fid)), self.ctx.h,
+              "decode_frame")
+        return bool(shown.value), RasterHandle(self.ctx, fid.value)
+
+    def get_frame_output(self, chunk):
+        shown, fid = C.c_int(0), C.c_int32(-1)
+        check(self.L.vp8gpu_decoder_decode(self.h, chunk, len(chunk), C.byref(shown), C.byref(fid)), self.ctx.h,
+              "get_frame_output")
+        return bool(shown.value), RasterHandle(self.ctx, fid.value)
+
+    def parse_and_decode_frame(self, chunk):
+        shown, raster = self.get_frame_output(chunk)
+        return raster if shown else None
+
+    def __eq__(self, other):
+        eq = C.c_int(0)
+        check(self.L.vp8gpu_decoder_equal(self.h, other.h, C.byref(eq)), self.ctx.h, "decoder_equal")
+        return bool(eq.value)
+
+
+def read_ivf(data):
+    """util/ivf.cc:36-82 -> (width, height, [frames])"""
+    if data[:4] != b"DKIF":
+        raise capi.Invalid(capi.ERR_INVALID, "missing IVF file header")
+    w, h = struct.unpack_from("<HH", data, 12)
+    n = struct.unpack_from("<I", data, 24)[0]
+    frames, pos = [], 32
+    for _ in range(n):
+        if pos + 12 > len(data):
+            raise capi.Invalid(capi.ERR_INVALID, "IVF file truncated")
+        flen = struct.unpack_from("<I", data, pos)[0]
+        frames.append(bytes(data[pos + 12:pos + 12 + flen]))
+        pos += 12 + flen
+    return w, h, frames
+
+
+class FilePlayer:
+    """FilePlayer (player.cc:88-143): starts at the first key frame, advance() skips hidden frames."""
+
+    def __init__(self, ctx, ivf_bytes):
+        w, h, self.frames = read_ivf(ivf_bytes)
+        if (w, h) != (ctx.width, ctx.height):
+            raise capi.Unsupported(capi.ERR_UNSUPPORTED, "IVF size does not match the context")
+        self.decoder = Decoder(ctx)
+        self.frame_no = 0
+        while self.frame_no < len(self.frames) and (self.frames[self.frame_no][0] & 1):
+            self.frame_no += 1
+
+    def eof(self):
+        return self.frame_no == len(self.frames)
+
+    def advance(self):
+        while not self.eof():
+            r = self.decoder.parse_and_decode_frame(self.frames[self.frame_no])
+            self.frame_no += 1
+            if r is not None:
+                return r
+        raise capi.Unsupported(capi.ERR_UNSUPPORTED, "hidden frames at end of file")
+
+
+def decode_ivf(ctx, ivf_bytes, threads=1, want_output=True):
+    """Whole-stream decode through vp8gpu_decode_ivf (GOP-parallel host workers).
+    Returns (display bytes of all shown frames or None, n_decoded, n_shown)."""
+    L = ctx.L
+    _, _, frames = read_ivf(ivf_bytes)
+    start = 0
+    while start < len(frames) and (frames[start][0] & 1):
+        start += 1
+    n_shown_guess = sum(1 for f in frames[start:] if len(f) and (f[0] >> 4) & 1)
+    size = n_shown_guess * ctx.display_bytes
+    dst = None
+    ptr = C.c_void_p()
+    if want_output and size:
+        check(L.vp8gpu_host_alloc(C.byref(ptr), size), ctx.h, "host_alloc")
+    nd, ns = C.c_uint32(0), C.c_uint32(0)
+    try:
+        check(L.vp8gpu_decode_ivf(ctx.h, ivf_bytes, len(ivf_bytes), threads, ptr, size if ptr else 0, C.byref(nd),
+                                  C.byref(ns)), ctx.h, "decode_ivf")
+        check(L.vp8gpu_ctx_sync(ctx.h), ctx.h, "sync")
+        if ptr:
+            dst = C.string_at(ptr, ns.value * ctx.display_bytes)
+    finally:
+        if ptr:
+            L.vp8gpu_host_free(ptr)
+    return dst, nd.value, ns.value

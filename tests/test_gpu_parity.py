@@ -1,0 +1,152 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against
+(a) the reference's golden SHA-1 vectors and (b) the CPU oracle frame by frame.  Bit-exact:
+this is integer / byte work, the tolerance is zero."""
+import ctypes as C
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from conftest import GOLDEN_DIR, golden_vectors
+
+pytestmark = pytest.mark.gpu
+
+
+def _read(name):
+    return open(os.path.join(GOLDEN_DIR, name), "rb").read()
+
+
+@pytest.mark.parametrize("name", golden_vectors())
+def test_fileplayer_reproduces_golden_sha1(name):
+    """decode-to-stdout (src/tests/decode-to-stdout.cc:43-49) on the GPU path: sha1 == file name"""
+    from alfalfa_b200 import Context, FilePlayer
+    data = _read(name)
+    w, h, _ = O.read_ivf(data)
+    ctx = Context(w, h, max_frames=16)
+    player = FilePlayer(ctx, data)
+    sha = hashlib.sha1()
+    while not player.eof():
+        sha.update(player.advance().display_bytes())
+    del player
+    ctx.close()
+    assert sha.hexdigest() == name
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+@pytest.mark.parametrize("name", ["2a4c049c2f8e3a19ee39ffd7074cecd68006a101",
+                                  "45502fe01a62b82d498b83dc50824741402436db",
+                                  "ff2941dde20090835032c32c0644b6d401610c57"])
+def test_gop_parallel_stream_decode_matches_golden(name, threads):
+    from alfalfa_b200 import Context, decode_ivf
+    data = _read(name)
+    w, h, _ = O.read_ivf(data)
+    ctx = Context(w, h, max_frames=48)
+    out, n_dec, n_shown = decode_ivf(ctx, data, threads=threads)
+    ctx.close()
+    assert n_shown > 0 and hashlib.sha1(out).hexdigest() == name
+
+
+@pytest.mark.parametrize("name", ["0b546dad90ddefea5085c7751b5fa2f117630b1c",
+                                  "e01c6f92f23eefecb1e120230a2c4b2767cce066",
+                                  "a4dace04a77fc9f969a8d7a645c99c0271f1f73e"])
+def test_every_frame_matches_oracle_including_hidden_and_references(name):
+    """frame-by-frame (not only shown frames): decoded raster and the three references"""
+    from alfalfa_b200 import Context, Decoder
+    data = _read(name)
+    w, h, frames = O.read_ivf(data)
+    ctx = Context(w, h, max_frames=16)
+    dec = Decoder(ctx)
+    od = O.OracleDecoder(w, h)
+    started = False
+    for i, f in enumerate(frames[:40]):
+        if not started and (f[0] & 1):
+            continue
+        started = True
+        want = od.decode(f)
+        shown, raster = dec.get_frame_output(f)
+        assert shown == want["shown"]
+        for g, w_ in zip(raster.planes(), want["planes"]):
+            assert np.array_equal(g, w_), "frame %d" % i
+        raster.release()
+    for k, r in enumerate(dec.get_references()):
+        for g, w_ in zip(r.planes(), O.raster_planes(od.L.vp8o_decoder_ref(od.d, k))):
+            assert np.array_equal(g, w_), "reference %d" % k
+        r.release()
+    del dec
+    ctx.close()
+
+
+def test_decoder_copy_shares_state_and_diverges_independently():
+    """explicit state passing: a copied Decoder continues independently (salsify-sender.cc:492-518)"""
+    from alfalfa_b200 import Context, Decoder
+    data = _read("2a4c049c2f8e3a19ee39ffd7074cecd68006a101")
+    w, h, frames = O.read_ivf(data)
+    ctx = Context(w, h, max_frames=24)
+    a = Decoder(ctx)
+    for f in frames[:5]:
+        a.get_frame_output(f)[1].release()
+    b = a.copy()
+    assert a == b
+    ra = a.get_frame_output(frames[5])[1]
+    assert not (a == b)
+    rb = b.get_frame_output(frames[5])[1]
+    assert a == b
+    assert all(np.array_equal(x, y) for x, y in zip(ra.planes(), rb.planes()))
+    ra.release()
+    rb.release()
+    del a, b
+    ctx.close()
+
+
+def test_batched_seam_matches_oracle():
+    """vp8gpu_decode_batch: independent key frames of one stream decoded in one set of launches"""
+    from alfalfa_b200 import Context, capi
+    data = _read("45502fe01a62b82d498b83dc50824741402436db")  # 320x240, 30 key frames
+    w, h, frames = O.read_ivf(data)
+    ctx = Context(w, h, max_frames=40)
+    L = ctx.L
+    od = O.OracleDecoder(w, h)
+    keep, jobs, outs, wants = [], (capi.Job * 8)(), [], []
+    for i, f in enumerate(frames[:8]):
+        r = od.decode(f)
+        p = od.parsed()
+        assert p.desc.key_frame
+        mbs, tok, sp = (np.ascontiguousarray(x) for x in (p.mbs, p.tokens, p.split))
+        desc = capi.FrameDesc.from_buffer_copy(bytes(p.desc))
+        out = ctx.alloc_frame()
+        keep.append((mbs, tok, sp, desc))
+        jobs[i].desc = C.pointer(desc)
+        jobs[i].mbs = mbs.ctypes.data
+        jobs[i].tokens = tok.ctypes.data if tok.size else None
+        jobs[i].split = None
+        jobs[i].refs[:] = [-1, -1, -1]
+        jobs[i].out = out.id
+        outs.append(out)
+        wants.append(r["planes"])
+    capi.check(L.vp8gpu_decode_batch(ctx.h, 0, jobs, 8), ctx.h, "decode_batch")
+    for out, want in zip(outs, wants):
+        assert all(np.array_equal(g, w_) for g, w_ in zip(out.planes(), want))
+        out.release()
+    ctx.close()
+
+
+def test_errors_mirror_reference_exception_classes():
+    from alfalfa_b200 import Context, Decoder, Invalid, Unsupported
+    ctx = Context(320, 240)
+    dec = Decoder(ctx)
+    with pytest.raises(Invalid):
+        dec.get_frame_output(b"\x00\x00")  # truncated tag
+    data = _read("45502fe01a62b82d498b83dc50824741402436db")
+    _, _, frames = O.read_ivf(data)
+    bad = bytearray(frames[0])
+    bad[3] = 0  # broken start code (uncompressed_chunk.cc:101-103)
+    with pytest.raises(Invalid):
+        dec.get_frame_output(bytes(bad))
+    other = Context(176, 144)
+    with pytest.raises(Unsupported):  # size mismatch (uncompressed_chunk.cc:111-115)
+        Decoder(other).get_frame_output(frames[0])
+    del dec
+    ctx.close()
+    other.close()
