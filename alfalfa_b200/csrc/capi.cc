@@ -174,6 +174,14 @@ int vp8gpu_batch_upload(vp8gpu_ctx* ctx, const vp8gpu_job* jobs, int n, vp8gpu_r
 int vp8gpu_batch_run(vp8gpu_ctx* ctx, int lane, vp8gpu_resident_batch* b, float* kernel_ms) {
   return ctx->engine->resident_run(lane, b->r, kernel_ms);
 }
+int vp8gpu_batches_run(vp8gpu_ctx* ctx, int lane, vp8gpu_resident_batch* const* batches, int n, float* total_ms) {
+  std::vector<Engine::Resident*> rs;
+  for (int i = 0; i < n; i++) rs.push_back(batches[i]->r);
+  return ctx->engine->resident_run_many(lane, rs.data(), n, total_ms);
+}
+int vp8gpu_batch_run_timed(vp8gpu_ctx* ctx, int lane, vp8gpu_resident_batch* b, float kernel_ms[3]) {
+  return ctx->engine->resident_run_timed(lane, b->r, kernel_ms);
+}
 void vp8gpu_batch_free(vp8gpu_ctx* ctx, vp8gpu_resident_batch* b) {
   if (!b) return;
   ctx->engine->resident_free(b->r);

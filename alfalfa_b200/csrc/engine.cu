@@ -291,16 +291,18 @@ Layout plan(const Geom& g, const HostJob* jobs, int n) {
 }  // namespace
 
 int Engine::build_and_launch(int lane, const DevJob* d_jobs, int* d_sync, int n, bool any_inter, bool any_intra,
-                             bool any_lf) {
+                             bool any_lf, cudaEvent_t* between) {
   cudaStream_t s = lanes_[lane];
   if (any_inter) {
     if (int e = launch_inter(d_jobs, n, g_, s)) return cuda_fail((cudaError_t)e, "k_inter launch");
     launches_++;
   }
+  if (between) CU(cudaEventRecord(between[0], s));
   if (any_intra) {
     if (int e = launch_intra(d_jobs, n, g_, d_sync + 0, s)) return cuda_fail((cudaError_t)e, "k_intra launch");
     launches_++;
   }
+  if (between) CU(cudaEventRecord(between[1], s));
   if (any_lf) {
     if (int e = launch_loopfilter(d_jobs, n, g_, d_sync + 32, s)) return cuda_fail((cudaError_t)e, "k_loopfilter launch");
     launches_++;
@@ -519,6 +521,57 @@ int Engine::resident_run(int lane, Resident* r, float* ms) {
     CU(cudaEventSynchronize(r->t1));
     CU(cudaEventElapsedTime(ms, r->t0, r->t1));
   }
+  return VP8GPU_OK;
+}
+
+int Engine::resident_run_many(int lane, Resident* const* rs, int n, float* total_ms) {
+  if (n <= 0) return VP8GPU_OK;
+  if (int rc = ensure_lane(lane)) return rc;
+  cudaStream_t s = lanes_[lane];
+  if (total_ms) CU(cudaEventRecord(rs[0]->t0, s));
+  for (int i = 0; i < n; i++)
+    if (int rc = resident_run(lane, rs[i], nullptr)) return rc;
+  if (total_ms) {
+    CU(cudaEventRecord(rs[0]->t1, s));
+    CU(cudaEventSynchronize(rs[0]->t1));
+    CU(cudaEventElapsedTime(total_ms, rs[0]->t0, rs[0]->t1));
+  }
+  return VP8GPU_OK;
+}
+
+int Engine::resident_run_timed(int lane, Resident* r, float ms[3]) {
+  if (int rc = ensure_lane(lane)) return rc;
+  CU(cudaSetDevice(device_));
+  cudaStream_t s = lanes_[lane];
+  cudaEvent_t mid[2];
+  CU(cudaEventCreate(&mid[0]));
+  CU(cudaEventCreate(&mid[1]));
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (int id : r->outs)
+      if (int rc = wait_for(frames_[id], lane, s)) return rc;
+    for (int id : r->refs)
+      if (int rc = wait_for(frames_[id], lane, s)) return rc;
+  }
+  CU(cudaMemsetAsync(r->dev + r->sync_off, 0, r->sync_bytes, s));
+  CU(cudaEventRecord(r->t0, s));
+  if (int rc = build_and_launch(lane, reinterpret_cast<const DevJob*>(r->dev), reinterpret_cast<int*>(r->dev + r->sync_off),
+                                r->n, r->any_inter, r->any_intra, r->any_lf, mid))
+    return rc;
+  CU(cudaEventRecord(r->t1, s));
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (int id : r->outs)
+      if (int rc = touch(frames_[id], lane)) return rc;
+    for (int id : r->refs)
+      if (int rc = touch(frames_[id], lane)) return rc;
+  }
+  CU(cudaEventSynchronize(r->t1));
+  CU(cudaEventElapsedTime(&ms[0], r->t0, mid[0]));
+  CU(cudaEventElapsedTime(&ms[1], mid[0], mid[1]));
+  CU(cudaEventElapsedTime(&ms[2], mid[1], r->t1));
+  cudaEventDestroy(mid[0]);
+  cudaEventDestroy(mid[1]);
   return VP8GPU_OK;
 }
 

@@ -57,6 +57,8 @@ class Engine {
   struct Resident;
   int resident_upload(const HostJob* jobs, int n, Resident** out);
   int resident_run(int lane, Resident* r, float* ms);
+  int resident_run_many(int lane, Resident* const* rs, int n, float* total_ms);
+  int resident_run_timed(int lane, Resident* r, float ms[3]);
   void resident_free(Resident* r);
 
   int sync_all();
@@ -87,7 +89,7 @@ class Engine {
   int touch(Frame& f, int slot);                     // record "slot used this frame"
   int wait_for(Frame& f, int slot, cudaStream_t s);  // make stream s wait for other users
   int build_and_launch(int lane, const DevJob* d_jobs, int* d_sync, int n, bool any_inter, bool any_intra,
-                       bool any_lf);
+                       bool any_lf, cudaEvent_t* between = nullptr);
   int count_jobs(const HostJob& j, uint32_t* n_intra, uint32_t* n_inter, uint32_t* n_filtered) const;
 
   int device_ = 0, width_ = 0, height_ = 0;

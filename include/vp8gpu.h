@@ -188,6 +188,13 @@ typedef struct vp8gpu_resident_batch vp8gpu_resident_batch;
 int vp8gpu_batch_upload(vp8gpu_ctx* ctx, const vp8gpu_job* jobs, int n, vp8gpu_resident_batch** out);
 int vp8gpu_batch_run(vp8gpu_ctx* ctx, int lane, vp8gpu_resident_batch* b, float* kernel_ms);
 void vp8gpu_batch_free(vp8gpu_ctx* ctx, vp8gpu_resident_batch* b);
+/* Run n resident batches back to back on one lane (e.g. the 30 frame positions of a set of
+ * GOPs) without host synchronisation in between; *total_ms = device time from the first launch
+ * to the last kernel's end (CUDA events on the launching stream). */
+int vp8gpu_batches_run(vp8gpu_ctx* ctx, int lane, vp8gpu_resident_batch* const* batches, int n, float* total_ms);
+/* Run one resident batch with a CUDA event between the kernels:
+ * kernel_ms[0..2] = k_inter, k_intra, k_loopfilter device time (0 for a kernel that did not run). */
+int vp8gpu_batch_run_timed(vp8gpu_ctx* ctx, int lane, vp8gpu_resident_batch* b, float kernel_ms[3]);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 uint64_t vp8gpu_launch_count(const vp8gpu_ctx* ctx);
 

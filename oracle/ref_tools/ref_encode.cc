@@ -1,0 +1,92 @@
+/* ref_encode -- TEST INFRASTRUCTURE. Synthesises a seeded YUV420 clip and encodes it to VP8/IVF
+ * with the UNMODIFIED reference encoder (Encoder::encode_with_quantizer, encoder/encoder.cc:559),
+ * because no >=1080p VP8 material and no external encoder exist in this image.
+ * A new Encoder per GOP makes every GOP start with a key frame.
+ *
+ * usage: ref_encode OUT.ivf WIDTH HEIGHT FRAMES GOP QINDEX [SEED] [KIND]
+ *   KIND 0: smooth moving sinusoid + noise ("easy");  1: translating random-texture tiles ("hard");
+ *        2: translating softly textured tiles, light noise ("medium", broadcast-like bitrate)
+ */
+#include <cmath>
+#include <cstdio>
+#include <iostream>
+#include <random>
+#include <vector>
+
+#include "encoder.hh"
+#include "ivf_writer.hh"
+
+using namespace std;
+
+static void synth(MutableRasterHandle& h, int w, int hgt, int t, int seed, int kind) {
+  VP8Raster& r = h.get();
+  const int W = r.width(), H = r.height();
+  mt19937 rng(seed + t);
+  uniform_int_distribution<int> noise(kind == 2 ? -1 : -3, kind == 2 ? 1 : 3);
+  static vector<uint8_t> tex;
+  if (kind >= 1 && tex.empty()) {
+    const int rad = kind == 2 ? 9 : 3;
+    mt19937 trng(seed * 7919 + 1);
+    tex.resize(512 * 512);
+    /* low-pass random texture so that sub-pel motion is meaningful */
+    vector<int> raw(512 * 512);
+    for (auto& v : raw) v = trng() & 255;
+    for (int y = 0; y < 512; y++)
+      for (int x = 0; x < 512; x++) {
+        int s = 0;
+        for (int dy = 0; dy < rad; dy++)
+          for (int dx = 0; dx < rad; dx++) s += raw[((y + dy) & 511) * 512 + ((x + dx) & 511)];
+        s /= rad * rad;
+        if (kind == 2) s = 128 + (s - 128) * 4; /* restore contrast lost to the blur */
+        tex[y * 512 + x] = s < 0 ? 0 : (s > 255 ? 255 : s);
+      }
+  }
+  for (int y = 0; y < H; y++) {
+    const int yy = y < hgt ? y : hgt - 1;
+    for (int x = 0; x < W; x++) {
+      const int xx = x < w ? x : w - 1; /* edge-extend like yuv4mpeg.cc:231-271 */
+      int v;
+      if (kind == 0) {
+        v = 128 + (int)lround(60.0 * sin(0.02 * (xx + 3 * t)) * cos(0.015 * (yy + 2 * t)));
+      } else {
+        const int tile = ((xx >> 6) + (yy >> 6)) & 3;
+        const double vx = (tile & 1 ? 3.25 : -3.25), vy = (tile & 2 ? 1.75 : -1.75);
+        const int sx = (int)floor(xx + vx * t), sy = (int)floor(yy + vy * t);
+        v = tex[(sy & 511) * 512 + (sx & 511)];
+      }
+      if (x < w && y < hgt) v += noise(rng);
+      r.Y().at(x, y) = v < 0 ? 0 : (v > 255 ? 255 : v);
+    }
+  }
+  for (int y = 0; y < H / 2; y++)
+    for (int x = 0; x < W / 2; x++) {
+      const int xx = min(x, (w + 1) / 2 - 1), yy = min(y, (hgt + 1) / 2 - 1);
+      r.U().at(x, y) = 128 + (int)lround(30.0 * sin(0.01 * (xx + t)));
+      r.V().at(x, y) = 128 + (int)lround(30.0 * cos(0.012 * (yy - t)));
+    }
+}
+
+int main(int argc, char** argv) {
+  try {
+    if (argc < 7) { cerr << "usage: ref_encode OUT.ivf W H FRAMES GOP QINDEX [SEED] [KIND]\n"; return 2; }
+    const int w = atoi(argv[2]), h = atoi(argv[3]), frames = atoi(argv[4]), gop = atoi(argv[5]), qi = atoi(argv[6]);
+    const int seed = argc > 7 ? atoi(argv[7]) : 1234, kind = argc > 8 ? atoi(argv[8]) : 0;
+    IVFWriter out(argv[1], "VP80", w, h, 30, 1);
+    Optional<Encoder> enc;
+    size_t total = 0;
+    for (int t = 0; t < frames; t++) {
+      if (t % gop == 0) { enc.clear(); enc.initialize(w, h, false, REALTIME_QUALITY); }
+      MutableRasterHandle raster(w, h);
+      synth(raster, w, h, t, seed, kind);
+      const vector<uint8_t> f = enc.get().encode_with_quantizer(raster.get(), qi);
+      out.append_frame(Chunk(&f.at(0), f.size()));
+      total += f.size();
+      cerr << "frame " << t << " " << f.size() << " bytes\n";
+    }
+    cerr << "total " << total << " bytes\n";
+  } catch (const exception& e) {
+    cerr << "ref_encode: " << e.what() << "\n";
+    return 1;
+  }
+  return 0;
+}
