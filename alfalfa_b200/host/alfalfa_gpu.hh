@@ -1,0 +1,194 @@
+// alfalfa_gpu.hh -- C++ host-side mirror of the reference's decoder interface on top of the C ABI
+// (include/vp8gpu.h).  Same class and method names, argument meaning and error behaviour as
+// /root/reference/src/decoder/decoder.hh:123-300 and raster_handle.hh, so that callers such as
+// FramePlayer::decode (player.cc:60), xc-dump, xc-enc or salsify-receiver keep compiling when
+// the include is switched.  Header-only; link with -lvp8gpu.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/vp8gpu.h"
+
+namespace alfalfa_gpu {
+
+// util/exception.hh:76-98
+class Invalid : public std::runtime_error { public: using std::runtime_error::runtime_error; };
+class Unsupported : public std::runtime_error { public: using std::runtime_error::runtime_error; };
+class LogicError : public std::logic_error { public: using std::logic_error::logic_error; };
+class DeviceError : public std::runtime_error { public: using std::runtime_error::runtime_error; };
+
+inline void check(int rc, vp8gpu_ctx* ctx, const char* what) {
+  if (rc == VP8GPU_OK) return;
+  const std::string msg = std::string(what) + ": " + (ctx ? vp8gpu_last_error(ctx) : "");
+  switch (rc) {
+    case VP8GPU_ERR_INVALID: throw Invalid(msg);
+    case VP8GPU_ERR_UNSUPPORTED: throw Unsupported(msg);
+    case VP8GPU_ERR_LOGIC: throw LogicError(msg);
+    default: throw DeviceError(msg);
+  }
+}
+
+// util/chunk.hh:38: a (pointer, length) view of compressed bytes
+struct Chunk {
+  const uint8_t* buffer;
+  uint64_t size;
+  Chunk(const uint8_t* b, uint64_t n) : buffer(b), size(n) {}
+  explicit Chunk(const std::vector<uint8_t>& v) : buffer(v.data()), size(v.size()) {}
+};
+
+// one context per (device, frame size); shared by every Decoder of that size
+class Context {
+  std::shared_ptr<vp8gpu_ctx> h_;
+ public:
+  Context(int device, uint16_t width, uint16_t height, int max_frames = 0) {
+    vp8gpu_ctx* c = nullptr;
+    check(vp8gpu_ctx_create(device, width, height, max_frames, &c), nullptr, "vp8gpu_ctx_create");
+    h_.reset(c, vp8gpu_ctx_destroy);
+  }
+  vp8gpu_ctx* get() const { return h_.get(); }
+  void sync() const { check(vp8gpu_ctx_sync(get()), get(), "sync"); }
+};
+
+// RasterHandle (raster_handle.hh:95-123): shared, immutable, device resident
+class RasterHandle {
+  struct Rep {
+    Context ctx;
+    vp8gpu_frame_id id;
+    Rep(const Context& c, vp8gpu_frame_id i) : ctx(c), id(i) {}
+    ~Rep() { vp8gpu_frame_release(ctx.get(), id); }
+  };
+  std::shared_ptr<const Rep> rep_;
+ public:
+  RasterHandle() = default;
+  RasterHandle(const Context& c, vp8gpu_frame_id owned_id) : rep_(std::make_shared<Rep>(c, owned_id)) {}
+  vp8gpu_frame_id id() const { return rep_->id; }
+  bool initialized() const { return static_cast<bool>(rep_); }
+  bool operator==(const RasterHandle& o) const { return rep_ == o.rep_; }
+  // BaseRaster::dump (util/raster.cc:85-114): display rectangle, planar Y,U,V; blocks until decoded
+  std::vector<uint8_t> dump(uint16_t width, uint16_t height) const {
+    std::vector<uint8_t> out(size_t(width) * height + 2 * size_t((width + 1) / 2) * ((height + 1) / 2));
+    check(vp8gpu_frame_download_display(rep_->ctx.get(), rep_->id, out.data(), out.size()), rep_->ctx.get(), "dump");
+    return out;
+  }
+};
+
+// DecoderState (decoder.hh:190-225) as a value
+class DecoderState {
+  std::shared_ptr<vp8gpu_state> h_;
+ public:
+  DecoderState(unsigned width, unsigned height) {
+    vp8gpu_state* s = nullptr;
+    check(vp8gpu_state_create(width, height, &s), nullptr, "state_create");
+    h_.reset(s, vp8gpu_state_destroy);
+  }
+  explicit DecoderState(const vp8gpu_state* borrowed) {
+    vp8gpu_state* s = nullptr;
+    check(vp8gpu_state_clone(borrowed, &s), nullptr, "state_clone");
+    h_.reset(s, vp8gpu_state_destroy);
+  }
+  const vp8gpu_state* get() const { return h_.get(); }
+  bool operator==(const DecoderState& o) const { return vp8gpu_state_equal(get(), o.get()); }
+  bool operator!=(const DecoderState& o) const { return !(*this == o); }
+  size_t hash() const { return vp8gpu_state_hash(get()); }
+};
+
+// References (decoder.hh:123-149)
+struct References {
+  RasterHandle last, golden, alternative;
+};
+
+// KeyFrame / InterFrame (frame.hh:126-127) in flat form
+class ParsedFrame {
+  std::shared_ptr<vp8gpu_parsed> h_;
+ public:
+  ParsedFrame() {
+    vp8gpu_parsed* p = nullptr;
+    check(vp8gpu_parsed_create(&p), nullptr, "parsed_create");
+    h_.reset(p, vp8gpu_parsed_destroy);
+  }
+  vp8gpu_parsed* get() const { return h_.get(); }
+  bool show_frame() const { return vp8gpu_parsed_desc(get())->show_frame; }
+  bool key_frame() const { return vp8gpu_parsed_desc(get())->key_frame; }
+};
+
+// Decoder (decoder.hh:244-300).  Copying is O(1) in pixels and shares the reference rasters.
+class Decoder {
+  Context ctx_;
+  uint16_t width_, height_;
+  vp8gpu_decoder* h_ = nullptr;
+ public:
+  Decoder(const Context& ctx, uint16_t width, uint16_t height) : ctx_(ctx), width_(width), height_(height) {
+    check(vp8gpu_decoder_create(ctx_.get(), &h_), ctx_.get(), "decoder_create");
+  }
+  Decoder(const Context& ctx, const DecoderState& state, const References& refs, uint16_t width, uint16_t height)
+      : ctx_(ctx), width_(width), height_(height) {
+    const vp8gpu_frame_id ids[3] = {refs.last.id(), refs.golden.id(), refs.alternative.id()};
+    check(vp8gpu_decoder_create_from(ctx_.get(), state.get(), ids, &h_), ctx_.get(), "decoder_create_from");
+  }
+  Decoder(const Decoder& o) : ctx_(o.ctx_), width_(o.width_), height_(o.height_) {
+    check(vp8gpu_decoder_clone(o.h_, &h_), ctx_.get(), "decoder_clone");
+  }
+  Decoder& operator=(const Decoder& o) {
+    if (this != &o) {
+      Decoder tmp(o);
+      std::swap(h_, tmp.h_);
+    }
+    return *this;
+  }
+  ~Decoder() { vp8gpu_decoder_destroy(h_); }
+
+  uint16_t get_width() const { return width_; }
+  uint16_t get_height() const { return height_; }
+
+  // parse_frame<KeyFrame|InterFrame>( decompress_frame( chunk ) ) (decoder.cc:83-98)
+  ParsedFrame parse_frame(const Chunk& compressed_frame) {
+    ParsedFrame p;
+    check(vp8gpu_parse_frame(vp8gpu_decoder_state(h_), compressed_frame.buffer, compressed_frame.size, p.get()),
+          ctx_.get(), "parse_frame");
+    return p;
+  }
+  // decode_frame (decoder.cc:101-118)
+  std::pair<bool, RasterHandle> decode_frame(const ParsedFrame& frame) {
+    int shown = 0;
+    vp8gpu_frame_id id = -1;
+    check(vp8gpu_decoder_decode_parsed(h_, frame.get(), &shown, &id), ctx_.get(), "decode_frame");
+    return {shown != 0, RasterHandle(ctx_, id)};
+  }
+  // get_frame_output (decoder.cc:125-135)
+  std::pair<bool, RasterHandle> get_frame_output(const Chunk& compressed_frame) {
+    int shown = 0;
+    vp8gpu_frame_id id = -1;
+    check(vp8gpu_decoder_decode(h_, compressed_frame.buffer, compressed_frame.size, &shown, &id), ctx_.get(),
+          "get_frame_output");
+    return {shown != 0, RasterHandle(ctx_, id)};
+  }
+  // parse_and_decode_frame (decoder.cc:137-141): empty handle for hidden frames
+  RasterHandle parse_and_decode_frame(const Chunk& compressed_frame) {
+    auto out = get_frame_output(compressed_frame);
+    return out.first ? out.second : RasterHandle();
+  }
+  DecoderState get_state() const { return DecoderState(vp8gpu_decoder_state(h_)); }
+  References get_references() const {
+    vp8gpu_frame_id ids[3];
+    vp8gpu_decoder_references(h_, ids);
+    References r;
+    RasterHandle* slots[3] = {&r.last, &r.golden, &r.alternative};
+    for (int i = 0; i < 3; i++) {
+      check(vp8gpu_frame_retain(ctx_.get(), ids[i]), ctx_.get(), "retain");
+      *slots[i] = RasterHandle(ctx_, ids[i]);
+    }
+    return r;
+  }
+  bool operator==(const Decoder& o) const {
+    int eq = 0;
+    check(vp8gpu_decoder_equal(h_, o.h_, &eq), ctx_.get(), "decoder_equal");
+    return eq != 0;
+  }
+  bool operator!=(const Decoder& o) const { return !(*this == o); }
+};
+
+}  // namespace alfalfa_gpu

@@ -42,3 +42,13 @@ def test_no_device_fails_loudly_not_silently():
     from alfalfa_b200 import Context, CudaError
     with pytest.raises(CudaError):
         Context(320, 240)
+
+
+def test_cxx_host_mirror_compiles_and_links():
+    """alfalfa_b200/host/alfalfa_gpu.hh (Decoder / DecoderState / References / RasterHandle mirror)"""
+    import subprocess
+    import tempfile
+    src = os.path.join(ROOT, "tests", "host_mirror_compile.cc")
+    with tempfile.TemporaryDirectory() as d:
+        subprocess.check_call(["g++", "-std=c++14", "-Wall", "-Wextra", "-shared", "-fPIC", src, "-o",
+                               os.path.join(d, "m.so"), "-L" + os.path.join(ROOT, "alfalfa_b200"), "-l:libvp8gpu.so"])
