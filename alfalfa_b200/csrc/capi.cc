@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -20,10 +21,15 @@ using vp8::HostJob;
 using vp8::ParsedFrame;
 using vp8::State;
 
+struct vp8gpu_parsed;
 struct vp8gpu_ctx {
   Engine* engine = nullptr;
   std::string create_error;
   std::atomic<int> next_lane{0};
+  // pinned parsed-frame buffers are expensive to create (cudaHostAlloc serialises on the driver):
+  // decoders borrow them from this pool and hand them back when they are destroyed
+  std::mutex pool_mu;
+  std::vector<vp8gpu_parsed*> pinned_pool;
 };
 struct vp8gpu_state {
   State s;
@@ -84,6 +90,7 @@ int vp8gpu_ctx_create(int device, int width, int height, int max_frames, vp8gpu_
 }
 void vp8gpu_ctx_destroy(vp8gpu_ctx* ctx) {
   if (!ctx) return;
+  for (vp8gpu_parsed* p : ctx->pinned_pool) vp8gpu_parsed_destroy(p);
   delete ctx->engine;
   delete ctx;
 }
@@ -239,7 +246,7 @@ struct vp8gpu_decoder {
   int refs[3] = {-1, -1, -1};  // last, golden, alternative; each holds one reference count
   // ring of pinned parsed-frame buffers so the host can parse frame N+1 while the DMA engine
   // is still reading frame N's records
-  std::unique_ptr<vp8gpu_parsed> ring[vp8::kStagingDepth];
+  vp8gpu_parsed* ring[vp8::kStagingDepth] = {};
   int ring_next = 0;
   vp8gpu_decoder(vp8gpu_ctx* c, int w, int h) : ctx(c), state(w, h) {}
   vp8gpu_decoder(vp8gpu_ctx* c, const State& s) : ctx(c), state(s) {}
@@ -256,17 +263,32 @@ void set_ref(Engine* e, int* slot, int id) {
 }
 
 vp8gpu_parsed* next_ring_slot(vp8gpu_decoder* d) {
-  std::unique_ptr<vp8gpu_parsed>& p = d->ring[d->ring_next];
+  vp8gpu_parsed*& p = d->ring[d->ring_next];
   d->ring_next = (d->ring_next + 1) % vp8::kStagingDepth;
   if (!p) {
-    p.reset(new vp8gpu_parsed(kPinned));
-    cudaEventCreateWithFlags(&p->consumed, cudaEventDisableTiming);
+    {
+      std::lock_guard<std::mutex> lk(d->ctx->pool_mu);
+      if (!d->ctx->pinned_pool.empty()) {
+        p = d->ctx->pinned_pool.back();
+        d->ctx->pinned_pool.pop_back();
+      }
+    }
+    if (!p) {
+      p = new vp8gpu_parsed(kPinned);
+      cudaEventCreateWithFlags(&p->consumed, cudaEventDisableTiming);
+      // size the token buffer generously up front: growing pinned memory means a new cudaHostAlloc
+      const vp8::Geom& g = d->ctx->engine->geom();
+      const size_t n_mbs = (size_t)g.mb_cols * g.mb_rows;
+      p->f.mbs.reserve(n_mbs, 0);
+      p->f.tokens.reserve(n_mbs * 32 + 1024, 0);
+      p->f.split.reserve(256, 0);
+    }
   }
   if (p->busy) {
     cudaEventSynchronize(p->consumed);
     p->busy = false;
   }
-  return p.get();
+  return p;
 }
 
 // Decoder::decode_frame (decoder.cc:101-118): decode + loopfilter into a fresh raster, then
@@ -365,14 +387,17 @@ void vp8gpu_decoder_destroy(vp8gpu_decoder* d) {
   if (!d) return;
   Engine* e = d->ctx->engine;
   for (auto& p : d->ring)
-    if (p && p->busy) cudaEventSynchronize(p->consumed);
+    if (p && p->busy) {
+      cudaEventSynchronize(p->consumed);
+      p->busy = false;
+    }
   for (int i = 0; i < 3; i++)
     if (d->refs[i] >= 0) e->frame_release(d->refs[i]);
-  for (auto& p : d->ring)
-    if (p) {
-      if (p->consumed) cudaEventDestroy(p->consumed);
-      p->consumed = nullptr;
-    }
+  {
+    std::lock_guard<std::mutex> lk(d->ctx->pool_mu);
+    for (auto& p : d->ring)
+      if (p) d->ctx->pinned_pool.push_back(p);
+  }
   delete d;
 }
 

@@ -15,7 +15,8 @@
 //
 // Memory-model notes for the wavefront kernels: pixels written by another warp are read with
 // ld.global.cg (L2, never a stale L1 line); a finished macroblock is published with
-// __threadfence() by every lane, __syncwarp(), then one st.release-like volatile store.
+// __syncwarp() (orders every lane's stores before lane 0) and one st.release.gpu by lane 0; the
+// consumer polls with ld.acquire.gpu on lane 0 and __syncwarp()s before the other lanes read.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -284,14 +285,12 @@ __device__ __forceinline__ void st_progress(int* p, int v) {
 // wait until the row above has finished every macroblock left of `need`
 __device__ __forceinline__ void wait_row(const int* progress_above, int need, int lane) {
   if (lane == 0) {
-    while (ld_progress(progress_above) < need) __nanosleep(32);
+    while (ld_progress(progress_above) < need) __nanosleep(20);
   }
-  __syncwarp();
-  __threadfence();
+  __syncwarp();  // the other lanes' later loads are ordered after lane 0's acquire through this barrier
 }
 __device__ __forceinline__ void publish_row(int* progress, int value, int lane) {
-  __threadfence();
-  __syncwarp();
+  __syncwarp();  // every lane's stores happen-before lane 0's release store (cumulative at gpu scope)
   if (lane == 0) st_progress(progress, value);
 }
 __device__ __forceinline__ uint8_t ldcg_u8(const uint8_t* p) { return __ldcg(p); }
@@ -348,6 +347,9 @@ __global__ void __launch_bounds__(32) k_intra(const DevJob* __restrict__ jobs, i
 
   while (col >= 0) {
     const MbFields f = load_mb(row_mbs + col);
+    // the residual only depends on this macroblock's tokens: build it before waiting on the row above
+    const bool has_res = f.tok_cnt != 0;
+    if (has_res) build_residuals(J, f, coef, lane);
     if (row > 0) wait_row(progress - 1, min(col + 2, cols), lane);
 
     // ---- edges (prediction.cc:99-167), read through L2 ----
@@ -380,23 +382,24 @@ __global__ void __launch_bounds__(32) k_intra(const DevJob* __restrict__ jobs, i
     }
     __syncwarp();
 
-    const bool has_res = f.tok_cnt != 0;
-    if (has_res) build_residuals(J, f, coef, lane);
-
     // ---- chroma 8x8 prediction (prediction.cc:435-449): 128 pixels, 4 per lane ----
+    int cdc[2] = {128, 128};
+    if (f.uv_mode == VP8GPU_DC_PRED) {
+#pragma unroll
+      for (int plane = 0; plane < 2; plane++) {
+        int s = 0, n = 0;
+        if (row > 0) { for (int k = 0; k < 8; k++) s += aboveC[plane][1 + k]; n += 8; }
+        if (col > 0) { for (int k = 0; k < 8; k++) s += leftC[plane][k]; n += 8; }
+        cdc[plane] = n == 16 ? (s + 8) >> 4 : (n == 8 ? (s + 4) >> 3 : 128);
+      }
+    }
     for (int i = lane; i < 128; i += 32) {
       const int plane = i >> 6, y = (i >> 3) & 7, x = i & 7;
       const uint8_t* A = aboveC[plane] + 1;
       const uint8_t* L = leftC[plane];
       int v;
       switch (f.uv_mode) {
-        case VP8GPU_DC_PRED: {
-          int s = 0, n = 0;
-          if (row > 0) { for (int k = 0; k < 8; k++) s += A[k]; n += 8; }
-          if (col > 0) { for (int k = 0; k < 8; k++) s += L[k]; n += 8; }
-          v = n == 16 ? (s + 8) >> 4 : (n == 8 ? (s + 4) >> 3 : 128);
-          break;
-        }
+        case VP8GPU_DC_PRED: v = plane ? cdc[1] : cdc[0]; break;
         case VP8GPU_V_PRED: v = A[x]; break;
         case VP8GPU_H_PRED: v = L[y]; break;
         default: v = vp8m::clamp255(L[y] + A[x] - A[-1]);
@@ -490,28 +493,32 @@ __global__ void __launch_bounds__(32) k_intra(const DevJob* __restrict__ jobs, i
 // ================================================================================================
 // k_loopfilter
 // ================================================================================================
-// One edge position: 8 pixels p3..q3 spaced `step` bytes apart around `q0`.
-__device__ __forceinline__ void filter_position(uint8_t* q0p, int step, const vp8m::LfParams& lp, bool mb_edge) {
-  int p3 = q0p[-4 * step], p2 = q0p[-3 * step], p1 = q0p[-2 * step], p0 = q0p[-step];
-  int q0 = q0p[0], q1 = q0p[step], q2 = q0p[2 * step], q3 = q0p[3 * step];
-  const int mask = vp8m::lf_mask(lp.interior, mb_edge ? lp.mb_edge : lp.sub_edge, p3, p2, p1, p0, q0, q1, q2, q3);
-  if (!mask) return;  // filters are the identity when the mask is 0
-  const int hev = vp8m::lf_hev(lp.hev, p1, p0, q0, q1);
-  if (mb_edge) {
-    vp8m::lf_mbedge(mask, hev, p2, p1, p0, q0, q1, q2);
-    q0p[-3 * step] = (uint8_t)p2;
-    q0p[2 * step] = (uint8_t)q2;
-  } else {
-    vp8m::lf_inner(mask, hev, p1, p0, q0, q1);
+// One line of pixels across edges (a row for vertical edges, a column for horizontal ones), held in
+// registers: px[0..3] = the 4 pixels before the macroblock, px[4..] = the macroblock's own.
+// Edge order along the line = the reference's order for this direction (loopfilter.cc:133-154):
+// macroblock edge (position 4) first, then the sub-block edges at 8, 12, 16 (chroma: 8 only).
+__device__ __forceinline__ void filter_edge_at(int* px, int q, const vp8m::LfParams& lp, bool mb_edge) {
+  const int mask = vp8m::lf_mask(lp.interior, mb_edge ? lp.mb_edge : lp.sub_edge, px[q - 4], px[q - 3], px[q - 2],
+                                 px[q - 1], px[q], px[q + 1], px[q + 2], px[q + 3]);
+  if (!mask) return;  // both filters are the identity when the mask is 0
+  const int hev = vp8m::lf_hev(lp.hev, px[q - 2], px[q - 1], px[q], px[q + 1]);
+  if (mb_edge) vp8m::lf_mbedge(mask, hev, px[q - 3], px[q - 2], px[q - 1], px[q], px[q + 1], px[q + 2]);
+  else vp8m::lf_inner(mask, hev, px[q - 2], px[q - 1], px[q], px[q + 1]);
+}
+__device__ __forceinline__ void filter_line(int* px, bool luma, bool do_mb_edge, bool do_inner,
+                                            const vp8m::LfParams& lp) {
+  if (do_mb_edge) filter_edge_at(px, 4, lp, true);
+  if (do_inner) {
+    filter_edge_at(px, 8, lp, false);
+    if (luma) {
+      filter_edge_at(px, 12, lp, false);
+      filter_edge_at(px, 16, lp, false);
+    }
   }
-  q0p[-2 * step] = (uint8_t)p1;
-  q0p[-step] = (uint8_t)p0;
-  q0p[0] = (uint8_t)q0;
-  q0p[step] = (uint8_t)q1;
 }
 
 __global__ void __launch_bounds__(32) k_loopfilter(const DevJob* __restrict__ jobs, int njobs, Geom g, int* ticket) {
-  // region = the macroblock plus 4 pixels above and to the left
+  // region = the macroblock plus 4 pixels above and to the left: luma 20x20, chroma 12x12
   constexpr int YS = 20, CSZ = 12;
   __shared__ __align__(16) uint8_t ry[20 * YS];
   __shared__ __align__(16) uint8_t rc[2][12 * CSZ];
@@ -539,85 +546,144 @@ __global__ void __launch_bounds__(32) k_loopfilter(const DevJob* __restrict__ jo
   publish_row(progress, col < 0 ? cols : col, lane);
 
   uint8_t* const Y = J.out;
-  // lane roles on an edge: 0-15 luma positions, 16-23 U, 24-31 V
-  uint8_t* plane_base;
-  int stride, idx;
-  if (lane < 16) plane_base = ry, stride = YS, idx = lane;
-  else if (lane < 24) plane_base = rc[0], stride = CSZ, idx = lane - 16;
-  else plane_base = rc[1], stride = CSZ, idx = lane - 24;
-  const bool luma = lane < 16;
+  uint8_t* const U = J.out + g.u_off;
+  uint8_t* const V = J.out + g.v_off;
+  const int y_lo = row > 0 ? 0 : 4;  // first region row that exists in the frame
+
+  // per-lane addressing of the three transfer patterns (all in 32-bit words)
+  //  own block (3 words per lane): words 0-63 luma 16 rows x 4, 64-95 chroma 2 planes x 8 rows x 2
+  //  top rows  (1 word per lane):  lanes 0-15 luma 4 rows x 4, lanes 16-31 chroma 2 x 4 rows x 2
+  auto own_ptr = [&](int k, int c, const uint8_t*& gp, uint8_t*& sp) {
+    const int w = lane + 32 * k;
+    if (w < 64) {
+      const int r = w >> 2, wx = w & 3;
+      gp = Y + (size_t)(16 * row + r) * g.y_pitch + 16 * c + 4 * wx;
+      sp = ry + (4 + r) * YS + 4 + 4 * wx;
+    } else {
+      const int cw = w - 64, plane = cw >> 4, k2 = cw & 15, r = k2 >> 1, wx = k2 & 1;
+      gp = (plane ? V : U) + (size_t)(8 * row + r) * g.c_pitch + 8 * c + 4 * wx;
+      sp = rc[plane] + (4 + r) * CSZ + 4 + 4 * wx;
+    }
+  };
+  uint32_t own[3];
+  auto prefetch_own = [&](int c) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const uint8_t* gp;
+      uint8_t* sp;
+      own_ptr(k, c, gp, sp);
+      own[k] = __ldcg(reinterpret_cast<const uint32_t*>(gp));
+    }
+  };
+  if (col >= 0) prefetch_own(col);
+  int prev = -2;  // last column this warp filtered (its right 4 columns are still in shared memory)
 
   while (col >= 0) {
     const MbFields f = load_mb(row_mbs + col);
+    const bool have_left = prev == col - 1;
     if (row > 0) wait_row(progress - 1, min(col + 2, cols), lane);
 
-    // ---- load the region as 32-bit words through L2 ----
-    const int x_lo = col > 0 ? 0 : 1;  // first word column that exists
-    const int y_lo = row > 0 ? 0 : 4;
-    for (int i = lane; i < 100; i += 32) {
-      const int r = i / 5, wx = i - r * 5;
-      if (r >= y_lo && wx >= x_lo) {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(Y + (size_t)(16 * row - 4 + r) * g.y_pitch + 16 * col - 4 + 4 * wx);
-        *reinterpret_cast<uint32_t*>(ry + r * YS + 4 * wx) = __ldcg(src);
+    // ---- top 4 rows (final output of the row above), through L2: one word per lane ----
+    uint32_t top = 0;
+    if (row > 0) {
+      if (lane < 16) {
+        const int r = lane >> 2, wx = lane & 3;
+        top = __ldcg(reinterpret_cast<const uint32_t*>(Y + (size_t)(16 * row - 4 + r) * g.y_pitch + 16 * col + 4 * wx));
+      } else {
+        const int cw = lane - 16, plane = cw >> 3, k2 = cw & 7, r = k2 >> 1, wx = k2 & 1;
+        top = __ldcg(reinterpret_cast<const uint32_t*>((plane ? V : U) + (size_t)(8 * row - 4 + r) * g.c_pitch + 8 * col + 4 * wx));
       }
     }
-    for (int i = lane; i < 72; i += 32) {
-      const int plane = i / 36, k = i - plane * 36, r = k / 3, wx = k - r * 3;
-      if (r >= y_lo && wx >= x_lo) {
-        const uint8_t* P = Y + (plane ? g.v_off : g.u_off);
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(P + (size_t)(8 * row - 4 + r) * g.c_pitch + 8 * col - 4 + 4 * wx);
-        *reinterpret_cast<uint32_t*>(rc[plane] + r * CSZ + 4 * wx) = __ldcg(src);
+    // ---- left 4 columns: slide them over from the previous macroblock, or fetch them ----
+    uint32_t left0 = 0, left1 = 0;
+    if (col > 0) {
+      if (have_left) {
+        if (lane < 20) left0 = *reinterpret_cast<const uint32_t*>(ry + lane * YS + 16);
+        if (lane < 24) left1 = *reinterpret_cast<const uint32_t*>(rc[lane / 12] + (lane % 12) * CSZ + 8);
+      } else {
+        if (lane < 20 && lane >= y_lo)
+          left0 = __ldcg(reinterpret_cast<const uint32_t*>(Y + (size_t)(16 * row - 4 + lane) * g.y_pitch + 16 * col - 4));
+        if (lane < 24 && (lane % 12) >= y_lo)
+          left1 = __ldcg(reinterpret_cast<const uint32_t*>((lane / 12 ? V : U) + (size_t)(8 * row - 4 + lane % 12) * g.c_pitch + 8 * col - 4));
       }
+    }
+    __syncwarp();  // everybody has read the old region before it is overwritten
+    if (col > 0) {
+      if (lane < 20) *reinterpret_cast<uint32_t*>(ry + lane * YS) = left0;
+      if (lane < 24) *reinterpret_cast<uint32_t*>(rc[lane / 12] + (lane % 12) * CSZ) = left1;
+    }
+    if (row > 0) {
+      if (lane < 16) *reinterpret_cast<uint32_t*>(ry + (lane >> 2) * YS + 4 + 4 * (lane & 3)) = top;
+      else {
+        const int cw = lane - 16, plane = cw >> 3, k2 = cw & 7;
+        *reinterpret_cast<uint32_t*>(rc[plane] + (k2 >> 1) * CSZ + 4 + 4 * (k2 & 1)) = top;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const uint8_t* gp;
+      uint8_t* sp;
+      own_ptr(k, col, gp, sp);
+      *reinterpret_cast<uint32_t*>(sp) = own[k];
     }
     __syncwarp();
+    const int next = next_marked(my_word, col + 1, nwords);
+    if (next >= 0) prefetch_own(next);  // in flight while this macroblock is filtered
 
     const vp8m::LfParams lp = vp8m::lf_params(f.lf_level, J.sharpness, J.key_frame);
-    const bool skip_inner = (f.flags & VP8GPU_MB_HAS_Y2) && f.tok_cnt == 0;  // macroblock.cc:608
-    uint8_t* const origin = plane_base + 4 * stride + 4;  // pixel (0,0) of the macroblock
+    const bool do_inner = !((f.flags & VP8GPU_MB_HAS_Y2) && f.tok_cnt == 0);  // macroblock.cc:608
+    // lane roles on an edge: 0-15 luma positions, 16-23 U, 24-31 V
+    const bool luma = lane < 16;
+    uint8_t* const plane_base = luma ? ry : rc[(lane - 16) >> 3];
+    const int stride = luma ? YS : CSZ, idx = luma ? lane : (lane & 7), len = luma ? 20 : 12;
+    int px[20];
 
-    // 1: left macroblock edge
-    if (col > 0) filter_position(origin + idx * stride, 1, lp, true);
-    __syncwarp();
-    // 2: vertical sub-block edges (x = 4, 8, 12 luma; x = 4 chroma)
-    if (!skip_inner) {
-      filter_position(origin + idx * stride + 4, 1, lp, false);
-      __syncwarp();
-      if (luma) filter_position(origin + idx * stride + 8, 1, lp, false);
-      __syncwarp();
-      if (luma) filter_position(origin + idx * stride + 12, 1, lp, false);
-      __syncwarp();
+    // ---- vertical edges: one region row (4 + idx) per lane, in registers ----
+    {
+      const uint32_t* rw = reinterpret_cast<const uint32_t*>(plane_base + (4 + idx) * stride);
+#pragma unroll
+      for (int k = 0; k < 5; k++) {
+        const uint32_t v = (k < 3 || luma) ? rw[k] : 0u;
+        px[4 * k] = v & 0xFF, px[4 * k + 1] = (v >> 8) & 0xFF, px[4 * k + 2] = (v >> 16) & 0xFF, px[4 * k + 3] = v >> 24;
+      }
+      filter_line(px, luma, col > 0, do_inner, lp);
+      uint32_t* ww = reinterpret_cast<uint32_t*>(plane_base + (4 + idx) * stride);
+#pragma unroll
+      for (int k = 0; k < 5; k++)
+        if (k < 3 || luma) ww[k] = (uint32_t)px[4 * k] | ((uint32_t)px[4 * k + 1] << 8) | ((uint32_t)px[4 * k + 2] << 16) | ((uint32_t)px[4 * k + 3] << 24);
     }
-    // 3: top macroblock edge
-    if (row > 0) filter_position(origin + idx, stride, lp, true);
     __syncwarp();
-    // 4: horizontal sub-block edges
-    if (!skip_inner) {
-      filter_position(origin + 4 * stride + idx, stride, lp, false);
-      __syncwarp();
-      if (luma) filter_position(origin + 8 * stride + idx, stride, lp, false);
-      __syncwarp();
-      if (luma) filter_position(origin + 12 * stride + idx, stride, lp, false);
-      __syncwarp();
+    // ---- horizontal edges: one region column (4 + idx) per lane ----
+    {
+      uint8_t* cp = plane_base + 4 + idx;
+#pragma unroll
+      for (int k = 0; k < 20; k++) px[k] = k < len ? cp[k * stride] : 0;
+      filter_line(px, luma, row > 0, do_inner, lp);
+#pragma unroll
+      for (int k = 1; k < 19; k++)
+        if (k < len - 1) cp[k * stride] = (uint8_t)px[k];
     }
+    __syncwarp();
 
-    // ---- write the region back ----
-    for (int i = lane; i < 100; i += 32) {
-      const int r = i / 5, wx = i - r * 5;
-      if (r >= y_lo && wx >= x_lo) {
-        uint32_t* dst = reinterpret_cast<uint32_t*>(Y + (size_t)(16 * row - 4 + r) * g.y_pitch + 16 * col - 4 + 4 * wx);
-        *dst = *reinterpret_cast<const uint32_t*>(ry + r * YS + 4 * wx);
-      }
+    // ---- write back: region columns 0..15 (x -4..11); the last 4 columns travel with the next
+    //      macroblock unless this warp will not filter it ----
+    const int x_lo = col > 0 ? 0 : 1;
+    const bool flush_right = next != col + 1;
+    const int lw = flush_right ? 5 : 4, cw_n = flush_right ? 3 : 2;
+    for (int i = lane; i < 20 * lw; i += 32) {
+      const int r = i / lw, wx = i - r * lw;
+      if (r >= y_lo && wx >= x_lo)
+        *reinterpret_cast<uint32_t*>(Y + (size_t)(16 * row - 4 + r) * g.y_pitch + 16 * col - 4 + 4 * wx) =
+            *reinterpret_cast<const uint32_t*>(ry + r * YS + 4 * wx);
     }
-    for (int i = lane; i < 72; i += 32) {
-      const int plane = i / 36, k = i - plane * 36, r = k / 3, wx = k - r * 3;
-      if (r >= y_lo && wx >= x_lo) {
-        uint8_t* P = Y + (plane ? g.v_off : g.u_off);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(P + (size_t)(8 * row - 4 + r) * g.c_pitch + 8 * col - 4 + 4 * wx);
-        *dst = *reinterpret_cast<const uint32_t*>(rc[plane] + r * CSZ + 4 * wx);
-      }
+    for (int i = lane; i < 24 * cw_n; i += 32) {
+      const int plane = i / (12 * cw_n), k = i - plane * 12 * cw_n, r = k / cw_n, wx = k - r * cw_n;
+      if (r >= y_lo && wx >= x_lo)
+        *reinterpret_cast<uint32_t*>((plane ? V : U) + (size_t)(8 * row - 4 + r) * g.c_pitch + 8 * col - 4 + 4 * wx) =
+            *reinterpret_cast<const uint32_t*>(rc[plane] + r * CSZ + 4 * wx);
     }
-    const int next = next_marked(my_word, col + 1, nwords);
     publish_row(progress, next < 0 ? cols : next, lane);
+    prev = col;
     col = next;
   }
 }
