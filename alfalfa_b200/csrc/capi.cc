@@ -6,6 +6,8 @@
 #include <string.h>
 
 #include <atomic>
+#include <condition_variable>
+#include <deque>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -484,45 +486,203 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
   gop_start.push_back((uint32_t)items.size());
   const int n_gops = (int)gop_start.size() - 1;
   if (threads < 1) threads = 1;
-  if (threads > vp8::kMaxLanes) threads = vp8::kMaxLanes;
+  if (threads > 256) threads = 256;
   if (threads > n_gops) threads = n_gops > 0 ? n_gops : 1;
 
+  // Host workers only parse (CPU entropy front end) and keep the per-GOP codec state; a single
+  // dispatcher gathers whatever they have produced -- at most one frame per worker, because
+  // consecutive frames of a GOP depend on each other -- into ONE batched decode per round, so the
+  // device sees a few large launches instead of three small ones per frame, and the wavefront
+  // kernels get rows of many frames to hide their latency with.
+  constexpr int kSlots = 4;      // parsed frames a worker may have in flight
+  constexpr int kDispatchLanes = 4;
+  enum SlotState { kFree = 0, kQueued = 1 };
+  struct Pending {
+    vp8gpu_parsed* slot;
+    int refs[3];
+    int out;
+    int64_t out_off;
+    int* slot_state;
+  };
+  std::mutex mu;
+  std::condition_variable cv_workers, cv_dispatch;
+  std::vector<std::deque<Pending>> queues(threads);
+  int workers_running = threads;
   std::atomic<int> next_gop{0};
   std::atomic<int> first_error{VP8GPU_OK};
+  auto set_error = [&](int rc) {
+    int ok = VP8GPU_OK;
+    first_error.compare_exchange_strong(ok, rc);
+  };
+
   auto worker = [&](int tid) {
     cudaSetDevice(e->device());
-    vp8gpu_decoder* d = nullptr;
-    int rc = vp8gpu_decoder_create(ctx, &d);
-    if (rc != VP8GPU_OK) {
-      int ok = VP8GPU_OK;
-      first_error.compare_exchange_strong(ok, rc);
-      return;
-    }
-    d->lane = tid;  // one lane per worker
+    State state(w, h);
+    int refs[3] = {-1, -1, -1};
+    vp8gpu_parsed* slots[kSlots] = {};
+    int slot_state[kSlots] = {};
+    int next_slot = 0;
+    int rc = VP8GPU_OK;
     for (;;) {
       const int g = next_gop.fetch_add(1);
       if (g >= n_gops || first_error.load() != VP8GPU_OK) break;
-      for (uint32_t i = gop_start[g]; i < gop_start[g + 1]; i++) {
-        int shown = 0, id = -1;
-        rc = vp8gpu_decoder_decode(d, items[i].p, items[i].n, &shown, &id);
+      for (uint32_t i = gop_start[g]; i < gop_start[g + 1] && rc == VP8GPU_OK; i++) {
+        const int si = next_slot;
+        next_slot = (next_slot + 1) % kSlots;
+        if (!slots[si]) {
+          {
+            std::lock_guard<std::mutex> lk(ctx->pool_mu);
+            if (!ctx->pinned_pool.empty()) {
+              slots[si] = ctx->pinned_pool.back();
+              ctx->pinned_pool.pop_back();
+            }
+          }
+          if (!slots[si]) {
+            slots[si] = new vp8gpu_parsed(kPinned);
+            cudaEventCreateWithFlags(&slots[si]->consumed, cudaEventDisableTiming);
+            const size_t n_mbs = (size_t)e->geom().mb_cols * e->geom().mb_rows;
+            slots[si]->f.mbs.reserve(n_mbs, 0);
+            slots[si]->f.tokens.reserve(n_mbs * 32 + 1024, 0);
+            slots[si]->f.split.reserve(256, 0);
+          }
+        }
+        vp8gpu_parsed* p = slots[si];
+        {  // the dispatcher must have picked the slot's previous frame up ...
+          std::unique_lock<std::mutex> lk(mu);
+          cv_workers.wait(lk, [&] { return slot_state[si] == kFree; });
+        }
+        if (p->busy) {  // ... and the DMA engine must have read it
+          cudaEventSynchronize(p->consumed);
+          p->busy = false;
+        }
+        rc = vp8::parse_frame(state, items[i].p, items[i].n, p->f);
         if (rc != VP8GPU_OK) break;
-        if (dst && items[i].out_off >= 0)
-          rc = e->frame_download_display(id, d->lane, dst + items[i].out_off, frame_bytes, false);
-        e->frame_release(id);
+        count_mbs(p);
+        const vp8gpu_frame_desc& desc = p->f.desc;
+        Pending job;
+        job.slot = p;
+        job.slot_state = &slot_state[si];
+        job.out_off = (dst && desc.show_frame) ? items[i].out_off : -1;
+        rc = e->frame_alloc(&job.out);
         if (rc != VP8GPU_OK) break;
+        for (int k = 0; k < 3; k++) {
+          job.refs[k] = desc.key_frame ? -1 : refs[k];
+          if (job.refs[k] >= 0) e->frame_retain(job.refs[k]);  // keeps the raster alive until submitted
+        }
+        // Frame::copy_to (frame.cc:272-307)
+        const int out = job.out;
+        if (desc.key_frame) {
+          set_ref(e, &refs[0], out);
+          set_ref(e, &refs[1], out);
+          set_ref(e, &refs[2], out);
+        } else {
+          if (desc.copy_to_alternate == 1) set_ref(e, &refs[2], refs[0]);
+          else if (desc.copy_to_alternate == 2) set_ref(e, &refs[2], refs[1]);
+          if (desc.copy_to_golden == 1) set_ref(e, &refs[1], refs[0]);
+          else if (desc.copy_to_golden == 2) set_ref(e, &refs[1], refs[2]);
+          if (desc.refresh_golden) set_ref(e, &refs[1], out);
+          if (desc.refresh_alternate) set_ref(e, &refs[2], out);
+          if (desc.refresh_last) set_ref(e, &refs[0], out);
+        }
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          slot_state[si] = kQueued;
+          queues[tid].push_back(job);
+        }
+        cv_dispatch.notify_one();
       }
       if (rc != VP8GPU_OK) {
-        int ok = VP8GPU_OK;
-        first_error.compare_exchange_strong(ok, rc);
+        set_error(rc);
         break;
       }
     }
-    e->sync_lane(d->lane);
-    vp8gpu_decoder_destroy(d);
+    {  // wait until everything this worker queued has been submitted, then retire
+      std::unique_lock<std::mutex> lk(mu);
+      cv_workers.wait(lk, [&] {
+        for (int k = 0; k < kSlots; k++)
+          if (slot_state[k] != kFree) return false;  // the dispatcher still owns that slot
+        return true;
+      });
+      workers_running--;
+    }
+    cv_dispatch.notify_one();
+    for (int k = 0; k < 3; k++)
+      if (refs[k] >= 0) e->frame_release(refs[k]);
+    for (auto* p : slots)
+      if (p) {
+        if (p->busy) {
+          cudaEventSynchronize(p->consumed);
+          p->busy = false;
+        }
+        std::lock_guard<std::mutex> lk(ctx->pool_mu);
+        ctx->pinned_pool.push_back(p);
+      }
   };
+
+  auto dispatcher = [&]() {
+    cudaSetDevice(e->device());
+    std::vector<Pending> batch;
+    std::vector<HostJob> hj;
+    int round = 0;
+    for (;;) {
+      batch.clear();
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_dispatch.wait(lk, [&] {
+          if (workers_running == 0) return true;
+          for (auto& q : queues)
+            if (!q.empty()) return true;
+          return false;
+        });
+        for (auto& q : queues)
+          if (!q.empty()) {
+            batch.push_back(q.front());
+            q.pop_front();
+          }
+        if (batch.empty() && workers_running == 0) break;
+      }
+      if (batch.empty()) continue;
+      const int lane = round++ % kDispatchLanes;
+      hj.clear();
+      for (const Pending& b : batch) {
+        HostJob j;
+        j.desc = &b.slot->f.desc;
+        j.mbs = b.slot->f.mbs.data();
+        j.tokens = b.slot->f.tokens.data();
+        j.split = b.slot->f.split.data();
+        memcpy(j.refs, b.refs, sizeof(j.refs));
+        j.out = b.out;
+        j.n_intra = (int)b.slot->n_intra;
+        j.n_filtered = (int)b.slot->n_filtered;
+        hj.push_back(j);
+      }
+      int rc = e->submit(lane, hj.data(), (int)hj.size(), nullptr);
+      for (const Pending& b : batch) {
+        if (rc == VP8GPU_OK) {
+          cudaEventRecord(b.slot->consumed, e->stream(lane));
+          b.slot->busy = true;
+          if (b.out_off >= 0) {
+            const int r2 = e->frame_download_display(b.out, lane, dst + b.out_off, frame_bytes, false);
+            if (r2 != VP8GPU_OK) rc = r2;
+          }
+        }
+        for (int k = 0; k < 3; k++)
+          if (b.refs[k] >= 0) e->frame_release(b.refs[k]);
+        e->frame_release(b.out);
+      }
+      if (rc != VP8GPU_OK) set_error(rc);
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        for (const Pending& b : batch) *b.slot_state = kFree;
+      }
+      cv_workers.notify_all();
+    }
+    for (int l = 0; l < kDispatchLanes; l++) e->sync_lane(l);
+  };
+
   std::vector<std::thread> pool;
-  for (int t = 1; t < threads; t++) pool.emplace_back(worker, t);
-  worker(0);
+  for (int t = 0; t < threads; t++) pool.emplace_back(worker, t);
+  dispatcher();
   for (auto& t : pool) t.join();
   if (n_decoded) *n_decoded = (uint32_t)items.size();
   if (n_shown) *n_shown = shown_total;

@@ -179,7 +179,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="medium", choices=list(STREAMS))
     ap.add_argument("--gop-instances", type=int, default=16, help="GOPs advanced together in the HBM-resident run")
-    ap.add_argument("--replicas", type=int, default=16, help="stream repeats for the end-to-end run")
+    ap.add_argument("--replicas", type=int, default=48, help="stream repeats for the end-to-end run")
     ap.add_argument("--threads", type=int, default=0, help="host workers for the end-to-end run (0 = auto)")
     ap.add_argument("--ref-procs", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -345,11 +345,11 @@ def main():
         for fr in s_["frames"]:
             fr.release()
     ctx.close()
-    threads = a.threads or max(1, min(32, (os.cpu_count() or 1) // max(world, 1)))
+    threads = a.threads or max(1, min(64, (os.cpu_count() or 1) // max(world, 1) - 2))
     R = a.replicas
     big = replicate_ivf(data, R)
     n_e2e_frames = len(frames) * R
-    ctx2 = Context(w, h, device=local, max_frames=threads * 8 + 32)
+    ctx2 = Context(w, h, device=local, max_frames=threads * 10 + 64)
     out_bytes = ctx2.display_bytes * n_e2e_frames
     dst = C.c_void_p()
     capi.check(L.vp8gpu_host_alloc(C.byref(dst), out_bytes), ctx2.h, "host_alloc")
