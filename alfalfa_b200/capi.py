@@ -107,6 +107,7 @@ SYMBOLS = {
     "vp8gpu_decoder_references": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
     "vp8gpu_decoder_lane": (C.c_int, [_vp]),
     "vp8gpu_decoder_equal": (C.c_int, [_vp, _vp, C.POINTER(C.c_int)]),
+    "vp8gpu_decode_ivf_stats": (None, [_vp, C.POINTER(C.c_double)]),
     "vp8gpu_decode_ivf": (C.c_int, [_vp, C.c_char_p, C.c_size_t, C.c_int, _u8p, C.c_size_t, C.POINTER(C.c_uint32),
                                     C.POINTER(C.c_uint32)]),
 }

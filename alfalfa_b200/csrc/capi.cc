@@ -11,6 +11,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -32,6 +33,8 @@ struct vp8gpu_ctx {
   // decoders borrow them from this pool and hand them back when they are destroyed
   std::mutex pool_mu;
   std::vector<vp8gpu_parsed*> pinned_pool;
+  // wall-clock accounting of the last vp8gpu_decode_ivf call (seconds, summed over threads)
+  double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 struct vp8gpu_state {
   State s;
@@ -123,6 +126,7 @@ void vp8gpu_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
 uint64_t vp8gpu_launch_count(const vp8gpu_ctx* ctx) { return ctx->engine->launches(); }
+void vp8gpu_decode_ivf_stats(const vp8gpu_ctx* ctx, double out[8]) { memcpy(out, ctx->stats, sizeof(ctx->stats)); }
 
 // =============================================================================================
 // the seam
@@ -515,8 +519,13 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     first_error.compare_exchange_strong(ok, rc);
   };
 
+  std::mutex stats_mu;
+  double st_parse = 0, st_wait_slot = 0, st_wait_dma = 0, st_submit = 0, st_download = 0, st_disp_idle = 0;
+  double st_batches = 0, st_jobs = 0;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   auto worker = [&](int tid) {
     cudaSetDevice(e->device());
+    double t_parse = 0, t_slot = 0, t_dma = 0;
     State state(w, h);
     int refs[3] = {-1, -1, -1};
     vp8gpu_parsed* slots[kSlots] = {};
@@ -547,17 +556,23 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
           }
         }
         vp8gpu_parsed* p = slots[si];
+        const double t0 = now();
         {  // the dispatcher must have picked the slot's previous frame up ...
           std::unique_lock<std::mutex> lk(mu);
           cv_workers.wait(lk, [&] { return slot_state[si] == kFree; });
         }
+        const double t1 = now();
         if (p->busy) {  // ... and the DMA engine must have read it
           cudaEventSynchronize(p->consumed);
           p->busy = false;
         }
+        const double t2 = now();
         rc = vp8::parse_frame(state, items[i].p, items[i].n, p->f);
         if (rc != VP8GPU_OK) break;
         count_mbs(p);
+        t_slot += t1 - t0;
+        t_dma += t2 - t1;
+        t_parse += now() - t2;
         const vp8gpu_frame_desc& desc = p->f.desc;
         Pending job;
         job.slot = p;
@@ -606,6 +621,12 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
       workers_running--;
     }
     cv_dispatch.notify_one();
+    {
+      std::lock_guard<std::mutex> lk(stats_mu);
+      st_parse += t_parse;
+      st_wait_slot += t_slot;
+      st_wait_dma += t_dma;
+    }
     for (int k = 0; k < 3; k++)
       if (refs[k] >= 0) e->frame_release(refs[k]);
     for (auto* p : slots)
@@ -626,6 +647,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     int round = 0;
     for (;;) {
       batch.clear();
+      const double ti = now();
       {
         std::unique_lock<std::mutex> lk(mu);
         cv_dispatch.wait(lk, [&] {
@@ -642,6 +664,10 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
         if (batch.empty() && workers_running == 0) break;
       }
       if (batch.empty()) continue;
+      const double ts = now();
+      st_disp_idle += ts - ti;
+      st_batches += 1;
+      st_jobs += batch.size();
       const int lane = round++ % kDispatchLanes;
       hj.clear();
       for (const Pending& b : batch) {
@@ -657,6 +683,8 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
         hj.push_back(j);
       }
       int rc = e->submit(lane, hj.data(), (int)hj.size(), nullptr);
+      const double td = now();
+      st_submit += td - ts;
       for (const Pending& b : batch) {
         if (rc == VP8GPU_OK) {
           cudaEventRecord(b.slot->consumed, e->stream(lane));
@@ -671,6 +699,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
         e->frame_release(b.out);
       }
       if (rc != VP8GPU_OK) set_error(rc);
+      st_download += now() - td;
       {
         std::lock_guard<std::mutex> lk(mu);
         for (const Pending& b : batch) *b.slot_state = kFree;
@@ -684,6 +713,14 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
   for (int t = 0; t < threads; t++) pool.emplace_back(worker, t);
   dispatcher();
   for (auto& t : pool) t.join();
+  ctx->stats[0] = st_parse;
+  ctx->stats[1] = st_wait_slot;
+  ctx->stats[2] = st_wait_dma;
+  ctx->stats[3] = st_submit;
+  ctx->stats[4] = st_download;
+  ctx->stats[5] = st_disp_idle;
+  ctx->stats[6] = st_batches;
+  ctx->stats[7] = st_jobs;
   if (n_decoded) *n_decoded = (uint32_t)items.size();
   if (n_shown) *n_shown = shown_total;
   return first_error.load();

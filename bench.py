@@ -183,6 +183,8 @@ def main():
     ap.add_argument("--threads", type=int, default=0, help="host workers for the end-to-end run (0 = auto)")
     ap.add_argument("--ref-procs", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-output", action="store_true", help="diagnostic: leave decoded frames on the device")
+    ap.add_argument("--host-stats", action="store_true", help="diagnostic: print host time accounting to stderr")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 0)
 
@@ -357,8 +359,8 @@ def main():
 
     def e2e_step():
         t0 = time.perf_counter()
-        capi.check(L.vp8gpu_decode_ivf(ctx2.h, big, len(big), threads, dst, out_bytes, C.byref(nd), C.byref(ns)), ctx2.h,
-                   "decode_ivf")
+        capi.check(L.vp8gpu_decode_ivf(ctx2.h, big, len(big), threads, None if a.no_output else dst,
+                                       0 if a.no_output else out_bytes, C.byref(nd), C.byref(ns)), ctx2.h, "decode_ivf")
         capi.check(L.vp8gpu_ctx_sync(ctx2.h), ctx2.h, "sync")
         return time.perf_counter() - t0
 
@@ -367,6 +369,12 @@ def main():
     barrier(dist)
     e2e_s = [e2e_step() for _ in range(a.steps)]
     barrier(dist)
+    if a.host_stats:
+        stt = (C.c_double * 8)()
+        L.vp8gpu_decode_ivf_stats(ctx2.h, stt)
+        print("host stats (last step, s): parse %.3f wait_dispatch %.3f wait_dma %.3f | dispatcher: submit %.3f downloads %.3f "
+              "idle %.3f | batches %d frames %d | step wall %.3f" % (*list(stt)[:6], int(stt[6]), int(stt[7]), e2e_s[-1]),
+              file=sys.stderr)
     e2e_total = max_over_ranks(dist, local, sum(e2e_s))
     e2e_value = sum_over_ranks(dist, local, n_e2e_frames * mpix_frame * a.steps) / e2e_total
     launches_e2e = ctx2.launch_count()

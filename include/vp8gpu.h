@@ -262,6 +262,11 @@ int vp8gpu_decoder_equal(vp8gpu_decoder* a, vp8gpu_decoder* b, int* equal);
 int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threads, uint8_t* dst,
                       size_t dst_size, uint32_t* n_decoded, uint32_t* n_shown);
 
+/* Host-side time accounting of the last vp8gpu_decode_ivf call, seconds summed over threads:
+ * [0] parsing, [1] workers waiting for the dispatcher, [2] workers waiting for DMA, [3] dispatcher
+ * in submit, [4] dispatcher queueing downloads, [5] dispatcher idle, [6] batches, [7] frames. */
+void vp8gpu_decode_ivf_stats(const vp8gpu_ctx* ctx, double out[8]);
+
 #ifdef __cplusplus
 }
 #endif
