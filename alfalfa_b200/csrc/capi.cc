@@ -650,12 +650,19 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
       const double ti = now();
       {
         std::unique_lock<std::mutex> lk(mu);
-        cv_dispatch.wait(lk, [&] {
-          if (workers_running == 0) return true;
-          for (auto& q : queues)
-            if (!q.empty()) return true;
-          return false;
-        });
+        auto ready = [&] {
+          int n = 0;
+          for (auto& q : queues) n += !q.empty();
+          return n;
+        };
+        cv_dispatch.wait(lk, [&] { return workers_running == 0 || ready() > 0; });
+        // Device time per batch is almost flat in the number of frames (the wavefront kernels
+        // are latency bound), so give the other workers a moment to finish their current frame:
+        // go once most of them have something queued, or after a short grace period.
+        const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(1500);
+        while (workers_running > 0 && ready() < (workers_running * 3 + 3) / 4) {
+          if (cv_dispatch.wait_until(lk, deadline) == std::cv_status::timeout) break;
+        }
         for (auto& q : queues)
           if (!q.empty()) {
             batch.push_back(q.front());
@@ -680,6 +687,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
         j.out = b.out;
         j.n_intra = (int)b.slot->n_intra;
         j.n_filtered = (int)b.slot->n_filtered;
+        j.consumed = b.slot->consumed;  // fires as soon as the records are in HBM, before the kernels
         hj.push_back(j);
       }
       int rc = e->submit(lane, hj.data(), (int)hj.size(), nullptr);
@@ -687,7 +695,6 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
       st_submit += td - ts;
       for (const Pending& b : batch) {
         if (rc == VP8GPU_OK) {
-          cudaEventRecord(b.slot->consumed, e->stream(lane));
           b.slot->busy = true;
           if (b.out_off >= 0) {
             const int r2 = e->frame_download_display(b.out, lane, dst + b.out_off, frame_bytes, false);

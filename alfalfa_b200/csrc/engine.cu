@@ -110,7 +110,7 @@ int Engine::frame_alloc(int* id) {
   Frame& f = frames_[i];
   if (!f.dev) {
     CU(cudaSetDevice(device_));
-    CU(cudaMalloc(&f.dev, g_.frame_bytes));
+    CU(cudaMalloc(&f.dev, g_.frame_bytes + 64));  // slack: staged window rows are read as whole words
   }
   free_.pop_back();
   f.refcnt = 1;
@@ -390,6 +390,7 @@ int Engine::submit(int lane, const HostJob* jobs, int n, cudaEvent_t consumed) {
     if (j.desc->n_split)
       CU(cudaMemcpyAsync(st.dev + L.split_off[i], j.split, (size_t)j.desc->n_split * sizeof(vp8gpu_split_mvs),
                          cudaMemcpyHostToDevice, s));
+    if (j.consumed) CU(cudaEventRecord(j.consumed, s));
   }
   if (consumed) CU(cudaEventRecord(consumed, s));
   if (int rc = build_and_launch(lane, reinterpret_cast<const DevJob*>(st.dev), d_sync, n, any_inter, any_intra, any_lf))

@@ -27,6 +27,7 @@ struct HostJob {
   int out;
   int n_intra = -1;    // -1: count them here
   int n_filtered = -1;
+  cudaEvent_t consumed = nullptr;  // recorded as soon as this job's host arrays have been copied
 };
 
 class Engine {

@@ -75,42 +75,106 @@ __device__ __forceinline__ int chroma_component(int sum) {
 
 // ------------------------------------------------------------------------------------------------
 // Motion compensation of one N x N block by the whole warp (prediction.cc:655-674, 919-971).
-// (x0, y0) = block origin in the plane, mv in 1/8 pel.  The (N+5)^2 source window is fetched with
-// clamped coordinates (EdgeExtendedRaster::at, vp8_raster.hh:327-338), so no padded reference
-// planes are needed and vectors may point arbitrarily far outside the frame.
+// (x0, y0) = block origin in the plane, mv in 1/8 pel.
+//  * the source window ((N+5)^2, or N^2 for whole-pel vectors) is staged in shared memory; when it
+//    lies inside the plane it is fetched as aligned 32-bit words, otherwise pixel by pixel with
+//    clamped coordinates (EdgeExtendedRaster::at, vp8_raster.hh:327-338) -- no padded planes needed;
+//  * each lane filters strips of 4 outputs from a 9-pixel run (9 loads, 24 MACs);
+//  * a pass whose fraction is 0 is skipped: its taps are {0,0,128,0,0,0}, (128 p + 64) >> 7 = p.
 // ------------------------------------------------------------------------------------------------
+template <int N>
+struct Mc {
+  static constexpr int NW = (N + 11) / 4;  // words per staged row: covers 3 + N + 5 bytes
+  static constexpr int TS = 4 * NW;        // staged row stride in bytes (24 / 16 / 12)
+};
+
+// returns the byte offset of window column 0 inside a staged row
+template <int N>
+__device__ __forceinline__ int load_window(const uint8_t* __restrict__ ref, int pitch, int PW, int PH, int wx, int wy,
+                                           int wcols, int wrows, uint8_t* tile, int lane) {
+  constexpr int NW = Mc<N>::NW, TS = Mc<N>::TS;
+  if (wx >= 0 && wy >= 0 && wx + wcols <= PW && wy + wrows <= PH) {
+    const int o = wx & 3;
+    const uint8_t* base = ref + (size_t)wy * pitch + (wx - o);
+    uint32_t* tw = reinterpret_cast<uint32_t*>(tile);
+    for (int i = lane; i < wrows * NW; i += 32) {
+      const int r = i / NW, w = i - r * NW;
+      tw[i] = __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)r * pitch) + w);
+    }
+    return o;
+  }
+  for (int i = lane; i < wrows * wcols; i += 32) {
+    const int r = i / wcols, c = i - r * wcols;
+    tile[r * TS + c] = __ldg(ref + (size_t)clampi(wy + r, 0, PH - 1) * pitch + clampi(wx + c, 0, PW - 1));
+  }
+  return 0;
+}
+
+// horizontal 6-tap over `nrows` staged rows: out[r][c] from win[r][c .. c+5]; 4 outputs per item
+template <int N>
+__device__ __forceinline__ void hpass(const uint8_t* win, int nrows, const int16_t* hf, uint8_t* out, int ostride,
+                                      int lane) {
+  constexpr int G = N / 4, TS = Mc<N>::TS;
+  for (int i = lane; i < nrows * G; i += 32) {
+    const int r = i / G, g = i - r * G;
+    const uint8_t* t = win + r * TS + 4 * g;
+    int p[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) p[k] = t[k];
+    uint32_t o = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      o |= (uint32_t)vp8m::sixtap(p[j], p[j + 1], p[j + 2], p[j + 3], p[j + 4], p[j + 5], hf) << (8 * j);
+    *reinterpret_cast<uint32_t*>(out + r * ostride + 4 * g) = o;
+  }
+}
+// vertical 6-tap: dst[r][c] from src[r .. r+5][c]; each item = one column, 4 rows
+template <int N>
+__device__ __forceinline__ void vpass(const uint8_t* src, int sstride, const int16_t* vf, uint8_t* dst, int dstride,
+                                      int lane) {
+  constexpr int G = N / 4;
+  for (int i = lane; i < N * G; i += 32) {
+    const int g = i / N, c = i - g * N;
+    const uint8_t* m = src + (4 * g) * sstride + c;
+    int p[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) p[k] = m[k * sstride];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      dst[(4 * g + j) * dstride + c] = (uint8_t)vp8m::sixtap(p[j], p[j + 1], p[j + 2], p[j + 3], p[j + 4], p[j + 5], vf);
+  }
+}
+
 template <int N>
 __device__ __forceinline__ void mc_block(const uint8_t* __restrict__ ref, int pitch, int PW, int PH, int x0, int y0,
                                          int mvx, int mvy, uint8_t* dst, int dstride, uint8_t* tile, uint8_t* mid,
                                          int lane) {
+  constexpr int TS = Mc<N>::TS, G = N / 4;
   const int sx = x0 + (mvx >> 3), sy = y0 + (mvy >> 3);
   const int mx = mvx & 7, my = mvy & 7;
   if ((mx | my) == 0) {
-    for (int i = lane; i < N * N; i += 32) {
-      const int r = i / N, c = i % N;
-      dst[r * dstride + c] = __ldg(ref + (size_t)clampi(sy + r, 0, PH - 1) * pitch + clampi(sx + c, 0, PW - 1));
+    const int o = load_window<N>(ref, pitch, PW, PH, sx, sy, N, N, tile, lane);
+    __syncwarp();
+    for (int i = lane; i < N * G; i += 32) {
+      const int r = i / G, g = i - r * G;
+      const uint8_t* t = tile + r * TS + o + 4 * g;
+      *reinterpret_cast<uint32_t*>(dst + r * dstride + 4 * g) =
+          (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
     }
     __syncwarp();
     return;
   }
-  constexpr int TW = N + 5, TS = N + 8;
-  for (int i = lane; i < TW * TW; i += 32) {
-    const int r = i / TW, c = i % TW;
-    tile[r * TS + c] = __ldg(ref + (size_t)clampi(sy - 2 + r, 0, PH - 1) * pitch + clampi(sx - 2 + c, 0, PW - 1));
-  }
+  const int o = load_window<N>(ref, pitch, PW, PH, sx - 2, sy - 2, N + 5, N + 5, tile, lane);
   __syncwarp();
-  const int16_t* hf = c_sixtap[mx];
-  for (int i = lane; i < TW * N; i += 32) {
-    const int r = i / N, c = i % N;
-    const uint8_t* t = tile + r * TS + c;
-    mid[i] = (uint8_t)vp8m::sixtap(t[0], t[1], t[2], t[3], t[4], t[5], hf);
-  }
-  __syncwarp();
-  const int16_t* vf = c_sixtap[my];
-  for (int i = lane; i < N * N; i += 32) {
-    const int r = i / N, c = i % N;
-    const uint8_t* m = mid + r * N + c;
-    dst[r * dstride + c] = (uint8_t)vp8m::sixtap(m[0], m[N], m[2 * N], m[3 * N], m[4 * N], m[5 * N], vf);
+  const uint8_t* win = tile + o;
+  if (mx && my) {
+    hpass<N>(win, N + 5, c_sixtap[mx], mid, N, lane);
+    __syncwarp();
+    vpass<N>(mid, N, c_sixtap[my], dst, dstride, lane);
+  } else if (mx) {
+    hpass<N>(win + 2 * TS, N, c_sixtap[mx], dst, dstride, lane);
+  } else {
+    vpass<N>(win + 2, TS, c_sixtap[my], dst, dstride, lane);
   }
   __syncwarp();
 }
