@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvp8gpu.so")
+LIB_PATH = os.environ.get("VP8GPU_LIB", os.path.join(_HERE, "libvp8gpu.so"))  # override only for tools/phase_profile.py
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_LOGIC, ERR_CUDA, ERR_NOMEM = 0, -1, -2, -3, -4, -5
 

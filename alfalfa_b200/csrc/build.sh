@@ -13,3 +13,9 @@ $NVCC $FLAGS -x cu $ARCH -c capi.cc -o build/capi.o
 g++ -O3 -std=c++17 -fPIC -Wall -Wextra -c parser.cc -o build/parser.o
 $NVCC $ARCH -shared -o ../libvp8gpu.so build/kernels.o build/engine.o build/capi.o build/parser.o -Xcompiler -pthread
 echo "built $(cd .. && pwd)/libvp8gpu.so"
+# optional: phase-profiling variant of the library (tools/phase_profile.py)
+if [ "$1" = "prof" ]; then
+  $NVCC $ARCH $FLAGS -DVP8_PROFILE -c kernels.cu -o build/kernels_prof.o
+  $NVCC $ARCH -shared -o ../libvp8gpu_prof.so build/kernels_prof.o build/engine.o build/capi.o build/parser.o -Xcompiler -pthread
+  echo "built libvp8gpu_prof.so"
+fi

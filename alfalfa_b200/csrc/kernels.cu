@@ -34,6 +34,32 @@ __constant__ int16_t c_sixtap[8][6] = {{0, 0, 128, 0, 0, 0},     {0, -6, 123, 12
                                       {0, -9, 93, 50, -6, 0},   {3, -16, 77, 77, -16, 3}, {0, -6, 50, 93, -9, 0},
                                       {1, -8, 36, 108, -11, 2}, {0, -1, 12, 123, -6, 0}};
 
+// Optional phase profiling of the wavefront kernels (build with -DVP8_PROFILE, tools/phase_profile.py):
+// lane 0 of every warp accumulates clock64() deltas per phase and adds them to g_prof at exit.
+#ifdef VP8_PROFILE
+__device__ unsigned long long g_prof[32];
+#define PROF_DECL unsigned long long prof_t = clock64(), prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; unsigned prof_n = 0
+#define PROF(i)                                  \
+  do {                                           \
+    const unsigned long long now_ = clock64();   \
+    prof_acc[i] += now_ - prof_t;                \
+    prof_t = now_;                               \
+  } while (0)
+#define PROF_COUNT() (prof_n++)
+#define PROF_FLUSH(base)                                                           \
+  do {                                                                             \
+    if (lane == 0) {                                                               \
+      for (int i_ = 0; i_ < 8; i_++) atomicAdd(&g_prof[(base) + i_], prof_acc[i_]); \
+      atomicAdd(&g_prof[(base) + 8], (unsigned long long)prof_n);                  \
+    }                                                                              \
+  } while (0)
+#else
+#define PROF_DECL
+#define PROF(i)
+#define PROF_COUNT()
+#define PROF_FLUSH(base)
+#endif
+
 constexpr int CS = 18;          // int16 stride of one 4x4 coefficient block in shared memory (bank spread)
 constexpr int COEF_WORDS = 25 * CS / 2;  // 225 32-bit words
 
@@ -409,12 +435,17 @@ __global__ void __launch_bounds__(32) k_intra(const DevJob* __restrict__ jobs, i
   uint8_t* const U = J.out + g.u_off;
   uint8_t* const V = J.out + g.v_off;
 
+  PROF_DECL;
   while (col >= 0) {
+    PROF(7);
     const MbFields f = load_mb(row_mbs + col);
     // the residual only depends on this macroblock's tokens: build it before waiting on the row above
     const bool has_res = f.tok_cnt != 0;
+    PROF(0);
     if (has_res) build_residuals(J, f, coef, lane);
+    PROF(1);
     if (row > 0) wait_row(progress - 1, min(col + 2, cols), lane);
+    PROF(2);
 
     // ---- edges (prediction.cc:99-167), read through L2 ----
     {
@@ -445,6 +476,7 @@ __global__ void __launch_bounds__(32) k_intra(const DevJob* __restrict__ jobs, i
       }
     }
     __syncwarp();
+    PROF(3);
 
     // ---- chroma 8x8 prediction (prediction.cc:435-449): 128 pixels, 4 per lane ----
     int cdc[2] = {128, 128};
@@ -547,11 +579,16 @@ __global__ void __launch_bounds__(32) k_intra(const DevJob* __restrict__ jobs, i
       }
     }
     __syncwarp();
+    PROF(4);
     store_mb(pix, J.out, g, col, row, lane);
     const int next = next_marked(my_word, col + 1, nwords);
+    PROF(5);
     publish_row(progress, next < 0 ? cols : next, lane);
+    PROF(6);
+    PROF_COUNT();
     col = next;
   }
+  PROF_FLUSH(0);
 }
 
 // ================================================================================================
@@ -642,10 +679,14 @@ __global__ void __launch_bounds__(32) k_loopfilter(const DevJob* __restrict__ jo
   if (col >= 0) prefetch_own(col);
   int prev = -2;  // last column this warp filtered (its right 4 columns are still in shared memory)
 
+  PROF_DECL;
   while (col >= 0) {
+    PROF(7);
     const MbFields f = load_mb(row_mbs + col);
     const bool have_left = prev == col - 1;
+    PROF(0);
     if (row > 0) wait_row(progress - 1, min(col + 2, cols), lane);
+    PROF(1);
 
     // ---- top 4 rows (final output of the row above), through L2: one word per lane ----
     uint32_t top = 0;
@@ -691,6 +732,7 @@ __global__ void __launch_bounds__(32) k_loopfilter(const DevJob* __restrict__ jo
       *reinterpret_cast<uint32_t*>(sp) = own[k];
     }
     __syncwarp();
+    PROF(2);
     const int next = next_marked(my_word, col + 1, nwords);
     if (next >= 0) prefetch_own(next);  // in flight while this macroblock is filtered
 
@@ -729,6 +771,7 @@ __global__ void __launch_bounds__(32) k_loopfilter(const DevJob* __restrict__ jo
     }
     __syncwarp();
 
+    PROF(3);
     // ---- write back: region columns 0..15 (x -4..11); the last 4 columns travel with the next
     //      macroblock unless this warp will not filter it ----
     const int x_lo = col > 0 ? 0 : 1;
@@ -746,10 +789,14 @@ __global__ void __launch_bounds__(32) k_loopfilter(const DevJob* __restrict__ jo
         *reinterpret_cast<uint32_t*>((plane ? V : U) + (size_t)(8 * row - 4 + r) * g.c_pitch + 8 * col - 4 + 4 * wx) =
             *reinterpret_cast<const uint32_t*>(rc[plane] + r * CSZ + 4 * wx);
     }
+    PROF(4);
     publish_row(progress, next < 0 ? cols : next, lane);
+    PROF(5);
+    PROF_COUNT();
     prev = col;
     col = next;
   }
+  PROF_FLUSH(16);
 }
 
 // ================================================================================================
@@ -792,6 +839,17 @@ int launch_loopfilter(const DevJob* jobs, int njobs, const Geom& g, int* ticket,
   k_loopfilter<<<g.mb_rows * njobs, 32, 0, static_cast<cudaStream_t>(stream)>>>(jobs, njobs, g, ticket);
   return (int)cudaGetLastError();
 }
+
+#ifdef VP8_PROFILE
+extern "C" void vp8gpu_debug_profile(unsigned long long out[32], int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_prof, sizeof(unsigned long long) * 32);
+  if (reset) {
+    unsigned long long z[32] = {0};
+    cudaMemcpyToSymbol(g_prof, z, sizeof(z));
+  }
+}
+#endif
 
 int launch_compare(const uint8_t* a, const uint8_t* b, const Geom& g, int* d_flag, void* stream) {
   k_compare<<<296, 128, 0, static_cast<cudaStream_t>(stream)>>>(a, b, g, d_flag);
