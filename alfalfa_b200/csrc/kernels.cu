@@ -375,7 +375,11 @@ __device__ __forceinline__ void st_progress(int* p, int v) {
 // wait until the row above has finished every macroblock left of `need`
 __device__ __forceinline__ void wait_row(const int* progress_above, int need, int lane) {
   if (lane == 0) {
-    while (ld_progress(progress_above) < need) __nanosleep(20);
+    unsigned ns = 32;
+    while (ld_progress(progress_above) < need) {
+      __nanosleep(ns);
+      if (ns < 1024) ns += ns;  // back off: waiting warps should not steal issue slots from working ones
+    }
   }
   __syncwarp();  // the other lanes' later loads are ordered after lane 0's acquire through this barrier
 }
@@ -398,15 +402,50 @@ __device__ __forceinline__ int next_marked(uint32_t my_word, int from, int nword
 // ================================================================================================
 // k_intra
 // ================================================================================================
+// Luma workspace with its borders, so that every edge of every sub-block is one address formula:
+//   row 0            = the pixel row above the macroblock, x = -1 .. 19 (corner, 16 above, 4 above-right)
+//   rows 1..16       = macroblock rows, byte 15 = the pixel left of the row, bytes 16..31 = the row
+//   rows 4, 8, 12    additionally carry the 4 above-right pixels at bytes 32..35 (prediction.cc:153-160:
+//                    the right-column sub-blocks of rows 1-3 use the row above the MACROBLOCK)
+// pixel (x, y) lives at (y + 1) * WS + 16 + x; rows are 16-byte aligned for the vector stores.
+constexpr int WS = 48;
+
+__device__ __forceinline__ void add_residuals_intra(uint8_t* W, uint8_t* pixc, const int16_t* coef, int lane,
+                                                    bool luma_too) {
+  for (int g4 = (luma_too ? lane : 64 + lane); g4 < 96; g4 += 32) {
+    int blk, ry;
+    uint8_t* p;
+    if (g4 < 64) {
+      const int y = g4 >> 2, x4 = (g4 & 3) * 4;
+      blk = (y >> 2) * 4 + (x4 >> 2);
+      ry = y & 3;
+      p = W + (y + 1) * WS + 16 + x4;
+    } else {
+      const int c = g4 - 64, plane = c >> 4, cc = c & 15;
+      const int y = cc >> 1, x4 = (cc & 1) * 4;
+      blk = 16 + plane * 4 + (y >> 2) * 2 + (x4 >> 2);
+      ry = y & 3;
+      p = pixc + plane * 64 + y * 8 + x4;
+    }
+    const int16_t* r = coef + blk * CS + ry * 4;
+    const uint32_t v = *reinterpret_cast<uint32_t*>(p);
+    uint32_t o = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) o |= (uint32_t)vp8m::clamp255((int)((v >> (8 * k)) & 0xFF) + r[k]) << (8 * k);
+    *reinterpret_cast<uint32_t*>(p) = o;
+  }
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(32) k_intra(const DevJob* __restrict__ jobs, int njobs, Geom g, int* ticket) {
-  __shared__ __align__(16) uint8_t pix[384];
+  __shared__ __align__(16) uint8_t W[17 * WS];
+  __shared__ __align__(16) uint8_t pixc[128];  // U 8x8, V 8x8
   __shared__ __align__(16) int16_t coef[25 * CS];
-  __shared__ uint8_t aboveY[24];  // [0] = above-left, [1..16] = above, [17..20] = above-right
-  __shared__ uint8_t leftY[16];
   __shared__ uint8_t aboveC[2][12];  // [0] = above-left, [1..8] = above
   __shared__ uint8_t leftC[2][8];
-  __shared__ uint8_t edge[16];  // 13-entry edge vector of the current 4x4 sub-block
+  __shared__ uint16_t lut[128];
   const int lane = threadIdx.x;
+  for (int i = lane; i < 128; i += 32) lut[i] = k_bpred_lut[i];
   int t = 0;
   if (lane == 0) t = atomicAdd(ticket, 1);
   t = __shfl_sync(0xffffffffu, t, 0);
@@ -447,140 +486,145 @@ __global__ void __launch_bounds__(32) k_intra(const DevJob* __restrict__ jobs, i
     if (row > 0) wait_row(progress - 1, min(col + 2, cols), lane);
     PROF(2);
 
-    // ---- edges (prediction.cc:99-167), read through L2 ----
+    // ---- edges (prediction.cc:99-167), read through L2; the three loads of a lane are issued
+    //      back to back so their latencies overlap ----
     {
-      // luma above row incl. corner and above-right: 21 entries
-      if (lane < 21) {
-        int v;
-        if (row == 0) v = 127;
-        else if (lane == 0) v = col > 0 ? ldcg_u8(Y + (size_t)(16 * row - 1) * g.y_pitch + 16 * col - 1) : 129;
-        else if (lane <= 16) v = ldcg_u8(Y + (size_t)(16 * row - 1) * g.y_pitch + 16 * col + lane - 1);
-        else if (col == cols - 1) v = ldcg_u8(Y + (size_t)(16 * row - 1) * g.y_pitch + 16 * col + 15);
-        else v = ldcg_u8(Y + (size_t)(16 * row - 1) * g.y_pitch + 16 * col + lane - 1);
-        aboveY[lane] = (uint8_t)v;
+      const int outside_above = row == 0 ? 127 : 129;  // value of above[-1] when it is not a pixel
+      // (a) luma above row incl. corner and above-right: lanes 0..20
+      const uint8_t* pa = Y;
+      bool va = false;
+      if (lane < 21 && row > 0 && !(lane == 0 && col == 0)) {
+        const int x = (lane >= 17 && col == cols - 1) ? 15 : lane - 1;  // replicate at the right frame edge
+        pa = Y + (size_t)(16 * row - 1) * g.y_pitch + 16 * col + x;
+        va = true;
       }
-      if (lane < 16) leftY[lane] = col > 0 ? ldcg_u8(Y + (size_t)(16 * row + lane) * g.y_pitch + 16 * col - 1) : 129;
-      if (lane < 18) {
-        const int plane = lane / 9, k = lane % 9;
-        const uint8_t* P = plane ? V : U;
-        int v;
-        if (row == 0) v = 127;
-        else if (k == 0) v = col > 0 ? ldcg_u8(P + (size_t)(8 * row - 1) * g.c_pitch + 8 * col - 1) : 129;
-        else v = ldcg_u8(P + (size_t)(8 * row - 1) * g.c_pitch + 8 * col + k - 1);
-        aboveC[plane][k] = (uint8_t)v;
+      // (b) left columns: lanes 0..15 luma, 16..23 U, 24..31 V
+      const uint8_t* pb = Y;
+      if (col > 0) {
+        if (lane < 16) pb = Y + (size_t)(16 * row + lane) * g.y_pitch + 16 * col - 1;
+        else pb = ((lane & 8) ? V : U) + (size_t)(8 * row + (lane & 7)) * g.c_pitch + 8 * col - 1;
       }
-      if (lane >= 16) {
-        const int plane = (lane - 16) >> 3, k = (lane - 16) & 7;
-        const uint8_t* P = plane ? V : U;
-        leftC[plane][k] = col > 0 ? ldcg_u8(P + (size_t)(8 * row + k) * g.c_pitch + 8 * col - 1) : 129;
+      // (c) chroma above rows incl. corner: lanes 0..17
+      const uint8_t* pc = Y;
+      bool vc = false;
+      const int cpl = lane >= 9, ck = lane - 9 * cpl;
+      if (lane < 18 && row > 0 && !(ck == 0 && col == 0)) {
+        pc = (cpl ? V : U) + (size_t)(8 * row - 1) * g.c_pitch + 8 * col + ck - 1;
+        vc = true;
       }
+      const int a = va ? (int)ldcg_u8(pa) : outside_above;
+      const int b = col > 0 ? (int)ldcg_u8(pb) : 129;
+      const int c = vc ? (int)ldcg_u8(pc) : outside_above;
+      if (lane < 21) W[15 + lane] = (uint8_t)a;
+      if (lane < 16) W[(lane + 1) * WS + 15] = (uint8_t)b;
+      else leftC[(lane >> 3) & 1][lane & 7] = (uint8_t)b;
+      if (lane < 18) aboveC[cpl][ck] = (uint8_t)c;
     }
     __syncwarp();
     PROF(3);
 
-    // ---- chroma 8x8 prediction (prediction.cc:435-449): 128 pixels, 4 per lane ----
-    int cdc[2] = {128, 128};
-    if (f.uv_mode == VP8GPU_DC_PRED) {
-#pragma unroll
-      for (int plane = 0; plane < 2; plane++) {
-        int s = 0, n = 0;
-        if (row > 0) { for (int k = 0; k < 8; k++) s += aboveC[plane][1 + k]; n += 8; }
-        if (col > 0) { for (int k = 0; k < 8; k++) s += leftC[plane][k]; n += 8; }
-        cdc[plane] = n == 16 ? (s + 8) >> 4 : (n == 8 ? (s + 4) >> 3 : 128);
-      }
-    }
-    for (int i = lane; i < 128; i += 32) {
-      const int plane = i >> 6, y = (i >> 3) & 7, x = i & 7;
+    // ---- chroma 8x8 prediction (prediction.cc:435-449): one 4-pixel word per lane ----
+    {
+      const int plane = lane >> 4, y = (lane >> 1) & 7, x4 = (lane & 1) * 4;
       const uint8_t* A = aboveC[plane] + 1;
       const uint8_t* L = leftC[plane];
-      int v;
-      switch (f.uv_mode) {
-        case VP8GPU_DC_PRED: v = plane ? cdc[1] : cdc[0]; break;
-        case VP8GPU_V_PRED: v = A[x]; break;
-        case VP8GPU_H_PRED: v = L[y]; break;
-        default: v = vp8m::clamp255(L[y] + A[x] - A[-1]);
+      uint32_t word;
+      if (f.uv_mode == VP8GPU_DC_PRED) {
+        int s = 0, n = 0;
+        if (row > 0) { for (int k = 0; k < 8; k++) s += A[k]; n += 8; }
+        if (col > 0) { for (int k = 0; k < 8; k++) s += L[k]; n += 8; }
+        word = (uint32_t)(n == 16 ? (s + 8) >> 4 : (n == 8 ? (s + 4) >> 3 : 128)) * 0x01010101u;
+      } else if (f.uv_mode == VP8GPU_V_PRED) {
+        word = (uint32_t)A[x4] | ((uint32_t)A[x4 + 1] << 8) | ((uint32_t)A[x4 + 2] << 16) | ((uint32_t)A[x4 + 3] << 24);
+      } else if (f.uv_mode == VP8GPU_H_PRED) {
+        word = (uint32_t)L[y] * 0x01010101u;
+      } else {
+        const int base = L[y] - A[-1];
+        word = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) word |= (uint32_t)vp8m::clamp255(base + A[x4 + k]) << (8 * k);
       }
-      pix[256 + i] = (uint8_t)v;
+      *reinterpret_cast<uint32_t*>(pixc + plane * 64 + y * 8 + x4) = word;
     }
 
     if (f.y_mode != VP8GPU_B_PRED) {
-      // ---- luma 16x16 prediction (prediction.cc:451-467) ----
-      const uint8_t* A = aboveY + 1;
-      int dc = 128;
+      // ---- luma 16x16 prediction (prediction.cc:451-467): 8 pixels (two words) per lane ----
+      const int y = lane >> 1, x8 = (lane & 1) * 8;
+      const uint8_t* A = W + 16;  // above[x]
+      const int left = W[(y + 1) * WS + 15];
+      uint32_t w0, w1;
       if (f.y_mode == VP8GPU_DC_PRED) {
         int s = 0, n = 0;
         if (row > 0) { for (int k = 0; k < 16; k++) s += A[k]; n += 16; }
-        if (col > 0) { for (int k = 0; k < 16; k++) s += leftY[k]; n += 16; }
-        dc = n == 32 ? (s + 16) >> 5 : (n == 16 ? (s + 8) >> 4 : 128);
-      }
-      for (int i = lane; i < 256; i += 32) {
-        const int y = i >> 4, x = i & 15;
-        int v;
-        switch (f.y_mode) {
-          case VP8GPU_DC_PRED: v = dc; break;
-          case VP8GPU_V_PRED: v = A[x]; break;
-          case VP8GPU_H_PRED: v = leftY[y]; break;
-          default: v = vp8m::clamp255(leftY[y] + A[x] - A[-1]);
+        if (col > 0) { for (int k = 0; k < 16; k++) s += W[(k + 1) * WS + 15]; n += 16; }
+        w0 = w1 = (uint32_t)(n == 32 ? (s + 16) >> 5 : (n == 16 ? (s + 8) >> 4 : 128)) * 0x01010101u;
+      } else if (f.y_mode == VP8GPU_V_PRED) {
+        w0 = *reinterpret_cast<const uint32_t*>(A + x8);
+        w1 = *reinterpret_cast<const uint32_t*>(A + x8 + 4);
+      } else if (f.y_mode == VP8GPU_H_PRED) {
+        w0 = w1 = (uint32_t)left * 0x01010101u;
+      } else {
+        const int base = left - W[15];
+        w0 = w1 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          w0 |= (uint32_t)vp8m::clamp255(base + A[x8 + k]) << (8 * k);
+          w1 |= (uint32_t)vp8m::clamp255(base + A[x8 + 4 + k]) << (8 * k);
         }
-        pix[i] = (uint8_t)v;
       }
+      __syncwarp();  // all lanes have read the left column / above row they need
+      *reinterpret_cast<uint32_t*>(W + (y + 1) * WS + 16 + x8) = w0;
+      *reinterpret_cast<uint32_t*>(W + (y + 1) * WS + 20 + x8) = w1;
       __syncwarp();
-      if (has_res) add_residuals(pix, coef, lane);
+      if (has_res) add_residuals_intra(W, pixc, coef, lane, true);
     } else {
       // ---- B_PRED: 16 sub-blocks in raster order, each predicted from reconstructed
       //      neighbours, residual added before the next one starts (macroblock.cc:540-545) ----
+      if (lane < 12) W[(4 + 4 * (lane >> 2)) * WS + 32 + (lane & 3)] = W[32 + (lane & 3)];  // above-right copies
       __syncwarp();
-      if (has_res) {  // chroma residual first (it does not interact with luma)
-        for (int g4 = 64 + lane; g4 < 96; g4 += 32) {
-          const int c = g4 - 64, plane = c >> 4, cc = c & 15;
-          const int y = cc >> 1, x4 = (cc & 1) * 4;
-          const int blk = 16 + plane * 4 + (y >> 2) * 2 + (x4 >> 2);
-          const int16_t* r = coef + blk * CS + (y & 3) * 4;
-          uint8_t* p = pix + 256 + plane * 64 + y * 8 + x4;
-          for (int k = 0; k < 4; k++) p[k] = (uint8_t)vp8m::clamp255(p[k] + r[k]);
-        }
-      }
+      if (has_res) add_residuals_intra(W, pixc, coef, lane, false);  // chroma only
       const uint64_t modes = ((uint64_t)f.bm_hi << 32) | f.bm_lo;
+      const int x = lane & 3, y = (lane >> 2) & 3;
+#pragma unroll 4
       for (int b = 0; b < 16; b++) {
         const int bx = b & 3, by = b >> 2;
         const int mode = (int)((modes >> (4 * b)) & 15);
-        // edge vector: s[0..3] = left[3..0], s[4] = above[-1], s[5..12] = above[0..7]
-        if (lane < 13) {
-          int v;
-          if (lane < 4) {
-            const int k = 3 - lane;  // left[k]
-            v = bx ? pix[(4 * by + k) * 16 + 4 * bx - 1] : leftY[4 * by + k];
-          } else {
-            const int k = lane - 5;  // above[k], k = -1..7
-            if (by == 0) v = aboveY[1 + 4 * bx + k];
-            else if (k < 0) v = bx ? pix[(4 * by - 1) * 16 + 4 * bx - 1] : leftY[4 * by - 1];
-            else if (k < 4 || bx < 3) v = pix[(4 * by - 1) * 16 + 4 * bx + k];
-            else v = aboveY[17 + (k - 4)];  // right column, rows 1-3: the row above the macroblock
-          }
-          edge[lane] = (uint8_t)v;
-        }
-        __syncwarp();
+        // edge entry i of this sub-block: i < 4 -> left[3 - i], i = 4 -> above[-1], i > 4 -> above[i - 5]
+        const uint8_t* e0 = W + (4 * by) * WS + 15 + 4 * bx;  // = above[-1]
         if (lane < 16) {
-          const int x = lane & 3, y = lane >> 2;
           int v;
           if (mode == VP8GPU_B_DC_PRED) {
-            int s = 4;
-            for (int k = 0; k < 4; k++) s += edge[k] + edge[5 + k];
-            v = s >> 3;
+            int s4 = 4;
+#pragma unroll
+            for (int k = 0; k < 4; k++) s4 += e0[1 + k] + e0[(1 + k) * WS];
+            v = s4 >> 3;
           } else if (mode == VP8GPU_B_TM_PRED) {
-            v = vp8m::clamp255(edge[3 - y] + edge[5 + x] - edge[4]);
+            v = vp8m::clamp255(e0[(1 + y) * WS] + e0[1 + x] - e0[0]);
           } else {
-            v = vp8m::bpred_eval(k_bpred_lut[(mode - 2) * 16 + lane], edge);
+            const unsigned entry = lut[(mode - 2) * 16 + lane];
+            const int ia = entry & 15, ib = (entry >> 4) & 15, ic = (entry >> 8) & 15;
+            const int pa = e0[ia < 4 ? (4 - ia) * WS : ia - 4];
+            const int pb = e0[ib < 4 ? (4 - ib) * WS : ib - 4];
+            const int pc = e0[ic < 4 ? (4 - ic) * WS : ic - 4];
+            v = (entry & 0x1000) ? ((pa + 2 * pb + pc + 2) >> 2) : ((pa + pb + 1) >> 1);
           }
           if (has_res) v = vp8m::clamp255(v + coef[b * CS + lane]);
-          pix[(4 * by + y) * 16 + 4 * bx + x] = (uint8_t)v;
+          W[(4 * by + y + 1) * WS + 16 + 4 * bx + x] = (uint8_t)v;
         }
         __syncwarp();
       }
     }
     __syncwarp();
     PROF(4);
-    store_mb(pix, J.out, g, col, row, lane);
+    // ---- macroblock -> frame: 16-byte luma rows by lanes 0-15, 8-byte chroma rows by 16-31 ----
+    if (lane < 16) {
+      *reinterpret_cast<uint4*>(Y + (size_t)(16 * row + lane) * g.y_pitch + 16 * col) =
+          *reinterpret_cast<const uint4*>(W + (lane + 1) * WS + 16);
+    } else {
+      const int plane = (lane - 16) >> 3, yy = lane & 7;
+      *reinterpret_cast<uint2*>((plane ? V : U) + (size_t)(8 * row + yy) * g.c_pitch + 8 * col) =
+          *reinterpret_cast<const uint2*>(pixc + plane * 64 + yy * 8);
+    }
     const int next = next_marked(my_word, col + 1, nwords);
     PROF(5);
     publish_row(progress, next < 0 ? cols : next, lane);
@@ -776,18 +820,31 @@ __global__ void __launch_bounds__(32) k_loopfilter(const DevJob* __restrict__ jo
     //      macroblock unless this warp will not filter it ----
     const int x_lo = col > 0 ? 0 : 1;
     const bool flush_right = next != col + 1;
-    const int lw = flush_right ? 5 : 4, cw_n = flush_right ? 3 : 2;
-    for (int i = lane; i < 20 * lw; i += 32) {
-      const int r = i / lw, wx = i - r * lw;
-      if (r >= y_lo && wx >= x_lo)
-        *reinterpret_cast<uint32_t*>(Y + (size_t)(16 * row - 4 + r) * g.y_pitch + 16 * col - 4 + 4 * wx) =
-            *reinterpret_cast<const uint32_t*>(ry + r * YS + 4 * wx);
-    }
-    for (int i = lane; i < 24 * cw_n; i += 32) {
-      const int plane = i / (12 * cw_n), k = i - plane * 12 * cw_n, r = k / cw_n, wx = k - r * cw_n;
-      if (r >= y_lo && wx >= x_lo)
-        *reinterpret_cast<uint32_t*>((plane ? V : U) + (size_t)(8 * row - 4 + r) * g.c_pitch + 8 * col - 4 + 4 * wx) =
-            *reinterpret_cast<const uint32_t*>(rc[plane] + r * CSZ + 4 * wx);
+    {
+      uint8_t* const gy = Y + (size_t)(16 * row - 4) * g.y_pitch + 16 * col - 4;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {  // luma words 0..79: 20 rows x 4 words
+        const int w = lane + 32 * k, r = w >> 2, wx = w & 3;
+        if (w < 80 && r >= y_lo && wx >= x_lo)
+          *reinterpret_cast<uint32_t*>(gy + (size_t)r * g.y_pitch + 4 * wx) = *reinterpret_cast<const uint32_t*>(ry + r * YS + 4 * wx);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; k++) {  // chroma words 0..47: 2 planes x 12 rows x 2 words
+        const int w = lane + 32 * k, plane = w >= 24, kk = w - 24 * plane, r = kk >> 1, wx = kk & 1;
+        if (w < 48 && r >= y_lo && wx >= x_lo)
+          *reinterpret_cast<uint32_t*>((plane ? V : U) + (size_t)(8 * row - 4 + r) * g.c_pitch + 8 * col - 4 + 4 * wx) =
+              *reinterpret_cast<const uint32_t*>(rc[plane] + r * CSZ + 4 * wx);
+      }
+      if (flush_right) {
+        if (lane < 20 && lane >= y_lo)
+          *reinterpret_cast<uint32_t*>(gy + (size_t)lane * g.y_pitch + 16) = *reinterpret_cast<const uint32_t*>(ry + lane * YS + 16);
+        if (lane < 24) {
+          const int plane = lane >= 12, r = lane - 12 * plane;
+          if (r >= y_lo)
+            *reinterpret_cast<uint32_t*>((plane ? V : U) + (size_t)(8 * row - 4 + r) * g.c_pitch + 8 * col + 4) =
+                *reinterpret_cast<const uint32_t*>(rc[plane] + r * CSZ + 8);
+        }
+      }
     }
     PROF(4);
     publish_row(progress, next < 0 ? cols : next, lane);
