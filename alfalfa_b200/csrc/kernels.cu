@@ -375,10 +375,10 @@ __device__ __forceinline__ void st_progress(int* p, int v) {
 // wait until the row above has finished every macroblock left of `need`
 __device__ __forceinline__ void wait_row(const int* progress_above, int need, int lane) {
   if (lane == 0) {
-    unsigned ns = 32;
+    unsigned ns = 20;
     while (ld_progress(progress_above) < need) {
       __nanosleep(ns);
-      if (ns < 1024) ns += ns;  // back off: waiting warps should not steal issue slots from working ones
+      if (ns < 160) ns += ns;  // mild back-off: a step of the row above takes a few microseconds
     }
   }
   __syncwarp();  // the other lanes' later loads are ordered after lane 0's acquire through this barrier
@@ -585,8 +585,8 @@ __global__ void __launch_bounds__(32) k_intra(const DevJob* __restrict__ jobs, i
       if (has_res) add_residuals_intra(W, pixc, coef, lane, false);  // chroma only
       const uint64_t modes = ((uint64_t)f.bm_hi << 32) | f.bm_lo;
       const int x = lane & 3, y = (lane >> 2) & 3;
-#pragma unroll 4
-      for (int b = 0; b < 16; b++) {
+#pragma unroll
+      for (int b = 0; b < 16; b++) {  // fully unrolled: table entries and residuals load ahead of the chain
         const int bx = b & 3, by = b >> 2;
         const int mode = (int)((modes >> (4 * b)) & 15);
         // edge entry i of this sub-block: i < 4 -> left[3 - i], i = 4 -> above[-1], i > 4 -> above[i - 5]

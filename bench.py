@@ -87,41 +87,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def dist_setup(n_gpus):
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist_mod
-        torch.cuda.set_device(local)
-        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
-        dist = dist_mod
-    return rank, world, local, dist
-
-
-def barrier(dist):
-    if dist is not None:
-        dist.barrier()
-
-
-def max_over_ranks(dist, local, x):
-    if dist is None:
-        return x
-    import torch
-    t = torch.tensor([x], dtype=torch.float64, device="cuda:%d" % local)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
-
-
-def sum_over_ranks(dist, local, x):
-    if dist is None:
-        return x
-    import torch
-    t = torch.tensor([x], dtype=torch.float64, device="cuda:%d" % local)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return float(t.item())
+def effective_cpus():
+    """CPUs this process may actually use: affinity mask and cgroup quota (the GPU box gives the
+    container a CPU quota well below the 128 logical CPUs it shows)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
 
 
 def replicate_ivf(data, reps):
@@ -149,7 +125,7 @@ def run_reference_arm(a, rank, world):
     if rank != 0:
         return
     path = os.path.join(ROOT, "bench_data", STREAMS[a.workload])
-    cores = min(os.cpu_count() or 1, a.ref_procs)
+    cores = a.ref_procs or effective_cpus()
     if not os.path.exists(REF_DUMP):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_dump not built"}))
         return
@@ -167,7 +143,7 @@ def run_reference_arm(a, rank, world):
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": statistics.mean(walls) * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": "1080p30 IVF decode (%s), reference CPU decoder, C++ fallback build (no yasm)" % STREAMS[a.workload]},
-        "cpu_baseline": {"value": v, "unit": "Mpix/s", "cores": cores, "kind": "reference", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "Mpix/s", "cores": cores, "kind": "reference", "sample": sample, "usable_cpus": effective_cpus()},
         "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -179,21 +155,22 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="medium", choices=list(STREAMS))
     ap.add_argument("--gop-instances", type=int, default=16, help="GOPs advanced together in the HBM-resident run")
-    ap.add_argument("--replicas", type=int, default=48, help="stream repeats for the end-to-end run")
+    ap.add_argument("--replicas", type=int, default=0, help="stream repeats for the end-to-end run (0 = auto)")
     ap.add_argument("--threads", type=int, default=0, help="host workers for the end-to-end run (0 = auto)")
-    ap.add_argument("--ref-procs", type=int, default=128)
+    ap.add_argument("--ref-procs", type=int, default=0, help="reference processes (0 = usable CPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-output", action="store_true", help="diagnostic: leave decoded frames on the device")
     ap.add_argument("--host-stats", action="store_true", help="diagnostic: print host time accounting to stderr")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 0)
 
-    rank, world, local, dist = dist_setup(a.gpus)
-    if a.impl == "reference":
+    from alfalfa_b200 import multigpu as M
+    if a.impl == "reference":  # CPU arm: rank 0 alone runs it, no process group needed
+        rank, world, _ = M.rank_info()
         run_reference_arm(a, rank, world)
-        if dist is not None:
-            dist.destroy_process_group()
         return
+    rank, world, local, dist = M.init()
+    barrier, max_over_ranks, sum_over_ranks = M.barrier, M.reduce_max, M.reduce_sum
 
     import numpy as np
 
@@ -347,8 +324,9 @@ def main():
         for fr in s_["frames"]:
             fr.release()
     ctx.close()
-    threads = a.threads or max(1, min(64, (os.cpu_count() or 1) // max(world, 1) - 2))
-    R = a.replicas
+    # parse workers: twice the usable CPUs (they also wait on DMA / the dispatcher), shared by the ranks
+    threads = a.threads or max(2, min(64, 2 * effective_cpus() // max(world, 1)))
+    R = a.replicas or max(16, threads)  # 2 GOPs per repeat -> at least 2 GOPs per worker
     big = replicate_ivf(data, R)
     n_e2e_frames = len(frames) * R
     ctx2 = Context(w, h, device=local, max_frames=threads * 10 + 64)
