@@ -437,14 +437,25 @@ __device__ __forceinline__ void add_residuals_intra(uint8_t* W, uint8_t* pixc, c
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(32) k_intra(const DevJob* __restrict__ jobs, int njobs, Geom g, int* ticket) {
-  __shared__ __align__(16) uint8_t W[17 * WS];
-  __shared__ __align__(16) uint8_t pixc[128];  // U 8x8, V 8x8
-  __shared__ __align__(16) int16_t coef[25 * CS];
-  __shared__ uint8_t aboveC[2][12];  // [0] = above-left, [1..8] = above
-  __shared__ uint8_t leftC[2][8];
-  __shared__ uint16_t lut[128];
-  const int lane = threadIdx.x;
+// Two row-warps per CTA: an SM holds at most 32 CTAs, so single-warp CTAs would cap the rows in
+// flight at 32 per SM (69 frames of 1080p per GPU); with two it is the full 64 warps per SM.
+constexpr int WF_WARPS = 2;
+
+// 24 CTAs x 2 warps resident per SM (40 registers per thread, no spills)
+__global__ void __launch_bounds__(32 * WF_WARPS, 24) k_intra(const DevJob* __restrict__ jobs, int njobs, Geom g, int* ticket) {
+  __shared__ __align__(16) uint8_t s_W[WF_WARPS][17 * WS];
+  __shared__ __align__(16) uint8_t s_pixc[WF_WARPS][128];  // U 8x8, V 8x8
+  __shared__ __align__(16) int16_t s_coef[WF_WARPS][25 * CS];
+  __shared__ uint8_t s_aboveC[WF_WARPS][2][12];  // [0] = above-left, [1..8] = above
+  __shared__ uint8_t s_leftC[WF_WARPS][2][8];
+  __shared__ uint16_t s_lut[WF_WARPS][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* const W = s_W[warp];
+  uint8_t* const pixc = s_pixc[warp];
+  int16_t* const coef = s_coef[warp];
+  uint8_t (*const aboveC)[12] = s_aboveC[warp];
+  uint8_t (*const leftC)[8] = s_leftC[warp];
+  uint16_t* const lut = s_lut[warp];
   for (int i = lane; i < 128; i += 32) lut[i] = k_bpred_lut[i];
   int t = 0;
   if (lane == 0) t = atomicAdd(ticket, 1);
@@ -662,12 +673,15 @@ __device__ __forceinline__ void filter_line(int* px, bool luma, bool do_mb_edge,
   }
 }
 
-__global__ void __launch_bounds__(32) k_loopfilter(const DevJob* __restrict__ jobs, int njobs, Geom g, int* ticket) {
+// 16 CTAs x 2 warps resident per SM (64 registers per thread: a 20-pixel line lives in registers)
+__global__ void __launch_bounds__(32 * WF_WARPS, 16) k_loopfilter(const DevJob* __restrict__ jobs, int njobs, Geom g, int* ticket) {
   // region = the macroblock plus 4 pixels above and to the left: luma 20x20, chroma 12x12
   constexpr int YS = 20, CSZ = 12;
-  __shared__ __align__(16) uint8_t ry[20 * YS];
-  __shared__ __align__(16) uint8_t rc[2][12 * CSZ];
-  const int lane = threadIdx.x;
+  __shared__ __align__(16) uint8_t s_ry[WF_WARPS][20 * YS];
+  __shared__ __align__(16) uint8_t s_rc[WF_WARPS][2][12 * CSZ];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* const ry = s_ry[warp];
+  uint8_t (*const rc)[12 * CSZ] = s_rc[warp];
   int t = 0;
   if (lane == 0) t = atomicAdd(ticket, 1);
   t = __shfl_sync(0xffffffffu, t, 0);
@@ -889,11 +903,11 @@ int launch_inter(const DevJob* jobs, int njobs, const Geom& g, void* stream) {
   return (int)cudaGetLastError();
 }
 int launch_intra(const DevJob* jobs, int njobs, const Geom& g, int* ticket, void* stream) {
-  k_intra<<<g.mb_rows * njobs, 32, 0, static_cast<cudaStream_t>(stream)>>>(jobs, njobs, g, ticket);
+  k_intra<<<(g.mb_rows * njobs + WF_WARPS - 1) / WF_WARPS, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream)>>>(jobs, njobs, g, ticket);
   return (int)cudaGetLastError();
 }
 int launch_loopfilter(const DevJob* jobs, int njobs, const Geom& g, int* ticket, void* stream) {
-  k_loopfilter<<<g.mb_rows * njobs, 32, 0, static_cast<cudaStream_t>(stream)>>>(jobs, njobs, g, ticket);
+  k_loopfilter<<<(g.mb_rows * njobs + WF_WARPS - 1) / WF_WARPS, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream)>>>(jobs, njobs, g, ticket);
   return (int)cudaGetLastError();
 }
 
