@@ -1536,3 +1536,50 @@ int vp8o_time_ivf(const uint8_t* ivf, size_t len, int reps, uint32_t max_frames,
   memcpy(phase_s, best, sizeof(best));
   return VP8GPU_OK;
 }
+
+/* ============================ unit-level test hooks ============================ */
+/* (used by tests/test_math_host.py to check the arithmetic of csrc/vp8_math.cuh on the CPU) */
+void vp8o_test_idct_add(const int16_t c[16], uint8_t px[16]) { idct_add(c, px, 4); }
+void vp8o_test_iwht(const int16_t c[16], int16_t dc[16]) {
+  int16_t y[16][16];
+  memset(y, 0, sizeof(y));
+  iwht(c, y);
+  for (int i = 0; i < 16; i++) dc[i] = y[i][0];
+}
+void vp8o_test_lf_edge(uint8_t px[8], int level, int sharpness, int key_frame, int mb_edge) {
+  lf_params lp;
+  int interior = level;
+  if (sharpness) {
+    interior >>= sharpness > 4 ? 2 : 1;
+    if (interior > 9 - sharpness) interior = 9 - sharpness;
+  }
+  if (interior < 1) interior = 1;
+  lp.interior = interior;
+  lp.mb_edge = ((level + 2) * 2) + interior;
+  lp.sub_edge = (level * 2) + interior;
+  lp.hev = (level >= 15) + (level >= 40) + (level >= 20 && !key_frame);
+  edge(px + 4, 1, 8, 1, &lp, mb_edge);
+}
+/* s = edge vector: s[0..3] = left[3..0], s[4] = above[-1], s[5..12] = above[0..7] */
+void vp8o_test_bpred(int mode, const uint8_t s[13], uint8_t out[16]) {
+  uint8_t buf[16 * 16];
+  memset(buf, 0, sizeof(buf));
+  plane pl = {buf, 16, 16};
+  /* place the 4x4 block at sub-block (1,1) of a 16x16 plane so every neighbour is a real pixel */
+  for (int k = 0; k < 4; k++) buf[(4 + k) * 16 + 3] = s[3 - k];
+  for (int k = -1; k < 8; k++) buf[3 * 16 + 4 + k] = s[5 + k];
+  intra_predict_4x4(&pl, 1, 1, mode);
+  for (int y = 0; y < 4; y++)
+    for (int x = 0; x < 4; x++) out[y * 4 + x] = buf[(4 + y) * 16 + 4 + x];
+}
+/* N x N six-tap prediction from a (N+5)^2 window (window[2][2] = block origin) */
+void vp8o_test_sixtap(const uint8_t* window, int n, int mx, int my, uint8_t* out) {
+  const int ws = n + 5;
+  plane ref = {(uint8_t*)window, ws, ws};
+  uint8_t* tmp = (uint8_t*)calloc((size_t)ws * ws, 1);
+  plane o = {tmp, ws, ws};
+  /* block (col,row) = (0,0) of size n shifted by mv = (2*8 + mx, 2*8 + my) reads window[2+..] */
+  inter_predict(&o, &ref, n, 0, 0, 16 + mx, 16 + my);
+  for (int y = 0; y < n; y++) memcpy(out + y * n, tmp + y * ws, n);
+  free(tmp);
+}

@@ -150,3 +150,50 @@ def test_errors_mirror_reference_exception_classes():
     del dec
     ctx.close()
     other.close()
+
+
+@pytest.mark.parametrize("name,threads", [("synth1080p_medium_q90.ivf", 8), ("synth1080p_easy_q40.ivf", 3),
+                                          ("synth4k_medium_q90_8f.ivf", 2)])
+def test_full_size_clips_match_reference_decode(name, threads):
+    """BASELINE.json sizes (1080p bench workload, 4K): GPU decode through vp8gpu_decode_ivf vs the
+    SHA-1 of the unmodified reference's decode of the same clip (tests/golden/bench_clips.json)."""
+    import json
+    from alfalfa_b200 import Context, decode_ivf
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    want = json.load(open(os.path.join(root, "tests", "golden", "bench_clips.json")))[name]
+    data = open(os.path.join(root, "bench_data", name), "rb").read()
+    w, h, _ = O.read_ivf(data)
+    ctx = Context(w, h, max_frames=64)
+    out, n_dec, n_shown = decode_ivf(ctx, data, threads=threads)
+    ctx.close()
+    assert len(out) == want["bytes"] and hashlib.sha1(out).hexdigest() == want["sha1_of_reference_decode"]
+
+
+def test_many_independent_720p_streams_in_one_batch():
+    """BASELINE.json config 5 shape: frames of independent streams decoded by one batched launch set
+    (here 12 key frames of the real 720p vector as 12 streams)."""
+    from alfalfa_b200 import Context, capi
+    data = _read("ff2941dde20090835032c32c0644b6d401610c57")
+    w, h, frames = O.read_ivf(data)
+    ctx = Context(w, h, max_frames=32)
+    L = ctx.L
+    n = 12
+    keep, jobs, outs, wants = [], (capi.Job * n)(), [], []
+    for i in range(n):
+        od = O.OracleDecoder(w, h)  # every stream has its own decoder state
+        r = od.decode(frames[i * 5])
+        p = od.parsed()
+        mbs, tok = np.ascontiguousarray(p.mbs), np.ascontiguousarray(p.tokens)
+        desc = capi.FrameDesc.from_buffer_copy(bytes(p.desc))
+        out = ctx.alloc_frame()
+        keep.append((mbs, tok, desc))
+        jobs[i].desc, jobs[i].mbs, jobs[i].tokens, jobs[i].split = C.pointer(desc), mbs.ctypes.data, tok.ctypes.data, None
+        jobs[i].refs[:] = [-1, -1, -1]
+        jobs[i].out = out.id
+        outs.append(out)
+        wants.append(r["planes"])
+    capi.check(L.vp8gpu_decode_batch(ctx.h, 0, jobs, n), ctx.h, "decode_batch")
+    for out, want in zip(outs, wants):
+        assert all(np.array_equal(g, w_) for g, w_ in zip(out.planes(), want))
+        out.release()
+    ctx.close()

@@ -11,3 +11,15 @@ mkdir -p bench_data
 oracle/_ref/ref_encode bench_data/synth1080p_medium_q90.ivf 1920 1080 60 30 90 1234 2 2>/dev/null
 oracle/_ref/ref_encode bench_data/synth1080p_easy_q40.ivf 1920 1080 60 30 40 1234 0 2>/dev/null
 ls -la bench_data
+# short 4K clip (BASELINE.json config 4 parity case) and the reference's own answers for all clips
+oracle/_ref/ref_encode bench_data/synth4k_medium_q90_8f.ivf 3840 2160 8 4 90 77 2 2>/dev/null
+python - <<'PY'
+import hashlib, json, subprocess, os
+out = {}
+for n in sorted(os.listdir("bench_data")):
+    if n.endswith(".ivf"):
+        raw = subprocess.run(["oracle/_ref/ref_dump", "shown", "bench_data/" + n], capture_output=True).stdout
+        out[n] = {"sha1_of_reference_decode": hashlib.sha1(raw).hexdigest(), "bytes": len(raw)}
+json.dump(out, open("tests/golden/bench_clips.json", "w"), indent=1, sort_keys=True)
+print(json.dumps(out, indent=1))
+PY
