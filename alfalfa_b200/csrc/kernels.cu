@@ -171,38 +171,85 @@ __device__ __forceinline__ void vpass(const uint8_t* src, int sstride, const int
   }
 }
 
+// A planned block prediction: where its source window is, and (when the window lies inside the
+// plane) the window itself, already requested into registers so that the loads of several planes
+// are in flight together.
+template <int N>
+struct McPlan {
+  static constexpr int K = (Mc<N>::NW * (N + 5) + 31) / 32;  // words per lane: 4 / 2 / 1
+  int wx, wy, wsize, mx, my, o;
+  bool fast;
+  uint32_t regs[K];
+};
+
+template <int N>
+__device__ __forceinline__ void mc_plan(McPlan<N>& p, const uint8_t* __restrict__ ref, int pitch, int PW, int PH,
+                                        int x0, int y0, int mvx, int mvy, int lane) {
+  constexpr int NW = Mc<N>::NW;
+  p.mx = mvx & 7;
+  p.my = mvy & 7;
+  const bool whole = (p.mx | p.my) == 0;
+  p.wx = x0 + (mvx >> 3) - (whole ? 0 : 2);
+  p.wy = y0 + (mvy >> 3) - (whole ? 0 : 2);
+  p.wsize = whole ? N : N + 5;
+  p.fast = p.wx >= 0 && p.wy >= 0 && p.wx + p.wsize <= PW && p.wy + p.wsize <= PH;
+  p.o = p.fast ? (p.wx & 3) : 0;
+  if (p.fast) {
+    const uint8_t* base = ref + (size_t)p.wy * pitch + (p.wx - p.o);
+#pragma unroll
+    for (int k = 0; k < McPlan<N>::K; k++) {
+      const int i = lane + 32 * k;
+      const int r = i / NW, w = i - r * NW;
+      p.regs[k] = i < p.wsize * NW ? __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)r * pitch) + w) : 0u;
+    }
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void mc_finish(const McPlan<N>& p, const uint8_t* __restrict__ ref, int pitch, int PW, int PH,
+                                          uint8_t* dst, int dstride, uint8_t* tile, uint8_t* mid, int lane) {
+  constexpr int TS = Mc<N>::TS, NW = Mc<N>::NW, G = N / 4;
+  if (p.fast) {
+    uint32_t* tw = reinterpret_cast<uint32_t*>(tile);
+#pragma unroll
+    for (int k = 0; k < McPlan<N>::K; k++) {
+      const int i = lane + 32 * k;
+      if (i < p.wsize * NW) tw[i] = p.regs[k];
+    }
+  } else {
+    for (int i = lane; i < p.wsize * p.wsize; i += 32) {
+      const int r = i / p.wsize, c = i - r * p.wsize;
+      tile[r * TS + c] = __ldg(ref + (size_t)clampi(p.wy + r, 0, PH - 1) * pitch + clampi(p.wx + c, 0, PW - 1));
+    }
+  }
+  __syncwarp();
+  const uint8_t* win = tile + p.o;
+  if ((p.mx | p.my) == 0) {
+    for (int i = lane; i < N * G; i += 32) {
+      const int r = i / G, g = i - r * G;
+      const uint8_t* t = win + r * TS + 4 * g;
+      *reinterpret_cast<uint32_t*>(dst + r * dstride + 4 * g) =
+          (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+    }
+  } else if (p.mx && p.my) {
+    hpass<N>(win, N + 5, c_sixtap[p.mx], mid, N, lane);
+    __syncwarp();
+    vpass<N>(mid, N, c_sixtap[p.my], dst, dstride, lane);
+  } else if (p.mx) {
+    hpass<N>(win + 2 * TS, N, c_sixtap[p.mx], dst, dstride, lane);
+  } else {
+    vpass<N>(win + 2, TS, c_sixtap[p.my], dst, dstride, lane);
+  }
+  __syncwarp();
+}
+
 template <int N>
 __device__ __forceinline__ void mc_block(const uint8_t* __restrict__ ref, int pitch, int PW, int PH, int x0, int y0,
                                          int mvx, int mvy, uint8_t* dst, int dstride, uint8_t* tile, uint8_t* mid,
                                          int lane) {
-  constexpr int TS = Mc<N>::TS, G = N / 4;
-  const int sx = x0 + (mvx >> 3), sy = y0 + (mvy >> 3);
-  const int mx = mvx & 7, my = mvy & 7;
-  if ((mx | my) == 0) {
-    const int o = load_window<N>(ref, pitch, PW, PH, sx, sy, N, N, tile, lane);
-    __syncwarp();
-    for (int i = lane; i < N * G; i += 32) {
-      const int r = i / G, g = i - r * G;
-      const uint8_t* t = tile + r * TS + o + 4 * g;
-      *reinterpret_cast<uint32_t*>(dst + r * dstride + 4 * g) =
-          (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
-    }
-    __syncwarp();
-    return;
-  }
-  const int o = load_window<N>(ref, pitch, PW, PH, sx - 2, sy - 2, N + 5, N + 5, tile, lane);
-  __syncwarp();
-  const uint8_t* win = tile + o;
-  if (mx && my) {
-    hpass<N>(win, N + 5, c_sixtap[mx], mid, N, lane);
-    __syncwarp();
-    vpass<N>(mid, N, c_sixtap[my], dst, dstride, lane);
-  } else if (mx) {
-    hpass<N>(win + 2 * TS, N, c_sixtap[mx], dst, dstride, lane);
-  } else {
-    vpass<N>(win + 2, TS, c_sixtap[my], dst, dstride, lane);
-  }
-  __syncwarp();
+  McPlan<N> p;
+  mc_plan<N>(p, ref, pitch, PW, PH, x0, y0, mvx, mvy, lane);
+  mc_finish<N>(p, ref, pitch, PW, PH, dst, dstride, tile, mid, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -229,27 +276,47 @@ __device__ __forceinline__ void build_residuals(const DevJob& J, const MbFields&
   }
   __syncwarp();
   if (f.flags & VP8GPU_MB_HAS_Y2) {
-    if (lane == 0) {
-      int16_t dc[16];
-      vp8m::iwht16(coef + 24 * CS, dc);
-#pragma unroll
-      for (int k = 0; k < 16; k++) coef[k * CS] = dc[k];
+    // inverse WHT on 16 lanes (transform.cc:47-88): lane i first produces intermediate m[i]
+    // (column i & 3, butterfly output i >> 2), the row pass exchanges m through shuffles.
+    const int16_t* y2 = coef + 24 * CS;
+    int m = 0;
+    if (lane < 16) {
+      const int c = lane & 3;
+      const int v0 = y2[c], v1 = y2[c + 4], v2 = y2[c + 8], v3 = y2[c + 12];
+      const int a1 = v0 + v3, b1 = v1 + v2, c1 = v1 - v2, d1 = v0 - v3;
+      const int k = lane >> 2;
+      m = vp8m::wrap16(k == 0 ? a1 + b1 : (k == 1 ? c1 + d1 : (k == 2 ? a1 - b1 : d1 - c1)));
+    }
+    const int o4 = lane & 12;
+    const int m0 = __shfl_sync(0xffffffffu, m, o4), m1 = __shfl_sync(0xffffffffu, m, o4 + 1);
+    const int m2 = __shfl_sync(0xffffffffu, m, o4 + 2), m3 = __shfl_sync(0xffffffffu, m, o4 + 3);
+    if (lane < 16) {
+      const int a1 = m0 + m3, b1 = m1 + m2, c1 = m1 - m2, d1 = m0 - m3;
+      const int p = lane & 3;
+      const int x = p == 0 ? a1 + b1 : (p == 1 ? c1 + d1 : (p == 2 ? a1 - b1 : d1 - c1));
+      coef[lane * CS] = (int16_t)((x + 3) >> 3);  // DC of luma sub-block `lane`
     }
     __syncwarp();
   }
   if (lane < 24) {
     int16_t* c = coef + lane * CS;
-    const uint32_t* cw = reinterpret_cast<const uint32_t*>(c);
-    uint32_t any = 0;
+    uint32_t* cw = reinterpret_cast<uint32_t*>(c);
+    uint32_t ac = cw[0] & 0xFFFF0000u;
 #pragma unroll
-    for (int k = 0; k < 8; k++) any |= cw[k];
-    if (any) {
+    for (int k = 1; k < 8; k++) ac |= cw[k];
+    if (ac) {
       int16_t in[16], r[16];
 #pragma unroll
       for (int k = 0; k < 16; k++) in[k] = c[k];
       vp8m::idct16(in, r);
 #pragma unroll
       for (int k = 0; k < 16; k++) c[k] = r[k];
+    } else if (cw[0]) {
+      // DC only: both passes of idct_add reduce to (dc + 4) >> 3 for every pixel
+      const uint32_t r = (uint32_t)(uint16_t)(((int)(int16_t)(cw[0] & 0xFFFF) + 4) >> 3);
+      const uint32_t rr = r | (r << 16);
+#pragma unroll
+      for (int k = 0; k < 8; k++) cw[k] = rr;
     }
   }
   __syncwarp();
@@ -348,10 +415,16 @@ __global__ void __launch_bounds__(INTER_WARPS * 32) k_inter(const DevJob* __rest
                   tile, mid, lane);
     }
   } else {
-    mc_block<16>(ref, g.y_pitch, g.W, g.H, 16 * col, 16 * row, f.mv_x, f.mv_y, pix, 16, tile, mid, lane);
+    // request the three source windows first, then filter: one memory latency instead of three
     const int cmx = chroma_component(4 * f.mv_x), cmy = chroma_component(4 * f.mv_y);
-    mc_block<8>(refU, g.c_pitch, CW, CH, 8 * col, 8 * row, cmx, cmy, pix + 256, 8, tile, mid, lane);
-    mc_block<8>(refV, g.c_pitch, CW, CH, 8 * col, 8 * row, cmx, cmy, pix + 320, 8, tile, mid, lane);
+    McPlan<16> py;
+    McPlan<8> pu, pv;
+    mc_plan<16>(py, ref, g.y_pitch, g.W, g.H, 16 * col, 16 * row, f.mv_x, f.mv_y, lane);
+    mc_plan<8>(pu, refU, g.c_pitch, CW, CH, 8 * col, 8 * row, cmx, cmy, lane);
+    mc_plan<8>(pv, refV, g.c_pitch, CW, CH, 8 * col, 8 * row, cmx, cmy, lane);
+    mc_finish<16>(py, ref, g.y_pitch, g.W, g.H, pix, 16, tile, mid, lane);
+    mc_finish<8>(pu, refU, g.c_pitch, CW, CH, pix + 256, 8, tile, mid, lane);
+    mc_finish<8>(pv, refV, g.c_pitch, CW, CH, pix + 320, 8, tile, mid, lane);
   }
 
   if (f.tok_cnt) {  // Macroblock::has_nonzero_ (macroblock.cc:579,593)
