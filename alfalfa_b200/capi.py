@@ -74,6 +74,7 @@ SYMBOLS = {
     "vp8gpu_frame_download": (C.c_int, [_vp, C.c_int32, _u8p, C.c_size_t, _u8p, _u8p, C.c_size_t]),
     "vp8gpu_frame_download_display": (C.c_int, [_vp, C.c_int32, _u8p, C.c_size_t]),
     "vp8gpu_frame_download_display_async": (C.c_int, [_vp, C.c_int32, _u8p, C.c_size_t]),
+    "vp8gpu_frame_hash": (C.c_int, [_vp, C.c_int32, C.POINTER(C.c_uint64)]),
     "vp8gpu_ctx_sync": (C.c_int, [_vp]),
     "vp8gpu_host_alloc": (C.c_int, [_pp, C.c_size_t]),
     "vp8gpu_host_free": (None, [_vp]),

@@ -13,6 +13,7 @@
 namespace vp8 {
 
 int launch_compare(const uint8_t* a, const uint8_t* b, const Geom& g, int* d_flag, void* stream);
+int launch_hash(const uint8_t* a, const Geom& g, unsigned long long* d_out, void* stream);
 
 namespace {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -227,7 +228,7 @@ int Engine::frames_equal(int a, int b, int lane, int* equal) {
   cudaStream_t s = lanes_[lane];
   {
     std::lock_guard<std::mutex> lk(mu_);
-    if (!cmp_scratch_) CU(cudaMalloc(&cmp_scratch_, 256));
+    if (!cmp_scratch_) CU(cudaMalloc(&cmp_scratch_, 512));
     flag = reinterpret_cast<int*>(cmp_scratch_);
     if (int rc = wait_for(frames_[a], lane, s)) return rc;
     if (int rc = wait_for(frames_[b], lane, s)) return rc;
@@ -241,6 +242,28 @@ int Engine::frames_equal(int a, int b, int lane, int* equal) {
   CU(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   *equal = h == 0;
+  return VP8GPU_OK;
+}
+
+int Engine::frame_hash(int id, int lane, uint64_t* out) {
+  if (int rc = ensure_lane(lane)) return rc;
+  unsigned long long* d;
+  cudaStream_t s = lanes_[lane];
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (id < 0 || id >= (int)frames_.size() || frames_[id].refcnt <= 0) return fail(VP8GPU_ERR_LOGIC, "hash: bad frame id");
+    if (!cmp_scratch_) CU(cudaMalloc(&cmp_scratch_, 512));
+    d = reinterpret_cast<unsigned long long*>(cmp_scratch_ + 64 + 8 * lane);
+    if (int rc = wait_for(frames_[id], lane, s)) return rc;
+    CU(cudaMemsetAsync(d, 0, sizeof(unsigned long long), s));
+    if (int e = launch_hash(frames_[id].dev, g_, d, s)) return cuda_fail((cudaError_t)e, "hash");
+    launches_++;
+    if (int rc = touch(frames_[id], lane)) return rc;
+  }
+  unsigned long long h = 0;
+  CU(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  *out = h;
   return VP8GPU_OK;
 }
 

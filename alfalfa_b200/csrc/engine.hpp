@@ -49,6 +49,7 @@ class Engine {
   int frame_download_display(int id, int lane, uint8_t* dst, size_t dst_size, bool wait);
   int frame_clear(int id, int lane);  // all-zero raster (initial References)
   int frames_equal(int a, int b, int lane, int* equal);
+  int frame_hash(int id, int lane, uint64_t* out);
 
   // decode n frames in one set of launches on `lane`; host arrays must stay valid until the
   // returned event (*consumed, optional) has fired (pinned) or are consumed on return (pageable)

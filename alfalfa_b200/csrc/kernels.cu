@@ -964,6 +964,37 @@ __global__ void k_compare(const uint8_t* __restrict__ a, const uint8_t* __restri
   if (diff) atomicOr(flag, 1);
 }
 
+// ================================================================================================
+// k_hash: a 64-bit content hash of the visible pixels of a raster (HashCachedRaster::hash,
+// raster_handle.hh:60-75, is the reference's analogue; the value is ours, not boost's).  Position
+// dependent, order independent in evaluation: sum over 32-bit words of mix(word, plane row, index).
+// ================================================================================================
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdull;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ull;
+  x ^= x >> 33;
+  return x;
+}
+__global__ void k_hash(const uint8_t* __restrict__ a, Geom g, unsigned long long* out) {
+  const int words_y = g.W / 4, words_c = g.W / 8;
+  const int rows_total = g.H + g.H;
+  unsigned long long acc = 0;
+  for (int r = blockIdx.x; r < rows_total; r += gridDim.x) {
+    size_t off;
+    int nw;
+    if (r < g.H) off = (size_t)r * g.y_pitch, nw = words_y;
+    else if (r < g.H + g.H / 2) off = g.u_off + (size_t)(r - g.H) * g.c_pitch, nw = words_c;
+    else off = g.v_off + (size_t)(r - g.H - g.H / 2) * g.c_pitch, nw = words_c;
+    const uint32_t* pa = reinterpret_cast<const uint32_t*>(a + off);
+    for (int i = threadIdx.x; i < nw; i += blockDim.x)
+      acc += mix64(((unsigned long long)pa[i] << 32) ^ ((unsigned long long)r << 16) ^ (unsigned long long)i);
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -994,6 +1025,11 @@ extern "C" void vp8gpu_debug_profile(unsigned long long out[32], int reset) {
   }
 }
 #endif
+
+int launch_hash(const uint8_t* a, const Geom& g, unsigned long long* d_out, void* stream) {
+  k_hash<<<296, 128, 0, static_cast<cudaStream_t>(stream)>>>(a, g, d_out);
+  return (int)cudaGetLastError();
+}
 
 int launch_compare(const uint8_t* a, const uint8_t* b, const Geom& g, int* d_flag, void* stream) {
   k_compare<<<296, 128, 0, static_cast<cudaStream_t>(stream)>>>(a, b, g, d_flag);

@@ -93,6 +93,13 @@ class RasterHandle:
         check(c.L.vp8gpu_frame_upload(c.h, self.id, y.ctypes.data, y.shape[1], u.ctypes.data, v.ctypes.data,
                                       u.shape[1]), c.h, "frame_upload")
 
+    def hash(self):
+        """RasterHandle::hash(): 64-bit content hash computed on the device"""
+        c = self.ctx
+        h = C.c_uint64(0)
+        check(c.L.vp8gpu_frame_hash(c.h, self.id, C.byref(h)), c.h, "frame_hash")
+        return int(h.value)
+
     def display_bytes(self):
         """BaseRaster::dump (util/raster.cc:85-114)"""
         c = self.ctx

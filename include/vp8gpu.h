@@ -150,6 +150,9 @@ int vp8gpu_frame_download_display(vp8gpu_ctx* ctx, vp8gpu_frame_id id, uint8_t* 
 /* Same copy, asynchronous: queued behind the frame's producer; `dst` should be pinned
  * (vp8gpu_host_alloc).  vp8gpu_ctx_sync waits for everything queued so far. */
 int vp8gpu_frame_download_display_async(vp8gpu_ctx* ctx, vp8gpu_frame_id id, uint8_t* dst, size_t dst_size);
+/* RasterHandle::hash() (raster_handle.hh:60-75): 64-bit content hash of the MB-aligned pixels,
+ * computed on the device (our own function, not boost::hash_range). Blocks until decoded. */
+int vp8gpu_frame_hash(vp8gpu_ctx* ctx, vp8gpu_frame_id id, uint64_t* out);
 int vp8gpu_ctx_sync(vp8gpu_ctx* ctx);
 int vp8gpu_host_alloc(void** out, size_t bytes); /* pinned host memory */
 void vp8gpu_host_free(void* p);

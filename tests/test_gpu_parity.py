@@ -197,3 +197,27 @@ def test_many_independent_720p_streams_in_one_batch():
         assert all(np.array_equal(g, w_) for g, w_ in zip(out.planes(), want))
         out.release()
     ctx.close()
+
+
+def test_device_hash_tracks_content_and_references():
+    """RasterHandle::hash analogue: equal rasters hash equal, different ones differ; the three
+    references of two decoders fed the same frames hash identically (multi-GPU correctness check)."""
+    from alfalfa_b200 import Context, Decoder
+    data = _read("2a4c049c2f8e3a19ee39ffd7074cecd68006a101")
+    w, h, frames = O.read_ivf(data)
+    ctx = Context(w, h, max_frames=32)
+    a, b = Decoder(ctx), Decoder(ctx)
+    hashes = []
+    for f in frames[:6]:
+        ra, rb = a.get_frame_output(f)[1], b.get_frame_output(f)[1]
+        assert ra.hash() == rb.hash()
+        hashes.append(ra.hash())
+        ra.release()
+        rb.release()
+    assert len(set(hashes)) == len(hashes)
+    for x, y in zip(a.get_references(), b.get_references()):
+        assert x.hash() == y.hash()
+        x.release()
+        y.release()
+    del a, b
+    ctx.close()
