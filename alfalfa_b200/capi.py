@@ -49,6 +49,12 @@ class FrameDesc(C.Structure):
                 ("copy_to_alternate", C.c_uint8), ("pad1", C.c_uint8 * 3)]
 
 
+class EncodeHeader(C.Structure):
+    _fields_ = [("width", C.c_uint16), ("height", C.c_uint16), ("key_frame", C.c_uint8), ("show_frame", C.c_uint8),
+                ("y_ac_qi", C.c_uint8), ("loop_filter_level", C.c_uint8), ("sharpness", C.c_uint8),
+                ("optimize_token_probs", C.c_uint8), ("pad", C.c_uint8 * 2)]
+
+
 class Job(C.Structure):
     _fields_ = [("desc", C.POINTER(FrameDesc)), ("mbs", C.c_void_p), ("tokens", C.c_void_p), ("split", C.c_void_p),
                 ("refs", C.c_int32 * 3), ("out", C.c_int32)]
@@ -108,6 +114,7 @@ SYMBOLS = {
     "vp8gpu_decoder_references": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
     "vp8gpu_decoder_lane": (C.c_int, [_vp]),
     "vp8gpu_decoder_equal": (C.c_int, [_vp, _vp, C.POINTER(C.c_int)]),
+    "vp8gpu_serialize_frame": (C.c_int, [C.POINTER(EncodeHeader), _vp, _vp, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "vp8gpu_decode_ivf_stats": (None, [_vp, C.POINTER(C.c_double)]),
     "vp8gpu_decode_ivf": (C.c_int, [_vp, C.c_char_p, C.c_size_t, C.c_int, _u8p, C.c_size_t, C.POINTER(C.c_uint32),
                                     C.POINTER(C.c_uint32)]),

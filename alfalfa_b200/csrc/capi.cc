@@ -18,6 +18,7 @@
 #include "../../include/vp8gpu.h"
 #include "engine.hpp"
 #include "parser.h"
+#include "serializer.h"
 
 using vp8::Engine;
 using vp8::HostJob;
@@ -127,6 +128,25 @@ void vp8gpu_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
 uint64_t vp8gpu_launch_count(const vp8gpu_ctx* ctx) { return ctx->engine->launches(); }
+int vp8gpu_serialize_frame(const vp8gpu_encode_header* hdr, const vp8gpu_mb* mbs, const vp8gpu_token* tokens,
+                           const vp8gpu_split_mvs* split, uint8_t* out, size_t cap, size_t* size) {
+  if (!hdr || !mbs || !size) return VP8GPU_ERR_LOGIC;
+  vp8::EncodeHeader h;
+  h.key_frame = hdr->key_frame;
+  h.show_frame = hdr->show_frame;
+  h.width = hdr->width;
+  h.height = hdr->height;
+  h.y_ac_qi = hdr->y_ac_qi;
+  h.loop_filter_level = hdr->loop_filter_level;
+  h.sharpness = hdr->sharpness;
+  h.optimize_token_probs = hdr->optimize_token_probs;
+  const std::vector<uint8_t> bytes = vp8::serialize_frame(h, mbs, tokens, split);
+  if (bytes.empty()) return VP8GPU_ERR_UNSUPPORTED;
+  *size = bytes.size();
+  if (!out || cap < bytes.size()) return VP8GPU_ERR_NOMEM;
+  memcpy(out, bytes.data(), bytes.size());
+  return VP8GPU_OK;
+}
 void vp8gpu_decode_ivf_stats(const vp8gpu_ctx* ctx, double out[8]) { memcpy(out, ctx->stats, sizeof(ctx->stats)); }
 
 // =============================================================================================

@@ -1,0 +1,559 @@
+// serializer.cc -- see serializer.h.  Host-only C++.
+//
+// The syntax written here is the exact inverse of what parser.cc reads (and therefore of the
+// reference's decoder/*.cc); the reference's own writer is encoder/serializer.cc:388-829,
+// encode_tree.cc and bool_encoder.hh.  Every macroblock element is written with the context the
+// decoder will have when it reads it.
+#include "serializer.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+#include "vp8_tables.h"
+
+namespace vp8 {
+
+// ------------------------------------------------------------------------------------------
+// BoolWriter: RFC 6386 section 7.3
+// ------------------------------------------------------------------------------------------
+void BoolWriter::add_one() {
+  size_t i = out_.size();
+  while (i > 0 && out_[i - 1] == 255) out_[--i] = 0;
+  if (i > 0) ++out_[i - 1];
+}
+void BoolWriter::put(int bit, int prob) {
+  const uint32_t split = 1 + (((range_ - 1) * static_cast<uint32_t>(prob)) >> 8);
+  if (bit) {
+    bottom_ += split;
+    range_ -= split;
+  } else {
+    range_ = split;
+  }
+  while (range_ < 128) {
+    range_ <<= 1;
+    if (bottom_ & (1u << 31)) add_one();
+    bottom_ <<= 1;
+    if (!--bit_count_) {
+      out_.push_back(static_cast<uint8_t>(bottom_ >> 24));
+      bottom_ &= (1u << 24) - 1;
+      bit_count_ = 8;
+    }
+  }
+}
+void BoolWriter::literal(int value, int width) {
+  for (int i = width - 1; i >= 0; i--) put((value >> i) & 1, 128);
+}
+std::vector<uint8_t> BoolWriter::finish() {
+  // pad like libvpx's vp8_stop_encode (and the reference, bool_encoder.hh:78-82): 32 zero bits
+  for (int i = 0; i < 32; i++) put(0, 128);
+  return std::move(out_);
+}
+
+namespace {
+
+// trees: same arrays the decoder walks (modemv_data.cc:186-250)
+const int8_t kKfYModeTree[8] = {-VP8GPU_B_PRED, 2, 4, 6, -VP8GPU_DC_PRED, -VP8GPU_V_PRED, -VP8GPU_H_PRED, -VP8GPU_TM_PRED};
+const int8_t kYModeTree[8] = {-VP8GPU_DC_PRED, 2, 4, 6, -VP8GPU_V_PRED, -VP8GPU_H_PRED, -VP8GPU_TM_PRED, -VP8GPU_B_PRED};
+const int8_t kUvModeTree[6] = {-VP8GPU_DC_PRED, 2, -VP8GPU_V_PRED, 4, -VP8GPU_H_PRED, -VP8GPU_TM_PRED};
+const int8_t kBModeTree[18] = {-VP8GPU_B_DC_PRED, 2,  -VP8GPU_B_TM_PRED, 4,  -VP8GPU_B_VE_PRED, 6,
+                               8,                 12, -VP8GPU_B_HE_PRED, 10, -VP8GPU_B_RD_PRED, -VP8GPU_B_VR_PRED,
+                               -VP8GPU_B_LD_PRED, 14, -VP8GPU_B_VL_PRED, 16, -VP8GPU_B_HD_PRED, -VP8GPU_B_HU_PRED};
+const int8_t kSmallMvTree[14] = {2, 8, 4, 6, -0, -1, -2, -3, 10, 12, -4, -5, -6, -7};
+const int8_t kMvRefTree[8] = {-VP8GPU_ZEROMV, 2, -VP8GPU_NEARESTMV, 4, -VP8GPU_NEARMV, 6, -VP8GPU_NEWMV, -VP8GPU_SPLITMV};
+enum { kSubLeft = 0, kSubAbove = 1, kSubZero = 2, kSubNew = 3 };
+const int8_t kSubMvTree[6] = {-kSubLeft, 2, -kSubAbove, 4, -kSubZero, -kSubNew};
+const int8_t kSplitTree[6] = {-3, 2, -2, 4, -0, -1};
+const uint16_t kSplitFill[4][16] = {{0x00FF, 0xFF00},
+                                    {0x3333, 0xCCCC},
+                                    {0x0033, 0x00CC, 0x3300, 0xCC00},
+                                    {0x0001, 0x0002, 0x0004, 0x0008, 0x0010, 0x0020, 0x0040, 0x0080, 0x0100, 0x0200,
+                                     0x0400, 0x0800, 0x1000, 0x2000, 0x4000, 0x8000}};
+const uint8_t kSplitCount[4] = {2, 2, 4, 16};
+const uint8_t kBand[16] = {0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7};
+const uint8_t kZigzag[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
+
+// write `value` with the tree the decoder walks (inverse of tree.cc:35-57)
+bool write_tree_from(BoolWriter& bw, const int8_t* nodes, const uint8_t* probs, int value, int i) {
+  for (int b = 0; b < 2; b++) {
+    const int n = nodes[i + b];
+    if (n <= 0) {
+      if (-n == value) {
+        bw.put(b, probs[i >> 1]);
+        return true;
+      }
+    } else {
+      // look ahead without writing: find out whether the value is below this child
+      struct Probe {
+        static bool has(const int8_t* nd, int at, int v) {
+          for (int k = 0; k < 2; k++) {
+            const int m = nd[at + k];
+            if (m <= 0 ? -m == v : has(nd, m, v)) return true;
+          }
+          return false;
+        }
+      };
+      if (Probe::has(nodes, n, value)) {
+        bw.put(b, probs[i >> 1]);
+        return write_tree_from(bw, nodes, probs, value, n);
+      }
+    }
+  }
+  return false;
+}
+inline void write_tree(BoolWriter& bw, const int8_t* nodes, const uint8_t* probs, int value) {
+  write_tree_from(bw, nodes, probs, value, 0);
+}
+
+// inverse of MotionVector::read_component (macroblock.cc:198-229); v in 1/8 pel, luma values even
+void write_mv_component(BoolWriter& bw, int v, const uint8_t* p) {
+  const int a = abs(v) >> 1;
+  if (a < 8) {
+    bw.put(0, p[0]);
+    write_tree(bw, kSmallMvTree, p + 2, a);
+  } else {
+    bw.put(1, p[0]);
+    for (int i = 0; i < 3; i++) bw.put((a >> i) & 1, p[9 + i]);
+    for (int i = 9; i > 3; i--) bw.put((a >> i) & 1, p[9 + i]);
+    if (a & 0xFFF0) bw.put((a >> 3) & 1, p[9 + 3]);
+  }
+  if (a) bw.put(v < 0, p[1]);
+}
+
+struct Mv {
+  int x, y;
+};
+struct MbInfo {
+  uint8_t inter = 0, y_mode = 0;
+  uint8_t bm[16] = {0};
+  int16_t mv[16][2] = {{0, 0}};
+};
+struct Bounds {
+  int left, right, top, bottom;
+};
+inline Mv clamp_mv(Mv m, const Bounds& b) {
+  m.x = m.x < b.left ? b.left : (m.x > b.right ? b.right : m.x);
+  m.y = m.y < b.top ? b.top : (m.y > b.bottom ? b.bottom : m.y);
+  return m;
+}
+// Scorer (scorer.hh:35-78); sign bias is never used by this writer (LAST only)
+struct Census {
+  int score[4] = {0, 0, 0, 0};
+  Mv mv[4] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+  int index = 0, split_score = 0;
+  void add(int weight, const MbInfo* nb) {
+    if (!nb || !nb->inter) return;
+    const int x = nb->mv[15][0], y = nb->mv[15][1];
+    if ((x | y) == 0) {
+      score[0] += weight;
+    } else {
+      if (x != mv[index].x || y != mv[index].y) {
+        index++;
+        mv[index].x = x;
+        mv[index].y = y;
+      }
+      score[index] += weight;
+    }
+    if (nb->y_mode == VP8GPU_SPLITMV) split_score += weight;
+  }
+  void finish() {
+    if (score[3] && mv[index].x == mv[1].x && mv[index].y == mv[1].y) score[1] += score[3];
+    if (score[2] > score[1]) {
+      const int s = score[1];
+      score[1] = score[2];
+      score[2] = s;
+      const Mv m = mv[1];
+      mv[1] = mv[2];
+      mv[2] = m;
+    }
+    if (score[1] >= score[0]) mv[0] = mv[1];
+  }
+};
+inline uint8_t implied_bmode(int y_mode) {
+  static const uint8_t t[4] = {VP8GPU_B_DC_PRED, VP8GPU_B_VE_PRED, VP8GPU_B_HE_PRED, VP8GPU_B_TM_PRED};
+  return t[y_mode];
+}
+
+// one arithmetic-coded decision of the token partition, recorded first so that branch statistics
+// can choose the frame's probabilities before anything is written
+struct TokenBit {
+  uint16_t slot;  // index into the 1056-entry coefficient probability table, or 0xFFFF
+  uint8_t fixed;  // probability when slot == 0xFFFF
+  uint8_t bit;
+};
+
+struct TokenRecorder {
+  std::vector<TokenBit> bits;
+  void coef(int slot, int bit) { bits.push_back({static_cast<uint16_t>(slot), 0, static_cast<uint8_t>(bit)}); }
+  void fixed(int prob, int bit) { bits.push_back({0xFFFF, static_cast<uint8_t>(prob), static_cast<uint8_t>(bit)}); }
+};
+
+void put_extra(TokenRecorder& t, int v, const uint8_t* probs, int n) {
+  for (int i = n - 1; i >= 0; i--) t.fixed(probs[n - 1 - i], (v >> i) & 1);
+}
+
+// inverse of Block::parse_tokens (tokens.cc:50-135); returns has_nonzero
+int record_block(TokenRecorder& t, const int16_t* coefs /* raster order */, int type, int ctx, int first) {
+  static const uint8_t cat2[2] = {165, 145}, cat3[3] = {173, 148, 140}, cat4[4] = {176, 155, 140, 135},
+                       cat5[5] = {180, 157, 141, 134, 130},
+                       cat6[11] = {254, 254, 243, 230, 196, 177, 153, 140, 133, 130, 129};
+  int last = -1;
+  for (int i = first; i < 16; i++)
+    if (coefs[kZigzag[i]]) last = i;
+  bool prev_zero = false;
+  for (int i = first; i <= last; i++) {
+    const int base = ((type * 8 + kBand[i]) * 3 + ctx) * 11;
+    const int v = coefs[kZigzag[i]];
+    const int a = abs(v);
+    if (!prev_zero) t.coef(base + 0, 1);  // not end of block
+    if (a == 0) {
+      t.coef(base + 1, 0);
+      prev_zero = true;
+      ctx = 0;
+      continue;
+    }
+    prev_zero = false;
+    t.coef(base + 1, 1);
+    if (a == 1) {
+      t.coef(base + 2, 0);
+      ctx = 1;
+    } else {
+      ctx = 2;
+      t.coef(base + 2, 1);
+      if (a <= 4) {
+        t.coef(base + 3, 0);
+        if (a == 2) {
+          t.coef(base + 4, 0);
+        } else {
+          t.coef(base + 4, 1);
+          t.coef(base + 5, a == 4);
+        }
+      } else {
+        t.coef(base + 3, 1);
+        if (a <= 10) {
+          t.coef(base + 6, 0);
+          if (a <= 6) {
+            t.coef(base + 7, 0);
+            t.fixed(159, a - 5);
+          } else {
+            t.coef(base + 7, 1);
+            put_extra(t, a - 7, cat2, 2);
+          }
+        } else {
+          t.coef(base + 6, 1);
+          if (a <= 34) {
+            t.coef(base + 8, 0);
+            if (a <= 18) {
+              t.coef(base + 9, 0);
+              put_extra(t, a - 11, cat3, 3);
+            } else {
+              t.coef(base + 9, 1);
+              put_extra(t, a - 19, cat4, 4);
+            }
+          } else {
+            t.coef(base + 8, 1);
+            if (a <= 66) {
+              t.coef(base + 10, 0);
+              put_extra(t, a - 35, cat5, 5);
+            } else {
+              t.coef(base + 10, 1);
+              put_extra(t, a - 67, cat6, 11);
+            }
+          }
+        }
+      }
+    }
+    t.fixed(128, v < 0);
+  }
+  if (last < 15) {
+    // end of block -- impossible to signal right after a zero token, but `last` is non-zero
+    const int i = last + 1 < first ? first : last + 1;
+    const int base = ((type * 8 + kBand[i]) * 3 + ctx) * 11;
+    t.coef(base + 0, 0);
+  }
+  return last >= first;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// serialize_frame
+// ------------------------------------------------------------------------------------------
+std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs, const vp8gpu_token* tokens,
+                                     const vp8gpu_split_mvs* split) {
+  const int cols = (h.width + 15) / 16, rows = (h.height + 15) / 16;
+  const size_t n_mbs = static_cast<size_t>(cols) * rows;
+  std::vector<MbInfo> info(n_mbs);
+
+  // ---- pass 1: token partition decisions + per-macroblock skip flags ----
+  TokenRecorder rec;
+  rec.bits.reserve(n_mbs * 64);
+  std::vector<uint8_t> above_nz(static_cast<size_t>(cols) * 9, 0);
+  std::vector<uint8_t> skip(n_mbs, 0);
+  size_t n_skipped = 0;
+  for (int row = 0; row < rows; row++) {
+    uint8_t left_nz[9] = {0};
+    for (int col = 0; col < cols; col++) {
+      const size_t idx = static_cast<size_t>(row) * cols + col;
+      const vp8gpu_mb& mb = mbs[idx];
+      uint8_t* a = &above_nz[static_cast<size_t>(col) * 9];
+      const bool has_y2 = mb.y_mode != VP8GPU_B_PRED && mb.y_mode != VP8GPU_SPLITMV;
+      if (mb.tok_cnt == 0) {
+        skip[idx] = 1;
+        n_skipped++;
+        memset(a, 0, 8);
+        memset(left_nz, 0, 8);
+        if (has_y2) a[8] = left_nz[8] = 0;
+        continue;
+      }
+      int16_t c[25][16];
+      memset(c, 0, sizeof(c));
+      for (unsigned t = 0; t < mb.tok_cnt; t++) {
+        const uint32_t tk = tokens[mb.tok_off + t];
+        c[(tk >> 20) & 31][(tk >> 16) & 15] = static_cast<int16_t>(tk & 0xFFFF);
+      }
+      if (has_y2) a[8] = left_nz[8] = static_cast<uint8_t>(record_block(rec, c[24], 1, a[8] + left_nz[8], 0));
+      const int ytype = has_y2 ? 0 : 3, yfirst = has_y2 ? 1 : 0;
+      for (int i = 0; i < 16; i++) {
+        const int bx = i & 3, by = i >> 2;
+        a[bx] = left_nz[by] = static_cast<uint8_t>(record_block(rec, c[i], ytype, a[bx] + left_nz[by], yfirst));
+      }
+      for (int pl = 0; pl < 2; pl++)
+        for (int i = 0; i < 4; i++) {
+          const int bx = 4 + 2 * pl + (i & 1), by = 4 + 2 * pl + (i >> 1);
+          a[bx] = left_nz[by] = static_cast<uint8_t>(record_block(rec, c[16 + 4 * pl + i], 2, a[bx] + left_nz[by], 0));
+        }
+    }
+  }
+
+  // ---- frame probabilities ----
+  uint8_t coef_probs[1056];
+  memcpy(coef_probs, k_coef_default_probs, sizeof(coef_probs));
+  std::vector<uint8_t> updated(1056, 0);
+  if (h.optimize_token_probs) {
+    std::vector<uint32_t> cnt(2 * 1056, 0);
+    for (const TokenBit& b : rec.bits)
+      if (b.slot != 0xFFFF) cnt[2 * b.slot + b.bit]++;
+    for (int i = 0; i < 1056; i++) {
+      const uint32_t total = cnt[2 * i] + cnt[2 * i + 1];
+      if (!total) continue;
+      int p = static_cast<int>((static_cast<uint64_t>(cnt[2 * i]) * 256 + total / 2) / total);
+      p = p < 1 ? 1 : (p > 255 ? 255 : p);
+      // update only when the saving on the coded bits pays for the 8 + 1 bit update (rough cost model)
+      const int old = coef_probs[i];
+      if (abs(p - old) >= 8 && total >= 32) {
+        coef_probs[i] = static_cast<uint8_t>(p);
+        updated[i] = 1;
+      }
+    }
+  }
+  int skip_prob = static_cast<int>(((n_mbs - n_skipped) * 256 + n_mbs / 2) / n_mbs);  // P(not skipped)
+  skip_prob = skip_prob < 1 ? 1 : (skip_prob > 255 ? 255 : skip_prob);
+  size_t n_inter = 0;
+  for (size_t i = 0; i < n_mbs; i++) n_inter += mbs[i].ref_frame != VP8GPU_REF_CURRENT;
+  int prob_inter = static_cast<int>(((n_mbs - n_inter) * 256 + n_mbs / 2) / n_mbs);  // P(intra) = P(bit 0)
+  prob_inter = prob_inter < 1 ? 1 : (prob_inter > 255 ? 255 : prob_inter);
+
+  // ---- first partition: frame header ----
+  BoolWriter bw;
+  if (h.key_frame) {
+    bw.put(0);  // color_space
+    bw.put(0);  // clamping_type
+  }
+  bw.put(0);  // segmentation_enabled
+  bw.put(0);  // filter_type: normal
+  bw.literal(h.loop_filter_level, 6);
+  bw.literal(h.sharpness, 3);
+  bw.put(0);  // mode_ref_lf_delta_enabled
+  bw.literal(0, 2);  // one DCT partition
+  bw.literal(h.y_ac_qi, 7);
+  for (int i = 0; i < 5; i++) bw.put(0);  // no quantizer deltas
+  // refresh_entropy_probs = 0: probability updates are valid for this frame only, so the writer
+  // needs no memory of earlier frames (every frame is coded relative to the default tables)
+  const int refresh_entropy = h.optimize_token_probs ? 0 : 1;
+  if (h.key_frame) {
+    bw.put(refresh_entropy);
+  } else {
+    bw.put(0);  // refresh_golden_frame
+    bw.put(0);  // refresh_alternate_frame
+    bw.literal(0, 2);  // copy_buffer_to_golden: none
+    bw.literal(0, 2);  // copy_buffer_to_alternate: none
+    bw.put(0);  // sign_bias_golden
+    bw.put(0);  // sign_bias_alternate
+    bw.put(refresh_entropy);
+    bw.put(1);  // refresh_last
+  }
+  for (int i = 0; i < 1056; i++) {
+    bw.put(updated[i], k_coef_update_probs[i]);
+    if (updated[i]) bw.literal(coef_probs[i], 8);
+  }
+  bw.put(1);  // mb_no_coeff_skip
+  bw.literal(skip_prob, 8);
+  if (!h.key_frame) {
+    bw.literal(prob_inter, 8);
+    bw.literal(255, 8);  // prob_references_last: always LAST
+    bw.literal(128, 8);  // prob_references_golden
+    bw.put(0);           // intra_16x16_prob unchanged
+    bw.put(0);           // intra_chroma_prob unchanged
+    for (int i = 0; i < 38; i++) bw.put(0, k_mv_update_probs[i]);  // motion vector probabilities unchanged
+  }
+  const uint8_t(*mv_probs)[19] = reinterpret_cast<const uint8_t(*)[19]>(k_mv_default_probs);
+
+  // ---- first partition: macroblock headers (macroblock.cc:44-71, 84-111, 343-456 inverted) ----
+  for (int row = 0; row < rows; row++) {
+    for (int col = 0; col < cols; col++) {
+      const size_t idx = static_cast<size_t>(row) * cols + col;
+      const vp8gpu_mb& mb = mbs[idx];
+      MbInfo& me = info[idx];
+      const MbInfo* above = row > 0 ? &info[idx - cols] : nullptr;
+      const MbInfo* left = col > 0 ? &info[idx - 1] : nullptr;
+      const MbInfo* above_left = (row > 0 && col > 0) ? &info[idx - cols - 1] : nullptr;
+      bw.put(skip[idx], skip_prob);
+      me.y_mode = mb.y_mode;
+      if (mb.ref_frame == VP8GPU_REF_CURRENT) {
+        if (!h.key_frame) bw.put(0, prob_inter);
+        if (h.key_frame) {
+          write_tree(bw, kKfYModeTree, k_kf_ymode_probs, mb.y_mode);
+          for (int i = 0; i < 16; i++) {
+            if (mb.y_mode == VP8GPU_B_PRED) {
+              const int m = static_cast<int>((mb.b_modes >> (4 * i)) & 15);
+              const int am = i >= 4 ? me.bm[i - 4] : (above ? above->bm[12 + (i & 3)] : VP8GPU_B_DC_PRED);
+              const int lm = (i & 3) ? me.bm[i - 1] : (left ? left->bm[((i >> 2) & 3) * 4 + 3] : VP8GPU_B_DC_PRED);
+              write_tree(bw, kBModeTree, k_kf_bmode_probs + (am * 10 + lm) * 9, m);
+              me.bm[i] = static_cast<uint8_t>(m);
+            } else {
+              me.bm[i] = implied_bmode(mb.y_mode);
+            }
+          }
+          write_tree(bw, kUvModeTree, k_kf_uvmode_probs, mb.uv_mode);
+        } else {
+          write_tree(bw, kYModeTree, k_ymode_default_probs, mb.y_mode);
+          if (mb.y_mode == VP8GPU_B_PRED)
+            for (int i = 0; i < 16; i++) write_tree(bw, kBModeTree, k_bmode_probs, static_cast<int>((mb.b_modes >> (4 * i)) & 15));
+          write_tree(bw, kUvModeTree, k_uvmode_default_probs, mb.uv_mode);
+        }
+        continue;
+      }
+      if (h.key_frame || mb.ref_frame != VP8GPU_REF_LAST) return {};
+      me.inter = 1;
+      bw.put(1, prob_inter);
+      bw.put(0, 255);  // reference = LAST
+      Census census;
+      census.add(2, above);
+      census.add(2, left);
+      census.add(1, above_left);
+      census.finish();
+      const uint8_t ref_probs[4] = {k_mv_count_probs[census.score[0] * 4 + 0], k_mv_count_probs[census.score[1] * 4 + 1],
+                                    k_mv_count_probs[census.score[2] * 4 + 2], k_mv_count_probs[census.split_score * 4 + 3]};
+      Bounds b;
+      b.left = -((col * 16) << 3) - 128;
+      b.right = (((cols - 1 - col) * 16) << 3) + 128;
+      b.top = -((row * 16) << 3) - 128;
+      b.bottom = (((rows - 1 - row) * 16) << 3) + 128;
+      const Mv nearest = clamp_mv(census.mv[1], b), near = clamp_mv(census.mv[2], b), best = clamp_mv(census.mv[0], b);
+      if (mb.y_mode == VP8GPU_SPLITMV) {
+        const int16_t(*mv)[2] = split[mb.split_idx].mv;
+        memcpy(me.mv, mv, sizeof(me.mv));
+        int layout = 3;
+        for (int cand = 0; cand < 3; cand++) {
+          bool ok = true;
+          for (int part = 0; part < kSplitCount[cand] && ok; part++) {
+            const unsigned members = kSplitFill[cand][part];
+            const int first = __builtin_ctz(members);
+            for (unsigned m = members; m; m &= m - 1) {
+              const int i = __builtin_ctz(m);
+              if (mv[i][0] != mv[first][0] || mv[i][1] != mv[first][1]) ok = false;
+            }
+          }
+          if (ok) {
+            layout = cand;
+            break;
+          }
+        }
+        write_tree(bw, kMvRefTree, ref_probs, VP8GPU_SPLITMV);
+        write_tree(bw, kSplitTree, k_split_probs, layout);
+        int16_t done[16][2];  // vectors as the decoder knows them so far
+        memset(done, 0, sizeof(done));
+        for (int part = 0; part < kSplitCount[layout]; part++) {
+          const unsigned members = kSplitFill[layout][part];
+          const int first = __builtin_ctz(members);
+          const int bx = first & 3, by = first >> 2;
+          const int lx = bx ? done[first - 1][0] : (left ? left->mv[by * 4 + 3][0] : 0);
+          const int ly = bx ? done[first - 1][1] : (left ? left->mv[by * 4 + 3][1] : 0);
+          const int ax = by ? done[first - 4][0] : (above ? above->mv[12 + bx][0] : 0);
+          const int ay = by ? done[first - 4][1] : (above ? above->mv[12 + bx][1] : 0);
+          const bool lz = (lx | ly) == 0, az = (ax | ay) == 0, same = lx == ax && ly == ay;
+          int ctx = 0;
+          if (same && lz) ctx = 4;
+          else if (same) ctx = 3;
+          else if (az) ctx = 2;
+          else if (lz) ctx = 1;
+          const int vx = mv[first][0], vy = mv[first][1];
+          const uint8_t* sp = k_submv_ref_probs + ctx * 3;
+          if (vx == lx && vy == ly) write_tree(bw, kSubMvTree, sp, kSubLeft);
+          else if (vx == ax && vy == ay) write_tree(bw, kSubMvTree, sp, kSubAbove);
+          else if ((vx | vy) == 0) write_tree(bw, kSubMvTree, sp, kSubZero);
+          else {
+            write_tree(bw, kSubMvTree, sp, kSubNew);
+            const int dx = vx - best.x, dy = vy - best.y;
+            if (abs(dx) > 2046 || abs(dy) > 2046) return {};
+            write_mv_component(bw, dy, mv_probs[0]);
+            write_mv_component(bw, dx, mv_probs[1]);
+          }
+          for (unsigned m = members; m; m &= m - 1) {
+            const int i = __builtin_ctz(m);
+            done[i][0] = static_cast<int16_t>(vx);
+            done[i][1] = static_cast<int16_t>(vy);
+          }
+        }
+      } else {
+        // unsplit: pick the cheapest representation that decodes to exactly (mv_x, mv_y)
+        const int vx = mb.mv_x, vy = mb.mv_y;
+        int mode;
+        if ((vx | vy) == 0) mode = VP8GPU_ZEROMV;
+        else if (vx == nearest.x && vy == nearest.y) mode = VP8GPU_NEARESTMV;
+        else if (vx == near.x && vy == near.y) mode = VP8GPU_NEARMV;
+        else mode = VP8GPU_NEWMV;
+        me.y_mode = static_cast<uint8_t>(mode);
+        write_tree(bw, kMvRefTree, ref_probs, mode);
+        if (mode == VP8GPU_NEWMV) {
+          const int dx = vx - best.x, dy = vy - best.y;
+          if (abs(dx) > 2046 || abs(dy) > 2046 || (dx & 1) || (dy & 1)) return {};
+          write_mv_component(bw, dy, mv_probs[0]);
+          write_mv_component(bw, dx, mv_probs[1]);
+        }
+        for (int i = 0; i < 16; i++) {
+          me.mv[i][0] = static_cast<int16_t>(vx);
+          me.mv[i][1] = static_cast<int16_t>(vy);
+        }
+      }
+    }
+  }
+  const std::vector<uint8_t> first = bw.finish();
+
+  // ---- token partition ----
+  BoolWriter tw;
+  for (const TokenBit& b : rec.bits) tw.put(b.bit, b.slot == 0xFFFF ? b.fixed : coef_probs[b.slot]);
+  const std::vector<uint8_t> second = tw.finish();
+
+  // ---- frame tag (uncompressed_chunk.cc:49-77 inverted) ----
+  std::vector<uint8_t> out;
+  const uint32_t tag = (h.key_frame ? 0u : 1u) | (0u << 1) | (static_cast<uint32_t>(h.show_frame) << 4) |
+                       (static_cast<uint32_t>(first.size()) << 5);
+  out.push_back(tag & 0xFF);
+  out.push_back((tag >> 8) & 0xFF);
+  out.push_back((tag >> 16) & 0xFF);
+  if (h.key_frame) {
+    out.push_back(0x9d);
+    out.push_back(0x01);
+    out.push_back(0x2a);
+    out.push_back(h.width & 0xFF);
+    out.push_back((h.width >> 8) & 0x3F);
+    out.push_back(h.height & 0xFF);
+    out.push_back((h.height >> 8) & 0x3F);
+  }
+  out.insert(out.end(), first.begin(), first.end());
+  out.insert(out.end(), second.begin(), second.end());
+  return out;
+}
+
+}  // namespace vp8

@@ -265,6 +265,24 @@ int vp8gpu_decoder_equal(vp8gpu_decoder* a, vp8gpu_decoder* b, int* equal);
 int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threads, uint8_t* dst,
                       size_t dst_size, uint32_t* n_decoded, uint32_t* n_shown);
 
+/* ---- encoder side: bitstream writer (Frame::serialize, encoder/serializer.cc:388-829) ----
+ * Turns flat records (modes / vectors / quantised-coefficient tokens, as produced by the device
+ * encode kernels or by vp8gpu_parse_frame) into one compressed VP8 frame: frame tag, header, mode
+ * partition, one DCT partition.  Written subset: no segmentation, no loop-filter deltas, LAST
+ * reference only.  Returns VP8GPU_ERR_UNSUPPORTED if a record is outside that subset and
+ * VP8GPU_ERR_NOMEM if `cap` is too small (*size then holds the needed size). */
+typedef struct vp8gpu_encode_header {
+  uint16_t width, height;
+  uint8_t key_frame, show_frame;
+  uint8_t y_ac_qi;            /* 0..127, all quantiser deltas zero */
+  uint8_t loop_filter_level;  /* 0..63 */
+  uint8_t sharpness;          /* 0..7 */
+  uint8_t optimize_token_probs;
+  uint8_t pad[2];
+} vp8gpu_encode_header;
+int vp8gpu_serialize_frame(const vp8gpu_encode_header* hdr, const vp8gpu_mb* mbs, const vp8gpu_token* tokens,
+                           const vp8gpu_split_mvs* split, uint8_t* out, size_t cap, size_t* size);
+
 /* Host-side time accounting of the last vp8gpu_decode_ivf call, seconds summed over threads:
  * [0] parsing, [1] workers waiting for the dispatcher, [2] workers waiting for DMA, [3] dispatcher
  * in submit, [4] dispatcher queueing downloads, [5] dispatcher idle, [6] batches, [7] frames. */
