@@ -114,6 +114,13 @@ SYMBOLS = {
     "vp8gpu_decoder_references": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
     "vp8gpu_decoder_lane": (C.c_int, [_vp]),
     "vp8gpu_decoder_equal": (C.c_int, [_vp, _vp, C.POINTER(C.c_int)]),
+    "vp8gpu_encoder_create": (C.c_int, [_vp, _pp]),
+    "vp8gpu_encoder_destroy": (None, [_vp]),
+    "vp8gpu_encoder_encode_with_quantizer": (C.c_int, [_vp, _u8p, C.c_size_t, _u8p, _u8p, C.c_size_t, C.c_int, _u8p, C.c_size_t,
+                                                       C.POINTER(C.c_size_t)]),
+    "vp8gpu_encoder_encode_with_target_size": (C.c_int, [_vp, _u8p, C.c_size_t, _u8p, _u8p, C.c_size_t, C.c_size_t, _u8p,
+                                                         C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
+    "vp8gpu_encoder_reconstruction": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
     "vp8gpu_serialize_frame": (C.c_int, [C.POINTER(EncodeHeader), _vp, _vp, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "vp8gpu_decode_ivf_stats": (None, [_vp, C.POINTER(C.c_double)]),
     "vp8gpu_decode_ivf": (C.c_int, [_vp, C.c_char_p, C.c_size_t, C.c_int, _u8p, C.c_size_t, C.POINTER(C.c_uint32),

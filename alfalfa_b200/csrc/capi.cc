@@ -82,6 +82,10 @@ void count_mbs(vp8gpu_parsed* p) {
 // =============================================================================================
 extern "C" {
 
+// internal hooks for encoder.cu
+Engine* vp8gpu_ctx_engine(vp8gpu_ctx* ctx) { return ctx->engine; }
+int vp8gpu_ctx_next_lane(vp8gpu_ctx* ctx) { return ctx->next_lane.fetch_add(1) % vp8::kMaxLanes; }
+
 int vp8gpu_ctx_create(int device, int width, int height, int max_frames, vp8gpu_ctx** out) {
   if (!out) return VP8GPU_ERR_LOGIC;
   *out = nullptr;

@@ -35,10 +35,30 @@ struct DevJob {
   uint32_t pad2;
 };
 
+// One frame's ENCODE job (device pointers).  The encoder runs a motion search against the last
+// reconstructed frame, then one wavefront pass that decides modes, transforms, quantises,
+// emits tokens + macroblock records and reconstructs exactly what a decoder will reconstruct.
+struct EncJob {
+  const uint8_t* src;      // source raster (same layout as every other raster)
+  const uint8_t* ref;      // last reconstructed + loop-filtered frame; nullptr for key frames
+  uint8_t* out;            // reconstruction (before the loop filter, which runs afterwards in place)
+  vp8gpu_mb* mbs;          // [mb_cols * mb_rows] records written by the device
+  vp8gpu_token* tokens;    // token pool
+  uint32_t* tok_counter;   // tokens used so far (atomic)
+  uint32_t tok_cap;
+  int* mv;                 // [n_mbs][2] best motion vector per macroblock, 1/8 pel (inter frames)
+  uint32_t* sad;           // [n_mbs] luma SAD of that vector
+  int* progress;           // [mb_rows] wavefront counters (zeroed)
+  vp8gpu_quant q;
+  uint8_t key_frame, lf_level, pad[2];
+};
+
 // Kernel launchers (kernels.cu).  `stream` is a cudaStream_t passed as void* so this header
 // stays free of CUDA includes.  Return 0 or a cudaError_t value.
 int launch_inter(const DevJob* jobs, int njobs, const Geom& g, void* stream);
 int launch_intra(const DevJob* jobs, int njobs, const Geom& g, int* ticket, void* stream);
 int launch_loopfilter(const DevJob* jobs, int njobs, const Geom& g, int* ticket, void* stream);
+int launch_enc_motion(const EncJob* job, const Geom& g, void* stream);
+int launch_enc_mb(const EncJob* job, const Geom& g, int* ticket, void* stream);
 
 }  // namespace vp8

@@ -63,6 +63,12 @@ class Engine {
   int resident_run_timed(int lane, Resident* r, float ms[3]);
   void resident_free(Resident* r);
 
+  // for other device-side users of rasters (the encoder): raw pointer + stream-ordering hooks
+  uint8_t* frame_dev(int id) { return frames_[id].dev; }
+  int acquire_frames(int lane, const int* ids, int n);  // stream `lane` waits for other users
+  int mark_frames(int lane, const int* ids, int n);     // record that `lane` used them
+  void count_launches(int n) { launches_ += n; }
+
   int sync_all();
   int sync_lane(int lane);
   cudaStream_t stream(int lane) const { return lanes_[lane]; }

@@ -258,6 +258,9 @@ __device__ __forceinline__ void mc_block(const uint8_t* __restrict__ ref, int pi
 // and the inverse DCT (transform.cc:100-137).  On return coef[blk*CS + y*4 + x] holds the
 // RESIDUAL of pixel (x, y) of block blk (0-15 Y, 16-19 U, 20-23 V).
 // ------------------------------------------------------------------------------------------------
+// second half, shared with the encoder's reconstruction: coef holds DEQUANTISED coefficients
+__device__ __forceinline__ void inverse_transforms(int16_t* coef, bool has_y2, int lane);
+
 __device__ __forceinline__ void build_residuals(const DevJob& J, const MbFields& f, int16_t* coef, int lane) {
   uint32_t* w = reinterpret_cast<uint32_t*>(coef);
   for (int i = lane; i < COEF_WORDS; i += 32) w[i] = 0;
@@ -275,7 +278,11 @@ __device__ __forceinline__ void build_residuals(const DevJob& J, const MbFields&
     coef[blk * CS + pos] = (int16_t)(val * factor);
   }
   __syncwarp();
-  if (f.flags & VP8GPU_MB_HAS_Y2) {
+  inverse_transforms(coef, (f.flags & VP8GPU_MB_HAS_Y2) != 0, lane);
+}
+
+__device__ __forceinline__ void inverse_transforms(int16_t* coef, bool has_y2, int lane) {
+  if (has_y2) {
     // inverse WHT on 16 lanes (transform.cc:47-88): lane i first produces intermediate m[i]
     // (column i & 3, butterfly output i >> 2), the row pass exchanges m through shuffles.
     const int16_t* y2 = coef + 24 * CS;
@@ -944,6 +951,417 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 16) k_loopfilter(const DevJob* 
 }
 
 // ================================================================================================
+// ENCODER kernels (first slice): luma_mb_inter_predict / diamond_search
+// (encoder/encode_inter.cc:172-369), luma_mb_best_prediction_mode + chroma (encode_intra.cc:83-355),
+// subtract_dct / wht / quantize (dct.cc:45-164, quantization.cc:148-178) and the reconstruction a
+// decoder will perform (macroblock.cc:504-601).  Decisions use SAD (the reference's RD search is
+// not reproduced yet); what is reproduced exactly is the transform / quantiser arithmetic and the
+// closed loop: the emitted records decode to the `out` raster bit for bit.
+// ================================================================================================
+__device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
+
+constexpr int ME_RANGE = 15;           // full-pel search range
+constexpr int ME_WIN = 16 + 2 * 16;    // staged window: 48 x 48 around the macroblock
+constexpr int ENC_WARPS = 4;
+
+// 16x16 SAD of the source block against the staged window at full-pel offset (dx, dy)
+__device__ __forceinline__ int sad_window(const uint8_t* src, const uint8_t* win, int dx, int dy, int lane) {
+  const int y = lane >> 1, x0 = (lane & 1) * 8;
+  const uint8_t* s = src + y * 16 + x0;
+  const uint8_t* w = win + (16 + dy + y) * ME_WIN + 16 + dx + x0;
+  int acc = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) acc += abs((int)s[k] - (int)w[k]);
+  return warp_sum(acc);
+}
+__device__ __forceinline__ int sad_16x16(const uint8_t* a, const uint8_t* b, int lane) {
+  const int o = (lane >> 1) * 16 + (lane & 1) * 8;
+  int acc = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) acc += abs((int)a[o + k] - (int)b[o + k]);
+  return warp_sum(acc);
+}
+
+__global__ void __launch_bounds__(ENC_WARPS * 32) k_enc_motion(const EncJob* __restrict__ jobp, Geom g) {
+  __shared__ __align__(16) uint8_t s_src[ENC_WARPS][256];
+  __shared__ __align__(16) uint8_t s_win[ENC_WARPS][ME_WIN * ME_WIN];
+  __shared__ __align__(16) uint8_t s_pred[ENC_WARPS][256];
+  __shared__ __align__(16) uint8_t s_tile[ENC_WARPS][21 * 24];
+  __shared__ __align__(16) uint8_t s_mid[ENC_WARPS][21 * 16];
+  const EncJob& J = *jobp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mbi = blockIdx.x * ENC_WARPS + warp;
+  if (mbi >= g.mb_cols * g.mb_rows) return;
+  const int row = mbi / g.mb_cols, col = mbi - row * g.mb_cols;
+  uint8_t* src = s_src[warp];
+  uint8_t* win = s_win[warp];
+  uint8_t* pred = s_pred[warp];
+  // source macroblock: 64 words
+  for (int i = lane; i < 64; i += 32) {
+    const int r = i >> 2, w = i & 3;
+    reinterpret_cast<uint32_t*>(src)[i] = __ldg(reinterpret_cast<const uint32_t*>(J.src + (size_t)(16 * row + r) * g.y_pitch + 16 * col) + w);
+  }
+  // search window with clamped coordinates (the reference searches a 256-pixel padded SafeRaster)
+  const int wx = 16 * col - 16, wy = 16 * row - 16;
+  if (wx >= 0 && wy >= 0 && wx + ME_WIN <= g.W && wy + ME_WIN <= g.H) {
+    for (int i = lane; i < ME_WIN * (ME_WIN / 4); i += 32) {
+      const int r = i / (ME_WIN / 4), w = i - r * (ME_WIN / 4);
+      reinterpret_cast<uint32_t*>(win)[i] = __ldg(reinterpret_cast<const uint32_t*>(J.ref + (size_t)(wy + r) * g.y_pitch + wx) + w);
+    }
+  } else {
+    for (int i = lane; i < ME_WIN * ME_WIN; i += 32) {
+      const int r = i / ME_WIN, c = i - r * ME_WIN;
+      win[i] = __ldg(J.ref + (size_t)clampi(wy + r, 0, g.H - 1) * g.y_pitch + clampi(wx + c, 0, g.W - 1));
+    }
+  }
+  __syncwarp();
+
+  // ---- full-pel: greedy 4-point pattern with shrinking step (a small diamond search) ----
+  int bx = 0, by = 0;
+  int best = sad_window(src, win, 0, 0, lane);
+  for (int step = 8; step >= 1; step >>= 1) {
+    for (int iter = 0; iter < 4; iter++) {
+      bool moved = false;
+#pragma unroll
+      for (int d = 0; d < 4; d++) {
+        const int cx = bx + ((d == 0) - (d == 1)) * step, cy = by + ((d == 2) - (d == 3)) * step;
+        if (abs(cx) > ME_RANGE || abs(cy) > ME_RANGE) continue;
+        const int s = sad_window(src, win, cx, cy, lane);
+        if (s < best) {
+          best = s;
+          bx = cx;
+          by = cy;
+          moved = true;
+        }
+      }
+      if (!moved) break;
+    }
+  }
+  // ---- sub-pel: half-pel then quarter-pel neighbours of the best vector, six-tap predicted ----
+  int mvx = bx * 8, mvy = by * 8;
+  if (best > 64) {
+    for (int step = 4; step >= 2; step >>= 1) {
+      int cbx = mvx, cby = mvy;
+      for (int d = 0; d < 8; d++) {
+        const int ox = (d == 0 || d == 4 || d == 6) ? -1 : ((d == 1 || d == 5 || d == 7) ? 1 : 0);
+        const int oy = (d == 2 || d == 4 || d == 5) ? -1 : ((d == 3 || d == 6 || d == 7) ? 1 : 0);
+        const int cx = mvx + ox * step, cy = mvy + oy * step;
+        mc_block<16>(J.ref, g.y_pitch, g.W, g.H, 16 * col, 16 * row, cx, cy, pred, 16, s_tile[warp], s_mid[warp], lane);
+        const int s = sad_16x16(src, pred, lane);
+        if (s < best) {
+          best = s;
+          cbx = cx;
+          cby = cy;
+        }
+      }
+      mvx = cbx;
+      mvy = cby;
+    }
+  }
+  if (lane == 0) {
+    J.mv[2 * mbi] = mvx;
+    J.mv[2 * mbi + 1] = mvy;
+    J.sad[mbi] = (uint32_t)best;
+  }
+}
+
+__global__ void __launch_bounds__(32 * WF_WARPS, 12) k_enc_mb(const EncJob* __restrict__ jobp, Geom g, int* ticket) {
+  __shared__ __align__(16) uint8_t s_W[WF_WARPS][17 * WS];
+  __shared__ __align__(16) uint8_t s_pixc[WF_WARPS][128];
+  __shared__ __align__(16) uint8_t s_src[WF_WARPS][384];
+  __shared__ __align__(16) uint8_t s_pinter[WF_WARPS][384];
+  __shared__ __align__(16) int16_t s_coef[WF_WARPS][25 * CS];
+  __shared__ __align__(16) uint8_t s_tile[WF_WARPS][21 * 24];
+  __shared__ __align__(16) uint8_t s_mid[WF_WARPS][21 * 16];
+  __shared__ uint8_t s_aboveC[WF_WARPS][2][12];
+  __shared__ uint8_t s_leftC[WF_WARPS][2][8];
+  const EncJob& J = *jobp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* const W = s_W[warp];
+  uint8_t* const pixc = s_pixc[warp];
+  uint8_t* const src = s_src[warp];
+  uint8_t* const pinter = s_pinter[warp];
+  int16_t* const coef = s_coef[warp];
+  uint8_t (*const aboveC)[12] = s_aboveC[warp];
+  uint8_t (*const leftC)[8] = s_leftC[warp];
+  int t = 0;
+  if (lane == 0) t = atomicAdd(ticket, 1);
+  t = __shfl_sync(0xffffffffu, t, 0);
+  const int row = t;
+  if (row >= g.mb_rows) return;
+  const int cols = g.mb_cols;
+  int* progress = J.progress + row;
+  uint8_t* const Y = J.out;
+  uint8_t* const U = J.out + g.u_off;
+  uint8_t* const V = J.out + g.v_off;
+  const int CW = g.W >> 1, CH = g.H >> 1;
+  const vp8gpu_quant q = J.q;
+
+  for (int col = 0; col < cols; col++) {
+    const int mbi = row * cols + col;
+    // ---- source macroblock (96 words) and, for inter frames, the motion-compensated candidate ----
+    for (int i = lane; i < 96; i += 32) {
+      const uint8_t* gp;
+      if (i < 64) gp = J.src + (size_t)(16 * row + (i >> 2)) * g.y_pitch + 16 * col + 4 * (i & 3);
+      else {
+        const int c = i - 64, plane = c >> 4, k = c & 15;
+        gp = J.src + (plane ? g.v_off : g.u_off) + (size_t)(8 * row + (k >> 1)) * g.c_pitch + 8 * col + 4 * (k & 1);
+      }
+      reinterpret_cast<uint32_t*>(src)[i] = __ldg(reinterpret_cast<const uint32_t*>(gp));
+    }
+    int mvx = 0, mvy = 0, cost_inter = 0x7fffffff;
+    if (!J.key_frame) {
+      mvx = J.mv[2 * mbi];
+      mvy = J.mv[2 * mbi + 1];
+      const int cmx = chroma_component(4 * mvx), cmy = chroma_component(4 * mvy);
+      mc_block<16>(J.ref, g.y_pitch, g.W, g.H, 16 * col, 16 * row, mvx, mvy, pinter, 16, s_tile[warp], s_mid[warp], lane);
+      mc_block<8>(J.ref + g.u_off, g.c_pitch, CW, CH, 8 * col, 8 * row, cmx, cmy, pinter + 256, 8, s_tile[warp], s_mid[warp], lane);
+      mc_block<8>(J.ref + g.v_off, g.c_pitch, CW, CH, 8 * col, 8 * row, cmx, cmy, pinter + 320, 8, s_tile[warp], s_mid[warp], lane);
+      int acc = 0;
+      for (int i = lane; i < 384; i += 32) acc += abs((int)src[i] - (int)pinter[i]);
+      cost_inter = warp_sum(acc);
+    }
+    __syncwarp();
+    if (row > 0) wait_row(progress - 1, min(col + 2, cols), lane);
+
+    // ---- edges of the reconstruction so far (same rules as the decoder, prediction.cc:99-167) ----
+    {
+      const int outside_above = row == 0 ? 127 : 129;
+      const uint8_t* pa = Y;
+      bool va = false;
+      if (lane < 21 && row > 0 && !(lane == 0 && col == 0)) {
+        const int x = (lane >= 17 && col == cols - 1) ? 15 : lane - 1;
+        pa = Y + (size_t)(16 * row - 1) * g.y_pitch + 16 * col + x;
+        va = true;
+      }
+      const uint8_t* pb = Y;
+      if (col > 0) {
+        if (lane < 16) pb = Y + (size_t)(16 * row + lane) * g.y_pitch + 16 * col - 1;
+        else pb = ((lane & 8) ? V : U) + (size_t)(8 * row + (lane & 7)) * g.c_pitch + 8 * col - 1;
+      }
+      const uint8_t* pc = Y;
+      bool vc = false;
+      const int cpl = lane >= 9, ck = lane - 9 * cpl;
+      if (lane < 18 && row > 0 && !(ck == 0 && col == 0)) {
+        pc = (cpl ? V : U) + (size_t)(8 * row - 1) * g.c_pitch + 8 * col + ck - 1;
+        vc = true;
+      }
+      const int a = va ? (int)ldcg_u8(pa) : outside_above;
+      const int b = col > 0 ? (int)ldcg_u8(pb) : 129;
+      const int c = vc ? (int)ldcg_u8(pc) : outside_above;
+      if (lane < 21) W[15 + lane] = (uint8_t)a;
+      if (lane < 16) W[(lane + 1) * WS + 15] = (uint8_t)b;
+      else leftC[(lane >> 3) & 1][lane & 7] = (uint8_t)b;
+      if (lane < 18) aboveC[cpl][ck] = (uint8_t)c;
+    }
+    __syncwarp();
+
+    // ---- intra candidates: SAD of the four 16x16 luma modes and the four chroma modes ----
+    const uint8_t* A = W + 16;
+    int dcY = 128;
+    {
+      int s = 0, n = 0;
+      if (row > 0) { for (int k = 0; k < 16; k++) s += A[k]; n += 16; }
+      if (col > 0) { for (int k = 0; k < 16; k++) s += W[(k + 1) * WS + 15]; n += 16; }
+      dcY = n == 32 ? (s + 16) >> 5 : (n == 16 ? (s + 8) >> 4 : 128);
+    }
+    int sdc = 0, sv = 0, sh = 0, stm = 0;
+    {
+      const int y = lane >> 1, x8 = (lane & 1) * 8;
+      const int left = W[(y + 1) * WS + 15], corner = W[15];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int sp = src[y * 16 + x8 + k], ab = A[x8 + k];
+        sdc += abs(sp - dcY);
+        sv += abs(sp - ab);
+        sh += abs(sp - left);
+        stm += abs(sp - vp8m::clamp255(left + ab - corner));
+      }
+    }
+    sdc = warp_sum(sdc);
+    sv = warp_sum(sv);
+    sh = warp_sum(sh);
+    stm = warp_sum(stm);
+    int y_mode = VP8GPU_DC_PRED, sadY = sdc;
+    if (sv < sadY) sadY = sv, y_mode = VP8GPU_V_PRED;
+    if (sh < sadY) sadY = sh, y_mode = VP8GPU_H_PRED;
+    if (stm < sadY) sadY = stm, y_mode = VP8GPU_TM_PRED;
+    int cdc[2];
+#pragma unroll
+    for (int plane = 0; plane < 2; plane++) {
+      int s = 0, n = 0;
+      if (row > 0) { for (int k = 0; k < 8; k++) s += aboveC[plane][1 + k]; n += 8; }
+      if (col > 0) { for (int k = 0; k < 8; k++) s += leftC[plane][k]; n += 8; }
+      cdc[plane] = n == 16 ? (s + 8) >> 4 : (n == 8 ? (s + 4) >> 3 : 128);
+    }
+    int cs0 = 0, cs1 = 0, cs2 = 0, cs3 = 0;
+    const int cplane = lane >> 4, cy = (lane >> 1) & 7, cx4 = (lane & 1) * 4;
+    {
+      const uint8_t* CA = aboveC[cplane] + 1;
+      const int cl = leftC[cplane][cy], ccorner = CA[-1], cd = cplane ? cdc[1] : cdc[0];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int sp = src[256 + cplane * 64 + cy * 8 + cx4 + k], ab = CA[cx4 + k];
+        cs0 += abs(sp - cd);
+        cs1 += abs(sp - ab);
+        cs2 += abs(sp - cl);
+        cs3 += abs(sp - vp8m::clamp255(cl + ab - ccorner));
+      }
+    }
+    cs0 = warp_sum(cs0);
+    cs1 = warp_sum(cs1);
+    cs2 = warp_sum(cs2);
+    cs3 = warp_sum(cs3);
+    int uv_mode = VP8GPU_DC_PRED, sadC = cs0;
+    if (cs1 < sadC) sadC = cs1, uv_mode = VP8GPU_V_PRED;
+    if (cs2 < sadC) sadC = cs2, uv_mode = VP8GPU_H_PRED;
+    if (cs3 < sadC) sadC = cs3, uv_mode = VP8GPU_TM_PRED;
+
+    // ---- inter or intra?  (intra macroblocks of inter frames cost more header bits: small bias) ----
+    const bool inter = !J.key_frame && cost_inter <= sadY + sadC + 192;
+
+    // ---- materialise the chosen prediction in the workspace ----
+    if (inter) {
+      for (int i = lane; i < 64; i += 32) {
+        const int y = i >> 2, x4 = (i & 3) * 4;
+        *reinterpret_cast<uint32_t*>(W + (y + 1) * WS + 16 + x4) = *reinterpret_cast<const uint32_t*>(pinter + y * 16 + x4);
+      }
+      reinterpret_cast<uint32_t*>(pixc)[lane] = reinterpret_cast<const uint32_t*>(pinter + 256)[lane];
+    } else {
+      {
+        const uint8_t* CA = aboveC[cplane] + 1;
+        const int cl = leftC[cplane][cy];
+        uint32_t word;
+        if (uv_mode == VP8GPU_DC_PRED) word = (uint32_t)(cplane ? cdc[1] : cdc[0]) * 0x01010101u;
+        else if (uv_mode == VP8GPU_V_PRED) word = (uint32_t)CA[cx4] | ((uint32_t)CA[cx4 + 1] << 8) | ((uint32_t)CA[cx4 + 2] << 16) | ((uint32_t)CA[cx4 + 3] << 24);
+        else if (uv_mode == VP8GPU_H_PRED) word = (uint32_t)cl * 0x01010101u;
+        else {
+          const int base = cl - CA[-1];
+          word = 0;
+#pragma unroll
+          for (int k = 0; k < 4; k++) word |= (uint32_t)vp8m::clamp255(base + CA[cx4 + k]) << (8 * k);
+        }
+        *reinterpret_cast<uint32_t*>(pixc + cplane * 64 + cy * 8 + cx4) = word;
+      }
+      const int y = lane >> 1, x8 = (lane & 1) * 8;
+      const int left = W[(y + 1) * WS + 15];
+      uint32_t w0, w1;
+      if (y_mode == VP8GPU_DC_PRED) w0 = w1 = (uint32_t)dcY * 0x01010101u;
+      else if (y_mode == VP8GPU_V_PRED) {
+        w0 = *reinterpret_cast<const uint32_t*>(A + x8);
+        w1 = *reinterpret_cast<const uint32_t*>(A + x8 + 4);
+      } else if (y_mode == VP8GPU_H_PRED) w0 = w1 = (uint32_t)left * 0x01010101u;
+      else {
+        const int base = left - W[15];
+        w0 = w1 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          w0 |= (uint32_t)vp8m::clamp255(base + A[x8 + k]) << (8 * k);
+          w1 |= (uint32_t)vp8m::clamp255(base + A[x8 + 4 + k]) << (8 * k);
+        }
+      }
+      __syncwarp();
+      *reinterpret_cast<uint32_t*>(W + (y + 1) * WS + 16 + x8) = w0;
+      *reinterpret_cast<uint32_t*>(W + (y + 1) * WS + 20 + x8) = w1;
+    }
+    __syncwarp();
+
+    // ---- residual -> forward DCT (one 4x4 block per lane), Y2 = WHT of the 16 luma DCs ----
+    if (lane < 24) {
+      int16_t d[16], o[16];
+      if (lane < 16) {
+        const int bx = lane & 3, by = lane >> 2;
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+          d[k] = (int16_t)((int)src[(4 * by + (k >> 2)) * 16 + 4 * bx + (k & 3)] - (int)W[(4 * by + (k >> 2) + 1) * WS + 16 + 4 * bx + (k & 3)]);
+      } else {
+        const int c = lane - 16, plane = c >> 2, bx = c & 1, by = (c >> 1) & 1;
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+          d[k] = (int16_t)((int)src[256 + plane * 64 + (4 * by + (k >> 2)) * 8 + 4 * bx + (k & 3)] -
+                           (int)pixc[plane * 64 + (4 * by + (k >> 2)) * 8 + 4 * bx + (k & 3)]);
+      }
+      vp8m::fdct16(d, o);
+#pragma unroll
+      for (int k = 0; k < 16; k++) coef[lane * CS + k] = o[k];
+    }
+    __syncwarp();
+    if (lane == 24) {
+      int16_t in[16], o[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) in[k] = coef[k * CS];
+      vp8m::fwht16(in, o);
+#pragma unroll
+      for (int k = 0; k < 16; k++) coef[24 * CS + k] = o[k];
+    }
+    __syncwarp();
+    // ---- quantise (truncating division), emit tokens, dequantise in place ----
+    int cnt = 0;
+    int16_t qv[16];
+    if (lane < 25) {
+      const int dcq = lane < 16 ? q.y_dc : (lane < 24 ? q.uv_dc : q.y2_dc);
+      const int acq = lane < 16 ? q.y_ac : (lane < 24 ? q.uv_ac : q.y2_ac);
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        int c = coef[lane * CS + k];
+        if (lane < 16 && k == 0) c = 0;  // the luma DCs travel in Y2
+        int v = vp8m::quantize_trunc(c, k ? acq : dcq);
+        v = v > 2047 ? 2047 : (v < -2047 ? -2047 : v);  // largest magnitude a DCT token can carry is 2114
+        qv[k] = (int16_t)v;
+        cnt += v != 0;
+        coef[lane * CS + k] = (int16_t)(v * (k ? acq : dcq));  // DCTCoefficients::dequantize
+      }
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t base = 0;
+    if (lane == 0 && total) base = atomicAdd(J.tok_counter, (uint32_t)total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (lane < 25 && cnt && base + total <= J.tok_cap) {
+      uint32_t at = base + incl - cnt;
+#pragma unroll
+      for (int k = 0; k < 16; k++)
+        if (qv[k]) J.tokens[at++] = VP8GPU_TOKEN(lane, k, qv[k]);
+    }
+    __syncwarp();
+    // ---- reconstruct exactly like a decoder will ----
+    if (total) {
+      inverse_transforms(coef, true, lane);
+      add_residuals_intra(W, pixc, coef, lane, true);
+    }
+    if (lane < 16) {
+      *reinterpret_cast<uint4*>(Y + (size_t)(16 * row + lane) * g.y_pitch + 16 * col) = *reinterpret_cast<const uint4*>(W + (lane + 1) * WS + 16);
+    } else {
+      const int plane = (lane - 16) >> 3, yy = lane & 7;
+      *reinterpret_cast<uint2*>((plane ? V : U) + (size_t)(8 * row + yy) * g.c_pitch + 8 * col) = *reinterpret_cast<const uint2*>(pixc + plane * 64 + yy * 8);
+    }
+    if (lane == 0) {
+      vp8gpu_mb m;
+      m.tok_off = base;
+      m.tok_cnt = (uint16_t)total;
+      m.y_mode = (uint8_t)(inter ? ((mvx | mvy) ? VP8GPU_NEWMV : VP8GPU_ZEROMV) : y_mode);
+      m.uv_mode = (uint8_t)(inter ? 0 : uv_mode);
+      m.ref_frame = inter ? VP8GPU_REF_LAST : VP8GPU_REF_CURRENT;
+      m.segment_id = 0;
+      m.lf_level = J.lf_level;
+      m.flags = VP8GPU_MB_HAS_Y2;
+      m.mv_x = (int16_t)(inter ? mvx : 0);
+      m.mv_y = (int16_t)(inter ? mvy : 0);
+      m.split_idx = 0;
+      m.reserved = 0;
+      m.b_modes = 0;
+      J.mbs[mbi] = m;
+    }
+    publish_row(progress, col + 1, lane);
+  }
+}
+
+// ================================================================================================
 // k_compare: References::operator== (decoder.cc:249-254) on the device; flag != 0 when any visible
 // pixel of the MB-aligned planes differs (pitch padding is ignored).
 // ================================================================================================
@@ -1012,6 +1430,16 @@ int launch_intra(const DevJob* jobs, int njobs, const Geom& g, int* ticket, void
 }
 int launch_loopfilter(const DevJob* jobs, int njobs, const Geom& g, int* ticket, void* stream) {
   k_loopfilter<<<(g.mb_rows * njobs + WF_WARPS - 1) / WF_WARPS, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream)>>>(jobs, njobs, g, ticket);
+  return (int)cudaGetLastError();
+}
+
+int launch_enc_motion(const EncJob* job, const Geom& g, void* stream) {
+  const int n_mbs = g.mb_cols * g.mb_rows;
+  k_enc_motion<<<(n_mbs + ENC_WARPS - 1) / ENC_WARPS, ENC_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(job, g);
+  return (int)cudaGetLastError();
+}
+int launch_enc_mb(const EncJob* job, const Geom& g, int* ticket, void* stream) {
+  k_enc_mb<<<(g.mb_rows + WF_WARPS - 1) / WF_WARPS, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream)>>>(job, g, ticket);
   return (int)cudaGetLastError();
 }
 

@@ -70,6 +70,55 @@ VP8_HD void idct16(const int16_t* c, int16_t* r) {
   }
 }
 
+// ---- forward DCT / WHT and quantiser (encoder): decoder/dct.cc:45-164, quantization.cc:148-178 ----
+// d = residual (source - prediction), raster order; out[4 * vertical_freq + horizontal_freq]
+VP8_HD void fdct16(const int16_t* d, int16_t* out) {
+  int t[16];
+  for (int i = 0; i < 4; i++) {
+    const int a1 = (d[4 * i + 0] + d[4 * i + 3]) * 8, b1 = (d[4 * i + 1] + d[4 * i + 2]) * 8;
+    const int c1 = (d[4 * i + 1] - d[4 * i + 2]) * 8, d1 = (d[4 * i + 0] - d[4 * i + 3]) * 8;
+    t[4 * i + 0] = wrap16(a1 + b1);
+    t[4 * i + 2] = wrap16(a1 - b1);
+    t[4 * i + 1] = wrap16((c1 * 2217 + d1 * 5352 + 14500) >> 12);
+    t[4 * i + 3] = wrap16((d1 * 2217 - c1 * 5352 + 7500) >> 12);
+  }
+  for (int i = 0; i < 4; i++) {
+    const int a1 = t[i] + t[i + 12], b1 = t[i + 4] + t[i + 8];
+    const int c1 = t[i + 4] - t[i + 8], d1 = t[i] - t[i + 12];
+    out[i] = (int16_t)((a1 + b1 + 7) >> 4);
+    out[i + 8] = (int16_t)((a1 - b1 + 7) >> 4);
+    out[i + 4] = (int16_t)(((c1 * 2217 + d1 * 5352 + 12000) >> 16) + (d1 != 0));
+    out[i + 12] = (int16_t)((d1 * 2217 - c1 * 5352 + 51000) >> 16);
+  }
+}
+// in = the 16 luma DC coefficients (raster order of sub-blocks); out = Y2 coefficients
+VP8_HD void fwht16(const int16_t* in, int16_t* out) {
+  int t[16];
+  for (int i = 0; i < 4; i++) {
+    const int a1 = (in[4 * i + 0] + in[4 * i + 2]) * 4, d1 = (in[4 * i + 1] + in[4 * i + 3]) * 4;
+    const int c1 = (in[4 * i + 1] - in[4 * i + 3]) * 4, b1 = (in[4 * i + 0] - in[4 * i + 2]) * 4;
+    t[4 * i + 0] = wrap16(a1 + d1 + (a1 != 0));
+    t[4 * i + 1] = wrap16(b1 + c1);
+    t[4 * i + 2] = wrap16(b1 - c1);
+    t[4 * i + 3] = wrap16(a1 - d1);
+  }
+  for (int i = 0; i < 4; i++) {
+    const int a1 = t[i] + t[i + 8], d1 = t[i + 4] + t[i + 12];
+    const int c1 = t[i + 4] - t[i + 12], b1 = t[i] - t[i + 8];
+    int a2 = a1 + d1, b2 = b1 + c1, c2 = b1 - c1, d2 = a1 - d1;
+    a2 += a2 < 0;
+    b2 += b2 < 0;
+    c2 += c2 < 0;
+    d2 += d2 < 0;
+    out[i] = (int16_t)((a2 + 3) >> 3);
+    out[i + 4] = (int16_t)((b2 + 3) >> 3);
+    out[i + 8] = (int16_t)((c2 + 3) >> 3);
+    out[i + 12] = (int16_t)((d2 + 3) >> 3);
+  }
+}
+// DCTCoefficients::quantize: C++ integer division, i.e. truncation toward zero
+VP8_HD int quantize_trunc(int coef, int factor) { return coef / factor; }
+
 // ---- six-tap sub-pixel filter: decoder/prediction.cc:645-653, 919-971 ------------------------
 VP8_HD int sixtap(int p0, int p1, int p2, int p3, int p4, int p5, const int16_t* t) {
   return clamp255((p0 * t[0] + p1 * t[1] + p2 * t[2] + p3 * t[3] + p4 * t[4] + p5 * t[5] + 64) >> 7);

@@ -300,3 +300,54 @@ def decode_ivf(ctx, ivf_bytes, threads=1, want_output=True):
         if ptr:
             L.vp8gpu_host_free(ptr)
     return dst, nd.value, ns.value
+
+
+class Encoder:
+    """Encoder (encoder/encoder.hh:345-382), first slice: encode_with_quantizer / encode_with_target_size.
+    Source frames are display-size (Y, U, V) numpy planes; the result is one compressed VP8 frame."""
+
+    def __init__(self, ctx):
+        self.ctx, self.L = ctx, ctx.L
+        self.h = C.c_void_p()
+        check(self.L.vp8gpu_encoder_create(ctx.h, C.byref(self.h)), ctx.h, "encoder_create")
+        self._out = np.empty(ctx.width * ctx.height * 3 + (1 << 16), np.uint8)
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.L.vp8gpu_encoder_destroy(self.h)
+        except Exception:
+            pass
+
+    def _planes(self, y, u, v):
+        return tuple(np.ascontiguousarray(a, dtype=np.uint8) for a in (y, u, v))
+
+    def encode_with_quantizer(self, y, u, v, y_ac_qi):
+        y, u, v = self._planes(y, u, v)
+        size = C.c_size_t(0)
+        check(self.L.vp8gpu_encoder_encode_with_quantizer(self.h, y.ctypes.data, y.shape[1], u.ctypes.data, v.ctypes.data,
+                                                          u.shape[1], y_ac_qi, self._out.ctypes.data, self._out.size,
+                                                          C.byref(size)), self.ctx.h, "encode_with_quantizer")
+        return self._out[:size.value].tobytes()
+
+    def encode_with_target_size(self, y, u, v, target_size):
+        y, u, v = self._planes(y, u, v)
+        size, qi = C.c_size_t(0), C.c_int(0)
+        check(self.L.vp8gpu_encoder_encode_with_target_size(self.h, y.ctypes.data, y.shape[1], u.ctypes.data, v.ctypes.data,
+                                                            u.shape[1], target_size, self._out.ctypes.data, self._out.size,
+                                                            C.byref(size), C.byref(qi)), self.ctx.h, "encode_with_target_size")
+        return self._out[:size.value].tobytes(), qi.value
+
+    def reconstruction(self):
+        """the encoder's LAST reference (what a decoder holds after decoding the frame just emitted)"""
+        fid = C.c_int32(-1)
+        check(self.L.vp8gpu_encoder_reconstruction(self.h, C.byref(fid)), self.ctx.h, "encoder_reconstruction")
+        return RasterHandle(self.ctx, fid.value)
+
+
+def write_ivf(width, height, frames):
+    """util/ivf_writer.cc: 32-byte DKIF header + 12-byte frame headers"""
+    out = bytearray(b"DKIF" + struct.pack("<HH4sHHIII", 0, 32, b"VP80", width, height, 30, 1, len(frames), 0))
+    for i, f in enumerate(frames):
+        out += struct.pack("<IQ", len(f), i) + f
+    return bytes(out)

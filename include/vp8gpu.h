@@ -283,6 +283,27 @@ typedef struct vp8gpu_encode_header {
 int vp8gpu_serialize_frame(const vp8gpu_encode_header* hdr, const vp8gpu_mb* mbs, const vp8gpu_token* tokens,
                            const vp8gpu_split_mvs* split, uint8_t* out, size_t cap, size_t* size);
 
+/* ---- Encoder (encoder/encoder.hh:345-382), first slice ----
+ * Explicit state: the encoder owns its LAST reference (the reconstruction of the previous frame);
+ * the first frame is a key frame, later frames are inter frames (encoder.cc:559-590).  Source planes
+ * are the display-size Y, U, V planes on the host; they are edge-extended to macroblock size like
+ * the reference's input reader does.  The emitted frame is a standard VP8 frame. */
+typedef struct vp8gpu_encoder vp8gpu_encoder;
+int vp8gpu_encoder_create(vp8gpu_ctx* ctx, vp8gpu_encoder** out);
+void vp8gpu_encoder_destroy(vp8gpu_encoder* enc);
+/* Encoder::encode_with_quantizer (encoder.cc:559-590) */
+int vp8gpu_encoder_encode_with_quantizer(vp8gpu_encoder* enc, const uint8_t* y, size_t y_stride, const uint8_t* u,
+                                         const uint8_t* v, size_t uv_stride, int y_ac_qi, uint8_t* out, size_t cap,
+                                         size_t* size);
+/* Encoder::encode_with_target_size (encoder.cc:592-629): smallest quantiser index in the searched
+ * range whose frame fits `target_size` bytes; *chosen_qi (optional) receives it. */
+int vp8gpu_encoder_encode_with_target_size(vp8gpu_encoder* enc, const uint8_t* y, size_t y_stride, const uint8_t* u,
+                                           const uint8_t* v, size_t uv_stride, size_t target_size, uint8_t* out,
+                                           size_t cap, size_t* size, int* chosen_qi);
+/* the reconstruction of the last encoded frame = the decoder's LAST reference after decoding it
+ * (Encoder::export_decoder, encoder.hh:378); the caller releases the returned raster */
+int vp8gpu_encoder_reconstruction(vp8gpu_encoder* enc, vp8gpu_frame_id* out);
+
 /* Host-side time accounting of the last vp8gpu_decode_ivf call, seconds summed over threads:
  * [0] parsing, [1] workers waiting for the dispatcher, [2] workers waiting for DMA, [3] dispatcher
  * in submit, [4] dispatcher queueing downloads, [5] dispatcher idle, [6] batches, [7] frames. */

@@ -1583,3 +1583,49 @@ void vp8o_test_sixtap(const uint8_t* window, int n, int mx, int my, uint8_t* out
   for (int y = 0; y < n; y++) memcpy(out + y * n, tmp + y * ws, n);
   free(tmp);
 }
+
+/* ---- forward transforms of the encoder (decoder/dct.cc:45-164), restated for unit tests ---- */
+void vp8o_test_fdct(const uint8_t src[16], const uint8_t pred[16], int16_t out[16]) {
+  int16_t in[16], c[16];
+  for (int i = 0; i < 16; i++) in[i] = (int16_t)(src[i] - pred[i]);
+  for (int i = 0; i < 4; i++) { /* rows */
+    const int a1 = (in[4 * i + 0] + in[4 * i + 3]) * 8, b1 = (in[4 * i + 1] + in[4 * i + 2]) * 8;
+    const int c1 = (in[4 * i + 1] - in[4 * i + 2]) * 8, d1 = (in[4 * i + 0] - in[4 * i + 3]) * 8;
+    c[4 * i + 0] = (int16_t)(a1 + b1);
+    c[4 * i + 2] = (int16_t)(a1 - b1);
+    c[4 * i + 1] = (int16_t)((c1 * 2217 + d1 * 5352 + 14500) >> 12);
+    c[4 * i + 3] = (int16_t)((d1 * 2217 - c1 * 5352 + 7500) >> 12);
+  }
+  for (int i = 0; i < 4; i++) { /* columns */
+    const int a1 = c[i + 0] + c[i + 12], b1 = c[i + 4] + c[i + 8];
+    const int c1 = c[i + 4] - c[i + 8], d1 = c[i + 0] - c[i + 12];
+    out[i + 0] = (int16_t)((a1 + b1 + 7) >> 4);
+    out[i + 8] = (int16_t)((a1 - b1 + 7) >> 4);
+    out[i + 4] = (int16_t)(((c1 * 2217 + d1 * 5352 + 12000) >> 16) + (d1 != 0));
+    out[i + 12] = (int16_t)((d1 * 2217 - c1 * 5352 + 51000) >> 16);
+  }
+}
+void vp8o_test_fwht(const int16_t in[16], int16_t out[16]) {
+  int16_t c[16];
+  for (int i = 0; i < 4; i++) {
+    const int a1 = (in[4 * i + 0] + in[4 * i + 2]) * 4, d1 = (in[4 * i + 1] + in[4 * i + 3]) * 4;
+    const int c1 = (in[4 * i + 1] - in[4 * i + 3]) * 4, b1 = (in[4 * i + 0] - in[4 * i + 2]) * 4;
+    c[4 * i + 0] = (int16_t)(a1 + d1 + (a1 != 0));
+    c[4 * i + 1] = (int16_t)(b1 + c1);
+    c[4 * i + 2] = (int16_t)(b1 - c1);
+    c[4 * i + 3] = (int16_t)(a1 - d1);
+  }
+  for (int i = 0; i < 4; i++) {
+    const int a1 = c[i + 0] + c[i + 8], d1 = c[i + 4] + c[i + 12];
+    const int c1 = c[i + 4] - c[i + 12], b1 = c[i + 0] - c[i + 8];
+    int a2 = a1 + d1, b2 = b1 + c1, c2 = b1 - c1, d2 = a1 - d1;
+    a2 += a2 < 0;
+    b2 += b2 < 0;
+    c2 += c2 < 0;
+    d2 += d2 < 0;
+    out[i + 0] = (int16_t)((a2 + 3) >> 3);
+    out[i + 4] = (int16_t)((b2 + 3) >> 3);
+    out[i + 8] = (int16_t)((c2 + 3) >> 3);
+    out[i + 12] = (int16_t)((d2 + 3) >> 3);
+  }
+}

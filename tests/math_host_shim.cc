@@ -16,6 +16,12 @@ void m_idct_add(const int16_t* c, uint8_t* px) {
   vp8m::idct16(c, r);
   for (int i = 0; i < 16; i++) px[i] = (uint8_t)vp8m::clamp255(px[i] + r[i]);
 }
+void m_fdct(const uint8_t* src, const uint8_t* pred, int16_t* out) {
+  int16_t d[16];
+  for (int i = 0; i < 16; i++) d[i] = (int16_t)(src[i] - pred[i]);
+  vp8m::fdct16(d, out);
+}
+void m_fwht(const int16_t* in, int16_t* out) { vp8m::fwht16(in, out); }
 void m_iwht(const int16_t* c, int16_t* dc) { vp8m::iwht16(c, dc); }
 void m_lf_edge(uint8_t* px, int level, int sharpness, int key_frame, int mb_edge) {
   const vp8m::LfParams lp = vp8m::lf_params(level, sharpness, key_frame);

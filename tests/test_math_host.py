@@ -96,3 +96,20 @@ def test_sixtap(libs, n):
                 M.m_sixtap(_p(win), n, mx, my, _p(a))
                 L.vp8o_test_sixtap(_p(win), n, mx, my, _p(b))
                 assert np.array_equal(a, b), (it, mx, my)
+
+
+def test_forward_dct_and_wht(libs):
+    """encoder transforms (decoder/dct.cc:45-164)"""
+    M, L = libs
+    rng = np.random.default_rng(6)
+    for it in range(3000):
+        src = rng.integers(0, 256, 16).astype(np.uint8)
+        pred = rng.integers(0, 256, 16).astype(np.uint8) if it % 3 else src.copy()
+        a, b = np.zeros(16, np.int16), np.zeros(16, np.int16)
+        M.m_fdct(_p(src), _p(pred), _p(a))
+        L.vp8o_test_fdct(_p(src), _p(pred), _p(b))
+        assert np.array_equal(a, b), it
+        dc = rng.integers(-2040, 2041, 16).astype(np.int16)
+        M.m_fwht(_p(dc), _p(a))
+        L.vp8o_test_fwht(_p(dc), _p(b))
+        assert np.array_equal(a, b), it
