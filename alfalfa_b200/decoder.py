@@ -347,7 +347,7 @@ class Encoder:
 
 def write_ivf(width, height, frames):
     """util/ivf_writer.cc: 32-byte DKIF header + 12-byte frame headers"""
-    out = bytearray(b"DKIF" + struct.pack("<HH4sHHIII", 0, 32, b"VP80", width, height, 30, 1, len(frames), 0))
+    out = bytearray(b"DKIF" + struct.pack("<HH4sHHIIII", 0, 32, b"VP80", width, height, 30, 1, len(frames), 0))
     for i, f in enumerate(frames):
         out += struct.pack("<IQ", len(f), i) + f
     return bytes(out)
