@@ -147,6 +147,82 @@ def run_reference_arm(a, rank, world):
         "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def synth_1080p(t, w=1920, h=1080, seed=11):
+    """seeded synthetic source: drifting smooth pattern, four translating softly textured tiles, light noise"""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    tex = rng.integers(0, 256, (256, 256)).astype(np.float32)
+    for _ in range(3):
+        tex = (tex + np.roll(tex, 1, 0) + np.roll(tex, 1, 1) + np.roll(tex, (1, 1), (0, 1))) / 4
+    tex = np.clip(128 + (tex - 128) * 3, 0, 255)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    y = 128 + 50 * np.sin(0.012 * (xx + 3 * t)) * np.cos(0.009 * (yy + 2 * t))
+    for k, (vx, vy) in enumerate(((3, 1), (-2, 2), (1, -3), (-3, -2))):
+        ox, oy = 200 + 400 * k + vx * t, 150 + 180 * k + vy * t
+        y[oy:oy + 256, ox:ox + 256] = tex
+    y += np.random.default_rng(seed + 1 + t).integers(-1, 2, (h, w))
+    cy, cx = np.mgrid[0:(h + 1) // 2, 0:(w + 1) // 2].astype(np.float32)
+    u = 128 + 30 * np.sin(0.01 * (cx + t))
+    v = 128 + 30 * np.cos(0.012 * (cy - t))
+    return tuple(np.clip(p, 0, 255).astype(np.uint8) for p in (y, u, v))
+
+
+def bench_encode(a, local):
+    """fps of Encoder::encode_with_target_size at 1080p through the C ABI (host planes in, compressed
+    frame out, every step incl. H2D of the source and D2H of the records), next to the reference
+    encoder (REALTIME_QUALITY, one core) on the same raw frames."""
+    import numpy as np
+
+    from alfalfa_b200 import Context, Encoder
+    w, h, n = 1920, 1080, a.encode_frames
+    src = [synth_1080p(t) for t in range(n)]
+    ctx = Context(w, h, device=local, max_frames=32)
+    enc = Encoder(ctx)
+    enc.encode_with_target_size(*src[0], a.encode_target)  # warm-up (key frame, allocations)
+    del enc
+    enc = Encoder(ctx)
+    sizes, qis, psnrs, times = [], [], [], []
+    for t in range(n):
+        t0 = time.perf_counter()
+        blob, qi = enc.encode_with_target_size(*src[t], a.encode_target)
+        times.append(time.perf_counter() - t0)
+        sizes.append(len(blob))
+        qis.append(qi)
+        rec = enc.reconstruction()
+        ry = rec.planes()[0][:h, :w]
+        rec.release()
+        mse = float(np.mean((ry.astype(np.float64) - src[t][0].astype(np.float64)) ** 2))
+        psnrs.append(99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse))
+    launches = ctx.launch_count()
+    del enc
+    ctx.close()
+    out = {"metric": "encode_with_target_size fps @1080p", "frames": n, "target_bytes": a.encode_target,
+           "fps": (n - 1) / sum(times[1:]), "key_frame_ms": times[0] * 1e3, "inter_frame_ms": 1e3 * sum(times[1:]) / (n - 1),
+           "bytes_per_frame": sum(sizes) / n, "qi": qis, "psnr_y": sum(psnrs) / n, "gpu_launches": int(launches),
+           "note": "first slice: SAD decisions, 16x16 intra modes, LAST reference; closed loop verified in tests/test_gpu_encoder.py"}
+    ref_enc = os.path.join(ROOT, "oracle", "_ref", "ref_encode")
+    if os.path.exists(ref_enc):
+        import tempfile
+        m = min(n, 6)  # bounded sample: the reference runs at a few fps
+        with tempfile.TemporaryDirectory() as d:
+            raw = os.path.join(d, "src.yuv")
+            with open(raw, "wb") as f:
+                for t in range(m):
+                    for p in src[t]:
+                        f.write(p.tobytes())
+            env = dict(os.environ, REF_RAW=raw, REF_TARGET=str(a.encode_target))
+            r = subprocess.run([ref_enc, os.path.join(d, "o.ivf"), str(w), str(h), str(m), "1000", "0"], env=env,
+                               capture_output=True, text=True)
+            try:
+                j = json.loads(r.stdout.strip().splitlines()[-1])
+                out["reference"] = {"fps": j["fps"], "bytes_per_frame": j["bytes"] / m, "psnr_y": j["psnr_y"], "frames": m,
+                                    "cores": 1, "kind": "reference", "sample": "unmodified reference encoder, REALTIME_QUALITY, "
+                                    "encode_with_target_size, same raw frames, SSIM restated (parity unpinned)"}
+            except Exception as e:  # noqa: BLE001
+                out["reference"] = {"unavailable": "%s %s" % (e, r.stderr[-200:])}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -159,6 +235,9 @@ def main():
     ap.add_argument("--threads", type=int, default=0, help="host workers for the end-to-end run (0 = auto)")
     ap.add_argument("--ref-procs", type=int, default=0, help="reference processes (0 = usable CPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-encode", action="store_true", help="skip the 1080p encode section")
+    ap.add_argument("--encode-frames", type=int, default=12)
+    ap.add_argument("--encode-target", type=int, default=45000, help="bytes per frame for encode_with_target_size")
     ap.add_argument("--no-output", action="store_true", help="diagnostic: leave decoded frames on the device")
     ap.add_argument("--host-stats", action="store_true", help="diagnostic: print host time accounting to stderr")
     a = ap.parse_args()
@@ -363,6 +442,11 @@ def main():
     L.vp8gpu_host_free(dst)
     ctx2.close()
 
+    # ---------------- encode: 1080p encode_with_target_size (BASELINE.json config 3) ----------------
+    encode = None
+    if rank == 0 and not a.no_encode:
+        encode = bench_encode(a, local)
+
     # ---------------- CPU baseline (rank 0, one core, bounded sample) ----------------
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
@@ -393,7 +477,7 @@ def main():
                     "d2h_bytes_per_step": int(out_bytes), "ms_per_step": e2e_total / a.steps * 1e3,
                     "api": "vp8gpu_decode_ivf (host IVF bytes -> pinned host YUV)"},
             "gpu_launches": int(launches_resident), "gpu_launches_e2e": int(launches_e2e),
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}))
+            "roofline": roofline, "cpu_baseline": cpu, "encode": encode, "clocks": clocks}))
     if dist is not None:
         dist.destroy_process_group()
 

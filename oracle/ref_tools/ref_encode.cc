@@ -4,9 +4,14 @@
  * A new Encoder per GOP makes every GOP start with a key frame.
  *
  * usage: ref_encode OUT.ivf WIDTH HEIGHT FRAMES GOP QINDEX [SEED] [KIND]
+ *   environment: REF_RAW=file.yuv  read planar YUV420 frames (display size) instead of synthesising;
+ *                REF_TARGET=bytes  use Encoder::encode_with_target_size instead of a fixed quantiser;
+ *   prints one JSON line with encode seconds (source generation excluded), bytes and luma PSNR of
+ *   the encoder's own reconstruction (Encoder::export_decoder, encoder.hh:378).
  *   KIND 0: smooth moving sinusoid + noise ("easy");  1: translating random-texture tiles ("hard");
  *        2: translating softly textured tiles, light noise ("medium", broadcast-like bitrate)
  */
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <iostream>
@@ -74,16 +79,48 @@ int main(int argc, char** argv) {
     IVFWriter out(argv[1], "VP80", w, h, 30, 1);
     Optional<Encoder> enc;
     size_t total = 0;
+    const char* raw_path = getenv("REF_RAW");
+    const char* target_env = getenv("REF_TARGET");
+    FILE* raw = raw_path ? fopen(raw_path, "rb") : nullptr;
+    double enc_seconds = 0, sse = 0;
     for (int t = 0; t < frames; t++) {
       if (t % gop == 0) { enc.clear(); enc.initialize(w, h, false, REALTIME_QUALITY); }
       MutableRasterHandle raster(w, h);
-      synth(raster, w, h, t, seed, kind);
-      const vector<uint8_t> f = enc.get().encode_with_quantizer(raster.get(), qi);
+      if (raw) {
+        VP8Raster& r = raster.get();
+        vector<uint8_t> line(w);
+        for (int y = 0; y < (int)r.height(); y++) {
+          if (y < h && fread(line.data(), 1, w, raw) != (size_t)w) throw runtime_error("raw input too short");
+          for (int x = 0; x < (int)r.width(); x++) r.Y().at(x, y) = line[x < w ? x : w - 1];
+        }
+        const int cw = (w + 1) / 2, ch = (h + 1) / 2;
+        for (int pl = 0; pl < 2; pl++)
+          for (int y = 0; y < (int)r.height() / 2; y++) {
+            if (y < ch && fread(line.data(), 1, cw, raw) != (size_t)cw) throw runtime_error("raw input too short");
+            for (int x = 0; x < (int)r.width() / 2; x++) (pl ? r.V() : r.U()).at(x, y) = line[x < cw ? x : cw - 1];
+          }
+      } else {
+        synth(raster, w, h, t, seed, kind);
+      }
+      const auto t0 = chrono::steady_clock::now();
+      const vector<uint8_t> f = target_env ? enc.get().encode_with_target_size(raster.get(), atoi(target_env))
+                                           : enc.get().encode_with_quantizer(raster.get(), qi);
+      enc_seconds += chrono::duration<double>(chrono::steady_clock::now() - t0).count();
       out.append_frame(Chunk(&f.at(0), f.size()));
       total += f.size();
+      const VP8Raster& rec = enc.get().export_decoder().get_references().last;
+      for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+          const double d = (double)rec.Y().at(x, y) - (double)raster.get().Y().at(x, y);
+          sse += d * d;
+        }
       cerr << "frame " << t << " " << f.size() << " bytes\n";
     }
+    if (raw) fclose(raw);
     cerr << "total " << total << " bytes\n";
+    const double mse = sse / ((double)w * h * frames);
+    printf("{\"frames\": %d, \"encode_s\": %.4f, \"fps\": %.3f, \"bytes\": %zu, \"psnr_y\": %.3f}\n", frames,
+           enc_seconds, frames / enc_seconds, total, mse > 0 ? 10 * log10(255.0 * 255.0 / mse) : 99.0);
   } catch (const exception& e) {
     cerr << "ref_encode: " << e.what() << "\n";
     return 1;
