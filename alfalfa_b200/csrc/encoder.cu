@@ -75,7 +75,7 @@ int default_filter_level(int qi) {
 
 // run the device pipeline for one candidate quantiser; returns the compressed frame in `bytes` and
 // the new reconstruction in *out_frame (caller releases it or keeps it as LAST)
-int run_encode(vp8gpu_encoder* enc, bool key, int qi, std::vector<uint8_t>& bytes, int* out_frame) {
+int run_encode(vp8gpu_encoder* enc, bool key, int qi, bool search_motion, std::vector<uint8_t>& bytes, int* out_frame) {
   Engine* e = enc->e;
   const vp8::Geom& g = e->geom();
   const size_t n_mbs = (size_t)g.mb_cols * g.mb_rows;
@@ -131,7 +131,7 @@ int run_encode(vp8gpu_encoder* enc, bool key, int qi, std::vector<uint8_t>& byte
   const vp8::EncJob* d_ej = reinterpret_cast<const vp8::EncJob*>(enc->dev + enc->off_encjob);
   const vp8::DevJob* d_dj = reinterpret_cast<const vp8::DevJob*>(enc->dev + enc->off_encjob + 512);
   int launches = 0;
-  if (!key) {
+  if (!key && search_motion) {  // vectors do not depend on the quantiser: searched once per source frame
     if (int ce = vp8::launch_enc_motion(d_ej, g, s)) return fail(e->cuda_fail((cudaError_t)ce, "k_enc_motion"));
     launches++;
   }
@@ -278,7 +278,7 @@ int vp8gpu_encoder_encode_with_quantizer(vp8gpu_encoder* enc, const uint8_t* y, 
   if (rc != VP8GPU_OK) return rc;
   std::vector<uint8_t> bytes;
   int frame = -1;
-  rc = run_encode(enc, !enc->has_state, y_ac_qi, bytes, &frame);
+  rc = run_encode(enc, !enc->has_state, y_ac_qi, true, bytes, &frame);
   if (rc != VP8GPU_OK) return rc;
   return finish_frame(enc, bytes, frame, y_ac_qi, out, cap, size);
 }
@@ -300,10 +300,12 @@ int vp8gpu_encoder_encode_with_target_size(vp8gpu_encoder* enc, const uint8_t* y
   int best = -1, best_frame = -1;
   std::vector<uint8_t> best_bytes, bytes;
   const bool key = !enc->has_state;
+  bool first_probe = true;
   while (lo <= hi) {
     const int qi = (lo + hi) / 2;
     int frame = -1;
-    rc = run_encode(enc, key, qi, bytes, &frame);
+    rc = run_encode(enc, key, qi, first_probe, bytes, &frame);
+    first_probe = false;
     if (rc != VP8GPU_OK) {
       if (best_frame >= 0) enc->e->frame_release(best_frame);
       return rc;

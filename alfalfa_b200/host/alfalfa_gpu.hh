@@ -191,4 +191,51 @@ class Decoder {
   bool operator!=(const Decoder& o) const { return !(*this == o); }
 };
 
+// Encoder (encoder/encoder.hh:345-382), first slice.  The source raster is passed as display-size
+// planes in host memory (the reference takes a VP8Raster filled by its input readers).
+struct SourceFrame {
+  const uint8_t *y, *u, *v;
+  size_t y_stride, uv_stride;
+};
+
+class Encoder {
+  Context ctx_;
+  uint16_t width_, height_;
+  vp8gpu_encoder* h_ = nullptr;
+  std::vector<uint8_t> buf_;
+
+  std::vector<uint8_t> take(size_t n) const { return std::vector<uint8_t>(buf_.begin(), buf_.begin() + n); }
+
+ public:
+  Encoder(const Context& ctx, uint16_t width, uint16_t height)
+      : ctx_(ctx), width_(width), height_(height), buf_(size_t(width) * height * 3 + 65536) {
+    check(vp8gpu_encoder_create(ctx_.get(), &h_), ctx_.get(), "encoder_create");
+  }
+  Encoder(const Encoder&) = delete;
+  Encoder& operator=(const Encoder&) = delete;
+  ~Encoder() { vp8gpu_encoder_destroy(h_); }
+
+  // encode_with_quantizer (encoder.cc:559-590)
+  std::vector<uint8_t> encode_with_quantizer(const SourceFrame& f, uint8_t y_ac_qi) {
+    size_t n = 0;
+    check(vp8gpu_encoder_encode_with_quantizer(h_, f.y, f.y_stride, f.u, f.v, f.uv_stride, y_ac_qi, buf_.data(), buf_.size(), &n),
+          ctx_.get(), "encode_with_quantizer");
+    return take(n);
+  }
+  // encode_with_target_size (encoder.cc:592-629)
+  std::vector<uint8_t> encode_with_target_size(const SourceFrame& f, size_t target_size) {
+    size_t n = 0;
+    check(vp8gpu_encoder_encode_with_target_size(h_, f.y, f.y_stride, f.u, f.v, f.uv_stride, target_size, buf_.data(),
+                                                 buf_.size(), &n, nullptr),
+          ctx_.get(), "encode_with_target_size");
+    return take(n);
+  }
+  // the LAST reference of export_decoder() (encoder.hh:378)
+  RasterHandle reconstruction() const {
+    vp8gpu_frame_id id = -1;
+    check(vp8gpu_encoder_reconstruction(h_, &id), ctx_.get(), "reconstruction");
+    return RasterHandle(ctx_, id);
+  }
+};
+
 }  // namespace alfalfa_gpu
