@@ -1097,9 +1097,11 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 12) k_enc_mb(const EncJob* __re
   const int CW = g.W >> 1, CH = g.H >> 1;
   const vp8gpu_quant q = J.q;
 
+  int left_mvx = 0, left_mvy = 0;
+  bool left_inter = false;
   for (int col = 0; col < cols; col++) {
     const int mbi = row * cols + col;
-    // ---- source macroblock (96 words) and, for inter frames, the motion-compensated candidate ----
+    // ---- source macroblock (96 words) ----
     for (int i = lane; i < 96; i += 32) {
       const uint8_t* gp;
       if (i < 64) gp = J.src + (size_t)(16 * row + (i >> 2)) * g.y_pitch + 16 * col + 4 * (i & 3);
@@ -1110,19 +1112,43 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 12) k_enc_mb(const EncJob* __re
       reinterpret_cast<uint32_t*>(src)[i] = __ldg(reinterpret_cast<const uint32_t*>(gp));
     }
     int mvx = 0, mvy = 0, cost_inter = 0x7fffffff;
+    __syncwarp();
+    if (row > 0) wait_row(progress - 1, min(col + 2, cols), lane);
     if (!J.key_frame) {
-      mvx = J.mv[2 * mbi];
-      mvy = J.mv[2 * mbi + 1];
+      // candidate vectors: the searched one, zero, and the vectors the left / above macroblocks chose
+      // (cheap to code: they become ZEROMV / NEARESTMV / NEARMV in the bitstream).  A candidate's cost
+      // is its luma SAD plus lambda * (rough bits of the mode + vector), lambda ~ quantiser step.
+      const int lambda = max(1, (int)q.y_ac >> 3);
+      int best_cost = 0x7fffffff;
+      int cand_x[4], cand_y[4], cand_bits[4], n_cand = 0;
+      cand_x[n_cand] = 0, cand_y[n_cand] = 0, cand_bits[n_cand++] = 2;
+      if (col > 0 && left_inter && (left_mvx | left_mvy)) cand_x[n_cand] = left_mvx, cand_y[n_cand] = left_mvy, cand_bits[n_cand++] = 4;
+      if (row > 0) {
+        const uint4 ar = __ldcg(reinterpret_cast<const uint4*>(J.mbs + mbi - cols));
+        const int a_ref = ar.z & 0xFF, ax = (int16_t)(ar.w & 0xFFFF), ay = (int16_t)(ar.w >> 16);
+        if (a_ref != VP8GPU_REF_CURRENT && (ax | ay) && !(n_cand == 2 && ax == cand_x[1] && ay == cand_y[1]))
+          cand_x[n_cand] = ax, cand_y[n_cand] = ay, cand_bits[n_cand++] = 4;
+      }
+      {
+        const int sx = J.mv[2 * mbi], sy = J.mv[2 * mbi + 1];
+        bool dup = false;
+        for (int k = 0; k < n_cand; k++) dup |= cand_x[k] == sx && cand_y[k] == sy;
+        if (!dup) cand_x[n_cand] = sx, cand_y[n_cand] = sy, cand_bits[n_cand++] = 16;
+      }
+      for (int k = 0; k < n_cand; k++) {
+        mc_block<16>(J.ref, g.y_pitch, g.W, g.H, 16 * col, 16 * row, cand_x[k], cand_y[k], pinter, 16, s_tile[warp], s_mid[warp], lane);
+        const int c = sad_16x16(src, pinter, lane) + lambda * cand_bits[k];
+        if (c < best_cost) best_cost = c, mvx = cand_x[k], mvy = cand_y[k];
+      }
       const int cmx = chroma_component(4 * mvx), cmy = chroma_component(4 * mvy);
       mc_block<16>(J.ref, g.y_pitch, g.W, g.H, 16 * col, 16 * row, mvx, mvy, pinter, 16, s_tile[warp], s_mid[warp], lane);
       mc_block<8>(J.ref + g.u_off, g.c_pitch, CW, CH, 8 * col, 8 * row, cmx, cmy, pinter + 256, 8, s_tile[warp], s_mid[warp], lane);
       mc_block<8>(J.ref + g.v_off, g.c_pitch, CW, CH, 8 * col, 8 * row, cmx, cmy, pinter + 320, 8, s_tile[warp], s_mid[warp], lane);
       int acc = 0;
-      for (int i = lane; i < 384; i += 32) acc += abs((int)src[i] - (int)pinter[i]);
-      cost_inter = warp_sum(acc);
+      for (int i = 256 + lane; i < 384; i += 32) acc += abs((int)src[i] - (int)pinter[i]);
+      cost_inter = best_cost + warp_sum(acc);
     }
     __syncwarp();
-    if (row > 0) wait_row(progress - 1, min(col + 2, cols), lane);
 
     // ---- edges of the reconstruction so far (same rules as the decoder, prediction.cc:99-167) ----
     {
@@ -1218,7 +1244,7 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 12) k_enc_mb(const EncJob* __re
     if (cs3 < sadC) sadC = cs3, uv_mode = VP8GPU_TM_PRED;
 
     // ---- inter or intra?  (intra macroblocks of inter frames cost more header bits: small bias) ----
-    const bool inter = !J.key_frame && cost_inter <= sadY + sadC + 192;
+    const bool inter = !J.key_frame && cost_inter <= sadY + sadC + max(1, (int)q.y_ac >> 3) * 12;
 
     // ---- materialise the chosen prediction in the workspace ----
     if (inter) {
@@ -1357,6 +1383,9 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 12) k_enc_mb(const EncJob* __re
       m.b_modes = 0;
       J.mbs[mbi] = m;
     }
+    left_mvx = inter ? mvx : 0;
+    left_mvy = inter ? mvy : 0;
+    left_inter = inter;
     publish_row(progress, col + 1, lane);
   }
 }
