@@ -29,11 +29,18 @@ void BoolWriter::put(int bit, int prob) {
   } else {
     range_ = split;
   }
-  while (range_ < 128) {
-    range_ <<= 1;
-    if (bottom_ & (1u << 31)) add_one();
-    bottom_ <<= 1;
-    if (!--bit_count_) {
+  // renormalise: same effect as shifting one bit at a time (RFC 6386 section 7.3), done in one step
+  int shift = __builtin_clz(range_) - 24;
+  range_ <<= shift;
+  while (shift > 0) {
+    const int n = shift < bit_count_ ? shift : bit_count_;  // bits until the next output byte
+    // bits leaving the top are carries into bytes already written
+    for (uint32_t carry = static_cast<uint32_t>((static_cast<uint64_t>(bottom_) << n) >> 32); carry; carry &= carry - 1)
+      add_one();
+    bottom_ <<= n;
+    bit_count_ -= n;
+    shift -= n;
+    if (!bit_count_) {
       out_.push_back(static_cast<uint8_t>(bottom_ >> 24));
       bottom_ &= (1u << 24) - 1;
       bit_count_ = 8;
