@@ -65,6 +65,8 @@ MB_DTYPE = np.dtype([("tok_off", "<u4"), ("tok_cnt", "<u2"), ("y_mode", "u1"), (
                      ("mv_x", "<i2"), ("mv_y", "<i2"), ("split_idx", "<u4"), ("reserved", "<u4"),
                      ("b_modes", "<u8")])
 
+OPT_DEVICE_TOKENS = 1  # VP8GPU_OPT_DEVICE_TOKENS
+
 # every symbol include/vp8gpu.h declares: name -> (restype, argtypes)
 _vp = C.c_void_p
 _pp = C.POINTER(C.c_void_p)
@@ -104,6 +106,9 @@ SYMBOLS = {
     "vp8gpu_parsed_tokens": (_vp, [_vp]),
     "vp8gpu_parsed_split": (_vp, [_vp]),
     "vp8gpu_parse_frame": (C.c_int, [_vp, C.c_char_p, C.c_size_t, _vp]),
+    "vp8gpu_parse_frame_device": (C.c_int, [_vp, _vp, C.c_char_p, C.c_size_t, _vp]),
+    "vp8gpu_ctx_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "vp8gpu_decoder_set_device_tokens": (C.c_int, [_vp, C.c_int]),
     "vp8gpu_decoder_create": (C.c_int, [_vp, _pp]),
     "vp8gpu_decoder_create_from": (C.c_int, [_vp, _vp, C.POINTER(C.c_int32), _pp]),
     "vp8gpu_decoder_clone": (C.c_int, [_vp, _pp]),

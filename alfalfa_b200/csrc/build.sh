@@ -8,16 +8,17 @@ ARCH="-gencode arch=compute_100a,code=sm_100a"
 FLAGS="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wextra,-pthread"
 mkdir -p build
 $NVCC $ARCH $FLAGS -Xptxas -v -c kernels.cu -o build/kernels.o 2> build/ptxas_kernels.log || { cat build/ptxas_kernels.log; exit 1; }
+$NVCC $ARCH $FLAGS -Xptxas -v -c tokens.cu -o build/tokens.o 2> build/ptxas_tokens.log || { cat build/ptxas_tokens.log; exit 1; }
 $NVCC $ARCH $FLAGS -c engine.cu -o build/engine.o
 $NVCC $FLAGS -x cu $ARCH -c capi.cc -o build/capi.o
 $NVCC $ARCH $FLAGS -c encoder.cu -o build/encoder.o
 g++ -O3 -std=c++17 -fPIC -Wall -Wextra -c parser.cc -o build/parser.o
 g++ -O3 -std=c++17 -fPIC -Wall -Wextra -c serializer.cc -o build/serializer.o
-$NVCC $ARCH -shared -o ../libvp8gpu.so build/kernels.o build/engine.o build/capi.o build/encoder.o build/parser.o build/serializer.o -Xcompiler -pthread
+$NVCC $ARCH -shared -o ../libvp8gpu.so build/kernels.o build/tokens.o build/engine.o build/capi.o build/encoder.o build/parser.o build/serializer.o -Xcompiler -pthread
 echo "built $(cd .. && pwd)/libvp8gpu.so"
 # optional: phase-profiling variant of the library (tools/phase_profile.py)
 if [ "$1" = "prof" ]; then
   $NVCC $ARCH $FLAGS -DVP8_PROFILE -c kernels.cu -o build/kernels_prof.o
-  $NVCC $ARCH -shared -o ../libvp8gpu_prof.so build/kernels_prof.o build/engine.o build/capi.o build/encoder.o build/parser.o build/serializer.o -Xcompiler -pthread
+  $NVCC $ARCH -shared -o ../libvp8gpu_prof.so build/kernels_prof.o build/tokens.o build/engine.o build/capi.o build/encoder.o build/parser.o build/serializer.o -Xcompiler -pthread
   echo "built libvp8gpu_prof.so"
 fi

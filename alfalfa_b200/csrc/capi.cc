@@ -36,6 +36,13 @@ struct vp8gpu_ctx {
   std::vector<vp8gpu_parsed*> pinned_pool;
   // wall-clock accounting of the last vp8gpu_decode_ivf call (seconds, summed over threads)
   double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // device-side token decoding: option, a one-slot ring for vp8gpu_parse_frame_device, and the
+  // rings / streams of vp8gpu_decode_ivf's workers (kept between calls: cudaMalloc / cudaHostAlloc
+  // of hundreds of MB are slow)
+  std::atomic<int> device_tokens{1};
+  std::mutex scratch_mu;
+  vp8::TokenRing* scratch_ring = nullptr;
+  std::vector<struct ivf_worker_kit*> kit_pool;
 };
 struct vp8gpu_state {
   State s;
@@ -48,6 +55,16 @@ struct vp8gpu_parsed {
   cudaEvent_t consumed = nullptr;  // set for pinned instances owned by a decoder
   bool busy = false;
   explicit vp8gpu_parsed(const vp8::Allocator& a) : f(a) {}
+};
+// what one vp8gpu_decode_ivf worker needs for device-side token decoding
+constexpr int kTokSlots = 24;  // frames a worker may have between "first partition parsed" and "pixels done"
+constexpr int kTokChunk = 8;   // frames per k_tokens launch
+struct ivf_worker_kit {
+  vp8::TokenRing* ring = nullptr;
+  cudaStream_t stream = nullptr;
+  vp8gpu_parsed* parsed[kTokSlots] = {};
+  cudaEvent_t ready[kTokSlots] = {}, finished[kTokSlots] = {};
+  bool busy[kTokSlots] = {};
 };
 struct vp8gpu_resident_batch {
   Engine::Resident* r = nullptr;
@@ -101,6 +118,18 @@ int vp8gpu_ctx_create(int device, int width, int height, int max_frames, vp8gpu_
 void vp8gpu_ctx_destroy(vp8gpu_ctx* ctx) {
   if (!ctx) return;
   for (vp8gpu_parsed* p : ctx->pinned_pool) vp8gpu_parsed_destroy(p);
+  ctx->engine->sync_all();
+  if (ctx->scratch_ring) ctx->engine->token_ring_free(ctx->scratch_ring);
+  for (ivf_worker_kit* k : ctx->kit_pool) {
+    ctx->engine->token_ring_free(k->ring);
+    if (k->stream) cudaStreamDestroy(k->stream);
+    for (int i = 0; i < kTokSlots; i++) {
+      if (k->parsed[i]) vp8gpu_parsed_destroy(k->parsed[i]);
+      if (k->ready[i]) cudaEventDestroy(k->ready[i]);
+      if (k->finished[i]) cudaEventDestroy(k->finished[i]);
+    }
+    delete k;
+  }
   delete ctx->engine;
   delete ctx;
 }
@@ -265,6 +294,57 @@ int vp8gpu_parse_frame(vp8gpu_state* state, const uint8_t* data, size_t len, vp8
   return rc;
 }
 
+int vp8gpu_ctx_set_option(vp8gpu_ctx* ctx, int option, int value) {
+  if (!ctx) return VP8GPU_ERR_LOGIC;
+  if (option == VP8GPU_OPT_DEVICE_TOKENS) {
+    ctx->device_tokens = value != 0;
+    return VP8GPU_OK;
+  }
+  return ctx->engine->fail(VP8GPU_ERR_LOGIC, "unknown context option");
+}
+
+int vp8gpu_parse_frame_device(vp8gpu_ctx* ctx, vp8gpu_state* state, const uint8_t* data, size_t len,
+                              vp8gpu_parsed* out) {
+  if (!ctx || !state || !data || !out) return VP8GPU_ERR_LOGIC;
+  Engine* e = ctx->engine;
+  cudaSetDevice(e->device());
+  int rc = vp8::parse_frame(state->s, data, len, out->f, true);
+  if (rc != VP8GPU_OK) return rc;
+  std::lock_guard<std::mutex> lk(ctx->scratch_mu);
+  if (ctx->scratch_ring && ctx->scratch_ring->bits_cap < out->f.tw.bits_len) {
+    e->sync_all();
+    e->token_ring_free(ctx->scratch_ring);
+    ctx->scratch_ring = nullptr;
+  }
+  if (!ctx->scratch_ring) {
+    rc = e->token_ring_create(1, len * 2 + 4096, &ctx->scratch_ring);
+    if (rc != VP8GPU_OK) return rc;
+  }
+  vp8::TokenRing* r = ctx->scratch_ring;
+  rc = e->ensure_lane(0);
+  if (rc != VP8GPU_OK) return rc;
+  cudaStream_t s = e->stream(0);
+  rc = e->token_ring_stage(r, 0, out->f, s);
+  if (rc == VP8GPU_OK) rc = e->token_ring_launch(r, 0, 1, s);
+  uint32_t result[2] = {0, 0};
+  if (rc == VP8GPU_OK) rc = e->token_ring_result(r, 0, s, result);
+  if (rc != VP8GPU_OK) return rc;
+  if (result[1] || result[0] > r->tok_cap) return e->fail(VP8GPU_ERR_NOMEM, "device token pool overflow");
+  const vp8gpu_frame_desc& d = out->f.desc;
+  const size_t n_mbs = (size_t)d.mb_cols * d.mb_rows;
+  if (!out->f.tokens.reserve(result[0] + 1, 0)) return VP8GPU_ERR_NOMEM;
+  if (cudaMemcpyAsync(out->f.mbs.data(), r->dev_slot(0) + r->mbs_off, n_mbs * sizeof(vp8gpu_mb), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+      (result[0] && cudaMemcpyAsync(out->f.tokens.data(), r->dev_slot(0) + r->tok_off, (size_t)result[0] * sizeof(vp8gpu_token),
+                                    cudaMemcpyDeviceToHost, s) != cudaSuccess) ||
+      cudaStreamSynchronize(s) != cudaSuccess)
+    return e->fail(VP8GPU_ERR_CUDA, "parse_frame_device: copy back failed");
+  out->f.desc.n_tokens = result[0];
+  out->f.tw.deferred = false;
+  out->f.tw.bits = nullptr;
+  count_mbs(out);
+  return VP8GPU_OK;
+}
+
 }  // extern "C"
 
 // =============================================================================================
@@ -279,6 +359,12 @@ struct vp8gpu_decoder {
   // is still reading frame N's records
   vp8gpu_parsed* ring[vp8::kStagingDepth] = {};
   int ring_next = 0;
+  // optional device-side token decoding (vp8gpu_decoder_set_device_tokens)
+  bool device_tokens = false;
+  vp8::TokenRing* tok_ring = nullptr;
+  cudaEvent_t tok_finished[vp8::kStagingDepth] = {};
+  bool tok_busy[vp8::kStagingDepth] = {};
+  int tok_next = 0;
   vp8gpu_decoder(vp8gpu_ctx* c, int w, int h) : ctx(c), state(w, h) {}
   vp8gpu_decoder(vp8gpu_ctx* c, const State& s) : ctx(c), state(s) {}
 };
@@ -324,7 +410,8 @@ vp8gpu_parsed* next_ring_slot(vp8gpu_decoder* d) {
 
 // Decoder::decode_frame (decoder.cc:101-118): decode + loopfilter into a fresh raster, then
 // Frame::copy_to (frame.cc:272-307) on the references.
-int decode_parsed_impl(vp8gpu_decoder* d, vp8gpu_parsed* p, bool pinned_ring, int* shown, int* out_id) {
+int decode_parsed_impl(vp8gpu_decoder* d, vp8gpu_parsed* p, bool pinned_ring, int* shown, int* out_id,
+                       int tok_slot = -1) {
   Engine* e = d->ctx->engine;
   const vp8gpu_frame_desc& desc = p->f.desc;
   int out = -1;
@@ -339,6 +426,11 @@ int decode_parsed_impl(vp8gpu_decoder* d, vp8gpu_parsed* p, bool pinned_ring, in
   j.out = out;
   j.n_intra = (int)p->n_intra;
   j.n_filtered = (int)p->n_filtered;
+  if (tok_slot >= 0) {  // records and tokens are already in the ring, produced on this lane's stream
+    j.ring = d->tok_ring;
+    j.ring_slot = tok_slot;
+    j.finished = d->tok_finished[tok_slot];
+  }
   rc = e->submit(d->lane, &j, 1, pinned_ring ? p->consumed : nullptr);
   if (rc != VP8GPU_OK) {
     e->frame_release(out);
@@ -429,17 +521,64 @@ void vp8gpu_decoder_destroy(vp8gpu_decoder* d) {
     for (auto& p : d->ring)
       if (p) d->ctx->pinned_pool.push_back(p);
   }
+  if (d->tok_ring) {
+    e->sync_lane(d->lane);
+    e->token_ring_free(d->tok_ring);
+  }
+  for (auto& ev : d->tok_finished)
+    if (ev) cudaEventDestroy(ev);
   delete d;
+}
+
+int vp8gpu_decoder_set_device_tokens(vp8gpu_decoder* d, int on) {
+  if (!d) return VP8GPU_ERR_LOGIC;
+  d->device_tokens = on != 0;
+  return VP8GPU_OK;
 }
 
 int vp8gpu_decoder_decode(vp8gpu_decoder* d, const uint8_t* data, size_t len, int* shown, vp8gpu_frame_id* out) {
   if (!d || !data) return VP8GPU_ERR_LOGIC;
-  cudaSetDevice(d->ctx->engine->device());
+  Engine* e = d->ctx->engine;
+  cudaSetDevice(e->device());
   vp8gpu_parsed* p = next_ring_slot(d);
-  const int rc = vp8::parse_frame(d->state.s, data, len, p->f);
-  if (rc != VP8GPU_OK) return d->ctx->engine->fail(rc, "parse_frame failed");
+  if (!d->device_tokens) {
+    const int rc = vp8::parse_frame(d->state.s, data, len, p->f);
+    if (rc != VP8GPU_OK) return e->fail(rc, "parse_frame failed");
+    count_mbs(p);
+    return decode_parsed_impl(d, p, true, shown, out);
+  }
+  // host: first partition; device: DCT partitions, then the pixel kernels, all on this lane
+  int rc = e->ensure_lane(d->lane);
+  if (rc != VP8GPU_OK) return rc;
+  if (d->tok_ring && d->tok_ring->bits_cap < len) {
+    e->sync_lane(d->lane);
+    e->token_ring_free(d->tok_ring);
+    d->tok_ring = nullptr;
+    for (bool& b : d->tok_busy) b = false;
+  }
+  if (!d->tok_ring) {
+    rc = e->token_ring_create(vp8::kStagingDepth, len * 2 + 65536, &d->tok_ring);
+    if (rc != VP8GPU_OK) return rc;
+    for (auto& ev : d->tok_finished)
+      if (!ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  }
+  const int slot = d->tok_next;
+  d->tok_next = (d->tok_next + 1) % vp8::kStagingDepth;
+  if (d->tok_busy[slot]) {
+    cudaEventSynchronize(d->tok_finished[slot]);
+    d->tok_busy[slot] = false;
+  }
+  rc = vp8::parse_frame(d->state.s, data, len, p->f, true);
+  if (rc != VP8GPU_OK) return e->fail(rc, "parse_frame failed");
   count_mbs(p);
-  return decode_parsed_impl(d, p, true, shown, out);
+  cudaStream_t s = e->stream(d->lane);
+  rc = e->token_ring_stage(d->tok_ring, slot, p->f, s);
+  if (rc == VP8GPU_OK) rc = e->token_ring_launch(d->tok_ring, slot, 1, s);
+  if (rc != VP8GPU_OK) return rc;
+  p->f.tw.bits = nullptr;  // staged: the caller's buffer is no longer needed
+  rc = decode_parsed_impl(d, p, true, shown, out, slot);
+  if (rc == VP8GPU_OK) d->tok_busy[slot] = true;
+  return rc;
 }
 
 int vp8gpu_decoder_decode_parsed(vp8gpu_decoder* d, const vp8gpu_parsed* parsed, int* shown, vp8gpu_frame_id* out) {
@@ -517,6 +656,17 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
   if (threads < 1) threads = 1;
   if (threads > 256) threads = 256;
   if (threads > n_gops) threads = n_gops > 0 ? n_gops : 1;
+  // device-side token decoding needs rasters for the frames a worker keeps in flight
+  uint32_t max_frame_bytes = 0;
+  for (const Item& it : items) max_frame_bytes = it.n > max_frame_bytes ? it.n : max_frame_bytes;
+  int tok_slots = 0;
+  if (ctx->device_tokens.load()) {
+    tok_slots = e->frames_free() / threads - 4;
+    if (tok_slots > kTokSlots) tok_slots = kTokSlots;
+    if (tok_slots < 4) tok_slots = 0;  // pool too small: the host workers parse everything
+  }
+  const bool device_tokens = tok_slots > 0;
+  const int tok_chunk = tok_slots >= 2 * kTokChunk ? kTokChunk : (tok_slots / 2 > 0 ? tok_slots / 2 : 1);
 
   // Host workers only parse (CPU entropy front end) and keep the per-GOP codec state; a single
   // dispatcher gathers whatever they have produced -- at most one frame per worker, because
@@ -532,6 +682,10 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     int out;
     int64_t out_off;
     int* slot_state;
+    // device-side tokens: the records live in ring slot `ring_slot` once `ready` has fired
+    const vp8::TokenRing* ring = nullptr;
+    int ring_slot = 0;
+    cudaEvent_t ready = nullptr, finished = nullptr;
   };
   std::mutex mu;
   std::condition_variable cv_workers, cv_dispatch;
@@ -665,6 +819,165 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
       }
   };
 
+  // ---- workers with device-side token decoding: the host only walks the first partition; the DCT
+  //      partitions of up to tok_chunk frames go to the device in one k_tokens launch on the worker's
+  //      own stream, tok_slots frames may be in flight per worker, and the dispatcher picks a frame up
+  //      once its `ready` event has fired ----
+  auto acquire_kit = [&]() -> ivf_worker_kit* {
+    ivf_worker_kit* k = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(ctx->pool_mu);
+      for (size_t i = 0; i < ctx->kit_pool.size(); i++)
+        if (ctx->kit_pool[i]->ring->bits_cap >= max_frame_bytes + 16) {
+          k = ctx->kit_pool[i];
+          ctx->kit_pool.erase(ctx->kit_pool.begin() + i);
+          break;
+        }
+    }
+    if (k) return k;
+    k = new ivf_worker_kit();
+    if (e->token_ring_create(kTokSlots, (size_t)max_frame_bytes + max_frame_bytes / 4 + 4096, &k->ring) != VP8GPU_OK ||
+        cudaStreamCreateWithFlags(&k->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      if (k->ring) e->token_ring_free(k->ring);
+      delete k;
+      return nullptr;
+    }
+    const size_t n_mbs = (size_t)e->geom().mb_cols * e->geom().mb_rows;
+    for (int i = 0; i < kTokSlots; i++) {
+      k->parsed[i] = new vp8gpu_parsed(kPinned);
+      k->parsed[i]->f.mbs.reserve(n_mbs, 0);
+      k->parsed[i]->f.split.reserve(256, 0);
+      cudaEventCreateWithFlags(&k->ready[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&k->finished[i], cudaEventDisableTiming);
+    }
+    return k;
+  };
+  auto worker_dev = [&](int tid) {
+    cudaSetDevice(e->device());
+    double t_parse = 0, t_slot = 0, t_dma = 0;
+    State state(w, h);
+    int refs[3] = {-1, -1, -1};
+    int slot_state[kTokSlots] = {};
+    int next_slot = 0;
+    int rc = VP8GPU_OK;
+    ivf_worker_kit* kit = acquire_kit();
+    if (!kit) rc = e->fail(VP8GPU_ERR_NOMEM, "decode_ivf: token ring allocation failed");
+    while (rc == VP8GPU_OK) {
+      const int g = next_gop.fetch_add(1);
+      if (g >= n_gops || first_error.load() != VP8GPU_OK) break;
+      uint32_t i = gop_start[g];
+      while (i < gop_start[g + 1] && rc == VP8GPU_OK) {
+        const uint32_t left = gop_start[g + 1] - i;
+        const int n = (int)left < tok_chunk ? (int)left : tok_chunk;
+        const int first_slot = next_slot;
+        int staged = 0;
+        for (int c = 0; c < n && rc == VP8GPU_OK; c++) {
+          const int si = (first_slot + c) % tok_slots;
+          const double t0 = now();
+          {  // the dispatcher must have submitted the slot's previous frame ...
+            std::unique_lock<std::mutex> lk(mu);
+            cv_workers.wait(lk, [&] { return slot_state[si] == kFree; });
+          }
+          const double t1 = now();
+          if (kit->busy[si]) {  // ... and the pixel kernels must have read its records
+            cudaEventSynchronize(kit->finished[si]);
+            kit->busy[si] = false;
+          }
+          const double t2 = now();
+          vp8gpu_parsed* p = kit->parsed[si];
+          rc = vp8::parse_frame(state, items[i + c].p, items[i + c].n, p->f, true);
+          if (rc != VP8GPU_OK) break;
+          count_mbs(p);
+          rc = e->token_ring_stage(kit->ring, si, p->f, kit->stream);
+          if (rc != VP8GPU_OK) break;
+          staged++;
+          t_slot += t1 - t0;
+          t_dma += t2 - t1;
+          t_parse += now() - t2;
+        }
+        if (rc != VP8GPU_OK) break;
+        // the ring is used modulo tok_slots (<= its real size): a chunk that wraps needs two launches
+        const int until_wrap = tok_slots - first_slot;
+        rc = e->token_ring_launch(kit->ring, first_slot, staged < until_wrap ? staged : until_wrap, kit->stream);
+        if (rc == VP8GPU_OK && staged > until_wrap) rc = e->token_ring_launch(kit->ring, 0, staged - until_wrap, kit->stream);
+        if (rc != VP8GPU_OK) break;
+        for (int c = 0; c < staged; c++) cudaEventRecord(kit->ready[(first_slot + c) % tok_slots], kit->stream);
+        for (int c = 0; c < staged && rc == VP8GPU_OK; c++) {
+          const int si = (first_slot + c) % tok_slots;
+          vp8gpu_parsed* p = kit->parsed[si];
+          const vp8gpu_frame_desc& desc = p->f.desc;
+          Pending job;
+          job.slot = p;
+          job.slot_state = &slot_state[si];
+          job.out_off = (dst && desc.show_frame) ? items[i + c].out_off : -1;
+          job.ring = kit->ring;
+          job.ring_slot = si;
+          job.ready = kit->ready[si];
+          job.finished = kit->finished[si];
+          rc = e->frame_alloc(&job.out);
+          if (rc != VP8GPU_OK) break;
+          for (int k = 0; k < 3; k++) {
+            job.refs[k] = desc.key_frame ? -1 : refs[k];
+            if (job.refs[k] >= 0) e->frame_retain(job.refs[k]);
+          }
+          const int out = job.out;  // Frame::copy_to (frame.cc:272-307)
+          if (desc.key_frame) {
+            set_ref(e, &refs[0], out);
+            set_ref(e, &refs[1], out);
+            set_ref(e, &refs[2], out);
+          } else {
+            if (desc.copy_to_alternate == 1) set_ref(e, &refs[2], refs[0]);
+            else if (desc.copy_to_alternate == 2) set_ref(e, &refs[2], refs[1]);
+            if (desc.copy_to_golden == 1) set_ref(e, &refs[1], refs[0]);
+            else if (desc.copy_to_golden == 2) set_ref(e, &refs[1], refs[2]);
+            if (desc.refresh_golden) set_ref(e, &refs[1], out);
+            if (desc.refresh_alternate) set_ref(e, &refs[2], out);
+            if (desc.refresh_last) set_ref(e, &refs[0], out);
+          }
+          kit->busy[si] = true;
+          {
+            std::lock_guard<std::mutex> lk(mu);
+            slot_state[si] = kQueued;
+            queues[tid].push_back(job);
+          }
+          cv_dispatch.notify_one();
+        }
+        next_slot = (first_slot + staged) % tok_slots;
+        i += (uint32_t)staged;
+      }
+      if (rc != VP8GPU_OK) break;
+    }
+    if (rc != VP8GPU_OK) set_error(rc);
+    {  // wait until everything this worker queued has been submitted, then retire
+      std::unique_lock<std::mutex> lk(mu);
+      cv_workers.wait(lk, [&] {
+        for (int k = 0; k < kTokSlots; k++)
+          if (slot_state[k] != kFree) return false;
+        return true;
+      });
+      workers_running--;
+    }
+    cv_dispatch.notify_one();
+    {
+      std::lock_guard<std::mutex> lk(stats_mu);
+      st_parse += t_parse;
+      st_wait_slot += t_slot;
+      st_wait_dma += t_dma;
+    }
+    for (int k = 0; k < 3; k++)
+      if (refs[k] >= 0) e->frame_release(refs[k]);
+    if (kit) {
+      for (int k = 0; k < kTokSlots; k++)
+        if (kit->busy[k]) {
+          cudaEventSynchronize(kit->finished[k]);
+          kit->busy[k] = false;
+        }
+      cudaStreamSynchronize(kit->stream);
+      std::lock_guard<std::mutex> lk(ctx->pool_mu);
+      ctx->kit_pool.push_back(kit);
+    }
+  };
+
   auto dispatcher = [&]() {
     cudaSetDevice(e->device());
     std::vector<Pending> batch;
@@ -675,25 +988,43 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
       const double ti = now();
       {
         std::unique_lock<std::mutex> lk(mu);
+        // a queue's front is eligible once its tokens are in HBM (device-side token decoding)
+        auto eligible = [&](const std::deque<Pending>& q) {
+          return !q.empty() && (!q.front().ready || cudaEventQuery(q.front().ready) == cudaSuccess);
+        };
         auto ready = [&] {
           int n = 0;
-          for (auto& q : queues) n += !q.empty();
+          for (auto& q : queues) n += eligible(q);
           return n;
         };
-        cv_dispatch.wait(lk, [&] { return workers_running == 0 || ready() > 0; });
+        auto queued = [&] {
+          for (auto& q : queues)
+            if (!q.empty()) return true;
+          return false;
+        };
+        // nothing signals the condition variable when a CUDA event fires: poll while frames wait for one
+        while (!(workers_running == 0 && !queued()) && ready() == 0) {
+          if (queued()) cv_dispatch.wait_for(lk, std::chrono::microseconds(100));
+          else cv_dispatch.wait(lk);
+        }
         // Device time per batch is almost flat in the number of frames (the wavefront kernels
         // are latency bound), so give the other workers a moment to finish their current frame:
         // go once most of them have something queued, or after a short grace period.
         const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(1500);
         while (workers_running > 0 && ready() < (workers_running * 3 + 3) / 4) {
-          if (cv_dispatch.wait_until(lk, deadline) == std::cv_status::timeout) break;
+          if (device_tokens) {
+            if (std::chrono::steady_clock::now() >= deadline) break;
+            cv_dispatch.wait_for(lk, std::chrono::microseconds(100));
+          } else if (cv_dispatch.wait_until(lk, deadline) == std::cv_status::timeout) {
+            break;
+          }
         }
         for (auto& q : queues)
-          if (!q.empty()) {
+          if (eligible(q)) {
             batch.push_back(q.front());
             q.pop_front();
           }
-        if (batch.empty() && workers_running == 0) break;
+        if (batch.empty() && workers_running == 0 && !queued()) break;
       }
       if (batch.empty()) continue;
       const double ts = now();
@@ -713,6 +1044,13 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
         j.n_intra = (int)b.slot->n_intra;
         j.n_filtered = (int)b.slot->n_filtered;
         j.consumed = b.slot->consumed;  // fires as soon as the records are in HBM, before the kernels
+        if (b.ring) {
+          j.ring = b.ring;
+          j.ring_slot = b.ring_slot;
+          j.ready = nullptr;  // already fired (eligible() checked it)
+          j.finished = b.finished;
+          j.consumed = nullptr;
+        }
         hj.push_back(j);
       }
       int rc = e->submit(lane, hj.data(), (int)hj.size(), nullptr);
@@ -720,7 +1058,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
       st_submit += td - ts;
       for (const Pending& b : batch) {
         if (rc == VP8GPU_OK) {
-          b.slot->busy = true;
+          if (!b.ring) b.slot->busy = true;
           if (b.out_off >= 0) {
             const int r2 = e->frame_download_display(b.out, lane, dst + b.out_off, frame_bytes, false);
             if (r2 != VP8GPU_OK) rc = r2;
@@ -742,7 +1080,10 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
   };
 
   std::vector<std::thread> pool;
-  for (int t = 0; t < threads; t++) pool.emplace_back(worker, t);
+  for (int t = 0; t < threads; t++) {
+    if (device_tokens) pool.emplace_back(worker_dev, t);
+    else pool.emplace_back(worker, t);
+  }
   dispatcher();
   for (auto& t : pool) t.join();
   ctx->stats[0] = st_parse;

@@ -78,6 +78,7 @@ Engine::~Engine() {
     if (f.dev) cudaFree(f.dev);
     for (auto& ev : f.ev)
       if (ev) cudaEventDestroy(ev);
+    if (f.wev) cudaEventDestroy(f.wev);
   }
   for (int l = 0; l < kMaxLanes; l++)
     for (auto& s : staging_[l]) {
@@ -131,14 +132,31 @@ int Engine::frame_release(int id) {
   return VP8GPU_OK;
 }
 
-// caller holds mu_
-int Engine::touch(Frame& f, int slot) {
+int Engine::frames_free() {
+  std::lock_guard<std::mutex> lk(mu_);
+  return (int)free_.size();
+}
+
+// Stream ordering of rasters.  A raster remembers the stream slot that last WROTE it (wev) and the
+// slots that READ it since (ev[slot]): a reader only waits for the writer, so that e.g. the
+// download of a frame does not delay the next frame's motion compensation from it; a writer
+// (a recycled raster) waits for everybody.  Caller holds mu_.
+int Engine::touch(Frame& f, int slot, bool write) {
+  if (write) {
+    if (!f.wev) CU(cudaEventCreateWithFlags(&f.wev, cudaEventDisableTiming));
+    CU(cudaEventRecord(f.wev, lanes_[slot]));
+    f.wslot = slot;
+    f.pending = 0;  // the preceding wait_for(write) ordered this stream after every reader
+    return VP8GPU_OK;
+  }
   if (!f.ev[slot]) CU(cudaEventCreateWithFlags(&f.ev[slot], cudaEventDisableTiming));
   CU(cudaEventRecord(f.ev[slot], lanes_[slot]));
   f.pending |= 1ull << slot;
   return VP8GPU_OK;
 }
-int Engine::wait_for(Frame& f, int slot, cudaStream_t s) {
+int Engine::wait_for(Frame& f, int slot, cudaStream_t s, bool write) {
+  if (f.wslot >= 0 && f.wslot != slot) CU(cudaStreamWaitEvent(s, f.wev, 0));
+  if (!write) return VP8GPU_OK;
   uint64_t m = f.pending & ~(1ull << slot);
   while (m) {
     const int t = __builtin_ctzll(m);
@@ -154,7 +172,6 @@ int Engine::frame_clear(int id, int lane) {
   Frame& f = frames_[id];
   if (int rc = wait_for(f, lane, lanes_[lane])) return rc;
   CU(cudaMemsetAsync(f.dev, 0, g_.frame_bytes, lanes_[lane]));
-  f.pending = 0;
   return touch(f, lane);
 }
 
@@ -168,7 +185,6 @@ int Engine::frame_upload(int id, const uint8_t* y, size_t ys, const uint8_t* u, 
   CU(cudaMemcpy2DAsync(f.dev, g_.y_pitch, y, ys, g_.W, g_.H, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpy2DAsync(f.dev + g_.u_off, g_.c_pitch, u, cs, g_.W / 2, g_.H / 2, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpy2DAsync(f.dev + g_.v_off, g_.c_pitch, v, cs, g_.W / 2, g_.H / 2, cudaMemcpyHostToDevice, s));
-  f.pending = 0;
   if (int rc = touch(f, 0)) return rc;
   CU(cudaStreamSynchronize(s));
   return VP8GPU_OK;
@@ -183,11 +199,11 @@ int Engine::frame_download(int id, uint8_t* y, size_t ys, uint8_t* u, uint8_t* v
     Frame& f = frames_[id];
     const int slot = kMaxLanes + 0;
     s = lanes_[slot];
-    if (int rc = wait_for(f, slot, s)) return rc;
+    if (int rc = wait_for(f, slot, s, false)) return rc;
     CU(cudaMemcpy2DAsync(y, ys, f.dev, g_.y_pitch, g_.W, g_.H, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpy2DAsync(u, cs, f.dev + g_.u_off, g_.c_pitch, g_.W / 2, g_.H / 2, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpy2DAsync(v, cs, f.dev + g_.v_off, g_.c_pitch, g_.W / 2, g_.H / 2, cudaMemcpyDeviceToHost, s));
-    if (int rc = touch(f, slot)) return rc;
+    if (int rc = touch(f, slot, false)) return rc;
   }
   CU(cudaStreamSynchronize(s));
   return VP8GPU_OK;
@@ -205,14 +221,14 @@ int Engine::frame_download_display(int id, int lane, uint8_t* dst, size_t dst_si
     Frame& f = frames_[id];
     const int slot = kMaxLanes + lane;
     s = lanes_[slot];
-    if (int rc = wait_for(f, slot, s)) return rc;
+    if (int rc = wait_for(f, slot, s, false)) return rc;
     uint8_t* p = dst;
     CU(cudaMemcpy2DAsync(p, width_, f.dev, g_.y_pitch, width_, height_, cudaMemcpyDeviceToHost, s));
     p += (size_t)width_ * height_;
     CU(cudaMemcpy2DAsync(p, cw, f.dev + g_.u_off, g_.c_pitch, cw, ch, cudaMemcpyDeviceToHost, s));
     p += (size_t)cw * ch;
     CU(cudaMemcpy2DAsync(p, cw, f.dev + g_.v_off, g_.c_pitch, cw, ch, cudaMemcpyDeviceToHost, s));
-    if (int rc = touch(f, slot)) return rc;
+    if (int rc = touch(f, slot, false)) return rc;
   }
   if (wait) CU(cudaStreamSynchronize(s));
   return VP8GPU_OK;
@@ -230,13 +246,13 @@ int Engine::frames_equal(int a, int b, int lane, int* equal) {
     std::lock_guard<std::mutex> lk(mu_);
     if (!cmp_scratch_) CU(cudaMalloc(&cmp_scratch_, 512));
     flag = reinterpret_cast<int*>(cmp_scratch_);
-    if (int rc = wait_for(frames_[a], lane, s)) return rc;
-    if (int rc = wait_for(frames_[b], lane, s)) return rc;
+    if (int rc = wait_for(frames_[a], lane, s, false)) return rc;
+    if (int rc = wait_for(frames_[b], lane, s, false)) return rc;
     CU(cudaMemsetAsync(flag, 0, sizeof(int), s));
     if (int e = launch_compare(frames_[a].dev, frames_[b].dev, g_, flag, s)) return cuda_fail((cudaError_t)e, "compare");
     launches_++;
-    if (int rc = touch(frames_[a], lane)) return rc;
-    if (int rc = touch(frames_[b], lane)) return rc;
+    if (int rc = touch(frames_[a], lane, false)) return rc;
+    if (int rc = touch(frames_[b], lane, false)) return rc;
   }
   int h = 0;
   CU(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -254,11 +270,11 @@ int Engine::frame_hash(int id, int lane, uint64_t* out) {
     if (id < 0 || id >= (int)frames_.size() || frames_[id].refcnt <= 0) return fail(VP8GPU_ERR_LOGIC, "hash: bad frame id");
     if (!cmp_scratch_) CU(cudaMalloc(&cmp_scratch_, 512));
     d = reinterpret_cast<unsigned long long*>(cmp_scratch_ + 64 + 8 * lane);
-    if (int rc = wait_for(frames_[id], lane, s)) return rc;
+    if (int rc = wait_for(frames_[id], lane, s, false)) return rc;
     CU(cudaMemsetAsync(d, 0, sizeof(unsigned long long), s));
     if (int e = launch_hash(frames_[id].dev, g_, d, s)) return cuda_fail((cudaError_t)e, "hash");
     launches_++;
-    if (int rc = touch(frames_[id], lane)) return rc;
+    if (int rc = touch(frames_[id], lane, false)) return rc;
   }
   unsigned long long h = 0;
   CU(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, s));
@@ -301,6 +317,12 @@ Layout plan(const Geom& g, const HostJob* jobs, int n) {
   size_t off = align_up(L.sync_off + L.sync_bytes, 256);
   const size_t n_mbs = (size_t)g.mb_cols * g.mb_rows;
   for (int i = 0; i < n; i++) {
+    if (jobs[i].ring) {  // records already in HBM
+      L.mbs_off.push_back(0);
+      L.tok_off.push_back(0);
+      L.split_off.push_back(0);
+      continue;
+    }
     L.mbs_off.push_back(off);
     off = align_up(off + n_mbs * sizeof(vp8gpu_mb), 256);
     L.tok_off.push_back(off);
@@ -330,6 +352,94 @@ int Engine::build_and_launch(int lane, const DevJob* d_jobs, int* d_sync, int n,
     if (int e = launch_loopfilter(d_jobs, n, g_, d_sync + 32, s)) return cuda_fail((cudaError_t)e, "k_loopfilter launch");
     launches_++;
   }
+  return VP8GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// device-side token decoding (tokens.cu)
+// ------------------------------------------------------------------------------------------
+int Engine::token_ring_create(int nslots, size_t max_frame_bytes, TokenRing** out) {
+  CU(cudaSetDevice(device_));
+  const size_t n_mbs = (size_t)g_.mb_cols * g_.mb_rows;
+  TokenRing* r = new TokenRing();
+  r->nslots = nslots;
+  r->bits_cap = (uint32_t)align_up(max_frame_bytes + 16, 256);
+  r->split_cap = (uint32_t)n_mbs;
+  // Every non-zero token ends with a sign decoded at probability 128, which consumes >= 0.98 bit
+  // of the partition, and past the end of the data every block ends at once (only zero bits
+  // arrive): tokens <= 8.2 * bytes + lookahead.  Never more than 25 * 16 per macroblock.
+  const size_t by_bytes = (size_t)r->bits_cap * 9 + 1024, by_blocks = n_mbs * 400;
+  r->tok_cap = (uint32_t)(by_bytes < by_blocks ? by_bytes : by_blocks);
+  size_t off = 256;  // TokJob
+  r->probs_off = off;
+  off += 1280;
+  r->bits_off = off;
+  off = align_up(off + r->bits_cap, 256);
+  r->host_stride = off;
+  r->result_off = off;
+  off += 256;
+  r->mbs_off = off;
+  off = align_up(off + n_mbs * sizeof(vp8gpu_mb), 256);
+  r->split_off = off;
+  off = align_up(off + (size_t)r->split_cap * sizeof(vp8gpu_split_mvs), 256);
+  r->tok_off = off;
+  off = align_up(off + (size_t)r->tok_cap * sizeof(vp8gpu_token), 256);
+  r->stride = off;
+  if (cudaMalloc(&r->dev, r->stride * nslots) != cudaSuccess ||
+      cudaHostAlloc(&r->host, r->host_stride * nslots, cudaHostAllocDefault) != cudaSuccess) {
+    token_ring_free(r);
+    return fail(VP8GPU_ERR_NOMEM, "token ring allocation failed");
+  }
+  *out = r;
+  return VP8GPU_OK;
+}
+
+void Engine::token_ring_free(TokenRing* r) {
+  if (!r) return;
+  cudaSetDevice(device_);
+  if (r->dev) cudaFree(r->dev);
+  if (r->host) cudaFreeHost(r->host);
+  delete r;
+}
+
+int Engine::token_ring_stage(TokenRing* r, int slot, const ParsedFrame& f, cudaStream_t s) {
+  const TokenWork& tw = f.tw;
+  if (!tw.deferred) return fail(VP8GPU_ERR_LOGIC, "token_ring_stage: frame was not parsed with defer_tokens");
+  if (tw.bits_len > r->bits_cap || f.desc.n_split > r->split_cap)
+    return fail(VP8GPU_ERR_NOMEM, "token_ring_stage: frame larger than the ring was sized for");
+  uint8_t* h = r->host_slot(slot);
+  uint8_t* d = r->dev_slot(slot);
+  TokJob* j = reinterpret_cast<TokJob*>(h);
+  j->mbs = reinterpret_cast<vp8gpu_mb*>(d + r->mbs_off);
+  j->tokens = reinterpret_cast<vp8gpu_token*>(d + r->tok_off);
+  j->bits = d + r->bits_off;
+  j->coef_probs = d + r->probs_off;
+  j->result = reinterpret_cast<uint32_t*>(d + r->result_off);
+  memcpy(j->part_off, tw.part_off, sizeof(j->part_off));
+  memcpy(j->part_len, tw.part_len, sizeof(j->part_len));
+  j->nparts = tw.nparts;
+  j->tok_cap = r->tok_cap;
+  memcpy(h + r->probs_off, tw.coef_probs, 1056);
+  memcpy(h + r->bits_off, tw.bits, tw.bits_len);
+  const size_t n_mbs = (size_t)g_.mb_cols * g_.mb_rows;
+  CU(cudaMemcpyAsync(d, h, r->bits_off + align_up(tw.bits_len, 16), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(d + r->mbs_off, f.mbs.data(), n_mbs * sizeof(vp8gpu_mb), cudaMemcpyHostToDevice, s));
+  if (f.desc.n_split)
+    CU(cudaMemcpyAsync(d + r->split_off, f.split.data(), (size_t)f.desc.n_split * sizeof(vp8gpu_split_mvs),
+                       cudaMemcpyHostToDevice, s));
+  return VP8GPU_OK;
+}
+
+int Engine::token_ring_launch(TokenRing* r, int first, int count, cudaStream_t s) {
+  if (count <= 0) return VP8GPU_OK;
+  if (int e = launch_tokens(r->dev, r->stride, first, count, r->nslots, g_, s)) return cuda_fail((cudaError_t)e, "k_tokens launch");
+  launches_++;
+  return VP8GPU_OK;
+}
+
+int Engine::token_ring_result(TokenRing* r, int slot, cudaStream_t s, uint32_t result[2]) {
+  CU(cudaMemcpyAsync(result, r->dev_slot(slot) + r->result_off, 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
   return VP8GPU_OK;
 }
 
@@ -369,9 +479,16 @@ int Engine::submit(int lane, const HostJob* jobs, int n, cudaEvent_t consumed) {
       if (j.out < 0 || j.out >= (int)frames_.size() || frames_[j.out].refcnt <= 0)
         return fail(VP8GPU_ERR_LOGIC, "submit: bad output frame");
       DevJob& d = hj[i];
-      d.mbs = reinterpret_cast<const vp8gpu_mb*>(st.dev + L.mbs_off[i]);
-      d.tokens = reinterpret_cast<const vp8gpu_token*>(st.dev + L.tok_off[i]);
-      d.split = reinterpret_cast<const vp8gpu_split_mvs*>(st.dev + L.split_off[i]);
+      if (j.ring) {
+        const uint8_t* slot = j.ring->dev_slot(j.ring_slot);
+        d.mbs = reinterpret_cast<const vp8gpu_mb*>(slot + j.ring->mbs_off);
+        d.tokens = reinterpret_cast<const vp8gpu_token*>(slot + j.ring->tok_off);
+        d.split = reinterpret_cast<const vp8gpu_split_mvs*>(slot + j.ring->split_off);
+      } else {
+        d.mbs = reinterpret_cast<const vp8gpu_mb*>(st.dev + L.mbs_off[i]);
+        d.tokens = reinterpret_cast<const vp8gpu_token*>(st.dev + L.tok_off[i]);
+        d.split = reinterpret_cast<const vp8gpu_split_mvs*>(st.dev + L.split_off[i]);
+      }
       d.out = frames_[j.out].dev;
       for (int r = 0; r < 3; r++) {
         d.ref[r] = nullptr;
@@ -396,16 +513,19 @@ int Engine::submit(int lane, const HostJob* jobs, int n, cudaEvent_t consumed) {
     // stream ordering against other users of the rasters
     for (int i = 0; i < n; i++) {
       if (int rc = wait_for(frames_[jobs[i].out], lane, s)) return rc;
-      frames_[jobs[i].out].pending &= 1ull << lane;
       if (!jobs[i].desc->key_frame)
         for (int r = 0; r < 3; r++)
-          if (int rc = wait_for(frames_[jobs[i].refs[r]], lane, s)) return rc;
+          if (int rc = wait_for(frames_[jobs[i].refs[r]], lane, s, false)) return rc;
     }
   }
   CU(cudaMemcpyAsync(st.dev, st.host, hdr_bytes, cudaMemcpyHostToDevice, s));
   const size_t n_mbs = (size_t)g_.mb_cols * g_.mb_rows;
   for (int i = 0; i < n; i++) {
     const HostJob& j = jobs[i];
+    if (j.ring) {
+      if (j.ready) CU(cudaStreamWaitEvent(s, j.ready, 0));
+      continue;
+    }
     CU(cudaMemcpyAsync(st.dev + L.mbs_off[i], j.mbs, n_mbs * sizeof(vp8gpu_mb), cudaMemcpyHostToDevice, s));
     if (j.desc->n_tokens)
       CU(cudaMemcpyAsync(st.dev + L.tok_off[i], j.tokens, (size_t)j.desc->n_tokens * sizeof(vp8gpu_token),
@@ -424,11 +544,13 @@ int Engine::submit(int lane, const HostJob* jobs, int n, cudaEvent_t consumed) {
       if (int rc = touch(frames_[jobs[i].out], lane)) return rc;
       if (!jobs[i].desc->key_frame)
         for (int r = 0; r < 3; r++)
-          if (int rc = touch(frames_[jobs[i].refs[r]], lane)) return rc;
+          if (int rc = touch(frames_[jobs[i].refs[r]], lane, false)) return rc;
     }
   }
   CU(cudaEventRecord(st.done, s));
   st.in_flight = true;
+  for (int i = 0; i < n; i++)
+    if (jobs[i].finished) CU(cudaEventRecord(jobs[i].finished, s));
   return VP8GPU_OK;
 }
 

@@ -53,11 +53,25 @@ struct EncJob {
   uint8_t key_frame, lf_level, pad[2];
 };
 
-// Kernel launchers (kernels.cu).  `stream` is a cudaStream_t passed as void* so this header
+// One frame's token-decode job (tokens.cu): DCT partitions -> token stream + tok_off / tok_cnt.
+struct TokJob {
+  vp8gpu_mb* mbs;             // in: y_mode, VP8GPU_MB_SKIP; out: tok_off, tok_cnt, flag cleared
+  vp8gpu_token* tokens;       // out
+  const uint8_t* bits;        // the frame's DCT partitions, back to back
+  const uint8_t* coef_probs;  // 1056 bytes: the frame's coefficient probabilities
+  uint32_t* result;           // [0] tokens written, [1] non-zero if the pool was too small
+  uint32_t part_off[8], part_len[8];
+  uint32_t nparts;            // 1, 2, 4 or 8
+  uint32_t tok_cap;
+};
+
+// Kernel launchers (kernels.cu, tokens.cu).  `stream` is a cudaStream_t passed as void* so this header
 // stays free of CUDA includes.  Return 0 or a cudaError_t value.
 int launch_inter(const DevJob* jobs, int njobs, const Geom& g, void* stream);
 int launch_intra(const DevJob* jobs, int njobs, const Geom& g, int* ticket, void* stream);
 int launch_loopfilter(const DevJob* jobs, int njobs, const Geom& g, int* ticket, void* stream);
+// token jobs sit at the start of equally spaced ring slots: slot (first + i) % nslots for block i
+int launch_tokens(const uint8_t* ring, size_t stride, int first, int count, int nslots, const Geom& g, void* stream);
 int launch_enc_motion(const EncJob* job, const Geom& g, void* stream);
 int launch_enc_mb(const EncJob* job, const Geom& g, int* ticket, void* stream);
 

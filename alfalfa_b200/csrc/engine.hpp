@@ -17,6 +17,20 @@ namespace vp8 {
 constexpr int kMaxLanes = 32;       // compute lanes; lane i's copy stream is slot kMaxLanes + i
 constexpr int kStagingDepth = 3;    // device record buffers in flight per lane
 
+// Device + pinned staging for frames whose DCT partitions are decoded on the device (tokens.cu):
+// `nslots` slots of equal size in one allocation, so that consecutive slots can share one launch.
+// Device slot: TokJob | probabilities | partitions | result words | mbs | split MVs | tokens.
+struct TokenRing {
+  int nslots = 0;
+  uint8_t* dev = nullptr;
+  uint8_t* host = nullptr;       // pinned mirror of the first three parts of every slot
+  size_t stride = 0, host_stride = 0;
+  size_t probs_off = 0, bits_off = 0, result_off = 0, mbs_off = 0, split_off = 0, tok_off = 0;
+  uint32_t bits_cap = 0, split_cap = 0, tok_cap = 0;
+  uint8_t* dev_slot(int i) const { return dev + (size_t)i * stride; }
+  uint8_t* host_slot(int i) const { return host + (size_t)i * host_stride; }
+};
+
 // a decode job with host-side record arrays
 struct HostJob {
   const vp8gpu_frame_desc* desc;
@@ -28,6 +42,12 @@ struct HostJob {
   int n_intra = -1;    // -1: count them here
   int n_filtered = -1;
   cudaEvent_t consumed = nullptr;  // recorded as soon as this job's host arrays have been copied
+  // records already in HBM (token_ring_stage + token_ring_launch): nothing is copied, the stream
+  // waits for `ready` instead; `finished` (optional) is recorded after the job's kernels
+  const TokenRing* ring = nullptr;
+  int ring_slot = 0;
+  cudaEvent_t ready = nullptr;
+  cudaEvent_t finished = nullptr;
 };
 
 class Engine {
@@ -44,6 +64,7 @@ class Engine {
   int frame_alloc(int* id);
   int frame_retain(int id);
   int frame_release(int id);
+  int frames_free();  // rasters the pool can still hand out
   int frame_upload(int id, const uint8_t* y, size_t ys, const uint8_t* u, const uint8_t* v, size_t cs);
   int frame_download(int id, uint8_t* y, size_t ys, uint8_t* u, uint8_t* v, size_t cs);
   int frame_download_display(int id, int lane, uint8_t* dst, size_t dst_size, bool wait);
@@ -54,6 +75,16 @@ class Engine {
   // decode n frames in one set of launches on `lane`; host arrays must stay valid until the
   // returned event (*consumed, optional) has fired (pinned) or are consumed on return (pageable)
   int submit(int lane, const HostJob* jobs, int n, cudaEvent_t consumed);
+
+  // device-side token decoding
+  int token_ring_create(int nslots, size_t max_frame_bytes, TokenRing** out);
+  void token_ring_free(TokenRing* r);
+  // queue on `s` the upload of one frame parsed with defer_tokens (records + partitions)
+  int token_ring_stage(TokenRing* r, int slot, const ParsedFrame& f, cudaStream_t s);
+  // one k_tokens launch over `count` consecutive slots (wrapping around the ring)
+  int token_ring_launch(TokenRing* r, int first, int count, cudaStream_t s);
+  // synchronous: tokens written / overflow flag of a slot whose kernel has been queued on `s`
+  int token_ring_result(TokenRing* r, int slot, cudaStream_t s, uint32_t result[2]);
 
   // device-resident batches
   struct Resident;
@@ -69,6 +100,7 @@ class Engine {
   int mark_frames(int lane, const int* ids, int n);     // record that `lane` used them
   void count_launches(int n) { launches_ += n; }
 
+  int ensure_lane(int lane);  // creates the lane's streams on first use
   int sync_all();
   int sync_lane(int lane);
   cudaStream_t stream(int lane) const { return lanes_[lane]; }
@@ -82,8 +114,10 @@ class Engine {
   struct Frame {
     uint8_t* dev = nullptr;
     int refcnt = 0;
-    uint64_t pending = 0;                  // stream slots that touched it since the last wait
-    cudaEvent_t ev[2 * kMaxLanes] = {};    // lazily created
+    uint64_t pending = 0;                  // stream slots that read it since the last write
+    cudaEvent_t ev[2 * kMaxLanes] = {};    // one per reading slot, lazily created
+    int wslot = -1;                        // slot of the last writer
+    cudaEvent_t wev = nullptr;
   };
   struct Staging {
     uint8_t* dev = nullptr;
@@ -93,9 +127,8 @@ class Engine {
     cudaEvent_t done = nullptr;
     bool in_flight = false;
   };
-  int ensure_lane(int lane);
-  int touch(Frame& f, int slot);                     // record "slot used this frame"
-  int wait_for(Frame& f, int slot, cudaStream_t s);  // make stream s wait for other users
+  int touch(Frame& f, int slot, bool write = true);                     // record "slot used this frame"
+  int wait_for(Frame& f, int slot, cudaStream_t s, bool write = true);  // make stream s wait for other users
   int build_and_launch(int lane, const DevJob* d_jobs, int* d_sync, int n, bool any_inter, bool any_intra,
                        bool any_lf, cudaEvent_t* between = nullptr);
   int count_jobs(const HostJob& j, uint32_t* n_intra, uint32_t* n_inter, uint32_t* n_filtered) const;

@@ -436,7 +436,7 @@ inline int parse_block(BoolReader& br, const uint8_t* tp, int ctx, int i, uint32
 // ------------------------------------------------------------------------------------------
 // parse_frame
 // ------------------------------------------------------------------------------------------
-int parse_frame(State& state, const uint8_t* data, size_t len, ParsedFrame& out) {
+int parse_frame(State& state, const uint8_t* data, size_t len, ParsedFrame& out, bool defer_tokens) {
   // ---- frame tag and partition layout (uncompressed_chunk.cc:34-130) ----
   if (len < 3) return VP8GPU_ERR_INVALID;
   const uint32_t tag = data[0] | (data[1] << 8) | (static_cast<uint32_t>(data[2]) << 16);
@@ -511,22 +511,33 @@ int parse_frame(State& state, const uint8_t* data, size_t len, ParsedFrame& out)
   // ---- DCT partitions (uncompressed_chunk.cc:132-155) ----
   const int nparts = 1 << h.log2_parts;
   BoolReader parts[8];
+  TokenWork& tw = out.tw;
+  tw.deferred = defer_tokens;
   {
     const size_t table = static_cast<size_t>(3) * (nparts - 1);
     if (rest_len < table) return VP8GPU_ERR_INVALID;
     const uint8_t* p = rest + table;
     size_t left = rest_len - table;
+    tw.nparts = static_cast<uint32_t>(nparts);
+    tw.bits = p;
+    tw.bits_len = static_cast<uint32_t>(left);
     for (int i = 0; i < nparts; i++) {
       size_t n = left;
       if (i < nparts - 1) {
         n = rest[3 * i] | (rest[3 * i + 1] << 8) | (static_cast<size_t>(rest[3 * i + 2]) << 16);
         if (n > left) return VP8GPU_ERR_INVALID;
       }
-      parts[i].init(p, n);
+      if (defer_tokens) {
+        tw.part_off[i] = static_cast<uint32_t>(p - tw.bits);
+        tw.part_len[i] = static_cast<uint32_t>(n);
+      } else {
+        parts[i].init(p, n);
+      }
       p += n;
       left -= n;
     }
   }
+  if (defer_tokens) memcpy(tw.coef_probs, frame_coef, sizeof(frame_coef));
 
   const int cols = state.mb_cols, rows = state.mb_rows;
   const size_t n_mbs = static_cast<size_t>(cols) * rows;
@@ -785,7 +796,9 @@ int parse_frame(State& state, const uint8_t* data, size_t len, ParsedFrame& out)
       unsigned a_nz = above_nz[col];
       const size_t tok_off = n_tok;
       unsigned tok_cnt = 0;
-      if (skip) {
+      if (defer_tokens) {
+        // left to csrc/tokens.cu, which needs to know mb_skip_coeff
+      } else if (skip) {
         // every block of a skipped macroblock has has_nonzero_ == false; a coded Y2 becomes the
         // new (zero) Y2 context, a macroblock without Y2 leaves the previous one (frame.cc:252-269)
         const unsigned keep = has_y2 ? 0u : 0x100u;
@@ -837,7 +850,7 @@ int parse_frame(State& state, const uint8_t* data, size_t len, ParsedFrame& out)
       mb.ref_frame = static_cast<uint8_t>(ref);
       mb.segment_id = static_cast<uint8_t>(segment);
       mb.lf_level = static_cast<uint8_t>(level);
-      mb.flags = has_y2 ? VP8GPU_MB_HAS_Y2 : 0;
+      mb.flags = static_cast<uint8_t>((has_y2 ? VP8GPU_MB_HAS_Y2 : 0) | (defer_tokens && skip ? VP8GPU_MB_SKIP : 0));
       mb.mv_x = mv[15][0];
       mb.mv_y = mv[15][1];
       mb.split_idx = split_idx;

@@ -64,6 +64,17 @@ class Buffer {
   size_t cap_ = 0;
 };
 
+// What is left to do when parse_frame ran with defer_tokens: the DCT partitions, decoded on the
+// device by csrc/tokens.cu (Frame::parse_tokens, frame.cc:122-137).
+struct TokenWork {
+  bool deferred = false;
+  uint32_t nparts = 0;
+  uint32_t part_off[8] = {0}, part_len[8] = {0};  // relative to `bits`
+  const uint8_t* bits = nullptr;                  // points into the caller's frame data
+  uint32_t bits_len = 0;
+  uint8_t coef_probs[1056];                       // the frame's probabilities (after header updates)
+};
+
 // KeyFrame / InterFrame (decoder/frame.hh:126-127) in flat form.
 struct ParsedFrame {
   explicit ParsedFrame(const Allocator& a = kMallocAllocator) : mbs(a), tokens(a), split(a) {}
@@ -71,11 +82,14 @@ struct ParsedFrame {
   Buffer<vp8gpu_mb> mbs;
   Buffer<vp8gpu_token> tokens;
   Buffer<vp8gpu_split_mvs> split;
+  TokenWork tw;
 };
 
 // Parse one compressed frame and apply it to `state`.  Returns VP8GPU_OK or VP8GPU_ERR_*;
-// on error `state` is left untouched.
-int parse_frame(State& state, const uint8_t* data, size_t len, ParsedFrame& out);
+// on error `state` is left untouched.  With defer_tokens only the first partition (frame header,
+// macroblock modes, motion vectors) is decoded: records carry VP8GPU_MB_SKIP instead of
+// tok_off / tok_cnt, no tokens are produced, desc.n_tokens is 0 and out.tw describes the rest.
+int parse_frame(State& state, const uint8_t* data, size_t len, ParsedFrame& out, bool defer_tokens = false);
 
 // true if the frame tag says key frame (uncompressed_chunk.cc:53)
 inline bool is_key_frame(const uint8_t* data, size_t len) { return len > 0 && !(data[0] & 1); }

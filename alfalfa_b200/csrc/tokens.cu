@@ -1,0 +1,51 @@
+// tokens.cu -- device-side coefficient-token decoder (the DCT partitions of a VP8 frame).
+//
+// Replaces, for throughput-oriented callers (vp8gpu_decode_ivf), the token half of the CPU front
+// end: Frame::parse_tokens -> Macroblock::parse_tokens -> Block::parse_tokens (decoder/frame.cc:
+// 122-137, macroblock.cc:468-502, tokens.cc:50-135) over BoolDecoder (bool_decoder.hh:82-107).
+// The arithmetic code of one partition is inherently serial, and a macroblock row needs the
+// "has non-zero" context of the row above, so ONE thread walks one frame in raster order; the
+// parallelism is across frames: token partitions do not depend on pixels, so the host parses the
+// first partitions of many frames (cheap: ~12 % of the bytes) and launches this kernel over all of
+// them while the pixel kernels work on earlier frames.  One warp per frame: lane 0 decodes, the
+// other lanes only help to stage the probability table.
+//
+// In:  vp8gpu_mb records written by the host with y_mode and VP8GPU_MB_SKIP (mb_skip_coeff) set,
+//      the frame's coefficient probabilities (after the header's updates), the raw partitions.
+// Out: the same token stream the CPU front end emits (csrc/parser.cc parse_block) and, per
+//      record, tok_off / tok_cnt; VP8GPU_MB_SKIP is cleared, so the records end up byte-identical
+//      to the ones the CPU path produces.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "engine.h"
+#include "tokens_core.cuh"
+
+namespace vp8 {
+namespace {
+
+constexpr int kMaxCols = 1024;  // 16383 px / 16
+
+// jobs live at the start of equally spaced slots of a ring (engine.hpp TokenRing)
+__global__ void __launch_bounds__(32) k_tokens(const uint8_t* ring, size_t stride, int first, int nslots, Geom g) {
+  __shared__ uint8_t probs[1056];
+  __shared__ uint16_t above_nz[kMaxCols];
+  const TokJob& J = *reinterpret_cast<const TokJob*>(ring + static_cast<size_t>((first + blockIdx.x) % nslots) * stride);
+  const int lane = threadIdx.x;
+  for (int i = lane; i < 1056 / 4; i += 32)
+    reinterpret_cast<uint32_t*>(probs)[i] = __ldg(reinterpret_cast<const uint32_t*>(J.coef_probs) + i);
+  for (int i = lane; i < g.mb_cols; i += 32) above_nz[i] = 0;
+  __syncwarp();
+  if (lane != 0) return;
+  tok::decode_frame_tokens(J, g, probs, above_nz);
+}
+
+}  // namespace
+
+int launch_tokens(const uint8_t* ring, size_t stride, int first, int count, int nslots, const Geom& g, void* stream) {
+  if (g.mb_cols > kMaxCols) return (int)cudaErrorInvalidValue;
+  k_tokens<<<count, 32, 0, static_cast<cudaStream_t>(stream)>>>(ring, stride, first, nslots, g);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace vp8

@@ -50,6 +50,10 @@ class Context:
     def sync(self):
         check(self.L.vp8gpu_ctx_sync(self.h), self.h, "sync")
 
+    def set_device_tokens(self, on):
+        """VP8GPU_OPT_DEVICE_TOKENS: decode_ivf decodes the DCT partitions on the device (default on)"""
+        check(self.L.vp8gpu_ctx_set_option(self.h, capi.OPT_DEVICE_TOKENS, int(bool(on))), self.h, "set_option")
+
     def launch_count(self):
         return int(self.L.vp8gpu_launch_count(self.h))
 
@@ -212,6 +216,17 @@ class Decoder:
         st = C.c_void_p(self.L.vp8gpu_decoder_state(self.h))
         check(self.L.vp8gpu_parse_frame(st, chunk, len(chunk), p.h), self.ctx.h, "parse_frame")
         return p
+
+    def parse_frame_device(self, chunk):
+        """parse_frame with the DCT partitions decoded on the device (same records)"""
+        p = ParsedFrame()
+        st = C.c_void_p(self.L.vp8gpu_decoder_state(self.h))
+        check(self.L.vp8gpu_parse_frame_device(self.ctx.h, st, chunk, len(chunk), p.h), self.ctx.h, "parse_frame_device")
+        return p
+
+    def set_device_tokens(self, on):
+        """get_frame_output leaves the DCT partitions to the device (same output)"""
+        check(self.L.vp8gpu_decoder_set_device_tokens(self.h, int(bool(on))), self.ctx.h, "set_device_tokens")
 
     def decode_frame(self, parsed):
         shown, fid = C.c_int(0), C.c_int32(-1)

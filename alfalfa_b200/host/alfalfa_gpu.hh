@@ -51,6 +51,10 @@ class Context {
   }
   vp8gpu_ctx* get() const { return h_.get(); }
   void sync() const { check(vp8gpu_ctx_sync(get()), get(), "sync"); }
+  // vp8gpu_decode_ivf: DCT partitions on the device (default) or on the host workers
+  void set_device_tokens(bool on) const {
+    check(vp8gpu_ctx_set_option(get(), VP8GPU_OPT_DEVICE_TOKENS, on), get(), "set_option");
+  }
 };
 
 // RasterHandle (raster_handle.hh:95-123): shared, immutable, device resident
@@ -166,6 +170,8 @@ class Decoder {
           "get_frame_output");
     return {shown != 0, RasterHandle(ctx_, id)};
   }
+  // leave the DCT partitions of get_frame_output to the device (same output, less host time)
+  void set_device_tokens(bool on) { check(vp8gpu_decoder_set_device_tokens(h_, on), ctx_.get(), "set_device_tokens"); }
   // parse_and_decode_frame (decoder.cc:137-141): empty handle for hidden frames
   RasterHandle parse_and_decode_frame(const Chunk& compressed_frame) {
     auto out = get_frame_output(compressed_frame);

@@ -238,6 +238,8 @@ def main():
     ap.add_argument("--no-encode", action="store_true", help="skip the 1080p encode section")
     ap.add_argument("--encode-frames", type=int, default=12)
     ap.add_argument("--encode-target", type=int, default=45000, help="bytes per frame for encode_with_target_size")
+    ap.add_argument("--host-tokens", action="store_true",
+                    help="end-to-end run: DCT partitions decoded by the host workers instead of k_tokens on the device")
     ap.add_argument("--no-output", action="store_true", help="diagnostic: leave decoded frames on the device")
     ap.add_argument("--host-stats", action="store_true", help="diagnostic: print host time accounting to stderr")
     a = ap.parse_args()
@@ -273,6 +275,7 @@ def main():
     parsed = []  # per clip frame: (desc, mbs, tok, split) numpy copies
     n_mbs = ((w + 15) // 16) * ((h + 15) // 16)
     h2d_per_clip = 0
+    h2d_dev_tokens = 0
     z_blocks = 0
     for f in frames:
         capi.check(L.vp8gpu_parse_frame(st, f, len(f), pf), None, "parse")
@@ -284,6 +287,7 @@ def main():
               if d.n_split else np.zeros(64, "u1"))
         parsed.append((d, mbs, tok, sp))
         h2d_per_clip += n_mbs * 32 + d.n_tokens * 4 + d.n_split * 64 + 512
+        h2d_dev_tokens += n_mbs * 32 + d.n_split * 64 + 1536 + len(f)  # records + probabilities + raw partitions
         if d.n_tokens:
             z_blocks += len(np.unique((tok[:d.n_tokens] >> 20) & 31 | (np.repeat(np.arange(n_mbs), mbs["tok_cnt"]) << 5)))
     L.vp8gpu_state_destroy(st)
@@ -403,12 +407,16 @@ def main():
         for fr in s_["frames"]:
             fr.release()
     ctx.close()
-    # parse workers: twice the usable CPUs (they also wait on DMA / the dispatcher), shared by the ranks
-    threads = a.threads or max(2, min(64, 2 * effective_cpus() // max(world, 1)))
+    # Host workers, shared by the ranks.  With the DCT partitions decoded on the device a worker only
+    # walks first partitions, and the number of GOPs in flight (= workers) is what fills the device:
+    # four per usable CPU; when the workers parse everything, two (they also wait on DMA / the dispatcher).
+    per_cpu = 2 if a.host_tokens else 4
+    threads = a.threads or max(2, min(96, per_cpu * effective_cpus() // max(world, 1)))
     R = a.replicas or max(16, threads)  # 2 GOPs per repeat -> at least 2 GOPs per worker
     big = replicate_ivf(data, R)
     n_e2e_frames = len(frames) * R
-    ctx2 = Context(w, h, device=local, max_frames=threads * 10 + 64)
+    ctx2 = Context(w, h, device=local, max_frames=threads * (10 if a.host_tokens else 30) + 64)
+    ctx2.set_device_tokens(not a.host_tokens)
     out_bytes = ctx2.display_bytes * n_e2e_frames
     dst = C.c_void_p()
     capi.check(L.vp8gpu_host_alloc(C.byref(dst), out_bytes), ctx2.h, "host_alloc")
@@ -473,7 +481,8 @@ def main():
                        "frames_per_step": frames_per_step, "l2": "working set %.0f MB per step > 126 MB L2, no flush needed"
                        % (frames_per_step * 3.1), "e2e_frames_per_step": n_e2e_frames, "e2e_host_threads": threads,
                        "bit_exact": "tests/test_gpu_parity.py (53/53 golden SHA-1 + per-frame oracle)"},
-            "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": int(h2d_per_clip * R),
+            "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": int((h2d_per_clip if a.host_tokens else h2d_dev_tokens) * R),
+                    "dct_partitions": "host workers" if a.host_tokens else "k_tokens on the device",
                     "d2h_bytes_per_step": int(out_bytes), "ms_per_step": e2e_total / a.steps * 1e3,
                     "api": "vp8gpu_decode_ivf (host IVF bytes -> pinned host YUV)"},
             "gpu_launches": int(launches_resident), "gpu_launches_e2e": int(launches_e2e),

@@ -72,6 +72,10 @@ typedef uint32_t vp8gpu_token;
 #define VP8GPU_BLK_Y2 24
 
 #define VP8GPU_MB_HAS_Y2 1u /* Y2Block::coded(): y_mode is neither B_PRED nor SPLITMV */
+#define VP8GPU_MB_SKIP   2u /* mb_skip_coeff (macroblock.cc:57-58).  Only present while the token
+                               partitions of the frame are still to be decoded on the device
+                               (vp8gpu_decode_ivf); that kernel clears it, so records seen through
+                               vp8gpu_parse_frame / vp8gpu_decode_parsed never carry it */
 
 /* 32 bytes per macroblock. */
 typedef struct vp8gpu_mb {
@@ -232,6 +236,20 @@ const vp8gpu_split_mvs* vp8gpu_parsed_split(const vp8gpu_parsed* p);
  * On error `state` is unchanged. */
 int vp8gpu_parse_frame(vp8gpu_state* state, const uint8_t* data, size_t len, vp8gpu_parsed* out);
 
+/* Same contract and same output as vp8gpu_parse_frame, with the front end split the B200 way: the
+ * host decodes the first partition (frame header, macroblock modes, motion vectors: macroblock.cc:
+ * 44-456), the device decodes the DCT partitions (Frame::parse_tokens, frame.cc:122-137;
+ * tokens.cc:50-135) and the completed records are copied back into `out`.  Synchronous; the
+ * building block behind VP8GPU_OPT_DEVICE_TOKENS, exported so the records can be checked. */
+int vp8gpu_parse_frame_device(vp8gpu_ctx* ctx, vp8gpu_state* state, const uint8_t* data, size_t len,
+                              vp8gpu_parsed* out);
+
+/* Context options.  VP8GPU_OPT_DEVICE_TOKENS (default 1): vp8gpu_decode_ivf decodes the DCT
+ * partitions on the device (one thread per frame, many frames in flight) instead of on the host
+ * workers; 0 = the host workers parse everything.  Output is identical either way. */
+#define VP8GPU_OPT_DEVICE_TOKENS 1
+int vp8gpu_ctx_set_option(vp8gpu_ctx* ctx, int option, int value);
+
 /* ---- Decoder (decoder.hh:244-300): DecoderState + References, explicit state passing ---- */
 typedef struct vp8gpu_decoder vp8gpu_decoder;
 /* Decoder(width,height): references start as one shared all-zero raster. */
@@ -251,6 +269,9 @@ int vp8gpu_decoder_decode(vp8gpu_decoder* d, const uint8_t* data, size_t len, in
  * have been produced by vp8gpu_parse_frame on this decoder's state (vp8gpu_decoder_state). */
 int vp8gpu_decoder_decode_parsed(vp8gpu_decoder* d, const vp8gpu_parsed* parsed, int* shown,
                                  vp8gpu_frame_id* out);
+/* on != 0: vp8gpu_decoder_decode leaves the DCT partitions to the device (same stream as the pixel
+ * kernels, so this trades latency for host time); default off.  Output is identical. */
+int vp8gpu_decoder_set_device_tokens(vp8gpu_decoder* d, int on);
 vp8gpu_state* vp8gpu_decoder_state(vp8gpu_decoder* d);            /* get_state (borrowed) */
 int vp8gpu_decoder_references(const vp8gpu_decoder* d, vp8gpu_frame_id refs[3]); /* borrowed */
 int vp8gpu_decoder_lane(const vp8gpu_decoder* d);

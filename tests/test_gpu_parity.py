@@ -34,15 +34,18 @@ def test_fileplayer_reproduces_golden_sha1(name):
     assert sha.hexdigest() == name
 
 
+@pytest.mark.parametrize("device_tokens", [False, True])
 @pytest.mark.parametrize("threads", [1, 4])
 @pytest.mark.parametrize("name", ["2a4c049c2f8e3a19ee39ffd7074cecd68006a101",
                                   "45502fe01a62b82d498b83dc50824741402436db",
                                   "ff2941dde20090835032c32c0644b6d401610c57"])
-def test_gop_parallel_stream_decode_matches_golden(name, threads):
+def test_gop_parallel_stream_decode_matches_golden(name, threads, device_tokens):
+    """vp8gpu_decode_ivf, DCT partitions decoded by the host workers or by k_tokens on the device"""
     from alfalfa_b200 import Context, decode_ivf
     data = _read(name)
     w, h, _ = O.read_ivf(data)
     ctx = Context(w, h, max_frames=48)
+    ctx.set_device_tokens(device_tokens)
     out, n_dec, n_shown = decode_ivf(ctx, data, threads=threads)
     ctx.close()
     assert n_shown > 0 and hashlib.sha1(out).hexdigest() == name
@@ -152,9 +155,10 @@ def test_errors_mirror_reference_exception_classes():
     other.close()
 
 
+@pytest.mark.parametrize("device_tokens", [False, True])
 @pytest.mark.parametrize("name,threads", [("synth1080p_medium_q90.ivf", 8), ("synth1080p_easy_q40.ivf", 3),
                                           ("synth4k_medium_q90_8f.ivf", 2)])
-def test_full_size_clips_match_reference_decode(name, threads):
+def test_full_size_clips_match_reference_decode(name, threads, device_tokens):
     """BASELINE.json sizes (1080p bench workload, 4K): GPU decode through vp8gpu_decode_ivf vs the
     SHA-1 of the unmodified reference's decode of the same clip (tests/golden/bench_clips.json)."""
     import json
@@ -163,7 +167,8 @@ def test_full_size_clips_match_reference_decode(name, threads):
     want = json.load(open(os.path.join(root, "tests", "golden", "bench_clips.json")))[name]
     data = open(os.path.join(root, "bench_data", name), "rb").read()
     w, h, _ = O.read_ivf(data)
-    ctx = Context(w, h, max_frames=64)
+    ctx = Context(w, h, max_frames=256 if device_tokens else 64)
+    ctx.set_device_tokens(device_tokens)
     out, n_dec, n_shown = decode_ivf(ctx, data, threads=threads)
     ctx.close()
     assert len(out) == want["bytes"] and hashlib.sha1(out).hexdigest() == want["sha1_of_reference_decode"]
