@@ -3,6 +3,7 @@
 // reference rasters, explicit state passing as in decoder/decoder.hh:244-300) and the
 // GOP-parallel whole-stream helper.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -59,11 +60,16 @@ struct vp8gpu_parsed {
 // what one vp8gpu_decode_ivf worker needs for device-side token decoding
 constexpr int kTokSlots = 24;  // frames a worker may have between "first partition parsed" and "pixels done"
 constexpr int kTokChunk = 8;   // frames per k_tokens launch
+constexpr int kTokStreams = 4; // k_tokens launches of one worker that may overlap
 struct ivf_worker_kit {
   vp8::TokenRing* ring = nullptr;
-  cudaStream_t stream = nullptr;
+  // uploads never queue behind a running k_tokens: they have their own stream, and consecutive
+  // launches rotate over kTokStreams streams that only wait for their own upload
+  cudaStream_t copy_stream = nullptr;
+  cudaStream_t kstream[kTokStreams] = {};
+  int next_kstream = 0;
   vp8gpu_parsed* parsed[kTokSlots] = {};
-  cudaEvent_t ready[kTokSlots] = {}, finished[kTokSlots] = {};
+  cudaEvent_t staged[kTokSlots] = {}, ready[kTokSlots] = {}, finished[kTokSlots] = {};
   bool busy[kTokSlots] = {};
 };
 struct vp8gpu_resident_batch {
@@ -106,6 +112,10 @@ int vp8gpu_ctx_next_lane(vp8gpu_ctx* ctx) { return ctx->next_lane.fetch_add(1) %
 int vp8gpu_ctx_create(int device, int width, int height, int max_frames, vp8gpu_ctx** out) {
   if (!out) return VP8GPU_ERR_LOGIC;
   *out = nullptr;
+  // Many streams carry long-running k_tokens launches next to the short pixel launches; with the
+  // default 8 hardware queues, work of unrelated streams would line up behind them.  Only has an
+  // effect if the CUDA context does not exist yet; never overrides the user's choice.
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   vp8gpu_ctx* c = new vp8gpu_ctx();
   const int rc = Engine::create(device, width, height, max_frames, &c->engine, &c->create_error);
   if (rc != VP8GPU_OK) {
@@ -122,9 +132,12 @@ void vp8gpu_ctx_destroy(vp8gpu_ctx* ctx) {
   if (ctx->scratch_ring) ctx->engine->token_ring_free(ctx->scratch_ring);
   for (ivf_worker_kit* k : ctx->kit_pool) {
     ctx->engine->token_ring_free(k->ring);
-    if (k->stream) cudaStreamDestroy(k->stream);
+    if (k->copy_stream) cudaStreamDestroy(k->copy_stream);
+    for (cudaStream_t st : k->kstream)
+      if (st) cudaStreamDestroy(st);
     for (int i = 0; i < kTokSlots; i++) {
       if (k->parsed[i]) vp8gpu_parsed_destroy(k->parsed[i]);
+      if (k->staged[i]) cudaEventDestroy(k->staged[i]);
       if (k->ready[i]) cudaEventDestroy(k->ready[i]);
       if (k->finished[i]) cudaEventDestroy(k->finished[i]);
     }
@@ -836,9 +849,14 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     }
     if (k) return k;
     k = new ivf_worker_kit();
-    if (e->token_ring_create(kTokSlots, (size_t)max_frame_bytes + max_frame_bytes / 4 + 4096, &k->ring) != VP8GPU_OK ||
-        cudaStreamCreateWithFlags(&k->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    bool ok = e->token_ring_create(kTokSlots, (size_t)max_frame_bytes + max_frame_bytes / 4 + 4096, &k->ring) == VP8GPU_OK &&
+              cudaStreamCreateWithFlags(&k->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (cudaStream_t& st : k->kstream) ok = ok && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
+    if (!ok) {
       if (k->ring) e->token_ring_free(k->ring);
+      if (k->copy_stream) cudaStreamDestroy(k->copy_stream);
+      for (cudaStream_t st : k->kstream)
+        if (st) cudaStreamDestroy(st);
       delete k;
       return nullptr;
     }
@@ -847,6 +865,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
       k->parsed[i] = new vp8gpu_parsed(kPinned);
       k->parsed[i]->f.mbs.reserve(n_mbs, 0);
       k->parsed[i]->f.split.reserve(256, 0);
+      cudaEventCreateWithFlags(&k->staged[i], cudaEventDisableTiming);
       cudaEventCreateWithFlags(&k->ready[i], cudaEventDisableTiming);
       cudaEventCreateWithFlags(&k->finished[i], cudaEventDisableTiming);
     }
@@ -888,7 +907,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
           rc = vp8::parse_frame(state, items[i + c].p, items[i + c].n, p->f, true);
           if (rc != VP8GPU_OK) break;
           count_mbs(p);
-          rc = e->token_ring_stage(kit->ring, si, p->f, kit->stream);
+          rc = e->token_ring_stage(kit->ring, si, p->f, kit->copy_stream);
           if (rc != VP8GPU_OK) break;
           staged++;
           t_slot += t1 - t0;
@@ -896,12 +915,16 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
           t_parse += now() - t2;
         }
         if (rc != VP8GPU_OK) break;
+        cudaStream_t ks = kit->kstream[kit->next_kstream];
+        kit->next_kstream = (kit->next_kstream + 1) % kTokStreams;
+        cudaEventRecord(kit->staged[first_slot], kit->copy_stream);
+        cudaStreamWaitEvent(ks, kit->staged[first_slot], 0);
         // the ring is used modulo tok_slots (<= its real size): a chunk that wraps needs two launches
         const int until_wrap = tok_slots - first_slot;
-        rc = e->token_ring_launch(kit->ring, first_slot, staged < until_wrap ? staged : until_wrap, kit->stream);
-        if (rc == VP8GPU_OK && staged > until_wrap) rc = e->token_ring_launch(kit->ring, 0, staged - until_wrap, kit->stream);
+        rc = e->token_ring_launch(kit->ring, first_slot, staged < until_wrap ? staged : until_wrap, ks);
+        if (rc == VP8GPU_OK && staged > until_wrap) rc = e->token_ring_launch(kit->ring, 0, staged - until_wrap, ks);
         if (rc != VP8GPU_OK) break;
-        for (int c = 0; c < staged; c++) cudaEventRecord(kit->ready[(first_slot + c) % tok_slots], kit->stream);
+        for (int c = 0; c < staged; c++) cudaEventRecord(kit->ready[(first_slot + c) % tok_slots], ks);
         for (int c = 0; c < staged && rc == VP8GPU_OK; c++) {
           const int si = (first_slot + c) % tok_slots;
           vp8gpu_parsed* p = kit->parsed[si];
@@ -972,7 +995,8 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
           cudaEventSynchronize(kit->finished[k]);
           kit->busy[k] = false;
         }
-      cudaStreamSynchronize(kit->stream);
+      cudaStreamSynchronize(kit->copy_stream);
+      for (cudaStream_t st : kit->kstream) cudaStreamSynchronize(st);
       std::lock_guard<std::mutex> lk(ctx->pool_mu);
       ctx->kit_pool.push_back(kit);
     }

@@ -28,12 +28,11 @@ constexpr int kMaxCols = 1024;  // 16383 px / 16
 
 // jobs live at the start of equally spaced slots of a ring (engine.hpp TokenRing)
 __global__ void __launch_bounds__(32) k_tokens(const uint8_t* ring, size_t stride, int first, int nslots, Geom g) {
-  __shared__ uint8_t probs[1056];
+  __shared__ __align__(16) uint8_t probs[tok::kProbBytes];
   __shared__ uint16_t above_nz[kMaxCols];
   const TokJob& J = *reinterpret_cast<const TokJob*>(ring + static_cast<size_t>((first + blockIdx.x) % nslots) * stride);
   const int lane = threadIdx.x;
-  for (int i = lane; i < 1056 / 4; i += 32)
-    reinterpret_cast<uint32_t*>(probs)[i] = __ldg(reinterpret_cast<const uint32_t*>(J.coef_probs) + i);
+  for (int e = lane; e < tok::kProbEntries; e += 32) tok::expand_prob_entry(J.coef_probs, probs, e);
   for (int i = lane; i < g.mb_cols; i += 32) above_nz[i] = 0;
   __syncwarp();
   if (lane != 0) return;

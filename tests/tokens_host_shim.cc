@@ -51,7 +51,9 @@ int th_frame(void* hp, const uint8_t* data, size_t len, uint32_t tok_cap_overrid
   memcpy(J.part_len, H.pb.tw.part_len, sizeof(J.part_len));
   J.nparts = H.pb.tw.nparts;
   J.tok_cap = (uint32_t)cap;
-  vp8::tok::decode_frame_tokens(J, g, H.pb.tw.coef_probs, H.above.data());
+  alignas(16) uint8_t probs16[vp8::tok::kProbBytes];
+  for (int e = 0; e < vp8::tok::kProbEntries; e++) vp8::tok::expand_prob_entry(H.pb.tw.coef_probs, probs16, e);
+  vp8::tok::decode_frame_tokens(J, g, probs16, H.above.data());
   if (n_tokens) *n_tokens = result[0];
   if (H.tokens[cap] != 0xDEADBEEFu) return 5;
   if (result[1]) return 5;
