@@ -687,7 +687,6 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
   // device sees a few large launches instead of three small ones per frame, and the wavefront
   // kernels get rows of many frames to hide their latency with.
   constexpr int kSlots = 4;      // parsed frames a worker may have in flight
-  constexpr int kDispatchLanes = 4;
   enum SlotState { kFree = 0, kQueued = 1 };
   struct Pending {
     vp8gpu_parsed* slot;
@@ -700,10 +699,13 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     int ring_slot = 0;
     cudaEvent_t ready = nullptr, finished = nullptr;
   };
+  const int n_disp = device_tokens ? (threads >= 32 ? 4 : (threads >= 8 ? 2 : 1)) : 1;
   std::mutex mu;
-  std::condition_variable cv_workers, cv_dispatch;
+  std::condition_variable cv_workers;
+  std::vector<std::condition_variable> cv_disp(n_disp);
   std::vector<std::deque<Pending>> queues(threads);
-  int workers_running = threads;
+  std::vector<int> running(n_disp, 0);  // workers each dispatcher still serves
+  for (int t = 0; t < threads; t++) running[t % n_disp]++;
   std::atomic<int> next_gop{0};
   std::atomic<int> first_error{VP8GPU_OK};
   auto set_error = [&](int rc) {
@@ -796,7 +798,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
           slot_state[si] = kQueued;
           queues[tid].push_back(job);
         }
-        cv_dispatch.notify_one();
+        cv_disp[tid % n_disp].notify_one();
       }
       if (rc != VP8GPU_OK) {
         set_error(rc);
@@ -810,9 +812,9 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
           if (slot_state[k] != kFree) return false;  // the dispatcher still owns that slot
         return true;
       });
-      workers_running--;
+      running[tid % n_disp]--;
     }
-    cv_dispatch.notify_one();
+    cv_disp[tid % n_disp].notify_one();
     {
       std::lock_guard<std::mutex> lk(stats_mu);
       st_parse += t_parse;
@@ -963,7 +965,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
             slot_state[si] = kQueued;
             queues[tid].push_back(job);
           }
-          cv_dispatch.notify_one();
+          cv_disp[tid % n_disp].notify_one();
         }
         next_slot = (first_slot + staged) % tok_slots;
         i += (uint32_t)staged;
@@ -978,9 +980,9 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
           if (slot_state[k] != kFree) return false;
         return true;
       });
-      workers_running--;
+      running[tid % n_disp]--;
     }
-    cv_dispatch.notify_one();
+    cv_disp[tid % n_disp].notify_one();
     {
       std::lock_guard<std::mutex> lk(stats_mu);
       st_parse += t_parse;
@@ -1002,11 +1004,15 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     }
   };
 
-  auto dispatcher = [&]() {
+  // Dispatchers: dispatcher d serves the workers with tid % D == d on its own two lanes.  Queueing a
+  // frame costs a few dozen driver calls (stream ordering of its rasters, the launches, the download),
+  // which one thread cannot do for more than ~10k frames/s.
+  auto dispatcher = [&](int di) {
     cudaSetDevice(e->device());
     std::vector<Pending> batch;
     std::vector<HostJob> hj;
     int round = 0;
+    double t_idle = 0, t_submit = 0, t_download = 0, n_batches = 0, n_jobs = 0;
     for (;;) {
       batch.clear();
       const double ti = now();
@@ -1018,44 +1024,44 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
         };
         auto ready = [&] {
           int n = 0;
-          for (auto& q : queues) n += eligible(q);
+          for (int t = di; t < threads; t += n_disp) n += eligible(queues[t]);
           return n;
         };
         auto queued = [&] {
-          for (auto& q : queues)
-            if (!q.empty()) return true;
+          for (int t = di; t < threads; t += n_disp)
+            if (!queues[t].empty()) return true;
           return false;
         };
         // nothing signals the condition variable when a CUDA event fires: poll while frames wait for one
-        while (!(workers_running == 0 && !queued()) && ready() == 0) {
-          if (queued()) cv_dispatch.wait_for(lk, std::chrono::microseconds(100));
-          else cv_dispatch.wait(lk);
+        while (!(running[di] == 0 && !queued()) && ready() == 0) {
+          if (queued()) cv_disp[di].wait_for(lk, std::chrono::microseconds(100));
+          else cv_disp[di].wait(lk);
         }
         // Device time per batch is almost flat in the number of frames (the wavefront kernels
         // are latency bound), so give the other workers a moment to finish their current frame:
         // go once most of them have something queued, or after a short grace period.
         const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(1500);
-        while (workers_running > 0 && ready() < (workers_running * 3 + 3) / 4) {
+        while (running[di] > 0 && ready() < (running[di] * 3 + 3) / 4) {
           if (device_tokens) {
             if (std::chrono::steady_clock::now() >= deadline) break;
-            cv_dispatch.wait_for(lk, std::chrono::microseconds(100));
-          } else if (cv_dispatch.wait_until(lk, deadline) == std::cv_status::timeout) {
+            cv_disp[di].wait_for(lk, std::chrono::microseconds(100));
+          } else if (cv_disp[di].wait_until(lk, deadline) == std::cv_status::timeout) {
             break;
           }
         }
-        for (auto& q : queues)
-          if (eligible(q)) {
-            batch.push_back(q.front());
-            q.pop_front();
+        for (int t = di; t < threads; t += n_disp)
+          if (eligible(queues[t])) {
+            batch.push_back(queues[t].front());
+            queues[t].pop_front();
           }
-        if (batch.empty() && workers_running == 0 && !queued()) break;
+        if (batch.empty() && running[di] == 0 && !queued()) break;
       }
       if (batch.empty()) continue;
       const double ts = now();
-      st_disp_idle += ts - ti;
-      st_batches += 1;
-      st_jobs += batch.size();
-      const int lane = round++ % kDispatchLanes;
+      t_idle += ts - ti;
+      n_batches += 1;
+      n_jobs += batch.size();
+      const int lane = 2 * di + (round++ & 1);
       hj.clear();
       for (const Pending& b : batch) {
         HostJob j;
@@ -1079,7 +1085,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
       }
       int rc = e->submit(lane, hj.data(), (int)hj.size(), nullptr);
       const double td = now();
-      st_submit += td - ts;
+      t_submit += td - ts;
       for (const Pending& b : batch) {
         if (rc == VP8GPU_OK) {
           if (!b.ring) b.slot->busy = true;
@@ -1093,14 +1099,21 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
         e->frame_release(b.out);
       }
       if (rc != VP8GPU_OK) set_error(rc);
-      st_download += now() - td;
+      t_download += now() - td;
       {
         std::lock_guard<std::mutex> lk(mu);
         for (const Pending& b : batch) *b.slot_state = kFree;
       }
       cv_workers.notify_all();
     }
-    for (int l = 0; l < kDispatchLanes; l++) e->sync_lane(l);
+    e->sync_lane(2 * di);
+    e->sync_lane(2 * di + 1);
+    std::lock_guard<std::mutex> lk(stats_mu);
+    st_disp_idle += t_idle;
+    st_submit += t_submit;
+    st_download += t_download;
+    st_batches += n_batches;
+    st_jobs += n_jobs;
   };
 
   std::vector<std::thread> pool;
@@ -1108,7 +1121,10 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     if (device_tokens) pool.emplace_back(worker_dev, t);
     else pool.emplace_back(worker, t);
   }
-  dispatcher();
+  std::vector<std::thread> dispatchers;
+  for (int d = 1; d < n_disp; d++) dispatchers.emplace_back(dispatcher, d);
+  dispatcher(0);
+  for (auto& t : dispatchers) t.join();
   for (auto& t : pool) t.join();
   ctx->stats[0] = st_parse;
   ctx->stats[1] = st_wait_slot;
