@@ -78,6 +78,10 @@ struct vp8gpu_resident_batch {
 
 namespace {
 
+// events a host thread waits on: block instead of spinning -- vp8gpu_decode_ivf runs more host threads
+// than there are CPUs, and a spinning waiter takes the core the dispatcher needs
+constexpr unsigned kWaitableEvent = cudaEventDisableTiming | cudaEventBlockingSync;
+
 void* pinned_alloc(size_t n) {
   void* p = nullptr;
   return cudaHostAlloc(&p, n, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
@@ -405,7 +409,7 @@ vp8gpu_parsed* next_ring_slot(vp8gpu_decoder* d) {
     }
     if (!p) {
       p = new vp8gpu_parsed(kPinned);
-      cudaEventCreateWithFlags(&p->consumed, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&p->consumed, kWaitableEvent);
       // size the token buffer generously up front: growing pinned memory means a new cudaHostAlloc
       const vp8::Geom& g = d->ctx->engine->geom();
       const size_t n_mbs = (size_t)g.mb_cols * g.mb_rows;
@@ -573,7 +577,7 @@ int vp8gpu_decoder_decode(vp8gpu_decoder* d, const uint8_t* data, size_t len, in
     rc = e->token_ring_create(vp8::kStagingDepth, len * 2 + 65536, &d->tok_ring);
     if (rc != VP8GPU_OK) return rc;
     for (auto& ev : d->tok_finished)
-      if (!ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+      if (!ev) cudaEventCreateWithFlags(&ev, kWaitableEvent);
   }
   const int slot = d->tok_next;
   d->tok_next = (d->tok_next + 1) % vp8::kStagingDepth;
@@ -742,7 +746,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
           }
           if (!slots[si]) {
             slots[si] = new vp8gpu_parsed(kPinned);
-            cudaEventCreateWithFlags(&slots[si]->consumed, cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&slots[si]->consumed, kWaitableEvent);
             const size_t n_mbs = (size_t)e->geom().mb_cols * e->geom().mb_rows;
             slots[si]->f.mbs.reserve(n_mbs, 0);
             slots[si]->f.tokens.reserve(n_mbs * 32 + 1024, 0);
@@ -869,7 +873,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
       k->parsed[i]->f.split.reserve(256, 0);
       cudaEventCreateWithFlags(&k->staged[i], cudaEventDisableTiming);
       cudaEventCreateWithFlags(&k->ready[i], cudaEventDisableTiming);
-      cudaEventCreateWithFlags(&k->finished[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&k->finished[i], kWaitableEvent);
     }
     return k;
   };

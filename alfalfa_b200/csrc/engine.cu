@@ -455,7 +455,7 @@ int Engine::submit(int lane, const HostJob* jobs, int n, cudaEvent_t consumed) {
     CU(cudaEventSynchronize(st.done));
     st.in_flight = false;
   }
-  if (!st.done) CU(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+  if (!st.done) CU(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming | cudaEventBlockingSync));
   const size_t hdr_bytes = align_up(L.sync_off + L.sync_bytes, 256);
   if (st.host_cap < hdr_bytes) {
     if (st.host) CU(cudaFreeHost(st.host));
