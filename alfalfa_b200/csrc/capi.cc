@@ -58,8 +58,8 @@ struct vp8gpu_parsed {
   explicit vp8gpu_parsed(const vp8::Allocator& a) : f(a) {}
 };
 // what one vp8gpu_decode_ivf worker needs for device-side token decoding
-constexpr int kTokSlots = 24;  // frames a worker may have between "first partition parsed" and "pixels done"
-constexpr int kTokChunk = 8;   // frames per k_tokens launch
+constexpr int kTokSlots = 64;  // frames a worker may have between "first partition parsed" and "pixels done"
+constexpr int kTokChunk = 15;  // frames per k_tokens launch (at most a quarter of the slots)
 constexpr int kTokStreams = 4; // k_tokens launches of one worker that may overlap
 struct ivf_worker_kit {
   vp8::TokenRing* ring = nullptr;
@@ -88,6 +88,10 @@ void* pinned_alloc(size_t n) {
 }
 void pinned_free(void* p) { cudaFreeHost(p); }
 const vp8::Allocator kPinned = {&pinned_alloc, &pinned_free};
+
+// partition capacity of a token ring for streams whose largest frame has n bytes (some slack, so
+// that a pooled ring fits the next stream too)
+size_t ring_bytes_for(size_t n) { return n + n / 4 + 4096; }
 
 void count_mbs(vp8gpu_parsed* p) {
   const vp8gpu_frame_desc& d = p->f.desc;
@@ -143,7 +147,6 @@ void vp8gpu_ctx_destroy(vp8gpu_ctx* ctx) {
       if (k->parsed[i]) vp8gpu_parsed_destroy(k->parsed[i]);
       if (k->staged[i]) cudaEventDestroy(k->staged[i]);
       if (k->ready[i]) cudaEventDestroy(k->ready[i]);
-      if (k->finished[i]) cudaEventDestroy(k->finished[i]);
     }
     delete k;
   }
@@ -446,7 +449,7 @@ int decode_parsed_impl(vp8gpu_decoder* d, vp8gpu_parsed* p, bool pinned_ring, in
   if (tok_slot >= 0) {  // records and tokens are already in the ring, produced on this lane's stream
     j.ring = d->tok_ring;
     j.ring_slot = tok_slot;
-    j.finished = d->tok_finished[tok_slot];
+    j.finished = &d->tok_finished[tok_slot];
   }
   rc = e->submit(d->lane, &j, 1, pinned_ring ? p->consumed : nullptr);
   if (rc != VP8GPU_OK) {
@@ -542,8 +545,6 @@ void vp8gpu_decoder_destroy(vp8gpu_decoder* d) {
     e->sync_lane(d->lane);
     e->token_ring_free(d->tok_ring);
   }
-  for (auto& ev : d->tok_finished)
-    if (ev) cudaEventDestroy(ev);
   delete d;
 }
 
@@ -576,13 +577,11 @@ int vp8gpu_decoder_decode(vp8gpu_decoder* d, const uint8_t* data, size_t len, in
   if (!d->tok_ring) {
     rc = e->token_ring_create(vp8::kStagingDepth, len * 2 + 65536, &d->tok_ring);
     if (rc != VP8GPU_OK) return rc;
-    for (auto& ev : d->tok_finished)
-      if (!ev) cudaEventCreateWithFlags(&ev, kWaitableEvent);
   }
   const int slot = d->tok_next;
   d->tok_next = (d->tok_next + 1) % vp8::kStagingDepth;
   if (d->tok_busy[slot]) {
-    cudaEventSynchronize(d->tok_finished[slot]);
+    if (d->tok_finished[slot]) cudaEventSynchronize(d->tok_finished[slot]);
     d->tok_busy[slot] = false;
   }
   rc = vp8::parse_frame(d->state.s, data, len, p->f, true);
@@ -671,7 +670,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
   gop_start.push_back((uint32_t)items.size());
   const int n_gops = (int)gop_start.size() - 1;
   if (threads < 1) threads = 1;
-  if (threads > 256) threads = 256;
+  if (threads > 512) threads = 512;
   if (threads > n_gops) threads = n_gops > 0 ? n_gops : 1;
   // device-side token decoding needs rasters for the frames a worker keeps in flight
   uint32_t max_frame_bytes = 0;
@@ -679,11 +678,23 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
   int tok_slots = 0;
   if (ctx->device_tokens.load()) {
     tok_slots = e->frames_free() / threads - 4;
-    if (tok_slots > kTokSlots) tok_slots = kTokSlots;
+    // k_tokens needs tens of milliseconds per frame (one thread each), so a worker wants to run a
+    // GOP or two ahead of the pixel kernels; bounded by a device-memory budget for the rings
+    const size_t ring_budget = (size_t)12 << 30;
+    const size_t stride = e->token_ring_layout(ring_bytes_for(max_frame_bytes)).stride;
+    int want = (int)(ring_budget / (stride * (size_t)threads));
+    if (want > 60) want = 60;
+    if (const char* v = getenv("VP8GPU_TOK_SLOTS")) want = atoi(v);  // tuning knob
+    if (want > kTokSlots) want = kTokSlots;
+    if (tok_slots > want) tok_slots = want;
     if (tok_slots < 4) tok_slots = 0;  // pool too small: the host workers parse everything
   }
   const bool device_tokens = tok_slots > 0;
-  const int tok_chunk = tok_slots >= 2 * kTokChunk ? kTokChunk : (tok_slots / 2 > 0 ? tok_slots / 2 : 1);
+  int tok_chunk = tok_slots / 4 > kTokChunk ? kTokChunk : (tok_slots / 4 > 0 ? tok_slots / 4 : 1);
+  if (const char* v = getenv("VP8GPU_TOK_CHUNK")) {  // tuning knob
+    const int c = atoi(v);
+    if (c >= 1 && c <= tok_slots / 2) tok_chunk = c;
+  }
 
   // Host workers only parse (CPU entropy front end) and keep the per-GOP codec state; a single
   // dispatcher gathers whatever they have produced -- at most one frame per worker, because
@@ -701,7 +712,8 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     // device-side tokens: the records live in ring slot `ring_slot` once `ready` has fired
     const vp8::TokenRing* ring = nullptr;
     int ring_slot = 0;
-    cudaEvent_t ready = nullptr, finished = nullptr;
+    cudaEvent_t ready = nullptr;
+    cudaEvent_t* finished = nullptr;  // where submit() leaves the event that fires after the pixel kernels
   };
   const int n_disp = device_tokens ? (threads >= 32 ? 4 : (threads >= 8 ? 2 : 1)) : 1;
   std::mutex mu;
@@ -847,7 +859,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     {
       std::lock_guard<std::mutex> lk(ctx->pool_mu);
       for (size_t i = 0; i < ctx->kit_pool.size(); i++)
-        if (ctx->kit_pool[i]->ring->bits_cap >= max_frame_bytes + 16) {
+        if (ctx->kit_pool[i]->ring->bits_cap >= max_frame_bytes + 16 && ctx->kit_pool[i]->ring->nslots >= tok_slots) {
           k = ctx->kit_pool[i];
           ctx->kit_pool.erase(ctx->kit_pool.begin() + i);
           break;
@@ -855,7 +867,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     }
     if (k) return k;
     k = new ivf_worker_kit();
-    bool ok = e->token_ring_create(kTokSlots, (size_t)max_frame_bytes + max_frame_bytes / 4 + 4096, &k->ring) == VP8GPU_OK &&
+    bool ok = e->token_ring_create(tok_slots, ring_bytes_for(max_frame_bytes), &k->ring) == VP8GPU_OK &&
               cudaStreamCreateWithFlags(&k->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (cudaStream_t& st : k->kstream) ok = ok && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
     if (!ok) {
@@ -867,13 +879,12 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
       return nullptr;
     }
     const size_t n_mbs = (size_t)e->geom().mb_cols * e->geom().mb_rows;
-    for (int i = 0; i < kTokSlots; i++) {
+    for (int i = 0; i < tok_slots; i++) {
       k->parsed[i] = new vp8gpu_parsed(kPinned);
       k->parsed[i]->f.mbs.reserve(n_mbs, 0);
       k->parsed[i]->f.split.reserve(256, 0);
       cudaEventCreateWithFlags(&k->staged[i], cudaEventDisableTiming);
       cudaEventCreateWithFlags(&k->ready[i], cudaEventDisableTiming);
-      cudaEventCreateWithFlags(&k->finished[i], kWaitableEvent);
     }
     return k;
   };
@@ -905,7 +916,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
           }
           const double t1 = now();
           if (kit->busy[si]) {  // ... and the pixel kernels must have read its records
-            cudaEventSynchronize(kit->finished[si]);
+            if (kit->finished[si]) cudaEventSynchronize(kit->finished[si]);
             kit->busy[si] = false;
           }
           const double t2 = now();
@@ -942,7 +953,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
           job.ring = kit->ring;
           job.ring_slot = si;
           job.ready = kit->ready[si];
-          job.finished = kit->finished[si];
+          job.finished = &kit->finished[si];
           rc = e->frame_alloc(&job.out);
           if (rc != VP8GPU_OK) break;
           for (int k = 0; k < 3; k++) {
@@ -998,7 +1009,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     if (kit) {
       for (int k = 0; k < kTokSlots; k++)
         if (kit->busy[k]) {
-          cudaEventSynchronize(kit->finished[k]);
+          if (kit->finished[k]) cudaEventSynchronize(kit->finished[k]);
           kit->busy[k] = false;
         }
       cudaStreamSynchronize(kit->copy_stream);
@@ -1015,6 +1026,8 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     cudaSetDevice(e->device());
     std::vector<Pending> batch;
     std::vector<HostJob> hj;
+    std::vector<int> dl_ids;
+    std::vector<uint8_t*> dl_dst;
     int round = 0;
     double t_idle = 0, t_submit = 0, t_download = 0, n_batches = 0, n_jobs = 0;
     for (;;) {
@@ -1090,14 +1103,19 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
       int rc = e->submit(lane, hj.data(), (int)hj.size(), nullptr);
       const double td = now();
       t_submit += td - ts;
-      for (const Pending& b : batch) {
-        if (rc == VP8GPU_OK) {
+      if (rc == VP8GPU_OK) {
+        dl_ids.clear();
+        dl_dst.clear();
+        for (const Pending& b : batch) {
           if (!b.ring) b.slot->busy = true;
           if (b.out_off >= 0) {
-            const int r2 = e->frame_download_display(b.out, lane, dst + b.out_off, frame_bytes, false);
-            if (r2 != VP8GPU_OK) rc = r2;
+            dl_ids.push_back(b.out);
+            dl_dst.push_back(dst + b.out_off);
           }
         }
+        if (!dl_ids.empty()) rc = e->frames_download_display(dl_ids.data(), dl_dst.data(), (int)dl_ids.size(), lane);
+      }
+      for (const Pending& b : batch) {
         for (int k = 0; k < 3; k++)
           if (b.refs[k] >= 0) e->frame_release(b.refs[k]);
         e->frame_release(b.out);

@@ -76,10 +76,10 @@ Engine::~Engine() {
   cudaDeviceSynchronize();
   for (auto& f : frames_) {
     if (f.dev) cudaFree(f.dev);
-    for (auto& ev : f.ev)
-      if (ev) cudaEventDestroy(ev);
-    if (f.wev) cudaEventDestroy(f.wev);
   }
+  for (auto& ring : ring_)
+    for (auto& ev : ring)
+      if (ev) cudaEventDestroy(ev);
   for (int l = 0; l < kMaxLanes; l++)
     for (auto& s : staging_[l]) {
       if (s.dev) cudaFree(s.dev);
@@ -137,32 +137,56 @@ int Engine::frames_free() {
   return (int)free_.size();
 }
 
-// Stream ordering of rasters.  A raster remembers the stream slot that last WROTE it (wev) and the
-// slots that READ it since (ev[slot]): a reader only waits for the writer, so that e.g. the
-// download of a frame does not delay the next frame's motion compensation from it; a writer
-// (a recycled raster) waits for everybody.  Caller holds mu_.
-int Engine::touch(Frame& f, int slot, bool write) {
-  if (write) {
-    if (!f.wev) CU(cudaEventCreateWithFlags(&f.wev, cudaEventDisableTiming));
-    CU(cudaEventRecord(f.wev, lanes_[slot]));
-    f.wslot = slot;
-    f.pending = 0;  // the preceding wait_for(write) ordered this stream after every reader
-    return VP8GPU_OK;
+// Stream ordering of rasters.  A raster remembers the stream slot that last WROTE it (wslot, wev)
+// and the slots that READ it since (pending, ev[slot]): a reader only waits for the writer, so that
+// e.g. the download of a frame does not delay the next frame's motion compensation from it; a
+// writer (a recycled raster) waits for everybody.  The events are not owned by the raster: they come
+// from a small ring per stream slot, and one record serves every raster a batch touched.  A ring
+// entry that has been re-recorded since only makes a later waiter wait for newer work of the same
+// stream (conservative, and never cyclic: waits always point at work queued earlier).
+// Caller holds mu_.
+cudaEvent_t Engine::next_event(int slot) {
+  cudaEvent_t& ev = ring_[slot][ring_next_[slot]];
+  ring_next_[slot] = (ring_next_[slot] + 1) % kEventRing;
+  if (!ev && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) return nullptr;
+  return ev;
+}
+int Engine::touch(Frame& f, int slot, bool write, cudaEvent_t shared) {
+  cudaEvent_t ev = shared;
+  if (!ev) {
+    ev = next_event(slot);
+    if (!ev) return fail(VP8GPU_ERR_CUDA, "event creation failed");
+    CU(cudaEventRecord(ev, lanes_[slot]));
   }
-  if (!f.ev[slot]) CU(cudaEventCreateWithFlags(&f.ev[slot], cudaEventDisableTiming));
-  CU(cudaEventRecord(f.ev[slot], lanes_[slot]));
-  f.pending |= 1ull << slot;
+  if (write) {
+    f.wev = ev;
+    f.wslot = slot;
+    f.pending = 0;  // the preceding wait ordered this stream after every reader
+  } else {
+    f.ev[slot] = ev;
+    f.pending |= 1ull << slot;
+  }
   return VP8GPU_OK;
 }
-int Engine::wait_for(Frame& f, int slot, cudaStream_t s, bool write) {
-  if (f.wslot >= 0 && f.wslot != slot) CU(cudaStreamWaitEvent(s, f.wev, 0));
-  if (!write) return VP8GPU_OK;
+void Engine::collect_waits(const Frame& f, int slot, bool write, std::vector<cudaEvent_t>& out) const {
+  auto add = [&out](cudaEvent_t ev) {
+    for (cudaEvent_t o : out)
+      if (o == ev) return;
+    out.push_back(ev);
+  };
+  if (f.wslot >= 0 && f.wslot != slot) add(f.wev);
+  if (!write) return;
   uint64_t m = f.pending & ~(1ull << slot);
   while (m) {
     const int t = __builtin_ctzll(m);
     m &= m - 1;
-    CU(cudaStreamWaitEvent(s, f.ev[t], 0));
+    add(f.ev[t]);
   }
+}
+int Engine::wait_for(Frame& f, int slot, cudaStream_t s, bool write) {
+  std::vector<cudaEvent_t> w;
+  collect_waits(f, slot, write, w);
+  for (cudaEvent_t ev : w) CU(cudaStreamWaitEvent(s, ev, 0));
   return VP8GPU_OK;
 }
 
@@ -209,28 +233,55 @@ int Engine::frame_download(int id, uint8_t* y, size_t ys, uint8_t* u, uint8_t* v
   return VP8GPU_OK;
 }
 
-int Engine::frame_download_display(int id, int lane, uint8_t* dst, size_t dst_size, bool wait) {
+int Engine::frames_download_display(const int* ids, uint8_t* const* dsts, int n, int lane) {
+  if (n <= 0) return VP8GPU_OK;
   if (int rc = ensure_lane(lane)) return rc;
+  const int cw = (width_ + 1) / 2, ch = (height_ + 1) / 2;
+  const int slot = kMaxLanes + lane;
+  cudaStream_t s = lanes_[slot];
+  std::vector<cudaEvent_t> waits;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (int i = 0; i < n; i++) {
+      if (ids[i] < 0 || ids[i] >= (int)frames_.size() || frames_[ids[i]].refcnt <= 0)
+        return fail(VP8GPU_ERR_LOGIC, "download: bad frame id");
+      collect_waits(frames_[ids[i]], slot, false, waits);
+    }
+  }
+  for (cudaEvent_t ev : waits) CU(cudaStreamWaitEvent(s, ev, 0));
+  // rows are contiguous when the pitch equals the display width (e.g. 1080p): plain copies
+  const bool flat = g_.y_pitch == width_ && g_.c_pitch == cw;
+  for (int i = 0; i < n; i++) {
+    const uint8_t* src = frames_[ids[i]].dev;
+    uint8_t* p = dsts[i];
+    if (flat) {
+      CU(cudaMemcpyAsync(p, src, (size_t)width_ * height_, cudaMemcpyDeviceToHost, s));
+      p += (size_t)width_ * height_;
+      CU(cudaMemcpyAsync(p, src + g_.u_off, (size_t)cw * ch, cudaMemcpyDeviceToHost, s));
+      p += (size_t)cw * ch;
+      CU(cudaMemcpyAsync(p, src + g_.v_off, (size_t)cw * ch, cudaMemcpyDeviceToHost, s));
+    } else {
+      CU(cudaMemcpy2DAsync(p, width_, src, g_.y_pitch, width_, height_, cudaMemcpyDeviceToHost, s));
+      p += (size_t)width_ * height_;
+      CU(cudaMemcpy2DAsync(p, cw, src + g_.u_off, g_.c_pitch, cw, ch, cudaMemcpyDeviceToHost, s));
+      p += (size_t)cw * ch;
+      CU(cudaMemcpy2DAsync(p, cw, src + g_.v_off, g_.c_pitch, cw, ch, cudaMemcpyDeviceToHost, s));
+    }
+  }
+  std::lock_guard<std::mutex> lk(mu_);
+  cudaEvent_t ev = next_event(slot);
+  if (!ev) return fail(VP8GPU_ERR_CUDA, "event creation failed");
+  CU(cudaEventRecord(ev, s));
+  for (int i = 0; i < n; i++) touch(frames_[ids[i]], slot, false, ev);
+  return VP8GPU_OK;
+}
+
+int Engine::frame_download_display(int id, int lane, uint8_t* dst, size_t dst_size, bool wait) {
   const int cw = (width_ + 1) / 2, ch = (height_ + 1) / 2;
   const size_t need = (size_t)width_ * height_ + 2 * (size_t)cw * ch;
   if (dst_size < need) return fail(VP8GPU_ERR_LOGIC, "download_display: destination too small");
-  cudaStream_t s;
-  {
-    std::lock_guard<std::mutex> lk(mu_);
-    if (id < 0 || id >= (int)frames_.size() || frames_[id].refcnt <= 0) return fail(VP8GPU_ERR_LOGIC, "download: bad frame id");
-    Frame& f = frames_[id];
-    const int slot = kMaxLanes + lane;
-    s = lanes_[slot];
-    if (int rc = wait_for(f, slot, s, false)) return rc;
-    uint8_t* p = dst;
-    CU(cudaMemcpy2DAsync(p, width_, f.dev, g_.y_pitch, width_, height_, cudaMemcpyDeviceToHost, s));
-    p += (size_t)width_ * height_;
-    CU(cudaMemcpy2DAsync(p, cw, f.dev + g_.u_off, g_.c_pitch, cw, ch, cudaMemcpyDeviceToHost, s));
-    p += (size_t)cw * ch;
-    CU(cudaMemcpy2DAsync(p, cw, f.dev + g_.v_off, g_.c_pitch, cw, ch, cudaMemcpyDeviceToHost, s));
-    if (int rc = touch(f, slot, false)) return rc;
-  }
-  if (wait) CU(cudaStreamSynchronize(s));
+  if (int rc = frames_download_display(&id, &dst, 1, lane)) return rc;
+  if (wait) CU(cudaStreamSynchronize(lanes_[kMaxLanes + lane]));
   return VP8GPU_OK;
 }
 
@@ -358,33 +409,38 @@ int Engine::build_and_launch(int lane, const DevJob* d_jobs, int* d_sync, int n,
 // ------------------------------------------------------------------------------------------
 // device-side token decoding (tokens.cu)
 // ------------------------------------------------------------------------------------------
-int Engine::token_ring_create(int nslots, size_t max_frame_bytes, TokenRing** out) {
-  CU(cudaSetDevice(device_));
+TokenRing Engine::token_ring_layout(size_t max_frame_bytes) const {
   const size_t n_mbs = (size_t)g_.mb_cols * g_.mb_rows;
-  TokenRing* r = new TokenRing();
-  r->nslots = nslots;
-  r->bits_cap = (uint32_t)align_up(max_frame_bytes + 16, 256);
-  r->split_cap = (uint32_t)n_mbs;
+  TokenRing r;
+  r.bits_cap = (uint32_t)align_up(max_frame_bytes + 16, 256);
+  r.split_cap = (uint32_t)n_mbs;
   // Every non-zero token ends with a sign decoded at probability 128, which consumes >= 0.98 bit
   // of the partition, and past the end of the data every block ends at once (only zero bits
   // arrive): tokens <= 8.2 * bytes + lookahead.  Never more than 25 * 16 per macroblock.
-  const size_t by_bytes = (size_t)r->bits_cap * 9 + 1024, by_blocks = n_mbs * 400;
-  r->tok_cap = (uint32_t)(by_bytes < by_blocks ? by_bytes : by_blocks);
+  const size_t by_bytes = (size_t)r.bits_cap * 9 + 1024, by_blocks = n_mbs * 400;
+  r.tok_cap = (uint32_t)(by_bytes < by_blocks ? by_bytes : by_blocks);
   size_t off = 256;  // TokJob
-  r->probs_off = off;
+  r.probs_off = off;
   off += 1280;
-  r->bits_off = off;
-  off = align_up(off + r->bits_cap, 256);
-  r->host_stride = off;
-  r->result_off = off;
+  r.bits_off = off;
+  off = align_up(off + r.bits_cap, 256);
+  r.host_stride = off;
+  r.result_off = off;
   off += 256;
-  r->mbs_off = off;
+  r.mbs_off = off;
   off = align_up(off + n_mbs * sizeof(vp8gpu_mb), 256);
-  r->split_off = off;
-  off = align_up(off + (size_t)r->split_cap * sizeof(vp8gpu_split_mvs), 256);
-  r->tok_off = off;
-  off = align_up(off + (size_t)r->tok_cap * sizeof(vp8gpu_token), 256);
-  r->stride = off;
+  r.split_off = off;
+  off = align_up(off + (size_t)r.split_cap * sizeof(vp8gpu_split_mvs), 256);
+  r.tok_off = off;
+  off = align_up(off + (size_t)r.tok_cap * sizeof(vp8gpu_token), 256);
+  r.stride = off;
+  return r;
+}
+
+int Engine::token_ring_create(int nslots, size_t max_frame_bytes, TokenRing** out) {
+  CU(cudaSetDevice(device_));
+  TokenRing* r = new TokenRing(token_ring_layout(max_frame_bytes));
+  r->nslots = nslots;
   if (cudaMalloc(&r->dev, r->stride * nslots) != cudaSuccess ||
       cudaHostAlloc(&r->host, r->host_stride * nslots, cudaHostAllocDefault) != cudaSuccess) {
     token_ring_free(r);
@@ -472,6 +528,7 @@ int Engine::submit(int lane, const HostJob* jobs, int n, cudaEvent_t consumed) {
   DevJob* hj = reinterpret_cast<DevJob*>(st.host);
   int* d_sync = reinterpret_cast<int*>(st.dev + L.sync_off);
   bool any_inter = false, any_intra = false, any_lf = false;
+  std::vector<cudaEvent_t> waits;
   {
     std::lock_guard<std::mutex> lk(mu_);
     for (int i = 0; i < n; i++) {
@@ -510,14 +567,15 @@ int Engine::submit(int lane, const HostJob* jobs, int n, cudaEvent_t consumed) {
       any_intra |= d.n_intra != 0;
       any_lf |= d.lf_enabled != 0;
     }
-    // stream ordering against other users of the rasters
+    // stream ordering against other users of the rasters: most frames of a batch were last touched
+    // by the same earlier batch, i.e. share one event
     for (int i = 0; i < n; i++) {
-      if (int rc = wait_for(frames_[jobs[i].out], lane, s)) return rc;
+      collect_waits(frames_[jobs[i].out], lane, true, waits);
       if (!jobs[i].desc->key_frame)
-        for (int r = 0; r < 3; r++)
-          if (int rc = wait_for(frames_[jobs[i].refs[r]], lane, s, false)) return rc;
+        for (int r = 0; r < 3; r++) collect_waits(frames_[jobs[i].refs[r]], lane, false, waits);
     }
   }
+  for (cudaEvent_t ev : waits) CU(cudaStreamWaitEvent(s, ev, 0));
   CU(cudaMemcpyAsync(st.dev, st.host, hdr_bytes, cudaMemcpyHostToDevice, s));
   const size_t n_mbs = (size_t)g_.mb_cols * g_.mb_rows;
   for (int i = 0; i < n; i++) {
@@ -540,17 +598,18 @@ int Engine::submit(int lane, const HostJob* jobs, int n, cudaEvent_t consumed) {
     return rc;
   {
     std::lock_guard<std::mutex> lk(mu_);
+    cudaEvent_t ev = next_event(lane);  // one record for every raster of the batch
+    if (!ev) return fail(VP8GPU_ERR_CUDA, "event creation failed");
+    CU(cudaEventRecord(ev, s));
     for (int i = 0; i < n; i++) {
-      if (int rc = touch(frames_[jobs[i].out], lane)) return rc;
+      touch(frames_[jobs[i].out], lane, true, ev);
       if (!jobs[i].desc->key_frame)
-        for (int r = 0; r < 3; r++)
-          if (int rc = touch(frames_[jobs[i].refs[r]], lane, false)) return rc;
+        for (int r = 0; r < 3; r++) touch(frames_[jobs[i].refs[r]], lane, false, ev);
+      if (jobs[i].finished) *jobs[i].finished = ev;
     }
   }
   CU(cudaEventRecord(st.done, s));
   st.in_flight = true;
-  for (int i = 0; i < n; i++)
-    if (jobs[i].finished) CU(cudaEventRecord(jobs[i].finished, s));
   return VP8GPU_OK;
 }
 
@@ -658,10 +717,11 @@ int Engine::resident_run(int lane, Resident* r, float* ms) {
   if (ms) CU(cudaEventRecord(r->t1, s));
   {
     std::lock_guard<std::mutex> lk(mu_);
-    for (int id : r->outs)
-      if (int rc = touch(frames_[id], lane)) return rc;
-    for (int id : r->refs)
-      if (int rc = touch(frames_[id], lane)) return rc;
+    cudaEvent_t ev = next_event(lane);
+    if (!ev) return fail(VP8GPU_ERR_CUDA, "event creation failed");
+    CU(cudaEventRecord(ev, s));
+    for (int id : r->refs) touch(frames_[id], lane, false, ev);
+    for (int id : r->outs) touch(frames_[id], lane, true, ev);
   }
   if (ms) {
     CU(cudaEventSynchronize(r->t1));
@@ -707,10 +767,11 @@ int Engine::resident_run_timed(int lane, Resident* r, float ms[3]) {
   CU(cudaEventRecord(r->t1, s));
   {
     std::lock_guard<std::mutex> lk(mu_);
-    for (int id : r->outs)
-      if (int rc = touch(frames_[id], lane)) return rc;
-    for (int id : r->refs)
-      if (int rc = touch(frames_[id], lane)) return rc;
+    cudaEvent_t ev = next_event(lane);
+    if (!ev) return fail(VP8GPU_ERR_CUDA, "event creation failed");
+    CU(cudaEventRecord(ev, s));
+    for (int id : r->refs) touch(frames_[id], lane, false, ev);
+    for (int id : r->outs) touch(frames_[id], lane, true, ev);
   }
   CU(cudaEventSynchronize(r->t1));
   CU(cudaEventElapsedTime(&ms[0], r->t0, mid[0]));

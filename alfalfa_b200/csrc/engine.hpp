@@ -47,7 +47,7 @@ struct HostJob {
   const TokenRing* ring = nullptr;
   int ring_slot = 0;
   cudaEvent_t ready = nullptr;
-  cudaEvent_t finished = nullptr;
+  cudaEvent_t* finished = nullptr;  // out: an event (owned by the engine) that fires after the job's kernels
 };
 
 class Engine {
@@ -68,6 +68,9 @@ class Engine {
   int frame_upload(int id, const uint8_t* y, size_t ys, const uint8_t* u, const uint8_t* v, size_t cs);
   int frame_download(int id, uint8_t* y, size_t ys, uint8_t* u, uint8_t* v, size_t cs);
   int frame_download_display(int id, int lane, uint8_t* dst, size_t dst_size, bool wait);
+  // asynchronous display-rectangle downloads of n rasters on lane's copy stream (one stream wait and
+  // one event for the whole batch); every dst holds width*height*3/2-ish bytes like the call above
+  int frames_download_display(const int* ids, uint8_t* const* dsts, int n, int lane);
   int frame_clear(int id, int lane);  // all-zero raster (initial References)
   int frames_equal(int a, int b, int lane, int* equal);
   int frame_hash(int id, int lane, uint64_t* out);
@@ -77,6 +80,7 @@ class Engine {
   int submit(int lane, const HostJob* jobs, int n, cudaEvent_t consumed);
 
   // device-side token decoding
+  TokenRing token_ring_layout(size_t max_frame_bytes) const;  // offsets and capacities only
   int token_ring_create(int nslots, size_t max_frame_bytes, TokenRing** out);
   void token_ring_free(TokenRing* r);
   // queue on `s` the upload of one frame parsed with defer_tokens (records + partitions)
@@ -115,9 +119,9 @@ class Engine {
     uint8_t* dev = nullptr;
     int refcnt = 0;
     uint64_t pending = 0;                  // stream slots that read it since the last write
-    cudaEvent_t ev[2 * kMaxLanes] = {};    // one per reading slot, lazily created
+    cudaEvent_t ev[2 * kMaxLanes] = {};    // per reading slot: the event recorded after the read (not owned)
     int wslot = -1;                        // slot of the last writer
-    cudaEvent_t wev = nullptr;
+    cudaEvent_t wev = nullptr;             // recorded after the write (not owned)
   };
   struct Staging {
     uint8_t* dev = nullptr;
@@ -127,7 +131,11 @@ class Engine {
     cudaEvent_t done = nullptr;
     bool in_flight = false;
   };
-  int touch(Frame& f, int slot, bool write = true);                     // record "slot used this frame"
+  static constexpr int kEventRing = 64;
+  cudaEvent_t next_event(int slot);  // next event of the slot's ring (caller records it)
+  // note that `slot` used the frame; `shared` = an event of that slot the caller has already recorded
+  int touch(Frame& f, int slot, bool write = true, cudaEvent_t shared = nullptr);
+  void collect_waits(const Frame& f, int slot, bool write, std::vector<cudaEvent_t>& out) const;
   int wait_for(Frame& f, int slot, cudaStream_t s, bool write = true);  // make stream s wait for other users
   int build_and_launch(int lane, const DevJob* d_jobs, int* d_sync, int n, bool any_inter, bool any_intra,
                        bool any_lf, cudaEvent_t* between = nullptr);
@@ -139,6 +147,8 @@ class Engine {
   std::vector<Frame> frames_;
   std::vector<int> free_;
   cudaStream_t lanes_[2 * kMaxLanes] = {};
+  cudaEvent_t ring_[2 * kMaxLanes][kEventRing] = {};
+  int ring_next_[2 * kMaxLanes] = {};
   Staging staging_[kMaxLanes][kStagingDepth];
   int staging_next_[kMaxLanes] = {};
   uint8_t* cmp_scratch_ = nullptr;

@@ -415,7 +415,7 @@ def main():
     R = a.replicas or max(16, threads)  # 2 GOPs per repeat -> at least 2 GOPs per worker
     big = replicate_ivf(data, R)
     n_e2e_frames = len(frames) * R
-    ctx2 = Context(w, h, device=local, max_frames=threads * (10 if a.host_tokens else 30) + 64)
+    ctx2 = Context(w, h, device=local, max_frames=threads * (10 if a.host_tokens else int(os.environ.get("VP8GPU_TOK_SLOTS", 60)) + 6) + 64)
     ctx2.set_device_tokens(not a.host_tokens)
     out_bytes = ctx2.display_bytes * n_e2e_frames
     dst = C.c_void_p()
