@@ -895,6 +895,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     int refs[3] = {-1, -1, -1};
     int slot_state[kTokSlots] = {};
     int next_slot = 0;
+    int launches_done = 0;
     int rc = VP8GPU_OK;
     ivf_worker_kit* kit = acquire_kit();
     if (!kit) rc = e->fail(VP8GPU_ERR_NOMEM, "decode_ivf: token ring allocation failed");
@@ -904,7 +905,12 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
       uint32_t i = gop_start[g];
       while (i < gop_start[g + 1] && rc == VP8GPU_OK) {
         const uint32_t left = gop_start[g + 1] - i;
-        const int n = (int)left < tok_chunk ? (int)left : tok_chunk;
+        // slow start: the first launches of a worker are small so that its pixel work can begin
+        // after one k_tokens latency instead of after a whole chunk's parse time on top of it
+        int want = tok_chunk;
+        if (launches_done < 3 && (2 << launches_done) < want) want = 2 << launches_done;
+        launches_done++;
+        const int n = (int)left < want ? (int)left : want;
         const int first_slot = next_slot;
         int staged = 0;
         for (int c = 0; c < n && rc == VP8GPU_OK; c++) {

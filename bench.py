@@ -230,7 +230,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="medium", choices=list(STREAMS))
-    ap.add_argument("--gop-instances", type=int, default=16, help="GOPs advanced together in the HBM-resident run")
+    ap.add_argument("--gop-instances", type=int, default=64, help="GOPs advanced together in the HBM-resident run")
     ap.add_argument("--replicas", type=int, default=0, help="stream repeats for the end-to-end run (0 = auto)")
     ap.add_argument("--threads", type=int, default=0, help="host workers for the end-to-end run (0 = auto)")
     ap.add_argument("--ref-procs", type=int, default=0, help="reference processes (0 = usable CPUs)")
