@@ -55,6 +55,19 @@ class EncodeHeader(C.Structure):
                 ("optimize_token_probs", C.c_uint8), ("pad", C.c_uint8 * 2)]
 
 
+class EncodeFeatures(C.Structure):
+    _fields_ = [("log2_partitions", C.c_uint8), ("segmentation_enabled", C.c_uint8),
+                ("update_mb_segmentation_map", C.c_uint8), ("update_segment_feature_data", C.c_uint8),
+                ("segment_feature_absolute", C.c_uint8), ("segment_quant", C.c_int8 * 4), ("segment_lf", C.c_int8 * 4),
+                ("segment_tree_probs", C.c_uint8 * 3), ("lf_delta_enabled", C.c_uint8), ("lf_delta_update", C.c_uint8),
+                ("ref_lf_delta", C.c_int8 * 4), ("mode_lf_delta", C.c_int8 * 4), ("y_dc_delta", C.c_int8),
+                ("y2_dc_delta", C.c_int8), ("y2_ac_delta", C.c_int8), ("uv_dc_delta", C.c_int8), ("uv_ac_delta", C.c_int8),
+                ("refresh_golden", C.c_uint8), ("refresh_alternate", C.c_uint8), ("refresh_last", C.c_uint8),
+                ("refresh_entropy_probs", C.c_uint8), ("copy_to_golden", C.c_uint8), ("copy_to_alternate", C.c_uint8),
+                ("sign_bias_golden", C.c_uint8), ("sign_bias_alternate", C.c_uint8), ("pad", C.c_uint8 * 3),
+                ("saved_coef_probs", C.c_void_p)]
+
+
 class Job(C.Structure):
     _fields_ = [("desc", C.POINTER(FrameDesc)), ("mbs", C.c_void_p), ("tokens", C.c_void_p), ("split", C.c_void_p),
                 ("refs", C.c_int32 * 3), ("out", C.c_int32)]
@@ -127,6 +140,8 @@ SYMBOLS = {
                                                          C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
     "vp8gpu_encoder_reconstruction": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
     "vp8gpu_serialize_frame": (C.c_int, [C.POINTER(EncodeHeader), _vp, _vp, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "vp8gpu_serialize_frame_ex": (C.c_int, [C.POINTER(EncodeHeader), C.POINTER(EncodeFeatures), _vp, _vp, _vp, _vp, C.c_size_t,
+                                            C.POINTER(C.c_size_t)]),
     "vp8gpu_decode_ivf_stats": (None, [_vp, C.POINTER(C.c_double)]),
     "vp8gpu_decode_ivf": (C.c_int, [_vp, C.c_char_p, C.c_size_t, C.c_int, _u8p, C.c_size_t, C.POINTER(C.c_uint32),
                                     C.POINTER(C.c_uint32)]),

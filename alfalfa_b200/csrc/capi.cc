@@ -181,8 +181,9 @@ void vp8gpu_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
 uint64_t vp8gpu_launch_count(const vp8gpu_ctx* ctx) { return ctx->engine->launches(); }
-int vp8gpu_serialize_frame(const vp8gpu_encode_header* hdr, const vp8gpu_mb* mbs, const vp8gpu_token* tokens,
-                           const vp8gpu_split_mvs* split, uint8_t* out, size_t cap, size_t* size) {
+int vp8gpu_serialize_frame_ex(const vp8gpu_encode_header* hdr, const vp8gpu_encode_features* ft, const vp8gpu_mb* mbs,
+                              const vp8gpu_token* tokens, const vp8gpu_split_mvs* split, uint8_t* out, size_t cap,
+                              size_t* size) {
   if (!hdr || !mbs || !size) return VP8GPU_ERR_LOGIC;
   vp8::EncodeHeader h;
   h.key_frame = hdr->key_frame;
@@ -193,12 +194,47 @@ int vp8gpu_serialize_frame(const vp8gpu_encode_header* hdr, const vp8gpu_mb* mbs
   h.loop_filter_level = hdr->loop_filter_level;
   h.sharpness = hdr->sharpness;
   h.optimize_token_probs = hdr->optimize_token_probs;
-  const std::vector<uint8_t> bytes = vp8::serialize_frame(h, mbs, tokens, split);
+  vp8::EncodeFeatures x;
+  if (ft) {
+    x.log2_partitions = ft->log2_partitions;
+    x.segmentation_enabled = ft->segmentation_enabled;
+    x.update_mb_segmentation_map = ft->update_mb_segmentation_map;
+    x.update_segment_feature_data = ft->update_segment_feature_data;
+    x.segment_feature_absolute = ft->segment_feature_absolute;
+    for (int i = 0; i < 4; i++) {
+      x.segment_quant[i] = ft->segment_quant[i];
+      x.segment_lf[i] = ft->segment_lf[i];
+      x.ref_lf_delta[i] = ft->ref_lf_delta[i];
+      x.mode_lf_delta[i] = ft->mode_lf_delta[i];
+    }
+    for (int i = 0; i < 3; i++) x.segment_tree_probs[i] = ft->segment_tree_probs[i];
+    x.lf_delta_enabled = ft->lf_delta_enabled;
+    x.lf_delta_update = ft->lf_delta_update;
+    x.y_dc_delta = ft->y_dc_delta;
+    x.y2_dc_delta = ft->y2_dc_delta;
+    x.y2_ac_delta = ft->y2_ac_delta;
+    x.uv_dc_delta = ft->uv_dc_delta;
+    x.uv_ac_delta = ft->uv_ac_delta;
+    x.refresh_golden = ft->refresh_golden;
+    x.refresh_alternate = ft->refresh_alternate;
+    x.refresh_last = ft->refresh_last;
+    x.refresh_entropy_probs = ft->refresh_entropy_probs;
+    x.copy_to_golden = ft->copy_to_golden;
+    x.copy_to_alternate = ft->copy_to_alternate;
+    x.sign_bias_golden = ft->sign_bias_golden;
+    x.sign_bias_alternate = ft->sign_bias_alternate;
+    x.saved_coef_probs = ft->saved_coef_probs;
+  }
+  const std::vector<uint8_t> bytes = vp8::serialize_frame(h, mbs, tokens, split, ft ? &x : nullptr);
   if (bytes.empty()) return VP8GPU_ERR_UNSUPPORTED;
   *size = bytes.size();
   if (!out || cap < bytes.size()) return VP8GPU_ERR_NOMEM;
   memcpy(out, bytes.data(), bytes.size());
   return VP8GPU_OK;
+}
+int vp8gpu_serialize_frame(const vp8gpu_encode_header* hdr, const vp8gpu_mb* mbs, const vp8gpu_token* tokens,
+                           const vp8gpu_split_mvs* split, uint8_t* out, size_t cap, size_t* size) {
+  return vp8gpu_serialize_frame_ex(hdr, nullptr, mbs, tokens, split, out, cap, size);
 }
 void vp8gpu_decode_ivf_stats(const vp8gpu_ctx* ctx, double out[8]) { memcpy(out, ctx->stats, sizeof(ctx->stats)); }
 

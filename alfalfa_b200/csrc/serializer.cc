@@ -130,7 +130,7 @@ struct Mv {
   int x, y;
 };
 struct MbInfo {
-  uint8_t inter = 0, y_mode = 0;
+  uint8_t inter = 0, y_mode = 0, flipped = 0;
   uint8_t bm[16] = {0};
   int16_t mv[16][2] = {{0, 0}};
 };
@@ -142,14 +142,20 @@ inline Mv clamp_mv(Mv m, const Bounds& b) {
   m.y = m.y < b.top ? b.top : (m.y > b.bottom ? b.bottom : m.y);
   return m;
 }
-// Scorer (scorer.hh:35-78); sign bias is never used by this writer (LAST only)
+// Scorer (scorer.hh:35-78 + macroblock.cc:141-171): a neighbour whose reference has the other sign
+// bias contributes its vector negated
 struct Census {
   int score[4] = {0, 0, 0, 0};
   Mv mv[4] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
   int index = 0, split_score = 0;
+  bool flipped = false;
   void add(int weight, const MbInfo* nb) {
     if (!nb || !nb->inter) return;
-    const int x = nb->mv[15][0], y = nb->mv[15][1];
+    int x = nb->mv[15][0], y = nb->mv[15][1];
+    if ((nb->flipped != 0) != flipped) {
+      x = -x;
+      y = -y;
+    }
     if ((x | y) == 0) {
       score[0] += weight;
     } else {
@@ -286,7 +292,11 @@ int record_block(TokenRecorder& t, const int16_t* coefs /* raster order */, int 
 // serialize_frame
 // ------------------------------------------------------------------------------------------
 std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs, const vp8gpu_token* tokens,
-                                     const vp8gpu_split_mvs* split) {
+                                     const vp8gpu_split_mvs* split, const EncodeFeatures* features) {
+  static const EncodeFeatures kPlain;
+  const EncodeFeatures& x = features ? *features : kPlain;
+  if (x.log2_partitions < 0 || x.log2_partitions > 3) return {};
+  const int nparts = 1 << x.log2_partitions;
   const int cols = (h.width + 15) / 16, rows = (h.height + 15) / 16;
   const size_t n_mbs = static_cast<size_t>(cols) * rows;
   std::vector<MbInfo> info(n_mbs);
@@ -297,8 +307,10 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
   std::vector<uint8_t> above_nz(static_cast<size_t>(cols) * 9, 0);
   std::vector<uint8_t> skip(n_mbs, 0);
   size_t n_skipped = 0;
+  std::vector<size_t> row_start(static_cast<size_t>(rows) + 1, 0);
   for (int row = 0; row < rows; row++) {
     uint8_t left_nz[9] = {0};
+    row_start[row] = rec.bits.size();
     for (int col = 0; col < cols; col++) {
       const size_t idx = static_cast<size_t>(row) * cols + col;
       const vp8gpu_mb& mb = mbs[idx];
@@ -332,9 +344,12 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
     }
   }
 
+  row_start[rows] = rec.bits.size();
+
   // ---- frame probabilities ----
   uint8_t coef_probs[1056];
-  memcpy(coef_probs, k_coef_default_probs, sizeof(coef_probs));
+  if (x.saved_coef_probs && h.key_frame) memcpy(x.saved_coef_probs, k_coef_default_probs, 1056);
+  memcpy(coef_probs, x.saved_coef_probs ? x.saved_coef_probs : k_coef_default_probs, sizeof(coef_probs));
   std::vector<uint8_t> updated(1056, 0);
   if (h.optimize_token_probs) {
     std::vector<uint32_t> cnt(2 * 1056, 0);
@@ -359,6 +374,25 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
   for (size_t i = 0; i < n_mbs; i++) n_inter += mbs[i].ref_frame != VP8GPU_REF_CURRENT;
   int prob_inter = static_cast<int>(((n_mbs - n_inter) * 256 + n_mbs / 2) / n_mbs);  // P(intra) = P(bit 0)
   prob_inter = prob_inter < 1 ? 1 : (prob_inter > 255 ? 255 : prob_inter);
+  size_t n_last = 0, n_golden = 0;
+  for (size_t i = 0; i < n_mbs; i++) {
+    n_last += mbs[i].ref_frame == VP8GPU_REF_LAST;
+    n_golden += mbs[i].ref_frame == VP8GPU_REF_GOLDEN;
+  }
+  auto prob_of = [](size_t zeros, size_t total) {  // P(bit 0) scaled to 1..255
+    if (!total) return 128;
+    const int p = static_cast<int>((zeros * 256 + total / 2) / total);
+    return p < 1 ? 1 : (p > 255 ? 255 : p);
+  };
+  const int prob_last = features ? prob_of(n_last, n_inter) : 255;
+  const int prob_golden = features ? prob_of(n_golden, n_inter - n_last) : 128;
+  auto put_flagged_signed = [](BoolWriter& w, int v, int width) {  // frame_header.hh Flagged<Signed<width>>
+    w.put(v != 0);
+    if (v) {
+      w.literal(abs(v), width);
+      w.put(v < 0);
+    }
+  };
 
   // ---- first partition: frame header ----
   BoolWriter bw;
@@ -366,29 +400,57 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
     bw.put(0);  // color_space
     bw.put(0);  // clamping_type
   }
-  bw.put(0);  // segmentation_enabled
+  bw.put(x.segmentation_enabled);
+  if (x.segmentation_enabled) {  // frame_header.hh:37-66
+    bw.put(x.update_mb_segmentation_map);
+    bw.put(x.update_segment_feature_data);
+    if (x.update_segment_feature_data) {
+      bw.put(x.segment_feature_absolute);
+      for (int i = 0; i < 4; i++) put_flagged_signed(bw, x.segment_quant[i], 7);
+      for (int i = 0; i < 4; i++) put_flagged_signed(bw, x.segment_lf[i], 6);
+    }
+    if (x.update_mb_segmentation_map)
+      for (int i = 0; i < 3; i++) {
+        bw.put(x.segment_tree_probs[i] != 255);
+        if (x.segment_tree_probs[i] != 255) bw.literal(x.segment_tree_probs[i], 8);
+      }
+  }
   bw.put(0);  // filter_type: normal
   bw.literal(h.loop_filter_level, 6);
   bw.literal(h.sharpness, 3);
-  bw.put(0);  // mode_ref_lf_delta_enabled
-  bw.literal(0, 2);  // one DCT partition
+  bw.put(x.lf_delta_enabled);
+  if (x.lf_delta_enabled) {  // frame_header.hh:70-84
+    bw.put(x.lf_delta_update);
+    if (x.lf_delta_update) {
+      for (int i = 0; i < 4; i++) put_flagged_signed(bw, x.ref_lf_delta[i], 6);
+      for (int i = 0; i < 4; i++) put_flagged_signed(bw, x.mode_lf_delta[i], 6);
+    }
+  }
+  bw.literal(x.log2_partitions, 2);
   bw.literal(h.y_ac_qi, 7);
-  for (int i = 0; i < 5; i++) bw.put(0);  // no quantizer deltas
-  // refresh_entropy_probs = 0: probability updates are valid for this frame only, so the writer
-  // needs no memory of earlier frames (every frame is coded relative to the default tables)
-  const int refresh_entropy = h.optimize_token_probs ? 0 : 1;
+  put_flagged_signed(bw, x.y_dc_delta, 4);
+  put_flagged_signed(bw, x.y2_dc_delta, 4);
+  put_flagged_signed(bw, x.y2_ac_delta, 4);
+  put_flagged_signed(bw, x.uv_dc_delta, 4);
+  put_flagged_signed(bw, x.uv_ac_delta, 4);
+  // Without a saved table (stateless writer) refresh_entropy_probs = 0 whenever probabilities are
+  // updated: the updates are then valid for this frame only and every frame is coded relative to
+  // the default tables.
+  const int refresh_entropy =
+      x.saved_coef_probs ? x.refresh_entropy_probs : (features ? 0 : (h.optimize_token_probs ? 0 : 1));
   if (h.key_frame) {
     bw.put(refresh_entropy);
   } else {
-    bw.put(0);  // refresh_golden_frame
-    bw.put(0);  // refresh_alternate_frame
-    bw.literal(0, 2);  // copy_buffer_to_golden: none
-    bw.literal(0, 2);  // copy_buffer_to_alternate: none
-    bw.put(0);  // sign_bias_golden
-    bw.put(0);  // sign_bias_alternate
+    bw.put(x.refresh_golden);
+    bw.put(x.refresh_alternate);
+    if (!x.refresh_golden) bw.literal(x.copy_to_golden, 2);
+    if (!x.refresh_alternate) bw.literal(x.copy_to_alternate, 2);
+    bw.put(x.sign_bias_golden);
+    bw.put(x.sign_bias_alternate);
     bw.put(refresh_entropy);
-    bw.put(1);  // refresh_last
+    bw.put(features ? x.refresh_last : 1);
   }
+  if (x.saved_coef_probs && refresh_entropy) memcpy(x.saved_coef_probs, coef_probs, 1056);
   for (int i = 0; i < 1056; i++) {
     bw.put(updated[i], k_coef_update_probs[i]);
     if (updated[i]) bw.literal(coef_probs[i], 8);
@@ -397,8 +459,8 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
   bw.literal(skip_prob, 8);
   if (!h.key_frame) {
     bw.literal(prob_inter, 8);
-    bw.literal(255, 8);  // prob_references_last: always LAST
-    bw.literal(128, 8);  // prob_references_golden
+    bw.literal(prob_last, 8);
+    bw.literal(prob_golden, 8);
     bw.put(0);           // intra_16x16_prob unchanged
     bw.put(0);           // intra_chroma_prob unchanged
     for (int i = 0; i < 38; i++) bw.put(0, k_mv_update_probs[i]);  // motion vector probabilities unchanged
@@ -414,6 +476,14 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
       const MbInfo* above = row > 0 ? &info[idx - cols] : nullptr;
       const MbInfo* left = col > 0 ? &info[idx - 1] : nullptr;
       const MbInfo* above_left = (row > 0 && col > 0) ? &info[idx - cols - 1] : nullptr;
+      if (x.segmentation_enabled && x.update_mb_segmentation_map) {
+        // segment tree {2, 4, -0, -1, -2, -3} (modemv_data.cc): the first decision picks the pair
+        const uint8_t sp[3] = {static_cast<uint8_t>(x.segment_tree_probs[0]), static_cast<uint8_t>(x.segment_tree_probs[1]),
+                               static_cast<uint8_t>(x.segment_tree_probs[2])};
+        if (mb.segment_id > 3) return {};
+        bw.put(mb.segment_id >> 1, sp[0]);
+        bw.put(mb.segment_id & 1, sp[1 + (mb.segment_id >> 1)]);
+      }
       bw.put(skip[idx], skip_prob);
       me.y_mode = mb.y_mode;
       if (mb.ref_frame == VP8GPU_REF_CURRENT) {
@@ -440,11 +510,15 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
         }
         continue;
       }
-      if (h.key_frame || mb.ref_frame != VP8GPU_REF_LAST) return {};
+      if (h.key_frame || mb.ref_frame > VP8GPU_REF_ALTREF || (!features && mb.ref_frame != VP8GPU_REF_LAST)) return {};
       me.inter = 1;
+      me.flipped = (mb.ref_frame == VP8GPU_REF_GOLDEN && x.sign_bias_golden) ||
+                   (mb.ref_frame == VP8GPU_REF_ALTREF && x.sign_bias_alternate);
       bw.put(1, prob_inter);
-      bw.put(0, 255);  // reference = LAST
+      bw.put(mb.ref_frame != VP8GPU_REF_LAST, prob_last);
+      if (mb.ref_frame != VP8GPU_REF_LAST) bw.put(mb.ref_frame == VP8GPU_REF_ALTREF, prob_golden);
       Census census;
+      census.flipped = me.flipped != 0;
       census.add(2, above);
       census.add(2, left);
       census.add(1, above_left);
@@ -537,10 +611,17 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
   }
   const std::vector<uint8_t> first = bw.finish();
 
-  // ---- token partition ----
-  BoolWriter tw;
-  for (const TokenBit& b : rec.bits) tw.put(b.bit, b.slot == 0xFFFF ? b.fixed : coef_probs[b.slot]);
-  const std::vector<uint8_t> second = tw.finish();
+  // ---- token partitions: row r goes to partition r % n (frame.cc:131-136) ----
+  std::vector<std::vector<uint8_t>> parts(nparts);
+  for (int p = 0; p < nparts; p++) {
+    BoolWriter tw;
+    for (int row = p; row < rows; row += nparts)
+      for (size_t k = row_start[row]; k < row_start[row + 1]; k++) {
+        const TokenBit& b = rec.bits[k];
+        tw.put(b.bit, b.slot == 0xFFFF ? b.fixed : coef_probs[b.slot]);
+      }
+    parts[p] = tw.finish();
+  }
 
   // ---- frame tag (uncompressed_chunk.cc:49-77 inverted) ----
   std::vector<uint8_t> out;
@@ -559,7 +640,12 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
     out.push_back((h.height >> 8) & 0x3F);
   }
   out.insert(out.end(), first.begin(), first.end());
-  out.insert(out.end(), second.begin(), second.end());
+  for (int p = 0; p + 1 < nparts; p++) {  // partition sizes, all but the last (uncompressed_chunk.cc:132-155)
+    out.push_back(parts[p].size() & 0xFF);
+    out.push_back((parts[p].size() >> 8) & 0xFF);
+    out.push_back((parts[p].size() >> 16) & 0xFF);
+  }
+  for (int p = 0; p < nparts; p++) out.insert(out.end(), parts[p].begin(), parts[p].end());
   return out;
 }
 

@@ -7,8 +7,12 @@
 // with the same context modelling the decoder uses (mode contexts from the MV census, B_PRED
 // contexts, token contexts), one DCT partition.  It stays on the CPU.
 //
-// Subset written: no segmentation, no loop-filter deltas, one token partition, LAST reference
-// only, default probabilities with optional per-frame token-probability updates.
+// Written by the encoder path: no segmentation, no loop-filter deltas, one token partition, LAST
+// reference only, default probabilities with optional per-frame token-probability updates.  With an
+// EncodeFeatures block the writer also covers the rest of the format (segmentation, loop-filter deltas,
+// quantiser deltas, 1-8 token partitions, golden / altref references with sign bias, reference
+// refresh / copy flags, persistent probabilities) -- used to synthesise feature-complete test streams
+// (bitstream B); the truth for those is the reference decoder.
 #pragma once
 #include <stdint.h>
 
@@ -25,6 +29,25 @@ struct EncodeHeader {
   int loop_filter_level = 0;  // 0..63
   int sharpness = 0;          // 0..7
   bool optimize_token_probs = false;  // per-frame coefficient probability updates (encoder.cc:419-440)
+};
+
+// frame_header.hh:37-131, 213-325: everything the plain header leaves at its default
+struct EncodeFeatures {
+  int log2_partitions = 0;  // 0..3
+  bool segmentation_enabled = false, update_mb_segmentation_map = false, update_segment_feature_data = false;
+  bool segment_feature_absolute = false;
+  int segment_quant[4] = {0, 0, 0, 0}, segment_lf[4] = {0, 0, 0, 0};
+  int segment_tree_probs[3] = {255, 255, 255};  // 255 = not sent
+  bool lf_delta_enabled = false, lf_delta_update = false;
+  int ref_lf_delta[4] = {0, 0, 0, 0}, mode_lf_delta[4] = {0, 0, 0, 0};
+  int y_dc_delta = 0, y2_dc_delta = 0, y2_ac_delta = 0, uv_dc_delta = 0, uv_ac_delta = 0;  // -15..15
+  bool refresh_golden = false, refresh_alternate = false, refresh_last = true, refresh_entropy_probs = false;
+  int copy_to_golden = 0, copy_to_alternate = 0;  // 0 none, 1 last, 2 the other one
+  bool sign_bias_golden = false, sign_bias_alternate = false;
+  // the stream's saved coefficient probabilities (DecoderState): read as the base of this frame's
+  // updates and written back when refresh_entropy_probs is set (key frames reset it to the defaults
+  // first); nullptr = stateless writer, every frame relative to the default tables
+  uint8_t* saved_coef_probs = nullptr;
 };
 
 // RFC 6386 section 7 arithmetic encoder (same code stream as encoder/bool_encoder.hh)
@@ -47,6 +70,6 @@ class BoolWriter {
 // Returns the compressed frame, or an empty vector if a record cannot be represented
 // (e.g. a reference other than LAST, a motion vector out of range).
 std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs, const vp8gpu_token* tokens,
-                                     const vp8gpu_split_mvs* split);
+                                     const vp8gpu_split_mvs* split, const EncodeFeatures* features = nullptr);
 
 }  // namespace vp8

@@ -304,6 +304,31 @@ typedef struct vp8gpu_encode_header {
 int vp8gpu_serialize_frame(const vp8gpu_encode_header* hdr, const vp8gpu_mb* mbs, const vp8gpu_token* tokens,
                            const vp8gpu_split_mvs* split, uint8_t* out, size_t cap, size_t* size);
 
+/* The rest of the frame header (frame_header.hh:37-131, 213-325) for vp8gpu_serialize_frame_ex: with it
+ * the writer covers the whole format -- segmentation (records' segment_id), loop-filter deltas,
+ * quantiser deltas, 1..8 DCT partitions, LAST / GOLDEN / ALTREF references with sign bias (records'
+ * ref_frame), reference refresh / copy flags, persistent coefficient probabilities.  Used to synthesise
+ * feature-complete test streams (tools/make_feature_stream.py); what they decode to is defined by the
+ * reference decoder. */
+typedef struct vp8gpu_encode_features {
+  uint8_t log2_partitions;                 /* 0..3 */
+  uint8_t segmentation_enabled, update_mb_segmentation_map, update_segment_feature_data, segment_feature_absolute;
+  int8_t  segment_quant[4], segment_lf[4];
+  uint8_t segment_tree_probs[3];           /* 255 = not sent */
+  uint8_t lf_delta_enabled, lf_delta_update;
+  int8_t  ref_lf_delta[4], mode_lf_delta[4];
+  int8_t  y_dc_delta, y2_dc_delta, y2_ac_delta, uv_dc_delta, uv_ac_delta; /* -15..15 */
+  uint8_t refresh_golden, refresh_alternate, refresh_last, refresh_entropy_probs;
+  uint8_t copy_to_golden, copy_to_alternate;   /* 0 none, 1 last frame, 2 the other buffer */
+  uint8_t sign_bias_golden, sign_bias_alternate;
+  uint8_t pad[3];
+  uint8_t* saved_coef_probs;  /* 1056 bytes of stream state (DecoderState's coefficient probabilities),
+                                 read and, with refresh_entropy_probs, updated; NULL = stateless */
+} vp8gpu_encode_features;
+int vp8gpu_serialize_frame_ex(const vp8gpu_encode_header* hdr, const vp8gpu_encode_features* features,
+                              const vp8gpu_mb* mbs, const vp8gpu_token* tokens, const vp8gpu_split_mvs* split,
+                              uint8_t* out, size_t cap, size_t* size);
+
 /* ---- Encoder (encoder/encoder.hh:345-382), first slice ----
  * Explicit state: the encoder owns its LAST reference (the reconstruction of the previous frame);
  * the first frame is a key frame, later frames are inter frames (encoder.cc:559-590).  Source planes

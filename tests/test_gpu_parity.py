@@ -157,10 +157,11 @@ def test_errors_mirror_reference_exception_classes():
 
 @pytest.mark.parametrize("device_tokens", [False, True])
 @pytest.mark.parametrize("name,threads", [("synth1080p_medium_q90.ivf", 8), ("synth1080p_easy_q40.ivf", 3),
-                                          ("synth4k_medium_q90_8f.ivf", 2)])
+                                          ("synth4k_medium_q90_8f.ivf", 2), ("features1080p_12f.ivf", 1)])
 def test_full_size_clips_match_reference_decode(name, threads, device_tokens):
-    """BASELINE.json sizes (1080p bench workload, 4K): GPU decode through vp8gpu_decode_ivf vs the
-    SHA-1 of the unmodified reference's decode of the same clip (tests/golden/bench_clips.json)."""
+    """BASELINE.json sizes (1080p bench workload, 4K, and the feature-complete 1080p stream of
+    tools/make_feature_stream.py): GPU decode through vp8gpu_decode_ivf vs the SHA-1 of the unmodified
+    reference's decode of the same clip (tests/golden/bench_clips.json)."""
     import json
     from alfalfa_b200 import Context, decode_ivf
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -13,6 +13,9 @@ oracle/_ref/ref_encode bench_data/synth1080p_easy_q40.ivf 1920 1080 60 30 40 123
 ls -la bench_data
 # short 4K clip (BASELINE.json config 4 parity case) and the reference's own answers for all clips
 oracle/_ref/ref_encode bench_data/synth4k_medium_q90_8f.ivf 3840 2160 8 4 90 77 2 2>/dev/null
+# feature-complete 1080p stream (SURVEY.md 8d bitstream B): written by the product's bitstream writer from
+# seeded-random records; needs alfalfa_b200/libvp8gpu.so (host code only)
+python tools/make_feature_stream.py bench_data/features1080p_12f.ivf 1920 1080 12 2024
 python - <<'PY'
 import hashlib, json, subprocess, os
 out = {}
