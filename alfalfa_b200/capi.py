@@ -112,6 +112,11 @@ SYMBOLS = {
     "vp8gpu_state_destroy": (None, [_vp]),
     "vp8gpu_state_equal": (C.c_int, [_vp, _vp]),
     "vp8gpu_state_hash": (C.c_uint64, [_vp]),
+    "vp8gpu_state_serialize": (C.c_size_t, [_vp, _u8p, C.c_size_t]),
+    "vp8gpu_state_deserialize": (C.c_int, [C.c_char_p, C.c_size_t, _pp]),
+    "vp8gpu_frame_bytes": (C.c_size_t, [_vp]),
+    "vp8gpu_frame_export": (C.c_int, [_vp, C.c_int32, _vp, C.c_size_t]),
+    "vp8gpu_frame_import": (C.c_int, [_vp, C.c_int32, _vp, C.c_size_t]),
     "vp8gpu_parsed_create": (C.c_int, [_pp]),
     "vp8gpu_parsed_destroy": (None, [_vp]),
     "vp8gpu_parsed_desc": (C.POINTER(FrameDesc), [_vp]),

@@ -173,6 +173,13 @@ int vp8gpu_frame_download_display_async(vp8gpu_ctx* ctx, vp8gpu_frame_id id, uin
   return ctx->engine->frame_download_display(id, 0, dst, dst_size, false);
 }
 int vp8gpu_frame_hash(vp8gpu_ctx* ctx, vp8gpu_frame_id id, uint64_t* out) { return ctx->engine->frame_hash(id, 0, out); }
+size_t vp8gpu_frame_bytes(const vp8gpu_ctx* ctx) { return ctx->engine->geom().frame_bytes; }
+int vp8gpu_frame_export(vp8gpu_ctx* ctx, vp8gpu_frame_id id, void* dst, size_t bytes) {
+  return ctx->engine->frame_copy_raw(id, dst, bytes, false);
+}
+int vp8gpu_frame_import(vp8gpu_ctx* ctx, vp8gpu_frame_id id, const void* src, size_t bytes) {
+  return ctx->engine->frame_copy_raw(id, const_cast<void*>(src), bytes, true);
+}
 int vp8gpu_ctx_sync(vp8gpu_ctx* ctx) { return ctx->engine->sync_all(); }
 int vp8gpu_host_alloc(void** out, size_t bytes) {
   return cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess ? VP8GPU_OK : VP8GPU_ERR_NOMEM;
@@ -327,6 +334,19 @@ int vp8gpu_state_clone(const vp8gpu_state* s, vp8gpu_state** out) {
 void vp8gpu_state_destroy(vp8gpu_state* s) { delete s; }
 int vp8gpu_state_equal(const vp8gpu_state* a, const vp8gpu_state* b) { return a && b && a->s == b->s; }
 uint64_t vp8gpu_state_hash(const vp8gpu_state* s) { return s->s.hash(); }
+size_t vp8gpu_state_serialize(const vp8gpu_state* s, uint8_t* out, size_t cap) {
+  if (!s) return 0;
+  const std::vector<uint8_t> b = s->s.serialize();
+  if (out && cap >= b.size()) memcpy(out, b.data(), b.size());
+  return b.size();
+}
+int vp8gpu_state_deserialize(const uint8_t* data, size_t len, vp8gpu_state** out) {
+  if (!data || !out) return VP8GPU_ERR_LOGIC;
+  State st(16, 16);
+  if (!State::deserialize(data, len, st)) return VP8GPU_ERR_INVALID;
+  *out = new vp8gpu_state(st);
+  return VP8GPU_OK;
+}
 
 int vp8gpu_parsed_create(vp8gpu_parsed** out) {
   if (!out) return VP8GPU_ERR_LOGIC;

@@ -199,6 +199,23 @@ int Engine::frame_clear(int id, int lane) {
   return touch(f, lane);
 }
 
+int Engine::frame_copy_raw(int id, void* buf, size_t bytes, bool into_frame) {
+  if (int rc = ensure_lane(0)) return rc;
+  if (!buf || bytes != g_.frame_bytes) return fail(VP8GPU_ERR_LOGIC, "frame_copy_raw: size must be vp8gpu_frame_bytes");
+  cudaStream_t s = lanes_[0];
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (id < 0 || id >= (int)frames_.size() || frames_[id].refcnt <= 0) return fail(VP8GPU_ERR_LOGIC, "frame_copy_raw: bad frame id");
+    Frame& f = frames_[id];
+    if (int rc = wait_for(f, 0, s, into_frame)) return rc;
+    if (into_frame) CU(cudaMemcpyAsync(f.dev, buf, bytes, cudaMemcpyDefault, s));
+    else CU(cudaMemcpyAsync(buf, f.dev, bytes, cudaMemcpyDefault, s));
+    if (int rc = touch(f, 0, into_frame)) return rc;
+  }
+  CU(cudaStreamSynchronize(s));
+  return VP8GPU_OK;
+}
+
 int Engine::frame_upload(int id, const uint8_t* y, size_t ys, const uint8_t* u, const uint8_t* v, size_t cs) {
   if (int rc = ensure_lane(0)) return rc;
   std::lock_guard<std::mutex> lk(mu_);

@@ -72,6 +72,8 @@ class Engine {
   // one event for the whole batch); every dst holds width*height*3/2-ish bytes like the call above
   int frames_download_display(const int* ids, uint8_t* const* dsts, int n, int lane);
   int frame_clear(int id, int lane);  // all-zero raster (initial References)
+  // whole raster <-> a host or device buffer of geom().frame_bytes bytes (synchronous)
+  int frame_copy_raw(int id, void* buf, size_t bytes, bool into_frame);
   int frames_equal(int a, int b, int lane, int* equal);
   int frame_hash(int id, int lane, uint64_t* out);
 

@@ -93,6 +93,60 @@ uint64_t State::hash() const {
   return h;
 }
 
+std::vector<uint8_t> State::serialize() const {
+  std::vector<uint8_t> b;
+  auto put = [&b](const void* p, size_t n) {
+    const uint8_t* q = static_cast<const uint8_t*>(p);
+    b.insert(b.end(), q, q + n);
+  };
+  const uint8_t head[12] = {'V', '8', 'S', 1, static_cast<uint8_t>(width & 0xFF), static_cast<uint8_t>(width >> 8),
+                            static_cast<uint8_t>(height & 0xFF), static_cast<uint8_t>(height >> 8), seg_enabled, seg_abs,
+                            lf_adj_enabled, 0};
+  put(head, sizeof(head));
+  put(coef_probs, sizeof(coef_probs));
+  put(ymode_probs, 4);
+  put(uvmode_probs, 3);
+  put(mv_probs, sizeof(mv_probs));
+  put(seg_quant, 4);
+  put(seg_lf, 4);
+  put(ref_adj, 4);
+  put(mode_adj, 4);
+  if (seg_enabled) put(seg_map.data(), seg_map.size());
+  return b;
+}
+
+bool State::deserialize(const uint8_t* d, size_t len, State& out) {
+  const size_t fixed = 12 + 1056 + 4 + 3 + 38 + 16;
+  if (len < fixed || d[0] != 'V' || d[1] != '8' || d[2] != 'S' || d[3] != 1) return false;
+  const int w = d[4] | (d[5] << 8), h = d[6] | (d[7] << 8);
+  if (w <= 0 || h <= 0) return false;
+  State s(w, h);
+  s.seg_enabled = d[8];
+  s.seg_abs = d[9];
+  s.lf_adj_enabled = d[10];
+  const uint8_t* p = d + 12;
+  auto get = [&p](void* to, size_t n) {
+    memcpy(to, p, n);
+    p += n;
+  };
+  get(s.coef_probs, sizeof(s.coef_probs));
+  get(s.ymode_probs, 4);
+  get(s.uvmode_probs, 3);
+  get(s.mv_probs, sizeof(s.mv_probs));
+  get(s.seg_quant, 4);
+  get(s.seg_lf, 4);
+  get(s.ref_adj, 4);
+  get(s.mode_adj, 4);
+  if (s.seg_enabled) {
+    if (len != fixed + s.seg_map.size()) return false;
+    get(s.seg_map.data(), s.seg_map.size());
+  } else if (len != fixed) {
+    return false;
+  }
+  out = s;
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------
 // arithmetic decoder.  Same code as bool_decoder.hh:82-107 produces, implemented with a
 // 64-bit look-ahead window so the renormalisation is one shift and bytes are fetched eight

@@ -36,6 +36,10 @@ struct State {
   void reset_probs();
   bool operator==(const State& o) const;  // DecoderState::operator==, decoder.cc:257-264
   uint64_t hash() const;
+  // DecoderState::serialize / deserialize (decoder.cc:266-330) as a flat little-endian blob
+  // (own layout, versioned; carries exactly the fields operator== compares)
+  std::vector<uint8_t> serialize() const;
+  static bool deserialize(const uint8_t* data, size_t len, State& out);
 };
 
 // Growable array whose storage comes from a pluggable allocator, so that the engine can

@@ -50,6 +50,10 @@ class Context:
     def sync(self):
         check(self.L.vp8gpu_ctx_sync(self.h), self.h, "sync")
 
+    @property
+    def frame_bytes(self):
+        return int(self.L.vp8gpu_frame_bytes(self.h))
+
     def set_device_tokens(self, on):
         """VP8GPU_OPT_DEVICE_TOKENS: decode_ivf decodes the DCT partitions on the device (default on)"""
         check(self.L.vp8gpu_ctx_set_option(self.h, capi.OPT_DEVICE_TOKENS, int(bool(on))), self.h, "set_option")
@@ -90,6 +94,13 @@ class RasterHandle:
         check(c.L.vp8gpu_frame_download(c.h, self.id, y.ctypes.data, W, u.ctypes.data, v.ctypes.data, W // 2), c.h,
               "frame_download")
         return y, u, v
+
+    def export_to(self, ptr, nbytes):
+        """whole raster (ctx.frame_bytes, pitched planes) into a host or same-device buffer"""
+        check(self.ctx.L.vp8gpu_frame_export(self.ctx.h, self.id, ptr, nbytes), self.ctx.h, "frame_export")
+
+    def import_from(self, ptr, nbytes):
+        check(self.ctx.L.vp8gpu_frame_import(self.ctx.h, self.id, ptr, nbytes), self.ctx.h, "frame_import")
 
     def upload(self, y, u, v):
         c = self.ctx
@@ -134,6 +145,19 @@ class DecoderState:
 
     def hash(self):
         return int(self.L.vp8gpu_state_hash(self.h))
+
+    def serialize(self):
+        """DecoderState::serialize: a flat blob (vp8gpu_state_serialize)"""
+        n = self.L.vp8gpu_state_serialize(self.h, None, 0)
+        buf = (C.c_uint8 * n)()
+        assert self.L.vp8gpu_state_serialize(self.h, buf, n) == n
+        return bytes(buf)
+
+    @staticmethod
+    def deserialize(blob):
+        h = C.c_void_p()
+        check(capi.lib().vp8gpu_state_deserialize(blob, len(blob), C.byref(h)), None, "state_deserialize")
+        return DecoderState(_h=h)
 
     def __del__(self):
         try:
@@ -190,6 +214,14 @@ class Decoder:
                 self.L.vp8gpu_decoder_destroy(self.h)
         except Exception:
             pass
+
+    @staticmethod
+    def from_state(ctx, state, refs):
+        """Decoder(DecoderState, References) (decoder.hh:254); refs = (last, golden, alternative) RasterHandles"""
+        ids = (C.c_int32 * 3)(*[r.id for r in refs])
+        h = C.c_void_p()
+        check(ctx.L.vp8gpu_decoder_create_from(ctx.h, state.h, ids, C.byref(h)), ctx.h, "decoder_create_from")
+        return Decoder(ctx, h)
 
     def copy(self):
         """copy construction: O(1) in pixels, shares the reference rasters"""

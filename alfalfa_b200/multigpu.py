@@ -1,8 +1,9 @@
 """Multi-GPU plumbing: the decode path shards at GOP / stream granularity -- a key
 frame resets all codec state (decoder_state.hh:90) -- so every rank decodes its own GOPs on its own
-GPU and there is NO data-path collective.  torch.distributed is used only for the barrier around
-the timed region and for reducing the timing / work counters (NCCL on the GPU box, gloo in the CPU
-tests)."""
+GPU and GOP-aligned shards need NO data-path collective: torch.distributed is used for the barrier
+around the timed region and for reducing the timing / work counters (NCCL on the GPU box, gloo in the
+CPU tests).  The one real exchange step of the path -- a GOP that continues on another GPU needs the
+DecoderState and the reference rasters -- is broadcast_decoder() at the end of this file."""
 import os
 import struct
 
@@ -92,3 +93,80 @@ def shard_ivf(ivf, rank, world):
     h = bytearray(hdr)
     struct.pack_into("<I", h, 24, len(recs))
     return bytes(h) + b"".join(recs), mine
+
+
+# ------------------------------------------------------------------------------------------------
+# A GOP that continues on another GPU (BASELINE.json config 4: "NCCL golden/altref broadcast over
+# NVLink"): frames inside a GOP depend on the three reference rasters and the DecoderState, so the
+# rank that decoded the first part broadcasts them -- the state as a byte blob, every DISTINCT
+# reference raster once (after a key frame all three are one raster) as a uint8 tensor on the
+# device (NCCL) or the host (gloo).  One exchange step per boundary; GOP-aligned shards need none.
+# ------------------------------------------------------------------------------------------------
+def reference_plan(ids):
+    """(unique ids in first-seen order, index of each of the 3 references into that list)"""
+    uniq = []
+    for i in ids:
+        if i not in uniq:
+            uniq.append(i)
+    return uniq, [uniq.index(i) for i in ids]
+
+
+def broadcast_bytes(dist, local, blob, src):
+    """every rank returns src's bytes"""
+    import torch
+    dev = _device(dist, local)
+    n = torch.tensor([len(blob) if blob is not None else 0], dtype=torch.int64, device=dev)
+    dist.broadcast(n, src)
+    buf = torch.empty(int(n.item()), dtype=torch.uint8, device=dev)
+    if dist.get_rank() == src:
+        buf.copy_(torch.frombuffer(bytearray(blob), dtype=torch.uint8))
+    dist.broadcast(buf, src)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+def _device(dist, local):
+    import torch
+    return torch.device("cuda", local) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def broadcast_decoder(ctx, decoder, src, dist, local, make_decoder=None):
+    """Decoder (state + references) of rank `src` on every rank.  `decoder` is ignored elsewhere.
+    Returns src's own decoder on src, a new Decoder on the other ranks (make_decoder(ctx, state_blob,
+    (last, golden, alternative) rasters) builds it; default: Decoder.from_state)."""
+    import torch
+    rank = dist.get_rank()
+    dev = _device(dist, local)
+    refs, head = None, None
+    if rank == src:
+        refs = decoder.get_references()
+        uniq, index = reference_plan([r.id for r in refs])
+        by_id = {r.id: r for r in refs}
+        head = struct.pack("<4B", len(uniq), *index) + decoder.get_state().serialize()
+    head = broadcast_bytes(dist, local, head, src)
+    n_uniq, index = head[0], list(head[1:4])
+    nbytes = ctx.frame_bytes
+    rasters = []
+    for k in range(n_uniq):
+        t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        if rank == src:
+            by_id[uniq[k]].export_to(t.data_ptr(), nbytes)   # synchronous: the tensor is complete
+        dist.broadcast(t, src)
+        if rank != src:
+            if dev.type == "cuda":
+                torch.cuda.synchronize(dev)   # the broadcast ran on torch's stream
+            fr = ctx.alloc_frame()
+            fr.import_from(t.data_ptr(), nbytes)
+            rasters.append(fr)
+    if rank == src:
+        for r in refs:
+            r.release()
+        return decoder
+    if make_decoder is None:
+        from .decoder import Decoder, DecoderState
+
+        def make_decoder(c, blob, three):
+            return Decoder.from_state(c, DecoderState.deserialize(blob), three)
+    out = make_decoder(ctx, head[4:], tuple(rasters[i] for i in index))
+    for fr in rasters:
+        fr.release()
+    return out

@@ -157,6 +157,13 @@ int vp8gpu_frame_download_display_async(vp8gpu_ctx* ctx, vp8gpu_frame_id id, uin
 /* RasterHandle::hash() (raster_handle.hh:60-75): 64-bit content hash of the MB-aligned pixels,
  * computed on the device (our own function, not boost::hash_range). Blocks until decoded. */
 int vp8gpu_frame_hash(vp8gpu_ctx* ctx, vp8gpu_frame_id id, uint64_t* out);
+/* The whole raster (macroblock-aligned planes in the context's pitched layout, vp8gpu_frame_bytes bytes)
+ * to / from a buffer that may live on the host or on this device (e.g. a tensor about to be
+ * broadcast over NCCL): how reference rasters (References, decoder.hh:123-141) travel between GPUs.
+ * Synchronous. */
+size_t vp8gpu_frame_bytes(const vp8gpu_ctx* ctx);
+int vp8gpu_frame_export(vp8gpu_ctx* ctx, vp8gpu_frame_id id, void* dst, size_t bytes);
+int vp8gpu_frame_import(vp8gpu_ctx* ctx, vp8gpu_frame_id id, const void* src, size_t bytes);
 int vp8gpu_ctx_sync(vp8gpu_ctx* ctx);
 int vp8gpu_host_alloc(void** out, size_t bytes); /* pinned host memory */
 void vp8gpu_host_free(void* p);
@@ -217,6 +224,12 @@ int vp8gpu_state_clone(const vp8gpu_state* s, vp8gpu_state** out);
 void vp8gpu_state_destroy(vp8gpu_state* s);
 int vp8gpu_state_equal(const vp8gpu_state* a, const vp8gpu_state* b);
 uint64_t vp8gpu_state_hash(const vp8gpu_state* s);
+/* DecoderState::serialize / deserialize (decoder.cc:266-330): the state as a flat blob (own versioned
+ * layout; the fields operator== compares).  serialize returns the size needed and writes only if
+ * cap suffices.  Together with vp8gpu_frame_export / _import this moves a Decoder between processes
+ * or GPUs (alfalfa_b200/multigpu.py broadcast_decoder: NCCL broadcast of the reference rasters). */
+size_t vp8gpu_state_serialize(const vp8gpu_state* s, uint8_t* out, size_t cap);
+int vp8gpu_state_deserialize(const uint8_t* data, size_t len, vp8gpu_state** out);
 
 /* A parsed frame (KeyFrame / InterFrame, frame.hh:126-127) in flat form. The arrays are
  * owned by the vp8gpu_parsed object and stay valid until it is destroyed or reused. */

@@ -1,0 +1,67 @@
+#!/usr/bin/env python3
+"""A GOP split across GPUs (BASELINE.json config 4): rank 0 decodes the first part of a single-GOP
+stream with live golden / altref references, broadcasts its Decoder (DecoderState blob + the distinct
+reference rasters as uint8 tensors, NCCL over NVLink), and the other ranks continue.  Every rank also
+decodes the whole stream by itself and checks that the continued decode is bit-identical: every frame
+after the hand-over, and the final Decoder (state + the three rasters).
+
+launch: python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+            --master-port 29533 tools/split_gop_check.py [ivf] [split_frame]"""
+import hashlib
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    from alfalfa_b200 import Context, Decoder, multigpu
+    from alfalfa_b200.decoder import read_ivf
+    path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "bench_data", "features1080p_12f.ivf")
+    rank, world, local, dist = multigpu.init()
+    assert dist is not None, "run under torch.distributed.run with >= 2 ranks"
+    w, h, frames = read_ivf(open(path, "rb").read())
+    split = int(sys.argv[2]) if len(sys.argv) > 2 else len(frames) // 2
+    ctx = Context(w, h, device=local, max_frames=32)
+    # everybody: the whole stream alone (the truth on this rank)
+    alone = Decoder(ctx)
+    want = []
+    for f in frames:
+        shown, r = alone.get_frame_output(f)
+        want.append(hashlib.sha1(r.display_bytes()).hexdigest())
+        r.release()
+    # rank 0 decodes the first part, then hands over
+    dec = None
+    if rank == 0:
+        dec = Decoder(ctx)
+        for i, f in enumerate(frames[:split]):
+            shown, r = dec.get_frame_output(f)
+            assert hashlib.sha1(r.display_bytes()).hexdigest() == want[i]
+            r.release()
+    multigpu.barrier(dist)
+    t0 = time.perf_counter()
+    dec = multigpu.broadcast_decoder(ctx, dec, 0, dist, local)
+    multigpu.barrier(dist)
+    dt = time.perf_counter() - t0
+    bad = 0
+    for i, f in enumerate(frames[split:], start=split):
+        shown, r = dec.get_frame_output(f)
+        bad += hashlib.sha1(r.display_bytes()).hexdigest() != want[i]
+        r.release()
+    equal = dec == alone
+    total_bad = multigpu.reduce_sum(dist, local, bad + (0 if equal else 1))
+    if rank == 0:
+        print(json.dumps({"check": "split GOP across GPUs", "ranks": world, "stream": os.path.basename(path),
+                          "frames": len(frames), "split_at": split, "mismatches": int(total_bad),
+                          "handover_ms": dt * 1e3, "raster_bytes": ctx.frame_bytes, "backend": dist.get_backend()}))
+    del dec, alone
+    ctx.close()
+    dist.destroy_process_group()
+    sys.exit(1 if total_bad else 0)
+
+
+if __name__ == "__main__":
+    main()
