@@ -3,6 +3,7 @@
 // reference rasters, explicit state passing as in decoder/decoder.hh:244-300) and the
 // GOP-parallel whole-stream helper.
 #include <cuda_runtime.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -1092,6 +1093,14 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     std::vector<uint8_t*> dl_dst;
     int round = 0;
     double t_idle = 0, t_submit = 0, t_download = 0, n_batches = 0, n_jobs = 0;
+    // VP8GPU_TRACE=1: device-side duration of every batch (diagnostic, printed to stderr)
+    struct Trace {
+      cudaEvent_t a, b;
+      int lane, n;
+      double host_t;
+    };
+    std::vector<Trace> trace;
+    const bool tracing = getenv("VP8GPU_TRACE") != nullptr;
     for (;;) {
       batch.clear();
       const double ti = now();
@@ -1162,7 +1171,18 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
         }
         hj.push_back(j);
       }
+      Trace tr{nullptr, nullptr, lane, (int)batch.size(), ts};
+      if (tracing) {
+        e->ensure_lane(lane);
+        cudaEventCreate(&tr.a);
+        cudaEventCreate(&tr.b);
+        cudaEventRecord(tr.a, e->stream(lane));
+      }
       int rc = e->submit(lane, hj.data(), (int)hj.size(), nullptr);
+      if (tracing) {
+        cudaEventRecord(tr.b, e->stream(lane));
+        trace.push_back(tr);
+      }
       const double td = now();
       t_submit += td - ts;
       if (rc == VP8GPU_OK) {
@@ -1192,6 +1212,27 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     }
     e->sync_lane(2 * di);
     e->sync_lane(2 * di + 1);
+    if (tracing && !trace.empty()) {
+      // per batch: device time from "stream reaches the batch" to "its kernels are done", and the
+      // device-side gap to the previous batch of this dispatcher
+      double sum_ms = 0, sum_gap = 0, first_host = trace.front().host_t, last_host = trace.back().host_t;
+      float ms = 0;
+      for (size_t i = 0; i < trace.size(); i++) {
+        cudaEventElapsedTime(&ms, trace[i].a, trace[i].b);
+        sum_ms += ms;
+        if (i) {
+          cudaEventElapsedTime(&ms, trace[i - 1].b, trace[i].b);
+          sum_gap += ms;
+        }
+      }
+      fprintf(stderr, "[trace] dispatcher %d: %zu batches, avg %.2f frames, device %.3f ms per batch, end-to-end period %.3f ms, "
+              "host span %.1f ms\n", di, trace.size(), n_jobs / n_batches, sum_ms / trace.size(),
+              trace.size() > 1 ? sum_gap / (trace.size() - 1) : 0.0, (last_host - first_host) * 1e3);
+      for (Trace& t : trace) {
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+      }
+    }
     std::lock_guard<std::mutex> lk(stats_mu);
     st_disp_idle += t_idle;
     st_submit += t_submit;
