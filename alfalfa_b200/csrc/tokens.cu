@@ -25,13 +25,20 @@ namespace vp8 {
 namespace {
 
 constexpr int kMaxCols = 1024;  // 16383 px / 16
+constexpr int kTokWarps = 8;    // frames per CTA: a thousand one-warp CTAs would exhaust the SMs' CTA slots
+                                // (32 per SM) and starve the pixel kernels that run next to this one
 
 // jobs live at the start of equally spaced slots of a ring (engine.hpp TokenRing)
-__global__ void __launch_bounds__(32) k_tokens(const uint8_t* ring, size_t stride, int first, int nslots, Geom g) {
-  __shared__ __align__(16) uint8_t probs[tok::kProbBytes];
-  __shared__ uint16_t above_nz[kMaxCols];
-  const TokJob& J = *reinterpret_cast<const TokJob*>(ring + static_cast<size_t>((first + blockIdx.x) % nslots) * stride);
-  const int lane = threadIdx.x;
+__global__ void __launch_bounds__(32 * kTokWarps) k_tokens(const uint8_t* ring, size_t stride, int first, int count,
+                                                          int nslots, Geom g) {
+  __shared__ __align__(16) uint8_t probs_all[kTokWarps][tok::kProbBytes];
+  __shared__ uint16_t above_all[kTokWarps][kMaxCols];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int job = blockIdx.x * kTokWarps + warp;
+  if (job >= count) return;
+  uint8_t* probs = probs_all[warp];
+  uint16_t* above_nz = above_all[warp];
+  const TokJob& J = *reinterpret_cast<const TokJob*>(ring + static_cast<size_t>((first + job) % nslots) * stride);
   for (int e = lane; e < tok::kProbEntries; e += 32) tok::expand_prob_entry(J.coef_probs, probs, e);
   for (int i = lane; i < g.mb_cols; i += 32) above_nz[i] = 0;
   __syncwarp();
@@ -43,7 +50,8 @@ __global__ void __launch_bounds__(32) k_tokens(const uint8_t* ring, size_t strid
 
 int launch_tokens(const uint8_t* ring, size_t stride, int first, int count, int nslots, const Geom& g, void* stream) {
   if (g.mb_cols > kMaxCols) return (int)cudaErrorInvalidValue;
-  k_tokens<<<count, 32, 0, static_cast<cudaStream_t>(stream)>>>(ring, stride, first, nslots, g);
+  k_tokens<<<(count + kTokWarps - 1) / kTokWarps, 32 * kTokWarps, 0, static_cast<cudaStream_t>(stream)>>>(
+      ring, stride, first, count, nslots, g);
   return (int)cudaGetLastError();
 }
 
