@@ -926,9 +926,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     k = new ivf_worker_kit();
     bool ok = e->token_ring_create(tok_slots, ring_bytes_for(max_frame_bytes), &k->ring) == VP8GPU_OK &&
               cudaStreamCreateWithFlags(&k->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
-    int prio_lo = 0, prio_hi = 0;
-    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // token kernels: lowest priority
-    for (cudaStream_t& st : k->kstream) ok = ok && cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_lo) == cudaSuccess;
+    for (cudaStream_t& st : k->kstream) ok = ok && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
     if (!ok) {
       if (k->ring) e->token_ring_free(k->ring);
       if (k->copy_stream) cudaStreamDestroy(k->copy_stream);

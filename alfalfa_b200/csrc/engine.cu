@@ -96,11 +96,7 @@ int Engine::ensure_lane(int lane) {
   std::lock_guard<std::mutex> lk(mu_);
   CU(cudaSetDevice(device_));
   if (!lanes_[lane]) {
-    // the pixel kernels are short and latency critical: their CTAs go first when they compete with the
-    // long-running token kernels (default-priority streams owned by vp8gpu_decode_ivf's workers)
-    int lo = 0, hi = 0;
-    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    CU(cudaStreamCreateWithPriority(&lanes_[lane], cudaStreamNonBlocking, hi));
+    CU(cudaStreamCreateWithFlags(&lanes_[lane], cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&lanes_[kMaxLanes + lane], cudaStreamNonBlocking));
   }
   return VP8GPU_OK;

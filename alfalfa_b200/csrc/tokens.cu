@@ -17,6 +17,7 @@
 //      to the ones the CPU path produces.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "engine.h"
 #include "tokens_core.cuh"
@@ -25,10 +26,9 @@ namespace vp8 {
 namespace {
 
 constexpr int kMaxCols = 1024;  // 16383 px / 16
-constexpr int kTokWarps = 8;    // frames per CTA: a thousand one-warp CTAs would exhaust the SMs' CTA slots
-                                // (32 per SM) and starve the pixel kernels that run next to this one
-
-// jobs live at the start of equally spaced slots of a ring (engine.hpp TokenRing)
+// jobs live at the start of equally spaced slots of a ring (engine.hpp TokenRing); one warp per frame,
+// kTokWarps frames per CTA (measured: one-warp CTAs spread over the SMs best; VP8GPU_TOK_WARPS=8 packs them)
+template <int kTokWarps>
 __global__ void __launch_bounds__(32 * kTokWarps) k_tokens(const uint8_t* ring, size_t stride, int first, int count,
                                                           int nslots, Geom g) {
   __shared__ __align__(16) uint8_t probs_all[kTokWarps][tok::kProbBytes];
@@ -50,8 +50,13 @@ __global__ void __launch_bounds__(32 * kTokWarps) k_tokens(const uint8_t* ring, 
 
 int launch_tokens(const uint8_t* ring, size_t stride, int first, int count, int nslots, const Geom& g, void* stream) {
   if (g.mb_cols > kMaxCols) return (int)cudaErrorInvalidValue;
-  k_tokens<<<(count + kTokWarps - 1) / kTokWarps, 32 * kTokWarps, 0, static_cast<cudaStream_t>(stream)>>>(
-      ring, stride, first, count, nslots, g);
+  static const int warps = [] {  // tuning knob: frames per CTA (1 or 8)
+    const char* v = getenv("VP8GPU_TOK_WARPS");
+    return v && atoi(v) == 8 ? 8 : 1;
+  }();
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (warps == 8) k_tokens<8><<<(count + 7) / 8, 256, 0, s>>>(ring, stride, first, count, nslots, g);
+  else k_tokens<1><<<count, 32, 0, s>>>(ring, stride, first, count, nslots, g);
   return (int)cudaGetLastError();
 }
 
