@@ -444,6 +444,8 @@ TokenRing Engine::token_ring_layout(size_t max_frame_bytes) const {
   r.host_stride = off;
   r.result_off = off;
   off += 256;
+  r.above_off = off;
+  off = align_up(off + 2 * (size_t)g_.mb_cols, 256);
   r.mbs_off = off;
   off = align_up(off + n_mbs * sizeof(vp8gpu_mb), 256);
   r.split_off = off;
@@ -488,6 +490,7 @@ int Engine::token_ring_stage(TokenRing* r, int slot, const ParsedFrame& f, cudaS
   j->bits = d + r->bits_off;
   j->coef_probs = d + r->probs_off;
   j->result = reinterpret_cast<uint32_t*>(d + r->result_off);
+  j->above = reinterpret_cast<uint16_t*>(d + r->above_off);
   memcpy(j->part_off, tw.part_off, sizeof(j->part_off));
   memcpy(j->part_len, tw.part_len, sizeof(j->part_len));
   j->nparts = tw.nparts;

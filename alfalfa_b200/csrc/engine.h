@@ -60,6 +60,7 @@ struct TokJob {
   const uint8_t* bits;        // the frame's DCT partitions, back to back
   const uint8_t* coef_probs;  // 1056 bytes: the frame's coefficient probabilities
   uint32_t* result;           // [0] tokens written, [1] non-zero if the pool was too small
+  uint16_t* above;            // mb_cols zeroed words of scratch (lock-step variant: the row of contexts above)
   uint32_t part_off[8], part_len[8];
   uint32_t nparts;            // 1, 2, 4 or 8
   uint32_t tok_cap;

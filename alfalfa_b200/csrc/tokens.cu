@@ -46,16 +46,30 @@ __global__ void __launch_bounds__(32 * kTokWarps) k_tokens(const uint8_t* ring, 
   tok::decode_frame_tokens(J, g, probs, above_nz);
 }
 
+// lock-step variant: one LANE per frame, 32 frames per warp (tokens_core.cuh decode_frame_tokens_lockstep)
+__global__ void __launch_bounds__(32) k_tokens_lockstep(const uint8_t* ring, size_t stride, int first, int count,
+                                                         int nslots, Geom g) {
+  __shared__ tok::LockstepTables T;
+  const int lane = threadIdx.x;
+  tok::fill_lockstep_tables(T, lane, 32);
+  __syncwarp();
+  const int job = blockIdx.x * 32 + lane;
+  if (job >= count) return;
+  const TokJob& J = *reinterpret_cast<const TokJob*>(ring + static_cast<size_t>((first + job) % nslots) * stride);
+  tok::decode_frame_tokens_lockstep(J, g, T);
+}
+
 }  // namespace
 
 int launch_tokens(const uint8_t* ring, size_t stride, int first, int count, int nslots, const Geom& g, void* stream) {
   if (g.mb_cols > kMaxCols) return (int)cudaErrorInvalidValue;
-  static const int warps = [] {  // tuning knob: frames per CTA (1 or 8)
+  static const int warps = [] {  // tuning knob: frames per CTA (1 or 8); 32 = one lane per frame
     const char* v = getenv("VP8GPU_TOK_WARPS");
-    return v && atoi(v) == 8 ? 8 : 1;
+    return v && atoi(v) == 8 ? 8 : (v && atoi(v) == 32 ? 32 : 1);
   }();
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (warps == 8) k_tokens<8><<<(count + 7) / 8, 256, 0, s>>>(ring, stride, first, count, nslots, g);
+  if (warps == 32) k_tokens_lockstep<<<(count + 31) / 32, 32, 0, s>>>(ring, stride, first, count, nslots, g);
+  else if (warps == 8) k_tokens<8><<<(count + 7) / 8, 256, 0, s>>>(ring, stride, first, count, nslots, g);
   else k_tokens<1><<<count, 32, 0, s>>>(ring, stride, first, count, nslots, g);
   return (int)cudaGetLastError();
 }

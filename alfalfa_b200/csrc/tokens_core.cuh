@@ -231,5 +231,219 @@ TK_DEV void decode_frame_tokens(const TokJob& J, const Geom& g, const uint8_t* p
   J.result[1] = overflow;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// The same decoder as a state machine that consumes exactly ONE arithmetic-coded decision per loop
+// iteration, so that the 32 lanes of a warp can each walk their OWN frame in lock-step: the expensive
+// part of an iteration (probability fetch + bool decode) is the same instruction stream for every
+// lane whatever token-tree node it is at, the transition is table driven, and only the rarer block /
+// macroblock boundaries diverge.  One thread per frame (above) spends a whole warp instruction on one
+// lane's decision; this form spends it on 32.
+//   node 0..10 = tree node reading probability p[node] (tokens.cc:50-135), 11 = extra bits of a
+//   DCT_CAT token, 12 = sign, 13 = block finished.
+// ------------------------------------------------------------------------------------------------
+constexpr int kNodeExtra = 11, kNodeSign = 12, kNodeEnd = 13;
+// transition on (node, bit): next node | magnitude << 4 | zero-token << 8 | category << 9
+#define TK_T(next, setv, zero, cat) static_cast<uint16_t>((next) | ((setv) << 4) | ((zero) << 8) | ((cat) << 9))
+TK_CONST uint16_t c_trans[22] = {
+    TK_T(kNodeEnd, 0, 0, 0),  TK_T(1, 0, 0, 0),           // p[0]: end of block?
+    TK_T(1, 0, 1, 0),         TK_T(2, 0, 0, 0),           // p[1]: zero token?  (no end-of-block test after it)
+    TK_T(kNodeSign, 1, 0, 0), TK_T(3, 0, 0, 0),           // p[2]: one?
+    TK_T(4, 0, 0, 0),         TK_T(6, 0, 0, 0),           // p[3]
+    TK_T(kNodeSign, 2, 0, 0), TK_T(5, 0, 0, 0),           // p[4]: two?
+    TK_T(kNodeSign, 3, 0, 0), TK_T(kNodeSign, 4, 0, 0),   // p[5]: three / four
+    TK_T(7, 0, 0, 0),         TK_T(8, 0, 0, 0),           // p[6]
+    TK_T(kNodeExtra, 0, 0, 1), TK_T(kNodeExtra, 0, 0, 2), // p[7]: DCT_CAT1 / 2
+    TK_T(9, 0, 0, 0),         TK_T(10, 0, 0, 0),          // p[8]
+    TK_T(kNodeExtra, 0, 0, 3), TK_T(kNodeExtra, 0, 0, 4), // p[9]: DCT_CAT3 / 4
+    TK_T(kNodeExtra, 0, 0, 5), TK_T(kNodeExtra, 0, 0, 6), // p[10]: DCT_CAT5 / 6
+};
+#undef TK_T
+// categories 1..6: base value, number of extra bits, their probabilities (tokens.hh:74-78)
+TK_CONST uint8_t c_cat_base[7] = {0, 5, 7, 11, 19, 35, 67};
+TK_CONST uint8_t c_cat_bits[7] = {0, 1, 2, 3, 4, 5, 11};
+TK_CONST uint8_t c_cat_prob[7][11] = {{0},
+                                      {159},
+                                      {165, 145},
+                                      {173, 148, 140},
+                                      {176, 155, 140, 135},
+                                      {180, 157, 141, 134, 130},
+                                      {254, 254, 243, 230, 196, 177, 153, 140, 133, 130, 129}};
+
+// The small tables above, gathered: lanes index them with different values, which constant memory
+// serialises -- the kernel keeps one copy per CTA in shared memory.
+struct LockstepTables {
+  uint16_t trans[22];
+  uint8_t band[16], zigzag[16], cat_base[8], cat_bits[8], cat_prob[7][11];
+};
+TK_DEV void fill_lockstep_tables(LockstepTables& T, int lane, int nlanes) {
+  for (int k = lane; k < 22; k += nlanes) T.trans[k] = c_trans[k];
+  for (int k = lane; k < 16; k += nlanes) {
+    T.band[k] = c_band[k];
+    T.zigzag[k] = c_zigzag[k];
+  }
+  for (int k = lane; k < 7; k += nlanes) {
+    T.cat_base[k] = c_cat_base[k];
+    T.cat_bits[k] = c_cat_bits[k];
+    for (int j = 0; j < 11; j++) T.cat_prob[k][j] = c_cat_prob[k][j];
+  }
+}
+
+// probs = the frame's 1056 probabilities as the header leaves them ([type][band][ctx][node]);
+// J.above = mb_cols words of per-frame scratch (the row of contexts above)
+TK_DEV void decode_frame_tokens_lockstep(const TokJob& J, const Geom& g, const LockstepTables& T) {
+  const uint8_t* const probs = J.coef_probs;
+  uint16_t* const above_nz = J.above;
+  for (int c = 0; c < g.mb_cols; c++) above_nz[c] = 0;
+  BoolReader parts[8];
+  const int nparts = static_cast<int>(J.nparts);
+  for (int k = 0; k < nparts; k++) br_init(parts[k], J.bits + J.part_off[k], J.part_len[k]);
+  vp8gpu_mb* const mbs = J.mbs;
+  vp8gpu_token* const t_begin = J.tokens;
+  vp8gpu_token* t = t_begin;
+  vp8gpu_token* t0 = t_begin;
+  const vp8gpu_token* const t_limit = t_begin + J.tok_cap;
+  uint32_t overflow = 0;
+  const uint32_t* rec = reinterpret_cast<const uint32_t*>(mbs);
+  const int n_mbs = g.mb_cols * g.mb_rows;
+
+  BoolReader tr = parts[0];
+  int idx = 0, col = 0, row = 0;
+  unsigned a_nz = 0, left_nz = 0;
+  uint32_t cur1 = 0, cur2 = 0;
+  int bq = 0, last_y_type = 0, first_y = 0;  // current block: -1 = Y2, 0..15 Y, 16..23 U V
+  int type_off = 0, bx = 0, by = 0;
+  int i = 0, ctx = 0, node = kNodeEnd, nz = 0;
+  int v = 0, acc = 0, cat = 0, nrem = 0, extra_k = 0;
+  bool need_mb = true;  // the next thing to do is to start macroblock idx
+  bool done = n_mbs == 0;
+
+  while (!done) {
+    // ---- boundaries (divergent, comparatively rare): finish a block, finish / start macroblocks ----
+    if (node == kNodeEnd) {
+      if (!need_mb) {  // a block has just ended
+        a_nz = (a_nz & ~(1u << bx)) | (static_cast<unsigned>(nz) << bx);
+        left_nz = (left_nz & ~(1u << by)) | (static_cast<unsigned>(nz) << by);
+        bq++;
+        if (bq == 24) {  // macroblock finished
+          above_nz[col] = static_cast<uint16_t>(a_nz);
+          uint32_t* wr = reinterpret_cast<uint32_t*>(mbs) + 8 * idx;
+          wr[0] = static_cast<uint32_t>(t0 - t_begin);
+          wr[1] = (cur1 & 0xFFFF0000u) | static_cast<uint32_t>(t - t0);
+          wr[2] = cur2 & ~(static_cast<uint32_t>(VP8GPU_MB_SKIP) << 24);
+          idx++;
+          col++;
+          need_mb = true;
+        }
+      }
+      // start macroblocks until one has blocks to decode (skipped ones are settled on the spot)
+      while (need_mb && !done) {
+        if (idx == n_mbs) {
+          done = true;
+          break;
+        }
+        if (col == g.mb_cols) {  // next row: its partition is row % n (frame.cc:131-136)
+          parts[row & (nparts - 1)] = tr;
+          row++;
+          col = 0;
+          left_nz = 0;
+          tr = parts[row & (nparts - 1)];
+        }
+        cur1 = TK_LDCG(rec + 8 * idx + 1);
+        cur2 = TK_LDCG(rec + 8 * idx + 2);
+        const int y_mode = (cur1 >> 16) & 0xFF;
+        const bool skip = (cur2 >> 24) & VP8GPU_MB_SKIP;
+        const bool has_y2 = y_mode != VP8GPU_B_PRED && y_mode != VP8GPU_SPLITMV;
+        a_nz = above_nz[col];
+        t0 = t;
+        bool settled = false;
+        if (skip) {  // frame.cc:252-269: without Y2 the previous Y2 context stays
+          const unsigned keep = has_y2 ? 0u : 0x100u;
+          a_nz &= keep;
+          left_nz &= keep;
+          settled = true;
+        } else if (t + 400 > t_limit) {
+          overflow = 1;
+          a_nz = 0;
+          left_nz = 0;
+          settled = true;
+        }
+        if (settled) {
+          above_nz[col] = static_cast<uint16_t>(a_nz);
+          uint32_t* wr = reinterpret_cast<uint32_t*>(mbs) + 8 * idx;
+          wr[0] = static_cast<uint32_t>(t0 - t_begin);
+          wr[1] = cur1 & 0xFFFF0000u;
+          wr[2] = cur2 & ~(static_cast<uint32_t>(VP8GPU_MB_SKIP) << 24);
+          idx++;
+          col++;
+          continue;
+        }
+        need_mb = false;
+        bq = has_y2 ? -1 : 0;
+        last_y_type = has_y2 ? 0 : 3;  // Y after Y2 / Y with DC
+        first_y = has_y2 ? 1 : 0;
+      }
+      if (done) break;
+      // set the block up: type, context bits, first coefficient
+      if (bq < 0) {
+        type_off = 1 * 264, bx = 8, by = 8, i = 0;
+      } else if (bq < 16) {
+        type_off = last_y_type * 264, bx = bq & 3, by = bq >> 2, i = first_y;
+      } else {
+        const int sh = 4 + 2 * ((bq - 16) >> 2);
+        type_off = 2 * 264, bx = sh + (bq & 1), by = sh + ((bq >> 1) & 1), i = 0;
+      }
+      ctx = ((a_nz >> bx) & 1) + ((left_nz >> by) & 1);
+      node = 0;
+      nz = 0;
+    }
+
+    // ---- one decision (the same code for every lane) ----
+    const int tree_node = node <= 10 ? node : 0;
+    const uint32_t p_tree = TK_LDG(probs + type_off + T.band[i & 15] * 33 + ctx * 11 + tree_node);
+    const uint32_t p_extra = T.cat_prob[cat][extra_k];
+    const uint32_t prob = node <= 10 ? p_tree : (node == kNodeExtra ? p_extra : 128u);
+    const int bit = br_get(tr, prob);
+
+    // ---- transition ----
+    if (node <= 10) {
+      const uint32_t e = T.trans[node * 2 + bit];
+      node = e & 15;
+      const int setv = (e >> 4) & 15;
+      v = setv ? setv : v;
+      if ((e >> 8) & 1) {  // zero token
+        i++;
+        ctx = 0;
+        if (i == 16) node = kNodeEnd;
+      }
+      const int c = (e >> 9) & 7;
+      if (c) {
+        cat = c;
+        nrem = T.cat_bits[c];
+        acc = 0;
+        extra_k = 0;
+      }
+    } else if (node == kNodeExtra) {
+      acc = (acc << 1) + bit;
+      extra_k++;
+      if (--nrem == 0) {
+        v = T.cat_base[cat] + acc;
+        extra_k = 0;
+        node = kNodeSign;
+      }
+    } else {  // sign: the token is complete
+      const int sv = bit ? -v : v;
+      const int blk = bq < 0 ? VP8GPU_BLK_Y2 : bq;
+      *t++ = (static_cast<uint32_t>(blk) << 20) | (static_cast<uint32_t>(T.zigzag[i]) << 16) | static_cast<uint16_t>(sv);
+      nz = 1;
+      ctx = v == 1 ? 1 : 2;
+      i++;
+      node = i == 16 ? kNodeEnd : 0;
+    }
+  }
+  J.result[0] = static_cast<uint32_t>(t - t_begin);
+  J.result[1] = overflow;
+}
+
 }  // namespace tok
 }  // namespace vp8

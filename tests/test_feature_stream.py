@@ -58,7 +58,9 @@ def test_host_front_end_and_device_token_logic_on_feature_streams(w, h, seed):
     T.th_new.restype = C.c_void_p
     T.th_new.argtypes = [C.c_int, C.c_int]
     T.th_frame.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_uint32)]
+    T.th_variant.argtypes = [C.c_void_p, C.c_int]
     H = T.th_new(w, h)
+    T.th_variant(H, seed & 1)   # one thread per frame / the lock-step state machine
     for i, f in enumerate(frames):
         od.decode(f, want_planes=False)
         op = od.parsed()

@@ -29,15 +29,19 @@ def shim():
     L.th_new.restype = C.c_void_p
     L.th_new.argtypes = [C.c_int, C.c_int]
     L.th_free.argtypes = [C.c_void_p]
+    L.th_variant.argtypes = [C.c_void_p, C.c_int]
     L.th_frame.restype = C.c_int
     L.th_frame.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_uint32)]
     return L
 
 
+@pytest.mark.parametrize("lockstep", [0, 1])
 @pytest.mark.parametrize("name", golden_vectors())
-def test_device_token_logic_matches_cpu_front_end(shim, name):
+def test_device_token_logic_matches_cpu_front_end(shim, name, lockstep):
+    """both forms of the kernel body: one thread per frame, and the one-decision-per-iteration state machine"""
     w, h, frames = O.read_ivf(open(os.path.join(GOLDEN_DIR, name), "rb").read())
     H = shim.th_new(w, h)
+    shim.th_variant(H, lockstep)
     started = False
     limit = 40 if w * h > 500000 else 400
     n = C.c_uint32(0)
@@ -61,6 +65,7 @@ def test_truncated_partitions(shim):
     first = ((f[0] | (f[1] << 8) | (f[2] << 16)) >> 5) + 10
     for cut in list(range(first + 1, min(len(f), first + 40))) + [len(f) - 1, len(f) - 7, (first + len(f)) // 2]:
         H = shim.th_new(w, h)
+        shim.th_variant(H, cut & 1)
         rc = shim.th_frame(H, f[:cut], cut, 0, None)
         assert rc <= 0, "cut %d: code %d" % (cut, rc)
         shim.th_free(H)

@@ -14,12 +14,15 @@ struct Harness {
   vp8::ParsedFrame pa, pb;
   std::vector<vp8gpu_token> tokens;
   std::vector<uint16_t> above;
+  bool lockstep = false;
   Harness(int w, int h) : a(w, h), b(w, h) {}
 };
 
 extern "C" {
 void* th_new(int w, int h) { return new Harness(w, h); }
 void th_free(void* p) { delete static_cast<Harness*>(p); }
+// which form of the decoder th_frame runs: 0 = one thread per frame, 1 = the lock-step state machine
+void th_variant(void* p, int lockstep) { static_cast<Harness*>(p)->lockstep = lockstep != 0; }
 
 // 0 = identical; 1 = parse error mismatch; 2 = descriptor; 3 = records; 4 = tokens; 5 = overflow; 6 = skip flag left
 // negative = both parsers rejected the frame with that code
@@ -51,9 +54,16 @@ int th_frame(void* hp, const uint8_t* data, size_t len, uint32_t tok_cap_overrid
   memcpy(J.part_len, H.pb.tw.part_len, sizeof(J.part_len));
   J.nparts = H.pb.tw.nparts;
   J.tok_cap = (uint32_t)cap;
-  alignas(16) uint8_t probs16[vp8::tok::kProbBytes];
-  for (int e = 0; e < vp8::tok::kProbEntries; e++) vp8::tok::expand_prob_entry(H.pb.tw.coef_probs, probs16, e);
-  vp8::tok::decode_frame_tokens(J, g, probs16, H.above.data());
+  if (H.lockstep) {
+    J.above = H.above.data();
+    vp8::tok::LockstepTables T;
+    vp8::tok::fill_lockstep_tables(T, 0, 1);
+    vp8::tok::decode_frame_tokens_lockstep(J, g, T);
+  } else {
+    alignas(16) uint8_t probs16[vp8::tok::kProbBytes];
+    for (int e = 0; e < vp8::tok::kProbEntries; e++) vp8::tok::expand_prob_entry(H.pb.tw.coef_probs, probs16, e);
+    vp8::tok::decode_frame_tokens(J, g, probs16, H.above.data());
+  }
   if (n_tokens) *n_tokens = result[0];
   if (H.tokens[cap] != 0xDEADBEEFu) return 5;
   if (result[1]) return 5;
