@@ -98,6 +98,19 @@ class DecoderState {
   bool operator==(const DecoderState& o) const { return vp8gpu_state_equal(get(), o.get()); }
   bool operator!=(const DecoderState& o) const { return !(*this == o); }
   size_t hash() const { return vp8gpu_state_hash(get()); }
+  // DecoderState::serialize / deserialize (decoder.cc:266-330): flat blob
+  std::vector<uint8_t> serialize() const {
+    std::vector<uint8_t> b(vp8gpu_state_serialize(get(), nullptr, 0));
+    vp8gpu_state_serialize(get(), b.data(), b.size());
+    return b;
+  }
+  static DecoderState deserialize(const std::vector<uint8_t>& blob) {
+    vp8gpu_state* s = nullptr;
+    check(vp8gpu_state_deserialize(blob.data(), blob.size(), &s), nullptr, "state_deserialize");
+    DecoderState out(s);  // clones
+    vp8gpu_state_destroy(s);
+    return out;
+  }
 };
 
 // References (decoder.hh:123-149)

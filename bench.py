@@ -147,6 +147,20 @@ def run_reference_arm(a, rank, world):
         "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def ncu_traffic(kernel, gop_instances, path=os.path.join(ROOT, "profiles", "r1c_ncu_full_summary.csv")):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full`
+    capture (profiles/r1c_notes.md; taken at 64 GOP instances, so only reported for that configuration)"""
+    if gop_instances != 64 or not os.path.exists(path):
+        return None
+    import csv
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    r_i, w_i = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+    vals = [float(r[r_i]) * scale[units[r_i]] + float(r[w_i]) * scale[units[w_i]] for r in rows[2:] if kernel + "(" in r[0]]
+    return sum(vals) / len(vals) if vals else None
+
+
 def synth_1080p(t, w=1920, h=1080, seed=11):
     """seeded synthetic source: drifting smooth pattern, four translating softly textured tiles, light noise"""
     import numpy as np
@@ -394,10 +408,15 @@ def main():
     inter_frames = sum(0 if p[0].key_frame else 1 for p in parsed) / n_gops_in_clip
     pipeline_bytes = G * (gop_len * P + inter_frames * P + 32 * z_blocks / n_gops_in_clip + 48 * n_mbs * gop_len)
     pipeline_gbs = pipeline_bytes / (statistics.mean(step_ms) / 1e3) / 1e9
+    per_kernel = {}
+    for k, nm in enumerate(names):
+        bpl = per_gop_bytes[nm] * G / launches_per_step[nm]
+        gbs = bpl / (k_total[k] / launches_per_step[nm] / 1e3) / 1e9
+        per_kernel[nm] = {"achieved": gbs, "frac": gbs / peak, "bytes_per_launch": bpl}
     roofline = {"bound": "hbm", "kernel": dname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": ncu_traffic(dname, G), "peak_source": peak_src,
                 "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_launch_ms,
-                "kernel_ms_per_step": dict(zip(names, [float(x) for x in k_total])),
+                "kernel_ms_per_step": dict(zip(names, [float(x) for x in k_total])), "kernels": per_kernel,
                 "pipeline_achieved": pipeline_gbs, "pipeline_frac": pipeline_gbs / peak}
 
     # ---------------- end-to-end run through the public API: `e2e` ----------------
@@ -412,14 +431,21 @@ def main():
     # four per usable CPU; when the workers parse everything, two (they also wait on DMA / the dispatcher).
     per_cpu = 2 if a.host_tokens else 4
     threads = a.threads or max(2, min(96, per_cpu * effective_cpus() // max(world, 1)))
-    R = a.replicas or max(16, threads)  # 2 GOPs per repeat -> at least 2 GOPs per worker
-    big = replicate_ivf(data, R)
-    n_e2e_frames = len(frames) * R
+    # 2 GOPs per repeat.  With device-side tokens a worker runs two GOPs ahead, so give it four: the
+    # start-up (one k_tokens latency before the first pixel round) is then a smaller part of the step.
+    R = a.replicas or max(16, threads * (1 if a.host_tokens else 2))
     ctx2 = Context(w, h, device=local, max_frames=threads * (10 if a.host_tokens else int(os.environ.get("VP8GPU_TOK_SLOTS", 60)) + 6) + 64)
     ctx2.set_device_tokens(not a.host_tokens)
-    out_bytes = ctx2.display_bytes * n_e2e_frames
     dst = C.c_void_p()
-    capi.check(L.vp8gpu_host_alloc(C.byref(dst), out_bytes), ctx2.h, "host_alloc")
+    while True:  # the pinned output buffer is 3.1 MB per frame: halve the run if the box cannot pin that much
+        out_bytes = ctx2.display_bytes * len(frames) * R
+        if L.vp8gpu_host_alloc(C.byref(dst), out_bytes) == 0:
+            break
+        if R <= 16:
+            capi.check(capi.ERR_NOMEM, ctx2.h, "host_alloc")
+        R //= 2
+    big = replicate_ivf(data, R)
+    n_e2e_frames = len(frames) * R
     nd, ns = C.c_uint32(0), C.c_uint32(0)
 
     def e2e_step():
