@@ -12,6 +12,14 @@ from conftest import GOLDEN_DIR
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
+
+def _free_port():
+    """a rendezvous port nobody is using right now (fixed ports collide with lingering sockets)"""
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return str(s.getsockname()[1])
+
 WORKER = r'''
 import hashlib, json, os, sys
 sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
@@ -38,9 +46,10 @@ def test_two_rank_gop_sharding_and_reductions(tmp_path):
     vec = os.path.join(GOLDEN_DIR, "45502fe01a62b82d498b83dc50824741402436db")  # 30 key frames = 30 GOPs
     script = tmp_path / "worker.py"
     script.write_text(WORKER % {"root": ROOT, "vec": vec})
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29541")
+    port = _free_port()
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
+                          "--master-addr", "127.0.0.1", "--master-port", port, str(script)],
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     import json
@@ -162,9 +171,10 @@ def test_two_rank_decoder_handover_over_gloo(tmp_path):
     vec = os.path.join(GOLDEN_DIR, "0b546dad90ddefea5085c7751b5fa2f117630b1c")
     script = tmp_path / "handover.py"
     script.write_text(HANDOVER % {"root": ROOT, "vec": vec})
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29547")
+    port = _free_port()
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29547", str(script)],
+                          "--master-addr", "127.0.0.1", "--master-port", port, str(script)],
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-3000:]
     rows = sorted((json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")), key=lambda r: r["rank"])
