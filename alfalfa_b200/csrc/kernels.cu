@@ -556,6 +556,17 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 24) k_intra(const DevJob* __res
     const uint32_t bits = __ballot_sync(0xffffffffu, intra);
     if (lane == w) my_word = bits;
   }
+  // the same mask for the row above: a macroblock only has to wait for the row above when one of the
+  // macroblocks it predicts from (above-left, above, above-right) is intra-coded too -- inter-coded
+  // neighbours were finished by k_inter before this kernel started
+  uint32_t above_word = 0;
+  if (row > 0)
+    for (int w = 0; w < nwords; w++) {
+      const int c = w * 32 + lane;
+      const bool intra = c < cols && (__ldg(reinterpret_cast<const uint32_t*>(row_mbs - cols + c) + 2) & 0xFF) == VP8GPU_REF_CURRENT;
+      const uint32_t bits = __ballot_sync(0xffffffffu, intra);
+      if (lane == w) above_word = bits;
+    }
   int col = next_marked(my_word, 0, nwords);
   int* progress = J.intra_progress + row;
   // progress = P means: every macroblock of this row with column < P is reconstructed
@@ -574,7 +585,17 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 24) k_intra(const DevJob* __res
     PROF(0);
     if (has_res) build_residuals(J, f, coef, lane);
     PROF(1);
-    if (row > 0) wait_row(progress - 1, min(col + 2, cols), lane);
+    if (row > 0) {
+      // highest intra-coded column among col-1, col, col+1 of the row above (-1: none, nothing to wait for)
+      int dep = -1;
+#pragma unroll
+      for (int d = -1; d <= 1; d++) {
+        const int c = col + d;
+        const uint32_t word = __shfl_sync(0xffffffffu, above_word, (c >> 5) & 31);
+        if (c >= 0 && c < cols && ((word >> (c & 31)) & 1)) dep = c;
+      }
+      if (dep >= 0) wait_row(progress - 1, dep + 1, lane);
+    }
     PROF(2);
 
     // ---- edges (prediction.cc:99-167), read through L2; the three loads of a lane are issued
@@ -823,7 +844,17 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 16) k_loopfilter(const DevJob* 
     const MbFields f = load_mb(row_mbs + col);
     const bool have_left = prev == col - 1;
     PROF(0);
-    if (row > 0) wait_row(progress - 1, min(col + 2, cols), lane);
+    if (row > 0) {
+      // highest intra-coded column among col-1, col, col+1 of the row above (-1: none, nothing to wait for)
+      int dep = -1;
+#pragma unroll
+      for (int d = -1; d <= 1; d++) {
+        const int c = col + d;
+        const uint32_t word = __shfl_sync(0xffffffffu, above_word, (c >> 5) & 31);
+        if (c >= 0 && c < cols && ((word >> (c & 31)) & 1)) dep = c;
+      }
+      if (dep >= 0) wait_row(progress - 1, dep + 1, lane);
+    }
     PROF(1);
 
     // ---- top 4 rows (final output of the row above), through L2: one word per lane ----
@@ -1113,7 +1144,17 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 12) k_enc_mb(const EncJob* __re
     }
     int mvx = 0, mvy = 0, cost_inter = 0x7fffffff;
     __syncwarp();
-    if (row > 0) wait_row(progress - 1, min(col + 2, cols), lane);
+    if (row > 0) {
+      // highest intra-coded column among col-1, col, col+1 of the row above (-1: none, nothing to wait for)
+      int dep = -1;
+#pragma unroll
+      for (int d = -1; d <= 1; d++) {
+        const int c = col + d;
+        const uint32_t word = __shfl_sync(0xffffffffu, above_word, (c >> 5) & 31);
+        if (c >= 0 && c < cols && ((word >> (c & 31)) & 1)) dep = c;
+      }
+      if (dep >= 0) wait_row(progress - 1, dep + 1, lane);
+    }
     if (!J.key_frame) {
       // candidate vectors: the searched one, zero, and the vectors the left / above macroblocks chose
       // (cheap to code: they become ZEROMV / NEARESTMV / NEARMV in the bitstream).  A candidate's cost
