@@ -844,17 +844,7 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 16) k_loopfilter(const DevJob* 
     const MbFields f = load_mb(row_mbs + col);
     const bool have_left = prev == col - 1;
     PROF(0);
-    if (row > 0) {
-      // highest intra-coded column among col-1, col, col+1 of the row above (-1: none, nothing to wait for)
-      int dep = -1;
-#pragma unroll
-      for (int d = -1; d <= 1; d++) {
-        const int c = col + d;
-        const uint32_t word = __shfl_sync(0xffffffffu, above_word, (c >> 5) & 31);
-        if (c >= 0 && c < cols && ((word >> (c & 31)) & 1)) dep = c;
-      }
-      if (dep >= 0) wait_row(progress - 1, dep + 1, lane);
-    }
+    if (row > 0) wait_row(progress - 1, min(col + 2, cols), lane);
     PROF(1);
 
     // ---- top 4 rows (final output of the row above), through L2: one word per lane ----
@@ -1144,17 +1134,7 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 12) k_enc_mb(const EncJob* __re
     }
     int mvx = 0, mvy = 0, cost_inter = 0x7fffffff;
     __syncwarp();
-    if (row > 0) {
-      // highest intra-coded column among col-1, col, col+1 of the row above (-1: none, nothing to wait for)
-      int dep = -1;
-#pragma unroll
-      for (int d = -1; d <= 1; d++) {
-        const int c = col + d;
-        const uint32_t word = __shfl_sync(0xffffffffu, above_word, (c >> 5) & 31);
-        if (c >= 0 && c < cols && ((word >> (c & 31)) & 1)) dep = c;
-      }
-      if (dep >= 0) wait_row(progress - 1, dep + 1, lane);
-    }
+    if (row > 0) wait_row(progress - 1, min(col + 2, cols), lane);
     if (!J.key_frame) {
       // candidate vectors: the searched one, zero, and the vectors the left / above macroblocks chose
       // (cheap to code: they become ZEROMV / NEARESTMV / NEARMV in the bitstream).  A candidate's cost
