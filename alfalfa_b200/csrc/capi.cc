@@ -174,6 +174,10 @@ int vp8gpu_frame_download_display_async(vp8gpu_ctx* ctx, vp8gpu_frame_id id, uin
   return ctx->engine->frame_download_display(id, 0, dst, dst_size, false);
 }
 int vp8gpu_frame_hash(vp8gpu_ctx* ctx, vp8gpu_frame_id id, uint64_t* out) { return ctx->engine->frame_hash(id, 0, out); }
+int vp8gpu_frame_ssim(vp8gpu_ctx* ctx, vp8gpu_frame_id a, vp8gpu_frame_id b, double* out) {
+  if (!ctx || !out) return VP8GPU_ERR_LOGIC;
+  return ctx->engine->frames_ssim(a, b, 0, out);
+}
 size_t vp8gpu_frame_bytes(const vp8gpu_ctx* ctx) { return ctx->engine->geom().frame_bytes; }
 int vp8gpu_frame_export(vp8gpu_ctx* ctx, vp8gpu_frame_id id, void* dst, size_t bytes) {
   return ctx->engine->frame_copy_raw(id, dst, bytes, false);

@@ -34,6 +34,8 @@ struct vp8gpu_encoder {
   int last = -1;      // LAST reference = previous reconstruction
   int src = -1;       // device raster holding the (edge-extended) source frame
   int last_qi = -1;   // last_y_ac_qi_
+  int last_lf = -1;   // loop_filter_level_ (encoder.hh:144): -1 = not initialised
+  double last_ssim = -1.0;  // encode_stats_.ssim of the last frame
   // device scratch: EncJob | DevJob | sync ints | mbs | mv | sad | tokens
   uint8_t* dev = nullptr;
   size_t off_encjob = 0, off_devjob = 0, off_sync = 0, off_mbs = 0, off_mv = 0, off_sad = 0, off_tokens = 0, dev_bytes = 0;
@@ -62,20 +64,16 @@ vp8gpu_quant make_quant(int qi) {  // Quantizer::Quantizer, quantization.cc:83-9
   if (q.uv_dc > 132) q.uv_dc = 132;
   return q;
 }
-// loop-filter strength from the quantiser (libvpx's initial guess; the reference searches by SSIM)
-int default_filter_level(int qi) {
-  int l = qi * 3 / 8;
-  return l > 63 ? 63 : l;
-}
 #define CUE(call)                                                       \
   do {                                                                  \
     cudaError_t e__ = (call);                                           \
     if (e__ != cudaSuccess) return enc->e->cuda_fail(e__, #call);       \
   } while (0)
 
-// run the device pipeline for one candidate quantiser; returns the compressed frame in `bytes` and
-// the new reconstruction in *out_frame (caller releases it or keeps it as LAST)
-int run_encode(vp8gpu_encoder* enc, bool key, int qi, bool search_motion, std::vector<uint8_t>& bytes, int* out_frame) {
+// One encoding pass at quantiser index qi: motion search (once per source frame), the mode-decision /
+// transform / reconstruction wavefront, records and tokens back on the host.  *out_frame = the
+// reconstruction BEFORE the loop filter (the caller releases it or keeps it as LAST).
+int encode_core(vp8gpu_encoder* enc, bool key, int qi, bool search_motion, int* out_frame) {
   Engine* e = enc->e;
   const vp8::Geom& g = e->geom();
   const size_t n_mbs = (size_t)g.mb_cols * g.mb_rows;
@@ -89,9 +87,7 @@ int run_encode(vp8gpu_encoder* enc, bool key, int qi, bool search_motion, std::v
     e->frame_release(out);
     return rc;
   }
-  const int lf_level = default_filter_level(qi);
   vp8::EncJob* ej = reinterpret_cast<vp8::EncJob*>(enc->h_hdr);
-  vp8::DevJob* dj = reinterpret_cast<vp8::DevJob*>(enc->h_hdr + 512);
   memset(enc->h_hdr, 0, 1024);
   int* d_sync = reinterpret_cast<int*>(enc->dev + enc->off_sync);
   ej->src = e->frame_dev(enc->src);
@@ -106,17 +102,7 @@ int run_encode(vp8gpu_encoder* enc, bool key, int qi, bool search_motion, std::v
   ej->progress = d_sync + 128;
   ej->q = make_quant(qi);
   ej->key_frame = key;
-  ej->lf_level = (uint8_t)lf_level;
-  dj->mbs = ej->mbs;
-  dj->tokens = ej->tokens;
-  dj->split = nullptr;
-  dj->out = ej->out;
-  dj->intra_progress = d_sync + 128;
-  dj->lf_progress = d_sync + 128 + g.mb_rows;
-  for (int i = 0; i < 4; i++) dj->quant[i] = ej->q;
-  dj->key_frame = key;
-  dj->sharpness = 0;
-  dj->lf_enabled = lf_level > 0;
+  ej->lf_level = 1;  // records carry "filtered"; the level itself is chosen afterwards (choose_loop_filter)
   auto fail = [&](int code) {
     e->frame_release(out);
     return code;
@@ -126,10 +112,9 @@ int run_encode(vp8gpu_encoder* enc, bool key, int qi, bool search_motion, std::v
     cudaError_t e__ = (call);                                            \
     if (e__ != cudaSuccess) return fail(e->cuda_fail(e__, #call));       \
   } while (0)
-  CUF(cudaMemcpyAsync(enc->dev + enc->off_encjob, enc->h_hdr, 1024, cudaMemcpyHostToDevice, s));
+  CUF(cudaMemcpyAsync(enc->dev + enc->off_encjob, enc->h_hdr, 512, cudaMemcpyHostToDevice, s));
   CUF(cudaMemsetAsync(d_sync, 0, sizeof(int) * (128 + 2 * (size_t)g.mb_rows), s));
   const vp8::EncJob* d_ej = reinterpret_cast<const vp8::EncJob*>(enc->dev + enc->off_encjob);
-  const vp8::DevJob* d_dj = reinterpret_cast<const vp8::DevJob*>(enc->dev + enc->off_encjob + 512);
   int launches = 0;
   if (!key && search_motion) {  // vectors do not depend on the quantiser: searched once per source frame
     if (int ce = vp8::launch_enc_motion(d_ej, g, s)) return fail(e->cuda_fail((cudaError_t)ce, "k_enc_motion"));
@@ -137,10 +122,6 @@ int run_encode(vp8gpu_encoder* enc, bool key, int qi, bool search_motion, std::v
   }
   if (int ce = vp8::launch_enc_mb(d_ej, g, d_sync + 0, s)) return fail(e->cuda_fail((cudaError_t)ce, "k_enc_mb"));
   launches++;
-  if (lf_level > 0) {
-    if (int ce = vp8::launch_loopfilter(d_dj, 1, g, d_sync + 32, s)) return fail(e->cuda_fail((cudaError_t)ce, "k_loopfilter"));
-    launches++;
-  }
   e->count_launches(launches);
   e->mark_frames(enc->lane, ids, key ? 2 : 3);
   // results back: token count first, then the records
@@ -153,6 +134,14 @@ int run_encode(vp8gpu_encoder* enc, bool key, int qi, bool search_motion, std::v
     CUF(cudaMemcpyAsync(enc->h_tokens, ej->tokens, (size_t)n_tok * sizeof(vp8gpu_token), cudaMemcpyDeviceToHost, s));
     CUF(cudaStreamSynchronize(s));
   }
+  *out_frame = out;
+  return VP8GPU_OK;
+#undef CUF
+}
+
+// the compressed frame of the last encode_core pass
+int encode_bytes(vp8gpu_encoder* enc, bool key, int qi, int lf_level, std::vector<uint8_t>& bytes) {
+  Engine* e = enc->e;
   vp8::EncodeHeader h;
   h.key_frame = key;
   h.show_frame = true;
@@ -163,10 +152,78 @@ int run_encode(vp8gpu_encoder* enc, bool key, int qi, bool search_motion, std::v
   h.sharpness = 0;
   h.optimize_token_probs = true;
   bytes = vp8::serialize_frame(h, enc->h_mbs, enc->h_tokens, nullptr);
-  if (bytes.empty()) return fail(e->fail(VP8GPU_ERR_LOGIC, "serializer rejected the device records"));
-  *out_frame = out;
+  if (bytes.empty()) return e->fail(VP8GPU_ERR_LOGIC, "serializer rejected the device records");
   return VP8GPU_OK;
-#undef CUF
+}
+
+// one loop-filter pass over `frame` with every macroblock at `level` (in place)
+int filter_frame(vp8gpu_encoder* enc, int frame, bool key, int level) {
+  Engine* e = enc->e;
+  const vp8::Geom& g = e->geom();
+  cudaStream_t s = e->stream(enc->lane);
+  if (level <= 0) return VP8GPU_OK;  // a frame-level 0 disables the filter (frame.cc:144)
+  vp8::DevJob* dj = reinterpret_cast<vp8::DevJob*>(enc->h_hdr + 512);
+  memset(dj, 0, 512);
+  int* d_sync = reinterpret_cast<int*>(enc->dev + enc->off_sync);
+  dj->mbs = reinterpret_cast<const vp8gpu_mb*>(enc->dev + enc->off_mbs);
+  dj->tokens = reinterpret_cast<const vp8gpu_token*>(enc->dev + enc->off_tokens);
+  dj->out = e->frame_dev(frame);
+  dj->lf_progress = d_sync + 128 + g.mb_rows;
+  dj->intra_progress = d_sync + 128;
+  dj->key_frame = key;
+  dj->sharpness = 0;
+  dj->lf_enabled = 1;
+  dj->lf_force = (uint8_t)level;
+  int ids[1] = {frame};
+  int rc = e->acquire_frames(enc->lane, ids, 1);
+  if (rc != VP8GPU_OK) return rc;
+  CUE(cudaMemcpyAsync(enc->dev + enc->off_encjob + 512, dj, 512, cudaMemcpyHostToDevice, s));
+  CUE(cudaMemsetAsync(d_sync + 32, 0, sizeof(int), s));                                     // ticket
+  CUE(cudaMemsetAsync(d_sync + 128 + g.mb_rows, 0, sizeof(int) * (size_t)g.mb_rows, s));    // row progress
+  const vp8::DevJob* d_dj = reinterpret_cast<const vp8::DevJob*>(enc->dev + enc->off_encjob + 512);
+  if (int ce = vp8::launch_loopfilter(d_dj, 1, g, d_sync + 32, s)) return e->cuda_fail((cudaError_t)ce, "k_loopfilter");
+  e->count_launches(1);
+  e->mark_frames(enc->lane, ids, 1);
+  // the pinned descriptor is rewritten by the next call: wait until it has been read
+  CUE(cudaStreamSynchronize(s));
+  return VP8GPU_OK;
+}
+
+// Encoder::apply_best_loopfilter_settings (encoder.cc:460-508): try loop-filter levels in ascending
+// order -- all of 0..63 for the first frame, the previous level +-1 afterwards -- on a copy of the
+// reconstruction, keep going while the luma SSIM against the source improves, then filter the
+// reconstruction itself at the best level.
+int choose_loop_filter(vp8gpu_encoder* enc, int recon, bool key, int* level_out, double* ssim_out) {
+  Engine* e = enc->e;
+  int lo = 0, hi = 63;
+  if (enc->last_lf >= 0) {
+    lo = enc->last_lf > 0 ? enc->last_lf - 1 : 0;
+    hi = enc->last_lf + 1 > 63 ? 63 : enc->last_lf + 1;
+  }
+  int temp = -1;
+  int rc = e->frame_alloc(&temp);
+  if (rc != VP8GPU_OK) return rc;
+  int best = 0;
+  double best_ssim = -1.0;
+  for (int level = lo; level <= hi; level++) {
+    rc = e->frame_copy(temp, recon, enc->lane);
+    if (rc == VP8GPU_OK) rc = filter_frame(enc, temp, key, level);
+    double q = 0;
+    if (rc == VP8GPU_OK) rc = e->frames_ssim(temp, enc->src, enc->lane, &q);
+    if (rc != VP8GPU_OK) break;
+    if (q > best_ssim) {
+      best_ssim = q;
+      best = level;
+    } else {
+      break;
+    }
+  }
+  e->frame_release(temp);
+  if (rc != VP8GPU_OK) return rc;
+  rc = filter_frame(enc, recon, key, best);
+  *level_out = best;
+  *ssim_out = best_ssim;
+  return rc;
 }
 
 // source planes (display size) -> MB-aligned raster on the device, edges replicated like the
@@ -253,8 +310,8 @@ void vp8gpu_encoder_destroy(vp8gpu_encoder* enc) {
   delete enc;
 }
 
-static int finish_frame(vp8gpu_encoder* enc, const std::vector<uint8_t>& bytes, int out_frame, int qi, uint8_t* out,
-                        size_t cap, size_t* size) {
+static int finish_frame(vp8gpu_encoder* enc, const std::vector<uint8_t>& bytes, int out_frame, int qi, int lf, double ssim,
+                        uint8_t* out, size_t cap, size_t* size) {
   *size = bytes.size();
   if (!out || cap < bytes.size()) {
     enc->e->frame_release(out_frame);
@@ -265,8 +322,26 @@ static int finish_frame(vp8gpu_encoder* enc, const std::vector<uint8_t>& bytes, 
   enc->last = out_frame;  // Frame::copy_to: key frames and refresh_last inter frames replace LAST
   enc->has_state = true;
   enc->last_qi = qi;
+  enc->last_lf = lf;      // encoder.cc:165
+  enc->last_ssim = ssim;
   enc->stat_frames++;
   return VP8GPU_OK;
+}
+
+// encode at qi, choose the loop filter, serialize: Encoder::encode_raster + write_frame (encoder.cc:140-178)
+static int encode_final(vp8gpu_encoder* enc, bool key, int qi, bool search_motion, uint8_t* out, size_t cap, size_t* size) {
+  int frame = -1, lf = 0;
+  double ssim = -1.0;
+  int rc = encode_core(enc, key, qi, search_motion, &frame);
+  if (rc != VP8GPU_OK) return rc;
+  rc = choose_loop_filter(enc, frame, key, &lf, &ssim);
+  std::vector<uint8_t> bytes;
+  if (rc == VP8GPU_OK) rc = encode_bytes(enc, key, qi, lf, bytes);
+  if (rc != VP8GPU_OK) {
+    enc->e->frame_release(frame);
+    return rc;
+  }
+  return finish_frame(enc, bytes, frame, qi, lf, ssim, out, cap, size);
 }
 
 int vp8gpu_encoder_encode_with_quantizer(vp8gpu_encoder* enc, const uint8_t* y, size_t y_stride, const uint8_t* u,
@@ -276,11 +351,7 @@ int vp8gpu_encoder_encode_with_quantizer(vp8gpu_encoder* enc, const uint8_t* y, 
   cudaSetDevice(enc->e->device());
   int rc = upload_source(enc, y, y_stride, u, v, uv_stride);
   if (rc != VP8GPU_OK) return rc;
-  std::vector<uint8_t> bytes;
-  int frame = -1;
-  rc = run_encode(enc, !enc->has_state, y_ac_qi, true, bytes, &frame);
-  if (rc != VP8GPU_OK) return rc;
-  return finish_frame(enc, bytes, frame, y_ac_qi, out, cap, size);
+  return encode_final(enc, !enc->has_state, y_ac_qi, true, out, cap, size);
 }
 
 int vp8gpu_encoder_encode_with_target_size(vp8gpu_encoder* enc, const uint8_t* y, size_t y_stride, const uint8_t* u,
@@ -291,39 +362,80 @@ int vp8gpu_encoder_encode_with_target_size(vp8gpu_encoder* enc, const uint8_t* y
   int rc = upload_source(enc, y, y_stride, u, v, uv_stride);
   if (rc != VP8GPU_OK) return rc;
   // bisection over y_ac_qi exactly as Encoder::encode_with_target_size (encoder.cc:597-626); the size
-  // of a candidate is its real size (the device encode is cheap), not the 1/16-sampled estimate
+  // of a candidate is its real size (a device pass is cheap), not the 1/16-sampled estimate of
+  // estimate_frame_size; the loop filter does not change the size, so candidates skip it
   int lo = 4, hi = 127;
   if (enc->last_qi >= 0) {
     if (enc->last_qi - 16 >= lo) lo = enc->last_qi - 16;
     if (enc->last_qi + 16 < hi) hi = enc->last_qi + 16;
   }
-  int best = -1, best_frame = -1;
-  std::vector<uint8_t> best_bytes, bytes;
+  int best = -1;
+  std::vector<uint8_t> bytes;
   const bool key = !enc->has_state;
   bool first_probe = true;
   while (lo <= hi) {
     const int qi = (lo + hi) / 2;
     int frame = -1;
-    rc = run_encode(enc, key, qi, first_probe, bytes, &frame);
+    rc = encode_core(enc, key, qi, first_probe, &frame);
     first_probe = false;
-    if (rc != VP8GPU_OK) {
-      if (best_frame >= 0) enc->e->frame_release(best_frame);
-      return rc;
-    }
+    if (rc != VP8GPU_OK) return rc;
+    enc->e->frame_release(frame);
+    rc = encode_bytes(enc, key, qi, 0, bytes);
+    if (rc != VP8GPU_OK) return rc;
     if (bytes.size() <= target_size || (lo == hi && best < 0)) {
-      if (best_frame >= 0) enc->e->frame_release(best_frame);
       best = qi;
-      best_frame = frame;
-      best_bytes.swap(bytes);
       hi = qi - 1;
     } else {
-      enc->e->frame_release(frame);
       lo = qi + 1;
     }
   }
   if (best < 0) return enc->e->fail(VP8GPU_ERR_LOGIC, "target size search failed");
   if (chosen_qi) *chosen_qi = best;
-  return finish_frame(enc, best_bytes, best_frame, best, out, cap, size);
+  return encode_final(enc, key, best, false, out, cap, size);  // encoder.cc:628: encode again at the chosen index
+}
+
+// Encoder::encode_with_minimum_ssim -> encode_with_quantizer_search (encoder.cc:510-557, 577-590): the
+// coarsest quantiser whose reconstruction (after the loop-filter choice) still reaches minimum_ssim
+int vp8gpu_encoder_encode_with_minimum_ssim(vp8gpu_encoder* enc, const uint8_t* y, size_t y_stride, const uint8_t* u,
+                                            const uint8_t* v, size_t uv_stride, double minimum_ssim, uint8_t* out,
+                                            size_t cap, size_t* size, int* chosen_qi) {
+  if (!enc || !y || !u || !v || !size) return VP8GPU_ERR_LOGIC;
+  cudaSetDevice(enc->e->device());
+  int rc = upload_source(enc, y, y_stride, u, v, uv_stride);
+  if (rc != VP8GPU_OK) return rc;
+  const bool key = !enc->has_state;
+  int lo = 0, hi = 127, best = 0;
+  bool found = false, first_probe = true;
+  while (lo <= hi) {
+    const int qi = (lo + hi) / 2;
+    int frame = -1, lf = 0;
+    double ssim = -1.0;
+    rc = encode_core(enc, key, qi, first_probe, &frame);
+    first_probe = false;
+    if (rc != VP8GPU_OK) return rc;
+    rc = choose_loop_filter(enc, frame, key, &lf, &ssim);
+    enc->e->frame_release(frame);
+    if (rc != VP8GPU_OK) return rc;
+    if (ssim >= minimum_ssim || (lo == hi && !found)) {
+      found = true;
+      best = qi;
+    }
+    if (lo == hi) break;
+    if (ssim < minimum_ssim) hi = qi - 1;
+    else lo = qi + 1;
+  }
+  if (chosen_qi) *chosen_qi = best;
+  return encode_final(enc, key, best, false, out, cap, size);
+}
+
+// EncoderStats (encoder.hh:118-127) of the last frame: luma SSIM after the loop filter, the chosen
+// loop-filter level and quantiser index
+int vp8gpu_encoder_stats(const vp8gpu_encoder* enc, double* ssim, int* loop_filter_level, int* y_ac_qi) {
+  if (!enc) return VP8GPU_ERR_LOGIC;
+  if (ssim) *ssim = enc->last_ssim;
+  if (loop_filter_level) *loop_filter_level = enc->last_lf;
+  if (y_ac_qi) *y_ac_qi = enc->last_qi;
+  return VP8GPU_OK;
 }
 
 // Encoder::export_decoder (encoder.hh:378): the reconstruction kept as LAST (one new reference for the caller)

@@ -199,6 +199,19 @@ int Engine::frame_clear(int id, int lane) {
   return touch(f, lane);
 }
 
+int Engine::frame_copy(int dst, int src, int lane) {
+  if (int rc = ensure_lane(lane)) return rc;
+  std::lock_guard<std::mutex> lk(mu_);
+  for (int id : {dst, src})
+    if (id < 0 || id >= (int)frames_.size() || frames_[id].refcnt <= 0) return fail(VP8GPU_ERR_LOGIC, "frame_copy: bad frame id");
+  cudaStream_t s = lanes_[lane];
+  if (int rc = wait_for(frames_[dst], lane, s, true)) return rc;
+  if (int rc = wait_for(frames_[src], lane, s, false)) return rc;
+  CU(cudaMemcpyAsync(frames_[dst].dev, frames_[src].dev, g_.frame_bytes, cudaMemcpyDeviceToDevice, s));
+  if (int rc = touch(frames_[src], lane, false)) return rc;
+  return touch(frames_[dst], lane, true);
+}
+
 int Engine::frame_copy_raw(int id, void* buf, size_t bytes, bool into_frame) {
   if (int rc = ensure_lane(0)) return rc;
   if (!buf || bytes != g_.frame_bytes) return fail(VP8GPU_ERR_LOGIC, "frame_copy_raw: size must be vp8gpu_frame_bytes");
@@ -312,7 +325,7 @@ int Engine::frames_equal(int a, int b, int lane, int* equal) {
   cudaStream_t s = lanes_[lane];
   {
     std::lock_guard<std::mutex> lk(mu_);
-    if (!cmp_scratch_) CU(cudaMalloc(&cmp_scratch_, 512));
+    if (!cmp_scratch_) CU(cudaMalloc(&cmp_scratch_, 1024));
     flag = reinterpret_cast<int*>(cmp_scratch_);
     if (int rc = wait_for(frames_[a], lane, s, false)) return rc;
     if (int rc = wait_for(frames_[b], lane, s, false)) return rc;
@@ -329,6 +342,32 @@ int Engine::frames_equal(int a, int b, int lane, int* equal) {
   return VP8GPU_OK;
 }
 
+int Engine::frames_ssim(int a, int b, int lane, double* out) {
+  if (int rc = ensure_lane(lane)) return rc;
+  cudaStream_t s = lanes_[lane];
+  double* d;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (int id : {a, b})
+      if (id < 0 || id >= (int)frames_.size() || frames_[id].refcnt <= 0) return fail(VP8GPU_ERR_LOGIC, "ssim: bad frame id");
+    if (!cmp_scratch_) CU(cudaMalloc(&cmp_scratch_, 1024));
+    d = reinterpret_cast<double*>(cmp_scratch_ + 512 + 8 * lane);
+    if (int rc = wait_for(frames_[a], lane, s, false)) return rc;
+    if (int rc = wait_for(frames_[b], lane, s, false)) return rc;
+    CU(cudaMemsetAsync(d, 0, sizeof(double), s));
+    if (int e = launch_ssim(frames_[a].dev, frames_[b].dev, g_, d, s)) return cuda_fail((cudaError_t)e, "ssim");
+    launches_++;
+    if (int rc = touch(frames_[a], lane, false)) return rc;
+    if (int rc = touch(frames_[b], lane, false)) return rc;
+  }
+  double sum = 0;
+  CU(cudaMemcpyAsync(&sum, d, sizeof(sum), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  const int n = (g_.W / 4 - 1) * (g_.H / 4 - 1);
+  *out = n > 0 ? sum / n : 0.0;
+  return VP8GPU_OK;
+}
+
 int Engine::frame_hash(int id, int lane, uint64_t* out) {
   if (int rc = ensure_lane(lane)) return rc;
   unsigned long long* d;
@@ -336,7 +375,7 @@ int Engine::frame_hash(int id, int lane, uint64_t* out) {
   {
     std::lock_guard<std::mutex> lk(mu_);
     if (id < 0 || id >= (int)frames_.size() || frames_[id].refcnt <= 0) return fail(VP8GPU_ERR_LOGIC, "hash: bad frame id");
-    if (!cmp_scratch_) CU(cudaMalloc(&cmp_scratch_, 512));
+    if (!cmp_scratch_) CU(cudaMalloc(&cmp_scratch_, 1024));
     d = reinterpret_cast<unsigned long long*>(cmp_scratch_ + 64 + 8 * lane);
     if (int rc = wait_for(frames_[id], lane, s, false)) return rc;
     CU(cudaMemsetAsync(d, 0, sizeof(unsigned long long), s));

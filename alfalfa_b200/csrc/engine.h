@@ -29,7 +29,9 @@ struct DevJob {
   int* intra_progress;     // [mb_rows] wavefront counters, zeroed before launch
   int* lf_progress;        // [mb_rows]
   vp8gpu_quant quant[4];
-  uint8_t key_frame, sharpness, lf_enabled, pad;
+  uint8_t key_frame, sharpness, lf_enabled;
+  uint8_t lf_force;        // != 0: every macroblock is filtered at this level instead of its record's
+                           // (the encoder's loop-filter search, encoder.cc:460-508)
   uint32_t n_intra;        // intra-coded macroblocks in the frame
   uint32_t n_inter;
   uint32_t pad2;
@@ -73,6 +75,7 @@ int launch_intra(const DevJob* jobs, int njobs, const Geom& g, int* ticket, void
 int launch_loopfilter(const DevJob* jobs, int njobs, const Geom& g, int* ticket, void* stream);
 // token jobs sit at the start of equally spaced ring slots: slot (first + i) % nslots for block i
 int launch_tokens(const uint8_t* ring, size_t stride, int first, int count, int nslots, const Geom& g, void* stream);
+int launch_ssim(const uint8_t* a, const uint8_t* b, const Geom& g, double* d_sum, void* stream);
 int launch_enc_motion(const EncJob* job, const Geom& g, void* stream);
 int launch_enc_mb(const EncJob* job, const Geom& g, int* ticket, void* stream);
 

@@ -72,10 +72,12 @@ class Engine {
   // one event for the whole batch); every dst holds width*height*3/2-ish bytes like the call above
   int frames_download_display(const int* ids, uint8_t* const* dsts, int n, int lane);
   int frame_clear(int id, int lane);  // all-zero raster (initial References)
+  int frame_copy(int dst, int src, int lane);  // VP8Raster::copy_from, asynchronous on the lane
   // whole raster <-> a host or device buffer of geom().frame_bytes bytes (synchronous)
   int frame_copy_raw(int id, void* buf, size_t bytes, bool into_frame);
   int frames_equal(int a, int b, int lane, int* equal);
   int frame_hash(int id, int lane, uint64_t* out);
+  int frames_ssim(int a, int b, int lane, double* out);  // BaseRaster::quality: luma SSIM, synchronous
 
   // decode n frames in one set of launches on `lane`; host arrays must stay valid until the
   // returned event (*consumed, optional) has fired (pinned) or are consumed on return (pageable)

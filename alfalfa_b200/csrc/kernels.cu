@@ -797,7 +797,7 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 16) k_loopfilter(const DevJob* 
   uint32_t my_word = 0;
   for (int w = 0; w < nwords; w++) {
     const int c = w * 32 + lane;
-    const bool filtered = c < cols && ((__ldg(reinterpret_cast<const uint32_t*>(row_mbs + c) + 2) >> 16) & 0xFF) != 0;
+    const bool filtered = c < cols && (J.lf_force || ((__ldg(reinterpret_cast<const uint32_t*>(row_mbs + c) + 2) >> 16) & 0xFF) != 0);
     const uint32_t bits = __ballot_sync(0xffffffffu, filtered);
     if (lane == w) my_word = bits;
   }
@@ -895,7 +895,7 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 16) k_loopfilter(const DevJob* 
     const int next = next_marked(my_word, col + 1, nwords);
     if (next >= 0) prefetch_own(next);  // in flight while this macroblock is filtered
 
-    const vp8m::LfParams lp = vp8m::lf_params(f.lf_level, J.sharpness, J.key_frame);
+    const vp8m::LfParams lp = vp8m::lf_params(J.lf_force ? J.lf_force : f.lf_level, J.sharpness, J.key_frame);
     const bool do_inner = !((f.flags & VP8GPU_MB_HAS_Y2) && f.tok_cnt == 0);  // macroblock.cc:608
     // lane roles on an edge: 0-15 luma positions, 16-23 U, 24-31 V
     const bool luma = lane < 16;
@@ -1433,6 +1433,52 @@ __global__ void k_compare(const uint8_t* __restrict__ a, const uint8_t* __restri
 }
 
 // ================================================================================================
+// k_ssim: BaseRaster::quality (util/raster.cc:63-66) = ssim( Y, other.Y ) over the macroblock-aligned
+// luma planes, the measure the reference encoder maximises when it picks the loop-filter level
+// (encoder.cc:489-508).  util/ssim.cc binds x264's pixel_ssim_wxh: sums over 4x4 blocks, combined over
+// every 8x8 window at a 4-pixel step, float ratio per window, mean over (W/4-1)(H/4-1) windows
+// (restated in oracle/ref_shim/ssim_stub.cc; parity with x264 itself is unpinned in this image).
+// One thread per window; the per-window floats are added in double (the reference adds them in float
+// in raster order: equal to ~1e-6).
+// ================================================================================================
+__global__ void k_ssim(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, Geom g, double* out) {
+  const int nx = g.W / 4 - 1, ny = g.H / 4 - 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float v = 0.f;
+  if (i < nx * ny) {
+    const int wy = i / nx, wx = i - wy * nx;
+    const uint8_t* pa = a + (size_t)(4 * wy) * g.y_pitch + 4 * wx;
+    const uint8_t* pb = b + (size_t)(4 * wy) * g.y_pitch + 4 * wx;
+    int s1 = 0, s2 = 0, ss = 0, s12 = 0;
+#pragma unroll
+    for (int y = 0; y < 8; y++) {
+      const uint32_t* ra = reinterpret_cast<const uint32_t*>(pa + (size_t)y * g.y_pitch);
+      const uint32_t* rb = reinterpret_cast<const uint32_t*>(pb + (size_t)y * g.y_pitch);
+#pragma unroll
+      for (int w = 0; w < 2; w++) {
+        const uint32_t xa = __ldg(ra + w), xb = __ldg(rb + w);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int p = (xa >> (8 * k)) & 0xFF, q = (xb >> (8 * k)) & 0xFF;
+          s1 += p;
+          s2 += q;
+          ss += p * p + q * q;
+          s12 += p * q;
+        }
+      }
+    }
+    const int c1 = (int)(.01 * .01 * 255 * 255 * 64 + .5);
+    const int c2 = (int)(.03 * .03 * 255 * 255 * 64 * 63 + .5);
+    const int vars = ss * 64 - s1 * s1 - s2 * s2, covar = s12 * 64 - s1 * s2;
+    v = (float)(2 * s1 * s2 + c1) * (float)(2 * covar + c2) / ((float)(s1 * s1 + s2 * s2 + c1) * (float)(vars + c2));
+  }
+  double d = v;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) d += __shfl_down_sync(0xffffffffu, d, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, d);
+}
+
+// ================================================================================================
 // k_hash: a 64-bit content hash of the visible pixels of a raster (HashCachedRaster::hash,
 // raster_handle.hh:60-75, is the reference's analogue; the value is ours, not boost's).  Position
 // dependent, order independent in evaluation: sum over 32-bit words of mix(word, plane row, index).
@@ -1506,6 +1552,13 @@ extern "C" void vp8gpu_debug_profile(unsigned long long out[32], int reset) {
 
 int launch_hash(const uint8_t* a, const Geom& g, unsigned long long* d_out, void* stream) {
   k_hash<<<296, 128, 0, static_cast<cudaStream_t>(stream)>>>(a, g, d_out);
+  return (int)cudaGetLastError();
+}
+
+int launch_ssim(const uint8_t* a, const uint8_t* b, const Geom& g, double* d_sum, void* stream) {
+  const int n = (g.W / 4 - 1) * (g.H / 4 - 1);
+  if (n <= 0) return 0;
+  k_ssim<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(a, b, g, d_sum);
   return (int)cudaGetLastError();
 }
 

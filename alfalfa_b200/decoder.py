@@ -95,6 +95,12 @@ class RasterHandle:
               "frame_download")
         return y, u, v
 
+    def ssim(self, other):
+        """BaseRaster::quality: luma SSIM against another raster of the same context"""
+        q = C.c_double(0)
+        check(self.ctx.L.vp8gpu_frame_ssim(self.ctx.h, self.id, other.id, C.byref(q)), self.ctx.h, "frame_ssim")
+        return q.value
+
     def export_to(self, ptr, nbytes):
         """whole raster (ctx.frame_bytes, pitched planes) into a host or same-device buffer"""
         check(self.ctx.L.vp8gpu_frame_export(self.ctx.h, self.id, ptr, nbytes), self.ctx.h, "frame_export")
@@ -384,6 +390,22 @@ class Encoder:
                                                             u.shape[1], target_size, self._out.ctypes.data, self._out.size,
                                                             C.byref(size), C.byref(qi)), self.ctx.h, "encode_with_target_size")
         return self._out[:size.value].tobytes(), qi.value
+
+    def encode_with_minimum_ssim(self, y, u, v, minimum_ssim):
+        """Encoder::encode_with_minimum_ssim (encoder.cc:577-590) -> (frame bytes, chosen y_ac_qi)"""
+        y, u, v = self._planes(y, u, v)
+        size, qi = C.c_size_t(0), C.c_int(0)
+        check(self.L.vp8gpu_encoder_encode_with_minimum_ssim(self.h, y.ctypes.data, y.shape[1], u.ctypes.data, v.ctypes.data,
+                                                             u.shape[1], float(minimum_ssim), self._out.ctypes.data,
+                                                             self._out.size, C.byref(size), C.byref(qi)), self.ctx.h,
+              "encode_with_minimum_ssim")
+        return self._out[:size.value].tobytes(), qi.value
+
+    def stats(self):
+        """EncoderStats of the last frame: dict(ssim, loop_filter_level, y_ac_qi)"""
+        q, lf, qi = C.c_double(0), C.c_int(0), C.c_int(0)
+        check(self.L.vp8gpu_encoder_stats(self.h, C.byref(q), C.byref(lf), C.byref(qi)), self.ctx.h, "encoder_stats")
+        return {"ssim": q.value, "loop_filter_level": lf.value, "y_ac_qi": qi.value}
 
     def reconstruction(self):
         """the encoder's LAST reference (what a decoder holds after decoding the frame just emitted)"""

