@@ -195,13 +195,16 @@ def bench_encode(a, local):
     enc.encode_with_target_size(*src[0], a.encode_target)  # warm-up (key frame, allocations)
     del enc
     enc = Encoder(ctx)
-    sizes, qis, psnrs, times = [], [], [], []
+    sizes, qis, psnrs, times, ssims, lfs = [], [], [], [], [], []
     for t in range(n):
         t0 = time.perf_counter()
         blob, qi = enc.encode_with_target_size(*src[t], a.encode_target)
         times.append(time.perf_counter() - t0)
         sizes.append(len(blob))
         qis.append(qi)
+        st = enc.stats()
+        ssims.append(st["ssim"])
+        lfs.append(st["loop_filter_level"])
         rec = enc.reconstruction()
         ry = rec.planes()[0][:h, :w]
         rec.release()
@@ -212,8 +215,10 @@ def bench_encode(a, local):
     ctx.close()
     out = {"metric": "encode_with_target_size fps @1080p", "frames": n, "target_bytes": a.encode_target,
            "fps": (n - 1) / sum(times[1:]), "key_frame_ms": times[0] * 1e3, "inter_frame_ms": 1e3 * sum(times[1:]) / (n - 1),
-           "bytes_per_frame": sum(sizes) / n, "qi": qis, "psnr_y": sum(psnrs) / n, "gpu_launches": int(launches),
-           "note": "first slice: SAD decisions, 16x16 intra modes, LAST reference; closed loop verified in tests/test_gpu_encoder.py"}
+           "bytes_per_frame": sum(sizes) / n, "qi": qis, "loop_filter_level": lfs, "psnr_y": sum(psnrs) / n,
+           "ssim_y": sum(ssims) / n, "gpu_launches": int(launches),
+           "note": "first slice: SAD decisions with zero/left/above vector candidates, 16x16 intra modes, LAST reference, "
+                   "SSIM-driven loop-filter search; closed loop verified in tests/test_gpu_encoder.py"}
     ref_enc = os.path.join(ROOT, "oracle", "_ref", "ref_encode")
     if os.path.exists(ref_enc):
         import tempfile
