@@ -671,6 +671,19 @@ int vp8gpu_decoder_references(const vp8gpu_decoder* d, vp8gpu_frame_id refs[3]) 
 }
 int vp8gpu_decoder_lane(const vp8gpu_decoder* d) { return d->lane; }
 
+int vp8gpu_decoder_hash(vp8gpu_decoder* d, uint64_t* out) {
+  if (!d || !out) return VP8GPU_ERR_LOGIC;
+  uint64_t h = d->state.s.hash();
+  for (int i = 0; i < 3; i++) {
+    uint64_t r = 0;
+    const int rc = d->ctx->engine->frame_hash(d->refs[i], d->lane, &r);
+    if (rc != VP8GPU_OK) return rc;
+    h = (h ^ r) * 0x9E3779B97F4A7C15ull + (h >> 29) + i;  // order dependent: last, golden, alternative
+  }
+  *out = h;
+  return VP8GPU_OK;
+}
+
 int vp8gpu_decoder_equal(vp8gpu_decoder* a, vp8gpu_decoder* b, int* equal) {
   if (!a || !b || !equal || a->ctx != b->ctx) return VP8GPU_ERR_LOGIC;
   *equal = 0;

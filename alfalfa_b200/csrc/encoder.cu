@@ -428,6 +428,24 @@ int vp8gpu_encoder_encode_with_minimum_ssim(vp8gpu_encoder* enc, const uint8_t* 
   return encode_final(enc, key, best, false, out, cap, size);
 }
 
+// Encoder::estimate_frame_size (size_estimation.cc:36-99): exact instead of sampled
+int vp8gpu_encoder_estimate_frame_size(vp8gpu_encoder* enc, const uint8_t* y, size_t y_stride, const uint8_t* u,
+                                       const uint8_t* v, size_t uv_stride, int y_ac_qi, size_t* size) {
+  if (!enc || !y || !u || !v || !size || y_ac_qi < 0 || y_ac_qi > 127) return VP8GPU_ERR_LOGIC;
+  cudaSetDevice(enc->e->device());
+  int rc = upload_source(enc, y, y_stride, u, v, uv_stride);
+  if (rc != VP8GPU_OK) return rc;
+  const bool key = !enc->has_state;
+  int frame = -1;
+  rc = encode_core(enc, key, y_ac_qi, true, &frame);
+  if (rc != VP8GPU_OK) return rc;
+  enc->e->frame_release(frame);
+  std::vector<uint8_t> bytes;
+  rc = encode_bytes(enc, key, y_ac_qi, 0, bytes);
+  if (rc == VP8GPU_OK) *size = bytes.size();
+  return rc;
+}
+
 // EncoderStats (encoder.hh:118-127) of the last frame: luma SSIM after the loop filter, the chosen
 // loop-filter level and quantiser index
 int vp8gpu_encoder_stats(const vp8gpu_encoder* enc, double* ssim, int* loop_filter_level, int* y_ac_qi) {

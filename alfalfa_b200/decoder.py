@@ -282,6 +282,16 @@ class Decoder:
         shown, raster = self.get_frame_output(chunk)
         return raster if shown else None
 
+    def get_hash(self):
+        """Decoder::get_hash: state + the three reference rasters"""
+        out = C.c_uint64(0)
+        check(self.L.vp8gpu_decoder_hash(self.h, C.byref(out)), self.ctx.h, "decoder_hash")
+        return out.value
+
+    def minihash(self):
+        h = self.get_hash()
+        return (h ^ (h >> 32)) & 0xFFFFFFFF
+
     def __eq__(self, other):
         eq = C.c_int(0)
         check(self.L.vp8gpu_decoder_equal(self.h, other.h, C.byref(eq)), self.ctx.h, "decoder_equal")
@@ -400,6 +410,14 @@ class Encoder:
                                                              self._out.size, C.byref(size), C.byref(qi)), self.ctx.h,
               "encode_with_minimum_ssim")
         return self._out[:size.value].tobytes(), qi.value
+
+    def estimate_frame_size(self, y, u, v, y_ac_qi):
+        """Encoder::estimate_frame_size: bytes at this quantiser index, without committing the frame"""
+        y, u, v = self._planes(y, u, v)
+        size = C.c_size_t(0)
+        check(self.L.vp8gpu_encoder_estimate_frame_size(self.h, y.ctypes.data, y.shape[1], u.ctypes.data, v.ctypes.data,
+                                                        u.shape[1], y_ac_qi, C.byref(size)), self.ctx.h, "estimate_frame_size")
+        return size.value
 
     def stats(self):
         """EncoderStats of the last frame: dict(ssim, loop_filter_level, y_ac_qi)"""

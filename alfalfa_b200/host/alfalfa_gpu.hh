@@ -208,6 +208,16 @@ class Decoder {
     }
     return r;
   }
+  // get_hash / minihash (decoder.hh:279-292): equal decoders hash equally (values are this library's)
+  uint64_t get_hash() const {
+    uint64_t h = 0;
+    check(vp8gpu_decoder_hash(h_, &h), ctx_.get(), "decoder_hash");
+    return h;
+  }
+  uint32_t minihash() const {
+    const uint64_t h = get_hash();
+    return static_cast<uint32_t>(h ^ (h >> 32));
+  }
   bool operator==(const Decoder& o) const {
     int eq = 0;
     check(vp8gpu_decoder_equal(h_, o.h_, &eq), ctx_.get(), "decoder_equal");
@@ -254,6 +264,13 @@ class Encoder {
                                                  buf_.size(), &n, nullptr),
           ctx_.get(), "encode_with_target_size");
     return take(n);
+  }
+  // estimate_frame_size (encoder.hh:376): exact size at this quantiser index, state untouched
+  size_t estimate_frame_size(const SourceFrame& f, uint8_t y_ac_qi) {
+    size_t n = 0;
+    check(vp8gpu_encoder_estimate_frame_size(h_, f.y, f.y_stride, f.u, f.v, f.uv_stride, y_ac_qi, &n), ctx_.get(),
+          "estimate_frame_size");
+    return n;
   }
   // encode_with_minimum_ssim (encoder.cc:577-590)
   std::vector<uint8_t> encode_with_minimum_ssim(const SourceFrame& f, double minimum_ssim) {

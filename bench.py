@@ -33,7 +33,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-STREAMS = {"medium": "synth1080p_medium_q90.ivf", "easy": "synth1080p_easy_q40.ivf"}
+STREAMS = {"medium": "synth1080p_medium_q90.ivf", "easy": "synth1080p_easy_q40.ivf",
+           "720p": "synth720p_medium_q90.ivf"}   # 720p: BASELINE.json config 5 (--gop-instances 64 = 64 streams in lock-step)
 REF_DUMP = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
 
 
@@ -142,7 +143,7 @@ def run_reference_arm(a, rank, world):
         "impl": "reference", "metric": "decode_throughput", "value": v, "unit": "Mpix/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": statistics.mean(walls) * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "1080p30 IVF decode (%s), reference CPU decoder, C++ fallback build (no yasm)" % STREAMS[a.workload]},
+        "config": {"workload": "IVF decode (%s), reference CPU decoder, C++ fallback build (no yasm)" % STREAMS[a.workload]},
         "cpu_baseline": {"value": v, "unit": "Mpix/s", "cores": cores, "kind": "reference", "sample": sample, "usable_cpus": effective_cpus()},
         "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -507,8 +508,8 @@ def main():
             "metric": "decode_throughput", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "1080p30 IVF decode, %s (reference-encoder synthetic 1080p, 2 GOPs x 30 frames), "
-                                   "%d GOP instances per GPU advanced in lock-step, records resident in HBM" % (STREAMS[a.workload], G),
+            "config": {"workload": "%dx%d IVF decode, %s (reference-encoder synthetic clip, 2 GOPs x 30 frames), "
+                                   "%d GOP instances per GPU advanced in lock-step, records resident in HBM" % (w, h, STREAMS[a.workload], G),
                        "frames_per_step": frames_per_step, "l2": "working set %.0f MB per step > 126 MB L2, no flush needed"
                        % (frames_per_step * 3.1), "e2e_frames_per_step": n_e2e_frames, "e2e_host_threads": threads,
                        "bit_exact": "tests/test_gpu_parity.py (53/53 golden SHA-1 + per-frame oracle)"},

@@ -291,6 +291,11 @@ int vp8gpu_decoder_set_device_tokens(vp8gpu_decoder* d, int on);
 vp8gpu_state* vp8gpu_decoder_state(vp8gpu_decoder* d);            /* get_state (borrowed) */
 int vp8gpu_decoder_references(const vp8gpu_decoder* d, vp8gpu_frame_id refs[3]); /* borrowed */
 int vp8gpu_decoder_lane(const vp8gpu_decoder* d);
+/* Decoder::get_hash (decoder.hh:279-292, DecoderHash): one value over the state and the contents of the
+ * three reference rasters (hashed on the device; the value is this library's, not boost's) -- equal
+ * decoders hash equally, which is what the reference uses it for (frame-graph bookkeeping, minihash
+ * fields of IVF frames).  minihash = its 32-bit fold. */
+int vp8gpu_decoder_hash(vp8gpu_decoder* d, uint64_t* out);
 /* Decoder::operator== (decoder.cc:153): state equal and the three rasters pixel-equal. */
 int vp8gpu_decoder_equal(vp8gpu_decoder* a, vp8gpu_decoder* b, int* equal);
 
@@ -367,6 +372,11 @@ int vp8gpu_encoder_encode_with_target_size(vp8gpu_encoder* enc, const uint8_t* y
 int vp8gpu_encoder_encode_with_minimum_ssim(vp8gpu_encoder* enc, const uint8_t* y, size_t y_stride, const uint8_t* u,
                                             const uint8_t* v, size_t uv_stride, double minimum_ssim, uint8_t* out,
                                             size_t cap, size_t* size, int* chosen_qi);
+/* Encoder::estimate_frame_size (encoder.hh:376, size_estimation.cc): the size in bytes the frame would
+ * have at quantiser index y_ac_qi.  The reference estimates it from a 1/16 sample of the macroblocks;
+ * here it is the exact size of a full device pass.  Does not change the encoder's state. */
+int vp8gpu_encoder_estimate_frame_size(vp8gpu_encoder* enc, const uint8_t* y, size_t y_stride, const uint8_t* u,
+                                       const uint8_t* v, size_t uv_stride, int y_ac_qi, size_t* size);
 /* EncoderStats (encoder.hh:118-127) of the last frame; any pointer may be NULL. */
 int vp8gpu_encoder_stats(const vp8gpu_encoder* enc, double* ssim, int* loop_filter_level, int* y_ac_qi);
 /* the reconstruction of the last encoded frame = the decoder's LAST reference after decoding it

@@ -163,8 +163,16 @@ def test_loop_filter_choice_and_minimum_ssim():
         for g, w_ in zip(rec.planes(), want["planes"]):
             assert np.array_equal(g, w_)
         rec.release()
-    # minimum SSIM: reached, and one step coarser would not reach it (checked with a twin encoder state)
+    # estimate_frame_size: exact, and leaves the encoder untouched
     y, u, v = synth(w, h, 4)
+    before = enc.stats()
+    est = enc.estimate_frame_size(y, u, v, 50)
+    assert enc.stats() == before
+    twin_blob = enc.encode_with_quantizer(y, u, v, 50)
+    assert len(twin_blob) == est
+    od.decode(twin_blob)
+    # minimum SSIM: reached, and one step coarser would not reach it (checked with a twin encoder state)
+    y, u, v = synth(w, h, 5)
     target = 0.93
     blob, qi = enc.encode_with_minimum_ssim(y, u, v, target)
     st = enc.stats()

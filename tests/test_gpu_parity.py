@@ -157,7 +157,8 @@ def test_errors_mirror_reference_exception_classes():
 
 @pytest.mark.parametrize("device_tokens", [False, True])
 @pytest.mark.parametrize("name,threads", [("synth1080p_medium_q90.ivf", 8), ("synth1080p_easy_q40.ivf", 3),
-                                          ("synth4k_medium_q90_8f.ivf", 2), ("features1080p_12f.ivf", 1)])
+                                          ("synth4k_medium_q90_8f.ivf", 2), ("features1080p_12f.ivf", 1),
+                                          ("synth720p_medium_q90.ivf", 2)])
 def test_full_size_clips_match_reference_decode(name, threads, device_tokens):
     """BASELINE.json sizes (1080p bench workload, 4K, and the feature-complete 1080p stream of
     tools/make_feature_stream.py): GPU decode through vp8gpu_decode_ivf vs the SHA-1 of the unmodified
@@ -202,6 +203,29 @@ def test_many_independent_720p_streams_in_one_batch():
     for out, want in zip(outs, wants):
         assert all(np.array_equal(g, w_) for g, w_ in zip(out.planes(), want))
         out.release()
+    ctx.close()
+
+
+def test_decoder_hash_follows_equality():
+    """Decoder::get_hash / minihash: copies and independently built equal decoders hash equally, a diverged
+    decoder does not (decoder.hh:279-292)"""
+    from alfalfa_b200 import Context, Decoder
+    data = _read("0b546dad90ddefea5085c7751b5fa2f117630b1c")
+    w, h, frames = O.read_ivf(data)
+    ctx = Context(w, h, max_frames=32)
+    a, b = Decoder(ctx), Decoder(ctx)
+    assert a.get_hash() == b.get_hash()
+    for f in frames[:6]:
+        a.get_frame_output(f)[1].release()
+    assert a.get_hash() != b.get_hash()
+    for f in frames[:6]:
+        b.get_frame_output(f)[1].release()
+    assert a == b and a.get_hash() == b.get_hash() and a.minihash() == b.minihash()
+    c = a.copy()
+    assert c.get_hash() == a.get_hash()
+    c.get_frame_output(frames[6])[1].release()
+    assert c.get_hash() != a.get_hash()
+    del a, b, c
     ctx.close()
 
 

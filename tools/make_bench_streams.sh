@@ -10,6 +10,7 @@ make -C oracle -j8 ref >/dev/null
 mkdir -p bench_data
 oracle/_ref/ref_encode bench_data/synth1080p_medium_q90.ivf 1920 1080 60 30 90 1234 2 2>/dev/null
 oracle/_ref/ref_encode bench_data/synth1080p_easy_q40.ivf 1920 1080 60 30 40 1234 0 2>/dev/null
+oracle/_ref/ref_encode bench_data/synth720p_medium_q90.ivf 1280 720 60 30 90 4321 2 2>/dev/null   # BASELINE.json config 5 (64 x 720p)
 ls -la bench_data
 # short 4K clip (BASELINE.json config 4 parity case) and the reference's own answers for all clips
 oracle/_ref/ref_encode bench_data/synth4k_medium_q90_8f.ivf 3840 2160 8 4 90 77 2 2>/dev/null
