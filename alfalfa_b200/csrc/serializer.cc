@@ -79,44 +79,45 @@ const uint8_t kSplitCount[4] = {2, 2, 4, 16};
 const uint8_t kBand[16] = {0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7};
 const uint8_t kZigzag[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
 
-// write `value` with the tree the decoder walks (inverse of tree.cc:35-57)
-bool write_tree_from(BoolWriter& bw, const int8_t* nodes, const uint8_t* probs, int value, int i) {
-  for (int b = 0; b < 2; b++) {
-    const int n = nodes[i + b];
-    if (n <= 0) {
-      if (-n == value) {
-        bw.put(b, probs[i >> 1]);
-        return true;
-      }
-    } else {
-      // look ahead without writing: find out whether the value is below this child
-      struct Probe {
-        static bool has(const int8_t* nd, int at, int v) {
-          for (int k = 0; k < 2; k++) {
-            const int m = nd[at + k];
-            if (m <= 0 ? -m == v : has(nd, m, v)) return true;
-          }
-          return false;
-        }
-      };
-      if (Probe::has(nodes, n, value)) {
-        bw.put(b, probs[i >> 1]);
-        return write_tree_from(bw, nodes, probs, value, n);
+// write `value` with the tree the decoder walks (inverse of tree.cc:35-57).  The path to every leaf
+// is looked up once per tree (the trees are the handful of constant arrays above) and cached.
+struct TreePaths {
+  // per leaf value: up to 8 steps of (probability index, bit)
+  uint8_t len[32] = {0};
+  uint8_t prob_index[32][8];
+  uint8_t bit[32][8];
+  void build(const int8_t* nodes, int at, uint8_t* pi, uint8_t* bi, int depth) {
+    for (int b = 0; b < 2; b++) {
+      pi[depth] = static_cast<uint8_t>(at >> 1);
+      bi[depth] = static_cast<uint8_t>(b);
+      const int n = nodes[at + b];
+      if (n <= 0) {
+        const int v = -n;
+        len[v] = static_cast<uint8_t>(depth + 1);
+        memcpy(prob_index[v], pi, depth + 1);
+        memcpy(bit[v], bi, depth + 1);
+      } else {
+        build(nodes, n, pi, bi, depth + 1);
       }
     }
   }
-  return false;
+  explicit TreePaths(const int8_t* nodes) {
+    uint8_t pi[8], bi[8];
+    build(nodes, 0, pi, bi, 0);
+  }
+};
+inline void write_path(BoolWriter& bw, const TreePaths& t, const uint8_t* probs, int value) {
+  for (int k = 0; k < t.len[value]; k++) bw.put(t.bit[value][k], probs[t.prob_index[value][k]]);
 }
-inline void write_tree(BoolWriter& bw, const int8_t* nodes, const uint8_t* probs, int value) {
-  write_tree_from(bw, nodes, probs, value, 0);
-}
+const TreePaths kKfYModePaths(kKfYModeTree), kYModePaths(kYModeTree), kUvModePaths(kUvModeTree), kBModePaths(kBModeTree),
+    kSmallMvPaths(kSmallMvTree), kMvRefPaths(kMvRefTree), kSubMvPaths(kSubMvTree), kSplitPaths(kSplitTree);
 
 // inverse of MotionVector::read_component (macroblock.cc:198-229); v in 1/8 pel, luma values even
 void write_mv_component(BoolWriter& bw, int v, const uint8_t* p) {
   const int a = abs(v) >> 1;
   if (a < 8) {
     bw.put(0, p[0]);
-    write_tree(bw, kSmallMvTree, p + 2, a);
+    write_path(bw, kSmallMvPaths, p + 2, a);
   } else {
     bw.put(1, p[0]);
     for (int i = 0; i < 3; i++) bw.put((a >> i) & 1, p[9 + i]);
@@ -186,18 +187,13 @@ inline uint8_t implied_bmode(int y_mode) {
   return t[y_mode];
 }
 
-// one arithmetic-coded decision of the token partition, recorded first so that branch statistics
-// can choose the frame's probabilities before anything is written
-struct TokenBit {
-  uint16_t slot;  // index into the 1056-entry coefficient probability table, or 0xFFFF
-  uint8_t fixed;  // probability when slot == 0xFFFF
-  uint8_t bit;
-};
-
+// One arithmetic-coded decision of the token partition, recorded first so that branch statistics can
+// choose the frame's probabilities before anything is written: (slot << 1) | bit, where slot < 1056
+// indexes the coefficient probability table and 1056 + p stands for the fixed probability p.
 struct TokenRecorder {
-  std::vector<TokenBit> bits;
-  void coef(int slot, int bit) { bits.push_back({static_cast<uint16_t>(slot), 0, static_cast<uint8_t>(bit)}); }
-  void fixed(int prob, int bit) { bits.push_back({0xFFFF, static_cast<uint8_t>(prob), static_cast<uint8_t>(bit)}); }
+  std::vector<uint16_t> bits;
+  void coef(int slot, int bit) { bits.push_back(static_cast<uint16_t>((slot << 1) | bit)); }
+  void fixed(int prob, int bit) { bits.push_back(static_cast<uint16_t>(((1056 + prob) << 1) | bit)); }
 };
 
 void put_extra(TokenRecorder& t, int v, const uint8_t* probs, int n) {
@@ -303,11 +299,13 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
 
   // ---- pass 1: token partition decisions + per-macroblock skip flags ----
   TokenRecorder rec;
-  rec.bits.reserve(n_mbs * 64);
+  rec.bits.reserve(n_mbs * 160);
   std::vector<uint8_t> above_nz(static_cast<size_t>(cols) * 9, 0);
   std::vector<uint8_t> skip(n_mbs, 0);
   size_t n_skipped = 0;
   std::vector<size_t> row_start(static_cast<size_t>(rows) + 1, 0);
+  int16_t c[25][16];  // coefficients of the current macroblock, raster order; all zero between macroblocks
+  memset(c, 0, sizeof(c));
   for (int row = 0; row < rows; row++) {
     uint8_t left_nz[9] = {0};
     row_start[row] = rec.bits.size();
@@ -324,23 +322,32 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
         if (has_y2) a[8] = left_nz[8] = 0;
         continue;
       }
-      int16_t c[25][16];
-      memset(c, 0, sizeof(c));
+      // scatter the tokens; only blocks that received one are walked in full (and cleared afterwards)
+      uint32_t touched = 0;
       for (unsigned t = 0; t < mb.tok_cnt; t++) {
         const uint32_t tk = tokens[mb.tok_off + t];
-        c[(tk >> 20) & 31][(tk >> 16) & 15] = static_cast<int16_t>(tk & 0xFFFF);
+        const unsigned blk = (tk >> 20) & 31, pos = (tk >> 16) & 15;
+        if (blk > 24) return {};
+        c[blk][pos] = static_cast<int16_t>(tk & 0xFFFF);
+        touched |= 1u << blk;
       }
-      if (has_y2) a[8] = left_nz[8] = static_cast<uint8_t>(record_block(rec, c[24], 1, a[8] + left_nz[8], 0));
+      auto block = [&](int blk, int type, int ctx, int first) -> uint8_t {
+        if (touched >> blk & 1) return static_cast<uint8_t>(record_block(rec, c[blk], type, ctx, first));
+        rec.coef(((type * 8 + kBand[first]) * 3 + ctx) * 11, 0);  // immediate end of block
+        return 0;
+      };
+      if (has_y2) a[8] = left_nz[8] = block(24, 1, a[8] + left_nz[8], 0);
       const int ytype = has_y2 ? 0 : 3, yfirst = has_y2 ? 1 : 0;
       for (int i = 0; i < 16; i++) {
         const int bx = i & 3, by = i >> 2;
-        a[bx] = left_nz[by] = static_cast<uint8_t>(record_block(rec, c[i], ytype, a[bx] + left_nz[by], yfirst));
+        a[bx] = left_nz[by] = block(i, ytype, a[bx] + left_nz[by], yfirst);
       }
       for (int pl = 0; pl < 2; pl++)
         for (int i = 0; i < 4; i++) {
           const int bx = 4 + 2 * pl + (i & 1), by = 4 + 2 * pl + (i >> 1);
-          a[bx] = left_nz[by] = static_cast<uint8_t>(record_block(rec, c[16 + 4 * pl + i], 2, a[bx] + left_nz[by], 0));
+          a[bx] = left_nz[by] = block(16 + 4 * pl + i, 2, a[bx] + left_nz[by], 0);
         }
+      for (uint32_t m = touched; m; m &= m - 1) memset(c[__builtin_ctz(m)], 0, sizeof(c[0]));
     }
   }
 
@@ -353,8 +360,8 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
   std::vector<uint8_t> updated(1056, 0);
   if (h.optimize_token_probs) {
     std::vector<uint32_t> cnt(2 * 1056, 0);
-    for (const TokenBit& b : rec.bits)
-      if (b.slot != 0xFFFF) cnt[2 * b.slot + b.bit]++;
+    for (const uint16_t b : rec.bits)
+      if (b < 2 * 1056) cnt[b]++;
     for (int i = 0; i < 1056; i++) {
       const uint32_t total = cnt[2 * i] + cnt[2 * i + 1];
       if (!total) continue;
@@ -489,24 +496,24 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
       if (mb.ref_frame == VP8GPU_REF_CURRENT) {
         if (!h.key_frame) bw.put(0, prob_inter);
         if (h.key_frame) {
-          write_tree(bw, kKfYModeTree, k_kf_ymode_probs, mb.y_mode);
+          write_path(bw, kKfYModePaths, k_kf_ymode_probs, mb.y_mode);
           for (int i = 0; i < 16; i++) {
             if (mb.y_mode == VP8GPU_B_PRED) {
               const int m = static_cast<int>((mb.b_modes >> (4 * i)) & 15);
               const int am = i >= 4 ? me.bm[i - 4] : (above ? above->bm[12 + (i & 3)] : VP8GPU_B_DC_PRED);
               const int lm = (i & 3) ? me.bm[i - 1] : (left ? left->bm[((i >> 2) & 3) * 4 + 3] : VP8GPU_B_DC_PRED);
-              write_tree(bw, kBModeTree, k_kf_bmode_probs + (am * 10 + lm) * 9, m);
+              write_path(bw, kBModePaths, k_kf_bmode_probs + (am * 10 + lm) * 9, m);
               me.bm[i] = static_cast<uint8_t>(m);
             } else {
               me.bm[i] = implied_bmode(mb.y_mode);
             }
           }
-          write_tree(bw, kUvModeTree, k_kf_uvmode_probs, mb.uv_mode);
+          write_path(bw, kUvModePaths, k_kf_uvmode_probs, mb.uv_mode);
         } else {
-          write_tree(bw, kYModeTree, k_ymode_default_probs, mb.y_mode);
+          write_path(bw, kYModePaths, k_ymode_default_probs, mb.y_mode);
           if (mb.y_mode == VP8GPU_B_PRED)
-            for (int i = 0; i < 16; i++) write_tree(bw, kBModeTree, k_bmode_probs, static_cast<int>((mb.b_modes >> (4 * i)) & 15));
-          write_tree(bw, kUvModeTree, k_uvmode_default_probs, mb.uv_mode);
+            for (int i = 0; i < 16; i++) write_path(bw, kBModePaths, k_bmode_probs, static_cast<int>((mb.b_modes >> (4 * i)) & 15));
+          write_path(bw, kUvModePaths, k_uvmode_default_probs, mb.uv_mode);
         }
         continue;
       }
@@ -550,8 +557,8 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
             break;
           }
         }
-        write_tree(bw, kMvRefTree, ref_probs, VP8GPU_SPLITMV);
-        write_tree(bw, kSplitTree, k_split_probs, layout);
+        write_path(bw, kMvRefPaths, ref_probs, VP8GPU_SPLITMV);
+        write_path(bw, kSplitPaths, k_split_probs, layout);
         int16_t done[16][2];  // vectors as the decoder knows them so far
         memset(done, 0, sizeof(done));
         for (int part = 0; part < kSplitCount[layout]; part++) {
@@ -570,11 +577,11 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
           else if (lz) ctx = 1;
           const int vx = mv[first][0], vy = mv[first][1];
           const uint8_t* sp = k_submv_ref_probs + ctx * 3;
-          if (vx == lx && vy == ly) write_tree(bw, kSubMvTree, sp, kSubLeft);
-          else if (vx == ax && vy == ay) write_tree(bw, kSubMvTree, sp, kSubAbove);
-          else if ((vx | vy) == 0) write_tree(bw, kSubMvTree, sp, kSubZero);
+          if (vx == lx && vy == ly) write_path(bw, kSubMvPaths, sp, kSubLeft);
+          else if (vx == ax && vy == ay) write_path(bw, kSubMvPaths, sp, kSubAbove);
+          else if ((vx | vy) == 0) write_path(bw, kSubMvPaths, sp, kSubZero);
           else {
-            write_tree(bw, kSubMvTree, sp, kSubNew);
+            write_path(bw, kSubMvPaths, sp, kSubNew);
             const int dx = vx - best.x, dy = vy - best.y;
             if (abs(dx) > 2046 || abs(dy) > 2046) return {};
             write_mv_component(bw, dy, mv_probs[0]);
@@ -595,7 +602,7 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
         else if (vx == near.x && vy == near.y) mode = VP8GPU_NEARMV;
         else mode = VP8GPU_NEWMV;
         me.y_mode = static_cast<uint8_t>(mode);
-        write_tree(bw, kMvRefTree, ref_probs, mode);
+        write_path(bw, kMvRefPaths, ref_probs, mode);
         if (mode == VP8GPU_NEWMV) {
           const int dx = vx - best.x, dy = vy - best.y;
           if (abs(dx) > 2046 || abs(dy) > 2046 || (dx & 1) || (dy & 1)) return {};
@@ -613,12 +620,16 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
 
   // ---- token partitions: row r goes to partition r % n (frame.cc:131-136) ----
   std::vector<std::vector<uint8_t>> parts(nparts);
+  uint8_t prob_of_slot[1056 + 256];
+  memcpy(prob_of_slot, coef_probs, 1056);
+  for (int p = 0; p < 256; p++) prob_of_slot[1056 + p] = static_cast<uint8_t>(p);
   for (int p = 0; p < nparts; p++) {
     BoolWriter tw;
+    tw.reserve((row_start[rows] - row_start[0]) / (4 * nparts) + 64);
     for (int row = p; row < rows; row += nparts)
       for (size_t k = row_start[row]; k < row_start[row + 1]; k++) {
-        const TokenBit& b = rec.bits[k];
-        tw.put(b.bit, b.slot == 0xFFFF ? b.fixed : coef_probs[b.slot]);
+        const uint16_t b = rec.bits[k];
+        tw.put(b & 1, prob_of_slot[b >> 1]);
       }
     parts[p] = tw.finish();
   }

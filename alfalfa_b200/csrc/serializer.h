@@ -57,6 +57,7 @@ class BoolWriter {
   void literal(int value, int width);
   std::vector<uint8_t> finish();
   size_t size_estimate() const { return out_.size(); }
+  void reserve(size_t bytes) { out_.reserve(bytes); }
 
  private:
   void add_one();
