@@ -789,7 +789,11 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     cudaEvent_t ready = nullptr;
     cudaEvent_t* finished = nullptr;  // where submit() leaves the event that fires after the pixel kernels
   };
-  const int n_disp = device_tokens ? (threads >= 32 ? 4 : (threads >= 8 ? 2 : 1)) : 1;
+  int n_disp = device_tokens ? (threads >= 32 ? 4 : (threads >= 8 ? 2 : 1)) : 1;
+  if (const char* v = getenv("VP8GPU_DISPATCHERS")) {  // tuning knob
+    const int n = atoi(v);
+    if (n >= 1 && n <= 16 && n <= threads) n_disp = n;
+  }
   std::mutex mu;
   std::condition_variable cv_workers;
   std::vector<std::condition_variable> cv_disp(n_disp);
