@@ -13,7 +13,7 @@ $NVCC $ARCH $FLAGS -c engine.cu -o build/engine.o
 $NVCC $FLAGS -x cu $ARCH -c capi.cc -o build/capi.o
 $NVCC $ARCH $FLAGS -c encoder.cu -o build/encoder.o
 g++ -O3 -std=c++17 -fPIC -Wall -Wextra -c parser.cc -o build/parser.o
-g++ -O3 -std=c++17 -fPIC -Wall -Wextra -c serializer.cc -o build/serializer.o
+g++ -O3 -std=c++17 -fPIC -Wall -Wextra -pthread -c serializer.cc -o build/serializer.o
 $NVCC $ARCH -shared -o ../libvp8gpu.so build/kernels.o build/tokens.o build/engine.o build/capi.o build/encoder.o build/parser.o build/serializer.o -Xcompiler -pthread
 echo "built $(cd .. && pwd)/libvp8gpu.so"
 # optional: phase-profiling variant of the library (tools/phase_profile.py)

@@ -151,7 +151,11 @@ int encode_bytes(vp8gpu_encoder* enc, bool key, int qi, int lf_level, std::vecto
   h.loop_filter_level = lf_level;
   h.sharpness = 0;
   h.optimize_token_probs = true;
-  bytes = vp8::serialize_frame(h, enc->h_mbs, enc->h_tokens, nullptr);
+  // eight DCT partitions (row r -> partition r % 8, frame.cc:131-136): the writer records and codes them
+  // on eight host threads, which is most of the host time of an encoding pass
+  vp8::EncodeFeatures ft;
+  ft.log2_partitions = (h.height + 15) / 16 >= 16 ? 3 : 0;
+  bytes = vp8::serialize_frame(h, enc->h_mbs, enc->h_tokens, nullptr, &ft);
   if (bytes.empty()) return e->fail(VP8GPU_ERR_LOGIC, "serializer rejected the device records");
   return VP8GPU_OK;
 }

@@ -9,6 +9,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <thread>
+
 #include "vp8_tables.h"
 
 namespace vp8 {
@@ -297,61 +299,101 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
   const size_t n_mbs = static_cast<size_t>(cols) * rows;
   std::vector<MbInfo> info(n_mbs);
 
-  // ---- pass 1: token partition decisions + per-macroblock skip flags ----
-  TokenRecorder rec;
-  rec.bits.reserve(n_mbs * 160);
-  std::vector<uint8_t> above_nz(static_cast<size_t>(cols) * 9, 0);
+  // ---- pass 0 (serial, cheap): which blocks of every macroblock hold a non-zero coefficient, and from
+  //      that the "above" token contexts of every macroblock.  The Y2 context of a column / row is the
+  //      last macroblock WITH a Y2 block (frame.cc:252-269), so it is carried through, not looked up. ----
+  std::vector<uint32_t> nzmask(n_mbs, 0);
+  std::vector<uint16_t> above_ctx(n_mbs, 0);  // bits 0-3 Y, 4-5 U, 6-7 V, 8 Y2
   std::vector<uint8_t> skip(n_mbs, 0);
   size_t n_skipped = 0;
-  std::vector<size_t> row_start(static_cast<size_t>(rows) + 1, 0);
-  int16_t c[25][16];  // coefficients of the current macroblock, raster order; all zero between macroblocks
-  memset(c, 0, sizeof(c));
-  for (int row = 0; row < rows; row++) {
-    uint8_t left_nz[9] = {0};
-    row_start[row] = rec.bits.size();
-    for (int col = 0; col < cols; col++) {
-      const size_t idx = static_cast<size_t>(row) * cols + col;
+  {
+    std::vector<uint16_t> above(static_cast<size_t>(cols), 0);
+    for (size_t idx = 0; idx < n_mbs; idx++) {
       const vp8gpu_mb& mb = mbs[idx];
-      uint8_t* a = &above_nz[static_cast<size_t>(col) * 9];
       const bool has_y2 = mb.y_mode != VP8GPU_B_PRED && mb.y_mode != VP8GPU_SPLITMV;
-      if (mb.tok_cnt == 0) {
-        skip[idx] = 1;
-        n_skipped++;
-        memset(a, 0, 8);
-        memset(left_nz, 0, 8);
-        if (has_y2) a[8] = left_nz[8] = 0;
-        continue;
-      }
-      // scatter the tokens; only blocks that received one are walked in full (and cleared afterwards)
-      uint32_t touched = 0;
+      uint32_t m = 0;
       for (unsigned t = 0; t < mb.tok_cnt; t++) {
         const uint32_t tk = tokens[mb.tok_off + t];
         const unsigned blk = (tk >> 20) & 31, pos = (tk >> 16) & 15;
         if (blk > 24) return {};
-        c[blk][pos] = static_cast<int16_t>(tk & 0xFFFF);
-        touched |= 1u << blk;
+        if ((tk & 0xFFFF) && !(has_y2 && blk < 16 && pos == 0)) m |= 1u << blk;
       }
-      auto block = [&](int blk, int type, int ctx, int first) -> uint8_t {
-        if (touched >> blk & 1) return static_cast<uint8_t>(record_block(rec, c[blk], type, ctx, first));
-        rec.coef(((type * 8 + kBand[first]) * 3 + ctx) * 11, 0);  // immediate end of block
-        return 0;
-      };
-      if (has_y2) a[8] = left_nz[8] = block(24, 1, a[8] + left_nz[8], 0);
-      const int ytype = has_y2 ? 0 : 3, yfirst = has_y2 ? 1 : 0;
-      for (int i = 0; i < 16; i++) {
-        const int bx = i & 3, by = i >> 2;
-        a[bx] = left_nz[by] = block(i, ytype, a[bx] + left_nz[by], yfirst);
+      nzmask[idx] = m;
+      uint16_t& a = above[idx % cols];
+      above_ctx[idx] = a;
+      if (mb.tok_cnt == 0) {
+        skip[idx] = 1;
+        n_skipped++;
+        a = has_y2 ? 0 : static_cast<uint16_t>(a & 0x100);
+        continue;
       }
-      for (int pl = 0; pl < 2; pl++)
-        for (int i = 0; i < 4; i++) {
-          const int bx = 4 + 2 * pl + (i & 1), by = 4 + 2 * pl + (i >> 1);
-          a[bx] = left_nz[by] = block(16 + 4 * pl + i, 2, a[bx] + left_nz[by], 0);
-        }
-      for (uint32_t m = touched; m; m &= m - 1) memset(c[__builtin_ctz(m)], 0, sizeof(c[0]));
+      // bottom row of Y blocks (12-15), bottom blocks of U (18, 19) and V (22, 23), Y2
+      uint16_t na = static_cast<uint16_t>(((m >> 12) & 15) | (((m >> 18) & 3) << 4) | (((m >> 22) & 3) << 6));
+      na |= has_y2 ? static_cast<uint16_t>(((m >> 24) & 1) << 8) : static_cast<uint16_t>(a & 0x100);
+      a = na;
     }
   }
 
-  row_start[rows] = rec.bits.size();
+  // ---- pass 1: the decisions of the token partitions.  Row r belongs to partition r % n
+  //      (frame.cc:131-136) and, given the above contexts, rows are independent: one recorder (and, with
+  //      more than one partition, one thread) per partition ----
+  struct PartWork {
+    TokenRecorder rec;
+    std::vector<uint32_t> cnt;
+    std::vector<uint8_t> bytes;
+  };
+  std::vector<PartWork> work(nparts);
+  auto record_partition = [&](int p) {
+    PartWork& W = work[p];
+    W.rec.bits.reserve(n_mbs * 160 / nparts + 1024);
+    W.cnt.assign(2 * (1056 + 256), 0);
+    int16_t c[25][16];  // coefficients of the current macroblock, raster order; all zero between macroblocks
+    memset(c, 0, sizeof(c));
+    for (int row = p; row < rows; row += nparts) {
+      unsigned left = 0;  // same bit layout as above_ctx
+      for (int col = 0; col < cols; col++) {
+        const size_t idx = static_cast<size_t>(row) * cols + col;
+        const vp8gpu_mb& mb = mbs[idx];
+        const bool has_y2 = mb.y_mode != VP8GPU_B_PRED && mb.y_mode != VP8GPU_SPLITMV;
+        if (mb.tok_cnt == 0) {
+          left = has_y2 ? 0 : (left & 0x100);
+          continue;
+        }
+        const uint32_t m = nzmask[idx];
+        for (unsigned t = 0; t < mb.tok_cnt; t++) {
+          const uint32_t tk = tokens[mb.tok_off + t];
+          c[(tk >> 20) & 31][(tk >> 16) & 15] = static_cast<int16_t>(tk & 0xFFFF);
+        }
+        unsigned a = above_ctx[idx];
+        auto block = [&](int blk, int type, int bx, int by, int first) {
+          const int ctx = ((a >> bx) & 1) + ((left >> by) & 1);
+          unsigned nz = 0;
+          if (m >> blk & 1) nz = static_cast<unsigned>(record_block(W.rec, c[blk], type, ctx, first));
+          else W.rec.coef(((type * 8 + kBand[first]) * 3 + ctx) * 11, 0);  // immediate end of block
+          a = (a & ~(1u << bx)) | (nz << bx);
+          left = (left & ~(1u << by)) | (nz << by);
+        };
+        if (has_y2) block(24, 1, 8, 8, 0);
+        const int ytype = has_y2 ? 0 : 3, yfirst = has_y2 ? 1 : 0;
+        for (int i = 0; i < 16; i++) block(i, ytype, i & 3, i >> 2, yfirst);
+        for (int pl = 0; pl < 2; pl++)
+          for (int i = 0; i < 4; i++) block(16 + 4 * pl + i, 2, 4 + 2 * pl + (i & 1), 4 + 2 * pl + (i >> 1), 0);
+        for (unsigned t = 0; t < mb.tok_cnt; t++) {
+          const uint32_t tk = tokens[mb.tok_off + t];
+          c[(tk >> 20) & 31][(tk >> 16) & 15] = 0;
+        }
+      }
+    }
+    for (const uint16_t bit : W.rec.bits) W.cnt[bit]++;
+  };
+  const bool threaded = nparts > 1 && n_mbs >= 1024;
+  {
+    std::vector<std::thread> th;
+    for (int p = 1; p < nparts && threaded; p++) th.emplace_back(record_partition, p);
+    record_partition(0);
+    for (int p = 1; p < nparts && !threaded; p++) record_partition(p);
+    for (auto& t : th) t.join();
+  }
 
   // ---- frame probabilities ----
   uint8_t coef_probs[1056];
@@ -360,8 +402,8 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
   std::vector<uint8_t> updated(1056, 0);
   if (h.optimize_token_probs) {
     std::vector<uint32_t> cnt(2 * 1056, 0);
-    for (const uint16_t b : rec.bits)
-      if (b < 2 * 1056) cnt[b]++;
+    for (const PartWork& W : work)
+      for (int i = 0; i < 2 * 1056; i++) cnt[i] += W.cnt[i];
     for (int i = 0; i < 1056; i++) {
       const uint32_t total = cnt[2 * i] + cnt[2 * i + 1];
       if (!total) continue;
@@ -400,6 +442,30 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
       w.put(v < 0);
     }
   };
+
+  // ---- token partitions, written while this thread writes the first partition ----
+  uint8_t prob_of_slot[1056 + 256];
+  memcpy(prob_of_slot, coef_probs, 1056);
+  for (int p = 0; p < 256; p++) prob_of_slot[1056 + p] = static_cast<uint8_t>(p);
+  auto write_partition = [&](int p) {
+    PartWork& W = work[p];
+    BoolWriter tw;
+    tw.reserve(W.rec.bits.size() / 4 + 64);
+    for (const uint16_t b : W.rec.bits) tw.put(b & 1, prob_of_slot[b >> 1]);
+    W.bytes = tw.finish();
+  };
+  struct Joiner {  // every return path below waits for the writers
+    std::vector<std::thread> th;
+    void join() {
+      for (auto& t : th)
+        if (t.joinable()) t.join();
+    }
+    ~Joiner() { join(); }
+  } writers;
+  for (int p = 0; p < nparts; p++) {
+    if (threaded) writers.th.emplace_back(write_partition, p);
+    else write_partition(p);
+  }
 
   // ---- first partition: frame header ----
   BoolWriter bw;
@@ -618,21 +684,7 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
   }
   const std::vector<uint8_t> first = bw.finish();
 
-  // ---- token partitions: row r goes to partition r % n (frame.cc:131-136) ----
-  std::vector<std::vector<uint8_t>> parts(nparts);
-  uint8_t prob_of_slot[1056 + 256];
-  memcpy(prob_of_slot, coef_probs, 1056);
-  for (int p = 0; p < 256; p++) prob_of_slot[1056 + p] = static_cast<uint8_t>(p);
-  for (int p = 0; p < nparts; p++) {
-    BoolWriter tw;
-    tw.reserve((row_start[rows] - row_start[0]) / (4 * nparts) + 64);
-    for (int row = p; row < rows; row += nparts)
-      for (size_t k = row_start[row]; k < row_start[row + 1]; k++) {
-        const uint16_t b = rec.bits[k];
-        tw.put(b & 1, prob_of_slot[b >> 1]);
-      }
-    parts[p] = tw.finish();
-  }
+  writers.join();
 
   // ---- frame tag (uncompressed_chunk.cc:49-77 inverted) ----
   std::vector<uint8_t> out;
@@ -652,11 +704,11 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
   }
   out.insert(out.end(), first.begin(), first.end());
   for (int p = 0; p + 1 < nparts; p++) {  // partition sizes, all but the last (uncompressed_chunk.cc:132-155)
-    out.push_back(parts[p].size() & 0xFF);
-    out.push_back((parts[p].size() >> 8) & 0xFF);
-    out.push_back((parts[p].size() >> 16) & 0xFF);
+    out.push_back(work[p].bytes.size() & 0xFF);
+    out.push_back((work[p].bytes.size() >> 8) & 0xFF);
+    out.push_back((work[p].bytes.size() >> 16) & 0xFF);
   }
-  for (int p = 0; p < nparts; p++) out.insert(out.end(), parts[p].begin(), parts[p].end());
+  for (int p = 0; p < nparts; p++) out.insert(out.end(), work[p].bytes.begin(), work[p].bytes.end());
   return out;
 }
 
