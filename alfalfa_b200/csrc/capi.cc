@@ -1098,6 +1098,14 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
         }
       cudaStreamSynchronize(kit->copy_stream);
       for (cudaStream_t st : kit->kstream) cudaStreamSynchronize(st);
+      // k_tokens reports a token pool that was too small instead of writing out of bounds; the capacity
+      // rule (Engine::token_ring_layout) makes that impossible, so a set flag is an internal error
+      uint32_t res[kTokSlots][2];
+      if (cudaMemcpy2D(res, 8, kit->ring->dev + kit->ring->result_off, kit->ring->stride, 8, (size_t)kit->ring->nslots,
+                       cudaMemcpyDeviceToHost) == cudaSuccess) {
+        for (int k = 0; k < kit->ring->nslots && k < tok_slots; k++)
+          if (res[k][1]) set_error(e->fail(VP8GPU_ERR_LOGIC, "device token pool overflow"));
+      }
       std::lock_guard<std::mutex> lk(ctx->pool_mu);
       ctx->kit_pool.push_back(kit);
     }

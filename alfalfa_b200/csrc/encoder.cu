@@ -8,6 +8,7 @@
 // the reconstruction the encoder keeps as its LAST reference, which is what Encoder::export_decoder
 // (encoder.hh:378) promises.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -155,6 +156,7 @@ int encode_bytes(vp8gpu_encoder* enc, bool key, int qi, int lf_level, std::vecto
   // on eight host threads, which is most of the host time of an encoding pass
   vp8::EncodeFeatures ft;
   ft.log2_partitions = (h.height + 15) / 16 >= 16 ? 3 : 0;
+  if (const char* v = getenv("VP8GPU_ENC_LOG2_PARTS")) ft.log2_partitions = atoi(v) & 3;  // tuning knob
   bytes = vp8::serialize_frame(h, enc->h_mbs, enc->h_tokens, nullptr, &ft);
   if (bytes.empty()) return e->fail(VP8GPU_ERR_LOGIC, "serializer rejected the device records");
   return VP8GPU_OK;
