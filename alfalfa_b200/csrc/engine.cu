@@ -504,6 +504,8 @@ int Engine::token_ring_create(int nslots, size_t max_frame_bytes, TokenRing** ou
     token_ring_free(r);
     return fail(VP8GPU_ERR_NOMEM, "token ring allocation failed");
   }
+  // result words (tokens written, overflow flag) of slots that are never used must read as "fine"
+  CU(cudaMemset2D(r->dev + r->result_off, r->stride, 0, 8, (size_t)nslots));
   *out = r;
   return VP8GPU_OK;
 }
