@@ -48,6 +48,13 @@ struct vp8gpu_encoder {
   uint8_t* h_src = nullptr;      // padded planes
   uint32_t* h_count = nullptr;
   uint64_t stat_frames = 0;
+  // candidates of a quantiser search run as concurrent device passes: two more sets of buffers on their
+  // own lanes (created on first use); they read this encoder's source, LAST and motion vectors
+  vp8gpu_encoder* helper[2] = {nullptr, nullptr};
+  vp8gpu_encoder* owner = nullptr;   // set in a helper
+  cudaEvent_t motion_done = nullptr; // the motion search of the current source frame (owner's lane)
+  int pending_out = -1;              // output raster of a pass that has been launched but not collected
+  bool pending_key = false;
 };
 
 namespace {
@@ -71,35 +78,35 @@ vp8gpu_quant make_quant(int qi) {  // Quantizer::Quantizer, quantization.cc:83-9
     if (e__ != cudaSuccess) return enc->e->cuda_fail(e__, #call);       \
   } while (0)
 
-// One encoding pass at quantiser index qi: motion search (once per source frame), the mode-decision /
-// transform / reconstruction wavefront, records and tokens back on the host.  *out_frame = the
-// reconstruction BEFORE the loop filter (the caller releases it or keeps it as LAST).
-int encode_core(vp8gpu_encoder* enc, bool key, int qi, bool search_motion, int* out_frame) {
+// launch half of a pass: everything up to the asynchronous download of the token count and the records
+int encode_launch(vp8gpu_encoder* enc, bool key, int qi, bool search_motion) {
   Engine* e = enc->e;
   const vp8::Geom& g = e->geom();
   const size_t n_mbs = (size_t)g.mb_cols * g.mb_rows;
+  vp8gpu_encoder* own = enc->owner ? enc->owner : enc;  // whose source / LAST / vectors are used
+  if (int rc = e->ensure_lane(enc->lane)) return rc;
   cudaStream_t s = e->stream(enc->lane);
   int out = -1;
   int rc = e->frame_alloc(&out);
   if (rc != VP8GPU_OK) return rc;
-  int ids[3] = {enc->src, out, enc->last};
-  rc = e->acquire_frames(enc->lane, ids, key ? 2 : 3);
+  int ids[3] = {own->src, out, own->last};
+  rc = e->acquire_frames(enc->lane, ids, key ? 2 : 3, 2u);  // only `out` is written
   if (rc != VP8GPU_OK) {
     e->frame_release(out);
     return rc;
   }
   vp8::EncJob* ej = reinterpret_cast<vp8::EncJob*>(enc->h_hdr);
-  memset(enc->h_hdr, 0, 1024);
+  memset(enc->h_hdr, 0, 512);
   int* d_sync = reinterpret_cast<int*>(enc->dev + enc->off_sync);
-  ej->src = e->frame_dev(enc->src);
-  ej->ref = key ? nullptr : e->frame_dev(enc->last);
+  ej->src = e->frame_dev(own->src);
+  ej->ref = key ? nullptr : e->frame_dev(own->last);
   ej->out = e->frame_dev(out);
   ej->mbs = reinterpret_cast<vp8gpu_mb*>(enc->dev + enc->off_mbs);
   ej->tokens = reinterpret_cast<vp8gpu_token*>(enc->dev + enc->off_tokens);
   ej->tok_counter = reinterpret_cast<uint32_t*>(d_sync + 96);
   ej->tok_cap = enc->tok_cap;
-  ej->mv = reinterpret_cast<int*>(enc->dev + enc->off_mv);
-  ej->sad = reinterpret_cast<uint32_t*>(enc->dev + enc->off_sad);
+  ej->mv = reinterpret_cast<int*>(own->dev + own->off_mv);
+  ej->sad = reinterpret_cast<uint32_t*>(own->dev + own->off_sad);
   ej->progress = d_sync + 128;
   ej->q = make_quant(qi);
   ej->key_frame = key;
@@ -117,27 +124,60 @@ int encode_core(vp8gpu_encoder* enc, bool key, int qi, bool search_motion, int* 
   CUF(cudaMemsetAsync(d_sync, 0, sizeof(int) * (128 + 2 * (size_t)g.mb_rows), s));
   const vp8::EncJob* d_ej = reinterpret_cast<const vp8::EncJob*>(enc->dev + enc->off_encjob);
   int launches = 0;
-  if (!key && search_motion) {  // vectors do not depend on the quantiser: searched once per source frame
-    if (int ce = vp8::launch_enc_motion(d_ej, g, s)) return fail(e->cuda_fail((cudaError_t)ce, "k_enc_motion"));
-    launches++;
+  if (!key) {
+    if (search_motion) {  // vectors do not depend on the quantiser: searched once per source frame, by the owner
+      if (enc->owner) return fail(e->fail(VP8GPU_ERR_LOGIC, "motion search belongs to the owning encoder"));
+      if (int ce = vp8::launch_enc_motion(d_ej, g, s)) return fail(e->cuda_fail((cudaError_t)ce, "k_enc_motion"));
+      launches++;
+      if (!enc->motion_done) CUF(cudaEventCreateWithFlags(&enc->motion_done, cudaEventDisableTiming));
+      CUF(cudaEventRecord(enc->motion_done, s));
+    } else if (enc->owner && own->motion_done) {
+      CUF(cudaStreamWaitEvent(s, own->motion_done, 0));  // the vectors come from the owner's lane
+    }
   }
   if (int ce = vp8::launch_enc_mb(d_ej, g, d_sync + 0, s)) return fail(e->cuda_fail((cudaError_t)ce, "k_enc_mb"));
   launches++;
   e->count_launches(launches);
-  e->mark_frames(enc->lane, ids, key ? 2 : 3);
+  e->mark_frames(enc->lane, ids, key ? 2 : 3, 2u);
   // results back: token count first, then the records
   CUF(cudaMemcpyAsync(enc->h_count, ej->tok_counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   CUF(cudaMemcpyAsync(enc->h_mbs, ej->mbs, n_mbs * sizeof(vp8gpu_mb), cudaMemcpyDeviceToHost, s));
-  CUF(cudaStreamSynchronize(s));
+  enc->pending_out = out;
+  enc->pending_key = key;
+  return VP8GPU_OK;
+#undef CUF
+}
+
+// collect half: wait for the pass, fetch the tokens.  *out_frame = the reconstruction BEFORE the loop
+// filter (the caller releases it or keeps it as LAST).
+int encode_collect(vp8gpu_encoder* enc, int* out_frame) {
+  Engine* e = enc->e;
+  cudaStream_t s = e->stream(enc->lane);
+  const int out = enc->pending_out;
+  enc->pending_out = -1;
+  if (out < 0) return e->fail(VP8GPU_ERR_LOGIC, "encode_collect without a launched pass");
+  auto fail = [&](int code) {
+    e->frame_release(out);
+    return code;
+  };
+  cudaError_t ce = cudaStreamSynchronize(s);
+  if (ce != cudaSuccess) return fail(e->cuda_fail(ce, "encoder pass"));
   const uint32_t n_tok = *enc->h_count;
   if (n_tok > enc->tok_cap) return fail(e->fail(VP8GPU_ERR_NOMEM, "encoder token pool overflow"));
   if (n_tok) {
-    CUF(cudaMemcpyAsync(enc->h_tokens, ej->tokens, (size_t)n_tok * sizeof(vp8gpu_token), cudaMemcpyDeviceToHost, s));
-    CUF(cudaStreamSynchronize(s));
+    ce = cudaMemcpyAsync(enc->h_tokens, enc->dev + enc->off_tokens, (size_t)n_tok * sizeof(vp8gpu_token), cudaMemcpyDeviceToHost, s);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    if (ce != cudaSuccess) return fail(e->cuda_fail(ce, "encoder token download"));
   }
   *out_frame = out;
   return VP8GPU_OK;
-#undef CUF
+}
+
+// One encoding pass at quantiser index qi: motion search (once per source frame), the mode-decision /
+// transform / reconstruction wavefront, records and tokens back on the host.
+int encode_core(vp8gpu_encoder* enc, bool key, int qi, bool search_motion, int* out_frame) {
+  const int rc = encode_launch(enc, key, qi, search_motion);
+  return rc == VP8GPU_OK ? encode_collect(enc, out_frame) : rc;
 }
 
 // the compressed frame of the last encode_core pass
@@ -303,6 +343,11 @@ int vp8gpu_encoder_create(vp8gpu_ctx* ctx, vp8gpu_encoder** out) {
 
 void vp8gpu_encoder_destroy(vp8gpu_encoder* enc) {
   if (!enc) return;
+  for (vp8gpu_encoder*& hlp : enc->helper) {
+    vp8gpu_encoder_destroy(hlp);
+    hlp = nullptr;
+  }
+  if (enc->motion_done) cudaEventDestroy(enc->motion_done);
   cudaSetDevice(enc->e->device());
   cudaStreamSynchronize(enc->e->stream(enc->lane));
   if (enc->last >= 0) enc->e->frame_release(enc->last);
@@ -375,26 +420,68 @@ int vp8gpu_encoder_encode_with_target_size(vp8gpu_encoder* enc, const uint8_t* y
     if (enc->last_qi - 16 >= lo) lo = enc->last_qi - 16;
     if (enc->last_qi + 16 < hi) hi = enc->last_qi + 16;
   }
+  // Candidates run three at a time as concurrent device passes (this encoder's buffers and two helpers' on
+  // their own lanes; the wavefront kernel is latency bound, so three cost about as much as one): the range
+  // shrinks to a quarter per round instead of a half.  Sizes fall as the index rises, which is also what
+  // the reference's bisection relies on, so the answer is the same: the smallest index that fits, or the
+  // top of the range if none does.
   int best = -1;
+  const int top = hi;
   std::vector<uint8_t> bytes;
   const bool key = !enc->has_state;
-  bool first_probe = true;
+  bool first_round = true;
+  for (int k = 0; k < 2; k++)
+    if (!enc->helper[k]) {
+      rc = vp8gpu_encoder_create(enc->ctx, &enc->helper[k]);
+      if (rc != VP8GPU_OK) return rc;
+      enc->helper[k]->owner = enc;
+    }
+  vp8gpu_encoder* const slot[3] = {enc, enc->helper[0], enc->helper[1]};
   while (lo <= hi) {
-    const int qi = (lo + hi) / 2;
-    int frame = -1;
-    rc = encode_core(enc, key, qi, first_probe, &frame);
-    first_probe = false;
-    if (rc != VP8GPU_OK) return rc;
-    enc->e->frame_release(frame);
-    rc = encode_bytes(enc, key, qi, 0, bytes);
-    if (rc != VP8GPU_OK) return rc;
-    if (bytes.size() <= target_size || (lo == hi && best < 0)) {
-      best = qi;
-      hi = qi - 1;
+    const int n = hi - lo + 1;
+    int q[3], nq;
+    if (n <= 3) {
+      nq = n;
+      for (int k = 0; k < n; k++) q[k] = lo + k;
     } else {
-      lo = qi + 1;
+      nq = 3;
+      q[0] = lo + n / 4;
+      q[1] = lo + n / 2;
+      q[2] = lo + (3 * n) / 4;
+    }
+    int launched = 0;
+    for (int k = 0; k < nq && rc == VP8GPU_OK; k++) {
+      rc = encode_launch(slot[k], key, q[k], first_round && k == 0);
+      if (rc == VP8GPU_OK) launched++;
+    }
+    first_round = false;
+    size_t sz[3] = {0, 0, 0};
+    for (int k = 0; k < launched; k++) {  // every launched pass is collected, also after an error
+      int frame = -1;
+      const int r2 = encode_collect(slot[k], &frame);
+      if (r2 != VP8GPU_OK) {
+        if (rc == VP8GPU_OK) rc = r2;
+        continue;
+      }
+      enc->e->frame_release(frame);
+      if (rc != VP8GPU_OK) continue;
+      const int r3 = encode_bytes(slot[k], key, q[k], 0, bytes);
+      if (r3 != VP8GPU_OK) rc = r3;
+      sz[k] = bytes.size();
+    }
+    if (rc != VP8GPU_OK) return rc;
+    int fit = -1;
+    for (int k = 0; k < nq && fit < 0; k++)
+      if (sz[k] <= target_size) fit = k;
+    if (fit >= 0) {
+      best = q[fit];
+      hi = q[fit] - 1;
+      if (fit > 0) lo = q[fit - 1] + 1;
+    } else {
+      lo = q[nq - 1] + 1;
     }
   }
+  if (best < 0) best = top;  // encoder.cc:618: nothing fits -> the last index of the range is taken
   if (best < 0) return enc->e->fail(VP8GPU_ERR_LOGIC, "target size search failed");
   if (chosen_qi) *chosen_qi = best;
   return encode_final(enc, key, best, false, out, cap, size);  // encoder.cc:628: encode again at the chosen index

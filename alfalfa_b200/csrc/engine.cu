@@ -853,19 +853,19 @@ void Engine::resident_free(Resident* r) {
   delete r;
 }
 
-int Engine::acquire_frames(int lane, const int* ids, int n) {
+int Engine::acquire_frames(int lane, const int* ids, int n, uint32_t write_mask) {
   if (int rc = ensure_lane(lane)) return rc;
   std::lock_guard<std::mutex> lk(mu_);
   for (int i = 0; i < n; i++) {
     if (ids[i] < 0 || ids[i] >= (int)frames_.size() || frames_[ids[i]].refcnt <= 0) return fail(VP8GPU_ERR_LOGIC, "bad frame id");
-    if (int rc = wait_for(frames_[ids[i]], lane, lanes_[lane])) return rc;
+    if (int rc = wait_for(frames_[ids[i]], lane, lanes_[lane], (write_mask >> i) & 1)) return rc;
   }
   return VP8GPU_OK;
 }
-int Engine::mark_frames(int lane, const int* ids, int n) {
+int Engine::mark_frames(int lane, const int* ids, int n, uint32_t write_mask) {
   std::lock_guard<std::mutex> lk(mu_);
   for (int i = 0; i < n; i++)
-    if (int rc = touch(frames_[ids[i]], lane)) return rc;
+    if (int rc = touch(frames_[ids[i]], lane, (write_mask >> i) & 1)) return rc;
   return VP8GPU_OK;
 }
 

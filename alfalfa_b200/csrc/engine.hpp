@@ -104,8 +104,9 @@ class Engine {
 
   // for other device-side users of rasters (the encoder): raw pointer + stream-ordering hooks
   uint8_t* frame_dev(int id) { return frames_[id].dev; }
-  int acquire_frames(int lane, const int* ids, int n);  // stream `lane` waits for other users
-  int mark_frames(int lane, const int* ids, int n);     // record that `lane` used them
+  // bit i of write_mask: ids[i] is written (waits for / excludes every other user); otherwise only read
+  int acquire_frames(int lane, const int* ids, int n, uint32_t write_mask = ~0u);  // stream `lane` waits for other users
+  int mark_frames(int lane, const int* ids, int n, uint32_t write_mask = ~0u);     // record that `lane` used them
   void count_launches(int n) { launches_ += n; }
 
   int ensure_lane(int lane);  // creates the lane's streams on first use
