@@ -76,6 +76,33 @@ def test_host_front_end_and_device_token_logic_on_feature_streams(w, h, seed):
         assert T.th_frame(H, f, len(f), 0, None) == 0, "frame %d: device token logic" % i
 
 
+@pytest.mark.parametrize("seed", range(100, 124))
+def test_many_small_feature_streams_oracle_and_front_end_agree(seed):
+    """fuzz: every seed draws its own mix of partitions / segmentation / references / modes; sizes cover
+    single-row, single-column and non-multiple-of-16 frames"""
+    from alfalfa_b200 import capi
+    L = capi.lib()
+    w, h = [(16, 16), (48, 16), (16, 80), (50, 34), (96, 64), (130, 98)][seed % 6]
+    data = _stream(w, h, 6, seed)
+    _, _, frames = O.read_ivf(data)
+    od = O.OracleDecoder(w, h)
+    st, pf = C.c_void_p(), C.c_void_p()
+    capi.check(L.vp8gpu_state_create(w, h, C.byref(st)))
+    capi.check(L.vp8gpu_parsed_create(C.byref(pf)))
+    for i, f in enumerate(frames):
+        od.decode(f, want_planes=False)
+        op = od.parsed()
+        assert L.vp8gpu_parse_frame(st, f, len(f), pf) == 0
+        desc = L.vp8gpu_parsed_desc(pf).contents
+        n = desc.mb_cols * desc.mb_rows
+        assert bytes(desc) == bytes(op.desc), "frame %d desc" % i
+        assert C.string_at(L.vp8gpu_parsed_mbs(pf), n * 32) == op.mbs.tobytes(), "frame %d mbs" % i
+        if desc.n_tokens:
+            assert C.string_at(L.vp8gpu_parsed_tokens(pf), desc.n_tokens * 4) == op.tokens.tobytes(), "frame %d tokens" % i
+    L.vp8gpu_parsed_destroy(pf)
+    L.vp8gpu_state_destroy(st)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("device_tokens", [False, True])
 @pytest.mark.parametrize("source", ["clip", (175, 143, 7), (640, 368, 8)])
