@@ -128,3 +128,21 @@ def test_gpu_every_frame_and_reference_matches_oracle(source, device_tokens):
         r.release()
     del dec
     ctx.close()
+
+
+REF_DUMP = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_DUMP), reason="unmodified reference decoder not built (oracle/_ref)")
+@pytest.mark.parametrize("seed", range(200, 212))
+def test_oracle_equals_the_unmodified_reference_decoder_on_fresh_feature_streams(seed):
+    """the oracle is pinned by the 53 golden vectors; here also against the reference decoder itself
+    (compiled in place by oracle/Makefile) on streams nobody has seen before"""
+    w, h = [(64, 48), (176, 144), (50, 34), (320, 96)][seed % 4]
+    data = _stream(w, h, 8, seed)
+    with tempfile.NamedTemporaryFile(suffix=".ivf") as f:
+        f.write(data)
+        f.flush()
+        raw = subprocess.run([REF_DUMP, "shown", f.name], capture_output=True)
+    assert raw.returncode == 0, raw.stderr[-500:]
+    assert hashlib.sha1(raw.stdout).hexdigest() == hashlib.sha1(O.decode_ivf_display(data)).hexdigest()
