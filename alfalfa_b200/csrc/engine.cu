@@ -8,6 +8,7 @@
 // or to recycle and overwrite, a raster first waits for the other streams' events.
 #include "engine.hpp"
 
+#include <cuda.h>  // CUtensorMap types only: the driver entry point is fetched through the runtime
 #include <string.h>
 
 namespace vp8 {
@@ -65,6 +66,11 @@ int Engine::create(int device, int width, int height, int max_frames, Engine** o
   g.v_off = g.u_off + (uint32_t)((size_t)g.c_pitch * (g.H / 2));
   g.frame_bytes = g.v_off + (uint32_t)((size_t)g.c_pitch * (g.H / 2));
   if (max_frames <= 0) max_frames = 64;
+  if (cudaMalloc(&en->tmaps_, (size_t)max_frames * 384) != cudaSuccess) {
+    if (err) *err = "cudaMalloc(tensor maps) failed";
+    delete en;
+    return VP8GPU_ERR_CUDA;
+  }
   en->frames_.resize(max_frames);
   for (int i = max_frames - 1; i >= 0; i--) en->free_.push_back(i);
   *out = en;
@@ -89,6 +95,40 @@ Engine::~Engine() {
   for (auto& s : lanes_)
     if (s) cudaStreamDestroy(s);
   if (cmp_scratch_) cudaFree(cmp_scratch_);
+  if (tmaps_) cudaFree(tmaps_);
+}
+
+// One 2-D tensor map per plane of raster `id` (u8 elements, plane size W x H resp. W/2 x H/2, row pitch
+// from Geom), box = 48 x 21 luma / 32 x 13 chroma: the source window of a six-tap prediction
+// (prediction.cc:655-674) with its 2 + 3 pixel halo, plus up to 15 pixels of slack because a box has to
+// start on a 16-byte boundary of the row.  Out-of-range pixels are zero-filled by the hardware, so
+// k_inter only uses TMA for windows inside the plane.
+int Engine::make_tensor_maps(int id) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(VP8GPU_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  alignas(64) CUtensorMap maps[3];
+  for (int p = 0; p < 3; p++) {
+    uint8_t* base = frames_[id].dev + (p == 0 ? 0 : (p == 1 ? g_.u_off : g_.v_off));
+    const cuuint64_t dims[2] = {(cuuint64_t)(p ? g_.W / 2 : g_.W), (cuuint64_t)(p ? g_.H / 2 : g_.H)};
+    const cuuint64_t strides[1] = {(cuuint64_t)(p ? g_.c_pitch : g_.y_pitch)};
+    const cuuint32_t box[2] = {p ? 32u : 48u, p ? 13u : 21u};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(&maps[p], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(VP8GPU_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  }
+  static_assert(sizeof(CUtensorMap) == 128, "tensor map size");
+  CU(cudaMemcpy(tmaps_ + (size_t)id * 384, maps, 384, cudaMemcpyHostToDevice));
+  return VP8GPU_OK;
 }
 
 int Engine::ensure_lane(int lane) {
@@ -113,6 +153,7 @@ int Engine::frame_alloc(int* id) {
   if (!f.dev) {
     CU(cudaSetDevice(device_));
     CU(cudaMalloc(&f.dev, g_.frame_bytes + 64));  // slack: staged window rows are read as whole words
+    if (int rc = make_tensor_maps(i)) return rc;
   }
   free_.pop_back();
   f.refcnt = 1;
@@ -610,10 +651,12 @@ int Engine::submit(int lane, const HostJob* jobs, int n, cudaEvent_t consumed) {
       d.out = frames_[j.out].dev;
       for (int r = 0; r < 3; r++) {
         d.ref[r] = nullptr;
+        d.ref_tmap[r] = nullptr;
         if (!j.desc->key_frame) {
           if (j.refs[r] < 0 || j.refs[r] >= (int)frames_.size() || frames_[j.refs[r]].refcnt <= 0)
             return fail(VP8GPU_ERR_LOGIC, "submit: bad reference frame");
           d.ref[r] = frames_[j.refs[r]].dev;
+          d.ref_tmap[r] = frame_tmaps(j.refs[r]);
         }
       }
       d.intra_progress = d_sync + kSyncHeaderInts + (size_t)(2 * i) * g_.mb_rows;
@@ -720,6 +763,7 @@ int Engine::resident_upload(const HostJob* jobs, int n, Resident** out) {
       r->outs.push_back(j.out);
       for (int k = 0; k < 3; k++) {
         d.ref[k] = nullptr;
+        d.ref_tmap[k] = nullptr;
         if (!j.desc->key_frame) {
           if (j.refs[k] < 0 || j.refs[k] >= (int)frames_.size() || frames_[j.refs[k]].refcnt <= 0) {
             cudaFree(r->dev);
@@ -727,6 +771,7 @@ int Engine::resident_upload(const HostJob* jobs, int n, Resident** out) {
             return fail(VP8GPU_ERR_LOGIC, "resident: bad reference frame");
           }
           d.ref[k] = frames_[j.refs[k]].dev;
+          d.ref_tmap[k] = frame_tmaps(j.refs[k]);
           r->refs.push_back(j.refs[k]);
         }
       }

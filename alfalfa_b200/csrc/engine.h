@@ -26,6 +26,7 @@ struct DevJob {
   const vp8gpu_split_mvs* split;
   uint8_t* out;
   const uint8_t* ref[3];   // last, golden, altref (ref_frame - 1)
+  const void* ref_tmap[3]; // per reference: its three TMA tensor maps (Y, U, V; 128 bytes each) in HBM
   int* intra_progress;     // [mb_rows] wavefront counters, zeroed before launch
   int* lf_progress;        // [mb_rows]
   vp8gpu_quant quant[4];

@@ -104,6 +104,8 @@ class Engine {
 
   // for other device-side users of rasters (the encoder): raw pointer + stream-ordering hooks
   uint8_t* frame_dev(int id) { return frames_[id].dev; }
+  // the raster's TMA tensor maps (Y, U, V; 128 bytes each) in device memory, for kernels that stage windows by TMA
+  const void* frame_tmaps(int id) const { return tmaps_ ? tmaps_ + (size_t)id * 384 : nullptr; }
   // bit i of write_mask: ids[i] is written (waits for / excludes every other user); otherwise only read
   int acquire_frames(int lane, const int* ids, int n, uint32_t write_mask = ~0u);  // stream `lane` waits for other users
   int mark_frames(int lane, const int* ids, int n, uint32_t write_mask = ~0u);     // record that `lane` used them
@@ -157,6 +159,8 @@ class Engine {
   Staging staging_[kMaxLanes][kStagingDepth];
   int staging_next_[kMaxLanes] = {};
   uint8_t* cmp_scratch_ = nullptr;
+  uint8_t* tmaps_ = nullptr;  // [max_frames][3] CUtensorMap, written when a raster's memory is first allocated
+  int make_tensor_maps(int id);
   std::atomic<uint64_t> launches_{0};
   std::string err_;
 };

@@ -60,8 +60,9 @@ __device__ unsigned long long g_prof[32];
 #define PROF_FLUSH(base)
 #endif
 
-constexpr int CS = 18;          // int16 stride of one 4x4 coefficient block in shared memory (bank spread)
-constexpr int COEF_WORDS = 25 * CS / 2;  // 225 32-bit words
+constexpr int CS = 20;          // int16 stride of one 4x4 coefficient block in shared memory: 40 bytes, so a block
+                                // row is one aligned 8-byte access and 16 lanes x 8 bytes hit 32 distinct banks
+constexpr int COEF_I16 = 25 * CS + 4;    // 504 int16 = 63 16-byte vectors (zeroed as vectors)
 
 struct MbFields {
   uint32_t tok_off, tok_cnt;
@@ -258,12 +259,13 @@ __device__ __forceinline__ void mc_block(const uint8_t* __restrict__ ref, int pi
 // and the inverse DCT (transform.cc:100-137).  On return coef[blk*CS + y*4 + x] holds the
 // RESIDUAL of pixel (x, y) of block blk (0-15 Y, 16-19 U, 20-23 V).
 // ------------------------------------------------------------------------------------------------
-// second half, shared with the encoder's reconstruction: coef holds DEQUANTISED coefficients
-__device__ __forceinline__ void inverse_transforms(int16_t* coef, bool has_y2, int lane);
+// second half, shared with the encoder's reconstruction: coef holds DEQUANTISED coefficients.
+// Returns the mask of blocks (bit b, b < 24) whose residual is not all zero.
+__device__ __forceinline__ uint32_t inverse_transforms(int16_t* coef, bool has_y2, int lane);
 
-__device__ __forceinline__ void build_residuals(const DevJob& J, const MbFields& f, int16_t* coef, int lane) {
-  uint32_t* w = reinterpret_cast<uint32_t*>(coef);
-  for (int i = lane; i < COEF_WORDS; i += 32) w[i] = 0;
+__device__ __forceinline__ uint32_t build_residuals(const DevJob& J, const MbFields& f, int16_t* coef, int lane) {
+  uint4* z = reinterpret_cast<uint4*>(coef);
+  for (int i = lane; i < COEF_I16 / 8; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncwarp();
   const vp8gpu_quant q = J.quant[f.segment];
   const vp8gpu_token* tok = J.tokens + f.tok_off;
@@ -278,10 +280,10 @@ __device__ __forceinline__ void build_residuals(const DevJob& J, const MbFields&
     coef[blk * CS + pos] = (int16_t)(val * factor);
   }
   __syncwarp();
-  inverse_transforms(coef, (f.flags & VP8GPU_MB_HAS_Y2) != 0, lane);
+  return inverse_transforms(coef, (f.flags & VP8GPU_MB_HAS_Y2) != 0, lane);
 }
 
-__device__ __forceinline__ void inverse_transforms(int16_t* coef, bool has_y2, int lane) {
+__device__ __forceinline__ uint32_t inverse_transforms(int16_t* coef, bool has_y2, int lane) {
   if (has_y2) {
     // inverse WHT on 16 lanes (transform.cc:47-88): lane i first produces intermediate m[i]
     // (column i & 3, butterfly output i >> 2), the row pass exchanges m through shuffles.
@@ -305,55 +307,38 @@ __device__ __forceinline__ void inverse_transforms(int16_t* coef, bool has_y2, i
     }
     __syncwarp();
   }
+  bool nonzero = false;
   if (lane < 24) {
-    int16_t* c = coef + lane * CS;
-    uint32_t* cw = reinterpret_cast<uint32_t*>(c);
-    uint32_t ac = cw[0] & 0xFFFF0000u;
+    uint2* cv = reinterpret_cast<uint2*>(coef + lane * CS);  // four 8-byte rows
+    uint2 v[4];
 #pragma unroll
-    for (int k = 1; k < 8; k++) ac |= cw[k];
+    for (int k = 0; k < 4; k++) v[k] = cv[k];
+    const uint32_t ac = (v[0].x & 0xFFFF0000u) | v[0].y | v[1].x | v[1].y | v[2].x | v[2].y | v[3].x | v[3].y;
     if (ac) {
       int16_t in[16], r[16];
 #pragma unroll
-      for (int k = 0; k < 16; k++) in[k] = c[k];
+      for (int k = 0; k < 4; k++) {
+        in[4 * k] = (int16_t)(v[k].x & 0xFFFF), in[4 * k + 1] = (int16_t)(v[k].x >> 16);
+        in[4 * k + 2] = (int16_t)(v[k].y & 0xFFFF), in[4 * k + 3] = (int16_t)(v[k].y >> 16);
+      }
       vp8m::idct16(in, r);
 #pragma unroll
-      for (int k = 0; k < 16; k++) c[k] = r[k];
-    } else if (cw[0]) {
+      for (int k = 0; k < 4; k++)
+        cv[k] = make_uint2((uint32_t)(uint16_t)r[4 * k] | ((uint32_t)(uint16_t)r[4 * k + 1] << 16),
+                           (uint32_t)(uint16_t)r[4 * k + 2] | ((uint32_t)(uint16_t)r[4 * k + 3] << 16));
+      nonzero = true;
+    } else if (v[0].x) {
       // DC only: both passes of idct_add reduce to (dc + 4) >> 3 for every pixel
-      const uint32_t r = (uint32_t)(uint16_t)(((int)(int16_t)(cw[0] & 0xFFFF) + 4) >> 3);
+      const uint32_t r = (uint32_t)(uint16_t)(((int)(int16_t)(v[0].x & 0xFFFF) + 4) >> 3);
       const uint32_t rr = r | (r << 16);
 #pragma unroll
-      for (int k = 0; k < 8; k++) cw[k] = rr;
+      for (int k = 0; k < 4; k++) cv[k] = make_uint2(rr, rr);
+      nonzero = r != 0;
     }
   }
+  const uint32_t nz = __ballot_sync(0xffffffffu, nonzero);
   __syncwarp();
-}
-
-// pixel = clamp255(prediction + residual) over the whole macroblock buffer
-// pix layout: Y 16x16 at 0, U 8x8 at 256, V 8x8 at 320.
-__device__ __forceinline__ void add_residuals(uint8_t* pix, const int16_t* coef, int lane) {
-  for (int g4 = lane; g4 < 96; g4 += 32) {
-    int blk, ry, off;
-    if (g4 < 64) {
-      const int y = g4 >> 2, x4 = (g4 & 3) * 4;
-      blk = (y >> 2) * 4 + (x4 >> 2);
-      ry = y & 3;
-      off = y * 16 + x4;
-    } else {
-      const int c = g4 - 64, plane = c >> 4, cc = c & 15;
-      const int y = cc >> 1, x4 = (cc & 1) * 4;
-      blk = 16 + plane * 4 + (y >> 2) * 2 + (x4 >> 2);
-      ry = y & 3;
-      off = 256 + plane * 64 + y * 8 + x4;
-    }
-    const int16_t* r = coef + blk * CS + ry * 4;
-    uint32_t p = *reinterpret_cast<uint32_t*>(pix + off);
-    uint32_t o = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) o |= (uint32_t)vp8m::clamp255((int)((p >> (8 * k)) & 0xFF) + r[k]) << (8 * k);
-    *reinterpret_cast<uint32_t*>(pix + off) = o;
-  }
-  __syncwarp();
+  return nz;
 }
 
 // macroblock buffer -> frame: 16-byte luma rows by lanes 0-15, 8-byte chroma rows by 16-31
@@ -371,15 +356,151 @@ __device__ __forceinline__ void store_mb(const uint8_t* pix, uint8_t* frame, con
 }
 
 // ================================================================================================
-// k_inter
+// k_inter: one warp per inter-coded macroblock (macroblock.cc:553-601).
+//
+//  * The three source windows (luma 21 x 21 inside a 48 x 21 box, chroma 13 x 13 inside 32 x 13 boxes) are
+//    fetched by TMA (cp.async.bulk.tensor.2d, one tensor map per plane of every raster, engine.cu) into
+//    the warp's shared-memory tile and signalled on the warp's mbarrier; lane 0 issues the three copies,
+//    nobody computes an address per pixel.  TMA wants the box to start on a 16-byte boundary of the row
+//    (tools/probe/tma_probe.cu), so the box starts at the window's x rounded down to 16 and the window
+//    sits at byte offset x & 15 of every tile row; the row filter re-aligns with one funnel shift per
+//    word.  A window that leaves the plane takes the clamped path (EdgeExtendedRaster::at,
+//    vp8_raster.hh:327-338): TMA fills out-of-range pixels with zeros, the reference replicates the edge.
+//  * While the tiles are in flight the warp expands the macroblock's tokens into residuals (dequant,
+//    IWHT, IDCT).
+//  * Six-tap filter on packed pixels (vp8_math.cuh): rows as two 4-byte dot products per output (dp4a),
+//    columns as 32-bit multiply-adds on pixel pairs; clamp + pack with cvt.pack.sat.  A pass whose
+//    fraction is 0 is skipped ((128 p + 64) >> 7 = p), a whole-pel vector is a copy.
+//  * SPLITMV: the 24 4x4 blocks (16 Y, 4 U, 4 V) are staged and filtered lane-parallel, (block, row)
+//    and (block, column pair) items spread over the warp.
 // ================================================================================================
 constexpr int INTER_WARPS = 4;
+constexpr int TSY = 48, TSC = 32;  // tile row strides = box widths
+constexpr uint32_t TILE_Y_BYTES = 21 * TSY, TILE_C_BYTES = 13 * TSC;  // TMA boxes (engine.cu make_tensor_maps)
 
-__global__ void __launch_bounds__(INTER_WARPS * 32) k_inter(const DevJob* __restrict__ jobs, Geom g) {
-  __shared__ __align__(16) uint8_t s_pix[INTER_WARPS][384];
-  __shared__ __align__(16) int16_t s_coef[INTER_WARPS][25 * CS];
-  __shared__ __align__(16) uint8_t s_tile[INTER_WARPS][21 * 24];
-  __shared__ __align__(16) uint8_t s_mid[INTER_WARPS][21 * 16];
+__constant__ uint32_t c_taps03[8] = {0x00800000u, 0x0c7bfa00u, 0x246cf502u, 0x325df700u, 0x4d4df003u, 0x5d32fa00u, 0x6c24f801u, 0x7b0cff00u};
+__constant__ uint32_t c_taps45[8] = {0x0000u, 0x00ffu, 0x01f8u, 0x00fau, 0x03f0u, 0x00f7u, 0x02f5u, 0x00fau};
+
+struct __align__(128) InterSmem {  // per warp
+  union {
+    struct {
+      uint8_t y[1024];     // 21 rows x 48 B (TMA destination, 128-byte aligned)
+      uint8_t u[512];      // 13 rows x 32 B
+      uint8_t v[512];
+      uint8_t mid_y[21 * 16];
+      uint8_t mid_c[2][13 * 8];
+    } n;
+    struct {
+      uint8_t win[24][9][12];  // SPLITMV: 9 x 9 window of every 4x4 block, window column 0 at byte 0
+      uint8_t mid[24][9][4];
+    } s;
+  };
+  uint8_t pix[384];            // Y 16x16 at 0, U 8x8 at 256, V 8x8 at 320
+  int16_t coef[COEF_I16];
+  unsigned long long bar;      // mbarrier
+  uint8_t nzlist[24];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int x, int y, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(dst)),
+               "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
+               : "memory");
+}
+// A tensor map that lives in global memory and was written by the host (cudaMemcpy) must be acquired by
+// the thread that is going to use it (tensormap proxy, system scope) before its first use.
+__device__ __forceinline__ void tmap_acquire(const void* tmap) {
+  asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(tmap) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+// window that leaves the plane: pixel by pixel with clamped coordinates into the same tile layout
+template <int TS>
+__device__ __forceinline__ void stage_clamped(uint8_t* tile, const uint8_t* __restrict__ ref, int pitch, int PW, int PH, int wx,
+                                              int wy, int wcols, int wrows, int lane) {
+  for (int i = lane; i < wrows * wcols; i += 32) {
+    const int r = i / wcols, c = i - r * wcols;
+    tile[r * TS + c] = __ldg(ref + (size_t)clampi(wy + r, 0, PH - 1) * pitch + clampi(wx + c, 0, PW - 1));
+  }
+}
+
+// rows: out[r][4g .. 4g+3] from tile[r][o + 4g .. o + 4g + 8]; o = byte offset of the window in a tile row
+template <int N, int TS, int OS>
+__device__ __forceinline__ void hpass2(const uint8_t* tile, int o, int nrows, int mx, uint8_t* out, int lane) {
+  constexpr int G = N / 4;
+  const uint32_t t03 = c_taps03[mx], t45 = c_taps45[mx];
+  const int sh = 8 * (o & 3);
+  for (int i = lane; i < nrows * G; i += 32) {
+    const int r = i / G, g = i - r * G;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(tile + r * TS) + (o >> 2) + g;
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+    *reinterpret_cast<uint32_t*>(out + r * OS + 4 * g) =
+        vp8m::sixtap_h4(vp8m::bytes_at(w0, w1, sh), vp8m::bytes_at(w1, w2, sh), vp8m::bytes_at(w2, w3, sh), t03, t45);
+  }
+}
+// the same walk without a filter (fraction 0): re-aligned copy of N pixels per row
+template <int N, int TS, int OS>
+__device__ __forceinline__ void hcopy(const uint8_t* tile, int o, int nrows, uint8_t* out, int lane) {
+  constexpr int G = N / 4;
+  const int sh = 8 * (o & 3);
+  for (int i = lane; i < nrows * G; i += 32) {
+    const int r = i / G, g = i - r * G;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(tile + r * TS) + (o >> 2) + g;
+    *reinterpret_cast<uint32_t*>(out + r * OS + 4 * g) = vp8m::bytes_at(w[0], w[1], sh);
+  }
+}
+// columns: R output rows of one pixel pair; s = &src[first input row][column], d = &dst[first output row][column]
+template <int R>
+__device__ __forceinline__ void vitem(const uint8_t* s, int ss, const int16_t* t, uint8_t* d, int ds) {
+  uint32_t p[R + 5];
+#pragma unroll
+  for (int k = 0; k < R + 5; k++) p[k] = vp8m::pair_of(*reinterpret_cast<const uint16_t*>(s + k * ss));
+#pragma unroll
+  for (int j = 0; j < R; j++)
+    *reinterpret_cast<uint16_t*>(d + j * ds) = (uint16_t)vp8m::sixtap_v2(p[j], p[j + 1], p[j + 2], p[j + 3], p[j + 4], p[j + 5], t);
+}
+
+// pixel = clamp255(prediction + residual) on the blocks of mask nz only; pix layout as in InterSmem
+__device__ __forceinline__ void add_residuals(uint8_t* pix, const int16_t* coef, uint32_t nz, uint8_t* nzlist, int lane) {
+  if ((nz >> lane) & 1) nzlist[__popc(nz & ((1u << lane) - 1))] = (uint8_t)lane;
+  __syncwarp();
+  const int n = 4 * __popc(nz);
+  for (int i = lane; i < n; i += 32) {
+    const int blk = nzlist[i >> 2], ry = i & 3;
+    int off;
+    if (blk < 16) off = ((blk >> 2) * 4 + ry) * 16 + (blk & 3) * 4;
+    else off = 256 + ((blk - 16) >> 2) * 64 + (((blk >> 1) & 1) * 4 + ry) * 8 + (blk & 1) * 4;
+    const uint2 r = *reinterpret_cast<const uint2*>(coef + blk * CS + ry * 4);
+    uint32_t* p = reinterpret_cast<uint32_t*>(pix + off);
+    *p = vp8m::add_residual4(*p, r.x, r.y);
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(INTER_WARPS * 32, 10) k_inter(const DevJob* __restrict__ jobs, Geom g) {
+  __shared__ InterSmem s_all[INTER_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const DevJob& J = jobs[blockIdx.y];
   const int mbi = blockIdx.x * INTER_WARPS + warp;
@@ -387,57 +508,167 @@ __global__ void __launch_bounds__(INTER_WARPS * 32) k_inter(const DevJob* __rest
   const MbFields f = load_mb(J.mbs + mbi);
   if (f.ref == VP8GPU_REF_CURRENT) return;  // intra macroblocks belong to k_intra
   const int row = mbi / g.mb_cols, col = mbi - row * g.mb_cols;
-  uint8_t* pix = s_pix[warp];
-  uint8_t* tile = s_tile[warp];
-  uint8_t* mid = s_mid[warp];
+  InterSmem& S = s_all[warp];
+  uint8_t* const pix = S.pix;
   const uint8_t* ref = J.ref[f.ref - 1];
   const uint8_t* refU = ref + g.u_off;
   const uint8_t* refV = ref + g.v_off;
   const int CW = g.W >> 1, CH = g.H >> 1;
+  uint32_t nz = 0;
 
-  if (f.y_mode == VP8GPU_SPLITMV) {
-    // lane i < 16 holds the vector of luma sub-block i
-    int my_x = 0, my_y = 0;
+  if (f.y_mode != VP8GPU_SPLITMV) {
+    // ---- where the windows are: first pixel the filter needs, and how much of the tile it reads ----
+    const int mx = f.mv_x & 7, my = f.mv_y & 7;
+    const int X = 16 * col + (f.mv_x >> 3) - (mx ? 2 : 0), Y = 16 * row + (f.mv_y >> 3) - (my ? 2 : 0);
+    const int ncols = 16 + (mx ? 5 : 0), nrows = 16 + (my ? 5 : 0);
+    const bool fastY = X >= 0 && Y >= 0 && X + ncols <= g.W && Y + nrows <= g.H;
+    const int cmvx = chroma_component(4 * f.mv_x), cmvy = chroma_component(4 * f.mv_y);
+    const int cmx = cmvx & 7, cmy = cmvy & 7;
+    const int CX = 8 * col + (cmvx >> 3) - (cmx ? 2 : 0), CY = 8 * row + (cmvy >> 3) - (cmy ? 2 : 0);
+    const int cncols = 8 + (cmx ? 5 : 0), cnrows = 8 + (cmy ? 5 : 0);
+    const bool fastC = CX >= 0 && CY >= 0 && CX + cncols <= CW && CY + cnrows <= CH;
+    const uint32_t tx = (fastY ? TILE_Y_BYTES : 0u) + (fastC ? 2 * TILE_C_BYTES : 0u);
+    const int oY = fastY ? (X & 15) : 0, oC = fastC ? (CX & 15) : 0;  // window's byte offset in a tile row
+    if (lane == 0) mbar_init(&S.bar, 1);
+    __syncwarp();
+    if (lane == 0 && tx) {
+      const uint8_t* maps = static_cast<const uint8_t*>(J.ref_tmap[f.ref - 1]);  // Y, U, V maps, 128 bytes each
+      mbar_expect_tx(&S.bar, tx);
+      if (fastY) {
+        tmap_acquire(maps);
+        tma_load_2d(S.n.y, maps, X & ~15, Y, &S.bar);
+      }
+      if (fastC) {
+        tmap_acquire(maps + 128);
+        tmap_acquire(maps + 256);
+        tma_load_2d(S.n.u, maps + 128, CX & ~15, CY, &S.bar);
+        tma_load_2d(S.n.v, maps + 256, CX & ~15, CY, &S.bar);
+      }
+    }
+    // ---- residuals while the tiles travel (Macroblock::has_nonzero_, macroblock.cc:579,593) ----
+    if (f.tok_cnt) nz = build_residuals(J, f, S.coef, lane);
+    if (!fastY) stage_clamped<TSY>(S.n.y, ref, g.y_pitch, g.W, g.H, X, Y, ncols, nrows, lane);
+    if (!fastC) {
+      stage_clamped<TSC>(S.n.u, refU, g.c_pitch, CW, CH, CX, CY, cncols, cnrows, lane);
+      stage_clamped<TSC>(S.n.v, refV, g.c_pitch, CW, CH, CX, CY, cncols, cnrows, lane);
+    }
+    if (tx) mbar_wait(&S.bar, 0);
+    __syncwarp();
+
+    // ---- luma 16x16: rows (filter or re-aligned copy), then columns on aligned data ----
+    if (my == 0) {
+      if (mx) hpass2<16, TSY, 16>(S.n.y, oY, 16, mx, pix, lane);
+      else hcopy<16, TSY, 16>(S.n.y, oY, 16, pix, lane);
+    } else {
+      if (mx) hpass2<16, TSY, 16>(S.n.y, oY, 21, mx, S.n.mid_y, lane);
+      else hcopy<16, TSY, 16>(S.n.y, oY, 21, S.n.mid_y, lane);
+      __syncwarp();
+      const int cp = lane & 7, rg = lane >> 3;
+      vitem<4>(S.n.mid_y + (4 * rg) * 16 + 2 * cp, 16, c_sixtap[my], pix + (4 * rg) * 16 + 2 * cp, 16);
+    }
+    // ---- chroma 8x8, both planes ----
+    if (cmy == 0) {
+      if (cmx) {
+        hpass2<8, TSC, 8>(S.n.u, oC, 8, cmx, pix + 256, lane);
+        hpass2<8, TSC, 8>(S.n.v, oC, 8, cmx, pix + 320, lane);
+      } else {
+        hcopy<8, TSC, 8>(lane < 16 ? S.n.u : S.n.v, oC, 8, pix + (lane < 16 ? 256 : 320), lane & 15);
+      }
+    } else {
+      if (cmx) {
+        hpass2<8, TSC, 8>(S.n.u, oC, 13, cmx, S.n.mid_c[0], lane);
+        hpass2<8, TSC, 8>(S.n.v, oC, 13, cmx, S.n.mid_c[1], lane);
+      } else {
+        hcopy<8, TSC, 8>(S.n.u, oC, 13, S.n.mid_c[0], lane);
+        hcopy<8, TSC, 8>(S.n.v, oC, 13, S.n.mid_c[1], lane);
+      }
+      __syncwarp();
+      const int plane = lane >> 4, cp = lane & 3, rg = (lane >> 2) & 3;
+      vitem<2>(S.n.mid_c[plane] + (2 * rg) * 8 + 2 * cp, 8, c_sixtap[cmy], pix + 256 + 64 * plane + (2 * rg) * 8 + 2 * cp, 8);
+    }
+    __syncwarp();
+  } else {
+    // ---- SPLITMV (macroblock.cc:560-575): lane b < 24 owns block b: 0-15 luma, 16-19 U, 20-23 V ----
+    if (f.tok_cnt) nz = build_residuals(J, f, S.coef, lane);
+    int lmx = 0, lmy = 0;
     if (lane < 16) {
       const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(J.split + f.split_idx) + lane);
-      my_x = (int16_t)(v & 0xFFFF);
-      my_y = (int16_t)(v >> 16);
+      lmx = (int16_t)(v & 0xFFFF);
+      lmy = (int16_t)(v >> 16);
     }
-    for (int b = 0; b < 16; b++) {
-      const int bx = b & 3, by = b >> 2;
-      const int mvx = __shfl_sync(0xffffffffu, my_x, b), mvy = __shfl_sync(0xffffffffu, my_y, b);
-      mc_block<4>(ref, g.y_pitch, g.W, g.H, 16 * col + 4 * bx, 16 * row + 4 * by, mvx, mvy, pix + by * 64 + bx * 4, 16,
-                  tile, mid, lane);
+    // chroma vector of 2x2 group q = (lane & 3): rounded average of four luma vectors (macroblock.cc:289-299)
+    const int qa = ((lane >> 1) & 1) * 8 + (lane & 1) * 2;
+    const int sx = __shfl_sync(0xffffffffu, lmx, qa) + __shfl_sync(0xffffffffu, lmx, qa + 1) + __shfl_sync(0xffffffffu, lmx, qa + 4) +
+                   __shfl_sync(0xffffffffu, lmx, qa + 5);
+    const int sy = __shfl_sync(0xffffffffu, lmy, qa) + __shfl_sync(0xffffffffu, lmy, qa + 1) + __shfl_sync(0xffffffffu, lmy, qa + 4) +
+                   __shfl_sync(0xffffffffu, lmy, qa + 5);
+    int bmvx = lmx, bmvy = lmy, bx0 = 16 * col + 4 * (lane & 3), by0 = 16 * row + 4 * ((lane >> 2) & 3);
+    if (lane >= 16) {
+      bmvx = chroma_component(sx), bmvy = chroma_component(sy);
+      bx0 = 8 * col + 4 * (lane & 1), by0 = 8 * row + 4 * ((lane >> 1) & 1);
     }
-    for (int b = 0; b < 4; b++) {
-      const int cx = b & 1, cy = b >> 1, a = cy * 8 + cx * 2;
-      const int sx = __shfl_sync(0xffffffffu, my_x, a) + __shfl_sync(0xffffffffu, my_x, a + 1) +
-                     __shfl_sync(0xffffffffu, my_x, a + 4) + __shfl_sync(0xffffffffu, my_x, a + 5);
-      const int sy = __shfl_sync(0xffffffffu, my_y, a) + __shfl_sync(0xffffffffu, my_y, a + 1) +
-                     __shfl_sync(0xffffffffu, my_y, a + 4) + __shfl_sync(0xffffffffu, my_y, a + 5);
-      const int cmx = chroma_component(sx), cmy = chroma_component(sy);
-      mc_block<4>(refU, g.c_pitch, CW, CH, 8 * col + 4 * cx, 8 * row + 4 * cy, cmx, cmy, pix + 256 + cy * 32 + cx * 4, 8,
-                  tile, mid, lane);
-      mc_block<4>(refV, g.c_pitch, CW, CH, 8 * col + 4 * cx, 8 * row + 4 * cy, cmx, cmy, pix + 320 + cy * 32 + cx * 4, 8,
-                  tile, mid, lane);
+    const int bX = bx0 + (bmvx >> 3) - 2, bY = by0 + (bmvy >> 3) - 2;  // window origin (always the full 9 x 9)
+    const int bfx = bmvx & 7, bfy = bmvy & 7;
+    // stage: item = (block, window row)
+    for (int it = 0; it < 7; it++) {
+      const int i = it * 32 + lane, b = min(i / 9, 23), r = i - 9 * (i / 9);
+      const int wx = __shfl_sync(0xffffffffu, bX, b), wy = __shfl_sync(0xffffffffu, bY, b);
+      if (i < 216) {
+        const uint8_t* plane = b < 16 ? ref : (b < 20 ? refU : refV);
+        const int pitch = b < 16 ? g.y_pitch : g.c_pitch, PW = b < 16 ? g.W : CW, PH = b < 16 ? g.H : CH;
+        const uint8_t* rowp = plane + (size_t)clampi(wy + r, 0, PH - 1) * pitch;
+        uint32_t a0, a1, a2;
+        if (wx >= 0 && wx + 9 <= PW) {
+          const int o = wx & 3;
+          const uint32_t* wp = reinterpret_cast<const uint32_t*>(rowp + (wx - o));
+          const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+          a0 = vp8m::bytes_at(w0, w1, 8 * o), a1 = vp8m::bytes_at(w1, w2, 8 * o), a2 = w2 >> (8 * o);
+        } else {
+          uint32_t px[9];
+#pragma unroll
+          for (int k = 0; k < 9; k++) px[k] = __ldg(rowp + clampi(wx + k, 0, PW - 1));
+          a0 = px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24);
+          a1 = px[4] | (px[5] << 8) | (px[6] << 16) | (px[7] << 24);
+          a2 = px[8];
+        }
+        uint32_t* d = reinterpret_cast<uint32_t*>(S.s.win[b][r]);
+        d[0] = a0, d[1] = a1, d[2] = a2;
+      }
     }
-  } else {
-    // request the three source windows first, then filter: one memory latency instead of three
-    const int cmx = chroma_component(4 * f.mv_x), cmy = chroma_component(4 * f.mv_y);
-    McPlan<16> py;
-    McPlan<8> pu, pv;
-    mc_plan<16>(py, ref, g.y_pitch, g.W, g.H, 16 * col, 16 * row, f.mv_x, f.mv_y, lane);
-    mc_plan<8>(pu, refU, g.c_pitch, CW, CH, 8 * col, 8 * row, cmx, cmy, lane);
-    mc_plan<8>(pv, refV, g.c_pitch, CW, CH, 8 * col, 8 * row, cmx, cmy, lane);
-    mc_finish<16>(py, ref, g.y_pitch, g.W, g.H, pix, 16, tile, mid, lane);
-    mc_finish<8>(pu, refU, g.c_pitch, CW, CH, pix + 256, 8, tile, mid, lane);
-    mc_finish<8>(pv, refV, g.c_pitch, CW, CH, pix + 320, 8, tile, mid, lane);
+    __syncwarp();
+    // rows: item = (block, window row) -> 4 pixels of mid
+    for (int it = 0; it < 7; it++) {
+      const int i = it * 32 + lane, b = min(i / 9, 23), r = i - 9 * (i / 9);
+      const int fx = __shfl_sync(0xffffffffu, bfx, b);
+      if (i < 216) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(S.s.win[b][r]);
+        *reinterpret_cast<uint32_t*>(S.s.mid[b][r]) =
+            fx ? vp8m::sixtap_h4(w[0], w[1], w[2], c_taps03[fx], c_taps45[fx]) : vp8m::bytes_at(w[0], w[1], 16);
+      }
+    }
+    __syncwarp();
+    // columns: item = (block, pixel pair) -> 4 rows x 2 pixels of the macroblock buffer
+    for (int it = 0; it < 2; it++) {
+      const int i = it * 32 + lane, b = min(i >> 1, 23), cp = i & 1;
+      const int fy = __shfl_sync(0xffffffffu, bfy, b);
+      if (i < 48) {
+        uint8_t* d;
+        int ds;
+        if (b < 16) d = pix + ((b >> 2) * 4) * 16 + (b & 3) * 4 + 2 * cp, ds = 16;
+        else d = pix + 256 + 64 * ((b - 16) >> 2) + (((b >> 1) & 1) * 4) * 8 + (b & 1) * 4 + 2 * cp, ds = 8;
+        const uint8_t* m = &S.s.mid[b][0][2 * cp];
+        if (fy) {
+          vitem<4>(m, 4, c_sixtap[fy], d, ds);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; j++) *reinterpret_cast<uint16_t*>(d + j * ds) = *reinterpret_cast<const uint16_t*>(m + (j + 2) * 4);
+        }
+      }
+    }
+    __syncwarp();
   }
 
-  if (f.tok_cnt) {  // Macroblock::has_nonzero_ (macroblock.cc:579,593)
-    build_residuals(J, f, s_coef[warp], lane);
-    add_residuals(pix, s_coef[warp], lane);
-  }
+  if (nz) add_residuals(pix, S.coef, nz, S.nzlist, lane);
   store_mb(pix, J.out, g, col, row, lane);
 }
 
@@ -525,7 +756,7 @@ constexpr int WF_WARPS = 2;
 __global__ void __launch_bounds__(32 * WF_WARPS, 24) k_intra(const DevJob* __restrict__ jobs, int njobs, Geom g, int* ticket) {
   __shared__ __align__(16) uint8_t s_W[WF_WARPS][17 * WS];
   __shared__ __align__(16) uint8_t s_pixc[WF_WARPS][128];  // U 8x8, V 8x8
-  __shared__ __align__(16) int16_t s_coef[WF_WARPS][25 * CS];
+  __shared__ __align__(16) int16_t s_coef[WF_WARPS][COEF_I16];
   __shared__ uint8_t s_aboveC[WF_WARPS][2][12];  // [0] = above-left, [1..8] = above
   __shared__ uint8_t s_leftC[WF_WARPS][2][8];
   __shared__ uint16_t s_lut[WF_WARPS][128];
@@ -1091,7 +1322,7 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 12) k_enc_mb(const EncJob* __re
   __shared__ __align__(16) uint8_t s_pixc[WF_WARPS][128];
   __shared__ __align__(16) uint8_t s_src[WF_WARPS][384];
   __shared__ __align__(16) uint8_t s_pinter[WF_WARPS][384];
-  __shared__ __align__(16) int16_t s_coef[WF_WARPS][25 * CS];
+  __shared__ __align__(16) int16_t s_coef[WF_WARPS][COEF_I16];
   __shared__ __align__(16) uint8_t s_tile[WF_WARPS][21 * 24];
   __shared__ __align__(16) uint8_t s_mid[WF_WARPS][21 * 16];
   __shared__ uint8_t s_aboveC[WF_WARPS][2][12];

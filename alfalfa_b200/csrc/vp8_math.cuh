@@ -124,6 +124,78 @@ VP8_HD int sixtap(int p0, int p1, int p2, int p3, int p4, int p5, const int16_t*
   return clamp255((p0 * t[0] + p1 * t[1] + p2 * t[2] + p3 * t[3] + p4 * t[4] + p5 * t[5] + 64) >> 7);
 }
 
+// ---- the same filter on packed pixels (what k_inter executes) ---------------------------------
+// Every non-identity tap set fits a signed byte (|tap| <= 123), so a row of six taps is two 4-byte
+// dot products: t03 = taps 0..3, t45 = taps 4..5 (upper two bytes zero).
+VP8_HD uint32_t pack_taps03(const int16_t* t) {
+  return (uint32_t)(uint8_t)t[0] | ((uint32_t)(uint8_t)t[1] << 8) | ((uint32_t)(uint8_t)t[2] << 16) | ((uint32_t)(uint8_t)t[3] << 24);
+}
+VP8_HD uint32_t pack_taps45(const int16_t* t) { return (uint32_t)(uint8_t)t[4] | ((uint32_t)(uint8_t)t[5] << 8); }
+// c + sum over the four bytes of (unsigned byte of a) * (signed byte of b)
+VP8_HD int dot4_us(uint32_t a, uint32_t b, int c) {
+#ifdef __CUDA_ARCH__
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+#else
+  for (int k = 0; k < 4; k++) c += (int)((a >> (8 * k)) & 0xFF) * (int)(int8_t)((b >> (8 * k)) & 0xFF);
+  return c;
+#endif
+}
+// bytes [s/8 .. s/8+3] of the 8-byte sequence lo | hi << 32 (s = 0, 8, 16, 24)
+VP8_HD uint32_t bytes_at(uint32_t lo, uint32_t hi, int s) {
+#ifdef __CUDA_ARCH__
+  return __funnelshift_r(lo, hi, s);
+#else
+  return s ? (lo >> s) | (hi << (32 - s)) : lo;
+#endif
+}
+// sat_u8(v3) << 24 | sat_u8(v2) << 16 | sat_u8(v1) << 8 | sat_u8(v0)
+VP8_HD uint32_t pack_sat4(int v0, int v1, int v2, int v3) {
+#ifdef __CUDA_ARCH__
+  uint32_t t, d;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(v3), "r"(v2), "r"(0));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(v1), "r"(v0), "r"(t));
+  return d;
+#else
+  return (uint32_t)clamp255(v0) | ((uint32_t)clamp255(v1) << 8) | ((uint32_t)clamp255(v2) << 16) | ((uint32_t)clamp255(v3) << 24);
+#endif
+}
+VP8_HD uint32_t pack_sat2(int v0, int v1) {
+#ifdef __CUDA_ARCH__
+  uint32_t d;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(v1), "r"(v0), "r"(0));
+  return d;
+#else
+  return (uint32_t)clamp255(v0) | ((uint32_t)clamp255(v1) << 8);
+#endif
+}
+// horizontal pass: four outputs from twelve consecutive pixels w0 | w1 | w2 (output j uses pixels j .. j+5)
+VP8_HD uint32_t sixtap_h4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t t03, uint32_t t45) {
+  int v[4];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int j = 0; j < 4; j++)
+    v[j] = dot4_us(bytes_at(w1, w2, 8 * j), t45, dot4_us(bytes_at(w0, w1, 8 * j), t03, 64)) >> 7;
+  return pack_sat4(v[0], v[1], v[2], v[3]);
+}
+// vertical pass on pixel PAIRS: each p[k] holds two pixels of row k in its 16-bit halves
+// (pixel | pixel' << 16).  With a bias of 8192 + 64 per half neither half can borrow from or carry into
+// the other (a filtered sum lies in [-8160, 40800]), so six 32-bit multiply-adds filter two columns.
+// Returns sat_u8(out) | sat_u8(out') << 8.
+VP8_HD uint32_t pair_of(uint32_t two_bytes) { return (two_bytes & 0xFF) | ((two_bytes & 0xFF00) << 8); }
+VP8_HD uint32_t sixtap_v2(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t p4, uint32_t p5, const int16_t* t) {
+  const uint32_t acc = 0x20402040u + p0 * (uint32_t)(int)t[0] + p1 * (uint32_t)(int)t[1] + p2 * (uint32_t)(int)t[2] +
+                       p3 * (uint32_t)(int)t[3] + p4 * (uint32_t)(int)t[4] + p5 * (uint32_t)(int)t[5];
+  return pack_sat2((int)((acc >> 7) & 0x1FF) - 64, (int)(acc >> 23) - 64);
+}
+// pixel + residual with saturation on four pixels: r01 / r23 hold the int16 residuals of pixels 0,1 / 2,3
+VP8_HD uint32_t add_residual4(uint32_t pix, uint32_t r01, uint32_t r23) {
+  return pack_sat4((int)(pix & 0xFF) + (int)(int16_t)(r01 & 0xFFFF), (int)((pix >> 8) & 0xFF) + ((int)r01 >> 16),
+                   (int)((pix >> 16) & 0xFF) + (int)(int16_t)(r23 & 0xFFFF), (int)(pix >> 24) + ((int)r23 >> 16));
+}
+
 // ---- 4x4 directional intra prediction through the generated table (tools/gen_bpred_lut.py) ----
 // s = 13-entry edge vector: s[0..3] = left[3..0], s[4] = above[-1], s[5..12] = above[0..7]
 VP8_HD int bpred_eval(unsigned entry, const uint8_t* s) {

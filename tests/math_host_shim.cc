@@ -67,4 +67,45 @@ void m_sixtap(const uint8_t* window, int n, int mx, int my, uint8_t* out) {
       out[r * n + c] = my ? (uint8_t)vp8m::sixtap(m[0], m[n], m[2 * n], m[3 * n], m[4 * n], m[5 * n], kSixtap[my]) : m[2 * n];
     }
 }
+// the packed filter arithmetic of k_inter (sixtap_h4 / sixtap_v2 / add_residual4) on the same window
+void m_sixtap_packed(const uint8_t* window, int n, int mx, int my, uint8_t* out) {
+  const int ws = n + 5;
+  uint8_t mid[21 * 16];
+  if (mx == 0 && my == 0) {
+    for (int y = 0; y < n; y++) memcpy(out + y * n, window + (y + 2) * ws + 2, n);
+    return;
+  }
+  for (int r = 0; r < n + 5; r++)
+    for (int g = 0; g < n / 4; g++) {
+      uint8_t b[12];
+      for (int k = 0; k < 12; k++) b[k] = (4 * g + k < ws) ? window[r * ws + 4 * g + k] : 0xEE;  // bytes past the window never matter
+      uint32_t w[3];
+      memcpy(w, b, 12);
+      uint32_t o;
+      if (mx) o = vp8m::sixtap_h4(w[0], w[1], w[2], vp8m::pack_taps03(kSixtap[mx]), vp8m::pack_taps45(kSixtap[mx]));
+      else memcpy(&o, b + 2, 4);
+      memcpy(mid + r * n + 4 * g, &o, 4);
+    }
+  for (int r = 0; r < n; r++)
+    for (int c = 0; c < n; c += 2) {
+      if (!my) {
+        out[r * n + c] = mid[(r + 2) * n + c];
+        out[r * n + c + 1] = mid[(r + 2) * n + c + 1];
+        continue;
+      }
+      uint32_t p[6];
+      for (int k = 0; k < 6; k++) p[k] = vp8m::pair_of((uint32_t)mid[(r + k) * n + c] | ((uint32_t)mid[(r + k) * n + c + 1] << 8));
+      const uint32_t o = vp8m::sixtap_v2(p[0], p[1], p[2], p[3], p[4], p[5], kSixtap[my]);
+      out[r * n + c] = (uint8_t)(o & 0xFF);
+      out[r * n + c + 1] = (uint8_t)(o >> 8);
+    }
+}
+void m_add_residual4(const uint8_t* px, const int16_t* r, uint8_t* out) {
+  uint32_t p, r01, r23;
+  memcpy(&p, px, 4);
+  memcpy(&r01, r, 4);
+  memcpy(&r23, r + 2, 4);
+  const uint32_t o = vp8m::add_residual4(p, r01, r23);
+  memcpy(out, &o, 4);
+}
 }

@@ -96,6 +96,24 @@ def test_sixtap(libs, n):
                 M.m_sixtap(_p(win), n, mx, my, _p(a))
                 L.vp8o_test_sixtap(_p(win), n, mx, my, _p(b))
                 assert np.array_equal(a, b), (it, mx, my)
+                # the packed arithmetic k_inter executes (dp4a rows, biased 16-bit pairs for columns)
+                c = np.zeros(n * n, np.uint8)
+                M.m_sixtap_packed(_p(win), n, mx, my, _p(c))
+                assert np.array_equal(c, b), ("packed", it, mx, my)
+
+
+def test_add_residual_packed(libs):
+    """pixel + residual with saturation on packed words (k_inter's add_residual4) == clamp255(p + r)"""
+    M, _ = libs
+    rng = np.random.default_rng(8)
+    for it in range(4000):
+        px = rng.integers(0, 256, 4).astype(np.uint8)
+        scale = [3, 300, 32767][it % 3]
+        r = rng.integers(-scale - 1, scale + 1, 4).astype(np.int16)
+        out = np.zeros(4, np.uint8)
+        M.m_add_residual4(_p(px), _p(r), _p(out))
+        want = np.clip(px.astype(np.int32) + r.astype(np.int32), 0, 255).astype(np.uint8)
+        assert np.array_equal(out, want), (it, px, r)
 
 
 def test_forward_dct_and_wht(libs):
