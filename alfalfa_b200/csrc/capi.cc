@@ -59,8 +59,8 @@ struct vp8gpu_parsed {
   explicit vp8gpu_parsed(const vp8::Allocator& a) : f(a) {}
 };
 // what one vp8gpu_decode_ivf worker needs for device-side token decoding
-constexpr int kTokSlots = 64;  // frames a worker may have between "first partition parsed" and "pixels done"
-constexpr int kTokChunk = 15;  // frames per k_tokens launch (at most a quarter of the slots)
+constexpr int kTokSlots = 96;  // frames a worker may have between "first partition parsed" and "pixels done"
+constexpr int kTokChunk = 32;  // frames per k_tokens launch: one lane each (at most a third of the slots)
 constexpr int kTokStreams = 4; // k_tokens launches of one worker that may overlap
 struct ivf_worker_kit {
   vp8::TokenRing* ring = nullptr;
@@ -754,17 +754,17 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     tok_slots = e->frames_free() / threads - 4;
     // k_tokens needs tens of milliseconds per frame (one thread each), so a worker wants to run a
     // GOP or two ahead of the pixel kernels; bounded by a device-memory budget for the rings
-    const size_t ring_budget = (size_t)12 << 30;
+    const size_t ring_budget = (size_t)40 << 30;
     const size_t stride = e->token_ring_layout(ring_bytes_for(max_frame_bytes)).stride;
     int want = (int)(ring_budget / (stride * (size_t)threads));
-    if (want > 60) want = 60;
+    if (want > kTokSlots) want = kTokSlots;
     if (const char* v = getenv("VP8GPU_TOK_SLOTS")) want = atoi(v);  // tuning knob
     if (want > kTokSlots) want = kTokSlots;
     if (tok_slots > want) tok_slots = want;
     if (tok_slots < 4) tok_slots = 0;  // pool too small: the host workers parse everything
   }
   const bool device_tokens = tok_slots > 0;
-  int tok_chunk = tok_slots / 4 > kTokChunk ? kTokChunk : (tok_slots / 4 > 0 ? tok_slots / 4 : 1);
+  int tok_chunk = tok_slots / 3 > kTokChunk ? kTokChunk : (tok_slots / 3 > 0 ? tok_slots / 3 : 1);
   if (const char* v = getenv("VP8GPU_TOK_CHUNK")) {  // tuning knob
     const int c = atoi(v);
     if (c >= 1 && c <= tok_slots / 2) tok_chunk = c;

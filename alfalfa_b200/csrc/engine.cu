@@ -18,6 +18,31 @@ int launch_hash(const uint8_t* a, const Geom& g, unsigned long long* d_out, void
 
 namespace {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Tensor maps live in a per-device arena whose slots are handed out once and never reused or freed: a map
+// is written (cudaMemcpy) before the first kernel that can see its address is launched and is immutable
+// afterwards, so the TMA unit's descriptor cache can never hold a stale copy and k_inter needs no
+// tensormap-proxy fence per use (measured: one `fence.proxy.tensormap::generic.acquire.sys` per window
+// makes k_inter 9x slower).  384 bytes per raster.
+std::mutex g_tmap_mu;
+struct TmapChunk {
+  uint8_t* base;
+  size_t used, cap;
+};
+std::vector<TmapChunk> g_tmap_chunks[64];
+uint8_t* tmap_arena_alloc(int device, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  if (device < 0 || device >= 64) return nullptr;
+  auto& chunks = g_tmap_chunks[device];
+  if (chunks.empty() || chunks.back().used + bytes > chunks.back().cap) {
+    TmapChunk c{nullptr, 0, bytes > ((size_t)4 << 20) ? bytes : ((size_t)4 << 20)};
+    if (cudaMalloc(&c.base, c.cap) != cudaSuccess) return nullptr;
+    chunks.push_back(c);
+  }
+  uint8_t* p = chunks.back().base + chunks.back().used;
+  chunks.back().used += align_up(bytes, 128);
+  return p;
+}
 constexpr int kSyncHeaderInts = 64;  // [0] = intra ticket, [32] = loop-filter ticket (own cache lines)
 }  // namespace
 
@@ -66,8 +91,9 @@ int Engine::create(int device, int width, int height, int max_frames, Engine** o
   g.v_off = g.u_off + (uint32_t)((size_t)g.c_pitch * (g.H / 2));
   g.frame_bytes = g.v_off + (uint32_t)((size_t)g.c_pitch * (g.H / 2));
   if (max_frames <= 0) max_frames = 64;
-  if (cudaMalloc(&en->tmaps_, (size_t)max_frames * 384) != cudaSuccess) {
-    if (err) *err = "cudaMalloc(tensor maps) failed";
+  en->tmaps_ = tmap_arena_alloc(device, (size_t)max_frames * 384);
+  if (!en->tmaps_) {
+    if (err) *err = "cudaMalloc(tensor map arena) failed";
     delete en;
     return VP8GPU_ERR_CUDA;
   }
@@ -95,7 +121,7 @@ Engine::~Engine() {
   for (auto& s : lanes_)
     if (s) cudaStreamDestroy(s);
   if (cmp_scratch_) cudaFree(cmp_scratch_);
-  if (tmaps_) cudaFree(tmaps_);
+  // tmaps_ belongs to the tensor-map arena: never reused, never freed
 }
 
 // One 2-D tensor map per plane of raster `id` (u8 elements, plane size W x H resp. W/2 x H/2, row pitch
@@ -519,6 +545,8 @@ TokenRing Engine::token_ring_layout(size_t max_frame_bytes) const {
   size_t off = 256;  // TokJob
   r.probs_off = off;
   off += 1280;
+  r.info_off = off;  // 2 bits per macroblock for the lock-step token decoder, one word of slack
+  off = align_up(off + 4 * ((n_mbs + 15) / 16 + 1), 256);
   r.bits_off = off;
   off = align_up(off + r.bits_cap, 256);
   r.host_stride = off;
@@ -573,6 +601,7 @@ int Engine::token_ring_stage(TokenRing* r, int slot, const ParsedFrame& f, cudaS
   j->coef_probs = d + r->probs_off;
   j->result = reinterpret_cast<uint32_t*>(d + r->result_off);
   j->above = reinterpret_cast<uint16_t*>(d + r->above_off);
+  j->mbinfo = reinterpret_cast<const uint32_t*>(d + r->info_off);
   memcpy(j->part_off, tw.part_off, sizeof(j->part_off));
   memcpy(j->part_len, tw.part_len, sizeof(j->part_len));
   j->nparts = tw.nparts;
@@ -580,6 +609,16 @@ int Engine::token_ring_stage(TokenRing* r, int slot, const ParsedFrame& f, cudaS
   memcpy(h + r->probs_off, tw.coef_probs, 1056);
   memcpy(h + r->bits_off, tw.bits, tw.bits_len);
   const size_t n_mbs = (size_t)g_.mb_cols * g_.mb_rows;
+  {
+    uint32_t* info = reinterpret_cast<uint32_t*>(h + r->info_off);
+    const vp8gpu_mb* m = f.mbs.data();
+    for (size_t w = 0; w < (n_mbs + 15) / 16; w++) {
+      uint32_t v = 0;
+      const size_t n = n_mbs - 16 * w < 16 ? n_mbs - 16 * w : 16;
+      for (size_t k = 0; k < n; k++) v |= (uint32_t)(m[16 * w + k].flags & 3u) << (2 * k);
+      info[w] = v;
+    }
+  }
   CU(cudaMemcpyAsync(d, h, r->bits_off + align_up(tw.bits_len, 16), cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(d + r->mbs_off, f.mbs.data(), n_mbs * sizeof(vp8gpu_mb), cudaMemcpyHostToDevice, s));
   if (f.desc.n_split)

@@ -63,7 +63,8 @@ struct TokJob {
   const uint8_t* bits;        // the frame's DCT partitions, back to back
   const uint8_t* coef_probs;  // 1056 bytes: the frame's coefficient probabilities
   uint32_t* result;           // [0] tokens written, [1] non-zero if the pool was too small
-  uint16_t* above;            // mb_cols zeroed words of scratch (lock-step variant: the row of contexts above)
+  uint16_t* above;            // mb_cols words of scratch (unused since the lock-step decoder keeps its contexts in shared memory)
+  const uint32_t* mbinfo;     // lock-step variant: 2 bits per macroblock (flags & 3), 16 macroblocks per word
   uint32_t part_off[8], part_len[8];
   uint32_t nparts;            // 1, 2, 4 or 8
   uint32_t tok_cap;

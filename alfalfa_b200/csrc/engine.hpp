@@ -25,7 +25,7 @@ struct TokenRing {
   uint8_t* dev = nullptr;
   uint8_t* host = nullptr;       // pinned mirror of the first three parts of every slot
   size_t stride = 0, host_stride = 0;
-  size_t probs_off = 0, bits_off = 0, result_off = 0, above_off = 0, mbs_off = 0, split_off = 0, tok_off = 0;
+  size_t probs_off = 0, info_off = 0, bits_off = 0, result_off = 0, above_off = 0, mbs_off = 0, split_off = 0, tok_off = 0;
   uint32_t bits_cap = 0, split_cap = 0, tok_cap = 0;
   uint8_t* dev_slot(int i) const { return dev + (size_t)i * stride; }
   uint8_t* host_slot(int i) const { return host + (size_t)i * host_stride; }

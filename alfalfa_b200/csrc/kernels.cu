@@ -416,10 +416,16 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int x, 
                "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
                : "memory");
 }
-// A tensor map that lives in global memory and was written by the host (cudaMemcpy) must be acquired by
-// the thread that is going to use it (tensormap proxy, system scope) before its first use.
+// A tensor map in global memory that is MODIFIED while kernels can see it must be acquired (tensormap
+// proxy) by the thread that uses it.  Ours are written once into never-reused arena slots before any
+// kernel gets their address (engine.cu tmap_arena_alloc), so the fence is compiled out; building with
+// -DVP8_TMAP_FENCE puts it back (9x slower k_inter, same results).
 __device__ __forceinline__ void tmap_acquire(const void* tmap) {
+#ifdef VP8_TMAP_FENCE
   asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(tmap) : "memory");
+#else
+  (void)tmap;
+#endif
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
   uint32_t done;

@@ -46,29 +46,53 @@ __global__ void __launch_bounds__(32 * kTokWarps) k_tokens(const uint8_t* ring, 
   tok::decode_frame_tokens(J, g, probs, above_nz);
 }
 
-// lock-step variant: one LANE per frame, 32 frames per warp (tokens_core.cuh decode_frame_tokens_lockstep)
+// lock-step variant: one LANE per frame, 32 frames per warp (tokens_core.cuh decode_frame_tokens_lockstep).
+// Dynamic shared memory: the 32 frames' probability tables transposed ([1056][32] bytes: lanes at the same
+// tree position read one 32-byte row), then the 32 rows of above-contexts, also transposed ([mb_cols][32]).
 __global__ void __launch_bounds__(32) k_tokens_lockstep(const uint8_t* ring, size_t stride, int first, int count,
                                                          int nslots, Geom g) {
+  extern __shared__ __align__(16) uint8_t dyn[];
   __shared__ tok::LockstepTables T;
+  uint8_t* const P = dyn;
+  uint16_t* const above = reinterpret_cast<uint16_t*>(dyn + 1056 * 32);
   const int lane = threadIdx.x;
   tok::fill_lockstep_tables(T, lane, 32);
-  __syncwarp();
   const int job = blockIdx.x * 32 + lane;
-  if (job >= count) return;
-  const TokJob& J = *reinterpret_cast<const TokJob*>(ring + static_cast<size_t>((first + job) % nslots) * stride);
-  tok::decode_frame_tokens_lockstep(J, g, T);
+  const TokJob* J = job < count ? reinterpret_cast<const TokJob*>(ring + static_cast<size_t>((first + job) % nslots) * stride) : nullptr;
+  if (J) {  // this frame's 1056 probabilities -> column `lane` (the table in HBM is 4-byte aligned, 264 words)
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(J->coef_probs);
+    for (int w = 0; w < 264; w++) {
+      const uint32_t v = __ldg(src + w);
+      P[(4 * w + 0) * 32 + lane] = v & 0xFF;
+      P[(4 * w + 1) * 32 + lane] = (v >> 8) & 0xFF;
+      P[(4 * w + 2) * 32 + lane] = (v >> 16) & 0xFF;
+      P[(4 * w + 3) * 32 + lane] = v >> 24;
+    }
+  }
+  __syncwarp();
+  if (!J) return;
+  tok::decode_frame_tokens_lockstep<32>(*J, g, T, P + lane, above + lane);
 }
 
 }  // namespace
 
 int launch_tokens(const uint8_t* ring, size_t stride, int first, int count, int nslots, const Geom& g, void* stream) {
   if (g.mb_cols > kMaxCols) return (int)cudaErrorInvalidValue;
-  static const int warps = [] {  // tuning knob: frames per CTA (1 or 8); 32 = one lane per frame
+  // Variant knob.  1 (default) = one warp per frame, lane 0 decodes: ~60 cycles per decision, 17 ms per 53 KB
+  // 1080p frame, but a whole warp instruction per decision.  32 = one LANE per frame (lock-step state
+  // machine, 32 x fewer issue slots, ~150 cycles per decision: 3 x the latency per frame; measured slower end
+  // to end while the pipeline is bounded by frames in flight, profiles/r2_notes.md).  8 = 8 frames per CTA.
+  static const int warps = [] {
     const char* v = getenv("VP8GPU_TOK_WARPS");
     return v && atoi(v) == 8 ? 8 : (v && atoi(v) == 32 ? 32 : 1);
   }();
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (warps == 32) k_tokens_lockstep<<<(count + 31) / 32, 32, 0, s>>>(ring, stride, first, count, nslots, g);
+  if (warps == 32) {
+    const size_t smem = 1056 * 32 + (size_t)g.mb_cols * 32 * sizeof(uint16_t);
+    static const cudaError_t attr = cudaFuncSetAttribute(k_tokens_lockstep, cudaFuncAttributeMaxDynamicSharedMemorySize, 1056 * 32 + kMaxCols * 64);
+    if (attr != cudaSuccess) return (int)attr;
+    k_tokens_lockstep<<<(count + 31) / 32, 32, smem, s>>>(ring, stride, first, count, nslots, g);
+  }
   else if (warps == 8) k_tokens<8><<<(count + 7) / 8, 256, 0, s>>>(ring, stride, first, count, nslots, g);
   else k_tokens<1><<<count, 32, 0, s>>>(ring, stride, first, count, nslots, g);
   return (int)cudaGetLastError();

@@ -289,29 +289,98 @@ TK_DEV void fill_lockstep_tables(LockstepTables& T, int lane, int nlanes) {
   }
 }
 
-// probs = the frame's 1056 probabilities as the header leaves them ([type][band][ctx][node]);
-// J.above = mb_cols words of per-frame scratch (the row of contexts above)
-TK_DEV void decode_frame_tokens_lockstep(const TokJob& J, const Geom& g, const LockstepTables& T) {
-  const uint8_t* const probs = J.coef_probs;
-  uint16_t* const above_nz = J.above;
-  for (int c = 0; c < g.mb_cols; c++) above_nz[c] = 0;
-  BoolReader parts[8];
+// ---- bit reader of the lock-step decoder ---------------------------------------------------------
+// Same decisions as BoolReader above, different plumbing: in lock-step a lane that waits for memory
+// stalls the other 31, so the stream is fetched as aligned 32-bit words ONE REFILL AHEAD (`nxt` is
+// requested when the previous word is consumed, ~30 decisions before it is needed).  The window is
+// consumed from the top and always holds >= 32 valid bits; past the end of the partition only zero
+// bits arrive (bool_decoder.hh:82-107).
+#ifdef __CUDACC__
+#define TK_BSWAP(x) __byte_perm((x), 0, 0x0123)
+#else
+#define TK_BSWAP(x) __builtin_bswap32(x)
+#endif
+struct LaneReader {
+  const uint8_t* p;    // next word to request (4-byte aligned)
+  const uint8_t* end;
+  uint64_t value;
+  int nbits;
+  uint32_t nxt;        // the next 32 bits of the stream, most significant bit first
+  uint32_t range;
+};
+TK_DEV uint32_t lr_fetch(LaneReader& b) {
+  uint32_t w = 0;
+  if (b.p + 4 <= b.end) {
+    w = TK_BSWAP(TK_LDG(reinterpret_cast<const uint32_t*>(b.p)));
+  } else {
+    for (int k = 0; k < 4; k++)
+      if (b.p + k < b.end) w |= static_cast<uint32_t>(TK_LDG(b.p + k)) << (24 - 8 * k);
+  }
+  b.p += 4;
+  return w;
+}
+TK_DEV void lr_refill(LaneReader& b) {  // nbits <= 32 on entry
+  b.value |= static_cast<uint64_t>(b.nxt) << (32 - b.nbits);
+  b.nbits += 32;
+  b.nxt = lr_fetch(b);
+}
+TK_DEV void lr_init(LaneReader& b, const uint8_t* data, uint32_t n) {
+  b.p = data;
+  b.end = data + n;
+  b.value = 0;
+  b.nbits = 0;
+  b.range = 255;
+  while ((reinterpret_cast<uintptr_t>(b.p) & 3) && b.p < b.end) {  // up to three bytes to reach a word boundary
+    b.value |= static_cast<uint64_t>(TK_LDG(b.p++)) << (56 - b.nbits);
+    b.nbits += 8;
+  }
+  if (b.p >= b.end) b.p = reinterpret_cast<const uint8_t*>((reinterpret_cast<uintptr_t>(b.p) + 3) & ~static_cast<uintptr_t>(3));
+  b.nxt = lr_fetch(b);
+  lr_refill(b);
+  if (b.nbits <= 32) lr_refill(b);
+}
+TK_DEV int lr_get(LaneReader& b, uint32_t prob) {
+  const uint32_t split = 1 + (((b.range - 1) * prob) >> 8);
+  uint32_t hi = static_cast<uint32_t>(b.value >> 32);
+  const uint32_t big = split << 24;
+  const int bit = hi >= big;
+  const uint32_t r = bit ? b.range - split : split;
+  hi -= bit ? big : 0u;
+  const int shift = TK_CLZ(r) - 24;
+  b.range = r << shift;
+  b.value = ((static_cast<uint64_t>(hi) << 32) | static_cast<uint32_t>(b.value)) << shift;
+  b.nbits -= shift;
+  if (b.nbits <= 32) lr_refill(b);
+  return bit;
+}
+
+// One lane = one frame.  P = this lane's column of the transposed probability table ([1056 entries][LS
+// lanes] bytes: entry e of this frame at P[e * LS]), above = this lane's column of the transposed row of
+// contexts ([mb_cols][LS] words); on the device both live in shared memory, LS = 32.  J.mbinfo = 2 bits
+// per macroblock (flags & 3: VP8GPU_MB_HAS_Y2 | VP8GPU_MB_SKIP), 16 macroblocks per word, read one word
+// ahead: the decoder never waits for a record.  Records get tok_off / tok_cnt / flags by plain stores.
+template <int LS>
+TK_DEV void decode_frame_tokens_lockstep(const TokJob& J, const Geom& g, const LockstepTables& T, const uint8_t* P,
+                                         uint16_t* above) {
+  for (int c = 0; c < g.mb_cols; c++) above[c * LS] = 0;
+  LaneReader parts[8];
   const int nparts = static_cast<int>(J.nparts);
-  for (int k = 0; k < nparts; k++) br_init(parts[k], J.bits + J.part_off[k], J.part_len[k]);
-  vp8gpu_mb* const mbs = J.mbs;
+  for (int k = 0; k < nparts; k++) lr_init(parts[k], J.bits + J.part_off[k], J.part_len[k]);
+  uint8_t* const mbs = reinterpret_cast<uint8_t*>(J.mbs);
   vp8gpu_token* const t_begin = J.tokens;
   vp8gpu_token* t = t_begin;
   vp8gpu_token* t0 = t_begin;
   const vp8gpu_token* const t_limit = t_begin + J.tok_cap;
   uint32_t overflow = 0;
-  const uint32_t* rec = reinterpret_cast<const uint32_t*>(mbs);
   const int n_mbs = g.mb_cols * g.mb_rows;
+  const int n_words = (n_mbs + 15) >> 4;
+  uint32_t info = n_words > 0 ? TK_LDG(J.mbinfo) : 0u, info_next = n_words > 1 ? TK_LDG(J.mbinfo + 1) : 0u;
 
-  BoolReader tr = parts[0];
+  LaneReader tr = parts[0];
   int idx = 0, col = 0, row = 0;
   unsigned a_nz = 0, left_nz = 0;
-  uint32_t cur1 = 0, cur2 = 0;
   int bq = 0, last_y_type = 0, first_y = 0;  // current block: -1 = Y2, 0..15 Y, 16..23 U V
+  int has_y2_cur = 0;
   int type_off = 0, bx = 0, by = 0;
   int i = 0, ctx = 0, node = kNodeEnd, nz = 0;
   int v = 0, acc = 0, cat = 0, nrem = 0, extra_k = 0;
@@ -326,11 +395,11 @@ TK_DEV void decode_frame_tokens_lockstep(const TokJob& J, const Geom& g, const L
         left_nz = (left_nz & ~(1u << by)) | (static_cast<unsigned>(nz) << by);
         bq++;
         if (bq == 24) {  // macroblock finished
-          above_nz[col] = static_cast<uint16_t>(a_nz);
-          uint32_t* wr = reinterpret_cast<uint32_t*>(mbs) + 8 * idx;
-          wr[0] = static_cast<uint32_t>(t0 - t_begin);
-          wr[1] = (cur1 & 0xFFFF0000u) | static_cast<uint32_t>(t - t0);
-          wr[2] = cur2 & ~(static_cast<uint32_t>(VP8GPU_MB_SKIP) << 24);
+          above[col * LS] = static_cast<uint16_t>(a_nz);
+          uint8_t* rec = mbs + 32 * static_cast<size_t>(idx);
+          *reinterpret_cast<uint32_t*>(rec) = static_cast<uint32_t>(t0 - t_begin);
+          *reinterpret_cast<uint16_t*>(rec + 4) = static_cast<uint16_t>(t - t0);
+          rec[11] = static_cast<uint8_t>(has_y2_cur ? VP8GPU_MB_HAS_Y2 : 0);
           idx++;
           col++;
           need_mb = true;
@@ -349,12 +418,16 @@ TK_DEV void decode_frame_tokens_lockstep(const TokJob& J, const Geom& g, const L
           left_nz = 0;
           tr = parts[row & (nparts - 1)];
         }
-        cur1 = TK_LDCG(rec + 8 * idx + 1);
-        cur2 = TK_LDCG(rec + 8 * idx + 2);
-        const int y_mode = (cur1 >> 16) & 0xFF;
-        const bool skip = (cur2 >> 24) & VP8GPU_MB_SKIP;
-        const bool has_y2 = y_mode != VP8GPU_B_PRED && y_mode != VP8GPU_SPLITMV;
-        a_nz = above_nz[col];
+        const unsigned bits2 = (info >> (2 * (idx & 15))) & 3u;
+        if ((idx & 15) == 15) {  // last macroblock of this word: move on, request the word after the next
+          info = info_next;
+          const int nw = (idx >> 4) + 2;
+          info_next = nw < n_words ? TK_LDG(J.mbinfo + nw) : 0u;
+        }
+        const bool skip = (bits2 & VP8GPU_MB_SKIP) != 0;
+        const bool has_y2 = (bits2 & VP8GPU_MB_HAS_Y2) != 0;
+        has_y2_cur = has_y2;
+        a_nz = above[col * LS];
         t0 = t;
         bool settled = false;
         if (skip) {  // frame.cc:252-269: without Y2 the previous Y2 context stays
@@ -369,11 +442,11 @@ TK_DEV void decode_frame_tokens_lockstep(const TokJob& J, const Geom& g, const L
           settled = true;
         }
         if (settled) {
-          above_nz[col] = static_cast<uint16_t>(a_nz);
-          uint32_t* wr = reinterpret_cast<uint32_t*>(mbs) + 8 * idx;
-          wr[0] = static_cast<uint32_t>(t0 - t_begin);
-          wr[1] = cur1 & 0xFFFF0000u;
-          wr[2] = cur2 & ~(static_cast<uint32_t>(VP8GPU_MB_SKIP) << 24);
+          above[col * LS] = static_cast<uint16_t>(a_nz);
+          uint8_t* rec = mbs + 32 * static_cast<size_t>(idx);
+          *reinterpret_cast<uint32_t*>(rec) = static_cast<uint32_t>(t0 - t_begin);
+          *reinterpret_cast<uint16_t*>(rec + 4) = 0;
+          rec[11] = static_cast<uint8_t>(has_y2 ? VP8GPU_MB_HAS_Y2 : 0);
           idx++;
           col++;
           continue;
@@ -400,10 +473,10 @@ TK_DEV void decode_frame_tokens_lockstep(const TokJob& J, const Geom& g, const L
 
     // ---- one decision (the same code for every lane) ----
     const int tree_node = node <= 10 ? node : 0;
-    const uint32_t p_tree = TK_LDG(probs + type_off + T.band[i & 15] * 33 + ctx * 11 + tree_node);
+    const uint32_t p_tree = P[(type_off + T.band[i & 15] * 33 + ctx * 11 + tree_node) * LS];
     const uint32_t p_extra = T.cat_prob[cat][extra_k];
     const uint32_t prob = node <= 10 ? p_tree : (node == kNodeExtra ? p_extra : 128u);
-    const int bit = br_get(tr, prob);
+    const int bit = lr_get(tr, prob);
 
     // ---- transition ----
     if (node <= 10) {

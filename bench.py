@@ -119,7 +119,7 @@ def clip_path(name):
     return name if os.path.isabs(name) else os.path.join(BD, name)
 
 
-def load_instances(names, inst_len=30):
+def load_instances(names, inst_len=30, per_clip=0):
     """The workload as independent streams ("instances"): every clip cut at key frames into runs of up to
     `inst_len` frames (one GOP of the synthetic clips; `inst_len` consecutive key frames of an all-key
     stream).  Returns (w, h, [list of frame bytes per instance])."""
@@ -131,6 +131,7 @@ def load_instances(names, inst_len=30):
         assert w in (None, cw) and h in (None, ch), "clips of one workload share a frame size"
         w, h = cw, ch
         cur = None
+        first = len(instances)
         for f in frames:
             key = not (f[0] & 1)
             if cur is None or (key and len(cur) >= inst_len):
@@ -138,12 +139,14 @@ def load_instances(names, inst_len=30):
                 instances.append(cur)
             if len(cur) < inst_len or not key:
                 cur.append(f)
+        if per_clip:
+            del instances[first + per_clip:]
     return w, h, [i for i in instances if i]
 
 
 def make_ivf(w, h, frames):
     import struct
-    out = [b"DKIF" + struct.pack("<HH4sHHIII", 0, 32, b"VP80", w, h, 30, 1, len(frames), 0)]
+    out = [b"DKIF" + struct.pack("<HH4sHHIIII", 0, 32, b"VP80", w, h, 30, 1, len(frames), 0)]
     for k, f in enumerate(frames):
         out.append(struct.pack("<IQ", len(f), k))
         out.append(f)
@@ -325,7 +328,7 @@ def main():
 
     from alfalfa_b200 import Context, capi
 
-    w, h, instances = load_instances(WORKLOADS[a.workload])
+    w, h, instances = load_instances(WORKLOADS[a.workload], per_clip=1 if a.workload == "720p" else 0)
     mpix_frame = w * h / 1e6
     L = capi.lib()
     n_mbs = ((w + 15) // 16) * ((h + 15) // 16)
@@ -503,7 +506,7 @@ def main():
     R = a.replicas or max(1, -(-4 * threads // n_inst))
     if a.workload == "4k":
         R = a.replicas or max(1, -(-threads // n_inst))
-    ctx2 = Context(w, h, device=local, max_frames=threads * (10 if a.host_tokens else int(os.environ.get("VP8GPU_TOK_SLOTS", 60)) + 6) + 64)
+    ctx2 = Context(w, h, device=local, max_frames=threads * (10 if a.host_tokens else int(os.environ.get("VP8GPU_TOK_SLOTS", 96)) + 6) + 64)
     ctx2.set_device_tokens(not a.host_tokens)
     dst = C.c_void_p()
     while True:  # the pinned output buffer is w*h*1.5 bytes per frame: halve the run if the box cannot pin that much

@@ -55,10 +55,14 @@ int th_frame(void* hp, const uint8_t* data, size_t len, uint32_t tok_cap_overrid
   J.nparts = H.pb.tw.nparts;
   J.tok_cap = (uint32_t)cap;
   if (H.lockstep) {
-    J.above = H.above.data();
+    // what Engine::token_ring_stage prepares: 2 bits per macroblock (flags & 3), 16 macroblocks per word
+    std::vector<uint32_t> mbinfo((n_mbs + 15) / 16 + 1, 0);
+    for (size_t i = 0; i < n_mbs; i++) mbinfo[i >> 4] |= (uint32_t)(H.pb.mbs.data()[i].flags & 3u) << (2 * (i & 15));
+    J.mbinfo = mbinfo.data();
     vp8::tok::LockstepTables T;
     vp8::tok::fill_lockstep_tables(T, 0, 1);
-    vp8::tok::decode_frame_tokens_lockstep(J, g, T);
+    // one lane: the "transposed" tables are the plain ones
+    vp8::tok::decode_frame_tokens_lockstep<1>(J, g, T, H.pb.tw.coef_probs, H.above.data());
   } else {
     alignas(16) uint8_t probs16[vp8::tok::kProbBytes];
     for (int e = 0; e < vp8::tok::kProbEntries; e++) vp8::tok::expand_prob_entry(H.pb.tw.coef_probs, probs16, e);
