@@ -45,7 +45,26 @@ struct vp8gpu_ctx {
   std::mutex scratch_mu;
   vp8::TokenRing* scratch_ring = nullptr;
   std::vector<struct ivf_worker_kit*> kit_pool;
+  // Optional limit (off by default, see vp8gpu_decode_ivf) on the frames whose DCT partitions may be on the
+  // device at the same time: counting semaphore, released by a host function the token stream runs after the
+  // kernel.
+  std::mutex tok_mu;
+  std::condition_variable tok_cv;
+  int tok_permits = 0, tok_capacity = 0;
 };
+struct TokRelease {
+  vp8gpu_ctx* ctx;
+  int n;
+};
+static void CUDART_CB tok_release_cb(void* p) {
+  TokRelease* r = static_cast<TokRelease*>(p);
+  {
+    std::lock_guard<std::mutex> lk(r->ctx->tok_mu);
+    r->ctx->tok_permits += r->n;
+  }
+  r->ctx->tok_cv.notify_all();
+  delete r;
+}
 struct vp8gpu_state {
   State s;
   vp8gpu_state(int w, int h) : s(w, h) {}
@@ -764,6 +783,19 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     if (tok_slots < 4) tok_slots = 0;  // pool too small: the host workers parse everything
   }
   const bool device_tokens = tok_slots > 0;
+  if (device_tokens) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device());
+    // Measured (profiles/r2_notes.md): limiting the token warps to 2 / 4 / 8 per SM HALVES the whole-decode
+    // throughput (7.6k / 9.3k / 8.4k vs 16.2k Mpix/s unlimited on the same box), so the default is no limit;
+    // the knob stays for experiments: VP8GPU_TOK_INFLIGHT=<frames>, 0 = unlimited.
+    int cap = 0;
+    (void)sms;
+    if (const char* v = getenv("VP8GPU_TOK_INFLIGHT")) cap = atoi(v);
+    std::lock_guard<std::mutex> lk(ctx->tok_mu);
+    ctx->tok_capacity = cap;
+    ctx->tok_permits = cap;  // every earlier call has returned: all permits are back
+  }
   int tok_chunk = tok_slots / 3 > kTokChunk ? kTokChunk : (tok_slots / 3 > 0 ? tok_slots / 3 : 1);
   if (const char* v = getenv("VP8GPU_TOK_CHUNK")) {  // tuning knob
     const int c = atoi(v);
@@ -990,7 +1022,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
         launches_done++;
         const int n = (int)left < want ? (int)left : want;
         const int first_slot = next_slot;
-        int staged = 0;
+        int staged = 0, permits_taken = 0;
         for (int c = 0; c < n && rc == VP8GPU_OK; c++) {
           const int si = (first_slot + c) % tok_slots;
           const double t0 = now();
@@ -1020,12 +1052,26 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
         kit->next_kstream = (kit->next_kstream + 1) % kTokStreams;
         cudaEventRecord(kit->staged[first_slot], kit->copy_stream);
         cudaStreamWaitEvent(ks, kit->staged[first_slot], 0);
+        if (ctx->tok_capacity > 0) {  // permits for the frames of this launch (returned by tok_release_cb when the kernel is done)
+          std::unique_lock<std::mutex> lk(ctx->tok_mu);
+          const int need = staged < ctx->tok_capacity ? staged : ctx->tok_capacity;
+          ctx->tok_cv.wait(lk, [&] { return ctx->tok_permits >= need; });
+          ctx->tok_permits -= need;
+          permits_taken = need;
+        }
         // the ring is used modulo tok_slots (<= its real size): a chunk that wraps needs two launches
         const int until_wrap = tok_slots - first_slot;
         rc = e->token_ring_launch(kit->ring, first_slot, staged < until_wrap ? staged : until_wrap, ks);
         if (rc == VP8GPU_OK && staged > until_wrap) rc = e->token_ring_launch(kit->ring, 0, staged - until_wrap, ks);
+        if (rc == VP8GPU_OK)
+          for (int c = 0; c < staged; c++) cudaEventRecord(kit->ready[(first_slot + c) % tok_slots], ks);
+        // the permits come back when the stream gets here (also after a failed launch); queued after the
+        // `ready` events so that the host-function thread is not on the frames' critical path
+        if (permits_taken && cudaLaunchHostFunc(ks, tok_release_cb, new TokRelease{ctx, permits_taken}) != cudaSuccess) {
+          std::lock_guard<std::mutex> lk(ctx->tok_mu);
+          ctx->tok_permits += permits_taken;
+        }
         if (rc != VP8GPU_OK) break;
-        for (int c = 0; c < staged; c++) cudaEventRecord(kit->ready[(first_slot + c) % tok_slots], ks);
         for (int c = 0; c < staged && rc == VP8GPU_OK; c++) {
           const int si = (first_slot + c) % tok_slots;
           vp8gpu_parsed* p = kit->parsed[si];

@@ -1,0 +1,86 @@
+// enc_costs.cc -- see enc_costs.h.  Restates Costs::fill_mode_costs / fill_mv_ref_costs /
+// fill_mv_component_costs / fill_mv_sad_costs (encoder/costs.cc:64-221) over flat tables.
+#include "enc_costs.h"
+
+#include <math.h>
+#include <string.h>
+
+#include "vp8_enc_tables.h"
+#include "vp8_tables.h"
+
+namespace vp8 {
+namespace {
+
+inline uint16_t cost_zero(uint8_t p) { return k_prob_cost[p]; }
+inline uint16_t cost_one(uint8_t p) { return k_prob_cost[255 - p]; }  // complement() = 255 - p (costs.cc:53)
+inline uint16_t cost_bit(uint8_t p, bool b) { return b ? cost_one(p) : cost_zero(p); }
+
+// Costs::compute_cost (costs.cc:145-168): cost of every leaf of a token tree; leaves are <= 0 (value = -entry)
+void tree_costs(uint16_t* out, const uint8_t* probs, const int8_t* tree, int index, uint16_t cost) {
+  const uint8_t p = probs[index / 2];
+  for (int i = 0; i < 2; i++) {
+    const int entry = tree[index + i];
+    const uint16_t c = (uint16_t)(cost + cost_bit(p, i != 0));
+    if (entry <= 0) out[-entry] = c;
+    else tree_costs(out, probs, tree, entry, c);
+  }
+}
+
+// modemv_data.cc:162-215
+const int8_t kKfYModeTree[8] = {-4, 2, 4, 6, 0, -1, -2, -3};
+const int8_t kYModeTree[8] = {0, 2, 4, 6, -1, -2, -3, -4};
+const int8_t kBModeTree[18] = {0, 2, -1, 4, -2, 6, 8, 12, -3, 10, -5, -6, -4, 14, -7, 16, -8, -9};
+const int8_t kSmallMvTree[14] = {2, 8, 4, 6, 0, -1, -2, -3, 10, 12, -4, -5, -6, -7};
+
+enum { IS_SHORT = 0, SIGN = 1, SHORT = 2, BITS = SHORT + 8 - 1, LONG_MV_WIDTH = 10 };
+
+// Costs::mv_component_cost (costs.cc:64-100) without the sign
+uint32_t mv_magnitude_cost(int num, const uint8_t* probs) {
+  const int x = num >> 1;
+  uint32_t cost;
+  if (x < 8) {
+    cost = cost_zero(probs[IS_SHORT]);
+    int idx = 0;
+    for (int n = 2; n >= 0; n--) {  // tree_cost( x, 3, small_mv_tree, probs + SHORT )
+      const int bit = (x >> n) & 1;
+      cost += cost_bit(probs[SHORT + idx / 2], bit);
+      idx = kSmallMvTree[idx + bit];
+    }
+  } else {
+    cost = cost_one(probs[IS_SHORT]);
+    for (int i = 0; i < 3; i++) cost += cost_bit(probs[BITS + i], (x >> i) & 1);
+    for (int i = LONG_MV_WIDTH - 1; i > 3; i--) cost += cost_bit(probs[BITS + i], (x >> i) & 1);
+    if (x & 0xfff0) cost += cost_bit(probs[BITS + 3], (x >> 3) & 1);
+  }
+  return cost;
+}
+
+}  // namespace
+
+void build_enc_tables(EncTables& t) {
+  memset(&t, 0, sizeof(t));
+  for (int a = 0; a < 10; a++)
+    for (int l = 0; l < 10; l++) tree_costs(t.bmode_cost[a][l], k_kf_bmode_probs + (a * 10 + l) * 9, kBModeTree, 0, 0);
+  tree_costs(t.ymode_cost[0], k_kf_ymode_probs, kKfYModeTree, 0, 0);
+  tree_costs(t.ymode_cost[1], k_ymode_default_probs, kYModeTree, 0, 0);
+  for (int k = 0; k < 4; k++)
+    for (int c = 0; c < 6; c++) {
+      t.mvref_zero[k][c] = cost_zero(k_mv_count_probs[c * 4 + k]);
+      t.mvref_one[k][c] = cost_one(k_mv_count_probs[c * 4 + k]);
+    }
+  // the encoder never updates the motion-vector probabilities (optimize_mv_probs is not called from
+  // encode_raster, encode_inter.cc:578-653): the default table prices every frame
+  for (int comp = 0; comp < 2; comp++) {
+    const uint8_t* probs = k_mv_default_probs + comp * 19;
+    for (int i = 0; i < 1024; i++) t.mv_mag_cost[comp][i] = (uint16_t)mv_magnitude_cost(i, probs);
+    t.mv_sign_cost[comp][0] = cost_zero(probs[SIGN]);
+    t.mv_sign_cost[comp][1] = cost_one(probs[SIGN]);
+  }
+  t.mv_sad_cost[0] = 300;
+  for (size_t i = 1; i <= 255; i++) {
+    const size_t cost = 256 * (2 * log2f(8 * i) + 0.6);  // the reference's expression, float then double (costs.cc:136)
+    t.mv_sad_cost[i] = (uint16_t)cost;
+  }
+}
+
+}  // namespace vp8

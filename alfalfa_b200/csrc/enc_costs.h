@@ -1,0 +1,34 @@
+// enc_costs.h -- rate tables of the encoder's mode decision (encoder/costs.cc), built once on the host
+// and kept in HBM for k_enc_rd.  All entries are the reference's integers (costs in 1/256 bit).
+#pragma once
+#include <stdint.h>
+
+namespace vp8 {
+
+struct EncTables {
+  uint16_t bmode_cost[10][10][10];  // [above mode][left mode][mode]      Costs::bmode_costs (costs.cc:196-203)
+  uint16_t ymode_cost[2][5];        // [0 key / 1 inter frame][DC V H TM B] Costs::mbmode_costs (costs.cc:205-207)
+  uint16_t mvref_zero[4][6];        // cost of a 0 at node k of mv_ref_tree given census count c: mv_counts_to_probs[c][k]
+  uint16_t mvref_one[4][6];         //         of a 1                       (Costs::fill_mv_ref_costs, costs.cc:218-221)
+  uint16_t mv_mag_cost[2][1024];    // [0 row (y) / 1 column (x)][|component|] without the sign (costs.cc:64-124)
+  uint16_t mv_sign_cost[2][2];      // [component][negative]
+  uint16_t mv_sad_cost[256];        // Costs::fill_mv_sad_costs (costs.cc:127-142)
+  uint16_t pad[2];
+};
+
+void build_enc_tables(EncTables& t);
+
+// Encoder::update_rd_multipliers (encoder.cc:179-194)
+inline void rd_multipliers(int y_ac, uint32_t* rate_mult, uint32_t* dist_mult) {
+  const double q_ac = y_ac < 160 ? y_ac : 160.0;
+  uint32_t rm = (uint32_t)(q_ac * q_ac * 2.80);
+  if (rm > 1000) {
+    *dist_mult = 1;
+    rm /= 100;
+  } else {
+    *dist_mult = 100;
+  }
+  *rate_mult = rm;
+}
+
+}  // namespace vp8

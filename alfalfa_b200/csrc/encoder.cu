@@ -14,16 +14,16 @@
 #include <vector>
 
 #include "../../include/vp8gpu.h"
+#include "enc_costs.h"
 #include "engine.hpp"
+#include "parser.h"
 #include "serializer.h"
+#include "vp8_enc_tables.h"
 #include "vp8_tables.h"
 
 using vp8::Engine;
 
 // shared with capi.cc
-struct vp8gpu_ctx_view {
-  Engine* engine;
-};
 extern "C" Engine* vp8gpu_ctx_engine(vp8gpu_ctx* ctx);
 extern "C" int vp8gpu_ctx_next_lane(vp8gpu_ctx* ctx);
 
@@ -32,14 +32,16 @@ struct vp8gpu_encoder {
   Engine* e = nullptr;
   int lane = 0;
   bool has_state = false;
-  int last = -1;      // LAST reference = previous reconstruction
-  int src = -1;       // device raster holding the (edge-extended) source frame
-  int last_qi = -1;   // last_y_ac_qi_
-  int last_lf = -1;   // loop_filter_level_ (encoder.hh:144): -1 = not initialised
-  double last_ssim = -1.0;  // encode_stats_.ssim of the last frame
-  // device scratch: EncJob | DevJob | sync ints | mbs | mv | sad | tokens
+  int refs[3] = {-1, -1, -1};  // References: last, golden, alternative (the encoder only ever predicts from LAST
+                               // and only refreshes LAST, encode_inter.cc:245,587-589; the others stay the key frame)
+  int src = -1;                // device raster holding the (edge-extended) source frame
+  int last_qi = -1;            // last_y_ac_qi_ (REALTIME_QUALITY, encoder.cc:164-167)
+  int last_lf = -1;            // loop_filter_level_ (encoder.hh:144): -1 = not initialised
+  double last_ssim = -1.0;     // encode_stats_.ssim of the last frame
+  vp8::State* dec_state = nullptr;  // DecoderState a decoder has after the frames emitted so far (export_decoder)
+  // device scratch: EncJob | DevJob | sync ints | mbs | tokens | rate tables
   uint8_t* dev = nullptr;
-  size_t off_encjob = 0, off_devjob = 0, off_sync = 0, off_mbs = 0, off_mv = 0, off_sad = 0, off_tokens = 0, dev_bytes = 0;
+  size_t off_encjob = 0, off_sync = 0, off_mbs = 0, off_tokens = 0, off_tab = 0, dev_bytes = 0;
   uint32_t tok_cap = 0;
   // pinned host buffers
   uint8_t* h_hdr = nullptr;      // EncJob + DevJob
@@ -48,13 +50,14 @@ struct vp8gpu_encoder {
   uint8_t* h_src = nullptr;      // padded planes
   uint32_t* h_count = nullptr;
   uint64_t stat_frames = 0;
-  // candidates of a quantiser search run as concurrent device passes: two more sets of buffers on their
-  // own lanes (created on first use); they read this encoder's source, LAST and motion vectors
-  vp8gpu_encoder* helper[2] = {nullptr, nullptr};
-  vp8gpu_encoder* owner = nullptr;   // set in a helper
-  cudaEvent_t motion_done = nullptr; // the motion search of the current source frame (owner's lane)
-  int pending_out = -1;              // output raster of a pass that has been launched but not collected
-  bool pending_key = false;
+  int pending_out = -1;          // output raster of a pass that has been launched but not collected
+  vp8::ParsedFrame* scratch = nullptr;  // for re-parsing the emitted frame into dec_state
+  // Bitstream writer.  0 (default): the reference Encoder's own header rules and one DCT partition
+  // (serializer.h RefWriterState) -- byte-identical output; 1: compact -- only token-probability updates that
+  // pay, no zero loop-filter deltas, eight DCT partitions written on eight host threads.
+  int writer = 0;
+  // header state of the reference's four frame objects: key_frame_, inter_frame_, subsampled_*_ (encoder.hh:128-142)
+  vp8::EncodeFeatures::RefWriterState ref_key, ref_inter, ref_sub_key, ref_sub_inter;
 };
 
 namespace {
@@ -78,18 +81,29 @@ vp8gpu_quant make_quant(int qi) {  // Quantizer::Quantizer, quantization.cc:83-9
     if (e__ != cudaSuccess) return enc->e->cuda_fail(e__, #call);       \
   } while (0)
 
+// macroblock grid of a pass: the whole frame, or the frame Encoder::estimate_size codes -- a
+// (width / 4) x (height / 4) frame whose macroblock (c, r) is source macroblock (4c, 4r) (size_estimation.cc:36-99)
+void pass_dims(const vp8gpu_encoder* enc, int sub, int* w, int* h, int* cols, int* rows) {
+  *w = sub == 1 ? enc->e->width() : (uint16_t)(enc->e->width() / sub);
+  *h = sub == 1 ? enc->e->height() : (uint16_t)(enc->e->height() / sub);
+  *cols = (*w + 15) / 16;
+  *rows = (*h + 15) / 16;
+}
+
 // launch half of a pass: everything up to the asynchronous download of the token count and the records
-int encode_launch(vp8gpu_encoder* enc, bool key, int qi, bool search_motion) {
+int encode_launch(vp8gpu_encoder* enc, bool key, int qi, int sub) {
   Engine* e = enc->e;
   const vp8::Geom& g = e->geom();
-  const size_t n_mbs = (size_t)g.mb_cols * g.mb_rows;
-  vp8gpu_encoder* own = enc->owner ? enc->owner : enc;  // whose source / LAST / vectors are used
+  int pw, ph, cols, rows;
+  pass_dims(enc, sub, &pw, &ph, &cols, &rows);
+  if (cols < 1 || rows < 1) return e->fail(VP8GPU_ERR_UNSUPPORTED, "frame too small for the sampled size estimate");
+  const size_t n_mbs = (size_t)cols * rows;
   if (int rc = e->ensure_lane(enc->lane)) return rc;
   cudaStream_t s = e->stream(enc->lane);
   int out = -1;
   int rc = e->frame_alloc(&out);
   if (rc != VP8GPU_OK) return rc;
-  int ids[3] = {own->src, out, own->last};
+  int ids[3] = {enc->src, out, enc->refs[0]};
   rc = e->acquire_frames(enc->lane, ids, key ? 2 : 3, 2u);  // only `out` is written
   if (rc != VP8GPU_OK) {
     e->frame_release(out);
@@ -98,19 +112,24 @@ int encode_launch(vp8gpu_encoder* enc, bool key, int qi, bool search_motion) {
   vp8::EncJob* ej = reinterpret_cast<vp8::EncJob*>(enc->h_hdr);
   memset(enc->h_hdr, 0, 512);
   int* d_sync = reinterpret_cast<int*>(enc->dev + enc->off_sync);
-  ej->src = e->frame_dev(own->src);
-  ej->ref = key ? nullptr : e->frame_dev(own->last);
+  ej->src = e->frame_dev(enc->src);
+  ej->ref = key ? nullptr : e->frame_dev(enc->refs[0]);
   ej->out = e->frame_dev(out);
   ej->mbs = reinterpret_cast<vp8gpu_mb*>(enc->dev + enc->off_mbs);
   ej->tokens = reinterpret_cast<vp8gpu_token*>(enc->dev + enc->off_tokens);
   ej->tok_counter = reinterpret_cast<uint32_t*>(d_sync + 96);
   ej->tok_cap = enc->tok_cap;
-  ej->mv = reinterpret_cast<int*>(own->dev + own->off_mv);
-  ej->sad = reinterpret_cast<uint32_t*>(own->dev + own->off_sad);
   ej->progress = d_sync + 128;
+  ej->tab = reinterpret_cast<const vp8::EncTables*>(enc->dev + enc->off_tab);
   ej->q = make_quant(qi);
+  vp8::rd_multipliers(ej->q.y_ac, &ej->rate_mult, &ej->dist_mult);
+  ej->cols = (uint16_t)cols;
+  ej->rows = (uint16_t)rows;
+  ej->sub = (uint8_t)sub;
   ej->key_frame = key;
   ej->lf_level = 1;  // records carry "filtered"; the level itself is chosen afterwards (choose_loop_filter)
+  ej->sad_per_bit = k_sad_per_bit16[clamp_q(qi)];
+  ej->realtime = 1;  // REALTIME_QUALITY, what Salsify runs (salsify-sender.cc:287-288)
   auto fail = [&](int code) {
     e->frame_release(out);
     return code;
@@ -123,27 +142,13 @@ int encode_launch(vp8gpu_encoder* enc, bool key, int qi, bool search_motion) {
   CUF(cudaMemcpyAsync(enc->dev + enc->off_encjob, enc->h_hdr, 512, cudaMemcpyHostToDevice, s));
   CUF(cudaMemsetAsync(d_sync, 0, sizeof(int) * (128 + 2 * (size_t)g.mb_rows), s));
   const vp8::EncJob* d_ej = reinterpret_cast<const vp8::EncJob*>(enc->dev + enc->off_encjob);
-  int launches = 0;
-  if (!key) {
-    if (search_motion) {  // vectors do not depend on the quantiser: searched once per source frame, by the owner
-      if (enc->owner) return fail(e->fail(VP8GPU_ERR_LOGIC, "motion search belongs to the owning encoder"));
-      if (int ce = vp8::launch_enc_motion(d_ej, g, s)) return fail(e->cuda_fail((cudaError_t)ce, "k_enc_motion"));
-      launches++;
-      if (!enc->motion_done) CUF(cudaEventCreateWithFlags(&enc->motion_done, cudaEventDisableTiming));
-      CUF(cudaEventRecord(enc->motion_done, s));
-    } else if (enc->owner && own->motion_done) {
-      CUF(cudaStreamWaitEvent(s, own->motion_done, 0));  // the vectors come from the owner's lane
-    }
-  }
-  if (int ce = vp8::launch_enc_mb(d_ej, g, d_sync + 0, s)) return fail(e->cuda_fail((cudaError_t)ce, "k_enc_mb"));
-  launches++;
-  e->count_launches(launches);
+  if (int ce = vp8::launch_enc_rd(d_ej, rows, g, d_sync + 0, s)) return fail(e->cuda_fail((cudaError_t)ce, "k_enc_rd"));
+  e->count_launches(1);
   e->mark_frames(enc->lane, ids, key ? 2 : 3, 2u);
   // results back: token count first, then the records
   CUF(cudaMemcpyAsync(enc->h_count, ej->tok_counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   CUF(cudaMemcpyAsync(enc->h_mbs, ej->mbs, n_mbs * sizeof(vp8gpu_mb), cudaMemcpyDeviceToHost, s));
   enc->pending_out = out;
-  enc->pending_key = key;
   return VP8GPU_OK;
 #undef CUF
 }
@@ -173,30 +178,51 @@ int encode_collect(vp8gpu_encoder* enc, int* out_frame) {
   return VP8GPU_OK;
 }
 
-// One encoding pass at quantiser index qi: motion search (once per source frame), the mode-decision /
-// transform / reconstruction wavefront, records and tokens back on the host.
-int encode_core(vp8gpu_encoder* enc, bool key, int qi, bool search_motion, int* out_frame) {
-  const int rc = encode_launch(enc, key, qi, search_motion);
+// One encoding pass at quantiser index qi over the whole frame (sub = 1) or the 1/16 sample (sub = 4):
+// decisions, transforms, reconstruction on the device; records and tokens back on the host.
+int encode_core(vp8gpu_encoder* enc, bool key, int qi, int sub, int* out_frame) {
+  const int rc = encode_launch(enc, key, qi, sub);
   return rc == VP8GPU_OK ? encode_collect(enc, out_frame) : rc;
 }
 
-// the compressed frame of the last encode_core pass
-int encode_bytes(vp8gpu_encoder* enc, bool key, int qi, int lf_level, std::vector<uint8_t>& bytes) {
+// The compressed frame of the last encode_core pass.  final: the frame that is emitted -- token
+// probabilities optimised and saved (refresh_entropy_probs, encode_intra.cc:402, encode_inter.cc:587) in
+// `probs`; otherwise a size estimate priced with the current tables, which are left alone
+// (size_estimation.cc:92,167: no optimize_probability_tables).
+int encode_bytes(vp8gpu_encoder* enc, bool key, int qi, int lf_level, int sub, bool final, uint8_t* probs, std::vector<uint8_t>& bytes) {
   Engine* e = enc->e;
+  int pw, ph, cols, rows;
+  pass_dims(enc, sub, &pw, &ph, &cols, &rows);
   vp8::EncodeHeader h;
   h.key_frame = key;
   h.show_frame = true;
-  h.width = e->width();
-  h.height = e->height();
+  h.width = pw;
+  h.height = ph;
   h.y_ac_qi = qi;
   h.loop_filter_level = lf_level;
   h.sharpness = 0;
-  h.optimize_token_probs = true;
-  // eight DCT partitions (row r -> partition r % 8, frame.cc:131-136): the writer records and codes them
-  // on eight host threads, which is most of the host time of an encoding pass
+  h.optimize_token_probs = final;
   vp8::EncodeFeatures ft;
-  ft.log2_partitions = (h.height + 15) / 16 >= 16 ? 3 : 0;
-  if (const char* v = getenv("VP8GPU_ENC_LOG2_PARTS")) ft.log2_partitions = atoi(v) & 3;  // tuning knob
+  if (enc->writer == 0) {
+    ft.ref_writer = final ? (key ? &enc->ref_key : &enc->ref_inter) : (key ? &enc->ref_sub_key : &enc->ref_sub_inter);
+    ft.ref_estimate = !final;
+    ft.log2_partitions = 0;
+  } else {
+    // Eight DCT partitions for the emitted frame (row r -> partition r % 8, frame.cc:131-136): the writer records
+    // and codes them on eight host threads, which is most of the host time of a pass (the reference writes one
+    // partition; seven more cost 21 bytes of partition sizes).  Estimates are small: one partition.
+    ft.log2_partitions = (final && rows >= 16) ? 3 : 0;
+    if (const char* v = getenv("VP8GPU_ENC_LOG2_PARTS")) ft.log2_partitions = atoi(v) & 3;  // tuning knob
+  }
+  ft.refresh_entropy_probs = true;
+  uint8_t scratch_probs[1056];
+  if (final) {
+    ft.saved_coef_probs = probs;
+  } else {
+    // estimate_size<KeyFrame> starts from a fresh DecoderState (default tables), <InterFrame> from the current one
+    memcpy(scratch_probs, key ? k_coef_default_probs : probs, 1056);
+    ft.saved_coef_probs = scratch_probs;
+  }
   bytes = vp8::serialize_frame(h, enc->h_mbs, enc->h_tokens, nullptr, &ft);
   if (bytes.empty()) return e->fail(VP8GPU_ERR_LOGIC, "serializer rejected the device records");
   return VP8GPU_OK;
@@ -302,10 +328,8 @@ int upload_source(vp8gpu_encoder* enc, const uint8_t* y, size_t ys, const uint8_
 
 }  // namespace
 
-extern "C" {
-
-int vp8gpu_encoder_create(vp8gpu_ctx* ctx, vp8gpu_encoder** out) {
-  if (!ctx || !out) return VP8GPU_ERR_LOGIC;
+// common part of create / clone / create_from: buffers on device and host, the rate tables
+static int encoder_alloc(vp8gpu_ctx* ctx, vp8gpu_encoder** out) {
   vp8gpu_encoder* enc = new vp8gpu_encoder();
   enc->ctx = ctx;
   enc->e = vp8gpu_ctx_engine(ctx);
@@ -321,10 +345,8 @@ int vp8gpu_encoder_create(vp8gpu_ctx* ctx, vp8gpu_encoder** out) {
   off = align_up(off + sizeof(int) * (128 + 2 * (size_t)g.mb_rows), 256);
   enc->off_mbs = off;
   off = align_up(off + n_mbs * sizeof(vp8gpu_mb), 256);
-  enc->off_mv = off;
-  off = align_up(off + n_mbs * 2 * sizeof(int), 256);
-  enc->off_sad = off;
-  off = align_up(off + n_mbs * sizeof(uint32_t), 256);
+  enc->off_tab = off;
+  off = align_up(off + sizeof(vp8::EncTables), 256);
   enc->off_tokens = off;
   off = align_up(off + (size_t)enc->tok_cap * sizeof(vp8gpu_token), 256);
   enc->dev_bytes = off;
@@ -337,20 +359,88 @@ int vp8gpu_encoder_create(vp8gpu_ctx* ctx, vp8gpu_encoder** out) {
     vp8gpu_encoder_destroy(enc);
     return e->fail(VP8GPU_ERR_NOMEM, "encoder allocation failed");
   }
+  static const vp8::EncTables* tables = [] {
+    vp8::EncTables* t = new vp8::EncTables();
+    vp8::build_enc_tables(*t);
+    return t;
+  }();
+  if (cudaMemcpy(enc->dev + enc->off_tab, tables, sizeof(vp8::EncTables), cudaMemcpyHostToDevice) != cudaSuccess) {
+    vp8gpu_encoder_destroy(enc);
+    return e->fail(VP8GPU_ERR_CUDA, "encoder rate tables upload failed");
+  }
+  enc->dec_state = new vp8::State(e->width(), e->height());
+  enc->scratch = new vp8::ParsedFrame();
+  *out = enc;
+  return VP8GPU_OK;
+}
+
+extern "C" {
+
+int vp8gpu_encoder_create(vp8gpu_ctx* ctx, vp8gpu_encoder** out) {
+  if (!ctx || !out) return VP8GPU_ERR_LOGIC;
+  return encoder_alloc(ctx, out);
+}
+
+// Encoder( const Encoder & ) (encoder.cc:92-102): an independent copy that shares the reference rasters
+// (immutable, reference counted); the two can then encode concurrently (salsify-sender.cc:492-518).
+int vp8gpu_encoder_clone(const vp8gpu_encoder* src, vp8gpu_encoder** out) {
+  if (!src || !out) return VP8GPU_ERR_LOGIC;
+  vp8gpu_encoder* enc = nullptr;
+  int rc = encoder_alloc(src->ctx, &enc);
+  if (rc != VP8GPU_OK) return rc;
+  enc->has_state = src->has_state;
+  enc->writer = src->writer;  // (the copy's frame objects, i.e. the writer's header state, start fresh: encoder.cc:92-102)
+  enc->last_qi = src->last_qi;
+  enc->last_lf = src->last_lf;
+  enc->last_ssim = src->last_ssim;
+  *enc->dec_state = *src->dec_state;
+  for (int k = 0; k < 3; k++) {
+    enc->refs[k] = src->refs[k];
+    if (enc->refs[k] >= 0) enc->e->frame_retain(enc->refs[k]);
+  }
+  *out = enc;
+  return VP8GPU_OK;
+}
+
+// Encoder( const Decoder &, two_pass, quality ) (encoder.hh:350-351): continue a stream from a decoder's
+// state and references (the next frame is an inter frame predicted from the decoder's LAST)
+int vp8gpu_encoder_create_from_decoder(vp8gpu_ctx* ctx, vp8gpu_decoder* dec, vp8gpu_encoder** out) {
+  if (!ctx || !dec || !out) return VP8GPU_ERR_LOGIC;
+  vp8gpu_frame_id refs[3];
+  const vp8gpu_state* st = vp8gpu_decoder_state(dec);
+  int rc = vp8gpu_decoder_references(dec, refs);
+  if (rc != VP8GPU_OK || !st) return VP8GPU_ERR_LOGIC;
+  vp8gpu_encoder* enc = nullptr;
+  rc = encoder_alloc(ctx, &enc);
+  if (rc != VP8GPU_OK) return rc;
+  uint8_t blob[16384];
+  const size_t n = vp8gpu_state_serialize(st, blob, sizeof(blob));
+  std::vector<uint8_t> big;
+  const uint8_t* bp = blob;
+  if (n > sizeof(blob)) {  // a segmentation map makes the blob larger
+    big.resize(n);
+    vp8gpu_state_serialize(st, big.data(), big.size());
+    bp = big.data();
+  }
+  if (!vp8::State::deserialize(bp, n, *enc->dec_state)) {
+    vp8gpu_encoder_destroy(enc);
+    return vp8gpu_ctx_engine(ctx)->fail(VP8GPU_ERR_LOGIC, "encoder_create_from_decoder: bad decoder state");
+  }
+  for (int k = 0; k < 3; k++) {
+    enc->refs[k] = refs[k];
+    if (refs[k] >= 0) enc->e->frame_retain(refs[k]);
+  }
+  enc->has_state = true;
   *out = enc;
   return VP8GPU_OK;
 }
 
 void vp8gpu_encoder_destroy(vp8gpu_encoder* enc) {
   if (!enc) return;
-  for (vp8gpu_encoder*& hlp : enc->helper) {
-    vp8gpu_encoder_destroy(hlp);
-    hlp = nullptr;
-  }
-  if (enc->motion_done) cudaEventDestroy(enc->motion_done);
   cudaSetDevice(enc->e->device());
-  cudaStreamSynchronize(enc->e->stream(enc->lane));
-  if (enc->last >= 0) enc->e->frame_release(enc->last);
+  if (enc->e->stream(enc->lane)) cudaStreamSynchronize(enc->e->stream(enc->lane));
+  for (int k = 0; k < 3; k++)
+    if (enc->refs[k] >= 0) enc->e->frame_release(enc->refs[k]);
   if (enc->src >= 0) enc->e->frame_release(enc->src);
   if (enc->dev) cudaFree(enc->dev);
   if (enc->h_hdr) cudaFreeHost(enc->h_hdr);
@@ -358,41 +448,71 @@ void vp8gpu_encoder_destroy(vp8gpu_encoder* enc) {
   if (enc->h_tokens) cudaFreeHost(enc->h_tokens);
   if (enc->h_src) cudaFreeHost(enc->h_src);
   if (enc->h_count) cudaFreeHost(enc->h_count);
+  delete enc->dec_state;
+  delete enc->scratch;
   delete enc;
 }
 
-static int finish_frame(vp8gpu_encoder* enc, const std::vector<uint8_t>& bytes, int out_frame, int qi, int lf, double ssim,
+static int finish_frame(vp8gpu_encoder* enc, bool key, const std::vector<uint8_t>& bytes, int out_frame, int qi, int lf, double ssim,
                         uint8_t* out, size_t cap, size_t* size) {
+  Engine* e = enc->e;
   *size = bytes.size();
   if (!out || cap < bytes.size()) {
-    enc->e->frame_release(out_frame);
-    return enc->e->fail(VP8GPU_ERR_NOMEM, "output buffer too small");
+    e->frame_release(out_frame);
+    return e->fail(VP8GPU_ERR_NOMEM, "output buffer too small");
   }
   memcpy(out, bytes.data(), bytes.size());
-  if (enc->last >= 0) enc->e->frame_release(enc->last);
-  enc->last = out_frame;  // Frame::copy_to: key frames and refresh_last inter frames replace LAST
+  // Encoder::write_frame -> update_decoder_state (encoder.cc:146-151): the state a decoder is in after this
+  // frame, obtained the way a decoder obtains it -- by parsing the frame (first partition only)
+  const int prc = vp8::parse_frame(*enc->dec_state, bytes.data(), bytes.size(), *enc->scratch, true);
+  if (prc != VP8GPU_OK) {
+    e->frame_release(out_frame);
+    return e->fail(VP8GPU_ERR_LOGIC, "the emitted frame does not parse");
+  }
+  // Frame::copy_to (frame.cc:272-307): a key frame replaces all three references, an inter frame of this
+  // encoder (refresh_last only) replaces LAST
+  for (int k = 0; k < (key ? 3 : 1); k++) {
+    if (enc->refs[k] >= 0) e->frame_release(enc->refs[k]);
+    enc->refs[k] = out_frame;
+    if (k) e->frame_retain(out_frame);
+  }
   enc->has_state = true;
-  enc->last_qi = qi;
-  enc->last_lf = lf;      // encoder.cc:165
+  enc->last_qi = qi;      // encoder.cc:164-167 (REALTIME_QUALITY)
+  enc->last_lf = lf;
   enc->last_ssim = ssim;
   enc->stat_frames++;
   return VP8GPU_OK;
 }
 
 // encode at qi, choose the loop filter, serialize: Encoder::encode_raster + write_frame (encoder.cc:140-178)
-static int encode_final(vp8gpu_encoder* enc, bool key, int qi, bool search_motion, uint8_t* out, size_t cap, size_t* size) {
+static int encode_final(vp8gpu_encoder* enc, bool key, int qi, uint8_t* out, size_t cap, size_t* size) {
   int frame = -1, lf = 0;
   double ssim = -1.0;
-  int rc = encode_core(enc, key, qi, search_motion, &frame);
+  int rc = encode_core(enc, key, qi, 1, &frame);
   if (rc != VP8GPU_OK) return rc;
   rc = choose_loop_filter(enc, frame, key, &lf, &ssim);
   std::vector<uint8_t> bytes;
-  if (rc == VP8GPU_OK) rc = encode_bytes(enc, key, qi, lf, bytes);
+  uint8_t probs[1056];
+  memcpy(probs, enc->dec_state->coef_probs, 1056);
+  if (rc == VP8GPU_OK) rc = encode_bytes(enc, key, qi, lf, 1, true, probs, bytes);
   if (rc != VP8GPU_OK) {
     enc->e->frame_release(frame);
     return rc;
   }
-  return finish_frame(enc, bytes, frame, qi, lf, ssim, out, cap, size);
+  return finish_frame(enc, key, bytes, frame, qi, lf, ssim, out, cap, size);
+}
+
+// Encoder::estimate_frame_size (size_estimation.cc:36-181): code the 1/16 sample at y_ac_qi, serialize it
+// with the current probability tables, multiply by 16
+static int estimate_size(vp8gpu_encoder* enc, bool key, int qi, size_t* size) {
+  int frame = -1;
+  int rc = encode_core(enc, key, qi, 4, &frame);
+  if (rc != VP8GPU_OK) return rc;
+  enc->e->frame_release(frame);
+  std::vector<uint8_t> bytes;
+  rc = encode_bytes(enc, key, qi, 0, 4, false, enc->dec_state->coef_probs, bytes);
+  if (rc == VP8GPU_OK) *size = bytes.size() * 16;
+  return rc;
 }
 
 int vp8gpu_encoder_encode_with_quantizer(vp8gpu_encoder* enc, const uint8_t* y, size_t y_stride, const uint8_t* u,
@@ -402,7 +522,7 @@ int vp8gpu_encoder_encode_with_quantizer(vp8gpu_encoder* enc, const uint8_t* y, 
   cudaSetDevice(enc->e->device());
   int rc = upload_source(enc, y, y_stride, u, v, uv_stride);
   if (rc != VP8GPU_OK) return rc;
-  return encode_final(enc, !enc->has_state, y_ac_qi, true, out, cap, size);
+  return encode_final(enc, !enc->has_state, y_ac_qi, out, cap, size);
 }
 
 int vp8gpu_encoder_encode_with_target_size(vp8gpu_encoder* enc, const uint8_t* y, size_t y_stride, const uint8_t* u,
@@ -412,79 +532,30 @@ int vp8gpu_encoder_encode_with_target_size(vp8gpu_encoder* enc, const uint8_t* y
   cudaSetDevice(enc->e->device());
   int rc = upload_source(enc, y, y_stride, u, v, uv_stride);
   if (rc != VP8GPU_OK) return rc;
-  // bisection over y_ac_qi exactly as Encoder::encode_with_target_size (encoder.cc:597-626); the size
-  // of a candidate is its real size (a device pass is cheap), not the 1/16-sampled estimate of
-  // estimate_frame_size; the loop filter does not change the size, so candidates skip it
+  // Encoder::encode_with_target_size (encoder.cc:592-629), statement for statement: bisection over y_ac_qi in
+  // [4, 127] or within 16 of the last frame's index; a candidate's size is the sampled estimate
+  const bool key = !enc->has_state;
   int lo = 4, hi = 127;
   if (enc->last_qi >= 0) {
     if (enc->last_qi - 16 >= lo) lo = enc->last_qi - 16;
     if (enc->last_qi + 16 < hi) hi = enc->last_qi + 16;
   }
-  // Candidates run three at a time as concurrent device passes (this encoder's buffers and two helpers' on
-  // their own lanes; the wavefront kernel is latency bound, so three cost about as much as one): the range
-  // shrinks to a quarter per round instead of a half.  Sizes fall as the index rises, which is also what
-  // the reference's bisection relies on, so the answer is the same: the smallest index that fits, or the
-  // top of the range if none does.
-  int best = -1;
-  const int top = hi;
-  std::vector<uint8_t> bytes;
-  const bool key = !enc->has_state;
-  bool first_round = true;
-  for (int k = 0; k < 2; k++)
-    if (!enc->helper[k]) {
-      rc = vp8gpu_encoder_create(enc->ctx, &enc->helper[k]);
-      if (rc != VP8GPU_OK) return rc;
-      enc->helper[k]->owner = enc;
-    }
-  vp8gpu_encoder* const slot[3] = {enc, enc->helper[0], enc->helper[1]};
+  int best = 255;
   while (lo <= hi) {
-    const int n = hi - lo + 1;
-    int q[3], nq;
-    if (n <= 3) {
-      nq = n;
-      for (int k = 0; k < n; k++) q[k] = lo + k;
-    } else {
-      nq = 3;
-      q[0] = lo + n / 4;
-      q[1] = lo + n / 2;
-      q[2] = lo + (3 * n) / 4;
-    }
-    int launched = 0;
-    for (int k = 0; k < nq && rc == VP8GPU_OK; k++) {
-      rc = encode_launch(slot[k], key, q[k], first_round && k == 0);
-      if (rc == VP8GPU_OK) launched++;
-    }
-    first_round = false;
-    size_t sz[3] = {0, 0, 0};
-    for (int k = 0; k < launched; k++) {  // every launched pass is collected, also after an error
-      int frame = -1;
-      const int r2 = encode_collect(slot[k], &frame);
-      if (r2 != VP8GPU_OK) {
-        if (rc == VP8GPU_OK) rc = r2;
-        continue;
-      }
-      enc->e->frame_release(frame);
-      if (rc != VP8GPU_OK) continue;
-      const int r3 = encode_bytes(slot[k], key, q[k], 0, bytes);
-      if (r3 != VP8GPU_OK) rc = r3;
-      sz[k] = bytes.size();
-    }
+    const int qi = (lo + hi) / 2;
+    size_t est = 0;
+    rc = estimate_size(enc, key, qi, &est);
     if (rc != VP8GPU_OK) return rc;
-    int fit = -1;
-    for (int k = 0; k < nq && fit < 0; k++)
-      if (sz[k] <= target_size) fit = k;
-    if (fit >= 0) {
-      best = q[fit];
-      hi = q[fit] - 1;
-      if (fit > 0) lo = q[fit - 1] + 1;
+    if (est <= target_size || (lo == hi && best == 255)) {
+      best = qi;
+      hi = qi - 1;
     } else {
-      lo = q[nq - 1] + 1;
+      lo = qi + 1;
     }
   }
-  if (best < 0) best = top;  // encoder.cc:618: nothing fits -> the last index of the range is taken
-  if (best < 0) return enc->e->fail(VP8GPU_ERR_LOGIC, "target size search failed");
+  if (best == 255) return enc->e->fail(VP8GPU_ERR_LOGIC, "target size search failed");
   if (chosen_qi) *chosen_qi = best;
-  return encode_final(enc, key, best, false, out, cap, size);  // encoder.cc:628: encode again at the chosen index
+  return encode_final(enc, key, best, out, cap, size);
 }
 
 // Encoder::encode_with_minimum_ssim -> encode_with_quantizer_search (encoder.cc:510-557, 577-590): the
@@ -498,13 +569,12 @@ int vp8gpu_encoder_encode_with_minimum_ssim(vp8gpu_encoder* enc, const uint8_t* 
   if (rc != VP8GPU_OK) return rc;
   const bool key = !enc->has_state;
   int lo = 0, hi = 127, best = 0;
-  bool found = false, first_probe = true;
+  bool found = false;
   while (lo <= hi) {
     const int qi = (lo + hi) / 2;
     int frame = -1, lf = 0;
     double ssim = -1.0;
-    rc = encode_core(enc, key, qi, first_probe, &frame);
-    first_probe = false;
+    rc = encode_core(enc, key, qi, 1, &frame);
     if (rc != VP8GPU_OK) return rc;
     rc = choose_loop_filter(enc, frame, key, &lf, &ssim);
     enc->e->frame_release(frame);
@@ -518,25 +588,23 @@ int vp8gpu_encoder_encode_with_minimum_ssim(vp8gpu_encoder* enc, const uint8_t* 
     else lo = qi + 1;
   }
   if (chosen_qi) *chosen_qi = best;
-  return encode_final(enc, key, best, false, out, cap, size);
+  return encode_final(enc, key, best, out, cap, size);
 }
 
-// Encoder::estimate_frame_size (size_estimation.cc:36-99): exact instead of sampled
 int vp8gpu_encoder_estimate_frame_size(vp8gpu_encoder* enc, const uint8_t* y, size_t y_stride, const uint8_t* u,
                                        const uint8_t* v, size_t uv_stride, int y_ac_qi, size_t* size) {
   if (!enc || !y || !u || !v || !size || y_ac_qi < 0 || y_ac_qi > 127) return VP8GPU_ERR_LOGIC;
   cudaSetDevice(enc->e->device());
   int rc = upload_source(enc, y, y_stride, u, v, uv_stride);
   if (rc != VP8GPU_OK) return rc;
-  const bool key = !enc->has_state;
-  int frame = -1;
-  rc = encode_core(enc, key, y_ac_qi, true, &frame);
-  if (rc != VP8GPU_OK) return rc;
-  enc->e->frame_release(frame);
-  std::vector<uint8_t> bytes;
-  rc = encode_bytes(enc, key, y_ac_qi, 0, bytes);
-  if (rc == VP8GPU_OK) *size = bytes.size();
-  return rc;
+  return estimate_size(enc, !enc->has_state, y_ac_qi, size);
+}
+
+// bitstream writer: 0 = byte-identical to the reference Encoder's output (default), 1 = compact / parallel
+int vp8gpu_encoder_set_writer(vp8gpu_encoder* enc, int mode) {
+  if (!enc || mode < 0 || mode > 1) return VP8GPU_ERR_LOGIC;
+  enc->writer = mode;
+  return VP8GPU_OK;
 }
 
 // EncoderStats (encoder.hh:118-127) of the last frame: luma SSIM after the loop filter, the chosen
@@ -549,11 +617,37 @@ int vp8gpu_encoder_stats(const vp8gpu_encoder* enc, double* ssim, int* loop_filt
   return VP8GPU_OK;
 }
 
-// Encoder::export_decoder (encoder.hh:378): the reconstruction kept as LAST (one new reference for the caller)
+// the reconstruction kept as LAST (one new reference for the caller)
 int vp8gpu_encoder_reconstruction(vp8gpu_encoder* enc, vp8gpu_frame_id* out) {
-  if (!enc || !out || enc->last < 0) return VP8GPU_ERR_LOGIC;
-  const int rc = enc->e->frame_retain(enc->last);
-  if (rc == VP8GPU_OK) *out = enc->last;
+  if (!enc || !out || enc->refs[0] < 0) return VP8GPU_ERR_LOGIC;
+  const int rc = enc->e->frame_retain(enc->refs[0]);
+  if (rc == VP8GPU_OK) *out = enc->refs[0];
+  return rc;
+}
+
+// Encoder::export_decoder (encoder.hh:378): a Decoder in the state a receiver is in after the frames emitted
+// so far -- DecoderState + the three references (shared, not copied)
+int vp8gpu_encoder_export_decoder(vp8gpu_encoder* enc, vp8gpu_decoder** out) {
+  if (!enc || !out || !enc->has_state) return VP8GPU_ERR_LOGIC;
+  const std::vector<uint8_t> blob = enc->dec_state->serialize();
+  vp8gpu_state* st = nullptr;
+  int rc = vp8gpu_state_deserialize(blob.data(), blob.size(), &st);
+  if (rc != VP8GPU_OK) return rc;
+  rc = vp8gpu_decoder_create_from(enc->ctx, st, enc->refs, out);
+  vp8gpu_state_destroy(st);
+  return rc;
+}
+
+// Encoder::minihash (encoder.hh:382) = export_decoder().minihash()
+int vp8gpu_encoder_minihash(vp8gpu_encoder* enc, uint32_t* out) {
+  if (!enc || !out) return VP8GPU_ERR_LOGIC;
+  vp8gpu_decoder* d = nullptr;
+  int rc = vp8gpu_encoder_export_decoder(enc, &d);
+  if (rc != VP8GPU_OK) return rc;
+  uint64_t h = 0;
+  rc = vp8gpu_decoder_hash(d, &h);
+  vp8gpu_decoder_destroy(d);
+  if (rc == VP8GPU_OK) *out = (uint32_t)(h ^ (h >> 32));  // same fold as Decoder::minihash
   return rc;
 }
 

@@ -121,6 +121,10 @@ Engine::~Engine() {
   for (auto& s : lanes_)
     if (s) cudaStreamDestroy(s);
   if (cmp_scratch_) cudaFree(cmp_scratch_);
+  for (float* p : ssim_dev_)
+    if (p) cudaFree(p);
+  for (float* p : ssim_host_)
+    if (p) cudaFreeHost(p);
   // tmaps_ belongs to the tensor-map arena: never reused, never freed
 }
 
@@ -412,26 +416,36 @@ int Engine::frames_equal(int a, int b, int lane, int* equal) {
 int Engine::frames_ssim(int a, int b, int lane, double* out) {
   if (int rc = ensure_lane(lane)) return rc;
   cudaStream_t s = lanes_[lane];
-  double* d;
+  const int n = (g_.W / 4 - 1) * (g_.H / 4 - 1);
+  if (n <= 0) {
+    *out = 0.0;
+    return VP8GPU_OK;
+  }
   {
     std::lock_guard<std::mutex> lk(mu_);
     for (int id : {a, b})
       if (id < 0 || id >= (int)frames_.size() || frames_[id].refcnt <= 0) return fail(VP8GPU_ERR_LOGIC, "ssim: bad frame id");
-    if (!cmp_scratch_) CU(cudaMalloc(&cmp_scratch_, 1024));
-    d = reinterpret_cast<double*>(cmp_scratch_ + 512 + 8 * lane);
+    if (!ssim_dev_[lane]) {
+      CU(cudaSetDevice(device_));
+      CU(cudaMalloc(&ssim_dev_[lane], (size_t)n * sizeof(float)));
+      CU(cudaHostAlloc(&ssim_host_[lane], (size_t)n * sizeof(float), cudaHostAllocDefault));
+    }
     if (int rc = wait_for(frames_[a], lane, s, false)) return rc;
     if (int rc = wait_for(frames_[b], lane, s, false)) return rc;
-    CU(cudaMemsetAsync(d, 0, sizeof(double), s));
-    if (int e = launch_ssim(frames_[a].dev, frames_[b].dev, g_, d, s)) return cuda_fail((cudaError_t)e, "ssim");
+    if (int e = launch_ssim(frames_[a].dev, frames_[b].dev, g_, ssim_dev_[lane], s)) return cuda_fail((cudaError_t)e, "ssim");
     launches_++;
     if (int rc = touch(frames_[a], lane, false)) return rc;
     if (int rc = touch(frames_[b], lane, false)) return rc;
   }
-  double sum = 0;
-  CU(cudaMemcpyAsync(&sum, d, sizeof(sum), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(ssim_host_[lane], ssim_dev_[lane], (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
-  const int n = (g_.W / 4 - 1) * (g_.H / 4 - 1);
-  *out = n > 0 ? sum / n : 0.0;
+  // x264's pixel_ssim_wxh adds the per-window values into one float in raster order (util/ssim.cc via
+  // oracle/ref_shim/ssim_stub.cc); the encoder's loop-filter search compares these sums with `>`, so the
+  // sum is formed the same way, on the host
+  float total = 0.0f;
+  const float* v = ssim_host_[lane];
+  for (int i = 0; i < n; i++) total += v[i];
+  *out = total / n;
   return VP8GPU_OK;
 }
 

@@ -38,22 +38,29 @@ struct DevJob {
   uint32_t pad2;
 };
 
-// One frame's ENCODE job (device pointers).  The encoder runs a motion search against the last
-// reconstructed frame, then one wavefront pass that decides modes, transforms, quantises,
+// One frame's ENCODE job (device pointers): one wavefront pass that takes the reference encoder's
+// decisions macroblock by macroblock (encoder/encode_intra.cc, encode_inter.cc), transforms, quantises,
 // emits tokens + macroblock records and reconstructs exactly what a decoder will reconstruct.
+struct EncTables;
 struct EncJob {
   const uint8_t* src;      // source raster (same layout as every other raster)
   const uint8_t* ref;      // last reconstructed + loop-filtered frame; nullptr for key frames
   uint8_t* out;            // reconstruction (before the loop filter, which runs afterwards in place)
-  vp8gpu_mb* mbs;          // [mb_cols * mb_rows] records written by the device
+  vp8gpu_mb* mbs;          // [cols * rows] records written by the device
   vp8gpu_token* tokens;    // token pool
   uint32_t* tok_counter;   // tokens used so far (atomic)
   uint32_t tok_cap;
-  int* mv;                 // [n_mbs][2] best motion vector per macroblock, 1/8 pel (inter frames)
-  uint32_t* sad;           // [n_mbs] luma SAD of that vector
-  int* progress;           // [mb_rows] wavefront counters (zeroed)
+  int* progress;           // [rows] wavefront counters (zeroed)
+  const EncTables* tab;    // rate tables (enc_costs.h)
   vp8gpu_quant q;
-  uint8_t key_frame, lf_level, pad[2];
+  uint32_t rate_mult, dist_mult;  // Encoder::update_rd_multipliers (encoder.cc:179-194)
+  uint16_t cols, rows;     // macroblocks coded by this pass: the whole frame, or the 1/16 sample of
+  uint8_t sub;             //   Encoder::estimate_size (size_estimation.cc:36-99): macroblock (c, r) of the pass is
+                           //   source macroblock (sub * c, sub * r); sub = 1 or 4
+  uint8_t key_frame, lf_level;
+  uint8_t sad_per_bit;     // sad_per_bit16lut[y_ac_qi] (encode_inter.cc:160-170)
+  uint8_t realtime;        // REALTIME_QUALITY: no B_PRED in inter frames, motion search on every 4th column and row
+  uint8_t pad[3];
 };
 
 // One frame's token-decode job (tokens.cu): DCT partitions -> token stream + tok_off / tok_cnt.
@@ -77,8 +84,7 @@ int launch_intra(const DevJob* jobs, int njobs, const Geom& g, int* ticket, void
 int launch_loopfilter(const DevJob* jobs, int njobs, const Geom& g, int* ticket, void* stream);
 // token jobs sit at the start of equally spaced ring slots: slot (first + i) % nslots for block i
 int launch_tokens(const uint8_t* ring, size_t stride, int first, int count, int nslots, const Geom& g, void* stream);
-int launch_ssim(const uint8_t* a, const uint8_t* b, const Geom& g, double* d_sum, void* stream);
-int launch_enc_motion(const EncJob* job, const Geom& g, void* stream);
-int launch_enc_mb(const EncJob* job, const Geom& g, int* ticket, void* stream);
+int launch_ssim(const uint8_t* a, const uint8_t* b, const Geom& g, float* d_windows, void* stream);
+int launch_enc_rd(const EncJob* job, int rows, const Geom& g, int* ticket, void* stream);
 
 }  // namespace vp8

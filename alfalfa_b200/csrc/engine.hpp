@@ -159,6 +159,8 @@ class Engine {
   Staging staging_[kMaxLanes][kStagingDepth];
   int staging_next_[kMaxLanes] = {};
   uint8_t* cmp_scratch_ = nullptr;
+  float* ssim_dev_[kMaxLanes] = {};   // per lane: one float per 8x8 SSIM window (frames_ssim)
+  float* ssim_host_[kMaxLanes] = {};
   uint8_t* tmaps_ = nullptr;  // [max_frames][3] CUtensorMap, written when a raster's memory is first allocated
   int make_tensor_maps(int id);
   std::atomic<uint64_t> launches_{0};

@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "enc_costs.h"
 #include "engine.h"
 #include "vp8_math.cuh"
 
@@ -1209,206 +1210,130 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 16) k_loopfilter(const DevJob* 
 }
 
 // ================================================================================================
-// ENCODER kernels (first slice): luma_mb_inter_predict / diamond_search
-// (encoder/encode_inter.cc:172-369), luma_mb_best_prediction_mode + chroma (encode_intra.cc:83-355),
-// subtract_dct / wht / quantize (dct.cc:45-164, quantization.cc:148-178) and the reconstruction a
-// decoder will perform (macroblock.cc:504-601).  Decisions use SAD (the reference's RD search is
-// not reproduced yet); what is reproduced exactly is the transform / quantiser arithmetic and the
-// closed loop: the emitted records decode to the `out` raster bit for bit.
+// ENCODER kernel: the reference's macroblock decision loop on the device.
+//   key frames    luma_mb_best_prediction_mode incl. the B_PRED trial (encode_intra.cc:83-161, 360-387),
+//                 chroma by minimum distortion (:250-285)
+//   inter frames  16x16 intra modes against ZEROMV / NEARESTMV / NEARMV / NEWMV of the LAST frame with the
+//                 motion-vector census, mode costs of the census, diamond search (encode_inter.cc:172-369)
+//   both          rdcost (encoder.cc:410-416), variance / sse / sad (variance.cc:34-82), subtract_dct / wht
+//                 (dct.cc:45-164), truncating quantiser (quantization.cc:148-178), and the reconstruction a
+//                 decoder will perform (macroblock.cc:504-601).
+// The decisions are the reference's integers in the reference's order (ties go to the earlier candidate), so
+// at the same quantiser the records equal the ones parsed back from the reference encoder's own output
+// (tests/test_gpu_encoder.py).  One warp per macroblock ROW, rows chained by progress counters (2-macroblock
+// lag: intra prediction reads the above-right macroblock, the census the above and above-left records).
 // ================================================================================================
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
-
-constexpr int ME_RANGE = 15;           // full-pel search range
-constexpr int ME_WIN = 16 + 2 * 16;    // staged window: 48 x 48 around the macroblock
-constexpr int ENC_WARPS = 4;
-
-// 16x16 SAD of the source block against the staged window at full-pel offset (dx, dy)
-__device__ __forceinline__ int sad_window(const uint8_t* src, const uint8_t* win, int dx, int dy, int lane) {
-  const int y = lane >> 1, x0 = (lane & 1) * 8;
-  const uint8_t* s = src + y * 16 + x0;
-  const uint8_t* w = win + (16 + dy + y) * ME_WIN + 16 + dx + x0;
-  int acc = 0;
-#pragma unroll
-  for (int k = 0; k < 8; k++) acc += abs((int)s[k] - (int)w[k]);
-  return warp_sum(acc);
+__device__ __forceinline__ uint32_t rdcost(uint32_t rate, uint32_t distortion, uint32_t rm, uint32_t dm) {
+  return ((128u + rate * rm) / 256u) + distortion * dm;
 }
-__device__ __forceinline__ int sad_16x16(const uint8_t* a, const uint8_t* b, int lane) {
+// Encoder::variance over 16x16: lanes hold partial sums of the differences and of their squares
+__device__ __forceinline__ uint32_t variance256(int sum, int sse) {
+  const long long s = warp_sum(sum);
+  const uint32_t q = (uint32_t)warp_sum(sse);
+  return q - (uint32_t)((s * s) / 256);
+}
+
+struct __align__(16) EncSmem {  // per warp
+  uint8_t W[17 * WS];      // luma workspace with borders (see k_intra): final prediction / reconstruction
+  uint8_t Wb[17 * WS];     // B_PRED trial reconstruction
+  uint8_t src[384];
+  uint8_t pcand[2][256];   // inter candidates: the one being tried, the best so far
+  uint8_t pixc[128];
+  uint8_t tile[21 * 24];
+  uint8_t mid[21 * 16];
+  int16_t coef[COEF_I16];
+  int16_t qb[16][16];      // quantised coefficients of the B_PRED trial
+  int16_t tmp[16];
+  uint8_t aboveC[2][12];
+  uint8_t leftC[2][8];
+};
+
+// 16x16 luma prediction of `mv` from the reference into dst (stride 16): Block<16>::inter_predict on a SafeRaster
+__device__ __forceinline__ void enc_mc16(const EncJob& J, const Geom& g, int px, int py, int mvx, int mvy, uint8_t* dst,
+                                         EncSmem& S, int lane) {
+  mc_block<16>(J.ref, g.y_pitch, g.W, g.H, px, py, mvx, mvy, dst, 16, S.tile, S.mid, lane);
+}
+__device__ __forceinline__ uint32_t enc_variance(const uint8_t* src, const uint8_t* pred, int lane) {
+  const int o = (lane >> 1) * 16 + (lane & 1) * 8;
+  int sum = 0, sse = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int d = (int)src[o + k] - (int)pred[o + k];
+    sum += d;
+    sse += d * d;
+  }
+  return variance256(sum, sse);
+}
+__device__ __forceinline__ uint32_t enc_sad(const uint8_t* src, const uint8_t* pred, int lane) {
   const int o = (lane >> 1) * 16 + (lane & 1) * 8;
   int acc = 0;
 #pragma unroll
-  for (int k = 0; k < 8; k++) acc += abs((int)a[o + k] - (int)b[o + k]);
-  return warp_sum(acc);
+  for (int k = 0; k < 8; k++) acc += abs((int)src[o + k] - (int)pred[o + k]);
+  return (uint32_t)warp_sum(acc);
+}
+// Scorer::clamp (macroblock.cc:183-195)
+__device__ __forceinline__ void clamp_mv(int& x, int& y, int col, int row, int cols, int rows) {
+  const int to_left = max(-((col * 16) << 3) - 128, -32768), to_right = min((((cols - 1 - col) * 16) << 3) + 128, 32767);
+  const int to_top = max(-((row * 16) << 3) - 128, -32768), to_bottom = min((((rows - 1 - row) * 16) << 3) + 128, 32767);
+  x = min(max(x, to_left), to_right);
+  y = min(max(y, to_top), to_bottom);
+}
+// KeyFrameMacroblock::implied_subblock_mode
+__device__ __forceinline__ int implied_bmode(int y_mode) {
+  return y_mode == VP8GPU_V_PRED ? VP8GPU_B_VE_PRED : (y_mode == VP8GPU_H_PRED ? VP8GPU_B_HE_PRED : (y_mode == VP8GPU_TM_PRED ? VP8GPU_B_TM_PRED : VP8GPU_B_DC_PRED));
 }
 
-__global__ void __launch_bounds__(ENC_WARPS * 32) k_enc_motion(const EncJob* __restrict__ jobp, Geom g) {
-  __shared__ __align__(16) uint8_t s_src[ENC_WARPS][256];
-  __shared__ __align__(16) uint8_t s_win[ENC_WARPS][ME_WIN * ME_WIN];
-  __shared__ __align__(16) uint8_t s_pred[ENC_WARPS][256];
-  __shared__ __align__(16) uint8_t s_tile[ENC_WARPS][21 * 24];
-  __shared__ __align__(16) uint8_t s_mid[ENC_WARPS][21 * 16];
-  const EncJob& J = *jobp;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mbi = blockIdx.x * ENC_WARPS + warp;
-  if (mbi >= g.mb_cols * g.mb_rows) return;
-  const int row = mbi / g.mb_cols, col = mbi - row * g.mb_cols;
-  uint8_t* src = s_src[warp];
-  uint8_t* win = s_win[warp];
-  uint8_t* pred = s_pred[warp];
-  // source macroblock: 64 words
-  for (int i = lane; i < 64; i += 32) {
-    const int r = i >> 2, w = i & 3;
-    reinterpret_cast<uint32_t*>(src)[i] = __ldg(reinterpret_cast<const uint32_t*>(J.src + (size_t)(16 * row + r) * g.y_pitch + 16 * col) + w);
-  }
-  // search window with clamped coordinates (the reference searches a 256-pixel padded SafeRaster)
-  const int wx = 16 * col - 16, wy = 16 * row - 16;
-  if (wx >= 0 && wy >= 0 && wx + ME_WIN <= g.W && wy + ME_WIN <= g.H) {
-    for (int i = lane; i < ME_WIN * (ME_WIN / 4); i += 32) {
-      const int r = i / (ME_WIN / 4), w = i - r * (ME_WIN / 4);
-      reinterpret_cast<uint32_t*>(win)[i] = __ldg(reinterpret_cast<const uint32_t*>(J.ref + (size_t)(wy + r) * g.y_pitch + wx) + w);
-    }
-  } else {
-    for (int i = lane; i < ME_WIN * ME_WIN; i += 32) {
-      const int r = i / ME_WIN, c = i - r * ME_WIN;
-      win[i] = __ldg(J.ref + (size_t)clampi(wy + r, 0, g.H - 1) * g.y_pitch + clampi(wx + c, 0, g.W - 1));
-    }
-  }
-  __syncwarp();
-
-  // ---- full-pel: greedy 4-point pattern with shrinking step (a small diamond search) ----
-  int bx = 0, by = 0;
-  int best = sad_window(src, win, 0, 0, lane);
-  for (int step = 8; step >= 1; step >>= 1) {
-    for (int iter = 0; iter < 4; iter++) {
-      bool moved = false;
-#pragma unroll
-      for (int d = 0; d < 4; d++) {
-        const int cx = bx + ((d == 0) - (d == 1)) * step, cy = by + ((d == 2) - (d == 3)) * step;
-        if (abs(cx) > ME_RANGE || abs(cy) > ME_RANGE) continue;
-        const int s = sad_window(src, win, cx, cy, lane);
-        if (s < best) {
-          best = s;
-          bx = cx;
-          by = cy;
-          moved = true;
-        }
-      }
-      if (!moved) break;
-    }
-  }
-  // ---- sub-pel: half-pel then quarter-pel neighbours of the best vector, six-tap predicted ----
-  int mvx = bx * 8, mvy = by * 8;
-  if (best > 64) {
-    for (int step = 4; step >= 2; step >>= 1) {
-      int cbx = mvx, cby = mvy;
-      for (int d = 0; d < 8; d++) {
-        const int ox = (d == 0 || d == 4 || d == 6) ? -1 : ((d == 1 || d == 5 || d == 7) ? 1 : 0);
-        const int oy = (d == 2 || d == 4 || d == 5) ? -1 : ((d == 3 || d == 6 || d == 7) ? 1 : 0);
-        const int cx = mvx + ox * step, cy = mvy + oy * step;
-        mc_block<16>(J.ref, g.y_pitch, g.W, g.H, 16 * col, 16 * row, cx, cy, pred, 16, s_tile[warp], s_mid[warp], lane);
-        const int s = sad_16x16(src, pred, lane);
-        if (s < best) {
-          best = s;
-          cbx = cx;
-          cby = cy;
-        }
-      }
-      mvx = cbx;
-      mvy = cby;
-    }
-  }
-  if (lane == 0) {
-    J.mv[2 * mbi] = mvx;
-    J.mv[2 * mbi + 1] = mvy;
-    J.sad[mbi] = (uint32_t)best;
-  }
-}
-
-__global__ void __launch_bounds__(32 * WF_WARPS, 12) k_enc_mb(const EncJob* __restrict__ jobp, Geom g, int* ticket) {
-  __shared__ __align__(16) uint8_t s_W[WF_WARPS][17 * WS];
-  __shared__ __align__(16) uint8_t s_pixc[WF_WARPS][128];
-  __shared__ __align__(16) uint8_t s_src[WF_WARPS][384];
-  __shared__ __align__(16) uint8_t s_pinter[WF_WARPS][384];
-  __shared__ __align__(16) int16_t s_coef[WF_WARPS][COEF_I16];
-  __shared__ __align__(16) uint8_t s_tile[WF_WARPS][21 * 24];
-  __shared__ __align__(16) uint8_t s_mid[WF_WARPS][21 * 16];
-  __shared__ uint8_t s_aboveC[WF_WARPS][2][12];
-  __shared__ uint8_t s_leftC[WF_WARPS][2][8];
+__global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __restrict__ jobp, Geom g, int* ticket) {
+  __shared__ EncSmem s_all[WF_WARPS];
+  __shared__ uint16_t s_lut[128];
   const EncJob& J = *jobp;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint8_t* const W = s_W[warp];
-  uint8_t* const pixc = s_pixc[warp];
-  uint8_t* const src = s_src[warp];
-  uint8_t* const pinter = s_pinter[warp];
-  int16_t* const coef = s_coef[warp];
-  uint8_t (*const aboveC)[12] = s_aboveC[warp];
-  uint8_t (*const leftC)[8] = s_leftC[warp];
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) s_lut[i] = k_bpred_lut[i];
+  __syncthreads();
+  EncSmem& S = s_all[warp];
+  uint8_t* const W = S.W;
+  uint8_t* const pixc = S.pixc;
+  uint8_t* const src = S.src;
+  int16_t* const coef = S.coef;
   int t = 0;
   if (lane == 0) t = atomicAdd(ticket, 1);
   t = __shfl_sync(0xffffffffu, t, 0);
   const int row = t;
-  if (row >= g.mb_rows) return;
-  const int cols = g.mb_cols;
+  const int cols = J.cols, rows = J.rows, sub = J.sub;
+  if (row >= rows) return;
   int* progress = J.progress + row;
   uint8_t* const Y = J.out;
   uint8_t* const U = J.out + g.u_off;
   uint8_t* const V = J.out + g.v_off;
   const int CW = g.W >> 1, CH = g.H >> 1;
   const vp8gpu_quant q = J.q;
+  const EncTables& T = *J.tab;
+  const uint32_t RM = J.rate_mult, DM = J.dist_mult;
+  const bool key = J.key_frame != 0;
 
-  int left_mvx = 0, left_mvy = 0;
+  // what the census and the B_PRED contexts need from the macroblock to the left (this warp's previous one)
   bool left_inter = false;
+  int left_mvx = 0, left_mvy = 0, left_ymode = VP8GPU_DC_PRED;
+  unsigned long long left_bm = 0;
+
   for (int col = 0; col < cols; col++) {
     const int mbi = row * cols + col;
+    const int scol = sub * col, srow = sub * row;  // source / reference position of this macroblock
     // ---- source macroblock (96 words) ----
     for (int i = lane; i < 96; i += 32) {
       const uint8_t* gp;
-      if (i < 64) gp = J.src + (size_t)(16 * row + (i >> 2)) * g.y_pitch + 16 * col + 4 * (i & 3);
+      if (i < 64) gp = J.src + (size_t)(16 * srow + (i >> 2)) * g.y_pitch + 16 * scol + 4 * (i & 3);
       else {
         const int c = i - 64, plane = c >> 4, k = c & 15;
-        gp = J.src + (plane ? g.v_off : g.u_off) + (size_t)(8 * row + (k >> 1)) * g.c_pitch + 8 * col + 4 * (k & 1);
+        gp = J.src + (plane ? g.v_off : g.u_off) + (size_t)(8 * srow + (k >> 1)) * g.c_pitch + 8 * scol + 4 * (k & 1);
       }
       reinterpret_cast<uint32_t*>(src)[i] = __ldg(reinterpret_cast<const uint32_t*>(gp));
     }
-    int mvx = 0, mvy = 0, cost_inter = 0x7fffffff;
     __syncwarp();
     if (row > 0) wait_row(progress - 1, min(col + 2, cols), lane);
-    if (!J.key_frame) {
-      // candidate vectors: the searched one, zero, and the vectors the left / above macroblocks chose
-      // (cheap to code: they become ZEROMV / NEARESTMV / NEARMV in the bitstream).  A candidate's cost
-      // is its luma SAD plus lambda * (rough bits of the mode + vector), lambda ~ quantiser step.
-      const int lambda = max(1, (int)q.y_ac >> 3);
-      int best_cost = 0x7fffffff;
-      int cand_x[4], cand_y[4], cand_bits[4], n_cand = 0;
-      cand_x[n_cand] = 0, cand_y[n_cand] = 0, cand_bits[n_cand++] = 2;
-      if (col > 0 && left_inter && (left_mvx | left_mvy)) cand_x[n_cand] = left_mvx, cand_y[n_cand] = left_mvy, cand_bits[n_cand++] = 4;
-      if (row > 0) {
-        const uint4 ar = __ldcg(reinterpret_cast<const uint4*>(J.mbs + mbi - cols));
-        const int a_ref = ar.z & 0xFF, ax = (int16_t)(ar.w & 0xFFFF), ay = (int16_t)(ar.w >> 16);
-        if (a_ref != VP8GPU_REF_CURRENT && (ax | ay) && !(n_cand == 2 && ax == cand_x[1] && ay == cand_y[1]))
-          cand_x[n_cand] = ax, cand_y[n_cand] = ay, cand_bits[n_cand++] = 4;
-      }
-      {
-        const int sx = J.mv[2 * mbi], sy = J.mv[2 * mbi + 1];
-        bool dup = false;
-        for (int k = 0; k < n_cand; k++) dup |= cand_x[k] == sx && cand_y[k] == sy;
-        if (!dup) cand_x[n_cand] = sx, cand_y[n_cand] = sy, cand_bits[n_cand++] = 16;
-      }
-      for (int k = 0; k < n_cand; k++) {
-        mc_block<16>(J.ref, g.y_pitch, g.W, g.H, 16 * col, 16 * row, cand_x[k], cand_y[k], pinter, 16, s_tile[warp], s_mid[warp], lane);
-        const int c = sad_16x16(src, pinter, lane) + lambda * cand_bits[k];
-        if (c < best_cost) best_cost = c, mvx = cand_x[k], mvy = cand_y[k];
-      }
-      const int cmx = chroma_component(4 * mvx), cmy = chroma_component(4 * mvy);
-      mc_block<16>(J.ref, g.y_pitch, g.W, g.H, 16 * col, 16 * row, mvx, mvy, pinter, 16, s_tile[warp], s_mid[warp], lane);
-      mc_block<8>(J.ref + g.u_off, g.c_pitch, CW, CH, 8 * col, 8 * row, cmx, cmy, pinter + 256, 8, s_tile[warp], s_mid[warp], lane);
-      mc_block<8>(J.ref + g.v_off, g.c_pitch, CW, CH, 8 * col, 8 * row, cmx, cmy, pinter + 320, 8, s_tile[warp], s_mid[warp], lane);
-      int acc = 0;
-      for (int i = 256 + lane; i < 384; i += 32) acc += abs((int)src[i] - (int)pinter[i]);
-      cost_inter = best_cost + warp_sum(acc);
-    }
-    __syncwarp();
 
-    // ---- edges of the reconstruction so far (same rules as the decoder, prediction.cc:99-167) ----
+    // ---- edges of the reconstruction so far (prediction.cc:99-167; same rules as k_intra) ----
     {
       const int outside_above = row == 0 ? 127 : 129;
       const uint8_t* pa = Y;
@@ -1435,107 +1360,318 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 12) k_enc_mb(const EncJob* __re
       const int c = vc ? (int)ldcg_u8(pc) : outside_above;
       if (lane < 21) W[15 + lane] = (uint8_t)a;
       if (lane < 16) W[(lane + 1) * WS + 15] = (uint8_t)b;
-      else leftC[(lane >> 3) & 1][lane & 7] = (uint8_t)b;
-      if (lane < 18) aboveC[cpl][ck] = (uint8_t)c;
+      else S.leftC[(lane >> 3) & 1][lane & 7] = (uint8_t)b;
+      if (lane < 18) S.aboveC[cpl][ck] = (uint8_t)c;
+    }
+    // the records above (census, B_PRED contexts): published by the row above before its progress moved on
+    uint4 rec_a = make_uint4(0, 0, 0, 0), rec_al = make_uint4(0, 0, 0, 0);
+    unsigned long long above_bm = 0;
+    if (row > 0) {
+      rec_a = __ldcg(reinterpret_cast<const uint4*>(J.mbs + mbi - cols));
+      above_bm = __ldcg(reinterpret_cast<const unsigned long long*>(J.mbs + mbi - cols) + 3);
+      if (col > 0) rec_al = __ldcg(reinterpret_cast<const uint4*>(J.mbs + mbi - cols - 1));
     }
     __syncwarp();
 
-    // ---- intra candidates: SAD of the four 16x16 luma modes and the four chroma modes ----
-    const uint8_t* A = W + 16;
-    int dcY = 128;
-    {
-      int s = 0, n = 0;
-      if (row > 0) { for (int k = 0; k < 16; k++) s += A[k]; n += 16; }
-      if (col > 0) { for (int k = 0; k < 16; k++) s += W[(k + 1) * WS + 15]; n += 16; }
-      dcY = n == 32 ? (s + 16) >> 5 : (n == 16 ? (s + 8) >> 4 : 128);
+    const uint8_t* A = W + 16;  // above[x]
+    // ================= luma: luma_mb_best_prediction_mode (encode_intra.cc:83-161) =================
+    uint32_t best_cost = 0xFFFFFFFFu;
+    int best_mode = VP8GPU_DC_PRED;
+    unsigned long long bm = 0;  // B_PRED sub-block modes
+    const bool try_bpred = key || !J.realtime;
+    if (try_bpred) {
+      // ---- B_PRED trial: sub-blocks in raster order, each chosen by rdcost(mode cost, sse of the prediction)
+      //      and reconstructed before the next one is predicted ----
+      uint8_t* const Wb = S.Wb;
+      if (lane < 21) Wb[15 + lane] = W[15 + lane];
+      if (lane < 16) Wb[(lane + 1) * WS + 15] = W[(lane + 1) * WS + 15];
+      __syncwarp();
+      if (lane < 12) Wb[(4 + 4 * (lane >> 2)) * WS + 32 + (lane & 3)] = Wb[32 + (lane & 3)];  // above-right copies
+      __syncwarp();
+      uint32_t rate = T.ymode_cost[key ? 0 : 1][VP8GPU_B_PRED], dist = 0;
+      const int above_ymode = (rec_a.y >> 16) & 0xFF, above_ref = rec_a.z & 0xFF;
+      const int half = lane >> 4, px = lane & 15, x = px & 3, y = px >> 2;
+      for (int b = 0; b < 16; b++) {
+        const int bx = b & 3, by = b >> 2;
+        // context modes (encode_intra.cc:124-127): the sub-block above / to the left, B_DC_PRED outside the frame
+        int am, lm;
+        if (by > 0) am = (int)((bm >> (4 * (b - 4))) & 15);
+        else if (row == 0) am = VP8GPU_B_DC_PRED;
+        else am = (above_ref == VP8GPU_REF_CURRENT && above_ymode == VP8GPU_B_PRED) ? (int)((above_bm >> (4 * (12 + bx))) & 15)
+                                                                                   : (above_ref == VP8GPU_REF_CURRENT ? implied_bmode(above_ymode) : VP8GPU_B_DC_PRED);
+        if (bx > 0) lm = (int)((bm >> (4 * (b - 1))) & 15);
+        else if (col == 0) lm = VP8GPU_B_DC_PRED;
+        else lm = (!left_inter && left_ymode == VP8GPU_B_PRED) ? (int)((left_bm >> (4 * (4 * by + 3))) & 15)
+                                                                : (!left_inter ? implied_bmode(left_ymode) : VP8GPU_B_DC_PRED);
+        const uint16_t* mode_cost = T.bmode_cost[am][lm];
+        const uint8_t* e0 = Wb + (4 * by) * WS + 15 + 4 * bx;  // = above[-1] of this sub-block
+        const int sp = src[(4 * by + y) * 16 + 4 * bx + x];
+        int pv[5];
+        uint32_t best_err = 0xFFFFFFFFu, best_sse = 0;
+        int best_b = 0;
+#pragma unroll
+        for (int r = 0; r < 5; r++) {  // two modes per round: lanes 0-15 mode 2r, lanes 16-31 mode 2r + 1
+          const int mode = 2 * r + half;
+          int v;
+          if (mode == VP8GPU_B_DC_PRED) {
+            int s4 = 4;
+#pragma unroll
+            for (int k = 0; k < 4; k++) s4 += e0[1 + k] + e0[(1 + k) * WS];
+            v = s4 >> 3;
+          } else if (mode == VP8GPU_B_TM_PRED) {
+            v = vp8m::clamp255(e0[(1 + y) * WS] + e0[1 + x] - e0[0]);
+          } else {
+            const unsigned entry = s_lut[(mode - 2) * 16 + px];
+            const int ia = entry & 15, ib = (entry >> 4) & 15, ic = (entry >> 8) & 15;
+            const int pa = e0[ia < 4 ? (4 - ia) * WS : ia - 4];
+            const int pb = e0[ib < 4 ? (4 - ib) * WS : ib - 4];
+            const int pc = e0[ic < 4 ? (4 - ic) * WS : ic - 4];
+            v = (entry & 0x1000) ? ((pa + 2 * pb + pc + 2) >> 2) : ((pa + pb + 1) >> 1);
+          }
+          pv[r] = v;
+          int d2 = (sp - v) * (sp - v);
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+          const uint32_t sse_even = (uint32_t)__shfl_sync(0xffffffffu, d2, 0), sse_odd = (uint32_t)__shfl_sync(0xffffffffu, d2, 16);
+          const uint32_t err_even = rdcost(mode_cost[2 * r], sse_even, RM, DM), err_odd = rdcost(mode_cost[2 * r + 1], sse_odd, RM, DM);
+          if (err_even < best_err) best_err = err_even, best_b = 2 * r, best_sse = sse_even;
+          if (err_odd < best_err) best_err = err_odd, best_b = 2 * r + 1, best_sse = sse_odd;
+        }
+        rate += mode_cost[best_b];
+        dist += best_sse;
+        bm |= (unsigned long long)best_b << (4 * b);
+        // the chosen prediction of pixel px sits in lane (best_b & 1) * 16 + px, round best_b >> 1
+        const int rr = best_b >> 1;
+        const int mine = rr == 0 ? pv[0] : (rr == 1 ? pv[1] : (rr == 2 ? pv[2] : (rr == 3 ? pv[3] : pv[4])));
+        const int pred = __shfl_sync(0xffffffffu, mine, (best_b & 1) * 16 + px);
+        // luma_sb_apply_intra_prediction: subtract_dct, quantise (Y without Y2: the DC uses y_dc), reconstruct
+        if (lane < 16) S.tmp[lane] = (int16_t)(sp - pred);
+        __syncwarp();
+        if (lane == 0) {
+          int16_t d[16], o[16];
+#pragma unroll
+          for (int k = 0; k < 16; k++) d[k] = S.tmp[k];
+          vp8m::fdct16(d, o);
+#pragma unroll
+          for (int k = 0; k < 16; k++) {
+            const int f = k ? q.y_ac : q.y_dc;
+            int qv = vp8m::quantize_trunc(o[k], f);
+            qv = qv > 2047 ? 2047 : (qv < -2047 ? -2047 : qv);
+            S.qb[b][k] = (int16_t)qv;
+            d[k] = (int16_t)(qv * f);
+          }
+          vp8m::idct16(d, o);
+#pragma unroll
+          for (int k = 0; k < 16; k++) S.tmp[k] = o[k];
+        }
+        __syncwarp();
+        if (lane < 16) Wb[(4 * by + y + 1) * WS + 16 + 4 * bx + x] = (uint8_t)vp8m::clamp255(pred + S.tmp[lane]);
+        __syncwarp();
+      }
+      best_cost = rdcost(rate, dist, RM, DM);
+      best_mode = VP8GPU_B_PRED;
     }
-    int sdc = 0, sv = 0, sh = 0, stm = 0;
+    // ---- 16x16 modes, in the reference's order TM, H, V, DC; distortion = variance of the prediction ----
     {
       const int y = lane >> 1, x8 = (lane & 1) * 8;
       const int left = W[(y + 1) * WS + 15], corner = W[15];
+      int dcY;
+      {
+        int s = 0, n = 0;
+        if (row > 0) { for (int k = 0; k < 16; k++) s += A[k]; n += 16; }
+        if (col > 0) { for (int k = 0; k < 16; k++) s += W[(k + 1) * WS + 15]; n += 16; }
+        dcY = n == 32 ? (s + 16) >> 5 : (n == 16 ? (s + 8) >> 4 : 128);
+      }
+      int s_tm = 0, q_tm = 0, s_h = 0, q_h = 0, s_v = 0, q_v = 0, s_dc = 0, q_dc = 0;
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         const int sp = src[y * 16 + x8 + k], ab = A[x8 + k];
-        sdc += abs(sp - dcY);
-        sv += abs(sp - ab);
-        sh += abs(sp - left);
-        stm += abs(sp - vp8m::clamp255(left + ab - corner));
+        int d = sp - vp8m::clamp255(left + ab - corner);
+        s_tm += d, q_tm += d * d;
+        d = sp - left;
+        s_h += d, q_h += d * d;
+        d = sp - ab;
+        s_v += d, q_v += d * d;
+        d = sp - dcY;
+        s_dc += d, q_dc += d * d;
+      }
+      const uint16_t* mc = T.ymode_cost[key ? 0 : 1];
+      uint32_t c = rdcost(mc[VP8GPU_TM_PRED], variance256(s_tm, q_tm), RM, DM);
+      if (c < best_cost) best_cost = c, best_mode = VP8GPU_TM_PRED;
+      c = rdcost(mc[VP8GPU_H_PRED], variance256(s_h, q_h), RM, DM);
+      if (c < best_cost) best_cost = c, best_mode = VP8GPU_H_PRED;
+      c = rdcost(mc[VP8GPU_V_PRED], variance256(s_v, q_v), RM, DM);
+      if (c < best_cost) best_cost = c, best_mode = VP8GPU_V_PRED;
+      c = rdcost(mc[VP8GPU_DC_PRED], variance256(s_dc, q_dc), RM, DM);
+      if (c < best_cost) best_cost = c, best_mode = VP8GPU_DC_PRED;
+    }
+
+    // ================= inter candidates: luma_mb_inter_predict (encode_inter.cc:231-369) =================
+    int best_mvx = 0, best_mvy = 0, keep = 0;  // keep: which pcand buffer holds the best inter prediction
+    if (!key) {
+      // ---- census of the vectors above, left and above-left (Scorer, macroblock.cc:143-174; all LAST: no sign flips) ----
+      int cmx[4] = {0, 0, 0, 0}, cmy[4] = {0, 0, 0, 0}, score[4] = {0, 0, 0, 0}, idx = 0;
+      auto add = [&](int weight, bool inter, int vx, int vy) {
+        if (!inter) return;
+        if ((vx | vy) == 0) {
+          score[0] += weight;
+        } else {
+          if (!(vx == cmx[idx] && vy == cmy[idx])) {
+            idx++;
+            cmx[idx] = vx, cmy[idx] = vy;
+          }
+          score[idx] += weight;
+        }
+      };
+      if (row > 0) add(2, (rec_a.z & 0xFF) != VP8GPU_REF_CURRENT, (int16_t)(rec_a.w & 0xFFFF), (int16_t)(rec_a.w >> 16));
+      if (col > 0) add(2, left_inter, left_mvx, left_mvy);
+      if (row > 0 && col > 0) add(1, (rec_al.z & 0xFF) != VP8GPU_REF_CURRENT, (int16_t)(rec_al.w & 0xFFFF), (int16_t)(rec_al.w >> 16));
+      if (score[3] && cmx[idx] == cmx[1] && cmy[idx] == cmy[1]) score[1] += score[3];
+      if (score[2] > score[1]) {
+        int tswap = score[1];
+        score[1] = score[2], score[2] = tswap;
+        tswap = cmx[1], cmx[1] = cmx[2], cmx[2] = tswap;
+        tswap = cmy[1], cmy[1] = cmy[2], cmy[2] = tswap;
+      }
+      if (score[1] >= score[0]) cmx[0] = cmx[1], cmy[0] = cmy[1];
+      int brx = cmx[0], bry = cmy[0], nrx = cmx[1], nry = cmy[1], nex = cmx[2], ney = cmy[2];
+      clamp_mv(brx, bry, col, row, cols, rows);
+      clamp_mv(nrx, nry, col, row, cols, rows);
+      clamp_mv(nex, ney, col, row, cols, rows);
+      // mode costs of this census (fill_mv_ref_costs; the split count is 0: the encoder never codes SPLITMV)
+      const uint32_t c_zero = T.mvref_zero[0][score[0]];
+      const uint32_t c_nearest = T.mvref_one[0][score[0]] + T.mvref_zero[1][score[1]];
+      const uint32_t c_near = T.mvref_one[0][score[0]] + T.mvref_one[1][score[1]] + T.mvref_zero[2][score[2]];
+      const uint32_t c_new = T.mvref_one[0][score[0]] + T.mvref_one[1][score[1]] + T.mvref_one[2][score[2]] + T.mvref_zero[3][0];
+      const int px0 = 16 * scol, py0 = 16 * srow;
+      int cur = 0;
+      auto consider = [&](int mode, int vx, int vy, uint32_t rate) {
+        enc_mc16(J, g, px0, py0, vx, vy, S.pcand[cur], S, lane);
+        const uint32_t c = rdcost(rate, enc_variance(src, S.pcand[cur], lane), RM, DM);
+        if (c < best_cost) {
+          best_cost = c, best_mode = mode, best_mvx = vx, best_mvy = vy;
+          keep = cur;
+          cur ^= 1;
+        }
+      };
+      consider(VP8GPU_ZEROMV, 0, 0, c_zero);
+      if (nrx | nry) consider(VP8GPU_NEARESTMV, nrx, nry, c_nearest);
+      if (nex | ney) consider(VP8GPU_NEARMV, nex, ney, c_near);
+      if (!J.realtime || ((col & 3) == 0 && (row & 3) == 0)) {
+        // ---- NEWMV: repeated diamond searches around the census' best vector (encode_inter.cc:172-229, 279-293) ----
+        int mvx = 0, mvy = 0;
+        for (int step = 512; step > 1;) {
+          int ox = mvx, oy = mvy, first_step = step / 2;
+          for (int sz = step; sz > 1; sz >>= 1) {
+            uint32_t bc = 0xFFFFFFFFu;
+            int bx2 = 0, by2 = 0;  // MBPredictionData{}.mv: if every site is out of bounds the origin becomes (0, 0)
+#pragma unroll 1
+            for (int site = 0; site < 5; site++) {
+              const int dx = site == 0 ? -1 : (site == 4 ? 1 : 0), dy = site == 1 ? -1 : (site == 3 ? 1 : 0);
+              const int cx = ox + sz * dx, cy = oy + sz * dy;
+              if (cx > 1023 || cx < -1023 || cy > 1023 || cy < -1023) continue;
+              int tx = (int16_t)(cx + brx), ty = (int16_t)(cy + bry);
+              clamp_mv(tx, ty, col, row, cols, rows);
+              enc_mc16(J, g, px0, py0, tx, ty, S.pcand[cur], S, lane);
+              const uint32_t sad = enc_sad(src, S.pcand[cur], lane);
+              const int sx = max(min(cx >> 2, 255), -255), sy = max(min(cy >> 2, 255), -255);
+              const uint32_t rate = ((uint32_t)(T.mv_sad_cost[abs(sy)] + T.mv_sad_cost[abs(sx)]) * J.sad_per_bit + 128u) / 256u;
+              const uint32_t c = ((128u + rate) / 256u) + sad;  // rdcost( rate, distortion, 1, 1 )
+              if (c < bc) bc = c, bx2 = cx, by2 = cy;
+            }
+            if (bx2 == ox && by2 == oy) first_step = sz / 2;
+            ox = bx2, oy = by2;
+          }
+          if (ox == mvx && oy == mvy) break;
+          mvx = ox, mvy = oy;
+          step = first_step;
+        }
+        const int dvx = mvx, dvy = mvy;  // mv - best_ref
+        mvx = (int16_t)(mvx + brx), mvy = (int16_t)(mvy + bry);
+        if (mvx | mvy) {
+          const uint32_t mvc = (uint32_t)(T.mv_mag_cost[0][abs(dvy)] + (dvy ? T.mv_sign_cost[0][dvy < 0] : 0) + T.mv_mag_cost[1][abs(dvx)] +
+                                          (dvx ? T.mv_sign_cost[1][dvx < 0] : 0));
+          consider(VP8GPU_NEWMV, mvx, mvy, c_new + (mvc * 96u) / 128u);
+        }
       }
     }
-    sdc = warp_sum(sdc);
-    sv = warp_sum(sv);
-    sh = warp_sum(sh);
-    stm = warp_sum(stm);
-    int y_mode = VP8GPU_DC_PRED, sadY = sdc;
-    if (sv < sadY) sadY = sv, y_mode = VP8GPU_V_PRED;
-    if (sh < sadY) sadY = sh, y_mode = VP8GPU_H_PRED;
-    if (stm < sadY) sadY = stm, y_mode = VP8GPU_TM_PRED;
-    int cdc[2];
-#pragma unroll
-    for (int plane = 0; plane < 2; plane++) {
-      int s = 0, n = 0;
-      if (row > 0) { for (int k = 0; k < 8; k++) s += aboveC[plane][1 + k]; n += 8; }
-      if (col > 0) { for (int k = 0; k < 8; k++) s += leftC[plane][k]; n += 8; }
-      cdc[plane] = n == 16 ? (s + 8) >> 4 : (n == 8 ? (s + 4) >> 3 : 128);
-    }
-    int cs0 = 0, cs1 = 0, cs2 = 0, cs3 = 0;
+    const bool inter = best_mode > VP8GPU_B_PRED;
+    __syncwarp();
+
+    // ================= chroma =================
+    int uv_mode = VP8GPU_DC_PRED;
     const int cplane = lane >> 4, cy = (lane >> 1) & 7, cx4 = (lane & 1) * 4;
-    {
-      const uint8_t* CA = aboveC[cplane] + 1;
-      const int cl = leftC[cplane][cy], ccorner = CA[-1], cd = cplane ? cdc[1] : cdc[0];
+    if (inter) {
+      const int cmvx = chroma_component(4 * best_mvx), cmvy = chroma_component(4 * best_mvy);
+      mc_block<8>(J.ref + g.u_off, g.c_pitch, CW, CH, 8 * scol, 8 * srow, cmvx, cmvy, pixc, 8, S.tile, S.mid, lane);
+      mc_block<8>(J.ref + g.v_off, g.c_pitch, CW, CH, 8 * scol, 8 * srow, cmvx, cmvy, pixc + 64, 8, S.tile, S.mid, lane);
+    } else {
+      // chroma_mb_best_prediction_mode (encode_intra.cc:250-285): smallest sse( U ) + sse( V ), DC V H TM, first wins
+      int cdc[2];
+#pragma unroll
+      for (int plane = 0; plane < 2; plane++) {
+        int s = 0, n = 0;
+        if (row > 0) { for (int k = 0; k < 8; k++) s += S.aboveC[plane][1 + k]; n += 8; }
+        if (col > 0) { for (int k = 0; k < 8; k++) s += S.leftC[plane][k]; n += 8; }
+        cdc[plane] = n == 16 ? (s + 8) >> 4 : (n == 8 ? (s + 4) >> 3 : 128);
+      }
+      const uint8_t* CA = S.aboveC[cplane] + 1;
+      const int cl = S.leftC[cplane][cy], ccorner = CA[-1], cd = cplane ? cdc[1] : cdc[0];
+      int e0 = 0, e1 = 0, e2 = 0, e3 = 0;
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         const int sp = src[256 + cplane * 64 + cy * 8 + cx4 + k], ab = CA[cx4 + k];
-        cs0 += abs(sp - cd);
-        cs1 += abs(sp - ab);
-        cs2 += abs(sp - cl);
-        cs3 += abs(sp - vp8m::clamp255(cl + ab - ccorner));
+        int d = sp - cd;
+        e0 += d * d;
+        d = sp - ab;
+        e1 += d * d;
+        d = sp - cl;
+        e2 += d * d;
+        d = sp - vp8m::clamp255(cl + ab - ccorner);
+        e3 += d * d;
       }
+      e0 = warp_sum(e0), e1 = warp_sum(e1), e2 = warp_sum(e2), e3 = warp_sum(e3);
+      uint32_t bd = (uint32_t)e0;
+      if ((uint32_t)e1 < bd) bd = e1, uv_mode = VP8GPU_V_PRED;
+      if ((uint32_t)e2 < bd) bd = e2, uv_mode = VP8GPU_H_PRED;
+      if ((uint32_t)e3 < bd) bd = e3, uv_mode = VP8GPU_TM_PRED;
+      uint32_t word;
+      if (uv_mode == VP8GPU_DC_PRED) word = (uint32_t)cd * 0x01010101u;
+      else if (uv_mode == VP8GPU_V_PRED) word = (uint32_t)CA[cx4] | ((uint32_t)CA[cx4 + 1] << 8) | ((uint32_t)CA[cx4 + 2] << 16) | ((uint32_t)CA[cx4 + 3] << 24);
+      else if (uv_mode == VP8GPU_H_PRED) word = (uint32_t)cl * 0x01010101u;
+      else {
+        const int base = cl - ccorner;
+        word = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) word |= (uint32_t)vp8m::clamp255(base + CA[cx4 + k]) << (8 * k);
+      }
+      *reinterpret_cast<uint32_t*>(pixc + cplane * 64 + cy * 8 + cx4) = word;
     }
-    cs0 = warp_sum(cs0);
-    cs1 = warp_sum(cs1);
-    cs2 = warp_sum(cs2);
-    cs3 = warp_sum(cs3);
-    int uv_mode = VP8GPU_DC_PRED, sadC = cs0;
-    if (cs1 < sadC) sadC = cs1, uv_mode = VP8GPU_V_PRED;
-    if (cs2 < sadC) sadC = cs2, uv_mode = VP8GPU_H_PRED;
-    if (cs3 < sadC) sadC = cs3, uv_mode = VP8GPU_TM_PRED;
+    __syncwarp();
 
-    // ---- inter or intra?  (intra macroblocks of inter frames cost more header bits: small bias) ----
-    const bool inter = !J.key_frame && cost_inter <= sadY + sadC + max(1, (int)q.y_ac >> 3) * 12;
-
-    // ---- materialise the chosen prediction in the workspace ----
+    // ================= luma prediction into the workspace, residual, transforms =================
+    const bool bpred = best_mode == VP8GPU_B_PRED;
     if (inter) {
+      const uint8_t* pbest = S.pcand[keep];
       for (int i = lane; i < 64; i += 32) {
         const int y = i >> 2, x4 = (i & 3) * 4;
-        *reinterpret_cast<uint32_t*>(W + (y + 1) * WS + 16 + x4) = *reinterpret_cast<const uint32_t*>(pinter + y * 16 + x4);
+        *reinterpret_cast<uint32_t*>(W + (y + 1) * WS + 16 + x4) = *reinterpret_cast<const uint32_t*>(pbest + y * 16 + x4);
       }
-      reinterpret_cast<uint32_t*>(pixc)[lane] = reinterpret_cast<const uint32_t*>(pinter + 256)[lane];
-    } else {
-      {
-        const uint8_t* CA = aboveC[cplane] + 1;
-        const int cl = leftC[cplane][cy];
-        uint32_t word;
-        if (uv_mode == VP8GPU_DC_PRED) word = (uint32_t)(cplane ? cdc[1] : cdc[0]) * 0x01010101u;
-        else if (uv_mode == VP8GPU_V_PRED) word = (uint32_t)CA[cx4] | ((uint32_t)CA[cx4 + 1] << 8) | ((uint32_t)CA[cx4 + 2] << 16) | ((uint32_t)CA[cx4 + 3] << 24);
-        else if (uv_mode == VP8GPU_H_PRED) word = (uint32_t)cl * 0x01010101u;
-        else {
-          const int base = cl - CA[-1];
-          word = 0;
-#pragma unroll
-          for (int k = 0; k < 4; k++) word |= (uint32_t)vp8m::clamp255(base + CA[cx4 + k]) << (8 * k);
-        }
-        *reinterpret_cast<uint32_t*>(pixc + cplane * 64 + cy * 8 + cx4) = word;
-      }
+    } else if (!bpred) {
       const int y = lane >> 1, x8 = (lane & 1) * 8;
       const int left = W[(y + 1) * WS + 15];
       uint32_t w0, w1;
-      if (y_mode == VP8GPU_DC_PRED) w0 = w1 = (uint32_t)dcY * 0x01010101u;
-      else if (y_mode == VP8GPU_V_PRED) {
+      if (best_mode == VP8GPU_DC_PRED) {
+        int s = 0, n = 0;
+        if (row > 0) { for (int k = 0; k < 16; k++) s += A[k]; n += 16; }
+        if (col > 0) { for (int k = 0; k < 16; k++) s += W[(k + 1) * WS + 15]; n += 16; }
+        w0 = w1 = (uint32_t)(n == 32 ? (s + 16) >> 5 : (n == 16 ? (s + 8) >> 4 : 128)) * 0x01010101u;
+      } else if (best_mode == VP8GPU_V_PRED) {
         w0 = *reinterpret_cast<const uint32_t*>(A + x8);
         w1 = *reinterpret_cast<const uint32_t*>(A + x8 + 4);
-      } else if (y_mode == VP8GPU_H_PRED) w0 = w1 = (uint32_t)left * 0x01010101u;
-      else {
+      } else if (best_mode == VP8GPU_H_PRED) {
+        w0 = w1 = (uint32_t)left * 0x01010101u;
+      } else {
         const int base = left - W[15];
         w0 = w1 = 0;
 #pragma unroll
@@ -1549,9 +1685,8 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 12) k_enc_mb(const EncJob* __re
       *reinterpret_cast<uint32_t*>(W + (y + 1) * WS + 20 + x8) = w1;
     }
     __syncwarp();
-
-    // ---- residual -> forward DCT (one 4x4 block per lane), Y2 = WHT of the 16 luma DCs ----
-    if (lane < 24) {
+    // forward DCT, one 4x4 block per lane (B_PRED: the luma blocks were coded during the trial)
+    if (lane < 24 && !(bpred && lane < 16)) {
       int16_t d[16], o[16];
       if (lane < 16) {
         const int bx = lane & 3, by = lane >> 2;
@@ -1570,7 +1705,7 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 12) k_enc_mb(const EncJob* __re
       for (int k = 0; k < 16; k++) coef[lane * CS + k] = o[k];
     }
     __syncwarp();
-    if (lane == 24) {
+    if (!bpred && lane == 24) {  // Y2 = WHT of the sixteen luma DCs
       int16_t in[16], o[16];
 #pragma unroll
       for (int k = 0; k < 16; k++) in[k] = coef[k * CS];
@@ -1579,18 +1714,24 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 12) k_enc_mb(const EncJob* __re
       for (int k = 0; k < 16; k++) coef[24 * CS + k] = o[k];
     }
     __syncwarp();
-    // ---- quantise (truncating division), emit tokens, dequantise in place ----
+    // ---- quantise (truncating division), count tokens, dequantise in place ----
     int cnt = 0;
     int16_t qv[16];
-    if (lane < 25) {
+    const bool has_blk = lane < 24 || (lane == 24 && !bpred);
+    if (has_blk) {
       const int dcq = lane < 16 ? q.y_dc : (lane < 24 ? q.uv_dc : q.y2_dc);
       const int acq = lane < 16 ? q.y_ac : (lane < 24 ? q.uv_ac : q.y2_ac);
 #pragma unroll
       for (int k = 0; k < 16; k++) {
-        int c = coef[lane * CS + k];
-        if (lane < 16 && k == 0) c = 0;  // the luma DCs travel in Y2
-        int v = vp8m::quantize_trunc(c, k ? acq : dcq);
-        v = v > 2047 ? 2047 : (v < -2047 ? -2047 : v);  // largest magnitude a DCT token can carry is 2114
+        int v;
+        if (bpred && lane < 16) {
+          v = S.qb[lane][k];
+        } else {
+          int c = coef[lane * CS + k];
+          if (lane < 16 && k == 0) c = 0;  // the luma DCs travel in Y2
+          v = vp8m::quantize_trunc(c, k ? acq : dcq);
+          v = v > 2047 ? 2047 : (v < -2047 ? -2047 : v);  // largest magnitude a DCT token carries is 2114
+        }
         qv[k] = (int16_t)v;
         cnt += v != 0;
         coef[lane * CS + k] = (int16_t)(v * (k ? acq : dcq));  // DCTCoefficients::dequantize
@@ -1606,15 +1747,48 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 12) k_enc_mb(const EncJob* __re
     uint32_t base = 0;
     if (lane == 0 && total) base = atomicAdd(J.tok_counter, (uint32_t)total);
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (lane < 25 && cnt && base + total <= J.tok_cap) {
+    if (has_blk && cnt && base + total <= J.tok_cap) {
       uint32_t at = base + incl - cnt;
 #pragma unroll
       for (int k = 0; k < 16; k++)
         if (qv[k]) J.tokens[at++] = VP8GPU_TOKEN(lane, k, qv[k]);
     }
     __syncwarp();
+    if (inter && sub != 1) {
+      // Encoder::estimate_size hands Macroblock::reconstruct_inter the macroblock of the SAMPLED grid, and
+      // reconstruct_inter predicts from the raster position it is given (macroblock.cc:589-591): the
+      // reconstruction of a sampled inter macroblock is the reference at (col, row) -- not (4 col, 4 row),
+      // where the residual was taken -- plus that residual.  Reproduced, because the next macroblocks'
+      // intra candidates are predicted from it and the size estimate steers the quantiser search.
+      enc_mc16(J, g, 16 * col, 16 * row, best_mvx, best_mvy, S.pcand[0], S, lane);
+      for (int i = lane; i < 64; i += 32) {
+        const int y = i >> 2, x4 = (i & 3) * 4;
+        *reinterpret_cast<uint32_t*>(W + (y + 1) * WS + 16 + x4) = *reinterpret_cast<const uint32_t*>(S.pcand[0] + y * 16 + x4);
+      }
+      const int cmvx = chroma_component(4 * best_mvx), cmvy = chroma_component(4 * best_mvy);
+      mc_block<8>(J.ref + g.u_off, g.c_pitch, CW, CH, 8 * col, 8 * row, cmvx, cmvy, pixc, 8, S.tile, S.mid, lane);
+      mc_block<8>(J.ref + g.v_off, g.c_pitch, CW, CH, 8 * col, 8 * row, cmvx, cmvy, pixc + 64, 8, S.tile, S.mid, lane);
+      __syncwarp();
+    }
     // ---- reconstruct exactly like a decoder will ----
-    if (total) {
+    if (bpred) {
+      // luma is the trial's reconstruction; chroma residual through the shared inverse transforms
+      for (int i = lane; i < 64; i += 32) {
+        const int y = i >> 2, x4 = (i & 3) * 4;
+        *reinterpret_cast<uint32_t*>(W + (y + 1) * WS + 16 + x4) = *reinterpret_cast<const uint32_t*>(S.Wb + (y + 1) * WS + 16 + x4);
+      }
+      __syncwarp();
+      if (total) {
+        if (lane < 16) {  // no residual left to add to luma: blank the (dequantised) luma blocks
+          uint2* cv = reinterpret_cast<uint2*>(coef + lane * CS);
+#pragma unroll
+          for (int k = 0; k < 4; k++) cv[k] = make_uint2(0u, 0u);
+        }
+        __syncwarp();
+        inverse_transforms(coef, false, lane);
+        add_residuals_intra(W, pixc, coef, lane, false);
+      }
+    } else if (total) {
       inverse_transforms(coef, true, lane);
       add_residuals_intra(W, pixc, coef, lane, true);
     }
@@ -1628,22 +1802,24 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 12) k_enc_mb(const EncJob* __re
       vp8gpu_mb m;
       m.tok_off = base;
       m.tok_cnt = (uint16_t)total;
-      m.y_mode = (uint8_t)(inter ? ((mvx | mvy) ? VP8GPU_NEWMV : VP8GPU_ZEROMV) : y_mode);
+      m.y_mode = (uint8_t)best_mode;
       m.uv_mode = (uint8_t)(inter ? 0 : uv_mode);
       m.ref_frame = inter ? VP8GPU_REF_LAST : VP8GPU_REF_CURRENT;
       m.segment_id = 0;
       m.lf_level = J.lf_level;
-      m.flags = VP8GPU_MB_HAS_Y2;
-      m.mv_x = (int16_t)(inter ? mvx : 0);
-      m.mv_y = (int16_t)(inter ? mvy : 0);
+      m.flags = bpred ? 0 : VP8GPU_MB_HAS_Y2;
+      m.mv_x = (int16_t)(inter ? best_mvx : 0);
+      m.mv_y = (int16_t)(inter ? best_mvy : 0);
       m.split_idx = 0;
       m.reserved = 0;
-      m.b_modes = 0;
+      m.b_modes = bpred ? bm : 0;
       J.mbs[mbi] = m;
     }
-    left_mvx = inter ? mvx : 0;
-    left_mvy = inter ? mvy : 0;
     left_inter = inter;
+    left_mvx = inter ? best_mvx : 0;
+    left_mvy = inter ? best_mvy : 0;
+    left_ymode = best_mode;
+    left_bm = bpred ? bm : 0;
     publish_row(progress, col + 1, lane);
   }
 }
@@ -1675,13 +1851,13 @@ __global__ void k_compare(const uint8_t* __restrict__ a, const uint8_t* __restri
 // (encoder.cc:489-508).  util/ssim.cc binds x264's pixel_ssim_wxh: sums over 4x4 blocks, combined over
 // every 8x8 window at a 4-pixel step, float ratio per window, mean over (W/4-1)(H/4-1) windows
 // (restated in oracle/ref_shim/ssim_stub.cc; parity with x264 itself is unpinned in this image).
-// One thread per window; the per-window floats are added in double (the reference adds them in float
-// in raster order: equal to ~1e-6).
+// One thread per window writes the window's float (the same expression as x264's ssim_end1, no fused
+// multiply-add in it); the host adds them in float in raster order like pixel_ssim_wxh does, so the value
+// equals the CPU restatement's bit for bit (Engine::frames_ssim).
 // ================================================================================================
-__global__ void k_ssim(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, Geom g, double* out) {
+__global__ void k_ssim(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, Geom g, float* out) {
   const int nx = g.W / 4 - 1, ny = g.H / 4 - 1;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  float v = 0.f;
   if (i < nx * ny) {
     const int wy = i / nx, wx = i - wy * nx;
     const uint8_t* pa = a + (size_t)(4 * wy) * g.y_pitch + 4 * wx;
@@ -1707,12 +1883,9 @@ __global__ void k_ssim(const uint8_t* __restrict__ a, const uint8_t* __restrict_
     const int c1 = (int)(.01 * .01 * 255 * 255 * 64 + .5);
     const int c2 = (int)(.03 * .03 * 255 * 255 * 64 * 63 + .5);
     const int vars = ss * 64 - s1 * s1 - s2 * s2, covar = s12 * 64 - s1 * s2;
-    v = (float)(2 * s1 * s2 + c1) * (float)(2 * covar + c2) / ((float)(s1 * s1 + s2 * s2 + c1) * (float)(vars + c2));
+    out[i] = __fdiv_rn(__fmul_rn((float)(2 * s1 * s2 + c1), (float)(2 * covar + c2)),
+                       __fmul_rn((float)(s1 * s1 + s2 * s2 + c1), (float)(vars + c2)));
   }
-  double d = v;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) d += __shfl_down_sync(0xffffffffu, d, o);
-  if ((threadIdx.x & 31) == 0) atomicAdd(out, d);
 }
 
 // ================================================================================================
@@ -1766,13 +1939,8 @@ int launch_loopfilter(const DevJob* jobs, int njobs, const Geom& g, int* ticket,
   return (int)cudaGetLastError();
 }
 
-int launch_enc_motion(const EncJob* job, const Geom& g, void* stream) {
-  const int n_mbs = g.mb_cols * g.mb_rows;
-  k_enc_motion<<<(n_mbs + ENC_WARPS - 1) / ENC_WARPS, ENC_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(job, g);
-  return (int)cudaGetLastError();
-}
-int launch_enc_mb(const EncJob* job, const Geom& g, int* ticket, void* stream) {
-  k_enc_mb<<<(g.mb_rows + WF_WARPS - 1) / WF_WARPS, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream)>>>(job, g, ticket);
+int launch_enc_rd(const EncJob* job, int rows, const Geom& g, int* ticket, void* stream) {
+  k_enc_rd<<<(rows + WF_WARPS - 1) / WF_WARPS, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream)>>>(job, g, ticket);
   return (int)cudaGetLastError();
 }
 
@@ -1792,10 +1960,10 @@ int launch_hash(const uint8_t* a, const Geom& g, unsigned long long* d_out, void
   return (int)cudaGetLastError();
 }
 
-int launch_ssim(const uint8_t* a, const uint8_t* b, const Geom& g, double* d_sum, void* stream) {
+int launch_ssim(const uint8_t* a, const uint8_t* b, const Geom& g, float* d_windows, void* stream) {
   const int n = (g.W / 4 - 1) * (g.H / 4 - 1);
   if (n <= 0) return 0;
-  k_ssim<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(a, b, g, d_sum);
+  k_ssim<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(a, b, g, d_windows);
   return (int)cudaGetLastError();
 }
 

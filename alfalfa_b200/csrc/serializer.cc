@@ -340,6 +340,7 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
   struct PartWork {
     TokenRecorder rec;
     std::vector<uint32_t> cnt;
+    std::vector<uint32_t> ref_skip_eob;  // reference writer policy: end-of-block counts of skipped macroblocks
     std::vector<uint8_t> bytes;
   };
   std::vector<PartWork> work(nparts);
@@ -347,6 +348,7 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
     PartWork& W = work[p];
     W.rec.bits.reserve(n_mbs * 160 / nparts + 1024);
     W.cnt.assign(2 * (1056 + 256), 0);
+    W.ref_skip_eob.assign(1056, 0);
     int16_t c[25][16];  // coefficients of the current macroblock, raster order; all zero between macroblocks
     memset(c, 0, sizeof(c));
     for (int row = p; row < rows; row += nparts) {
@@ -356,6 +358,21 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
         const vp8gpu_mb& mb = mbs[idx];
         const bool has_y2 = mb.y_mode != VP8GPU_B_PRED && mb.y_mode != VP8GPU_SPLITMV;
         if (mb.tok_cnt == 0) {
+          if (x.ref_writer) {
+            // the reference counts the (immediate) end of block of every Y / U / V block of a skipped
+            // macroblock too (Macroblock::accumulate_token_branches runs for every macroblock)
+            unsigned a = above_ctx[idx], l = left;
+            auto eob = [&](int type, int bx, int by, int first) {
+              const int ctx = ((a >> bx) & 1) + ((l >> by) & 1);
+              W.ref_skip_eob[((type * 8 + kBand[first]) * 3 + ctx) * 11]++;
+              a &= ~(1u << bx);
+              l &= ~(1u << by);
+            };
+            const int ytype = has_y2 ? 0 : 3, yfirst = has_y2 ? 1 : 0;
+            for (int i = 0; i < 16; i++) eob(ytype, i & 3, i >> 2, yfirst);
+            for (int pl = 0; pl < 2; pl++)
+              for (int i = 0; i < 4; i++) eob(2, 4 + 2 * pl + (i & 1), 4 + 2 * pl + (i >> 1), 0);
+          }
           left = has_y2 ? 0 : (left & 0x100);
           continue;
         }
@@ -400,7 +417,36 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
   if (x.saved_coef_probs && h.key_frame) memcpy(x.saved_coef_probs, k_coef_default_probs, 1056);
   memcpy(coef_probs, x.saved_coef_probs ? x.saved_coef_probs : k_coef_default_probs, sizeof(coef_probs));
   std::vector<uint8_t> updated(1056, 0);
-  if (h.optimize_token_probs) {
+  auto calc_prob = [](uint64_t falses, uint64_t total) -> int {  // Encoder::calc_prob (encoder.cc:48-55)
+    if (falses == 0) return 0;
+    const uint64_t p = 256 * falses / total;
+    return static_cast<int>(p < 1 ? 1 : (p > 255 ? 255 : p));
+  };
+  if (x.ref_writer) {
+    EncodeFeatures::RefWriterState& st = *x.ref_writer;
+    if (!x.ref_estimate) {
+      // Encoder::optimize_probability_tables (encoder.cc:419-440) over the reference's branch counts
+      for (int i = 0; i < 1056; i++) {
+        if (i / 264 == 1) continue;  // Y2 blocks are never counted
+        uint64_t f = 0, t = 0;
+        for (const PartWork& W : work) {
+          f += W.cnt[2 * i];
+          t += W.cnt[2 * i + 1];
+          if (i % 11 == 0) f += W.ref_skip_eob[i];
+        }
+        const int p = calc_prob(f, f + t);
+        if (p > 0 && p != coef_probs[i]) {
+          st.upd_flag[i] = 1;
+          st.upd_val[i] = static_cast<uint8_t>(p);
+        }
+      }
+      for (int i = 0; i < 1056; i++)
+        if (st.upd_flag[i]) {
+          updated[i] = 1;
+          coef_probs[i] = st.upd_val[i];
+        }
+    }
+  } else if (h.optimize_token_probs) {
     std::vector<uint32_t> cnt(2 * 1056, 0);
     for (const PartWork& W : work)
       for (int i = 0; i < 2 * 1056; i++) cnt[i] += W.cnt[i];
@@ -419,6 +465,7 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
   }
   int skip_prob = static_cast<int>(((n_mbs - n_skipped) * 256 + n_mbs / 2) / n_mbs);  // P(not skipped)
   skip_prob = skip_prob < 1 ? 1 : (skip_prob > 255 ? 255 : skip_prob);
+  if (x.ref_writer) skip_prob = calc_prob(n_mbs - n_skipped, n_mbs);  // Encoder::optimize_prob_skip (encoder.cc:442-457)
   size_t n_inter = 0;
   for (size_t i = 0; i < n_mbs; i++) n_inter += mbs[i].ref_frame != VP8GPU_REF_CURRENT;
   int prob_inter = static_cast<int>(((n_mbs - n_inter) * 256 + n_mbs / 2) / n_mbs);  // P(intra) = P(bit 0)
@@ -433,8 +480,20 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
     const int p = static_cast<int>((zeros * 256 + total / 2) / total);
     return p < 1 ? 1 : (p > 255 ? 255 : p);
   };
-  const int prob_last = features ? prob_of(n_last, n_inter) : 255;
-  const int prob_golden = features ? prob_of(n_golden, n_inter - n_last) : 128;
+  int prob_last = features ? prob_of(n_last, n_inter) : 255;
+  int prob_golden = features ? prob_of(n_golden, n_inter - n_last) : 128;
+  if (x.ref_writer && !h.key_frame) {
+    // Encoder::optimize_interframe_probs (encode_inter.cc:527-576): a zero estimate leaves the header field alone
+    EncodeFeatures::RefWriterState& st = *x.ref_writer;
+    const size_t n_other = n_inter - n_last;
+    int p = calc_prob(n_mbs - n_inter, n_mbs);
+    if (p > 0) st.prob_inter = p;
+    p = calc_prob(n_last, n_inter);
+    if (p > 0) st.prob_last = p;
+    p = calc_prob(n_golden, n_other);
+    if (p > 0) st.prob_golden = p;
+    prob_inter = st.prob_inter, prob_last = st.prob_last, prob_golden = st.prob_golden;
+  }
   auto put_flagged_signed = [](BoolWriter& w, int v, int width) {  // frame_header.hh Flagged<Signed<width>>
     w.put(v != 0);
     if (v) {
@@ -491,12 +550,26 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
   bw.put(0);  // filter_type: normal
   bw.literal(h.loop_filter_level, 6);
   bw.literal(h.sharpness, 3);
-  bw.put(x.lf_delta_enabled);
-  if (x.lf_delta_enabled) {  // frame_header.hh:70-84
-    bw.put(x.lf_delta_update);
-    if (x.lf_delta_update) {
-      for (int i = 0; i < 4; i++) put_flagged_signed(bw, x.ref_lf_delta[i], 6);
-      for (int i = 0; i < 4; i++) put_flagged_signed(bw, x.mode_lf_delta[i], 6);
+  if (x.ref_writer && x.ref_estimate) {
+    bw.put(0);  // the sampled frame of a size estimate never gets loop-filter settings (size_estimation.cc)
+  } else if (x.ref_writer) {
+    // Encoder::apply_best_loopfilter_settings (encoder.cc:464-470): mode_lf_adjustments present, updated, all
+    // eight deltas flagged with the value 0
+    bw.put(1);
+    bw.put(1);
+    for (int i = 0; i < 8; i++) {
+      bw.put(1);
+      bw.literal(0, 6);
+      bw.put(0);
+    }
+  } else {
+    bw.put(x.lf_delta_enabled);
+    if (x.lf_delta_enabled) {  // frame_header.hh:70-84
+      bw.put(x.lf_delta_update);
+      if (x.lf_delta_update) {
+        for (int i = 0; i < 4; i++) put_flagged_signed(bw, x.ref_lf_delta[i], 6);
+        for (int i = 0; i < 4; i++) put_flagged_signed(bw, x.mode_lf_delta[i], 6);
+      }
     }
   }
   bw.literal(x.log2_partitions, 2);
@@ -667,6 +740,11 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
         else if (vx == nearest.x && vy == nearest.y) mode = VP8GPU_NEARESTMV;
         else if (vx == near.x && vy == near.y) mode = VP8GPU_NEARMV;
         else mode = VP8GPU_NEWMV;
+        // the record's own label wins when it decodes to the same vector (an encoder may have chosen NEARMV or
+        // NEWMV where a cheaper label exists; a parsed stream is re-written the way it was written)
+        if (mb.y_mode == VP8GPU_NEWMV || (mb.y_mode == VP8GPU_NEARMV && vx == near.x && vy == near.y) ||
+            (mb.y_mode == VP8GPU_NEARESTMV && vx == nearest.x && vy == nearest.y) || (mb.y_mode == VP8GPU_ZEROMV && (vx | vy) == 0))
+          mode = mb.y_mode;
         me.y_mode = static_cast<uint8_t>(mode);
         write_path(bw, kMvRefPaths, ref_probs, mode);
         if (mode == VP8GPU_NEWMV) {

@@ -48,6 +48,21 @@ struct EncodeFeatures {
   // updates and written back when refresh_entropy_probs is set (key frames reset it to the defaults
   // first); nullptr = stateless writer, every frame relative to the default tables
   uint8_t* saved_coef_probs = nullptr;
+  // Reference-encoder writer policy (encoder/encoder.cc:419-457, encode_inter.cc:527-576): what the reference's
+  // Encoder puts into a header is decided by its own rules, not by what is cheapest -- every token probability whose
+  // estimate calc_prob( falses, total ) differs from the current one is sent (counted over the Y / U / V blocks of ALL
+  // macroblocks, skipped ones included, Y2 blocks never: serializer.cc:456-587), flags set in an earlier frame stay set
+  // in the Encoder's frame object, prob_skip / prob_inter / prob_references_last are calc_prob values that may be 0
+  // or left over from the previous frame, and a block of explicit zero loop-filter deltas is written
+  // (encoder.cc:464-470).  With ref_writer set the frame is written by exactly those rules, which makes the
+  // device encoder's output byte-identical to the reference encoder's; the struct is the state of the
+  // reference's per-type frame object and must persist between frames of one encoder.
+  struct RefWriterState {
+    uint8_t upd_flag[1056] = {0}, upd_val[1056] = {0};  // token_prob_update as left by earlier frames
+    int prob_inter = 0, prob_last = 0, prob_golden = 0; // InterFrameHeader fields start at 0 (zero_decoder) and persist
+  };
+  RefWriterState* ref_writer = nullptr;
+  bool ref_estimate = false;  // with ref_writer: a size estimate (size_estimation.cc): no token-probability updates
 };
 
 // RFC 6386 section 7 arithmetic encoder (same code stream as encoder/bool_encoder.hh)

@@ -366,14 +366,45 @@ def decode_ivf(ctx, ivf_bytes, threads=1, want_output=True):
 
 
 class Encoder:
-    """Encoder (encoder/encoder.hh:345-382), first slice: encode_with_quantizer / encode_with_target_size.
-    Source frames are display-size (Y, U, V) numpy planes; the result is one compressed VP8 frame."""
+    """Encoder (encoder/encoder.hh:345-382): a copyable value like the reference's.  Source frames are
+    display-size (Y, U, V) numpy planes; the result is one compressed VP8 frame."""
 
-    def __init__(self, ctx):
+    def __init__(self, ctx, _h=None):
         self.ctx, self.L = ctx, ctx.L
         self.h = C.c_void_p()
-        check(self.L.vp8gpu_encoder_create(ctx.h, C.byref(self.h)), ctx.h, "encoder_create")
+        if _h is not None:
+            self.h = _h
+        else:
+            check(self.L.vp8gpu_encoder_create(ctx.h, C.byref(self.h)), ctx.h, "encoder_create")
         self._out = np.empty(ctx.width * ctx.height * 3 + (1 << 16), np.uint8)
+
+    def copy(self):
+        """Encoder( const Encoder & ) (encoder.cc:92-102): O(1) in pixels, shares the reference rasters"""
+        h = C.c_void_p()
+        check(self.L.vp8gpu_encoder_clone(self.h, C.byref(h)), self.ctx.h, "encoder_clone")
+        return Encoder(self.ctx, _h=h)
+
+    @staticmethod
+    def from_decoder(ctx, decoder):
+        """Encoder( const Decoder &, two_pass, quality ) (encoder.hh:350-351)"""
+        h = C.c_void_p()
+        check(ctx.L.vp8gpu_encoder_create_from_decoder(ctx.h, decoder.h, C.byref(h)), ctx.h, "encoder_create_from_decoder")
+        return Encoder(ctx, _h=h)
+
+    def export_decoder(self):
+        """Encoder::export_decoder (encoder.hh:378)"""
+        h = C.c_void_p()
+        check(self.L.vp8gpu_encoder_export_decoder(self.h, C.byref(h)), self.ctx.h, "encoder_export_decoder")
+        return Decoder(self.ctx, _h=h)
+
+    def set_writer(self, mode):
+        """0: bitstream byte-identical to the reference encoder's (default); 1: compact writer, 8 partitions"""
+        check(self.L.vp8gpu_encoder_set_writer(self.h, int(mode)), self.ctx.h, "encoder_set_writer")
+
+    def minihash(self):
+        out = C.c_uint32(0)
+        check(self.L.vp8gpu_encoder_minihash(self.h, C.byref(out)), self.ctx.h, "encoder_minihash")
+        return out.value
 
     def __del__(self):
         try:

@@ -358,6 +358,23 @@ int vp8gpu_serialize_frame_ex(const vp8gpu_encode_header* hdr, const vp8gpu_enco
 typedef struct vp8gpu_encoder vp8gpu_encoder;
 int vp8gpu_encoder_create(vp8gpu_ctx* ctx, vp8gpu_encoder** out);
 void vp8gpu_encoder_destroy(vp8gpu_encoder* enc);
+/* Encoder( const Encoder & ) (encoder/encoder.cc:92-102): an independent copy that shares the (immutable,
+ * reference-counted) reference rasters; Salsify copies its encoder twice per frame and encodes on both
+ * copies concurrently (salsify/salsify-sender.cc:492-518). */
+int vp8gpu_encoder_clone(const vp8gpu_encoder* src, vp8gpu_encoder** out);
+/* Encoder( const Decoder &, two_pass, quality ) (encoder/encoder.hh:350-351): continue a stream from a
+ * decoder's state and references; the next frame is an inter frame. */
+int vp8gpu_encoder_create_from_decoder(vp8gpu_ctx* ctx, vp8gpu_decoder* dec, vp8gpu_encoder** out);
+/* Encoder::export_decoder (encoder/encoder.hh:378): a new Decoder in the state a receiver is in after the
+ * frames emitted so far (DecoderState + the three references, shared); the caller destroys it. */
+int vp8gpu_encoder_export_decoder(vp8gpu_encoder* enc, vp8gpu_decoder** out);
+/* Encoder::minihash (encoder/encoder.hh:382) = export_decoder().minihash() */
+int vp8gpu_encoder_minihash(vp8gpu_encoder* enc, uint32_t* out);
+/* Which bitstream writer the encoder uses.  0 (default): the reference Encoder's own header rules (every
+ * changed token probability is sent, explicit zero loop-filter deltas, one DCT partition): the emitted frames
+ * are byte-identical to the reference encoder's.  1: compact -- only the probability updates that pay, eight
+ * DCT partitions written on eight host threads (same decisions and reconstruction, fewer bytes, faster). */
+int vp8gpu_encoder_set_writer(vp8gpu_encoder* enc, int mode);
 /* Encoder::encode_with_quantizer (encoder.cc:559-590) */
 int vp8gpu_encoder_encode_with_quantizer(vp8gpu_encoder* enc, const uint8_t* y, size_t y_stride, const uint8_t* u,
                                          const uint8_t* v, size_t uv_stride, int y_ac_qi, uint8_t* out, size_t cap,
@@ -373,8 +390,9 @@ int vp8gpu_encoder_encode_with_minimum_ssim(vp8gpu_encoder* enc, const uint8_t* 
                                             const uint8_t* v, size_t uv_stride, double minimum_ssim, uint8_t* out,
                                             size_t cap, size_t* size, int* chosen_qi);
 /* Encoder::estimate_frame_size (encoder.hh:376, size_estimation.cc): the size in bytes the frame would
- * have at quantiser index y_ac_qi.  The reference estimates it from a 1/16 sample of the macroblocks;
- * here it is the exact size of a full device pass.  Does not change the encoder's state. */
+ * have at quantiser index y_ac_qi, estimated like the reference does: every fourth macroblock column and
+ * row is coded as a (width / 4) x (height / 4) frame with the current probability tables and its size
+ * multiplied by 16 (size_estimation.cc:36-181).  Does not change the encoder's state. */
 int vp8gpu_encoder_estimate_frame_size(vp8gpu_encoder* enc, const uint8_t* y, size_t y_stride, const uint8_t* u,
                                        const uint8_t* v, size_t uv_stride, int y_ac_qi, size_t* size);
 /* EncoderStats (encoder.hh:118-127) of the last frame; any pointer may be NULL. */
