@@ -124,6 +124,8 @@ SYMBOLS = {
     "vp8gpu_parsed_tokens": (_vp, [_vp]),
     "vp8gpu_parsed_split": (_vp, [_vp]),
     "vp8gpu_parse_frame": (C.c_int, [_vp, C.c_char_p, C.c_size_t, _vp]),
+    "vp8gpu_parsed_keep_labels": (C.c_int, [_vp, C.c_int]),
+    "vp8gpu_parsed_serialize": (C.c_int, [_vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "vp8gpu_parse_frame_device": (C.c_int, [_vp, _vp, C.c_char_p, C.c_size_t, _vp]),
     "vp8gpu_ctx_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),
     "vp8gpu_decoder_set_device_tokens": (C.c_int, [_vp, C.c_int]),

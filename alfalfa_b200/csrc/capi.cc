@@ -394,6 +394,22 @@ int vp8gpu_parse_frame(vp8gpu_state* state, const uint8_t* data, size_t len, vp8
   return rc;
 }
 
+int vp8gpu_parsed_keep_labels(vp8gpu_parsed* p, int on) {
+  if (!p) return VP8GPU_ERR_LOGIC;
+  p->f.keep_verbatim = on != 0;
+  return VP8GPU_OK;
+}
+int vp8gpu_parsed_serialize(const vp8gpu_parsed* p, uint8_t* out, size_t cap, size_t* size) {
+  if (!p || !size) return VP8GPU_ERR_LOGIC;
+  if (!p->f.keep_verbatim || p->f.verbatim.header_tape.empty()) return VP8GPU_ERR_LOGIC;
+  const std::vector<uint8_t> bytes = vp8::serialize_parsed(p->f);
+  if (bytes.empty()) return VP8GPU_ERR_UNSUPPORTED;
+  *size = bytes.size();
+  if (!out || cap < bytes.size()) return VP8GPU_ERR_NOMEM;
+  memcpy(out, bytes.data(), bytes.size());
+  return VP8GPU_OK;
+}
+
 int vp8gpu_ctx_set_option(vp8gpu_ctx* ctx, int option, int value) {
   if (!ctx) return VP8GPU_ERR_LOGIC;
   if (option == VP8GPU_OPT_DEVICE_TOKENS) {

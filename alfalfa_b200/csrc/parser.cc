@@ -299,8 +299,32 @@ struct FrameHeader {
   int skip_prob = 0, prob_inter = 0, prob_last = 0, prob_golden = 0;
 };
 
+// A view of the first partition's reader that also writes every decision to a tape (Verbatim::header_tape);
+// the header readers below are templates so that the plain path pays nothing for it.
+struct TapedReader {
+  BoolReader& r;
+  std::vector<uint16_t>& tape;
+  inline int get(uint32_t prob) {
+    const int b = r.get(prob);
+    tape.push_back(static_cast<uint16_t>((prob << 1) | static_cast<uint32_t>(b)));
+    return b;
+  }
+  inline int bit() { return get(128); }
+  inline int literal(int width) {
+    int v = 0;
+    for (int i = 0; i < width; i++) v = (v << 1) | get(128);
+    return v;
+  }
+  inline int signed_literal(int width) {
+    const int v = literal(width);
+    return get(128) ? -v : v;
+  }
+  inline int flagged_signed(int width) { return get(128) ? signed_literal(width) : 0; }
+};
+
 // the part of the frame header shared by key and inter frames (frame_header.hh:104-131, :70-84, :37-66)
-void read_common_header(BoolReader& br, FrameHeader& h) {
+template <class Reader>
+void read_common_header(Reader& br, FrameHeader& h) {
   h.seg_enabled = br.bit();
   if (h.seg_enabled) {
     h.seg_update_map = br.bit();
@@ -333,7 +357,8 @@ void read_common_header(BoolReader& br, FrameHeader& h) {
   h.uv_ac = br.flagged_signed(4);
 }
 
-void read_coef_updates(BoolReader& br, uint8_t* probs) {
+template <class Reader>
+void read_coef_updates(Reader& br, uint8_t* probs) {
   for (int i = 0; i < 1056; i++)
     if (br.get(k_coef_update_probs[i])) probs[i] = static_cast<uint8_t>(br.literal(8));
 }
@@ -490,6 +515,59 @@ inline int parse_block(BoolReader& br, const uint8_t* tp, int ctx, int i, uint32
 // ------------------------------------------------------------------------------------------
 // parse_frame
 // ------------------------------------------------------------------------------------------
+// the whole frame header (frame_header.hh:213-325) and the frame's probability tables: a key frame starts
+// from the defaults (decoder_state.hh:90, decoder.cc:236-243), an inter frame from the saved ones.  Returns
+// color_space | clamping_type of a key frame.
+template <class Reader>
+bool read_frame_header(Reader& br, FrameHeader& h, const State& state, uint8_t* frame_coef, uint8_t* frame_ymode,
+                       uint8_t* frame_uvmode, uint8_t (*frame_mv)[19]) {
+  bool color_or_clamp = false;
+  if (h.key) {
+    color_or_clamp = br.bit() | br.bit();
+    read_common_header(br, h);
+    h.refresh_entropy = br.bit();
+    // a key frame starts from default probabilities (decoder_state.hh:90, decoder.cc:236-243)
+    memcpy(frame_coef, k_coef_default_probs, 1056);
+    memcpy(frame_ymode, k_ymode_default_probs, 4);
+    memcpy(frame_uvmode, k_uvmode_default_probs, 3);
+    memcpy(frame_mv, k_mv_default_probs, 38);
+    read_coef_updates(br, frame_coef);
+    h.has_skip_prob = br.bit();
+    if (h.has_skip_prob) h.skip_prob = br.literal(8);
+  } else {
+    read_common_header(br, h);
+    h.refresh_golden = br.bit();
+    h.refresh_alt = br.bit();
+    h.copy_golden = h.refresh_golden ? 0 : br.literal(2);
+    h.copy_alt = h.refresh_alt ? 0 : br.literal(2);
+    h.sign_golden = br.bit();
+    h.sign_alt = br.bit();
+    h.refresh_entropy = br.bit();
+    h.refresh_last = br.bit();
+    memcpy(frame_coef, state.coef_probs, 1056);
+    memcpy(frame_ymode, state.ymode_probs, 4);
+    memcpy(frame_uvmode, state.uvmode_probs, 3);
+    memcpy(frame_mv, state.mv_probs, 38);
+    read_coef_updates(br, frame_coef);
+    h.has_skip_prob = br.bit();
+    if (h.has_skip_prob) h.skip_prob = br.literal(8);
+    h.prob_inter = br.literal(8);
+    h.prob_last = br.literal(8);
+    h.prob_golden = br.literal(8);
+    if (br.bit())
+      for (int i = 0; i < 4; i++) frame_ymode[i] = static_cast<uint8_t>(br.literal(8));
+    if (br.bit())
+      for (int i = 0; i < 3; i++) frame_uvmode[i] = static_cast<uint8_t>(br.literal(8));
+    for (int i = 0; i < 2; i++)
+      for (int j = 0; j < 19; j++)
+        if (br.get(k_mv_update_probs[i * 19 + j])) {
+          const int x = br.literal(7);
+          frame_mv[i][j] = static_cast<uint8_t>(x ? x << 1 : 1);
+        }
+  }
+  return color_or_clamp;
+}
+
 int parse_frame(State& state, const uint8_t* data, size_t len, ParsedFrame& out, bool defer_tokens) {
   // ---- frame tag and partition layout (uncompressed_chunk.cc:34-130) ----
   if (len < 3) return VP8GPU_ERR_INVALID;
@@ -517,48 +595,13 @@ int parse_frame(State& state, const uint8_t* data, size_t len, ParsedFrame& out,
   //      header (including the partition table) has been validated ----
   uint8_t frame_coef[1056], frame_ymode[4], frame_uvmode[3], frame_mv[2][19];
   bool color_or_clamp = false;
-  if (h.key) {
-    color_or_clamp = br.bit() | br.bit();
-    read_common_header(br, h);
-    h.refresh_entropy = br.bit();
-    // a key frame starts from default probabilities (decoder_state.hh:90, decoder.cc:236-243)
-    memcpy(frame_coef, k_coef_default_probs, sizeof(frame_coef));
-    memcpy(frame_ymode, k_ymode_default_probs, 4);
-    memcpy(frame_uvmode, k_uvmode_default_probs, 3);
-    memcpy(frame_mv, k_mv_default_probs, sizeof(frame_mv));
-    read_coef_updates(br, frame_coef);
-    h.has_skip_prob = br.bit();
-    if (h.has_skip_prob) h.skip_prob = br.literal(8);
+  if (out.keep_verbatim) {
+    if (defer_tokens) return VP8GPU_ERR_LOGIC;
+    out.verbatim.header_tape.clear();
+    TapedReader taped{br, out.verbatim.header_tape};
+    color_or_clamp = read_frame_header(taped, h, state, frame_coef, frame_ymode, frame_uvmode, frame_mv);
   } else {
-    read_common_header(br, h);
-    h.refresh_golden = br.bit();
-    h.refresh_alt = br.bit();
-    h.copy_golden = h.refresh_golden ? 0 : br.literal(2);
-    h.copy_alt = h.refresh_alt ? 0 : br.literal(2);
-    h.sign_golden = br.bit();
-    h.sign_alt = br.bit();
-    h.refresh_entropy = br.bit();
-    h.refresh_last = br.bit();
-    memcpy(frame_coef, state.coef_probs, sizeof(frame_coef));
-    memcpy(frame_ymode, state.ymode_probs, 4);
-    memcpy(frame_uvmode, state.uvmode_probs, 3);
-    memcpy(frame_mv, state.mv_probs, sizeof(frame_mv));
-    read_coef_updates(br, frame_coef);
-    h.has_skip_prob = br.bit();
-    if (h.has_skip_prob) h.skip_prob = br.literal(8);
-    h.prob_inter = br.literal(8);
-    h.prob_last = br.literal(8);
-    h.prob_golden = br.literal(8);
-    if (br.bit())
-      for (int i = 0; i < 4; i++) frame_ymode[i] = static_cast<uint8_t>(br.literal(8));
-    if (br.bit())
-      for (int i = 0; i < 3; i++) frame_uvmode[i] = static_cast<uint8_t>(br.literal(8));
-    for (int i = 0; i < 2; i++)
-      for (int j = 0; j < 19; j++)
-        if (br.get(k_mv_update_probs[i * 19 + j])) {
-          const int x = br.literal(7);
-          frame_mv[i][j] = static_cast<uint8_t>(x ? x << 1 : 1);
-        }
+    color_or_clamp = read_frame_header(br, h, state, frame_coef, frame_ymode, frame_uvmode, frame_mv);
   }
   if (color_or_clamp || h.filter_type) return VP8GPU_ERR_UNSUPPORTED;  // frame_header.hh:221-227,292-294
 
@@ -698,6 +741,22 @@ int parse_frame(State& state, const uint8_t* data, size_t len, ParsedFrame& out,
   const uint8_t* const coef_y_full = frame_coef + 3 * 264;
   const bool read_segment = h.seg_enabled && h.seg_update_map;
   const uint8_t(*mv_probs)[19] = frame_mv;
+  Verbatim* const vb = out.keep_verbatim ? &out.verbatim : nullptr;
+  if (vb) {
+    vb->key = h.key, vb->show = h.show;
+    vb->width = state.width, vb->height = state.height, vb->log2_parts = h.log2_parts;
+    vb->has_skip_prob = h.has_skip_prob, vb->read_segment = read_segment;
+    vb->sign_golden = h.sign_golden, vb->sign_alt = h.sign_alt;
+    vb->skip_prob = static_cast<uint8_t>(h.skip_prob), vb->prob_inter = static_cast<uint8_t>(h.prob_inter);
+    vb->prob_last = static_cast<uint8_t>(h.prob_last), vb->prob_golden = static_cast<uint8_t>(h.prob_golden);
+    memcpy(vb->seg_tree_probs, h.seg_tree_probs, 3);
+    memcpy(vb->coef, frame_coef, 1056);
+    memcpy(vb->ymode, frame_ymode, 4);
+    memcpy(vb->uvmode, frame_uvmode, 3);
+    memcpy(vb->mv, frame_mv, 38);
+    vb->mb_coded.assign(n_mbs, 0);
+    vb->sub_labels.clear();
+  }
 
   for (int row = 0; row < rows; row++) {
     Neighbour left, above_left;  // outside the frame: not inter, B_DC_PRED, zero vectors
@@ -786,6 +845,7 @@ int parse_frame(State& state, const uint8_t* data, size_t len, ParsedFrame& out,
         } else if (y_mode == VP8GPU_SPLITMV) {
           const int layout = br.tree(kSplitTree, k_split_probs);
           const Mv best = clamp_mv(census.mv[0], bounds);
+          uint32_t labels = 0;
           for (int part = 0; part < kSplitCount[layout]; part++) {
             const unsigned members = kSplitFill[layout][part];
             const int first = __builtin_ctz(members);
@@ -800,7 +860,9 @@ int parse_frame(State& state, const uint8_t* data, size_t len, ParsedFrame& out,
             else if (above_zero) ctx = 2;
             else if (left_zero) ctx = 1;
             int sx = 0, sy = 0;
-            switch (br.tree(kSubMvTree, k_submv_ref_probs + ctx * 3)) {
+            const int label = br.tree(kSubMvTree, k_submv_ref_probs + ctx * 3);
+            labels |= static_cast<uint32_t>(label) << (2 * part);
+            switch (label) {
               case kSubLeft: sx = lx, sy = ly; break;
               case kSubAbove: sx = ax, sy = ay; break;
               case kSubZero: break;
@@ -821,6 +883,10 @@ int parse_frame(State& state, const uint8_t* data, size_t len, ParsedFrame& out,
           if (!out.split.reserve(n_split + 1, n_split)) return VP8GPU_ERR_NOMEM;
           memcpy(out.split.data()[n_split].mv, mv, sizeof(mv));
           split_idx = n_split++;
+          if (vb) {
+            vb->sub_labels.push_back(labels);
+            vb->mb_coded[idx] |= static_cast<uint8_t>(layout << 1);
+          }
         }
         if (y_mode != VP8GPU_SPLITMV)
           for (int i = 0; i < 16; i++) {
@@ -829,6 +895,7 @@ int parse_frame(State& state, const uint8_t* data, size_t len, ParsedFrame& out,
           }
       }
       const bool has_y2 = y_mode != VP8GPU_B_PRED && y_mode != VP8GPU_SPLITMV;
+      if (vb) vb->mb_coded[idx] |= static_cast<uint8_t>(skip);
 
       // -- loop-filter level of this macroblock: frame.cc:150-166, loopfilter.cc:57-79,
       //    macroblock.cc:621, and the single clamp of loopfilter.cc:85 --

@@ -79,6 +79,25 @@ struct TokenWork {
   uint8_t coef_probs[1056];                       // the frame's probabilities (after header updates)
 };
 
+// What the reference's Frame object keeps beyond decoded values, and Frame::serialize
+// (encoder/serializer.cc:388-405) therefore writes back unchanged: the header exactly as coded (a
+// Flagged<Signed<n>> field distinguishes "absent" from a flagged +0 / -0, frame_header.hh:37-131) and every
+// label whose decoded meaning is ambiguous (mb_skip_coeff of a macroblock without coefficients, the
+// SPLITMV layout and LEFT4x4 / ABOVE4x4 / ZERO4x4 / NEW4x4 of each partition).  Filled by parse_frame when
+// ParsedFrame::keep_verbatim is set; consumed by serialize_parsed (serializer.h), which reproduces
+// the input frame byte for byte (the reference's gate: src/tests/roundtrip.cc:93-112).
+struct Verbatim {
+  std::vector<uint16_t> header_tape;  // every frame-header decision, in order: (probability << 1) | bit
+  bool key = false, show = false;
+  int width = 0, height = 0, log2_parts = 0;
+  bool has_skip_prob = false, read_segment = false, sign_golden = false, sign_alt = false;
+  uint8_t skip_prob = 0, prob_inter = 0, prob_last = 0, prob_golden = 0;
+  uint8_t seg_tree_probs[3] = {255, 255, 255};
+  uint8_t coef[1056], ymode[4], uvmode[3], mv[2][19];  // the frame's probability tables (after the header's updates)
+  std::vector<uint8_t> mb_coded;     // per macroblock: bit 0 = mb_skip_coeff as coded, bits 1-2 = SPLITMV layout
+  std::vector<uint32_t> sub_labels;  // per SPLITMV macroblock (split_idx): 2 bits per partition, coding order
+};
+
 // KeyFrame / InterFrame (decoder/frame.hh:126-127) in flat form.
 struct ParsedFrame {
   explicit ParsedFrame(const Allocator& a = kMallocAllocator) : mbs(a), tokens(a), split(a) {}
@@ -87,6 +106,8 @@ struct ParsedFrame {
   Buffer<vp8gpu_token> tokens;
   Buffer<vp8gpu_split_mvs> split;
   TokenWork tw;
+  bool keep_verbatim = false;  // ask parse_frame to fill `verbatim` (not compatible with defer_tokens)
+  Verbatim verbatim;
 };
 
 // Parse one compressed frame and apply it to `state`.  Returns VP8GPU_OK or VP8GPU_ERR_*;

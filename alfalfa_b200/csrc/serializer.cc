@@ -295,6 +295,7 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
   const EncodeFeatures& x = features ? *features : kPlain;
   if (x.log2_partitions < 0 || x.log2_partitions > 3) return {};
   const int nparts = 1 << x.log2_partitions;
+  const Verbatim* const vb = x.verbatim;  // re-serialisation of a parsed frame: header and labels as coded
   const int cols = (h.width + 15) / 16, rows = (h.height + 15) / 16;
   const size_t n_mbs = static_cast<size_t>(cols) * rows;
   std::vector<MbInfo> info(n_mbs);
@@ -321,7 +322,11 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
       nzmask[idx] = m;
       uint16_t& a = above[idx % cols];
       above_ctx[idx] = a;
-      if (mb.tok_cnt == 0) {
+      // mb_skip_coeff: the encoder path skips exactly the macroblocks without coefficients; a parsed frame
+      // keeps the flag it was coded with (a macroblock may spell out 25 empty blocks instead)
+      const bool coded_skip = vb ? (vb->has_skip_prob && (vb->mb_coded[idx] & 1)) : mb.tok_cnt == 0;
+      if (coded_skip) {
+        if (mb.tok_cnt) return {};
         skip[idx] = 1;
         n_skipped++;
         a = has_y2 ? 0 : static_cast<uint16_t>(a & 0x100);
@@ -357,7 +362,7 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
         const size_t idx = static_cast<size_t>(row) * cols + col;
         const vp8gpu_mb& mb = mbs[idx];
         const bool has_y2 = mb.y_mode != VP8GPU_B_PRED && mb.y_mode != VP8GPU_SPLITMV;
-        if (mb.tok_cnt == 0) {
+        if (skip[idx]) {
           if (x.ref_writer) {
             // the reference counts the (immediate) end of block of every Y / U / V block of a skipped
             // macroblock too (Macroblock::accumulate_token_branches runs for every macroblock)
@@ -416,13 +421,16 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
   uint8_t coef_probs[1056];
   if (x.saved_coef_probs && h.key_frame) memcpy(x.saved_coef_probs, k_coef_default_probs, 1056);
   memcpy(coef_probs, x.saved_coef_probs ? x.saved_coef_probs : k_coef_default_probs, sizeof(coef_probs));
+  if (vb) memcpy(coef_probs, vb->coef, sizeof(coef_probs));
   std::vector<uint8_t> updated(1056, 0);
   auto calc_prob = [](uint64_t falses, uint64_t total) -> int {  // Encoder::calc_prob (encoder.cc:48-55)
     if (falses == 0) return 0;
     const uint64_t p = 256 * falses / total;
     return static_cast<int>(p < 1 ? 1 : (p > 255 ? 255 : p));
   };
-  if (x.ref_writer) {
+  if (vb) {
+    // nothing to choose: the header is replayed
+  } else if (x.ref_writer) {
     EncodeFeatures::RefWriterState& st = *x.ref_writer;
     if (!x.ref_estimate) {
       // Encoder::optimize_probability_tables (encoder.cc:419-440) over the reference's branch counts
@@ -494,6 +502,7 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
     if (p > 0) st.prob_golden = p;
     prob_inter = st.prob_inter, prob_last = st.prob_last, prob_golden = st.prob_golden;
   }
+  if (vb) skip_prob = vb->skip_prob, prob_inter = vb->prob_inter, prob_last = vb->prob_last, prob_golden = vb->prob_golden;
   auto put_flagged_signed = [](BoolWriter& w, int v, int width) {  // frame_header.hh Flagged<Signed<width>>
     w.put(v != 0);
     if (v) {
@@ -528,90 +537,97 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
 
   // ---- first partition: frame header ----
   BoolWriter bw;
-  if (h.key_frame) {
-    bw.put(0);  // color_space
-    bw.put(0);  // clamping_type
-  }
-  bw.put(x.segmentation_enabled);
-  if (x.segmentation_enabled) {  // frame_header.hh:37-66
-    bw.put(x.update_mb_segmentation_map);
-    bw.put(x.update_segment_feature_data);
-    if (x.update_segment_feature_data) {
-      bw.put(x.segment_feature_absolute);
-      for (int i = 0; i < 4; i++) put_flagged_signed(bw, x.segment_quant[i], 7);
-      for (int i = 0; i < 4; i++) put_flagged_signed(bw, x.segment_lf[i], 6);
+  if (vb) {
+    for (const uint16_t d : vb->header_tape) bw.put(d & 1, d >> 1);
+  } else {
+    if (h.key_frame) {
+      bw.put(0);  // color_space
+      bw.put(0);  // clamping_type
     }
-    if (x.update_mb_segmentation_map)
-      for (int i = 0; i < 3; i++) {
-        bw.put(x.segment_tree_probs[i] != 255);
-        if (x.segment_tree_probs[i] != 255) bw.literal(x.segment_tree_probs[i], 8);
+    bw.put(x.segmentation_enabled);
+    if (x.segmentation_enabled) {  // frame_header.hh:37-66
+      bw.put(x.update_mb_segmentation_map);
+      bw.put(x.update_segment_feature_data);
+      if (x.update_segment_feature_data) {
+        bw.put(x.segment_feature_absolute);
+        for (int i = 0; i < 4; i++) put_flagged_signed(bw, x.segment_quant[i], 7);
+        for (int i = 0; i < 4; i++) put_flagged_signed(bw, x.segment_lf[i], 6);
       }
-  }
-  bw.put(0);  // filter_type: normal
-  bw.literal(h.loop_filter_level, 6);
-  bw.literal(h.sharpness, 3);
-  if (x.ref_writer && x.ref_estimate) {
-    bw.put(0);  // the sampled frame of a size estimate never gets loop-filter settings (size_estimation.cc)
-  } else if (x.ref_writer) {
-    // Encoder::apply_best_loopfilter_settings (encoder.cc:464-470): mode_lf_adjustments present, updated, all
-    // eight deltas flagged with the value 0
-    bw.put(1);
-    bw.put(1);
-    for (int i = 0; i < 8; i++) {
+      if (x.update_mb_segmentation_map)
+        for (int i = 0; i < 3; i++) {
+          bw.put(x.segment_tree_probs[i] != 255);
+          if (x.segment_tree_probs[i] != 255) bw.literal(x.segment_tree_probs[i], 8);
+        }
+    }
+    bw.put(0);  // filter_type: normal
+    bw.literal(h.loop_filter_level, 6);
+    bw.literal(h.sharpness, 3);
+    if (x.ref_writer && x.ref_estimate) {
+      bw.put(0);  // the sampled frame of a size estimate never gets loop-filter settings (size_estimation.cc)
+    } else if (x.ref_writer) {
+      // Encoder::apply_best_loopfilter_settings (encoder.cc:464-470): mode_lf_adjustments present, updated, all
+      // eight deltas flagged with the value 0
       bw.put(1);
-      bw.literal(0, 6);
-      bw.put(0);
-    }
-  } else {
-    bw.put(x.lf_delta_enabled);
-    if (x.lf_delta_enabled) {  // frame_header.hh:70-84
-      bw.put(x.lf_delta_update);
-      if (x.lf_delta_update) {
-        for (int i = 0; i < 4; i++) put_flagged_signed(bw, x.ref_lf_delta[i], 6);
-        for (int i = 0; i < 4; i++) put_flagged_signed(bw, x.mode_lf_delta[i], 6);
+      bw.put(1);
+      for (int i = 0; i < 8; i++) {
+        bw.put(1);
+        bw.literal(0, 6);
+        bw.put(0);
+      }
+    } else {
+      bw.put(x.lf_delta_enabled);
+      if (x.lf_delta_enabled) {  // frame_header.hh:70-84
+        bw.put(x.lf_delta_update);
+        if (x.lf_delta_update) {
+          for (int i = 0; i < 4; i++) put_flagged_signed(bw, x.ref_lf_delta[i], 6);
+          for (int i = 0; i < 4; i++) put_flagged_signed(bw, x.mode_lf_delta[i], 6);
+        }
       }
     }
+    bw.literal(x.log2_partitions, 2);
+    bw.literal(h.y_ac_qi, 7);
+    put_flagged_signed(bw, x.y_dc_delta, 4);
+    put_flagged_signed(bw, x.y2_dc_delta, 4);
+    put_flagged_signed(bw, x.y2_ac_delta, 4);
+    put_flagged_signed(bw, x.uv_dc_delta, 4);
+    put_flagged_signed(bw, x.uv_ac_delta, 4);
+    // Without a saved table (stateless writer) refresh_entropy_probs = 0 whenever probabilities are
+    // updated: the updates are then valid for this frame only and every frame is coded relative to
+    // the default tables.
+    const int refresh_entropy =
+        x.saved_coef_probs ? x.refresh_entropy_probs : (features ? 0 : (h.optimize_token_probs ? 0 : 1));
+    if (h.key_frame) {
+      bw.put(refresh_entropy);
+    } else {
+      bw.put(x.refresh_golden);
+      bw.put(x.refresh_alternate);
+      if (!x.refresh_golden) bw.literal(x.copy_to_golden, 2);
+      if (!x.refresh_alternate) bw.literal(x.copy_to_alternate, 2);
+      bw.put(x.sign_bias_golden);
+      bw.put(x.sign_bias_alternate);
+      bw.put(refresh_entropy);
+      bw.put(features ? x.refresh_last : 1);
+    }
+    if (x.saved_coef_probs && refresh_entropy) memcpy(x.saved_coef_probs, coef_probs, 1056);
+    for (int i = 0; i < 1056; i++) {
+      bw.put(updated[i], k_coef_update_probs[i]);
+      if (updated[i]) bw.literal(coef_probs[i], 8);
+    }
+    bw.put(1);  // mb_no_coeff_skip
+    bw.literal(skip_prob, 8);
+    if (!h.key_frame) {
+      bw.literal(prob_inter, 8);
+      bw.literal(prob_last, 8);
+      bw.literal(prob_golden, 8);
+      bw.put(0);           // intra_16x16_prob unchanged
+      bw.put(0);           // intra_chroma_prob unchanged
+      for (int i = 0; i < 38; i++) bw.put(0, k_mv_update_probs[i]);  // motion vector probabilities unchanged
+    }
   }
-  bw.literal(x.log2_partitions, 2);
-  bw.literal(h.y_ac_qi, 7);
-  put_flagged_signed(bw, x.y_dc_delta, 4);
-  put_flagged_signed(bw, x.y2_dc_delta, 4);
-  put_flagged_signed(bw, x.y2_ac_delta, 4);
-  put_flagged_signed(bw, x.uv_dc_delta, 4);
-  put_flagged_signed(bw, x.uv_ac_delta, 4);
-  // Without a saved table (stateless writer) refresh_entropy_probs = 0 whenever probabilities are
-  // updated: the updates are then valid for this frame only and every frame is coded relative to
-  // the default tables.
-  const int refresh_entropy =
-      x.saved_coef_probs ? x.refresh_entropy_probs : (features ? 0 : (h.optimize_token_probs ? 0 : 1));
-  if (h.key_frame) {
-    bw.put(refresh_entropy);
-  } else {
-    bw.put(x.refresh_golden);
-    bw.put(x.refresh_alternate);
-    if (!x.refresh_golden) bw.literal(x.copy_to_golden, 2);
-    if (!x.refresh_alternate) bw.literal(x.copy_to_alternate, 2);
-    bw.put(x.sign_bias_golden);
-    bw.put(x.sign_bias_alternate);
-    bw.put(refresh_entropy);
-    bw.put(features ? x.refresh_last : 1);
-  }
-  if (x.saved_coef_probs && refresh_entropy) memcpy(x.saved_coef_probs, coef_probs, 1056);
-  for (int i = 0; i < 1056; i++) {
-    bw.put(updated[i], k_coef_update_probs[i]);
-    if (updated[i]) bw.literal(coef_probs[i], 8);
-  }
-  bw.put(1);  // mb_no_coeff_skip
-  bw.literal(skip_prob, 8);
-  if (!h.key_frame) {
-    bw.literal(prob_inter, 8);
-    bw.literal(prob_last, 8);
-    bw.literal(prob_golden, 8);
-    bw.put(0);           // intra_16x16_prob unchanged
-    bw.put(0);           // intra_chroma_prob unchanged
-    for (int i = 0; i < 38; i++) bw.put(0, k_mv_update_probs[i]);  // motion vector probabilities unchanged
-  }
-  const uint8_t(*mv_probs)[19] = reinterpret_cast<const uint8_t(*)[19]>(k_mv_default_probs);
+  const uint8_t(*mv_probs)[19] = reinterpret_cast<const uint8_t(*)[19]>(vb ? &vb->mv[0][0] : k_mv_default_probs);
+  const uint8_t* const ymode_probs = vb ? vb->ymode : k_ymode_default_probs;
+  const uint8_t* const uvmode_probs = vb ? vb->uvmode : k_uvmode_default_probs;
+  const bool write_segment = vb ? vb->read_segment : (x.segmentation_enabled && x.update_mb_segmentation_map);
 
   // ---- first partition: macroblock headers (macroblock.cc:44-71, 84-111, 343-456 inverted) ----
   for (int row = 0; row < rows; row++) {
@@ -622,15 +638,16 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
       const MbInfo* above = row > 0 ? &info[idx - cols] : nullptr;
       const MbInfo* left = col > 0 ? &info[idx - 1] : nullptr;
       const MbInfo* above_left = (row > 0 && col > 0) ? &info[idx - cols - 1] : nullptr;
-      if (x.segmentation_enabled && x.update_mb_segmentation_map) {
+      if (write_segment) {
         // segment tree {2, 4, -0, -1, -2, -3} (modemv_data.cc): the first decision picks the pair
-        const uint8_t sp[3] = {static_cast<uint8_t>(x.segment_tree_probs[0]), static_cast<uint8_t>(x.segment_tree_probs[1]),
-                               static_cast<uint8_t>(x.segment_tree_probs[2])};
+        uint8_t sp[3] = {static_cast<uint8_t>(x.segment_tree_probs[0]), static_cast<uint8_t>(x.segment_tree_probs[1]),
+                         static_cast<uint8_t>(x.segment_tree_probs[2])};
+        if (vb) memcpy(sp, vb->seg_tree_probs, 3);
         if (mb.segment_id > 3) return {};
         bw.put(mb.segment_id >> 1, sp[0]);
         bw.put(mb.segment_id & 1, sp[1 + (mb.segment_id >> 1)]);
       }
-      bw.put(skip[idx], skip_prob);
+      if (!vb || vb->has_skip_prob) bw.put(skip[idx], skip_prob);
       me.y_mode = mb.y_mode;
       if (mb.ref_frame == VP8GPU_REF_CURRENT) {
         if (!h.key_frame) bw.put(0, prob_inter);
@@ -649,10 +666,10 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
           }
           write_path(bw, kUvModePaths, k_kf_uvmode_probs, mb.uv_mode);
         } else {
-          write_path(bw, kYModePaths, k_ymode_default_probs, mb.y_mode);
+          write_path(bw, kYModePaths, ymode_probs, mb.y_mode);
           if (mb.y_mode == VP8GPU_B_PRED)
             for (int i = 0; i < 16; i++) write_path(bw, kBModePaths, k_bmode_probs, static_cast<int>((mb.b_modes >> (4 * i)) & 15));
-          write_path(bw, kUvModePaths, k_uvmode_default_probs, mb.uv_mode);
+          write_path(bw, kUvModePaths, uvmode_probs, mb.uv_mode);
         }
         continue;
       }
@@ -696,6 +713,12 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
             break;
           }
         }
+        uint32_t labels = 0;
+        if (vb) {
+          if (mb.split_idx >= vb->sub_labels.size()) return {};
+          layout = (vb->mb_coded[idx] >> 1) & 3;
+          labels = vb->sub_labels[mb.split_idx];
+        }
         write_path(bw, kMvRefPaths, ref_probs, VP8GPU_SPLITMV);
         write_path(bw, kSplitPaths, k_split_probs, layout);
         int16_t done[16][2];  // vectors as the decoder knows them so far
@@ -716,10 +739,14 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
           else if (lz) ctx = 1;
           const int vx = mv[first][0], vy = mv[first][1];
           const uint8_t* sp = k_submv_ref_probs + ctx * 3;
-          if (vx == lx && vy == ly) write_path(bw, kSubMvPaths, sp, kSubLeft);
-          else if (vx == ax && vy == ay) write_path(bw, kSubMvPaths, sp, kSubAbove);
-          else if ((vx | vy) == 0) write_path(bw, kSubMvPaths, sp, kSubZero);
-          else {
+          int label = kSubNew;
+          if (vx == lx && vy == ly) label = kSubLeft;
+          else if (vx == ax && vy == ay) label = kSubAbove;
+          else if ((vx | vy) == 0) label = kSubZero;
+          if (vb) label = static_cast<int>((labels >> (2 * part)) & 3);  // as coded (any label that decodes to the vector is legal)
+          if (label != kSubNew) {
+            write_path(bw, kSubMvPaths, sp, label);
+          } else {
             write_path(bw, kSubMvPaths, sp, kSubNew);
             const int dx = vx - best.x, dy = vy - best.y;
             if (abs(dx) > 2046 || abs(dy) > 2046) return {};
@@ -788,6 +815,22 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
   }
   for (int p = 0; p < nparts; p++) out.insert(out.end(), work[p].bytes.begin(), work[p].bytes.end());
   return out;
+}
+
+std::vector<uint8_t> serialize_parsed(const ParsedFrame& frame) {
+  const Verbatim& v = frame.verbatim;
+  if (v.header_tape.empty() || v.mb_coded.size() != static_cast<size_t>(frame.desc.mb_cols) * frame.desc.mb_rows) return {};
+  EncodeHeader h;
+  h.key_frame = v.key;
+  h.show_frame = v.show;
+  h.width = v.width;
+  h.height = v.height;
+  EncodeFeatures x;
+  x.log2_partitions = v.log2_parts;
+  x.sign_bias_golden = v.sign_golden;
+  x.sign_bias_alternate = v.sign_alt;
+  x.verbatim = &v;
+  return serialize_frame(h, frame.mbs.data(), frame.tokens.data(), frame.split.data(), &x);
 }
 
 }  // namespace vp8

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "../../include/vp8gpu.h"
+#include "parser.h"
 
 namespace vp8 {
 
@@ -62,6 +63,10 @@ struct EncodeFeatures {
     int prob_inter = 0, prob_last = 0, prob_golden = 0; // InterFrameHeader fields start at 0 (zero_decoder) and persist
   };
   RefWriterState* ref_writer = nullptr;
+  // Frame::serialize of a PARSED frame (encoder/serializer.cc:388-405; gate: src/tests/roundtrip.cc:93-112):
+  // header decisions and ambiguous labels come from the parse (parser.h Verbatim), everything else -- modes,
+  // vectors, token partitions with their contexts -- is written from the flat records.  Set by serialize_parsed.
+  const Verbatim* verbatim = nullptr;
   bool ref_estimate = false;  // with ref_writer: a size estimate (size_estimation.cc): no token-probability updates
 };
 
@@ -87,5 +92,10 @@ class BoolWriter {
 // (e.g. a reference other than LAST, a motion vector out of range).
 std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs, const vp8gpu_token* tokens,
                                      const vp8gpu_split_mvs* split, const EncodeFeatures* features = nullptr);
+
+// Frame::serialize( probability_tables ) of a frame that parse_frame produced with keep_verbatim
+// (encoder/serializer.cc:388-405, the reference's own round-trip gate src/tests/roundtrip.cc:93-112): the
+// result equals the parsed input byte for byte.  Empty vector if the frame was not parsed with keep_verbatim.
+std::vector<uint8_t> serialize_parsed(const ParsedFrame& frame);
 
 }  // namespace vp8

@@ -252,6 +252,17 @@ const vp8gpu_split_mvs* vp8gpu_parsed_split(const vp8gpu_parsed* p);
  * On error `state` is unchanged. */
 int vp8gpu_parse_frame(vp8gpu_state* state, const uint8_t* data, size_t len, vp8gpu_parsed* out);
 
+/* Frame::serialize( probability_tables ) of a parsed frame (encoder/serializer.cc:388-405), the inverse of
+ * vp8gpu_parse_frame.  The reference's Frame object keeps its header and every macroblock's labels, so its
+ * serialize() reproduces the input byte for byte (gate: src/tests/roundtrip.cc:93-112, tests/roundtrip-verify.test);
+ * here a vp8gpu_parsed keeps them when vp8gpu_parsed_keep_labels( p, 1 ) was called before the parse: the header
+ * decisions as coded, mb_skip_coeff of every macroblock, SPLITMV layouts and sub-vector labels.  Modes, vectors
+ * and the DCT partitions are re-written from the flat records with the decoder's contexts.
+ * vp8gpu_parsed_serialize: VP8GPU_ERR_LOGIC if the labels were not kept, VP8GPU_ERR_NOMEM if cap is too small
+ * (*size = needed). */
+int vp8gpu_parsed_keep_labels(vp8gpu_parsed* p, int on);
+int vp8gpu_parsed_serialize(const vp8gpu_parsed* p, uint8_t* out, size_t cap, size_t* size);
+
 /* Same contract and same output as vp8gpu_parse_frame, with the front end split the B200 way: the
  * host decodes the first partition (frame header, macroblock modes, motion vectors: macroblock.cc:
  * 44-456), the device decodes the DCT partitions (Frame::parse_tokens, frame.cc:122-137;
