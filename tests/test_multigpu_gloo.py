@@ -36,8 +36,8 @@ seconds = 1.0 + rank          # pretend rank 1 is slower: the job is as slow as 
 M.barrier(dist)
 agg = M.aggregate_throughput(dist, local, units, seconds)
 total_frames = M.reduce_sum(dist, local, len(frames))
-print(json.dumps({"rank": rank, "gops": mine, "frames": len(frames), "sha": hashlib.sha1(out).hexdigest(),
-                  "agg": agg, "total_frames": total_frames, "units": units}))
+os.write(1, (json.dumps({"rank": rank, "gops": mine, "frames": len(frames), "sha": hashlib.sha1(out).hexdigest(),
+                  "agg": agg, "total_frames": total_frames, "units": units}) + "\n").encode())
 dist.destroy_process_group()
 '''
 
@@ -158,8 +158,8 @@ got = M.broadcast_decoder(Ctx(), dec, 0, dist, local,
                           make_decoder=lambda c, blob, three: Dec(DecoderState.deserialize(blob), three))
 tail = records_digest(got.get_state(), frames[SPLIT:])
 refs = got.get_references()
-print(json.dumps({"rank": rank, "tail_ok": tail == want_tail, "state_equal": got.get_state() == straight,
-                  "fills": [int(r.buf[0]) for r in refs], "shared": refs[0] is refs[1], "distinct": refs[2] is not refs[0]}))
+os.write(1, (json.dumps({"rank": rank, "tail_ok": tail == want_tail, "state_equal": got.get_state() == straight,
+                  "fills": [int(r.buf[0]) for r in refs], "shared": refs[0] is refs[1], "distinct": refs[2] is not refs[0]}) + "\n").encode())
 dist.destroy_process_group()
 '''
 
