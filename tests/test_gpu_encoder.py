@@ -209,7 +209,9 @@ def test_encoder_value_semantics():
     cont = Encoder.from_decoder(ctx, dec)
     blob = cont.encode_with_quantizer(*nxt, 60)
     assert (blob[0] & 1) == 1  # continues with an inter frame
-    assert blob == out["a"]
+    # not byte-equal to out["a"] in general: an Encoder built from a Decoder has no previous loop-filter level
+    # (encoder.hh:144, Optional) and searches from level 0 (encoder.cc:475-487), a copy searches around the last one;
+    # what must hold is the closed loop below
     _, r = dec.get_frame_output(blob)
     assert cont.export_decoder() == dec
     r.release()
