@@ -152,6 +152,9 @@ class Decoder {
     const vp8gpu_frame_id ids[3] = {refs.last.id(), refs.golden.id(), refs.alternative.id()};
     check(vp8gpu_decoder_create_from(ctx_.get(), state.get(), ids, &h_), ctx_.get(), "decoder_create_from");
   }
+  // takes ownership of a decoder handle made by the C ABI (Encoder::export_decoder)
+  Decoder(const Context& ctx, vp8gpu_decoder* owned, uint16_t width, uint16_t height)
+      : ctx_(ctx), width_(width), height_(height), h_(owned) {}
   Decoder(const Decoder& o) : ctx_(o.ctx_), width_(o.width_), height_(o.height_) {
     check(vp8gpu_decoder_clone(o.h_, &h_), ctx_.get(), "decoder_clone");
   }
@@ -166,6 +169,8 @@ class Decoder {
 
   uint16_t get_width() const { return width_; }
   uint16_t get_height() const { return height_; }
+  vp8gpu_decoder* handle() const { return h_; }
+  const Context& context() const { return ctx_; }
 
   // parse_frame<KeyFrame|InterFrame>( decompress_frame( chunk ) ) (decoder.cc:83-98)
   ParsedFrame parse_frame(const Chunk& compressed_frame) {
@@ -226,8 +231,10 @@ class Decoder {
   bool operator!=(const Decoder& o) const { return !(*this == o); }
 };
 
-// Encoder (encoder/encoder.hh:345-382), first slice.  The source raster is passed as display-size
-// planes in host memory (the reference takes a VP8Raster filled by its input readers).
+// Encoder (encoder/encoder.hh:345-382).  The source raster is passed as display-size planes in host memory
+// (the reference takes a VP8Raster filled by its input readers).  Like the reference's, an Encoder is a
+// copyable value: copies share the (immutable) reference rasters and may encode concurrently on different
+// threads (salsify/salsify-sender.cc:492-518).
 struct SourceFrame {
   const uint8_t *y, *u, *v;
   size_t y_stride, uv_stride;
@@ -246,9 +253,39 @@ class Encoder {
       : ctx_(ctx), width_(width), height_(height), buf_(size_t(width) * height * 3 + 65536) {
     check(vp8gpu_encoder_create(ctx_.get(), &h_), ctx_.get(), "encoder_create");
   }
-  Encoder(const Encoder&) = delete;
-  Encoder& operator=(const Encoder&) = delete;
+  // Encoder( const Decoder &, two_pass, quality ) (encoder.hh:350-351): continue the decoder's stream
+  explicit Encoder(const Decoder& decoder)
+      : ctx_(decoder.context()), width_(decoder.get_width()), height_(decoder.get_height()),
+        buf_(size_t(width_) * height_ * 3 + 65536) {
+    check(vp8gpu_encoder_create_from_decoder(ctx_.get(), decoder.handle(), &h_), ctx_.get(), "encoder_create_from_decoder");
+  }
+  // Encoder( const Encoder & ) (encoder.cc:92-102)
+  Encoder(const Encoder& o) : ctx_(o.ctx_), width_(o.width_), height_(o.height_), buf_(o.buf_.size()) {
+    check(vp8gpu_encoder_clone(o.h_, &h_), ctx_.get(), "encoder_clone");
+  }
+  Encoder(Encoder&& o) noexcept : ctx_(o.ctx_), width_(o.width_), height_(o.height_), h_(o.h_), buf_(std::move(o.buf_)) {
+    o.h_ = nullptr;
+  }
+  Encoder& operator=(Encoder o) {
+    std::swap(h_, o.h_);
+    std::swap(buf_, o.buf_);
+    width_ = o.width_, height_ = o.height_;
+    return *this;
+  }
   ~Encoder() { vp8gpu_encoder_destroy(h_); }
+
+  // export_decoder (encoder.hh:378): the Decoder a receiver holds after the frames emitted so far
+  Decoder export_decoder() const {
+    vp8gpu_decoder* d = nullptr;
+    check(vp8gpu_encoder_export_decoder(h_, &d), ctx_.get(), "export_decoder");
+    return Decoder(ctx_, d, width_, height_);
+  }
+  // minihash (encoder.hh:382)
+  uint32_t minihash() const {
+    uint32_t m = 0;
+    check(vp8gpu_encoder_minihash(h_, &m), ctx_.get(), "minihash");
+    return m;
+  }
 
   // encode_with_quantizer (encoder.cc:559-590)
   std::vector<uint8_t> encode_with_quantizer(const SourceFrame& f, uint8_t y_ac_qi) {

@@ -1,0 +1,54 @@
+// C++ caller of the host mirror (alfalfa_b200/host/alfalfa_gpu.hh), in the shape of the reference's
+// src/tests/decode-to-stdout.cc:43-49: open an IVF, feed every frame to Decoder::parse_and_decode_frame,
+// write the display rectangle of every shown frame to stdout.  tests/test_gpu_cxx_host.py runs it over the
+// golden vectors on the GPU box and compares the SHA-1 of the output with the vector's name
+// (tests/decoding.test:14-15).  usage: decode_to_stdout FILE.ivf [device_tokens(0|1)]
+#include <cstdio>
+#include <cstdlib>
+#include <exception>
+#include <fstream>
+#include <iterator>
+#include <vector>
+
+#include "../../alfalfa_b200/host/alfalfa_gpu.hh"
+
+using namespace alfalfa_gpu;
+
+static uint32_t le32(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | (uint32_t(p[3]) << 24); }
+
+int main(int argc, char** argv) {
+  try {
+    if (argc < 2) {
+      std::fprintf(stderr, "usage: %s FILE.ivf [device_tokens]\n", argv[0]);
+      return 2;
+    }
+    std::ifstream in(argv[1], std::ios::binary);
+    const std::vector<uint8_t> file((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    if (file.size() < 32) throw Invalid("not an IVF file");
+    const uint16_t width = file[12] | (file[13] << 8), height = file[14] | (file[15] << 8);
+    const uint32_t frame_count = le32(&file[24]);
+
+    Context ctx(0, width, height, 16);
+    Decoder decoder(ctx, width, height);
+    if (argc > 2 && std::atoi(argv[2])) decoder.set_device_tokens(true);
+
+    size_t pos = 32;
+    bool started = false;
+    for (uint32_t i = 0; i < frame_count && pos + 12 <= file.size(); i++) {
+      const uint32_t n = le32(&file[pos]);
+      const Chunk frame(&file[pos + 12], n);
+      pos += 12 + n;
+      if (!started && (n == 0 || (frame.buffer[0] & 1))) continue;  // FilePlayer starts at the first key frame
+      started = true;
+      const RasterHandle raster = decoder.parse_and_decode_frame(frame);
+      if (raster.initialized()) {
+        const std::vector<uint8_t> pixels = raster.dump(width, height);
+        std::fwrite(pixels.data(), 1, pixels.size(), stdout);
+      }
+    }
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "%s: %s\n", argv[0], e.what());
+    return 1;
+  }
+  return 0;
+}
