@@ -679,6 +679,13 @@ int vp8gpu_decoder_decode(vp8gpu_decoder* d, const uint8_t* data, size_t len, in
   if (d->tok_busy[slot]) {
     if (d->tok_finished[slot]) cudaEventSynchronize(d->tok_finished[slot]);
     d->tok_busy[slot] = false;
+    // the frame that used this slot is done: k_tokens reports a token pool that was too small instead of
+    // writing out of bounds (the capacity rule of Engine::token_ring_layout makes that impossible, so a set
+    // flag is an internal error -- but it must not pass silently)
+    uint32_t res[2] = {0, 0};
+    if (cudaMemcpy(res, d->tok_ring->dev_slot(slot) + d->tok_ring->result_off, sizeof(res), cudaMemcpyDeviceToHost) != cudaSuccess)
+      return e->fail(VP8GPU_ERR_CUDA, "token result read failed");
+    if (res[1]) return e->fail(VP8GPU_ERR_LOGIC, "device token pool overflow in an earlier frame of this decoder");
   }
   rc = vp8::parse_frame(d->state.s, data, len, p->f, true);
   if (rc != VP8GPU_OK) return e->fail(rc, "parse_frame failed");
@@ -799,6 +806,12 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     if (tok_slots < 4) tok_slots = 0;  // pool too small: the host workers parse everything
   }
   const bool device_tokens = tok_slots > 0;
+  if (!device_tokens) {
+    // host-token path: a worker holds up to kSlots queued outputs plus its three references, and
+    // Engine::frame_alloc fails rather than blocks, so the worker count is bounded by the raster pool
+    const int fit = e->frames_free() / 8;
+    if (threads > fit) threads = fit > 0 ? fit : 1;
+  }
   if (device_tokens) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device());

@@ -46,11 +46,14 @@ uint8_t* tmap_arena_alloc(int device, size_t bytes) {
 constexpr int kSyncHeaderInts = 64;  // [0] = intra ticket, [32] = loop-filter ticket (own cache lines)
 }  // namespace
 
+// workers and dispatchers of vp8gpu_decode_ivf report errors concurrently: the text has its own lock
 int Engine::fail(int code, const std::string& what) {
+  std::lock_guard<std::mutex> lk(err_mu_);
   err_ = what;
   return code;
 }
 int Engine::cuda_fail(cudaError_t e, const char* what) {
+  std::lock_guard<std::mutex> lk(err_mu_);
   err_ = std::string(what) + ": " + cudaGetErrorString(e);
   return VP8GPU_ERR_CUDA;
 }
@@ -396,8 +399,10 @@ int Engine::frames_equal(int a, int b, int lane, int* equal) {
   cudaStream_t s = lanes_[lane];
   {
     std::lock_guard<std::mutex> lk(mu_);
+    for (int id : {a, b})
+      if (id < 0 || id >= (int)frames_.size() || frames_[id].refcnt <= 0) return fail(VP8GPU_ERR_LOGIC, "compare: bad frame id");
     if (!cmp_scratch_) CU(cudaMalloc(&cmp_scratch_, 1024));
-    flag = reinterpret_cast<int*>(cmp_scratch_);
+    flag = reinterpret_cast<int*>(cmp_scratch_ + 640 + 4 * lane);  // one flag per lane; the hash slots end at 64 + 8 * 64
     if (int rc = wait_for(frames_[a], lane, s, false)) return rc;
     if (int rc = wait_for(frames_[b], lane, s, false)) return rc;
     CU(cudaMemsetAsync(flag, 0, sizeof(int), s));

@@ -165,6 +165,7 @@ class Engine {
   int make_tensor_maps(int id);
   std::atomic<uint64_t> launches_{0};
   std::string err_;
+  std::mutex err_mu_;
 };
 
 }  // namespace vp8

@@ -111,7 +111,8 @@ struct ParsedFrame {
 };
 
 // Parse one compressed frame and apply it to `state`.  Returns VP8GPU_OK or VP8GPU_ERR_*;
-// on error `state` is left untouched.  With defer_tokens only the first partition (frame header,
+// on INVALID / UNSUPPORTED `state` is left untouched (the header is validated before anything is committed); an
+// allocation failure (VP8GPU_ERR_NOMEM) during the macroblock pass leaves it advanced.  With defer_tokens only the first partition (frame header,
 // macroblock modes, motion vectors) is decoded: records carry VP8GPU_MB_SKIP instead of
 // tok_off / tok_cnt, no tokens are produced, desc.n_tokens is 0 and out.tw describes the rest.
 int parse_frame(State& state, const uint8_t* data, size_t len, ParsedFrame& out, bool defer_tokens = false);

@@ -249,7 +249,7 @@ const vp8gpu_split_mvs* vp8gpu_parsed_split(const vp8gpu_parsed* p);
  * fill `out`.  Errors: INVALID (truncated / bad start code / bad partition sizes),
  * UNSUPPORTED (version != 0, scaling, colour space / clamping bits, simple filter,
  * size != state size), mirroring uncompressed_chunk.cc:34-130 and frame_header.hh:213-295.
- * On error `state` is unchanged. */
+ * On INVALID / UNSUPPORTED `state` is unchanged; after VP8GPU_ERR_NOMEM it must be discarded. */
 int vp8gpu_parse_frame(vp8gpu_state* state, const uint8_t* data, size_t len, vp8gpu_parsed* out);
 
 /* Frame::serialize( probability_tables ) of a parsed frame (encoder/serializer.cc:388-405), the inverse of
