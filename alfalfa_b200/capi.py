@@ -155,6 +155,8 @@ SYMBOLS = {
                                                           C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
     "vp8gpu_encoder_estimate_frame_size": (C.c_int, [_vp, _u8p, C.c_size_t, _u8p, _u8p, C.c_size_t, C.c_int,
                                                      C.POINTER(C.c_size_t)]),
+    "vp8gpu_decoder_serialize": (C.c_int, [_vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "vp8gpu_decoder_deserialize": (C.c_int, [_vp, C.c_char_p, C.c_size_t, _pp]),
     "vp8gpu_decoder_hash": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "vp8gpu_encoder_stats": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vp8gpu_frame_ssim": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),

@@ -616,6 +616,74 @@ int vp8gpu_decoder_create_from(vp8gpu_ctx* ctx, const vp8gpu_state* state, const
   return VP8GPU_OK;
 }
 
+// Decoder::serialize (decoder.cc:54-69) in the reference's tag-length-value format: DECODER { DECODER_STATE {...}
+// REFERENCES { display size, REF_LAST { planes } } }.  Like the reference, only the LAST reference is stored
+// (decoder.cc:177-197) and a deserialised Decoder has golden = alternative = last (decoder.cc:171-175).
+int vp8gpu_decoder_serialize(vp8gpu_decoder* d, uint8_t* out, size_t cap, size_t* size) {
+  if (!d || !size) return VP8GPU_ERR_LOGIC;
+  Engine* e = d->ctx->engine;
+  const vp8::Geom& g = e->geom();
+  const std::vector<uint8_t> st = d->state.s.serialize();
+  const size_t raster = (size_t)g.W * g.H + 2 * (size_t)(g.W / 2) * (g.H / 2);
+  const size_t refs_body = 4 + 5 + raster;
+  const size_t total = 5 + st.size() + 5 + refs_body;
+  *size = total;
+  if (!out || cap < total) return VP8GPU_ERR_NOMEM;
+  auto u32 = [](uint8_t* p, size_t v) { p[0] = v & 0xFF, p[1] = (v >> 8) & 0xFF, p[2] = (v >> 16) & 0xFF, p[3] = (v >> 24) & 0xFF; };
+  uint8_t* p = out;
+  *p++ = 11;  // EncoderSerDesTag::DECODER
+  u32(p, st.size() + 5 + refs_body);
+  p += 4;
+  memcpy(p, st.data(), st.size());
+  p += st.size();
+  *p++ = 7;  // REFERENCES
+  u32(p, refs_body);
+  p += 4;
+  p[0] = e->width() & 0xFF, p[1] = e->width() >> 8, p[2] = e->height() & 0xFF, p[3] = e->height() >> 8;
+  p += 4;
+  *p++ = 8;  // REF_LAST
+  u32(p, raster);
+  p += 4;
+  cudaSetDevice(e->device());
+  return e->frame_download(d->refs[0], p, g.W, p + (size_t)g.W * g.H, p + (size_t)g.W * g.H + (size_t)(g.W / 2) * (g.H / 2), g.W / 2);
+}
+
+// Decoder::deserialize (decoder.cc:71-81)
+int vp8gpu_decoder_deserialize(vp8gpu_ctx* ctx, const uint8_t* data, size_t len, vp8gpu_decoder** out) {
+  if (!ctx || !data || !out) return VP8GPU_ERR_LOGIC;
+  Engine* e = ctx->engine;
+  auto u32 = [](const uint8_t* p) { return (size_t)p[0] | ((size_t)p[1] << 8) | ((size_t)p[2] << 16) | ((size_t)p[3] << 24); };
+  if (len < 5 || data[0] != 11 || u32(data + 1) != len - 5) return e->fail(VP8GPU_ERR_INVALID, "not a serialised Decoder");
+  vp8gpu_state st(e->width(), e->height());
+  size_t used = 0;
+  if (!State::deserialize(data + 5, len - 5, st.s, &used)) return e->fail(VP8GPU_ERR_INVALID, "bad DECODER_STATE record");
+  if (st.s.width != e->width() || st.s.height != e->height())
+    return e->fail(VP8GPU_ERR_UNSUPPORTED, "serialised Decoder has another frame size than the context");
+  const uint8_t* p = data + 5 + used;
+  const size_t left = len - 5 - used;
+  const vp8::Geom& g = e->geom();
+  const size_t raster = (size_t)g.W * g.H + 2 * (size_t)(g.W / 2) * (g.H / 2);
+  if (left < 9 || p[0] != 7) return e->fail(VP8GPU_ERR_INVALID, "bad REFERENCES record");
+  const int rw = p[5] | (p[6] << 8), rh = p[7] | (p[8] << 8);
+  if (rw != e->width() || rh != e->height()) return e->fail(VP8GPU_ERR_INVALID, "REFERENCES size mismatch");
+  vp8gpu_frame_id id = -1;
+  cudaSetDevice(e->device());
+  int rc = e->frame_alloc(&id);
+  if (rc != VP8GPU_OK) return rc;
+  if (left >= 9 + 5 + raster && p[9] == 8 && u32(p + 10) == raster) {
+    const uint8_t* y = p + 14;
+    rc = e->frame_upload(id, y, g.W, y + (size_t)g.W * g.H, y + (size_t)g.W * g.H + (size_t)(g.W / 2) * (g.H / 2), g.W / 2);
+  } else if (left != 9) {
+    rc = e->fail(VP8GPU_ERR_INVALID, "bad REF_LAST record");
+  }  // no REF_LAST record: EncoderStateDeserializer::get_ref returns a fresh raster (enc_state_serializer.hh:168-190)
+  if (rc == VP8GPU_OK) {
+    const vp8gpu_frame_id three[3] = {id, id, id};
+    rc = vp8gpu_decoder_create_from(ctx, &st, three, out);
+  }
+  e->frame_release(id);
+  return rc;
+}
+
 int vp8gpu_decoder_clone(const vp8gpu_decoder* src, vp8gpu_decoder** out) {
   if (!src || !out) return VP8GPU_ERR_LOGIC;
   const vp8gpu_state tmp(src->state.s);

@@ -93,56 +93,124 @@ uint64_t State::hash() const {
   return h;
 }
 
+// DecoderState::serialize (decoder.cc:283-314) in the reference's own tag-length-value format
+// (enc_state_serializer.hh:43-116): every record is a one-byte EncoderSerDesTag, a little-endian u32 length and
+// the payload; integers are little-endian.  A blob written here is readable by the reference's
+// EncoderStateDeserializer and vice versa (tests/test_state_format.py compares the bytes).
+namespace {
+enum SerDesTag : uint8_t {  // EncoderSerDesTag, enc_state_serializer.hh:43-56
+  TAG_PROB_TABLE = 0, TAG_FILT_ADJ, TAG_SEGM_ABS, TAG_SEGM_REL, TAG_DECODER_STATE, TAG_OPT_EMPTY, TAG_OPT_FULL,
+  TAG_REFERENCES, TAG_REF_LAST, TAG_REF_GOLD, TAG_REF_ALT, TAG_DECODER
+};
+void put_u16(std::vector<uint8_t>& b, uint32_t v) {
+  b.push_back(static_cast<uint8_t>(v & 0xFF));
+  b.push_back(static_cast<uint8_t>((v >> 8) & 0xFF));
+}
+void put_u32(std::vector<uint8_t>& b, uint32_t v) {
+  put_u16(b, v & 0xFFFF);
+  put_u16(b, v >> 16);
+}
+uint32_t get_u16(const uint8_t* p) { return p[0] | (p[1] << 8); }
+uint32_t get_u32(const uint8_t* p) { return get_u16(p) | (get_u16(p + 2) << 16); }
+}  // namespace
+
 std::vector<uint8_t> State::serialize() const {
   std::vector<uint8_t> b;
-  auto put = [&b](const void* p, size_t n) {
-    const uint8_t* q = static_cast<const uint8_t*>(p);
-    b.insert(b.end(), q, q + n);
-  };
-  const uint8_t head[12] = {'V', '8', 'S', 1, static_cast<uint8_t>(width & 0xFF), static_cast<uint8_t>(width >> 8),
-                            static_cast<uint8_t>(height & 0xFF), static_cast<uint8_t>(height >> 8), seg_enabled, seg_abs,
-                            lf_adj_enabled, 0};
-  put(head, sizeof(head));
-  put(coef_probs, sizeof(coef_probs));
-  put(ymode_probs, 4);
-  put(uvmode_probs, 3);
-  put(mv_probs, sizeof(mv_probs));
-  put(seg_quant, 4);
-  put(seg_lf, 4);
-  put(ref_adj, 4);
-  put(mode_adj, 4);
-  if (seg_enabled) put(seg_map.data(), seg_map.size());
+  b.push_back(TAG_DECODER_STATE);
+  put_u32(b, 0);  // patched below
+  put_u16(b, static_cast<uint32_t>(width));
+  put_u16(b, static_cast<uint32_t>(height));
+  // ProbabilityTables::serialize (probability_tables.cc:126-158)
+  b.push_back(TAG_PROB_TABLE);
+  put_u32(b, 1056 + 4 + 3 + 38);
+  b.insert(b.end(), coef_probs, coef_probs + 1056);
+  b.insert(b.end(), ymode_probs, ymode_probs + 4);
+  b.insert(b.end(), uvmode_probs, uvmode_probs + 3);
+  b.insert(b.end(), &mv_probs[0][0], &mv_probs[0][0] + 38);
+  if (seg_enabled) {
+    // Segmentation::serialize (decoder.cc:396-422).  The reference sizes its SegmentationMap with the frame's
+    // PIXEL dimensions (decoder_state.hh:170-176: map( width, height, 3 )) and only ever touches the top-left
+    // mb_cols x mb_rows corner; the rest keeps the initial value 3.
+    b.push_back(TAG_OPT_FULL);
+    b.push_back(seg_abs ? TAG_SEGM_ABS : TAG_SEGM_REL);
+    put_u32(b, 4 + 4 + 4 + static_cast<uint32_t>(width) * static_cast<uint32_t>(height));
+    put_u16(b, static_cast<uint32_t>(width));
+    put_u16(b, static_cast<uint32_t>(height));
+    for (int i = 0; i < 4; i++) b.push_back(static_cast<uint8_t>(seg_quant[i]));
+    for (int i = 0; i < 4; i++) b.push_back(static_cast<uint8_t>(seg_lf[i]));
+    const size_t at = b.size();
+    b.resize(at + static_cast<size_t>(width) * height, 3);
+    for (int r = 0; r < mb_rows && r < height; r++)
+      memcpy(&b[at + static_cast<size_t>(r) * width], &seg_map[static_cast<size_t>(r) * mb_cols],
+             static_cast<size_t>(mb_cols < width ? mb_cols : width));
+  } else {
+    b.push_back(TAG_OPT_EMPTY);
+  }
+  if (lf_adj_enabled) {
+    // FilterAdjustments::serialize (decoder.cc:342-357)
+    b.push_back(TAG_OPT_FULL);
+    b.push_back(TAG_FILT_ADJ);
+    put_u32(b, 8);
+    for (int i = 0; i < 4; i++) b.push_back(static_cast<uint8_t>(ref_adj[i]));
+    for (int i = 0; i < 4; i++) b.push_back(static_cast<uint8_t>(mode_adj[i]));
+  } else {
+    b.push_back(TAG_OPT_EMPTY);
+  }
+  const uint32_t len = static_cast<uint32_t>(b.size() - 5);  // = 4 + sub-records + the two option tags
+  b[1] = static_cast<uint8_t>(len & 0xFF), b[2] = static_cast<uint8_t>((len >> 8) & 0xFF);
+  b[3] = static_cast<uint8_t>((len >> 16) & 0xFF), b[4] = static_cast<uint8_t>(len >> 24);
   return b;
 }
 
-bool State::deserialize(const uint8_t* d, size_t len, State& out) {
-  const size_t fixed = 12 + 1056 + 4 + 3 + 38 + 16;
-  if (len < fixed || d[0] != 'V' || d[1] != '8' || d[2] != 'S' || d[3] != 1) return false;
-  const int w = d[4] | (d[5] << 8), h = d[6] | (d[7] << 8);
+// DecoderState::deserialize (decoder.cc:316-330, :242-255); `used` (optional) = bytes consumed
+bool State::deserialize(const uint8_t* d, size_t len, State& out, size_t* used) {
+  if (len < 9 || d[0] != TAG_DECODER_STATE) return false;
+  const size_t body = get_u32(d + 1);
+  if (body + 5 > len) return false;
+  const uint8_t* p = d + 5;
+  const uint8_t* const end = d + 5 + body;
+  const int w = static_cast<int>(get_u16(p)), h = static_cast<int>(get_u16(p + 2));
+  p += 4;
   if (w <= 0 || h <= 0) return false;
   State s(w, h);
-  s.seg_enabled = d[8];
-  s.seg_abs = d[9];
-  s.lf_adj_enabled = d[10];
-  const uint8_t* p = d + 12;
-  auto get = [&p](void* to, size_t n) {
-    memcpy(to, p, n);
-    p += n;
-  };
-  get(s.coef_probs, sizeof(s.coef_probs));
-  get(s.ymode_probs, 4);
-  get(s.uvmode_probs, 3);
-  get(s.mv_probs, sizeof(s.mv_probs));
-  get(s.seg_quant, 4);
-  get(s.seg_lf, 4);
-  get(s.ref_adj, 4);
-  get(s.mode_adj, 4);
-  if (s.seg_enabled) {
-    if (len != fixed + s.seg_map.size()) return false;
-    get(s.seg_map.data(), s.seg_map.size());
-  } else if (len != fixed) {
+  const size_t prob_len = 1056 + 4 + 3 + 38;
+  if (static_cast<size_t>(end - p) < 5 + prob_len + 2 || p[0] != TAG_PROB_TABLE || get_u32(p + 1) != prob_len) return false;
+  p += 5;
+  memcpy(s.coef_probs, p, 1056);
+  memcpy(s.ymode_probs, p + 1056, 4);
+  memcpy(s.uvmode_probs, p + 1060, 3);
+  memcpy(s.mv_probs, p + 1063, 38);
+  p += prob_len;
+  const uint8_t seg_opt = *p++;
+  if (seg_opt == TAG_OPT_FULL) {
+    if (end - p < 5 + 12 || (p[0] != TAG_SEGM_ABS && p[0] != TAG_SEGM_REL)) return false;
+    s.seg_enabled = true;
+    s.seg_abs = p[0] == TAG_SEGM_ABS;
+    const size_t seg_len = get_u32(p + 1);
+    const size_t mw = get_u16(p + 5), mh = get_u16(p + 7);
+    if (seg_len != 12 + mw * mh || static_cast<size_t>(end - p) < 5 + seg_len) return false;
+    if (mw < static_cast<size_t>(s.mb_cols) || mh < static_cast<size_t>(s.mb_rows)) return false;
+    memcpy(s.seg_quant, p + 9, 4);
+    memcpy(s.seg_lf, p + 13, 4);
+    const uint8_t* map = p + 17;
+    for (int r = 0; r < s.mb_rows; r++) memcpy(&s.seg_map[static_cast<size_t>(r) * s.mb_cols], map + static_cast<size_t>(r) * mw, s.mb_cols);
+    p += 5 + seg_len;
+  } else if (seg_opt != TAG_OPT_EMPTY) {
     return false;
   }
+  if (p >= end) return false;
+  const uint8_t filt_opt = *p++;
+  if (filt_opt == TAG_OPT_FULL) {
+    if (end - p < 13 || p[0] != TAG_FILT_ADJ || get_u32(p + 1) != 8) return false;
+    s.lf_adj_enabled = true;
+    memcpy(s.ref_adj, p + 5, 4);
+    memcpy(s.mode_adj, p + 9, 4);
+    p += 13;
+  } else if (filt_opt != TAG_OPT_EMPTY) {
+    return false;
+  }
+  if (p != end) return false;
+  if (used) *used = 5 + body;
   out = s;
   return true;
 }

@@ -36,10 +36,10 @@ struct State {
   void reset_probs();
   bool operator==(const State& o) const;  // DecoderState::operator==, decoder.cc:257-264
   uint64_t hash() const;
-  // DecoderState::serialize / deserialize (decoder.cc:266-330) as a flat little-endian blob
-  // (own layout, versioned; carries exactly the fields operator== compares)
+  // DecoderState::serialize / deserialize (decoder.cc:283-330) in the reference's tag-length-value format
+  // (enc_state_serializer.hh): byte-compatible with the reference's EncoderStateSerializer / Deserializer
   std::vector<uint8_t> serialize() const;
-  static bool deserialize(const uint8_t* data, size_t len, State& out);
+  static bool deserialize(const uint8_t* data, size_t len, State& out, size_t* used = nullptr);
 };
 
 // Growable array whose storage comes from a pluggable allocator, so that the engine can

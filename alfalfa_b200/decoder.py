@@ -153,7 +153,7 @@ class DecoderState:
         return int(self.L.vp8gpu_state_hash(self.h))
 
     def serialize(self):
-        """DecoderState::serialize: a flat blob (vp8gpu_state_serialize)"""
+        """DecoderState::serialize (decoder.cc:283-314): the reference's DECODER_STATE record"""
         n = self.L.vp8gpu_state_serialize(self.h, None, 0)
         buf = (C.c_uint8 * n)()
         assert self.L.vp8gpu_state_serialize(self.h, buf, n) == n
@@ -234,6 +234,21 @@ class Decoder:
         h = C.c_void_p()
         check(self.L.vp8gpu_decoder_clone(self.h, C.byref(h)), self.ctx.h, "decoder_clone")
         return Decoder(self.ctx, h)
+
+    def serialize(self):
+        """Decoder::serialize (decoder.cc:54-69): the reference's tag-length-value blob (state + LAST raster)"""
+        size = C.c_size_t(0)
+        self.L.vp8gpu_decoder_serialize(self.h, None, 0, C.byref(size))
+        buf = (C.c_uint8 * size.value)()
+        check(self.L.vp8gpu_decoder_serialize(self.h, buf, size.value, C.byref(size)), self.ctx.h, "decoder_serialize")
+        return bytes(buf)
+
+    @staticmethod
+    def deserialize(ctx, blob):
+        """Decoder::deserialize (decoder.cc:71-81); golden = alternative = last as in the reference"""
+        h = C.c_void_p()
+        check(ctx.L.vp8gpu_decoder_deserialize(ctx.h, blob, len(blob), C.byref(h)), ctx.h, "decoder_deserialize")
+        return Decoder(ctx, h)
 
     def get_state(self):
         return DecoderState(_h=C.c_void_p(self.L.vp8gpu_decoder_state(self.h)), _owned=False).clone()

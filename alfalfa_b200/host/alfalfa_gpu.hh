@@ -104,7 +104,7 @@ class DecoderState {
   bool operator==(const DecoderState& o) const { return vp8gpu_state_equal(get(), o.get()); }
   bool operator!=(const DecoderState& o) const { return !(*this == o); }
   size_t hash() const { return vp8gpu_state_hash(get()); }
-  // DecoderState::serialize / deserialize (decoder.cc:266-330): flat blob
+  // DecoderState::serialize / deserialize (decoder.cc:283-330): the reference's DECODER_STATE record
   std::vector<uint8_t> serialize() const {
     std::vector<uint8_t> b(vp8gpu_state_serialize(get(), nullptr, 0));
     vp8gpu_state_serialize(get(), b.data(), b.size());
@@ -200,6 +200,19 @@ class Decoder {
   RasterHandle parse_and_decode_frame(const Chunk& compressed_frame) {
     auto out = get_frame_output(compressed_frame);
     return out.first ? out.second : RasterHandle();
+  }
+  // Decoder::serialize / deserialize (decoder.cc:54-81): the reference's EncoderStateSerializer format
+  std::vector<uint8_t> serialize() const {
+    size_t n = 0;
+    vp8gpu_decoder_serialize(h_, nullptr, 0, &n);
+    std::vector<uint8_t> b(n);
+    check(vp8gpu_decoder_serialize(h_, b.data(), b.size(), &n), ctx_.get(), "decoder_serialize");
+    return b;
+  }
+  static Decoder deserialize(const Context& ctx, const std::vector<uint8_t>& blob, uint16_t width, uint16_t height) {
+    vp8gpu_decoder* d = nullptr;
+    check(vp8gpu_decoder_deserialize(ctx.get(), blob.data(), blob.size(), &d), ctx.get(), "decoder_deserialize");
+    return Decoder(ctx, d, width, height);
   }
   DecoderState get_state() const { return DecoderState(vp8gpu_decoder_state(h_)); }
   References get_references() const {

@@ -227,9 +227,9 @@ int vp8gpu_state_clone(const vp8gpu_state* s, vp8gpu_state** out);
 void vp8gpu_state_destroy(vp8gpu_state* s);
 int vp8gpu_state_equal(const vp8gpu_state* a, const vp8gpu_state* b);
 uint64_t vp8gpu_state_hash(const vp8gpu_state* s);
-/* DecoderState::serialize / deserialize (decoder.cc:266-330): the state as a flat blob (own versioned
- * layout; the fields operator== compares).  serialize returns the size needed and writes only if
- * cap suffices.  Together with vp8gpu_frame_export / _import this moves a Decoder between processes
+/* DecoderState::serialize / deserialize (decoder.cc:283-330): the DECODER_STATE record of the reference's
+ * tag-length-value format (enc_state_serializer.hh), byte-compatible with the reference.  serialize returns
+ * the size needed and writes only if cap suffices.  Together with vp8gpu_frame_export / _import this moves a Decoder between processes
  * or GPUs (alfalfa_b200/multigpu.py broadcast_decoder: NCCL broadcast of the reference rasters). */
 size_t vp8gpu_state_serialize(const vp8gpu_state* s, uint8_t* out, size_t cap);
 int vp8gpu_state_deserialize(const uint8_t* data, size_t len, vp8gpu_state** out);
@@ -307,6 +307,15 @@ int vp8gpu_decoder_lane(const vp8gpu_decoder* d);
  * decoders hash equally, which is what the reference uses it for (frame-graph bookkeeping, minihash
  * fields of IVF frames).  minihash = its 32-bit fold. */
 int vp8gpu_decoder_hash(vp8gpu_decoder* d, uint64_t* out);
+/* Decoder::serialize / Decoder::deserialize (decoder.cc:54-81) in the reference's own tag-length-value
+ * format (decoder/enc_state_serializer.hh:43-190): DECODER { DECODER_STATE { size, PROB_TABLE, optional
+ * SEGM_ABS|SEGM_REL, optional FILT_ADJ } REFERENCES { display size, REF_LAST { Y, U, V planes of the
+ * macroblock-aligned raster } } }.  Blobs are interchangeable with the reference's (xc-enc -O / -I state files,
+ * EncoderStateDeserializer::build<Decoder>): as there, only the LAST reference travels and a deserialised
+ * Decoder has golden = alternative = last.  serialize: VP8GPU_ERR_NOMEM if cap is too small (*size = needed).
+ * vp8gpu_state_serialize / _deserialize carry the DECODER_STATE record alone. */
+int vp8gpu_decoder_serialize(vp8gpu_decoder* d, uint8_t* out, size_t cap, size_t* size);
+int vp8gpu_decoder_deserialize(vp8gpu_ctx* ctx, const uint8_t* data, size_t len, vp8gpu_decoder** out);
 /* Decoder::operator== (decoder.cc:153): state equal and the three rasters pixel-equal. */
 int vp8gpu_decoder_equal(vp8gpu_decoder* a, vp8gpu_decoder* b, int* equal);
 

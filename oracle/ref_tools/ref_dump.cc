@@ -13,6 +13,10 @@
  *   ref_dump full  FILE.ivf OUT.bin    every frame, MB-aligned planes, pre+post loop filter
  *   ref_dump time  FILE.ivf [REPS] [FIRST] [COUNT]
  *                                      one JSON line with seconds per phase (best of REPS)
+ *   ref_dump state FILE.ivf N          decode the first N frames, then Decoder::serialize (decoder.cc:54-69,
+ *                                      the EncoderStateSerializer format of xc-enc -O) -> stdout
+ *   ref_dump resume STATE FILE.ivf N   Decoder::deserialize( STATE ) (decoder.cc:71-81), then decode frames
+ *                                      N.. of the file; display rectangle of shown frames -> stdout
  */
 #include <chrono>
 #include <cstdio>
@@ -21,6 +25,7 @@
 #include <vector>
 
 #include "decoder.hh"
+#include "enc_state_serializer.hh"
 #include "decoder_state.hh"
 #include "frame.hh"
 #include "ivf.hh"
@@ -70,6 +75,16 @@ int main(int argc, char** argv) {
   try {
     if (argc < 3) { cerr << "usage: ref_dump shown|full|time FILE.ivf [...]\n"; return 2; }
     const string mode = argv[1];
+    if (mode == "resume") {
+      if (argc < 5) { cerr << "resume needs STATE FILE.ivf N\n"; return 2; }
+      IVF file(argv[3]);
+      Decoder decoder = EncoderStateDeserializer::build<Decoder>(string(argv[2]));
+      for (uint32_t i = atoi(argv[4]); i < file.frame_count(); i++) {
+        const Optional<RasterHandle> raster = decoder.parse_and_decode_frame(file.frame(i));
+        if (raster.initialized()) raster.get().get().dump(stdout);
+      }
+      return 0;
+    }
     IVF ivf(argv[2]);
     const uint16_t w = ivf.width(), h = ivf.height();
     FILE* full = nullptr;
@@ -80,6 +95,11 @@ int main(int argc, char** argv) {
     }
     int reps = 1;
     uint32_t first = 0, count = ivf.frame_count();
+    if (mode == "state") {
+      if (argc < 4) { cerr << "state needs N\n"; return 2; }
+      count = atoi(argv[3]);
+      if (count > ivf.frame_count()) count = ivf.frame_count();
+    }
     if (mode == "time") {
       if (argc > 3) reps = atoi(argv[3]);
       if (argc > 4) first = atoi(argv[4]);
@@ -99,6 +119,11 @@ int main(int argc, char** argv) {
         if (uc.key_frame()) run_frame<KeyFrame>(state, refs, uc, full, mode == "shown", ph, i);
         else run_frame<InterFrame>(state, refs, uc, full, mode == "shown", ph, i);
         decoded++;
+      }
+      if (mode == "state") {
+        EncoderStateSerializer odata;
+        Decoder(state, refs).serialize(odata);
+        odata.write(stdout);
       }
       double total = ph.parse + ph.recon + ph.lf;
       if (total < best_total) { best_total = total; best = ph; }
