@@ -329,6 +329,13 @@ def read_ivf(data):
     return w, h, frames
 
 
+def ivf_expected_decoder_minihash(data):
+    """IVF::expected_decoder_minihash (util/ivf.cc:46): header bytes 28..31"""
+    if len(data) < 32 or data[:4] != b"DKIF":
+        raise capi.Invalid(capi.ERR_INVALID, "missing IVF file header")
+    return struct.unpack_from("<I", data, 28)[0]
+
+
 class FilePlayer:
     """FilePlayer (player.cc:88-143): starts at the first key frame, advance() skips hidden frames."""
 
@@ -478,9 +485,12 @@ class Encoder:
         return RasterHandle(self.ctx, fid.value)
 
 
-def write_ivf(width, height, frames):
-    """util/ivf_writer.cc: 32-byte DKIF header + 12-byte frame headers"""
-    out = bytearray(b"DKIF" + struct.pack("<HH4sHHIIII", 0, 32, b"VP80", width, height, 30, 1, len(frames), 0))
+def write_ivf(width, height, frames, expected_decoder_minihash=0):
+    """util/ivf_writer.cc: 32-byte DKIF header + 12-byte frame headers.  Header bytes 28..31 carry ExCamera's
+    expected decoder entry minihash (IVFWriter::set_expected_decoder_entry_hash, ivf_writer.cc:92-99): the
+    minihash of the Decoder a chunk must be played into; 0 = not set."""
+    out = bytearray(b"DKIF" + struct.pack("<HH4sHHIIII", 0, 32, b"VP80", width, height, 30, 1, len(frames),
+                                          expected_decoder_minihash & 0xFFFFFFFF))
     for i, f in enumerate(frames):
         out += struct.pack("<IQ", len(f), i) + f
     return bytes(out)
