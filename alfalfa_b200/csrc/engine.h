@@ -17,6 +17,12 @@ struct Geom {
   int y_pitch, c_pitch;  // bytes
   uint32_t u_off, v_off; // byte offsets of the chroma planes
   uint32_t frame_bytes;
+  // Wavefront hand-over areas behind the pixels of every raster (zeroed once when the raster is allocated):
+  // rows of one frame pass their edges to the row below as 8-byte { data, epoch } words -- the flag travels
+  // in the same store as the data, so neither side needs a fence (kernels.cu "hand-over messages").
+  //   loop filter: [mb_rows][mb_cols + 1][32] words, intra prediction: [mb_rows][mb_cols][8] words
+  uint32_t msg_lf_off, msg_intra_off;
+  uint32_t alloc_bytes;  // pixels + both areas
 };
 
 // One frame's decode job as the kernels see it (an array of these lives in HBM).
@@ -80,8 +86,10 @@ struct TokJob {
 // Kernel launchers (kernels.cu, tokens.cu).  `stream` is a cudaStream_t passed as void* so this header
 // stays free of CUDA includes.  Return 0 or a cudaError_t value.
 int launch_inter(const DevJob* jobs, int njobs, const Geom& g, void* stream);
-int launch_intra(const DevJob* jobs, int njobs, const Geom& g, int* ticket, void* stream);
-int launch_loopfilter(const DevJob* jobs, int njobs, const Geom& g, int* ticket, void* stream);
+// `epoch`: a value no earlier launch on this context has used (Engine::next_epoch); it marks the hand-over
+// messages of this launch.  epoch == 0 selects the round-1 kernels (progress counters + acquire / release).
+int launch_intra(const DevJob* jobs, int njobs, const Geom& g, int* ticket, uint32_t epoch, void* stream);
+int launch_loopfilter(const DevJob* jobs, int njobs, const Geom& g, int* ticket, uint32_t epoch, void* stream);
 // token jobs sit at the start of equally spaced ring slots: slot (first + i) % nslots for block i
 int launch_tokens(const uint8_t* ring, size_t stride, int first, int count, int nslots, const Geom& g, void* stream);
 int launch_ssim(const uint8_t* a, const uint8_t* b, const Geom& g, float* d_windows, void* stream);

@@ -65,6 +65,13 @@ class Engine {
   int frame_retain(int id);
   int frame_release(int id);
   int frames_free();  // rasters the pool can still hand out
+  // marks the hand-over messages of one wavefront launch; never 0, never repeats within 2^32 launches
+  uint32_t next_epoch() {
+    if (legacy_wavefront_) return 0;
+    uint32_t e = ++epoch_;
+    if (e == 0) e = ++epoch_;
+    return e;
+  }
   int frame_upload(int id, const uint8_t* y, size_t ys, const uint8_t* u, const uint8_t* v, size_t cs);
   int frame_download(int id, uint8_t* y, size_t ys, uint8_t* u, uint8_t* v, size_t cs);
   int frame_download_display(int id, int lane, uint8_t* dst, size_t dst_size, bool wait);
@@ -166,6 +173,8 @@ class Engine {
   std::atomic<uint64_t> launches_{0};
   std::string err_;
   std::mutex err_mu_;
+  std::atomic<uint32_t> epoch_{0};
+  bool legacy_wavefront_ = false;  // VP8GPU_WAVEFRONT=legacy: round-1 kernels (A/B measurements)
 };
 
 }  // namespace vp8

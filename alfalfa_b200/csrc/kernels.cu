@@ -1209,6 +1209,8 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 16) k_loopfilter(const DevJob* 
   PROF_FLUSH(16);
 }
 
+#include "wavefront_ll.cuh"
+
 // ================================================================================================
 // ENCODER kernel: the reference's macroblock decision loop on the device.
 //   key frames    luma_mb_best_prediction_mode incl. the B_PRED trial (encode_intra.cc:83-161, 360-387),
@@ -1930,12 +1932,16 @@ int launch_inter(const DevJob* jobs, int njobs, const Geom& g, void* stream) {
   k_inter<<<grid, INTER_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(jobs, g);
   return (int)cudaGetLastError();
 }
-int launch_intra(const DevJob* jobs, int njobs, const Geom& g, int* ticket, void* stream) {
-  k_intra<<<(g.mb_rows * njobs + WF_WARPS - 1) / WF_WARPS, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream)>>>(jobs, njobs, g, ticket);
+int launch_intra(const DevJob* jobs, int njobs, const Geom& g, int* ticket, uint32_t epoch, void* stream) {
+  const int grid = (g.mb_rows * njobs + WF_WARPS - 1) / WF_WARPS;
+  if (epoch) k_intra_ll<<<grid, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream)>>>(jobs, njobs, g, ticket, epoch);
+  else k_intra<<<grid, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream)>>>(jobs, njobs, g, ticket);
   return (int)cudaGetLastError();
 }
-int launch_loopfilter(const DevJob* jobs, int njobs, const Geom& g, int* ticket, void* stream) {
-  k_loopfilter<<<(g.mb_rows * njobs + WF_WARPS - 1) / WF_WARPS, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream)>>>(jobs, njobs, g, ticket);
+int launch_loopfilter(const DevJob* jobs, int njobs, const Geom& g, int* ticket, uint32_t epoch, void* stream) {
+  const int grid = (g.mb_rows * njobs + WF_WARPS - 1) / WF_WARPS;
+  if (epoch) k_loopfilter_ll<<<grid, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream)>>>(jobs, njobs, g, ticket, epoch);
+  else k_loopfilter<<<grid, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream)>>>(jobs, njobs, g, ticket);
   return (int)cudaGetLastError();
 }
 
