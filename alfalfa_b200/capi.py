@@ -163,6 +163,13 @@ SYMBOLS = {
     "vp8gpu_serialize_frame": (C.c_int, [C.POINTER(EncodeHeader), _vp, _vp, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "vp8gpu_serialize_frame_ex": (C.c_int, [C.POINTER(EncodeHeader), C.POINTER(EncodeFeatures), _vp, _vp, _vp, _vp, C.c_size_t,
                                             C.POINTER(C.c_size_t)]),
+    "vp8gpu_comm_unique_id": (C.c_int, [_u8p]),
+    "vp8gpu_comm_create": (C.c_int, [_vp, C.c_int, C.c_int, _u8p, _pp]),
+    "vp8gpu_comm_destroy": (None, [_vp]),
+    "vp8gpu_comm_broadcast_frames": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int]),
+    "vp8gpu_comm_broadcast_bytes": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t]),
+    "vp8gpu_comm_rank": (C.c_int, [_vp]),
+    "vp8gpu_comm_size": (C.c_int, [_vp]),
     "vp8gpu_decode_ivf_stats": (None, [_vp, C.POINTER(C.c_double)]),
     "vp8gpu_decode_ivf": (C.c_int, [_vp, C.c_char_p, C.c_size_t, C.c_int, _u8p, C.c_size_t, C.POINTER(C.c_uint32),
                                     C.POINTER(C.c_uint32)]),

@@ -170,3 +170,79 @@ def broadcast_decoder(ctx, decoder, src, dist, local, make_decoder=None):
     for fr in rasters:
         fr.release()
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# The same hand-over through the C ABI (include/vp8gpu.h "the exchange step"): ncclBroadcast straight from /
+# into the rasters on the context's lane stream -- no torch tensors, no staging copies, no host synchronisation
+# on the raster path.  torch.distributed is only used once, to hand the NCCL id to the other ranks.
+# ------------------------------------------------------------------------------------------------
+class Comm:
+    """vp8gpu_comm: one NCCL communicator per context and rank set"""
+
+    def __init__(self, ctx, dist, local):
+        import ctypes as C
+
+        import torch
+        from . import capi
+        self.ctx, self.L = ctx, ctx.L
+        self.rank, self.size = dist.get_rank(), dist.get_world_size()
+        uid = (C.c_uint8 * 128)()
+        if self.rank == 0:
+            capi.check(self.L.vp8gpu_comm_unique_id(uid), ctx.h, "comm_unique_id")
+        t = torch.tensor(list(bytes(uid)), dtype=torch.uint8, device=_device(dist, local))
+        dist.broadcast(t, 0)
+        uid = (C.c_uint8 * 128)(*t.cpu().tolist())
+        self.h = C.c_void_p()
+        capi.check(self.L.vp8gpu_comm_create(ctx.h, self.rank, self.size, uid, C.byref(self.h)), ctx.h, "comm_create")
+
+    def close(self):
+        if self.h:
+            self.L.vp8gpu_comm_destroy(self.h)
+            self.h = None
+
+    def broadcast_bytes(self, blob, src):
+        import ctypes as C
+        from . import capi
+        n = (C.c_uint32 * 1)(len(blob) if self.rank == src else 0)
+        capi.check(self.L.vp8gpu_comm_broadcast_bytes(self.h, src, n, 4), self.ctx.h, "comm_broadcast_bytes")
+        buf = (C.c_uint8 * max(1, n[0]))()
+        if self.rank == src:
+            C.memmove(buf, blob, len(blob))
+        capi.check(self.L.vp8gpu_comm_broadcast_bytes(self.h, src, buf, n[0]), self.ctx.h, "comm_broadcast_bytes")
+        return bytes(buf[:n[0]])
+
+    def broadcast_frames(self, rasters, src, lane=0):
+        """collective; `rasters` = RasterHandles: the ones to send on src, freshly allocated ones elsewhere"""
+        import ctypes as C
+        from . import capi
+        ids = (C.c_int32 * len(rasters))(*[r.id for r in rasters])
+        capi.check(self.L.vp8gpu_comm_broadcast_frames(self.h, src, lane, ids, len(rasters)), self.ctx.h, "comm_broadcast_frames")
+
+
+def broadcast_decoder_capi(ctx, comm, decoder, src):
+    """broadcast_decoder over the C ABI communicator: returns src's decoder on src, a new Decoder elsewhere"""
+    from .decoder import Decoder, DecoderState
+    refs, head = None, b""
+    if comm.rank == src:
+        refs = decoder.get_references()
+        uniq, index = reference_plan([r.id for r in refs])
+        by_id = {r.id: r for r in refs}
+        head = struct.pack("<4B", len(uniq), *index) + decoder.get_state().serialize()
+    head = comm.broadcast_bytes(head, src)
+    n_uniq, index = head[0], list(head[1:4])
+    if comm.rank == src:
+        rasters = [by_id[u] for u in uniq]
+        lane = ctx.L.vp8gpu_decoder_lane(decoder.h)
+    else:
+        rasters = [ctx.alloc_frame() for _ in range(n_uniq)]
+        lane = 0
+    comm.broadcast_frames(rasters, src, lane)   # queued on the lane stream; later decodes order themselves after it
+    if comm.rank == src:
+        for r in refs:
+            r.release()
+        return decoder
+    out = Decoder.from_state(ctx, DecoderState.deserialize(head[4:]), tuple(rasters[i] for i in index))
+    for fr in rasters:
+        fr.release()
+    return out

@@ -319,6 +319,26 @@ int vp8gpu_decoder_deserialize(vp8gpu_ctx* ctx, const uint8_t* data, size_t len,
 /* Decoder::operator== (decoder.cc:153): state equal and the three rasters pixel-equal. */
 int vp8gpu_decoder_equal(vp8gpu_decoder* a, vp8gpu_decoder* b, int* equal);
 
+/* ---- the exchange step: reference rasters between GPUs (References, decoder.hh:123-141) ----
+ * GOPs and streams shard across GPUs without any exchange.  A GOP that continues on another GPU (a long
+ * single-GOP stream split across ranks, BASELINE.json configs[3]) needs the producer's reference rasters: they
+ * are broadcast device to device with NCCL over NVLink, queued on the context's lane stream between the kernels
+ * that wrote them and the kernels that will read them (no host synchronisation, no staging).  One communicator
+ * per context and rank set, created collectively like ncclCommInitRank: rank 0 makes the 128-byte id
+ * (vp8gpu_comm_unique_id) and hands it to the other ranks by whatever channel the caller has.  NCCL itself is
+ * resolved at run time; without it these calls return VP8GPU_ERR_UNSUPPORTED.
+ *   vp8gpu_comm_broadcast_frames  collective; ids[i] on the root = the rasters to send, on the other ranks =
+ *                                 rasters from vp8gpu_frame_alloc that receive them (same order everywhere)
+ *   vp8gpu_comm_broadcast_bytes   collective, synchronous: a small host buffer (vp8gpu_state_serialize output) */
+typedef struct vp8gpu_comm vp8gpu_comm;
+int vp8gpu_comm_unique_id(uint8_t out[128]);
+int vp8gpu_comm_create(vp8gpu_ctx* ctx, int rank, int nranks, const uint8_t unique_id[128], vp8gpu_comm** out);
+void vp8gpu_comm_destroy(vp8gpu_comm* comm);
+int vp8gpu_comm_broadcast_frames(vp8gpu_comm* comm, int root, int lane, const vp8gpu_frame_id* ids, int n);
+int vp8gpu_comm_broadcast_bytes(vp8gpu_comm* comm, int root, void* buf, size_t bytes);
+int vp8gpu_comm_rank(const vp8gpu_comm* comm);
+int vp8gpu_comm_size(const vp8gpu_comm* comm);
+
 /* ---- whole-stream helper (decoder/player.cc:60-143, FilePlayer) ----
  * Decode every frame of an in-memory IVF with `threads` host workers, one GOP (key frame
  * to next key frame) per task, each worker driving its own Decoder on its own lane.  The

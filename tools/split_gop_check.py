@@ -24,7 +24,7 @@ def main():
     rank, world, local, dist = multigpu.init()
     assert dist is not None, "run under torch.distributed.run with >= 2 ranks"
     w, h, frames = read_ivf(open(path, "rb").read())
-    split = int(sys.argv[2]) if len(sys.argv) > 2 else len(frames) // 2
+    split = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else len(frames) // 2
     ctx = Context(w, h, device=local, max_frames=32)
     # everybody: the whole stream alone (the truth on this rank)
     alone = Decoder(ctx)
@@ -41,11 +41,34 @@ def main():
             shown, r = dec.get_frame_output(f)
             assert hashlib.sha1(r.display_bytes()).hexdigest() == want[i]
             r.release()
+    # the hand-over through the C ABI communicator (ncclBroadcast straight between rasters on the lane stream);
+    # --torch uses the round-1 path (uint8 tensors + dist.broadcast + export / import copies) for comparison
+    use_torch = "--torch" in sys.argv
+    comm = None if use_torch else multigpu.Comm(ctx, dist, local)
+    exchange_us = None
+    if comm is not None:
+        # raster exchange alone, amortised: 50 broadcasts of one raster queued back to back on lane 0
+        probe = [ctx.alloc_frame()]
+        comm.broadcast_frames(probe, 0)
+        ctx.sync()
+        multigpu.barrier(dist)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            comm.broadcast_frames(probe, 0)
+        ctx.sync()
+        exchange_us = (time.perf_counter() - t0) / 50 * 1e6
+        probe[0].release()
     multigpu.barrier(dist)
     t0 = time.perf_counter()
-    dec = multigpu.broadcast_decoder(ctx, dec, 0, dist, local)
-    multigpu.barrier(dist)
+    if comm is not None:
+        dec = multigpu.broadcast_decoder_capi(ctx, comm, dec, 0)
+        t_queued = time.perf_counter() - t0
+        ctx.sync()
+    else:
+        dec = multigpu.broadcast_decoder(ctx, dec, 0, dist, local)
+        t_queued = time.perf_counter() - t0
     dt = time.perf_counter() - t0
+    multigpu.barrier(dist)
     bad = 0
     for i, f in enumerate(frames[split:], start=split):
         shown, r = dec.get_frame_output(f)
@@ -56,8 +79,12 @@ def main():
     if rank == 0:
         print(json.dumps({"check": "split GOP across GPUs", "ranks": world, "stream": os.path.basename(path),
                           "frames": len(frames), "split_at": split, "mismatches": int(total_bad),
-                          "handover_ms": dt * 1e3, "raster_bytes": ctx.frame_bytes, "backend": dist.get_backend()}))
+                          "handover_ms": dt * 1e3, "handover_queued_ms": t_queued * 1e3,
+                          "raster_exchange_us": exchange_us, "path": "torch tensors" if use_torch else "C ABI ncclBroadcast",
+                          "raster_bytes": ctx.frame_bytes, "backend": dist.get_backend()}))
     del dec, alone
+    if comm is not None:
+        comm.close()
     ctx.close()
     dist.destroy_process_group()
     sys.exit(1 if total_bad else 0)
