@@ -96,7 +96,8 @@ int Engine::create(int device, int width, int height, int max_frames, Engine** o
   g.msg_lf_off = (uint32_t)align_up((size_t)g.frame_bytes + 64, 256);  // + 64: slack read by staged window rows
   g.msg_intra_off = g.msg_lf_off + (uint32_t)((size_t)g.mb_rows * (g.mb_cols + 1) * 32 * 8);
   g.alloc_bytes = g.msg_intra_off + (uint32_t)((size_t)g.mb_rows * g.mb_cols * 8 * 8);
-  if (const char* v = getenv("VP8GPU_WAVEFRONT")) en->legacy_wavefront_ = strcmp(v, "legacy") == 0;
+  if (const char* v = getenv("VP8GPU_WAVEFRONT"))
+    en->ll_mask_ = !strcmp(v, "legacy") ? 0 : (!strcmp(v, "ll") ? 3 : (!strcmp(v, "lf-ll") ? 2 : (!strcmp(v, "intra-ll") ? 1 : en->ll_mask_)));
   if (max_frames <= 0) max_frames = 64;
   en->tmaps_ = tmap_arena_alloc(device, (size_t)max_frames * 384);
   if (!en->tmaps_) {
@@ -543,12 +544,12 @@ int Engine::build_and_launch(int lane, const DevJob* d_jobs, int* d_sync, int n,
   }
   if (between) CU(cudaEventRecord(between[0], s));
   if (any_intra) {
-    if (int e = launch_intra(d_jobs, n, g_, d_sync + 0, next_epoch(), s)) return cuda_fail((cudaError_t)e, "k_intra launch");
+    if (int e = launch_intra(d_jobs, n, g_, d_sync + 0, next_epoch(1), s)) return cuda_fail((cudaError_t)e, "k_intra launch");
     launches_++;
   }
   if (between) CU(cudaEventRecord(between[1], s));
   if (any_lf) {
-    if (int e = launch_loopfilter(d_jobs, n, g_, d_sync + 32, next_epoch(), s)) return cuda_fail((cudaError_t)e, "k_loopfilter launch");
+    if (int e = launch_loopfilter(d_jobs, n, g_, d_sync + 32, next_epoch(2), s)) return cuda_fail((cudaError_t)e, "k_loopfilter launch");
     launches_++;
   }
   return VP8GPU_OK;

@@ -66,8 +66,8 @@ class Engine {
   int frame_release(int id);
   int frames_free();  // rasters the pool can still hand out
   // marks the hand-over messages of one wavefront launch; never 0, never repeats within 2^32 launches
-  uint32_t next_epoch() {
-    if (legacy_wavefront_) return 0;
+  uint32_t next_epoch(int kernel_bit = 3) {
+    if (!(ll_mask_ & kernel_bit)) return 0;
     uint32_t e = ++epoch_;
     if (e == 0) e = ++epoch_;
     return e;
@@ -174,7 +174,9 @@ class Engine {
   std::string err_;
   std::mutex err_mu_;
   std::atomic<uint32_t> epoch_{0};
-  bool legacy_wavefront_ = false;  // VP8GPU_WAVEFRONT=legacy: round-1 kernels (A/B measurements)
+  // which wavefront kernels use hand-over messages (bit 0 intra prediction, bit 1 loop filter); the others run
+  // the round-1 kernels (progress counters).  VP8GPU_WAVEFRONT = legacy | ll | intra-ll | lf-ll for A/B runs.
+  int ll_mask_ = 1;
 };
 
 }  // namespace vp8

@@ -45,12 +45,22 @@ __device__ __forceinline__ uint32_t wait_msg(const unsigned long long* p, Msg m,
   unsigned ns = 32;
   for (;;) {
     const bool ok = !need || m.f == epoch;
-    if (__all_sync(0xffffffffu, ok)) break;
-    if (!ok) {
-      __nanosleep(ns);
-      m = ld_msg(p);
+    const unsigned late = __ballot_sync(0xffffffffu, !ok);
+    if (!late) break;
+    // one lane watches its word (one 8-byte request per retry instead of up to 32); the words of a message
+    // are written by one store instruction and arrive together, so when it turns valid the others are
+    // reloaded once -- and every lane still validates its own flag before using its data
+    const int watcher = __ffs(late) - 1;
+    if ((threadIdx.x & 31) == watcher) {
+      for (;;) {
+        __nanosleep(ns);
+        m = ld_msg(p);
+        if (m.f == epoch) break;
+        if (ns < 256) ns += ns;
+      }
     }
-    if (ns < 256) ns += ns;
+    __syncwarp();
+    if (!ok && (threadIdx.x & 31) != watcher) m = ld_msg(p);
   }
   return need ? m.d : 0u;
 }
@@ -363,7 +373,7 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 18) k_intra_ll(const DevJob* __
 // lanes 16-31: plane p, line j, word w of chroma (x = 8c - 4 + 4w); A(row, cols) carries the last 4 columns
 // in its words w = 0.  The row below needs x in [16c, 16c + 16) for its macroblock c: words 1-3 of A(c) and
 // word 0 of A(c + 1), i.e. one new message per step, requested one step ahead.
-__global__ void __launch_bounds__(32 * WF_WARPS, 16) k_loopfilter_ll(const DevJob* __restrict__ jobs, int njobs, Geom g, int* ticket,
+__global__ void __launch_bounds__(32 * WF_WARPS, 14) k_loopfilter_ll(const DevJob* __restrict__ jobs, int njobs, Geom g, int* ticket,
                                                                       uint32_t epoch) {
   constexpr int YS = 20, CSZ = 12;
   __shared__ __align__(16) uint8_t s_ry[WF_WARPS][20 * YS];
@@ -388,8 +398,10 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 16) k_loopfilter_ll(const DevJo
   const int y_lo = row > 0 ? 0 : 4;           // first region row that exists in the frame
   const int y_hi = last_row ? 20 : 16;        // luma region rows this warp writes: the bottom 4 lines of a
   const int yc_hi = last_row ? 12 : 8;        // macroblock row are final only after the row below filtered them
-  unsigned long long* const msg_out = reinterpret_cast<unsigned long long*>(J.out + g.msg_lf_off) + ((size_t)row * (cols + 1)) * 32 + lane;
-  const unsigned long long* const msg_in = msg_out - ((size_t)(cols + 1)) * 32;  // only dereferenced when row > 0
+  // message c of row r (this lane's word); derived from Y on use instead of being kept in registers
+  auto msg_at = [&](int r, int c) {
+    return reinterpret_cast<unsigned long long*>(Y + g.msg_lf_off) + ((size_t)r * (cols + 1) + c) * 32 + lane;
+  };
 
   // this lane's word in a message / in the top 4 lines of the region
   const bool luma_w = lane < 16;
@@ -422,30 +434,23 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 16) k_loopfilter_ll(const DevJo
     }
   };
   prefetch_own(0);
-  // of the record the filter needs tok_cnt (word 1) and lf_level / flags (word 2)
-  uint32_t rec_y = __ldg(reinterpret_cast<const uint32_t*>(row_mbs) + 1), rec_z = __ldg(reinterpret_cast<const uint32_t*>(row_mbs) + 2);
   uint32_t a0 = 0;
   Msg spec;
   spec.d = 0, spec.f = 0;
   if (row > 0) {
-    a0 = wait_msg(msg_in, ld_msg(msg_in), true, epoch);
-    spec = ld_msg(msg_in + 32);
+    a0 = wait_msg(msg_at(row - 1, 0), ld_msg(msg_at(row - 1, 0)), true, epoch);
+    spec = ld_msg(msg_at(row - 1, 1));
   }
 
   PROF_DECL;
   for (int col = 0; col < cols; col++) {
     PROF(7);
-    const int mb_tok_cnt = rec_y & 0xFFFF, mb_level = (rec_z >> 16) & 0xFF, mb_flags = rec_z >> 24;
-    if (col + 1 < cols) {
-      rec_y = __ldg(reinterpret_cast<const uint32_t*>(row_mbs + col + 1) + 1);
-      rec_z = __ldg(reinterpret_cast<const uint32_t*>(row_mbs + col + 1) + 2);
-    }
     PROF(0);
     // ---- top 4 lines (final output of the row above): words 1.. of A(col), word 0 of A(col + 1) ----
     uint32_t top = 0;
     if (row > 0) {
-      const uint32_t a1 = wait_msg(msg_in + (size_t)(col + 1) * 32, spec, true, epoch);
-      if (col + 2 <= cols) spec = ld_msg(msg_in + (size_t)(col + 2) * 32);  // in flight while this macroblock is filtered
+      const uint32_t a1 = wait_msg(msg_at(row - 1, col + 1), spec, true, epoch);
+      if (col + 2 <= cols) spec = ld_msg(msg_at(row - 1, col + 2));  // in flight while this macroblock is filtered
       const uint32_t t0 = __shfl_sync(0xffffffffu, a0, (line0 + ((mw + 1) & (words - 1))) & 31);
       const uint32_t t1 = __shfl_sync(0xffffffffu, a1, line0 & 31);
       top = mw == words - 1 ? t1 : t0;
@@ -478,6 +483,11 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 16) k_loopfilter_ll(const DevJo
     PROF(2);
     if (col + 1 < cols) prefetch_own(col + 1);  // in flight while this macroblock is filtered
 
+    // of the record the filter needs tok_cnt (word 1) and lf_level / flags (word 2); four records share a
+    // 128-byte line of the read-only cache, so this is rarely a round trip
+    const uint32_t rec_y = __ldg(reinterpret_cast<const uint32_t*>(row_mbs + col) + 1);
+    const uint32_t rec_z = __ldg(reinterpret_cast<const uint32_t*>(row_mbs + col) + 2);
+    const int mb_tok_cnt = rec_y & 0xFFFF, mb_level = (rec_z >> 16) & 0xFF, mb_flags = rec_z >> 24;
     const int level = J.lf_force ? J.lf_force : mb_level;
     if (level != 0) {
       const vp8m::LfParams lp = vp8m::lf_params(level, J.sharpness, J.key_frame);
@@ -520,8 +530,8 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 16) k_loopfilter_ll(const DevJo
     const bool last_col = col == cols - 1;
     if (!last_row) {
       const uint8_t* src = luma_w ? ry + (16 + mj) * YS : rc[mp] + (8 + mj) * CSZ;
-      st_msg(msg_out + (size_t)col * 32, *reinterpret_cast<const uint32_t*>(src + 4 * mw), epoch);
-      if (last_col) st_msg(msg_out + (size_t)cols * 32, *reinterpret_cast<const uint32_t*>(src + (luma_w ? 16 : 8)), epoch);
+      st_msg(msg_at(row, col), *reinterpret_cast<const uint32_t*>(src + 4 * mw), epoch);
+      if (last_col) st_msg(msg_at(row, cols), *reinterpret_cast<const uint32_t*>(src + (luma_w ? 16 : 8)), epoch);
     }
     // ---- write back: region columns 0..15 (x -4..11); the last 4 columns travel with the next macroblock ----
     const int x_lo = col > 0 ? 0 : 1;
