@@ -6,6 +6,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/resource.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <condition_variable>
@@ -1095,7 +1098,12 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     }
     return k;
   };
+  // The dispatchers feed the device and must not queue behind dozens of parsing workers for a CPU: the workers
+  // run at a lower priority (per-thread nice on Linux; VP8GPU_WORKER_NICE overrides, 0 = leave alone).
+  int worker_nice = 5;
+  if (const char* v = getenv("VP8GPU_WORKER_NICE")) worker_nice = atoi(v);
   auto worker_dev = [&](int tid) {
+    if (worker_nice > 0) setpriority(PRIO_PROCESS, (id_t)syscall(SYS_gettid), worker_nice);
     cudaSetDevice(e->device());
     double t_parse = 0, t_slot = 0, t_dma = 0;
     State state(w, h);
@@ -1270,6 +1278,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
       cudaEvent_t a, b;
       int lane, n;
       double host_t;
+      cudaEvent_t mid[3] = {nullptr, nullptr, nullptr};  // kernels start, after k_inter, after k_intra
     };
     std::vector<Trace> trace;
     const bool tracing = getenv("VP8GPU_TRACE") != nullptr;
@@ -1348,9 +1357,10 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
         e->ensure_lane(lane);
         cudaEventCreate(&tr.a);
         cudaEventCreate(&tr.b);
+        for (cudaEvent_t& m : tr.mid) cudaEventCreate(&m);
         cudaEventRecord(tr.a, e->stream(lane));
       }
-      int rc = e->submit(lane, hj.data(), (int)hj.size(), nullptr);
+      int rc = e->submit(lane, hj.data(), (int)hj.size(), nullptr, tracing ? tr.mid + 1 : nullptr);
       if (tracing) {
         cudaEventRecord(tr.b, e->stream(lane));
         trace.push_back(tr);
@@ -1388,8 +1398,11 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
       // per batch: device time from "stream reaches the batch" to "its kernels are done", and the
       // device-side gap to the previous batch of this dispatcher
       double sum_ms = 0, sum_gap = 0, first_host = trace.front().host_t, last_host = trace.back().host_t;
+      double sum_intra = 0, sum_lf = 0;
       float ms = 0;
       for (size_t i = 0; i < trace.size(); i++) {
+        if (cudaEventElapsedTime(&ms, trace[i].mid[1], trace[i].mid[2]) == cudaSuccess) sum_intra += ms;
+        if (cudaEventElapsedTime(&ms, trace[i].mid[2], trace[i].b) == cudaSuccess) sum_lf += ms;
         cudaEventElapsedTime(&ms, trace[i].a, trace[i].b);
         sum_ms += ms;
         if (i) {
@@ -1398,11 +1411,14 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
         }
       }
       fprintf(stderr, "[trace] dispatcher %d: %zu batches, avg %.2f frames, device %.3f ms per batch, end-to-end period %.3f ms, "
-              "host span %.1f ms\n", di, trace.size(), n_jobs / n_batches, sum_ms / trace.size(),
-              trace.size() > 1 ? sum_gap / (trace.size() - 1) : 0.0, (last_host - first_host) * 1e3);
+              "host span %.1f ms; k_intra %.3f ms, k_loopfilter %.3f ms per batch\n", di, trace.size(), n_jobs / n_batches,
+              sum_ms / trace.size(), trace.size() > 1 ? sum_gap / (trace.size() - 1) : 0.0, (last_host - first_host) * 1e3,
+              sum_intra / trace.size(), sum_lf / trace.size());
       for (Trace& t : trace) {
         cudaEventDestroy(t.a);
         cudaEventDestroy(t.b);
+        for (cudaEvent_t m : t.mid)
+          if (m) cudaEventDestroy(m);
       }
     }
     std::lock_guard<std::mutex> lk(stats_mu);

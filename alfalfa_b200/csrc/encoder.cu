@@ -628,7 +628,10 @@ int vp8gpu_encoder_reconstruction(vp8gpu_encoder* enc, vp8gpu_frame_id* out) {
 // Encoder::export_decoder (encoder.hh:378): a Decoder in the state a receiver is in after the frames emitted
 // so far -- DecoderState + the three references (shared, not copied)
 int vp8gpu_encoder_export_decoder(vp8gpu_encoder* enc, vp8gpu_decoder** out) {
-  if (!enc || !out || !enc->has_state) return VP8GPU_ERR_LOGIC;
+  if (!enc || !out) return VP8GPU_ERR_LOGIC;
+  // an Encoder that has not emitted a frame yet exports the Decoder it was built with: a fresh one
+  // (Encoder( width, height, ... ) holds DecoderState( width, height ) and blank References, encoder.cc:68-90)
+  if (!enc->has_state) return vp8gpu_decoder_create(enc->ctx, out);
   const std::vector<uint8_t> blob = enc->dec_state->serialize();
   vp8gpu_state* st = nullptr;
   int rc = vp8gpu_state_deserialize(blob.data(), blob.size(), &st);

@@ -93,11 +93,12 @@ int Engine::create(int device, int width, int height, int max_frames, Engine** o
   g.u_off = (uint32_t)((size_t)g.y_pitch * g.H);
   g.v_off = g.u_off + (uint32_t)((size_t)g.c_pitch * (g.H / 2));
   g.frame_bytes = g.v_off + (uint32_t)((size_t)g.c_pitch * (g.H / 2));
-  g.msg_lf_off = (uint32_t)align_up((size_t)g.frame_bytes + 64, 256);  // + 64: slack read by staged window rows
-  g.msg_intra_off = g.msg_lf_off + (uint32_t)((size_t)g.mb_rows * (g.mb_cols + 1) * 32 * 8);
-  g.alloc_bytes = g.msg_intra_off + (uint32_t)((size_t)g.mb_rows * g.mb_cols * 8 * 8);
   if (const char* v = getenv("VP8GPU_WAVEFRONT"))
     en->ll_mask_ = !strcmp(v, "legacy") ? 0 : (!strcmp(v, "ll") ? 3 : (!strcmp(v, "lf-ll") ? 2 : (!strcmp(v, "intra-ll") ? 1 : en->ll_mask_)));
+  // hand-over areas only for the kernels that use them (the loop filter's is two thirds of a raster)
+  g.msg_lf_off = (uint32_t)align_up((size_t)g.frame_bytes + 64, 256);  // + 64: slack read by staged window rows
+  g.msg_intra_off = g.msg_lf_off + ((en->ll_mask_ & 2) ? (uint32_t)((size_t)g.mb_rows * (g.mb_cols + 1) * 32 * 8) : 0u);
+  g.alloc_bytes = g.msg_intra_off + ((en->ll_mask_ & 1) ? (uint32_t)((size_t)g.mb_rows * g.mb_cols * 8 * 8) : 0u);
   if (max_frames <= 0) max_frames = 64;
   en->tmaps_ = tmap_arena_alloc(device, (size_t)max_frames * 384);
   if (!en->tmaps_) {
@@ -192,7 +193,7 @@ int Engine::frame_alloc(int* id) {
     CU(cudaSetDevice(device_));
     CU(cudaMalloc(&f.dev, g_.alloc_bytes));
     // the hand-over areas must never hold a value that a later launch could take for its epoch
-    CU(cudaMemset(f.dev + g_.msg_lf_off, 0, g_.alloc_bytes - g_.msg_lf_off));
+    if (g_.alloc_bytes > g_.msg_lf_off) CU(cudaMemset(f.dev + g_.msg_lf_off, 0, g_.alloc_bytes - g_.msg_lf_off));
     if (int rc = make_tensor_maps(i)) return rc;
   }
   free_.pop_back();
@@ -666,7 +667,7 @@ int Engine::token_ring_result(TokenRing* r, int slot, cudaStream_t s, uint32_t r
   return VP8GPU_OK;
 }
 
-int Engine::submit(int lane, const HostJob* jobs, int n, cudaEvent_t consumed) {
+int Engine::submit(int lane, const HostJob* jobs, int n, cudaEvent_t consumed, cudaEvent_t* between) {
   if (n <= 0) return VP8GPU_OK;
   if (int rc = ensure_lane(lane)) return rc;
   CU(cudaSetDevice(device_));
@@ -763,7 +764,7 @@ int Engine::submit(int lane, const HostJob* jobs, int n, cudaEvent_t consumed) {
     if (j.consumed) CU(cudaEventRecord(j.consumed, s));
   }
   if (consumed) CU(cudaEventRecord(consumed, s));
-  if (int rc = build_and_launch(lane, reinterpret_cast<const DevJob*>(st.dev), d_sync, n, any_inter, any_intra, any_lf))
+  if (int rc = build_and_launch(lane, reinterpret_cast<const DevJob*>(st.dev), d_sync, n, any_inter, any_intra, any_lf, between))
     return rc;
   {
     std::lock_guard<std::mutex> lk(mu_);

@@ -88,7 +88,8 @@ class Engine {
 
   // decode n frames in one set of launches on `lane`; host arrays must stay valid until the
   // returned event (*consumed, optional) has fired (pinned) or are consumed on return (pageable)
-  int submit(int lane, const HostJob* jobs, int n, cudaEvent_t consumed);
+  // `between` (optional, diagnostics): two events recorded after k_inter and after k_intra
+  int submit(int lane, const HostJob* jobs, int n, cudaEvent_t consumed, cudaEvent_t* between = nullptr);
 
   // device-side token decoding
   TokenRing token_ring_layout(size_t max_frame_bytes) const;  // offsets and capacities only
