@@ -9,6 +9,7 @@
 #include "engine.hpp"
 
 #include <cuda.h>  // CUtensorMap types only: the driver entry point is fetched through the runtime
+#include <stdlib.h>
 #include <string.h>
 
 namespace vp8 {
@@ -68,6 +69,11 @@ int Engine::create(int device, int width, int height, int max_frames, Engine** o
     if (err) *err = "bad frame size";
     return VP8GPU_ERR_LOGIC;
   }
+  // vp8gpu_decode_ivf keeps hundreds of streams busy (per worker: uploads, token kernels that run for tens of
+  // milliseconds one after the other); with the default 8 hardware work queues the short pixel batches of the
+  // dispatcher lanes queue behind them (false dependencies between streams that share a queue).  Ask for the
+  // maximum; only effective if this is the process's first CUDA call, and never overrides the user's setting.
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || device < 0 || device >= ndev) {
@@ -175,7 +181,11 @@ int Engine::ensure_lane(int lane) {
   std::lock_guard<std::mutex> lk(mu_);
   CU(cudaSetDevice(device_));
   if (!lanes_[lane]) {
-    CU(cudaStreamCreateWithFlags(&lanes_[lane], cudaStreamNonBlocking));
+    // the lanes carry the latency-critical pixel batches: highest priority, so that their thread blocks are
+    // placed ahead of the long-running token kernels' (lower number = higher priority)
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    CU(cudaStreamCreateWithPriority(&lanes_[lane], cudaStreamNonBlocking, prio_hi));
     CU(cudaStreamCreateWithFlags(&lanes_[kMaxLanes + lane], cudaStreamNonBlocking));
   }
   return VP8GPU_OK;
