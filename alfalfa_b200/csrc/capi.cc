@@ -1278,7 +1278,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
       cudaEvent_t a, b;
       int lane, n;
       double host_t;
-      cudaEvent_t mid[3] = {nullptr, nullptr, nullptr};  // kernels start, after k_inter, after k_intra
+      cudaEvent_t mid[4] = {nullptr, nullptr, nullptr, nullptr};  // -, after k_inter, after k_intra, before k_inter
     };
     std::vector<Trace> trace;
     const bool tracing = getenv("VP8GPU_TRACE") != nullptr;
@@ -1398,9 +1398,11 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
       // per batch: device time from "stream reaches the batch" to "its kernels are done", and the
       // device-side gap to the previous batch of this dispatcher
       double sum_ms = 0, sum_gap = 0, first_host = trace.front().host_t, last_host = trace.back().host_t;
-      double sum_intra = 0, sum_lf = 0;
+      double sum_intra = 0, sum_lf = 0, sum_inter = 0, sum_pre = 0;
       float ms = 0;
       for (size_t i = 0; i < trace.size(); i++) {
+        if (cudaEventElapsedTime(&ms, trace[i].mid[3], trace[i].mid[1]) == cudaSuccess) sum_inter += ms;
+        if (cudaEventElapsedTime(&ms, trace[i].a, trace[i].mid[3]) == cudaSuccess) sum_pre += ms;
         if (cudaEventElapsedTime(&ms, trace[i].mid[1], trace[i].mid[2]) == cudaSuccess) sum_intra += ms;
         if (cudaEventElapsedTime(&ms, trace[i].mid[2], trace[i].b) == cudaSuccess) sum_lf += ms;
         cudaEventElapsedTime(&ms, trace[i].a, trace[i].b);
@@ -1411,9 +1413,10 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
         }
       }
       fprintf(stderr, "[trace] dispatcher %d: %zu batches, avg %.2f frames, device %.3f ms per batch, end-to-end period %.3f ms, "
-              "host span %.1f ms; k_intra %.3f ms, k_loopfilter %.3f ms per batch\n", di, trace.size(), n_jobs / n_batches,
-              sum_ms / trace.size(), trace.size() > 1 ? sum_gap / (trace.size() - 1) : 0.0, (last_host - first_host) * 1e3,
-              sum_intra / trace.size(), sum_lf / trace.size());
+              "host span %.1f ms; per batch: waits + upload %.3f ms, k_inter %.3f ms, k_intra %.3f ms, k_loopfilter %.3f ms\n", di,
+              trace.size(), n_jobs / n_batches, sum_ms / trace.size(), trace.size() > 1 ? sum_gap / (trace.size() - 1) : 0.0,
+              (last_host - first_host) * 1e3, sum_pre / trace.size(), sum_inter / trace.size(), sum_intra / trace.size(),
+              sum_lf / trace.size());
       for (Trace& t : trace) {
         cudaEventDestroy(t.a);
         cudaEventDestroy(t.b);

@@ -549,6 +549,7 @@ Layout plan(const Geom& g, const HostJob* jobs, int n) {
 int Engine::build_and_launch(int lane, const DevJob* d_jobs, int* d_sync, int n, bool any_inter, bool any_intra,
                              bool any_lf, cudaEvent_t* between) {
   cudaStream_t s = lanes_[lane];
+  if (between) CU(cudaEventRecord(between[2], s));  // the stream has passed its waits and the record upload
   if (any_inter) {
     if (int e = launch_inter(d_jobs, n, g_, s)) return cuda_fail((cudaError_t)e, "k_inter launch");
     launches_++;
@@ -931,9 +932,8 @@ int Engine::resident_run_timed(int lane, Resident* r, float ms[3]) {
   if (int rc = ensure_lane(lane)) return rc;
   CU(cudaSetDevice(device_));
   cudaStream_t s = lanes_[lane];
-  cudaEvent_t mid[2];
-  CU(cudaEventCreate(&mid[0]));
-  CU(cudaEventCreate(&mid[1]));
+  cudaEvent_t mid[3];
+  for (cudaEvent_t& m : mid) CU(cudaEventCreate(&m));
   {
     std::lock_guard<std::mutex> lk(mu_);
     for (int id : r->outs)
@@ -961,6 +961,7 @@ int Engine::resident_run_timed(int lane, Resident* r, float ms[3]) {
   CU(cudaEventElapsedTime(&ms[2], mid[1], r->t1));
   cudaEventDestroy(mid[0]);
   cudaEventDestroy(mid[1]);
+  cudaEventDestroy(mid[2]);
   return VP8GPU_OK;
 }
 

@@ -88,7 +88,7 @@ class Engine {
 
   // decode n frames in one set of launches on `lane`; host arrays must stay valid until the
   // returned event (*consumed, optional) has fired (pinned) or are consumed on return (pageable)
-  // `between` (optional, diagnostics): two events recorded after k_inter and after k_intra
+  // `between` (optional, diagnostics): three events: [0] after k_inter, [1] after k_intra, [2] before k_inter
   int submit(int lane, const HostJob* jobs, int n, cudaEvent_t consumed, cudaEvent_t* between = nullptr);
 
   // device-side token decoding
