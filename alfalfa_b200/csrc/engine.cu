@@ -695,7 +695,8 @@ int Engine::submit(int lane, const HostJob* jobs, int n, cudaEvent_t consumed, c
   if (st.host_cap < hdr_bytes) {
     if (st.host) CU(cudaFreeHost(st.host));
     st.host_cap = hdr_bytes * 2;
-    CU(cudaHostAlloc(&st.host, st.host_cap, cudaHostAllocDefault));
+    CU(cudaHostAlloc(&st.host, st.host_cap, cudaHostAllocMapped));
+    CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&st.host_dev), st.host, 0));
   }
   if (st.dev_cap < L.total) {
     if (st.dev) CU(cudaFree(st.dev));
@@ -757,7 +758,8 @@ int Engine::submit(int lane, const HostJob* jobs, int n, cudaEvent_t consumed, c
     }
   }
   for (cudaEvent_t ev : waits) CU(cudaStreamWaitEvent(s, ev, 0));
-  CU(cudaMemcpyAsync(st.dev, st.host, hdr_bytes, cudaMemcpyHostToDevice, s));
+  if (int ce = launch_fetch_header(st.dev, st.host_dev, hdr_bytes, s)) return cuda_fail((cudaError_t)ce, "header fetch");
+  launches_++;
   const size_t n_mbs = (size_t)g_.mb_cols * g_.mb_rows;
   for (int i = 0; i < n; i++) {
     const HostJob& j = jobs[i];

@@ -92,6 +92,7 @@ int launch_intra(const DevJob* jobs, int njobs, const Geom& g, int* ticket, uint
 int launch_loopfilter(const DevJob* jobs, int njobs, const Geom& g, int* ticket, uint32_t epoch, void* stream);
 // token jobs sit at the start of equally spaced ring slots: slot (first + i) % nslots for block i
 int launch_tokens(const uint8_t* ring, size_t stride, int first, int count, int nslots, const Geom& g, void* stream);
+int launch_fetch_header(void* dst, const void* src_host_devptr, size_t bytes, void* stream);  // bytes % 16 == 0
 int launch_ssim(const uint8_t* a, const uint8_t* b, const Geom& g, float* d_windows, void* stream);
 int launch_enc_rd(const EncJob* job, int rows, const Geom& g, int* ticket, void* stream);
 

@@ -141,7 +141,8 @@ class Engine {
   struct Staging {
     uint8_t* dev = nullptr;
     size_t dev_cap = 0;
-    uint8_t* host = nullptr;  // pinned header: DevJob[n] + sync words
+    uint8_t* host = nullptr;  // pinned, device-mapped header: DevJob[n] + sync words
+    uint8_t* host_dev = nullptr;  // the device's address of `host`
     size_t host_cap = 0;
     cudaEvent_t done = nullptr;
     bool in_flight = false;

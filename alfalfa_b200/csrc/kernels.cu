@@ -1961,6 +1961,19 @@ extern "C" void vp8gpu_debug_profile(unsigned long long out[32], int reset) {
 }
 #endif
 
+// Batch header (job descriptors + zeroed tickets / counters) from mapped pinned host memory into HBM, read over
+// PCIe by one thread block.  A cudaMemcpyAsync would queue behind whatever the copy engines are busy with -- in
+// vp8gpu_decode_ivf that is megabytes of bitstream staged by the workers -- and stall the pixel batch for
+// milliseconds (profiles/r2_notes.md); a 30 KB read by the SMs takes microseconds.
+__global__ void k_fetch_header(uint4* __restrict__ dst, const uint4* __restrict__ src_host, int n16) {
+  for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src_host[i];
+}
+int launch_fetch_header(void* dst, const void* src_host_devptr, size_t bytes, void* stream) {
+  k_fetch_header<<<1, 512, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<uint4*>(dst), static_cast<const uint4*>(src_host_devptr),
+                                                                 (int)(bytes / 16));
+  return (int)cudaGetLastError();
+}
+
 int launch_hash(const uint8_t* a, const Geom& g, unsigned long long* d_out, void* stream) {
   k_hash<<<296, 128, 0, static_cast<cudaStream_t>(stream)>>>(a, g, d_out);
   return (int)cudaGetLastError();
