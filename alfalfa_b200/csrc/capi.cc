@@ -1398,7 +1398,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
       // per batch: device time from "stream reaches the batch" to "its kernels are done", and the
       // device-side gap to the previous batch of this dispatcher
       double sum_ms = 0, sum_gap = 0, first_host = trace.front().host_t, last_host = trace.back().host_t;
-      double sum_intra = 0, sum_lf = 0, sum_inter = 0, sum_pre = 0;
+      double sum_intra = 0, sum_lf = 0, sum_inter = 0, sum_pre = 0, sum_turn = 0;
       float ms = 0;
       for (size_t i = 0; i < trace.size(); i++) {
         if (cudaEventElapsedTime(&ms, trace[i].mid[3], trace[i].mid[1]) == cudaSuccess) sum_inter += ms;
@@ -1410,13 +1410,15 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
         if (i) {
           cudaEventElapsedTime(&ms, trace[i - 1].b, trace[i].b);
           sum_gap += ms;
+          // device-side turn-around: end of the previous batch -> first kernel of this one (negative: overlapped)
+          if (cudaEventElapsedTime(&ms, trace[i - 1].b, trace[i].mid[3]) == cudaSuccess) sum_turn += ms;
         }
       }
       fprintf(stderr, "[trace] dispatcher %d: %zu batches, avg %.2f frames, device %.3f ms per batch, end-to-end period %.3f ms, "
-              "host span %.1f ms; per batch: waits + upload %.3f ms, k_inter %.3f ms, k_intra %.3f ms, k_loopfilter %.3f ms\n", di,
+              "host span %.1f ms; per batch: waits + upload %.3f ms, k_inter %.3f ms, k_intra %.3f ms, k_loopfilter %.3f ms, turn-around %.3f ms\n", di,
               trace.size(), n_jobs / n_batches, sum_ms / trace.size(), trace.size() > 1 ? sum_gap / (trace.size() - 1) : 0.0,
               (last_host - first_host) * 1e3, sum_pre / trace.size(), sum_inter / trace.size(), sum_intra / trace.size(),
-              sum_lf / trace.size());
+              sum_lf / trace.size(), trace.size() > 1 ? sum_turn / (trace.size() - 1) : 0.0);
       for (Trace& t : trace) {
         cudaEventDestroy(t.a);
         cudaEventDestroy(t.b);
