@@ -147,7 +147,8 @@ class Engine {
     cudaEvent_t done = nullptr;
     bool in_flight = false;
   };
-  static constexpr int kEventRing = 64;
+  static constexpr int kEventRing = 2048;  // must exceed the number of batches a raster outlives on any one stream slot: a re-recorded
+                                            // entry makes a later waiter wait for NEWER work of that slot (false dependency, not an error)
   cudaEvent_t next_event(int slot);  // next event of the slot's ring (caller records it)
   // note that `slot` used the frame; `shared` = an event of that slot the caller has already recorded
   int touch(Frame& f, int slot, bool write = true, cudaEvent_t shared = nullptr);
