@@ -915,6 +915,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     int out;
     int64_t out_off;
     int* slot_state;
+    int tid = 0;  // the worker that queued it
     // device-side tokens: the records live in ring slot `ring_slot` once `ready` has fired
     const vp8::TokenRing* ring = nullptr;
     int ring_slot = 0;
@@ -927,7 +928,9 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     if (n >= 1 && n <= 16 && n <= threads) n_disp = n;
   }
   std::mutex mu;
-  std::condition_variable cv_workers;
+  // one condition variable per worker: a batch wakes exactly the workers whose slots it freed (a shared one
+  // woke every worker for every batch: hundreds of thousands of futile wake-ups per second of decoding)
+  std::vector<std::condition_variable> cv_worker(threads);
   std::vector<std::condition_variable> cv_disp(n_disp);
   std::vector<std::deque<Pending>> queues(threads);
   std::vector<int> running(n_disp, 0);  // workers each dispatcher still serves
@@ -979,7 +982,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
         const double t0 = now();
         {  // the dispatcher must have picked the slot's previous frame up ...
           std::unique_lock<std::mutex> lk(mu);
-          cv_workers.wait(lk, [&] { return slot_state[si] == kFree; });
+          cv_worker[tid].wait(lk, [&] { return slot_state[si] == kFree; });
         }
         const double t1 = now();
         if (p->busy) {  // ... and the DMA engine must have read it
@@ -1022,6 +1025,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
         {
           std::lock_guard<std::mutex> lk(mu);
           slot_state[si] = kQueued;
+          job.tid = tid;
           queues[tid].push_back(job);
         }
         cv_disp[tid % n_disp].notify_one();
@@ -1033,7 +1037,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     }
     {  // wait until everything this worker queued has been submitted, then retire
       std::unique_lock<std::mutex> lk(mu);
-      cv_workers.wait(lk, [&] {
+      cv_worker[tid].wait(lk, [&] {
         for (int k = 0; k < kSlots; k++)
           if (slot_state[k] != kFree) return false;  // the dispatcher still owns that slot
         return true;
@@ -1133,7 +1137,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
           const double t0 = now();
           {  // the dispatcher must have submitted the slot's previous frame ...
             std::unique_lock<std::mutex> lk(mu);
-            cv_workers.wait(lk, [&] { return slot_state[si] == kFree; });
+            cv_worker[tid].wait(lk, [&] { return slot_state[si] == kFree; });
           }
           const double t1 = now();
           if (kit->busy[si]) {  // ... and the pixel kernels must have read its records
@@ -1213,7 +1217,8 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
           {
             std::lock_guard<std::mutex> lk(mu);
             slot_state[si] = kQueued;
-            queues[tid].push_back(job);
+            job.tid = tid;
+          queues[tid].push_back(job);
           }
           cv_disp[tid % n_disp].notify_one();
         }
@@ -1225,7 +1230,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     if (rc != VP8GPU_OK) set_error(rc);
     {  // wait until everything this worker queued has been submitted, then retire
       std::unique_lock<std::mutex> lk(mu);
-      cv_workers.wait(lk, [&] {
+      cv_worker[tid].wait(lk, [&] {
         for (int k = 0; k < kTokSlots; k++)
           if (slot_state[k] != kFree) return false;
         return true;
@@ -1390,7 +1395,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
         std::lock_guard<std::mutex> lk(mu);
         for (const Pending& b : batch) *b.slot_state = kFree;
       }
-      cv_workers.notify_all();
+      for (const Pending& b : batch) cv_worker[b.tid].notify_one();
     }
     e->sync_lane(2 * di);
     e->sync_lane(2 * di + 1);
