@@ -107,6 +107,7 @@ SYMBOLS = {
     "vp8gpu_batches_run": (C.c_int, [_vp, C.c_int, _pp, C.c_int, C.POINTER(C.c_float)]),
     "vp8gpu_batch_run_timed": (C.c_int, [_vp, C.c_int, _vp, C.POINTER(C.c_float)]),
     "vp8gpu_launch_count": (C.c_uint64, [_vp]),
+    "vp8gpu_frames_in_use": (C.c_int, [_vp]),
     "vp8gpu_state_create": (C.c_int, [C.c_int, C.c_int, _pp]),
     "vp8gpu_state_clone": (C.c_int, [_vp, _pp]),
     "vp8gpu_state_destroy": (None, [_vp]),

@@ -215,6 +215,7 @@ void vp8gpu_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
 uint64_t vp8gpu_launch_count(const vp8gpu_ctx* ctx) { return ctx->engine->launches(); }
+int vp8gpu_frames_in_use(const vp8gpu_ctx* ctx) { return ctx->engine->frames_in_use(); }
 int vp8gpu_serialize_frame_ex(const vp8gpu_encode_header* hdr, const vp8gpu_encode_features* ft, const vp8gpu_mb* mbs,
                               const vp8gpu_token* tokens, const vp8gpu_split_mvs* split, uint8_t* out, size_t cap,
                               size_t* size) {
@@ -814,10 +815,29 @@ int vp8gpu_decoder_equal(vp8gpu_decoder* a, vp8gpu_decoder* b, int* equal) {
 // =============================================================================================
 // whole-stream helper: FilePlayer semantics (player.cc:88-143) with GOP-level parallelism
 // =============================================================================================
+// Tuning knobs of vp8gpu_decode_ivf, read ONCE per call from the environment (diagnostics and the sweeps of
+// tools/e2e_probe.py; the defaults are what profiles/r2_notes.md measured best).  -1 = not set.
+struct IvfKnobs {
+  int tok_slots = -1;      // VP8GPU_TOK_SLOTS     frames a worker keeps between "first partition parsed" and "pixels done"
+  int tok_chunk = -1;      // VP8GPU_TOK_CHUNK     frames per token-kernel launch
+  int tok_inflight = -1;   // VP8GPU_TOK_INFLIGHT  cap on frames inside token kernels (0 = unlimited)
+  int dispatchers = -1;    // VP8GPU_DISPATCHERS   dispatcher threads
+  int worker_nice = -1;    // VP8GPU_WORKER_NICE   niceness of the parsing workers (0 = leave alone)
+  bool trace = false;      // VP8GPU_TRACE         per-batch device times on stderr
+  static int num(const char* name) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : -1;
+  }
+  IvfKnobs()
+      : tok_slots(num("VP8GPU_TOK_SLOTS")), tok_chunk(num("VP8GPU_TOK_CHUNK")), tok_inflight(num("VP8GPU_TOK_INFLIGHT")),
+        dispatchers(num("VP8GPU_DISPATCHERS")), worker_nice(num("VP8GPU_WORKER_NICE")), trace(getenv("VP8GPU_TRACE") != nullptr) {}
+};
+
 int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threads, uint8_t* dst, size_t dst_size,
                       uint32_t* n_decoded, uint32_t* n_shown) {
   if (!ctx || !ivf) return VP8GPU_ERR_LOGIC;
   Engine* e = ctx->engine;
+  const IvfKnobs knobs;
   // IVF container (util/ivf.cc:36-82)
   if (len < 32 || memcmp(ivf, "DKIF", 4) != 0) return e->fail(VP8GPU_ERR_INVALID, "missing IVF file header");
   if ((ivf[4] | (ivf[5] << 8)) != 0) return e->fail(VP8GPU_ERR_UNSUPPORTED, "not an IVF version 0 file");
@@ -871,7 +891,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     const size_t stride = e->token_ring_layout(ring_bytes_for(max_frame_bytes)).stride;
     int want = (int)(ring_budget / (stride * (size_t)threads));
     if (want > kTokSlots) want = kTokSlots;
-    if (const char* v = getenv("VP8GPU_TOK_SLOTS")) want = atoi(v);  // tuning knob
+    if (knobs.tok_slots >= 0) want = knobs.tok_slots;
     if (want > kTokSlots) want = kTokSlots;
     if (tok_slots > want) tok_slots = want;
     if (tok_slots < 4) tok_slots = 0;  // pool too small: the host workers parse everything
@@ -891,14 +911,14 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     // the knob stays for experiments: VP8GPU_TOK_INFLIGHT=<frames>, 0 = unlimited.
     int cap = 0;
     (void)sms;
-    if (const char* v = getenv("VP8GPU_TOK_INFLIGHT")) cap = atoi(v);
+    if (knobs.tok_inflight >= 0) cap = knobs.tok_inflight;
     std::lock_guard<std::mutex> lk(ctx->tok_mu);
     ctx->tok_capacity = cap;
     ctx->tok_permits = cap;  // every earlier call has returned: all permits are back
   }
   int tok_chunk = tok_slots / 3 > kTokChunk ? kTokChunk : (tok_slots / 3 > 0 ? tok_slots / 3 : 1);
-  if (const char* v = getenv("VP8GPU_TOK_CHUNK")) {  // tuning knob
-    const int c = atoi(v);
+  if (knobs.tok_chunk >= 0) {
+    const int c = knobs.tok_chunk;
     if (c >= 1 && c <= tok_slots / 2) tok_chunk = c;
   }
 
@@ -923,8 +943,8 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     cudaEvent_t* finished = nullptr;  // where submit() leaves the event that fires after the pixel kernels
   };
   int n_disp = device_tokens ? (threads >= 32 ? 4 : (threads >= 8 ? 2 : 1)) : 1;
-  if (const char* v = getenv("VP8GPU_DISPATCHERS")) {  // tuning knob
-    const int n = atoi(v);
+  if (knobs.dispatchers >= 0) {
+    const int n = knobs.dispatchers;
     if (n >= 1 && n <= 16 && n <= threads) n_disp = n;
   }
   std::mutex mu;
@@ -1105,7 +1125,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
   // The dispatchers feed the device and must not queue behind dozens of parsing workers for a CPU: the workers
   // run at a lower priority (per-thread nice on Linux; VP8GPU_WORKER_NICE overrides, 0 = leave alone).
   int worker_nice = 5;
-  if (const char* v = getenv("VP8GPU_WORKER_NICE")) worker_nice = atoi(v);
+  if (knobs.worker_nice >= 0) worker_nice = knobs.worker_nice;
   auto worker_dev = [&](int tid) {
     if (worker_nice > 0) setpriority(PRIO_PROCESS, (id_t)syscall(SYS_gettid), worker_nice);
     cudaSetDevice(e->device());
@@ -1286,7 +1306,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
       cudaEvent_t mid[4] = {nullptr, nullptr, nullptr, nullptr};  // -, after k_inter, after k_intra, before k_inter
     };
     std::vector<Trace> trace;
-    const bool tracing = getenv("VP8GPU_TRACE") != nullptr;
+    const bool tracing = knobs.trace;
     for (;;) {
       batch.clear();
       const double ti = now();

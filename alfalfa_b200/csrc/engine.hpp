@@ -65,6 +65,12 @@ class Engine {
   int frame_retain(int id);
   int frame_release(int id);
   int frames_free();  // rasters the pool can still hand out
+  int frames_in_use() {
+    std::lock_guard<std::mutex> lk(mu_);
+    int n = 0;
+    for (const Frame& f : frames_) n += f.refcnt > 0;
+    return n;
+  }
   // marks the hand-over messages of one wavefront launch; never 0, never repeats within 2^32 launches
   uint32_t next_epoch(int kernel_bit = 3) {
     if (!(ll_mask_ & kernel_bit)) return 0;

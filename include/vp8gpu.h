@@ -214,6 +214,9 @@ int vp8gpu_batches_run(vp8gpu_ctx* ctx, int lane, vp8gpu_resident_batch* const* 
 int vp8gpu_batch_run_timed(vp8gpu_ctx* ctx, int lane, vp8gpu_resident_batch* b, float kernel_ms[3]);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 uint64_t vp8gpu_launch_count(const vp8gpu_ctx* ctx);
+/* rasters of the context's pool that are currently handed out (RasterHandle count of the reference's pool,
+ * raster_handle.cc:103-122); after an error every raster a call took must have come back */
+int vp8gpu_frames_in_use(const vp8gpu_ctx* ctx);
 
 /* ---- CPU entropy front end: DecoderState::parse_and_apply ----
  *

@@ -14,6 +14,9 @@
  *   ref_flatten decode LIBVP8GPU.so FILE.ivf the library is dlopen()ed (the binary is built in the container,
  *                                            the GPU is on another box); display rectangle of every shown
  *                                            frame -> stdout, same bytes as the reference's decode-to-stdout
+ *   ref_flatten decode LIBVP8GPU.so --out DIR FILE.ivf...
+ *                                            several files of ONE frame size in one process (the reference's frame
+ *                                            pool allows a single size per process, frame_pool.cc:54-57): DIR/<name>.yuv
  */
 #include <dlfcn.h>
 
@@ -206,59 +209,78 @@ struct GpuReferences {
   }
 };
 
+static void run_file(const string& mode, const char* path, Gpu* gpu, vp8gpu_ctx* ctx, FILE* sink) {
+  const bool decode = mode == "decode";
+  IVF ivf(path);
+  const uint16_t w = ivf.width(), h = ivf.height();
+  DecoderState state(w, h);
+  Flat flat;
+  unique_ptr<GpuReferences> refs;
+  if (decode) refs.reset(new GpuReferences{*gpu, ctx});
+  vector<uint8_t> display(size_t(w) * h + 2 * size_t((w + 1) / 2) * ((h + 1) / 2));
+  bool started = false;
+  for (uint32_t i = 0; i < ivf.frame_count(); i++) {
+    UncompressedChunk uc(ivf.frame(i), w, h, false);
+    if (!started && !uc.key_frame()) continue;
+    started = true;
+    if (uc.key_frame()) flatten(state.parse_and_apply<KeyFrame>(uc), state, flat);
+    else flatten(state.parse_and_apply<InterFrame>(uc), state, flat);
+    if (!decode) {
+      fwrite(&flat.desc, sizeof(flat.desc), 1, sink);
+      fwrite(flat.mbs.data(), sizeof(vp8gpu_mb), flat.mbs.size(), sink);
+      fwrite(flat.tokens.data(), sizeof(vp8gpu_token), flat.tokens.size(), sink);
+      fwrite(flat.split.data(), sizeof(vp8gpu_split_mvs), flat.split.size(), sink);
+      continue;
+    }
+    /* the seam: frame.decode( segmentation, references, raster ); frame.loopfilter( ... ) */
+    vp8gpu_frame_id raster = -1;
+    if (gpu->frame_alloc(ctx, &raster) != VP8GPU_OK) throw runtime_error(gpu->last_error(ctx));
+    const vp8gpu_frame_id three[3] = {refs->last, refs->golden, refs->alternative};
+    if (gpu->decode_parsed(ctx, 0, &flat.desc, flat.mbs.data(), flat.tokens.data(), flat.split.data(), three, raster) != VP8GPU_OK)
+      throw runtime_error(gpu->last_error(ctx));
+    refs->update(flat.desc, raster);
+    if (flat.desc.show_frame) {
+      if (gpu->download_display(ctx, raster, display.data(), display.size()) != VP8GPU_OK) throw runtime_error(gpu->last_error(ctx));
+      fwrite(display.data(), 1, display.size(), sink);
+    }
+    gpu->frame_release(ctx, raster);
+  }
+  if (decode) refs->assign(refs->last, -1), refs->assign(refs->golden, -1), refs->assign(refs->alternative, -1);
+}
+
 int main(int argc, char** argv) {
   try {
     if (argc < 3) {
-      cerr << "usage: ref_flatten records FILE.ivf | ref_flatten decode LIBVP8GPU.so FILE.ivf\n";
+      cerr << "usage: ref_flatten records FILE.ivf | ref_flatten decode LIBVP8GPU.so [--out DIR] FILE.ivf...\n";
       return 2;
     }
     const string mode = argv[1];
-    const bool decode = mode == "decode";
-    if (decode && argc < 4) return 2;
-    IVF ivf(argv[decode ? 3 : 2]);
-    const uint16_t w = ivf.width(), h = ivf.height();
-    DecoderState state(w, h);
-    Flat flat;
-    unique_ptr<Gpu> gpu;
+    if (mode != "decode") {
+      run_file(mode, argv[2], nullptr, nullptr, stdout);
+      return 0;
+    }
+    if (argc < 4) return 2;
+    Gpu gpu(argv[2]);
+    const bool many = string(argv[3]) == "--out";
+    if (many && argc < 6) return 2;
+    const int first = many ? 5 : 3;
     vp8gpu_ctx* ctx = nullptr;
-    unique_ptr<GpuReferences> refs;
-    if (decode) {
-      gpu.reset(new Gpu(argv[2]));
-      if (gpu->ctx_create(0, w, h, 16, &ctx) != VP8GPU_OK) throw runtime_error("vp8gpu_ctx_create failed (no CUDA device?)");
-      refs.reset(new GpuReferences{*gpu, ctx});
+    {
+      IVF probe(argv[first]);
+      if (gpu.ctx_create(0, probe.width(), probe.height(), 16, &ctx) != VP8GPU_OK)
+        throw runtime_error("vp8gpu_ctx_create failed (no CUDA device?)");
     }
-    vector<uint8_t> display(size_t(w) * h + 2 * size_t((w + 1) / 2) * ((h + 1) / 2));
-    bool started = false;
-    for (uint32_t i = 0; i < ivf.frame_count(); i++) {
-      UncompressedChunk uc(ivf.frame(i), w, h, false);
-      if (!started && !uc.key_frame()) continue;
-      started = true;
-      if (uc.key_frame()) flatten(state.parse_and_apply<KeyFrame>(uc), state, flat);
-      else flatten(state.parse_and_apply<InterFrame>(uc), state, flat);
-      if (!decode) {
-        fwrite(&flat.desc, sizeof(flat.desc), 1, stdout);
-        fwrite(flat.mbs.data(), sizeof(vp8gpu_mb), flat.mbs.size(), stdout);
-        fwrite(flat.tokens.data(), sizeof(vp8gpu_token), flat.tokens.size(), stdout);
-        fwrite(flat.split.data(), sizeof(vp8gpu_split_mvs), flat.split.size(), stdout);
-        continue;
+    for (int k = first; k < (many ? argc : first + 1); k++) {
+      FILE* sink = stdout;
+      if (many) {
+        const string path = argv[k];
+        sink = fopen((string(argv[4]) + "/" + path.substr(path.find_last_of('/') + 1) + ".yuv").c_str(), "wb");
+        if (!sink) throw runtime_error("cannot write the output");
       }
-      /* the seam: frame.decode( segmentation, references, raster ); frame.loopfilter( ... ) */
-      vp8gpu_frame_id raster = -1;
-      if (gpu->frame_alloc(ctx, &raster) != VP8GPU_OK) throw runtime_error(gpu->last_error(ctx));
-      const vp8gpu_frame_id three[3] = {refs->last, refs->golden, refs->alternative};
-      if (gpu->decode_parsed(ctx, 0, &flat.desc, flat.mbs.data(), flat.tokens.data(), flat.split.data(), three, raster) != VP8GPU_OK)
-        throw runtime_error(gpu->last_error(ctx));
-      refs->update(flat.desc, raster);
-      if (flat.desc.show_frame) {
-        if (gpu->download_display(ctx, raster, display.data(), display.size()) != VP8GPU_OK) throw runtime_error(gpu->last_error(ctx));
-        fwrite(display.data(), 1, display.size(), stdout);
-      }
-      gpu->frame_release(ctx, raster);
+      run_file(mode, argv[k], &gpu, ctx, sink);
+      if (many) fclose(sink);
     }
-    if (decode) {
-      refs->assign(refs->last, -1), refs->assign(refs->golden, -1), refs->assign(refs->alternative, -1);
-      gpu->ctx_destroy(ctx);
-    }
+    gpu.ctx_destroy(ctx);
   } catch (const exception& e) {
     cerr << "ref_flatten: " << e.what() << "\n";
     return 1;

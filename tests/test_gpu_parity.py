@@ -251,3 +251,33 @@ def test_device_hash_tracks_content_and_references():
         y.release()
     del a, b
     ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("device_tokens", [False, True])
+def test_decode_ivf_unwinds_after_a_corrupt_frame_in_the_middle(device_tokens):
+    """A frame that does not parse in GOP k of many: vp8gpu_decode_ivf returns the parser's error, every worker and
+    dispatcher retires, every raster goes back to the pool, and the same context then decodes the intact stream
+    bit-exactly."""
+    from alfalfa_b200 import Context, capi, decode_ivf, write_ivf
+    name = "0b546dad90ddefea5085c7751b5fa2f117630b1c"
+    data = open(os.path.join(GOLDEN_DIR, name), "rb").read()
+    w, h, frames = O.read_ivf(data)
+    gop = frames[:12]
+    # independent copies of the first GOP: truncate the 5th frame of copy 3 of 8
+    streams = [list(gop) for _ in range(8)]
+    streams[3][4] = streams[3][4][:7]
+    bad = write_ivf(w, h, [f for s in streams for f in s])
+    good = write_ivf(w, h, [f for _ in range(8) for f in gop])
+    ctx = Context(w, h, max_frames=8 * 110 + 64)
+    ctx.set_device_tokens(device_tokens)
+    base = ctx.L.vp8gpu_frames_in_use(ctx.h)
+    with pytest.raises(capi.Vp8Error):
+        decode_ivf(ctx, bad, threads=4)
+    ctx.sync()
+    assert ctx.L.vp8gpu_frames_in_use(ctx.h) == base, "rasters leaked by the failed call"
+    out, nd, ns = decode_ivf(ctx, good, threads=4)
+    want = O.decode_ivf_display(write_ivf(w, h, gop))
+    assert nd == 96 and out == want * 8
+    assert ctx.L.vp8gpu_frames_in_use(ctx.h) == base
+    ctx.close()
