@@ -18,6 +18,7 @@
 #include <string>
 #include <chrono>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/vp8gpu.h"
@@ -815,6 +816,59 @@ int vp8gpu_decoder_equal(vp8gpu_decoder* a, vp8gpu_decoder* b, int* equal) {
 // =============================================================================================
 // whole-stream helper: FilePlayer semantics (player.cc:88-143) with GOP-level parallelism
 // =============================================================================================
+// DIAGNOSTIC ONLY (VP8GPU_PARSE_CACHE=1, tools/e2e_probe.py): the bench decodes replicas of a few GOPs, so the result
+// of parsing a first partition can be remembered by content and replayed with a memcpy.  This answers "what would
+// vp8gpu_decode_ivf do if the host front end cost nothing" (first partitions on the device); it
+// is never enabled by default and the numbers it produces are not decode throughput.
+struct CachedFirstPartition {
+  vp8gpu_frame_desc desc;
+  std::vector<vp8gpu_mb> mbs;
+  std::vector<vp8gpu_split_mvs> split;
+  vp8::TokenWork tw;
+  size_t bits_delta = 0;
+};
+std::mutex g_parse_cache_mu;
+std::unordered_map<uint64_t, std::shared_ptr<CachedFirstPartition>> g_parse_cache;
+uint64_t frame_key(const uint8_t* p, size_t n) {
+  uint64_t h = 1469598103934665603ull ^ n;
+  auto mix = [&](const uint8_t* q, size_t k) {
+    for (size_t i = 0; i < k; i++) h = (h ^ q[i]) * 1099511628211ull;
+  };
+  mix(p, n < 64 ? n : 64);
+  if (n > 64) mix(p + n - 64, 64);
+  return h;
+}
+int parse_first_partition_cached(vp8::State& state, const uint8_t* data, size_t len, vp8::ParsedFrame& out) {
+  const uint64_t key = frame_key(data, len);
+  std::shared_ptr<CachedFirstPartition> c;
+  {
+    std::lock_guard<std::mutex> lk(g_parse_cache_mu);
+    auto it = g_parse_cache.find(key);
+    if (it != g_parse_cache.end()) c = it->second;
+  }
+  if (!c) {
+    const int rc = vp8::parse_frame(state, data, len, out, true);
+    if (rc != VP8GPU_OK) return rc;
+    c = std::make_shared<CachedFirstPartition>();
+    c->desc = out.desc;
+    const size_t n = (size_t)out.desc.mb_cols * out.desc.mb_rows;
+    c->mbs.assign(out.mbs.data(), out.mbs.data() + n);
+    c->split.assign(out.split.data(), out.split.data() + out.desc.n_split);
+    c->tw = out.tw;
+    c->bits_delta = (size_t)(out.tw.bits - data);
+    std::lock_guard<std::mutex> lk(g_parse_cache_mu);
+    g_parse_cache[key] = c;
+    return VP8GPU_OK;
+  }
+  out.desc = c->desc;
+  if (!out.mbs.reserve(c->mbs.size(), 0) || !out.split.reserve(c->split.size() + 1, 0)) return VP8GPU_ERR_NOMEM;
+  memcpy(out.mbs.data(), c->mbs.data(), c->mbs.size() * sizeof(vp8gpu_mb));
+  if (!c->split.empty()) memcpy(out.split.data(), c->split.data(), c->split.size() * sizeof(vp8gpu_split_mvs));
+  out.tw = c->tw;
+  out.tw.bits = data + c->bits_delta;
+  return VP8GPU_OK;
+}
+
 // Tuning knobs of vp8gpu_decode_ivf, read ONCE per call from the environment (diagnostics and the sweeps of
 // tools/e2e_probe.py; the defaults are what profiles/r2_notes.md measured best).  -1 = not set.
 struct IvfKnobs {
@@ -824,13 +878,15 @@ struct IvfKnobs {
   int dispatchers = -1;    // VP8GPU_DISPATCHERS   dispatcher threads
   int worker_nice = -1;    // VP8GPU_WORKER_NICE   niceness of the parsing workers (0 = leave alone)
   bool trace = false;      // VP8GPU_TRACE         per-batch device times on stderr
+  bool parse_cache = false;  // VP8GPU_PARSE_CACHE  diagnostic: replay remembered first partitions (see above)
   static int num(const char* name) {
     const char* v = getenv(name);
     return v ? atoi(v) : -1;
   }
   IvfKnobs()
       : tok_slots(num("VP8GPU_TOK_SLOTS")), tok_chunk(num("VP8GPU_TOK_CHUNK")), tok_inflight(num("VP8GPU_TOK_INFLIGHT")),
-        dispatchers(num("VP8GPU_DISPATCHERS")), worker_nice(num("VP8GPU_WORKER_NICE")), trace(getenv("VP8GPU_TRACE") != nullptr) {}
+        dispatchers(num("VP8GPU_DISPATCHERS")), worker_nice(num("VP8GPU_WORKER_NICE")), trace(getenv("VP8GPU_TRACE") != nullptr),
+        parse_cache(getenv("VP8GPU_PARSE_CACHE") != nullptr) {}
 };
 
 int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threads, uint8_t* dst, size_t dst_size,
@@ -1166,7 +1222,8 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
           }
           const double t2 = now();
           vp8gpu_parsed* p = kit->parsed[si];
-          rc = vp8::parse_frame(state, items[i + c].p, items[i + c].n, p->f, true);
+          rc = knobs.parse_cache ? parse_first_partition_cached(state, items[i + c].p, items[i + c].n, p->f)
+                                 : vp8::parse_frame(state, items[i + c].p, items[i + c].n, p->f, true);
           if (rc != VP8GPU_OK) break;
           count_mbs(p);
           rc = e->token_ring_stage(kit->ring, si, p->f, kit->copy_stream);
