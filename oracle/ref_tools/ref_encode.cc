@@ -102,6 +102,13 @@ int main(int argc, char** argv) {
       } else {
         synth(raster, w, h, t, seed, kind);
       }
+      if (const char* ef = getenv("REF_EST_FRAME")) {  /* diagnostic: the size estimates the target-size search sees */
+        if (atoi(ef) == t) {
+          const char* lo = getenv("REF_EST_LO"); const char* hi = getenv("REF_EST_HI");
+          for (int q = lo ? atoi(lo) : 4; q <= (hi ? atoi(hi) : 127); q++)
+            cerr << "estimate frame " << t << " qi " << q << " " << enc.get().estimate_frame_size(raster.get(), q) << "\n";
+        }
+      }
       const auto t0 = chrono::steady_clock::now();
       const vector<uint8_t> f = target_env ? enc.get().encode_with_target_size(raster.get(), atoi(target_env))
                                            : enc.get().encode_with_quantizer(raster.get(), qi);
