@@ -1250,7 +1250,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
         rc = e->token_ring_launch(kit->ring, first_slot, staged < until_wrap ? staged : until_wrap, ks);
         if (rc == VP8GPU_OK && staged > until_wrap) rc = e->token_ring_launch(kit->ring, 0, staged - until_wrap, ks);
         if (rc == VP8GPU_OK)
-          for (int c = 0; c < staged; c++) cudaEventRecord(kit->ready[(first_slot + c) % tok_slots], ks);
+          cudaEventRecord(kit->ready[first_slot], ks);  // one event per launch: its frames become ready together
         // the permits come back when the stream gets here (also after a failed launch); queued after the
         // `ready` events so that the host-function thread is not on the frames' critical path
         if (permits_taken && cudaLaunchHostFunc(ks, tok_release_cb, new TokRelease{ctx, permits_taken}) != cudaSuccess) {
@@ -1268,7 +1268,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
           job.out_off = (dst && desc.show_frame) ? items[i + c].out_off : -1;
           job.ring = kit->ring;
           job.ring_slot = si;
-          job.ready = kit->ready[si];
+          job.ready = kit->ready[first_slot];
           job.finished = &kit->finished[si];
           rc = e->frame_alloc(&job.out);
           if (rc != VP8GPU_OK) break;
@@ -1370,8 +1370,20 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
       {
         std::unique_lock<std::mutex> lk(mu);
         // a queue's front is eligible once its tokens are in HBM (device-side token decoding)
-        auto eligible = [&](const std::deque<Pending>& q) {
-          return !q.empty() && (!q.front().ready || cudaEventQuery(q.front().ready) == cudaSuccess);
+        // The answer is remembered: once the event of a chunk has fired, every frame of that chunk at the head of
+        // the queue is marked (a query takes the driver's lock, and this runs for every queue on every poll --
+        // hundreds of thousands of queries per second next to the workers' own CUDA calls).
+        auto eligible = [&](std::deque<Pending>& q) {
+          if (q.empty()) return false;
+          Pending& f = q.front();
+          if (!f.ready) return true;
+          if (cudaEventQuery(f.ready) != cudaSuccess) return false;
+          const cudaEvent_t fired = f.ready;
+          for (Pending& p : q) {
+            if (p.ready != fired) break;
+            p.ready = nullptr;
+          }
+          return true;
         };
         auto ready = [&] {
           int n = 0;
