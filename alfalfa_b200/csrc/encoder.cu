@@ -8,6 +8,7 @@
 // the reconstruction the encoder keeps as its LAST reference, which is what Encoder::export_decoder
 // (encoder.hh:378) promises.
 #include <cuda_runtime.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -512,6 +513,14 @@ static int estimate_size(vp8gpu_encoder* enc, bool key, int qi, size_t* size) {
   std::vector<uint8_t> bytes;
   rc = encode_bytes(enc, key, qi, 0, 4, false, enc->dec_state->coef_probs, bytes);
   if (rc == VP8GPU_OK) *size = bytes.size() * 16;
+  if (rc == VP8GPU_OK) {
+    if (const char* path = getenv("VP8GPU_EST_DUMP")) {  // diagnostic (tools/enc_estimates.py): the sampled frame itself
+      if (FILE* f = fopen(path, "wb")) {
+        fwrite(bytes.data(), 1, bytes.size(), f);
+        fclose(f);
+      }
+    }
+  }
   return rc;
 }
 

@@ -11,6 +11,20 @@
  *   KIND 0: smooth moving sinusoid + noise ("easy");  1: translating random-texture tiles ("hard");
  *        2: translating softly textured tiles, light noise ("medium", broadcast-like bitrate)
  */
+/* diagnostics below look at the sampled frame of Encoder::estimate_size (a private member): this is test
+ * infrastructure compiled against the unmodified headers, so the access specifiers are lifted for this file */
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+#define private public
+#define protected public
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -106,7 +120,14 @@ int main(int argc, char** argv) {
         if (atoi(ef) == t) {
           const char* lo = getenv("REF_EST_LO"); const char* hi = getenv("REF_EST_HI");
           for (int q = lo ? atoi(lo) : 4; q <= (hi ? atoi(hi) : 127); q++)
+          {
             cerr << "estimate frame " << t << " qi " << q << " " << enc.get().estimate_frame_size(raster.get(), q) << "\n";
+            const char* dump = getenv("REF_EST_DUMP");
+            if (dump && t > 0) {  /* the sampled inter frame of that estimate, serialised the way estimate_size does */
+              const vector<uint8_t> b = enc.get().subsampled_inter_frame_.get().serialize(enc.get().decoder_state_.probability_tables);
+              ofstream(string(dump) + "." + to_string(q), ios::binary).write(reinterpret_cast<const char*>(b.data()), b.size());
+            }
+          }
         }
       }
       const auto t0 = chrono::steady_clock::now();

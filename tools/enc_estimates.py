@@ -19,7 +19,14 @@ ctx = Context(w, h, max_frames=32)
 enc = Encoder(ctx)
 blob, qi = enc.encode_with_target_size(*src[0], target)
 print("frame 0: %d bytes, qi %d" % (len(blob), qi))
-ours = {q: enc.estimate_frame_size(*src[1], q) for q in range(qi - 2, qi + 10)}
+out_dir = os.path.join(ROOT, "gpurun_out")
+os.makedirs(out_dir, exist_ok=True)
+ours = {}
+for q in range(qi - 2, qi + 10):
+    os.environ["VP8GPU_EST_DUMP"] = os.path.join(out_dir, "est_ours.%d" % q)
+    ours[q] = enc.estimate_frame_size(*src[1], q)
+os.environ.pop("VP8GPU_EST_DUMP")
+open(os.path.join(out_dir, "est_frame0.bin"), "wb").write(blob)
 ref = {}
 tool = os.path.join(ROOT, "oracle", "_ref", "ref_encode")
 if os.path.exists(tool):
@@ -29,7 +36,8 @@ if os.path.exists(tool):
             for t in range(2):
                 for p in src[t]:
                     f.write(p.tobytes())
-        env = dict(os.environ, REF_RAW=raw, REF_TARGET=str(target), REF_EST_FRAME="1", REF_EST_LO=str(qi - 2), REF_EST_HI=str(qi + 9))
+        env = dict(os.environ, REF_RAW=raw, REF_TARGET=str(target), REF_EST_FRAME="1", REF_EST_LO=str(qi - 2), REF_EST_HI=str(qi + 9),
+                   REF_EST_DUMP=os.path.join(out_dir, "est_ref"))
         r = subprocess.run([tool, os.path.join(d, "o.ivf"), str(w), str(h), "2", "1000", "0"], env=env, capture_output=True, text=True)
         for line in r.stderr.splitlines():
             if line.startswith("estimate"):
