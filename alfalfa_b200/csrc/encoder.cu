@@ -38,6 +38,8 @@ struct vp8gpu_encoder {
   int src = -1;                // device raster holding the (edge-extended) source frame
   int last_qi = -1;            // last_y_ac_qi_ (REALTIME_QUALITY, encoder.cc:164-167)
   int last_lf = -1;            // loop_filter_level_ (encoder.hh:144): -1 = not initialised
+  bool mv_costs_filled = false;  // Costs::fill_mv_component_costs / fill_mv_sad_costs have run (encode_inter.cc:601-602: at the
+                                 // start of the first full inter-frame pass of this Encoder or of the one it was copied from)
   double last_ssim = -1.0;     // encode_stats_.ssim of the last frame
   vp8::State* dec_state = nullptr;  // DecoderState a decoder has after the frames emitted so far (export_decoder)
   // device scratch: EncJob | DevJob | sync ints | mbs | tokens | rate tables
@@ -131,6 +133,8 @@ int encode_launch(vp8gpu_encoder* enc, bool key, int qi, int sub) {
   ej->lf_level = 1;  // records carry "filtered"; the level itself is chosen afterwards (choose_loop_filter)
   ej->sad_per_bit = k_sad_per_bit16[clamp_q(qi)];
   ej->realtime = 1;  // REALTIME_QUALITY, what Salsify runs (salsify-sender.cc:287-288)
+  if (!key && sub == 1) enc->mv_costs_filled = true;  // encode_raster<InterFrame> fills the tables before it uses them
+  ej->mv_costs_zero = !key && !enc->mv_costs_filled;
   auto fail = [&](int code) {
     e->frame_release(out);
     return code;
@@ -393,6 +397,7 @@ int vp8gpu_encoder_clone(const vp8gpu_encoder* src, vp8gpu_encoder** out) {
   enc->writer = src->writer;  // (the copy's frame objects, i.e. the writer's header state, start fresh: encoder.cc:92-102)
   enc->last_qi = src->last_qi;
   enc->last_lf = src->last_lf;
+  enc->mv_costs_filled = src->mv_costs_filled;  // costs_( encoder.costs_ ), encoder.cc:96
   enc->last_ssim = src->last_ssim;
   *enc->dec_state = *src->dec_state;
   for (int k = 0; k < 3; k++) {

@@ -66,7 +66,10 @@ struct EncJob {
   uint8_t key_frame, lf_level;
   uint8_t sad_per_bit;     // sad_per_bit16lut[y_ac_qi] (encode_inter.cc:160-170)
   uint8_t realtime;        // REALTIME_QUALITY: no B_PRED in inter frames, motion search on every 4th column and row
-  uint8_t pad[3];
+  uint8_t mv_costs_zero;   // the reference fills its motion-vector cost tables (Costs::fill_mv_component_costs,
+                           //   fill_mv_sad_costs) at the start of the first FULL inter-frame pass (encode_inter.cc:601-602);
+                           //   the size estimates that precede it price every vector at 0
+  uint8_t pad[2];
 };
 
 // One frame's token-decode job (tokens.cu): DCT partitions -> token stream + tok_off / tok_cnt.

@@ -1577,7 +1577,8 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __res
               enc_mc16(J, g, px0, py0, tx, ty, S.pcand[cur], S, lane);
               const uint32_t sad = enc_sad(src, S.pcand[cur], lane);
               const int sx = max(min(cx >> 2, 255), -255), sy = max(min(cy >> 2, 255), -255);
-              const uint32_t rate = ((uint32_t)(T.mv_sad_cost[abs(sy)] + T.mv_sad_cost[abs(sx)]) * J.sad_per_bit + 128u) / 256u;
+              const uint32_t rate =
+                  J.mv_costs_zero ? 0u : ((uint32_t)(T.mv_sad_cost[abs(sy)] + T.mv_sad_cost[abs(sx)]) * J.sad_per_bit + 128u) / 256u;
               const uint32_t c = ((128u + rate) / 256u) + sad;  // rdcost( rate, distortion, 1, 1 )
               if (c < bc) bc = c, bx2 = cx, by2 = cy;
             }
@@ -1591,8 +1592,9 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __res
         const int dvx = mvx, dvy = mvy;  // mv - best_ref
         mvx = (int16_t)(mvx + brx), mvy = (int16_t)(mvy + bry);
         if (mvx | mvy) {
-          const uint32_t mvc = (uint32_t)(T.mv_mag_cost[0][abs(dvy)] + (dvy ? T.mv_sign_cost[0][dvy < 0] : 0) + T.mv_mag_cost[1][abs(dvx)] +
-                                          (dvx ? T.mv_sign_cost[1][dvx < 0] : 0));
+          const uint32_t mvc = J.mv_costs_zero ? 0u
+                                               : (uint32_t)(T.mv_mag_cost[0][abs(dvy)] + (dvy ? T.mv_sign_cost[0][dvy < 0] : 0) +
+                                                            T.mv_mag_cost[1][abs(dvx)] + (dvx ? T.mv_sign_cost[1][dvx < 0] : 0));
           consider(VP8GPU_NEWMV, mvx, mvy, c_new + (mvc * 96u) / 128u);
         }
       }

@@ -176,6 +176,26 @@ def test_rd_parity_at_target_size_1080p():
     ctx.close()
 
 
+@needs_ref
+def test_first_inter_frame_estimates_price_vectors_at_zero():
+    """The reference fills its motion-vector cost tables at the start of the first FULL inter-frame pass
+    (encode_inter.cc:601-602), so the size estimates of the first inter frame price every vector at 0 and the
+    sampled motion search runs off to long vectors; target 45 000 on the bench clip is where that decides the
+    quantiser (qi 102; 100 with priced vectors).  Every frame must equal the reference encoder's."""
+    from alfalfa_b200 import Context, Encoder
+    import bench
+    w, h, n, target = 1920, 1080, 6, 45000
+    frames = [bench.synth_1080p(t) for t in range(n)]
+    ref = reference_encode(frames, w, h, target=target)
+    ctx = Context(w, h, max_frames=32)
+    enc = Encoder(ctx)
+    for t in range(n):
+        blob, qi = enc.encode_with_target_size(*frames[t], target)
+        assert blob == ref[t], "frame %d (qi %d): %d bytes vs %d of the reference" % (t, qi, len(blob), len(ref[t]))
+    del enc
+    ctx.close()
+
+
 def test_encoder_value_semantics():
     """Encoder( const Encoder & ), Encoder( const Decoder &, ... ), export_decoder (encoder.hh:346-382): a copy
     encodes the same next frame as the original, concurrently (salsify-sender.cc:492-518); export_decoder is a
