@@ -6,6 +6,15 @@
 
 #include "../../include/vp8gpu.h"
 
+// Kernel launches go through one macro: in the product build it is the ordinary <<< >>> launch; the test-only
+// SIMT-emulated build (tests/simt: the same sources compiled with g++, kernels run as fibers on the CPU to check
+// their logic where there is no GPU; never part of libvp8gpu.so) turns it into a call of the emulator.
+#ifdef VP8GPU_SIMT_EMUL
+#define VP8_LAUNCH(kern, grid, block, smem, stream) ::simt::make_launch((grid), (block), (smem), [](auto... a_) { kern(a_...); })
+#else
+#define VP8_LAUNCH(kern, grid, block, smem, stream) kern<<<(grid), (block), (smem), (stream)>>>
+#endif
+
 namespace vp8 {
 
 // Geometry of every raster of a context.  Planes live in one allocation:

@@ -402,6 +402,7 @@ struct __align__(128) InterSmem {  // per warp
   uint8_t nzlist[24];
 };
 
+#ifndef VP8GPU_SIMT_EMUL
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -442,6 +443,20 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
         : "memory");
   } while (!done);
 }
+#else
+// tests/simt: the copy is done at issue time, the barrier word counts the bytes still expected and flips bit 63
+// when they have arrived (the kernel initialises the barrier for every macroblock and waits for phase 0 only)
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int) { *bar = 0; }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) { *bar = bytes; }
+__device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int x, int y, unsigned long long* bar) {
+  *bar -= simt::tma_copy_2d(dst, tmap, x, y);
+  if (*bar == 0) *bar = 1ull << 63;
+}
+__device__ __forceinline__ void tmap_acquire(const void*) {}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t) {
+  while (!(*bar >> 63)) simt::yield();
+}
+#endif
 
 // window that leaves the plane: pixel by pixel with clamped coordinates into the same tile layout
 template <int TS>
@@ -682,6 +697,7 @@ __global__ void __launch_bounds__(INTER_WARPS * 32, 10) k_inter(const DevJob* __
 // ================================================================================================
 // wavefront plumbing
 // ================================================================================================
+#ifndef VP8GPU_SIMT_EMUL
 __device__ __forceinline__ int ld_progress(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -690,6 +706,13 @@ __device__ __forceinline__ int ld_progress(const int* p) {
 __device__ __forceinline__ void st_progress(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+#else
+__device__ __forceinline__ int ld_progress(const int* p) {
+  simt::yield();  // tests/simt: a poll lets the other threads of the CTA run
+  return *reinterpret_cast<const volatile int*>(p);
+}
+__device__ __forceinline__ void st_progress(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
+#endif
 // wait until the row above has finished every macroblock left of `need`
 __device__ __forceinline__ void wait_row(const int* progress_above, int need, int lane) {
   if (lane == 0) {
@@ -1931,24 +1954,24 @@ __global__ void k_hash(const uint8_t* __restrict__ a, Geom g, unsigned long long
 int launch_inter(const DevJob* jobs, int njobs, const Geom& g, void* stream) {
   const int n_mbs = g.mb_cols * g.mb_rows;
   dim3 grid((n_mbs + INTER_WARPS - 1) / INTER_WARPS, njobs);
-  k_inter<<<grid, INTER_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(jobs, g);
+  VP8_LAUNCH(k_inter, grid, INTER_WARPS * 32, 0, static_cast<cudaStream_t>(stream))(jobs, g);
   return (int)cudaGetLastError();
 }
 int launch_intra(const DevJob* jobs, int njobs, const Geom& g, int* ticket, uint32_t epoch, void* stream) {
   const int grid = (g.mb_rows * njobs + WF_WARPS - 1) / WF_WARPS;
-  if (epoch) k_intra_ll<<<grid, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream)>>>(jobs, njobs, g, ticket, epoch);
-  else k_intra<<<grid, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream)>>>(jobs, njobs, g, ticket);
+  if (epoch) VP8_LAUNCH(k_intra_ll, grid, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream))(jobs, njobs, g, ticket, epoch);
+  else VP8_LAUNCH(k_intra, grid, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream))(jobs, njobs, g, ticket);
   return (int)cudaGetLastError();
 }
 int launch_loopfilter(const DevJob* jobs, int njobs, const Geom& g, int* ticket, uint32_t epoch, void* stream) {
   const int grid = (g.mb_rows * njobs + WF_WARPS - 1) / WF_WARPS;
-  if (epoch) k_loopfilter_ll<<<grid, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream)>>>(jobs, njobs, g, ticket, epoch);
-  else k_loopfilter<<<grid, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream)>>>(jobs, njobs, g, ticket);
+  if (epoch) VP8_LAUNCH(k_loopfilter_ll, grid, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream))(jobs, njobs, g, ticket, epoch);
+  else VP8_LAUNCH(k_loopfilter, grid, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream))(jobs, njobs, g, ticket);
   return (int)cudaGetLastError();
 }
 
 int launch_enc_rd(const EncJob* job, int rows, const Geom& g, int* ticket, void* stream) {
-  k_enc_rd<<<(rows + WF_WARPS - 1) / WF_WARPS, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream)>>>(job, g, ticket);
+  VP8_LAUNCH(k_enc_rd, (rows + WF_WARPS - 1) / WF_WARPS, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream))(job, g, ticket);
   return (int)cudaGetLastError();
 }
 
@@ -1971,25 +1994,25 @@ __global__ void k_fetch_header(uint4* __restrict__ dst, const uint4* __restrict_
   for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src_host[i];
 }
 int launch_fetch_header(void* dst, const void* src_host_devptr, size_t bytes, void* stream) {
-  k_fetch_header<<<1, 512, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<uint4*>(dst), static_cast<const uint4*>(src_host_devptr),
+  VP8_LAUNCH(k_fetch_header, 1, 512, 0, static_cast<cudaStream_t>(stream))(static_cast<uint4*>(dst), static_cast<const uint4*>(src_host_devptr),
                                                                  (int)(bytes / 16));
   return (int)cudaGetLastError();
 }
 
 int launch_hash(const uint8_t* a, const Geom& g, unsigned long long* d_out, void* stream) {
-  k_hash<<<296, 128, 0, static_cast<cudaStream_t>(stream)>>>(a, g, d_out);
+  VP8_LAUNCH(k_hash, 296, 128, 0, static_cast<cudaStream_t>(stream))(a, g, d_out);
   return (int)cudaGetLastError();
 }
 
 int launch_ssim(const uint8_t* a, const uint8_t* b, const Geom& g, float* d_windows, void* stream) {
   const int n = (g.W / 4 - 1) * (g.H / 4 - 1);
   if (n <= 0) return 0;
-  k_ssim<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(a, b, g, d_windows);
+  VP8_LAUNCH(k_ssim, (n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream))(a, b, g, d_windows);
   return (int)cudaGetLastError();
 }
 
 int launch_compare(const uint8_t* a, const uint8_t* b, const Geom& g, int* d_flag, void* stream) {
-  k_compare<<<296, 128, 0, static_cast<cudaStream_t>(stream)>>>(a, b, g, d_flag);
+  VP8_LAUNCH(k_compare, 296, 128, 0, static_cast<cudaStream_t>(stream))(a, b, g, d_flag);
   return (int)cudaGetLastError();
 }
 

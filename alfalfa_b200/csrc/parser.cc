@@ -388,11 +388,16 @@ struct TapedReader {
     return get(128) ? -v : v;
   }
   inline int flagged_signed(int width) { return get(128) ? signed_literal(width) : 0; }
+  uint32_t* marks = nullptr;  // Verbatim::mark_* (positions in the tape), in the order the header reader passes them
+  inline void mark(int id) { if (marks) marks[id] = static_cast<uint32_t>(tape.size()); }
 };
+inline void mark_header(BoolReader&, int) {}
+inline void mark_header(TapedReader& r, int id) { r.mark(id); }
 
 // the part of the frame header shared by key and inter frames (frame_header.hh:104-131, :70-84, :37-66)
 template <class Reader>
 void read_common_header(Reader& br, FrameHeader& h) {
+  mark_header(br, 0);
   h.seg_enabled = br.bit();
   if (h.seg_enabled) {
     h.seg_update_map = br.bit();
@@ -416,13 +421,16 @@ void read_common_header(Reader& br, FrameHeader& h) {
       for (int i = 0; i < 4; i++) h.mode_upd[i] = static_cast<int8_t>(br.flagged_signed(6));
     }
   }
+  mark_header(br, 1);
   h.log2_parts = br.literal(2);
   h.y_ac_qi = br.literal(7);
+  mark_header(br, 2);
   h.y_dc = br.flagged_signed(4);
   h.y2_dc = br.flagged_signed(4);
   h.y2_ac = br.flagged_signed(4);
   h.uv_dc = br.flagged_signed(4);
   h.uv_ac = br.flagged_signed(4);
+  mark_header(br, 3);
 }
 
 template <class Reader>
@@ -666,8 +674,11 @@ int parse_frame(State& state, const uint8_t* data, size_t len, ParsedFrame& out,
   if (out.keep_verbatim) {
     if (defer_tokens) return VP8GPU_ERR_LOGIC;
     out.verbatim.header_tape.clear();
-    TapedReader taped{br, out.verbatim.header_tape};
+    uint32_t marks[4] = {0, 0, 0, 0};
+    TapedReader taped{br, out.verbatim.header_tape, marks};
     color_or_clamp = read_frame_header(taped, h, state, frame_coef, frame_ymode, frame_uvmode, frame_mv);
+    Verbatim& v = out.verbatim;
+    v.mark_begin = marks[0], v.mark_parts = marks[1], v.mark_qdelta = marks[2], v.mark_qend = marks[3];
   } else {
     color_or_clamp = read_frame_header(br, h, state, frame_coef, frame_ymode, frame_uvmode, frame_mv);
   }
@@ -818,6 +829,13 @@ int parse_frame(State& state, const uint8_t* data, size_t len, ParsedFrame& out,
     vb->skip_prob = static_cast<uint8_t>(h.skip_prob), vb->prob_inter = static_cast<uint8_t>(h.prob_inter);
     vb->prob_last = static_cast<uint8_t>(h.prob_last), vb->prob_golden = static_cast<uint8_t>(h.prob_golden);
     memcpy(vb->seg_tree_probs, h.seg_tree_probs, 3);
+    vb->seg_enabled = h.seg_enabled;
+    vb->refresh_golden = h.refresh_golden, vb->refresh_alt = h.refresh_alt, vb->refresh_last = h.refresh_last;
+    vb->refresh_entropy = h.refresh_entropy;
+    vb->copy_golden = static_cast<uint8_t>(h.copy_golden), vb->copy_alt = static_cast<uint8_t>(h.copy_alt);
+    vb->y_ac_qi = static_cast<uint8_t>(h.y_ac_qi), vb->lf_level = static_cast<uint8_t>(h.lf_level);
+    vb->q_delta[0] = static_cast<int8_t>(h.y_dc), vb->q_delta[1] = static_cast<int8_t>(h.y2_dc), vb->q_delta[2] = static_cast<int8_t>(h.y2_ac);
+    vb->q_delta[3] = static_cast<int8_t>(h.uv_dc), vb->q_delta[4] = static_cast<int8_t>(h.uv_ac);
     memcpy(vb->coef, frame_coef, 1056);
     memcpy(vb->ymode, frame_ymode, 4);
     memcpy(vb->uvmode, frame_uvmode, 3);

@@ -95,6 +95,15 @@ struct Verbatim {
   uint8_t seg_tree_probs[3] = {255, 255, 255};
   uint8_t coef[1056], ymode[4], uvmode[3], mv[2][19];  // the frame's probability tables (after the header's updates)
   std::vector<uint8_t> mb_coded;     // per macroblock: bit 0 = mb_skip_coeff as coded, bits 1-2 = SPLITMV layout
+  // What Encoder::update_residues / reencode_as_interframe (encoder/reencode.cc:39-64, 248-281) copy from the
+  // frame they start from into the header of the frame they build: whole header sections, replayed from the
+  // tape so that a Flagged<Signed> +0 / -0 survives -- decisions [mark_begin, mark_parts) are the segmentation
+  // update, filter type / level / sharpness and the loop-filter adjustments, [mark_qdelta, mark_qend) the five
+  // quantiser deltas -- and single fields, kept decoded.
+  uint32_t mark_begin = 0, mark_parts = 0, mark_qdelta = 0, mark_qend = 0;
+  bool seg_enabled = false, refresh_golden = false, refresh_alt = false, refresh_last = false, refresh_entropy = false;
+  uint8_t copy_golden = 0, copy_alt = 0, y_ac_qi = 0, lf_level = 0;
+  int8_t q_delta[5] = {0, 0, 0, 0, 0};  // y_dc, y2_dc, y2_ac, uv_dc, uv_ac
   std::vector<uint32_t> sub_labels;  // per SPLITMV macroblock (split_idx): 2 bits per partition, coding order
 };
 

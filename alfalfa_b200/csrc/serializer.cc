@@ -537,8 +537,41 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
 
   // ---- first partition: frame header ----
   BoolWriter bw;
+  const Verbatim* const ro = x.residue_of;
+  if (ro && (vb || !x.ref_writer || h.key_frame || ro->key || ro->seg_enabled || ro->mark_qend > ro->header_tape.size())) return {};
   if (vb) {
     for (const uint16_t d : vb->header_tape) bw.put(d & 1, d >> 1);
+  } else if (ro) {
+    auto replay = [&](uint32_t from, uint32_t to) {
+      for (uint32_t i = from; i < to; i++) bw.put(ro->header_tape[i] & 1, ro->header_tape[i] >> 1);
+    };
+    replay(ro->mark_begin, ro->mark_parts);  // update_segmentation, filter_type, loop_filter_level, sharpness_level, mode_lf_adjustments
+    bw.literal(x.log2_partitions, 2);        // not copied: the new frame object's own field
+    bw.literal(h.y_ac_qi, 7);
+    replay(ro->mark_qdelta, ro->mark_qend);  // quant_indices = a copy of the source's with (possibly) another y_ac_qi
+    const bool all = x.residue_refresh_all;
+    const bool rg = all || ro->refresh_golden, ra = all || ro->refresh_alt;
+    bw.put(rg);
+    bw.put(ra);
+    if (!rg) bw.literal(ro->copy_golden, 2);
+    if (!ra) bw.literal(ro->copy_alt, 2);
+    bw.put(ro->sign_golden);
+    bw.put(ro->sign_alt);
+    bw.put(ro->refresh_entropy);
+    bw.put(all || ro->refresh_last);
+    if (x.saved_coef_probs && ro->refresh_entropy) memcpy(x.saved_coef_probs, coef_probs, 1056);
+    for (int i = 0; i < 1056; i++) {
+      bw.put(updated[i], k_coef_update_probs[i]);
+      if (updated[i]) bw.literal(coef_probs[i], 8);
+    }
+    bw.put(1);  // prob_skip_false.reset( calc_prob ): present, possibly 0
+    bw.literal(skip_prob, 8);
+    bw.literal(prob_inter, 8);
+    bw.literal(prob_last, 8);
+    bw.literal(prob_golden, 8);
+    bw.put(0);  // intra_16x16_prob, intra_chroma_prob, mv_prob_update: the new frame object carries none
+    bw.put(0);
+    for (int i = 0; i < 38; i++) bw.put(0, k_mv_update_probs[i]);
   } else {
     if (h.key_frame) {
       bw.put(0);  // color_space
@@ -624,9 +657,11 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
       for (int i = 0; i < 38; i++) bw.put(0, k_mv_update_probs[i]);  // motion vector probabilities unchanged
     }
   }
-  const uint8_t(*mv_probs)[19] = reinterpret_cast<const uint8_t(*)[19]>(vb ? &vb->mv[0][0] : k_mv_default_probs);
-  const uint8_t* const ymode_probs = vb ? vb->ymode : k_ymode_default_probs;
-  const uint8_t* const uvmode_probs = vb ? vb->uvmode : k_uvmode_default_probs;
+  const uint8_t(*mv_probs)[19] =
+      vb ? vb->mv : (x.mv_probs ? x.mv_probs : reinterpret_cast<const uint8_t(*)[19]>(k_mv_default_probs));
+  const uint8_t* const ymode_probs = vb ? vb->ymode : (x.ymode_probs ? x.ymode_probs : k_ymode_default_probs);
+  const uint8_t* const uvmode_probs = vb ? vb->uvmode : (x.uvmode_probs ? x.uvmode_probs : k_uvmode_default_probs);
+  const Verbatim* const labels_of = vb ? vb : ro;  // SPLITMV layouts and sub-block labels as the source frame coded them
   const bool write_segment = vb ? vb->read_segment : (x.segmentation_enabled && x.update_mb_segmentation_map);
 
   // ---- first partition: macroblock headers (macroblock.cc:44-71, 84-111, 343-456 inverted) ----
@@ -675,8 +710,8 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
       }
       if (h.key_frame || mb.ref_frame > VP8GPU_REF_ALTREF || (!features && mb.ref_frame != VP8GPU_REF_LAST)) return {};
       me.inter = 1;
-      me.flipped = (mb.ref_frame == VP8GPU_REF_GOLDEN && x.sign_bias_golden) ||
-                   (mb.ref_frame == VP8GPU_REF_ALTREF && x.sign_bias_alternate);
+      me.flipped = (mb.ref_frame == VP8GPU_REF_GOLDEN && (ro ? ro->sign_golden : x.sign_bias_golden)) ||
+                   (mb.ref_frame == VP8GPU_REF_ALTREF && (ro ? ro->sign_alt : x.sign_bias_alternate));
       bw.put(1, prob_inter);
       bw.put(mb.ref_frame != VP8GPU_REF_LAST, prob_last);
       if (mb.ref_frame != VP8GPU_REF_LAST) bw.put(mb.ref_frame == VP8GPU_REF_ALTREF, prob_golden);
@@ -714,10 +749,10 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
           }
         }
         uint32_t labels = 0;
-        if (vb) {
-          if (mb.split_idx >= vb->sub_labels.size()) return {};
-          layout = (vb->mb_coded[idx] >> 1) & 3;
-          labels = vb->sub_labels[mb.split_idx];
+        if (labels_of) {
+          if (mb.split_idx >= labels_of->sub_labels.size() || idx >= labels_of->mb_coded.size()) return {};
+          layout = (labels_of->mb_coded[idx] >> 1) & 3;
+          labels = labels_of->sub_labels[mb.split_idx];
         }
         write_path(bw, kMvRefPaths, ref_probs, VP8GPU_SPLITMV);
         write_path(bw, kSplitPaths, k_split_probs, layout);
@@ -743,7 +778,7 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
           if (vx == lx && vy == ly) label = kSubLeft;
           else if (vx == ax && vy == ay) label = kSubAbove;
           else if ((vx | vy) == 0) label = kSubZero;
-          if (vb) label = static_cast<int>((labels >> (2 * part)) & 3);  // as coded (any label that decodes to the vector is legal)
+          if (labels_of) label = static_cast<int>((labels >> (2 * part)) & 3);  // as coded (any label that decodes to the vector is legal)
           if (label != kSubNew) {
             write_path(bw, kSubMvPaths, sp, label);
           } else {

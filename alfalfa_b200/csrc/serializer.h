@@ -68,6 +68,21 @@ struct EncodeFeatures {
   // vectors, token partitions with their contexts -- is written from the flat records.  Set by serialize_parsed.
   const Verbatim* verbatim = nullptr;
   bool ref_estimate = false;  // with ref_writer: a size estimate (size_estimation.cc): no token-probability updates
+  // A frame built by Encoder::update_residues (encoder/reencode.cc:248-313): a NEW InterFrame object whose header
+  // takes the segmentation update, filter type / level / sharpness, loop-filter adjustments, quantiser deltas,
+  // sign biases, refresh_entropy_probs and prob_references_* of the frame it started from (replayed from that
+  // frame's tape, parser.h Verbatim marks) -- the reference flags too unless residue_refresh_all (last_frame) --
+  // while one token partition, prob_skip_false, prob_inter, the token probability updates and the absence of mode /
+  // motion-vector probability updates are what the reference Encoder decides (ref_writer must point to a FRESH
+  // state whose prob_last / prob_golden were preset to the source frame's).  The SPLITMV layouts and sub-block
+  // labels are the source frame's (the macroblock headers are copied, reencode.cc:141).
+  const Verbatim* residue_of = nullptr;
+  bool residue_refresh_all = false;
+  // the stream's saved mode / motion-vector probabilities (DecoderState) that macroblock headers are coded with;
+  // nullptr = the default tables (an Encoder that started from a key frame never changes them)
+  const uint8_t* ymode_probs = nullptr;
+  const uint8_t* uvmode_probs = nullptr;
+  const uint8_t (*mv_probs)[19] = nullptr;
 };
 
 // RFC 6386 section 7 arithmetic encoder (same code stream as encoder/bool_encoder.hh)

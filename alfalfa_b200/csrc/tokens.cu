@@ -51,7 +51,11 @@ __global__ void __launch_bounds__(32 * kTokWarps) k_tokens(const uint8_t* ring, 
 // tree position read one 32-byte row), then the 32 rows of above-contexts, also transposed ([mb_cols][32]).
 __global__ void __launch_bounds__(32) k_tokens_lockstep(const uint8_t* ring, size_t stride, int first, int count,
                                                          int nslots, Geom g) {
+#ifdef VP8GPU_SIMT_EMUL
+  uint8_t* const dyn = simt::dyn_smem();
+#else
   extern __shared__ __align__(16) uint8_t dyn[];
+#endif
   __shared__ tok::LockstepTables T;
   uint8_t* const P = dyn;
   uint16_t* const above = reinterpret_cast<uint16_t*>(dyn + 1056 * 32);
@@ -91,10 +95,10 @@ int launch_tokens(const uint8_t* ring, size_t stride, int first, int count, int 
     const size_t smem = 1056 * 32 + (size_t)g.mb_cols * 32 * sizeof(uint16_t);
     static const cudaError_t attr = cudaFuncSetAttribute(k_tokens_lockstep, cudaFuncAttributeMaxDynamicSharedMemorySize, 1056 * 32 + kMaxCols * 64);
     if (attr != cudaSuccess) return (int)attr;
-    k_tokens_lockstep<<<(count + 31) / 32, 32, smem, s>>>(ring, stride, first, count, nslots, g);
+    VP8_LAUNCH(k_tokens_lockstep, (count + 31) / 32, 32, smem, s)(ring, stride, first, count, nslots, g);
   }
-  else if (warps == 8) k_tokens<8><<<(count + 7) / 8, 256, 0, s>>>(ring, stride, first, count, nslots, g);
-  else k_tokens<1><<<count, 32, 0, s>>>(ring, stride, first, count, nslots, g);
+  else if (warps == 8) VP8_LAUNCH(k_tokens<8>, (count + 7) / 8, 256, 0, s)(ring, stride, first, count, nslots, g);
+  else VP8_LAUNCH(k_tokens<1>, count, 32, 0, s)(ring, stride, first, count, nslots, g);
   return (int)cudaGetLastError();
 }
 

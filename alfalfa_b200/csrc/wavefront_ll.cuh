@@ -27,6 +27,7 @@
 struct Msg {
   uint32_t d, f;
 };
+#ifndef VP8GPU_SIMT_EMUL
 __device__ __forceinline__ Msg ld_msg(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -39,6 +40,19 @@ __device__ __forceinline__ void st_msg(unsigned long long* p, uint32_t d, uint32
   const unsigned long long v = (unsigned long long)d | ((unsigned long long)f << 32);
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+#else
+__device__ __forceinline__ Msg ld_msg(const unsigned long long* p) {
+  simt::yield();  // tests/simt: a poll lets the other threads of the CTA run
+  const unsigned long long v = *reinterpret_cast<const volatile unsigned long long*>(p);
+  Msg m;
+  m.d = (uint32_t)v;
+  m.f = (uint32_t)(v >> 32);
+  return m;
+}
+__device__ __forceinline__ void st_msg(unsigned long long* p, uint32_t d, uint32_t f) {
+  *reinterpret_cast<volatile unsigned long long*>(p) = (unsigned long long)d | ((unsigned long long)f << 32);
+}
+#endif
 // Every lane with `need` retries its word until it carries this launch's epoch; `m` is the copy that was
 // requested earlier.  Returns the data word (0 for lanes without need).
 __device__ __forceinline__ uint32_t wait_msg(const unsigned long long* p, Msg m, bool need, uint32_t epoch) {
