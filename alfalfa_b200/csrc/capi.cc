@@ -140,6 +140,8 @@ extern "C" {
 // internal hooks for encoder.cu
 Engine* vp8gpu_ctx_engine(vp8gpu_ctx* ctx) { return ctx->engine; }
 int vp8gpu_ctx_next_lane(vp8gpu_ctx* ctx) { return ctx->next_lane.fetch_add(1) % vp8::kMaxLanes; }
+// internal (encoder.cu): the flat frame behind a vp8gpu_parsed handle
+const vp8::ParsedFrame* vp8gpu_parsed_frame(const vp8gpu_parsed* p) { return p ? &p->f : nullptr; }
 
 int vp8gpu_ctx_create(int device, int width, int height, int max_frames, vp8gpu_ctx** out) {
   if (!out) return VP8GPU_ERR_LOGIC;
@@ -399,6 +401,10 @@ int vp8gpu_parse_frame(vp8gpu_state* state, const uint8_t* data, size_t len, vp8
   return rc;
 }
 
+int vp8gpu_parsed_y_ac_qi(const vp8gpu_parsed* p) {
+  if (!p || p->f.verbatim.header_tape.empty()) return -1;
+  return p->f.verbatim.y_ac_qi;
+}
 int vp8gpu_parsed_keep_labels(vp8gpu_parsed* p, int on) {
   if (!p) return VP8GPU_ERR_LOGIC;
   p->f.keep_verbatim = on != 0;

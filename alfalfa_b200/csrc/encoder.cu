@@ -27,6 +27,7 @@ using vp8::Engine;
 // shared with capi.cc
 extern "C" Engine* vp8gpu_ctx_engine(vp8gpu_ctx* ctx);
 extern "C" int vp8gpu_ctx_next_lane(vp8gpu_ctx* ctx);
+extern "C" const vp8::ParsedFrame* vp8gpu_parsed_frame(const vp8gpu_parsed* p);
 
 struct vp8gpu_encoder {
   vp8gpu_ctx* ctx = nullptr;
@@ -46,6 +47,8 @@ struct vp8gpu_encoder {
   uint8_t* dev = nullptr;
   size_t off_encjob = 0, off_sync = 0, off_mbs = 0, off_tokens = 0, off_tab = 0, dev_bytes = 0;
   uint32_t tok_cap = 0;
+  uint8_t* d_split = nullptr;  // update_residues: the prediction frame's split-MV side array on the device
+  size_t split_cap = 0;
   // pinned host buffers
   uint8_t* h_hdr = nullptr;      // EncJob + DevJob
   vp8gpu_mb* h_mbs = nullptr;
@@ -449,6 +452,7 @@ void vp8gpu_encoder_destroy(vp8gpu_encoder* enc) {
     if (enc->refs[k] >= 0) enc->e->frame_release(enc->refs[k]);
   if (enc->src >= 0) enc->e->frame_release(enc->src);
   if (enc->dev) cudaFree(enc->dev);
+  if (enc->d_split) cudaFree(enc->d_split);
   if (enc->h_hdr) cudaFreeHost(enc->h_hdr);
   if (enc->h_mbs) cudaFreeHost(enc->h_mbs);
   if (enc->h_tokens) cudaFreeHost(enc->h_tokens);
@@ -665,6 +669,242 @@ int vp8gpu_encoder_minihash(vp8gpu_encoder* enc, uint32_t* out) {
   rc = vp8gpu_decoder_hash(d, &h);
   vp8gpu_decoder_destroy(d);
   if (rc == VP8GPU_OK) *out = (uint32_t)(h ^ (h >> 32));  // same fold as Decoder::minihash
+  return rc;
+}
+
+// ---- re-encoding (encoder/reencode.cc) -------------------------------------------------
+
+// Encoder::write_frame's state update (encoder.cc:146-170): decode the emitted frame like any receiver
+// (Frame::decode + loopfilter + copy_to on the device, through the library's own Decoder) and adopt the
+// DecoderState and References it ends with.
+static int apply_emitted_frame(vp8gpu_encoder* enc, const uint8_t* data, size_t len) {
+  Engine* e = enc->e;
+  vp8gpu_decoder* d = nullptr;
+  int rc = vp8gpu_encoder_export_decoder(enc, &d);
+  if (rc != VP8GPU_OK) return rc;
+  int shown = 0;
+  vp8gpu_frame_id raster = -1;
+  rc = vp8gpu_decoder_decode(d, data, len, &shown, &raster);
+  if (rc == VP8GPU_OK) {
+    if (raster >= 0) e->frame_release(raster);
+    const std::vector<uint8_t> blob = [&] {
+      const vp8gpu_state* st = vp8gpu_decoder_state(d);
+      std::vector<uint8_t> b(vp8gpu_state_serialize(st, nullptr, 0));
+      vp8gpu_state_serialize(st, b.data(), b.size());
+      return b;
+    }();
+    if (!vp8::State::deserialize(blob.data(), blob.size(), *enc->dec_state)) rc = e->fail(VP8GPU_ERR_LOGIC, "write_frame: bad decoder state");
+  }
+  if (rc == VP8GPU_OK) {
+    vp8gpu_frame_id refs[3];
+    vp8gpu_decoder_references(d, refs);
+    for (int k = 0; k < 3; k++)
+      if (refs[k] >= 0) e->frame_retain(refs[k]);
+    for (int k = 0; k < 3; k++) {
+      if (enc->refs[k] >= 0) e->frame_release(enc->refs[k]);
+      enc->refs[k] = refs[k];
+    }
+    enc->has_state = true;
+    enc->stat_frames++;
+  }
+  vp8gpu_decoder_destroy(d);
+  return rc;
+}
+
+static int emit(vp8gpu_encoder* enc, const std::vector<uint8_t>& bytes, uint8_t* out, size_t cap, size_t* size) {
+  *size = bytes.size();
+  if (!out || cap < bytes.size()) return enc->e->fail(VP8GPU_ERR_NOMEM, "output buffer too small");
+  memcpy(out, bytes.data(), bytes.size());
+  return apply_emitted_frame(enc, bytes.data(), bytes.size());
+}
+
+// Encoder::write_frame( KeyFrame ) (encoder.cc:146-176) as Encoder::reencode uses it for a key frame that is kept
+// (reencode.cc option 3): Frame::serialize of the parsed frame -- its own bytes -- and the Encoder moves past it.
+int vp8gpu_encoder_write_frame(vp8gpu_encoder* enc, const vp8gpu_parsed* frame, uint8_t* out, size_t cap, size_t* size) {
+  const vp8::ParsedFrame* pf = vp8gpu_parsed_frame(frame);
+  if (!enc || !pf || !size) return VP8GPU_ERR_LOGIC;
+  if (!pf->desc.key_frame) return enc->e->fail(VP8GPU_ERR_UNSUPPORTED, "write_frame: only key frames are written back unchanged");
+  if (pf->desc.width != enc->e->width() || pf->desc.height != enc->e->height()) return enc->e->fail(VP8GPU_ERR_LOGIC, "write_frame: raster size mismatch");
+  cudaSetDevice(enc->e->device());
+  const std::vector<uint8_t> bytes = vp8::serialize_parsed(*pf);
+  if (bytes.empty()) return enc->e->fail(VP8GPU_ERR_LOGIC, "write_frame: the frame was parsed without vp8gpu_parsed_keep_labels");
+  const int rc = emit(enc, bytes, out, cap, size);
+  if (rc == VP8GPU_OK) {  // encoder.cc:164-167
+    enc->last_qi = pf->verbatim.y_ac_qi;
+    enc->last_lf = pf->verbatim.lf_level;
+  }
+  return rc;
+}
+
+// Encoder::update_residues + write_frame (encoder/reencode.cc:131-313): the prediction frame's modes, vectors,
+// references and header are kept, its residues are recomputed against THIS encoder's references so that the frame
+// decodes close to the target raster; y_ac_qi < 0 keeps the frame's own quantiser index (the deltas always stay).
+int vp8gpu_encoder_update_residues(vp8gpu_encoder* enc, const uint8_t* y, size_t y_stride, const uint8_t* u, const uint8_t* v,
+                                   size_t uv_stride, const vp8gpu_parsed* prediction_frame, int y_ac_qi, int last_frame, uint8_t* out,
+                                   size_t cap, size_t* size) {
+  const vp8::ParsedFrame* pf = vp8gpu_parsed_frame(prediction_frame);
+  if (!enc || !y || !u || !v || !pf || !size || y_ac_qi > 127) return VP8GPU_ERR_LOGIC;
+  Engine* e = enc->e;
+  const vp8::Geom& g = e->geom();
+  const vp8::Verbatim& vb = pf->verbatim;
+  const size_t n_mbs = (size_t)g.mb_cols * g.mb_rows;
+  if (pf->desc.key_frame) return e->fail(VP8GPU_ERR_LOGIC, "update_residues: the prediction frame is a key frame");
+  if (vb.header_tape.empty() || vb.mb_coded.size() != n_mbs)
+    return e->fail(VP8GPU_ERR_LOGIC, "update_residues: the prediction frame was parsed without vp8gpu_parsed_keep_labels");
+  if (pf->desc.mb_cols != g.mb_cols || pf->desc.mb_rows != g.mb_rows) return e->fail(VP8GPU_ERR_LOGIC, "update_residues: raster size mismatch");
+  if (!enc->has_state || enc->refs[0] < 0 || enc->refs[1] < 0 || enc->refs[2] < 0)
+    return e->fail(VP8GPU_ERR_LOGIC, "update_residues: the encoder has no references yet");
+  // The reference copies update_segmentation into the new header but not the macroblocks' segment ids (a blank
+  // frame's macroblocks carry none, reencode.cc:259, macroblock.cc:55-58): when the prediction frame updates the
+  // segment map the frame the reference writes cannot be parsed.  Not reproduced.  Segmentation without a map
+  // update is reproduced as it is: one Quantizer for the residues (reencode.cc:283) whatever the segments say.
+  if (vb.read_segment) return e->fail(VP8GPU_ERR_UNSUPPORTED, "update_residues: the prediction frame updates the segment map");
+  cudaSetDevice(e->device());
+  int rc = upload_source(enc, y, y_stride, u, v, uv_stride);
+  if (rc != VP8GPU_OK) return rc;
+  if (int lrc = e->ensure_lane(enc->lane)) return lrc;
+  cudaStream_t s = e->stream(enc->lane);
+
+  const int qi = y_ac_qi < 0 ? vb.y_ac_qi : y_ac_qi;
+  vp8gpu_quant q;  // Quantizer::Quantizer (quantization.cc:83-93) of the frame's indices with y_ac_qi replaced
+  q.y_ac = k_ac_q[clamp_q(qi)];
+  q.y_dc = k_dc_q[clamp_q(qi + vb.q_delta[0])];
+  q.y2_dc = static_cast<uint16_t>(k_dc_q[clamp_q(qi + vb.q_delta[1])] * 2);
+  q.y2_ac = static_cast<uint16_t>(k_ac_q[clamp_q(qi + vb.q_delta[2])] * 155 / 100);
+  q.uv_dc = k_dc_q[clamp_q(qi + vb.q_delta[3])];
+  q.uv_ac = k_ac_q[clamp_q(qi + vb.q_delta[4])];
+  if (q.y2_ac < 8) q.y2_ac = 8;
+  if (q.uv_dc > 132) q.uv_dc = 132;
+
+  // records: the frame's, with empty token lists (step 1 predicts, steps 2 and 4 fill the lists in)
+  size_t n_intra = 0;
+  for (size_t i = 0; i < n_mbs; i++) {
+    vp8gpu_mb m = pf->mbs.data()[i];
+    m.tok_off = 0;
+    m.tok_cnt = 0;
+    m.flags = (m.y_mode != VP8GPU_B_PRED && m.y_mode != VP8GPU_SPLITMV) ? VP8GPU_MB_HAS_Y2 : 0;
+    if (m.y_mode == VP8GPU_SPLITMV && m.split_idx >= pf->desc.n_split) return e->fail(VP8GPU_ERR_LOGIC, "update_residues: bad split index");
+    n_intra += m.ref_frame == VP8GPU_REF_CURRENT;
+    enc->h_mbs[i] = m;
+  }
+  const size_t split_bytes = (size_t)pf->desc.n_split * sizeof(vp8gpu_split_mvs);
+  if (split_bytes > enc->split_cap) {
+    if (enc->d_split) cudaFree(enc->d_split);
+    enc->d_split = nullptr;
+    enc->split_cap = 0;
+    if (cudaMalloc(&enc->d_split, n_mbs * sizeof(vp8gpu_split_mvs)) != cudaSuccess) return e->fail(VP8GPU_ERR_NOMEM, "update_residues: split buffer");
+    enc->split_cap = n_mbs * sizeof(vp8gpu_split_mvs);
+  }
+
+  int recon = -1;
+  rc = e->frame_alloc(&recon);
+  if (rc != VP8GPU_OK) return rc;
+  auto fail = [&](int code) {
+    e->frame_release(recon);
+    return code;
+  };
+  int ids[5] = {enc->src, recon, enc->refs[0], -1, -1};
+  int n_ids = 3;
+  for (int k = 1; k < 3; k++) {
+    bool dup = false;
+    for (int j = 2; j < n_ids; j++) dup |= ids[j] == enc->refs[k];
+    if (!dup) ids[n_ids++] = enc->refs[k];
+  }
+  rc = e->acquire_frames(enc->lane, ids, n_ids, 2u);  // only `recon` is written
+  if (rc != VP8GPU_OK) return fail(rc);
+
+  memset(enc->h_hdr, 0, 1024);
+  vp8::ReencJob* rj = reinterpret_cast<vp8::ReencJob*>(enc->h_hdr);
+  vp8::DevJob* dj = reinterpret_cast<vp8::DevJob*>(enc->h_hdr + 512);
+  int* d_sync = reinterpret_cast<int*>(enc->dev + enc->off_sync);
+  vp8gpu_mb* d_mbs = reinterpret_cast<vp8gpu_mb*>(enc->dev + enc->off_mbs);
+  vp8gpu_token* d_tok = reinterpret_cast<vp8gpu_token*>(enc->dev + enc->off_tokens);
+  rj->target = e->frame_dev(enc->src);
+  rj->recon = e->frame_dev(recon);
+  rj->mbs_in = d_mbs;
+  rj->mbs_out = d_mbs;
+  rj->tokens = d_tok;
+  rj->tok_counter = reinterpret_cast<uint32_t*>(d_sync + 96);
+  rj->tok_cap = enc->tok_cap;
+  rj->progress = d_sync + 128;
+  rj->q = q;
+  rj->cols = (uint16_t)g.mb_cols;
+  rj->rows = (uint16_t)g.mb_rows;
+  dj->mbs = d_mbs;
+  dj->tokens = d_tok;
+  dj->split = reinterpret_cast<const vp8gpu_split_mvs*>(enc->d_split);
+  dj->out = e->frame_dev(recon);
+  for (int k = 0; k < 3; k++) {
+    dj->ref[k] = e->frame_dev(enc->refs[k]);
+    dj->ref_tmap[k] = e->frame_tmaps(enc->refs[k]);
+  }
+  dj->intra_progress = d_sync + 128;
+  dj->lf_progress = d_sync + 128 + g.mb_rows;
+  for (int k = 0; k < 4; k++) dj->quant[k] = q;
+#define CUF(call)                                                        \
+  do {                                                                   \
+    cudaError_t e__ = (call);                                            \
+    if (e__ != cudaSuccess) return fail(e->cuda_fail(e__, #call));       \
+  } while (0)
+  CUF(cudaMemcpyAsync(enc->dev + enc->off_encjob, enc->h_hdr, 1024, cudaMemcpyHostToDevice, s));
+  CUF(cudaMemcpyAsync(d_mbs, enc->h_mbs, n_mbs * sizeof(vp8gpu_mb), cudaMemcpyHostToDevice, s));
+  if (split_bytes) CUF(cudaMemcpyAsync(enc->d_split, pf->split.data(), split_bytes, cudaMemcpyHostToDevice, s));
+  CUF(cudaMemsetAsync(d_sync, 0, sizeof(int) * (128 + 2 * (size_t)g.mb_rows), s));
+  const vp8::ReencJob* d_rj = reinterpret_cast<const vp8::ReencJob*>(enc->dev + enc->off_encjob);
+  const vp8::DevJob* d_dj = reinterpret_cast<const vp8::DevJob*>(enc->dev + enc->off_encjob + 512);
+  int launches = 0;
+  if (n_intra < n_mbs) {
+    if (int ce = vp8::launch_inter(d_dj, 1, g, s)) return fail(e->cuda_fail((cudaError_t)ce, "k_inter (prediction)"));
+    if (int ce = vp8::launch_reenc_inter(d_rj, (int)n_mbs, g, s)) return fail(e->cuda_fail((cudaError_t)ce, "k_reenc_inter"));
+    if (int ce = vp8::launch_inter(d_dj, 1, g, s)) return fail(e->cuda_fail((cudaError_t)ce, "k_inter (reconstruction)"));
+    launches += 3;
+  }
+  if (n_intra) {
+    if (int ce = vp8::launch_reenc_intra(d_rj, g.mb_rows, g, d_sync + 0, s)) return fail(e->cuda_fail((cudaError_t)ce, "k_reenc_intra"));
+    launches++;
+  }
+  e->count_launches(launches);
+  e->mark_frames(enc->lane, ids, n_ids, 2u);
+  CUF(cudaMemcpyAsync(enc->h_count, rj->tok_counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CUF(cudaMemcpyAsync(enc->h_mbs, d_mbs, n_mbs * sizeof(vp8gpu_mb), cudaMemcpyDeviceToHost, s));
+  CUF(cudaStreamSynchronize(s));
+  const uint32_t n_tok = *enc->h_count;
+  if (n_tok > enc->tok_cap) return fail(e->fail(VP8GPU_ERR_NOMEM, "update_residues: token pool overflow"));
+  if (n_tok) {
+    CUF(cudaMemcpyAsync(enc->h_tokens, d_tok, (size_t)n_tok * sizeof(vp8gpu_token), cudaMemcpyDeviceToHost, s));
+    CUF(cudaStreamSynchronize(s));
+  }
+#undef CUF
+  e->frame_release(recon);  // the reference discards its reconstruction too: write_frame decodes the frame it wrote
+
+  // ---- the frame: header sections of the prediction frame + the reference Encoder's probability decisions ----
+  vp8::EncodeHeader h;
+  h.key_frame = false;
+  h.show_frame = true;  // InterFrame( width, height ): a new frame object is shown
+  h.width = e->width();
+  h.height = e->height();
+  h.y_ac_qi = qi;
+  vp8::EncodeFeatures ft;
+  vp8::EncodeFeatures::RefWriterState fresh;  // update_residues builds a new InterFrame object every time
+  fresh.prob_last = vb.prob_last;              // prob_references_* are copied from the prediction frame (reencode.cc:266-267)
+  fresh.prob_golden = vb.prob_golden;
+  ft.ref_writer = &fresh;
+  ft.residue_of = &vb;
+  ft.residue_refresh_all = last_frame != 0;
+  ft.log2_partitions = 0;
+  uint8_t probs[1056];
+  memcpy(probs, enc->dec_state->coef_probs, 1056);
+  ft.saved_coef_probs = probs;
+  ft.ymode_probs = enc->dec_state->ymode_probs;
+  ft.uvmode_probs = enc->dec_state->uvmode_probs;
+  ft.mv_probs = enc->dec_state->mv_probs;
+  const std::vector<uint8_t> bytes = vp8::serialize_frame(h, enc->h_mbs, enc->h_tokens, pf->split.data(), &ft);
+  if (bytes.empty()) return e->fail(VP8GPU_ERR_LOGIC, "update_residues: serializer rejected the records");
+  rc = emit(enc, bytes, out, cap, size);
+  if (rc == VP8GPU_OK) {  // write_frame, REALTIME_QUALITY (encoder.cc:164-167)
+    enc->last_qi = qi;
+    enc->last_lf = vb.lf_level;
+  }
   return rc;
 }
 

@@ -81,6 +81,21 @@ struct EncJob {
   uint8_t pad[2];
 };
 
+// Encoder::update_residues on the device (reencode.cuh): keep a coded frame's modes and vectors, recompute its
+// residues against the current references so that it decodes close to `target`.
+struct ReencJob {
+  const uint8_t* target;   // the raster to approximate (update_residues' original_raster)
+  uint8_t* recon;          // in: every inter macroblock predicted / reconstructed by k_inter; out: + the intra ones
+  const vp8gpu_mb* mbs_in; // the coded frame's records (modes, vectors, references); may alias mbs_out
+  vp8gpu_mb* mbs_out;      // the same records with the new tok_off / tok_cnt
+  vp8gpu_token* tokens;    // token pool
+  uint32_t* tok_counter;   // tokens used so far (atomic)
+  uint32_t tok_cap;
+  int* progress;           // [rows] wavefront counters (zeroed)
+  vp8gpu_quant q;          // Quantizer( quant_indices ): one for the whole frame (reencode.cc:283)
+  uint16_t cols, rows;
+};
+
 // One frame's token-decode job (tokens.cu): DCT partitions -> token stream + tok_off / tok_cnt.
 struct TokJob {
   vp8gpu_mb* mbs;             // in: y_mode, VP8GPU_MB_SKIP; out: tok_off, tok_cnt, flag cleared
@@ -98,6 +113,8 @@ struct TokJob {
 // Kernel launchers (kernels.cu, tokens.cu).  `stream` is a cudaStream_t passed as void* so this header
 // stays free of CUDA includes.  Return 0 or a cudaError_t value.
 int launch_inter(const DevJob* jobs, int njobs, const Geom& g, void* stream);
+int launch_reenc_inter(const ReencJob* job, int n_mbs, const Geom& g, void* stream);
+int launch_reenc_intra(const ReencJob* job, int rows, const Geom& g, int* ticket, void* stream);
 // `epoch`: a value no earlier launch on this context has used (Engine::next_epoch); it marks the hand-over
 // messages of this launch.  epoch == 0 selects the round-1 kernels (progress counters + acquire / release).
 int launch_intra(const DevJob* jobs, int njobs, const Geom& g, int* ticket, uint32_t epoch, void* stream);

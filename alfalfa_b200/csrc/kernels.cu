@@ -1851,6 +1851,8 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __res
   }
 }
 
+#include "reencode.cuh"
+
 // ================================================================================================
 // k_compare: References::operator== (decoder.cc:249-254) on the device; flag != 0 when any visible
 // pixel of the MB-aligned planes differs (pitch padding is ignored).
@@ -1972,6 +1974,15 @@ int launch_loopfilter(const DevJob* jobs, int njobs, const Geom& g, int* ticket,
 
 int launch_enc_rd(const EncJob* job, int rows, const Geom& g, int* ticket, void* stream) {
   VP8_LAUNCH(k_enc_rd, (rows + WF_WARPS - 1) / WF_WARPS, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream))(job, g, ticket);
+  return (int)cudaGetLastError();
+}
+
+int launch_reenc_inter(const ReencJob* job, int n_mbs, const Geom& g, void* stream) {
+  VP8_LAUNCH(k_reenc_inter, (n_mbs + REENC_WARPS - 1) / REENC_WARPS, 32 * REENC_WARPS, 0, static_cast<cudaStream_t>(stream))(job, g);
+  return (int)cudaGetLastError();
+}
+int launch_reenc_intra(const ReencJob* job, int rows, const Geom& g, int* ticket, void* stream) {
+  VP8_LAUNCH(k_reenc_intra, (rows + WF_WARPS - 1) / WF_WARPS, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream))(job, g, ticket);
   return (int)cudaGetLastError();
 }
 

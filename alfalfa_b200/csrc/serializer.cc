@@ -538,7 +538,7 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
   // ---- first partition: frame header ----
   BoolWriter bw;
   const Verbatim* const ro = x.residue_of;
-  if (ro && (vb || !x.ref_writer || h.key_frame || ro->key || ro->seg_enabled || ro->mark_qend > ro->header_tape.size())) return {};
+  if (ro && (vb || !x.ref_writer || h.key_frame || ro->key || ro->read_segment || ro->mark_qend > ro->header_tape.size())) return {};
   if (vb) {
     for (const uint16_t d : vb->header_tape) bw.put(d & 1, d >> 1);
   } else if (ro) {

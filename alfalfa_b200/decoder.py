@@ -263,9 +263,13 @@ class Decoder:
             out.append(RasterHandle(self.ctx, i))
         return tuple(out)
 
-    def parse_frame(self, chunk):
-        """Decoder::decompress_frame + parse_frame: updates the decoder's state"""
+    def parse_frame(self, chunk, keep_labels=False):
+        """Decoder::decompress_frame + parse_frame: updates the decoder's state.  keep_labels: keep the header as coded
+        and every ambiguous label, like the reference's Frame object does (needed by ParsedFrame re-serialisation
+        and by Encoder.reencode)"""
         p = ParsedFrame()
+        if keep_labels:
+            check(self.L.vp8gpu_parsed_keep_labels(p.h, 1), self.ctx.h, "keep_labels")
         st = C.c_void_p(self.L.vp8gpu_decoder_state(self.h))
         check(self.L.vp8gpu_parse_frame(st, chunk, len(chunk), p.h), self.ctx.h, "parse_frame")
         return p
@@ -471,6 +475,77 @@ class Encoder:
         check(self.L.vp8gpu_encoder_estimate_frame_size(self.h, y.ctypes.data, y.shape[1], u.ctypes.data, v.ctypes.data,
                                                         u.shape[1], y_ac_qi, C.byref(size)), self.ctx.h, "estimate_frame_size")
         return size.value
+
+    def update_residues(self, y, u, v, prediction_frame, y_ac_qi=-1, last_frame=False):
+        """Encoder::update_residues + write_frame (encoder/reencode.cc:131-313): keep the prediction frame's modes
+        and vectors, recompute its residues against this encoder's references towards the target planes"""
+        y, u, v = self._planes(y, u, v)
+        size = C.c_size_t(0)
+        check(self.L.vp8gpu_encoder_update_residues(self.h, y.ctypes.data, y.shape[1], u.ctypes.data, v.ctypes.data, u.shape[1],
+                                                    prediction_frame.h, int(y_ac_qi), int(bool(last_frame)), self._out.ctypes.data,
+                                                    self._out.size, C.byref(size)), self.ctx.h, "update_residues")
+        return self._out[:size.value].tobytes()
+
+    def write_frame(self, frame):
+        """Encoder::write_frame( KeyFrame ) (encoder.cc:146-176): emit a parsed key frame unchanged, move past it"""
+        size = C.c_size_t(0)
+        check(self.L.vp8gpu_encoder_write_frame(self.h, frame.h, self._out.ctypes.data, self._out.size, C.byref(size)), self.ctx.h,
+              "write_frame")
+        return self._out[:size.value].tobytes()
+
+    def reencode(self, original_rasters, prediction_frames, kf_q_weight=1.0, extra_frame_chunk=False):
+        """Encoder::reencode (encoder/reencode.cc:315-381), statement for statement.  original_rasters: (y, u, v)
+        planes per frame; prediction_frames: ParsedFrame per frame, parsed with keep_labels by the prediction
+        stream's own decoder state.  Returns the list of emitted frames (what the reference appends to its IVFWriter)."""
+        if not original_rasters:
+            raise RuntimeError("no rasters to re-encode")
+        if len(original_rasters) != len(prediction_frames):
+            raise RuntimeError("prediction/original_rasters mismatch")
+        out = []
+        start = 1 if extra_frame_chunk else 0
+
+        def qi_of(f):
+            q = self.L.vp8gpu_parsed_y_ac_qi(f.h)
+            if q < 0:
+                raise capi.LogicError(capi.ERR_LOGIC, "reencode: prediction frames must be parsed with keep_labels")
+            return q
+
+        def lrint(x):  # round half to even, like lrint in the default rounding mode
+            return int(round(x))
+
+        for i in range(start, len(original_rasters)):
+            y, u, v = original_rasters[i]
+            pred = prediction_frames[i]
+            last = i == len(prediction_frames) - 1
+            is_key = bool(pred.desc.key_frame)
+            if i == start and is_key:
+                # option 1: an initial key frame becomes an inter frame (reencode_as_interframe, reencode.cc:39-129)
+                qi = qi_of(pred)
+                if i + 1 < len(prediction_frames) and not prediction_frames[i + 1].desc.key_frame:
+                    qi = lrint(kf_q_weight * qi_of(pred) + (1 - kf_q_weight) * qi_of(prediction_frames[i + 1]))
+                out.append(self.reencode_as_interframe(y, u, v, pred, qi))
+            elif i == start and extra_frame_chunk:
+                # option 2: first inter frame of an extra-frame chunk: blend in the key frame's quantiser
+                if not prediction_frames[0].desc.key_frame:
+                    raise RuntimeError("extra-frame chunks must start with a keyframe.")
+                qi = lrint(kf_q_weight * qi_of(prediction_frames[0]) + (1 - kf_q_weight) * qi_of(pred))
+                out.append(self.update_residues(y, u, v, pred, qi, last))
+            elif is_key:
+                out.append(self.write_frame(pred))      # option 3: another key frame is preserved
+            else:
+                out.append(self.update_residues(y, u, v, pred, -1, last))  # option 4
+        return out
+
+    def reencode_as_interframe(self, y, u, v, key_frame, y_ac_qi):
+        """Encoder::reencode_as_interframe (encoder/reencode.cc:39-129)"""
+        y, u, v = self._planes(y, u, v)
+        size = C.c_size_t(0)
+        if not hasattr(self.L, "vp8gpu_encoder_reencode_as_interframe"):
+            raise capi.Unsupported(capi.ERR_UNSUPPORTED, "reencode_as_interframe is not built")
+        check(self.L.vp8gpu_encoder_reencode_as_interframe(self.h, y.ctypes.data, y.shape[1], u.ctypes.data, v.ctypes.data, u.shape[1],
+                                                           key_frame.h, int(y_ac_qi), self._out.ctypes.data, self._out.size,
+                                                           C.byref(size)), self.ctx.h, "reencode_as_interframe")
+        return self._out[:size.value].tobytes()
 
     def stats(self):
         """EncoderStats of the last frame: dict(ssim, loop_filter_level, y_ac_qi)"""

@@ -438,6 +438,28 @@ int vp8gpu_encoder_encode_with_minimum_ssim(vp8gpu_encoder* enc, const uint8_t* 
  * multiplied by 16 (size_estimation.cc:36-181).  Does not change the encoder's state. */
 int vp8gpu_encoder_estimate_frame_size(vp8gpu_encoder* enc, const uint8_t* y, size_t y_stride, const uint8_t* u,
                                        const uint8_t* v, size_t uv_stride, int y_ac_qi, size_t* size);
+/* ---- re-encoding (encoder/reencode.cc; ExCamera's "xc-enc --reencode", frontend/xc-enc.cc:262-327) ----
+ * The chunk's frames as they were coded independently ("prediction frames") are parsed by their own decoder
+ * state with vp8gpu_parsed_keep_labels on (the reference keeps them as KeyFrame / InterFrame objects); the Encoder
+ * was built from the Decoder a receiver has when the chunk starts (vp8gpu_encoder_create_from_decoder).
+ *
+ * vp8gpu_encoder_update_residues = Encoder::update_residues + write_frame (reencode.cc:131-313, encoder.cc:146-170):
+ * the prediction frame's header, modes, vectors and reference choices are kept; the residues are recomputed on the
+ * device against THIS encoder's references so that the frame decodes as close as possible to the target planes
+ * (display size, host); the emitted frame is then decoded like any receiver would to advance the Encoder.
+ * y_ac_qi < 0 keeps the frame's own quantiser index (its deltas are always kept); last_frame != 0 makes the frame
+ * refresh all three references (reencode.cc:269-275).  VP8GPU_ERR_UNSUPPORTED for frames with segmentation (the
+ * reference writes a frame there that does not decode to its own reconstruction). */
+int vp8gpu_encoder_update_residues(vp8gpu_encoder* enc, const uint8_t* y, size_t y_stride, const uint8_t* u,
+                                   const uint8_t* v, size_t uv_stride, const vp8gpu_parsed* prediction_frame, int y_ac_qi,
+                                   int last_frame, uint8_t* out, size_t cap, size_t* size);
+/* Encoder::write_frame( KeyFrame ) (encoder.cc:146-176) as Encoder::reencode uses it for a key frame that is
+ * kept (reencode.cc:363-365): the frame's own bytes are emitted and the Encoder moves past it. */
+int vp8gpu_encoder_write_frame(vp8gpu_encoder* enc, const vp8gpu_parsed* frame, uint8_t* out, size_t cap, size_t* size);
+/* header().quant_indices.y_ac_qi of a frame parsed with vp8gpu_parsed_keep_labels (Encoder::reencode blends the
+ * quantisers of neighbouring prediction frames, reencode.cc:334-361); -1 without kept labels */
+int vp8gpu_parsed_y_ac_qi(const vp8gpu_parsed* p);
+
 /* EncoderStats (encoder.hh:118-127) of the last frame; any pointer may be NULL. */
 int vp8gpu_encoder_stats(const vp8gpu_encoder* enc, double* ssim, int* loop_filter_level, int* y_ac_qi);
 /* the reconstruction of the last encoded frame = the decoder's LAST reference after decoding it

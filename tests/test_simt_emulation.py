@@ -65,3 +65,17 @@ def test_both_wavefront_protocols_emulated(simt_lib, mode):
 def test_stream_decode_and_device_token_decoder_emulated(simt_lib):
     """vp8gpu_decode_ivf with worker / dispatcher threads, host tokens and k_tokens; mid-stream failure unwinding"""
     run_gpu_tests_emulated(simt_lib, ["tests/test_gpu_parity.py", "-k", "not fileplayer and not full_size and not ff2941 and not every_frame"])
+
+
+def test_reencode_against_the_reference_emulated(simt_lib):
+    """Encoder::reencode / update_residues (SURVEY 8 f3): k_reenc_inter / k_reenc_intra + the host orchestration,
+    byte for byte against oracle/_ref/ref_reencode on reference-encoder and libvpx prediction streams"""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_reencode")):
+        pytest.skip("oracle/_ref/ref_reencode not built (make -C oracle ref)")
+    run_gpu_tests_emulated(simt_lib, ["tests/test_gpu_reencode.py"])
+
+
+def test_encoder_against_the_reference_encoder_emulated(simt_lib):
+    """k_enc_rd + the encoder's host side: decisions equal to the unmodified reference encoder's, closed loop,
+    target-size search, loop-filter choice, value semantics (the 1080p cases stay on the GPU: minutes here)"""
+    run_gpu_tests_emulated(simt_lib, ["tests/test_gpu_encoder.py", "-k", "not rd_parity and not first_inter_frame and not size3"])
