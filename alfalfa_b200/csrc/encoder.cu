@@ -39,8 +39,12 @@ struct vp8gpu_encoder {
   int src = -1;                // device raster holding the (edge-extended) source frame
   int last_qi = -1;            // last_y_ac_qi_ (REALTIME_QUALITY, encoder.cc:164-167)
   int last_lf = -1;            // loop_filter_level_ (encoder.hh:144): -1 = not initialised
-  bool mv_costs_filled = false;  // Costs::fill_mv_component_costs / fill_mv_sad_costs have run (encode_inter.cc:601-602: at the
-                                 // start of the first full inter-frame pass of this Encoder or of the one it was copied from)
+  bool mv_costs_filled = false;  // Costs::fill_mv_component_costs has run (encode_inter.cc:601: at the start of the first full
+                                 // inter-frame pass of this Encoder or of the one it was copied from; reencode.cc:85)
+  bool mv_sad_filled = false;    // Costs::fill_mv_sad_costs has run (encode_inter.cc:602 only)
+  uint32_t rd_rate = 300, rd_dist = 1;  // RATE_MULTIPLIER / DISTORTION_MULTIPLIER (encoder.hh:152-153) as the last
+                                        // update_rd_multipliers left them; a copy starts from the defaults again
+  int lf_sharpness = 0;          // sharpness_level of the frame being built (0 for the Encoder's own frames)
   double last_ssim = -1.0;     // encode_stats_.ssim of the last frame
   vp8::State* dec_state = nullptr;  // DecoderState a decoder has after the frames emitted so far (export_decoder)
   // device scratch: EncJob | DevJob | sync ints | mbs | tokens | rate tables
@@ -97,7 +101,9 @@ void pass_dims(const vp8gpu_encoder* enc, int sub, int* w, int* h, int* cols, in
 }
 
 // launch half of a pass: everything up to the asynchronous download of the token count and the records
-int encode_launch(vp8gpu_encoder* enc, bool key, int qi, int sub) {
+// reenc != nullptr: a pass of Encoder::reencode_as_interframe (reencode.cc:39-129) -- the quantiser comes with the
+// call (a key frame's indices with another y_ac_qi), update_rd_multipliers and fill_mv_sad_costs are NOT run
+int encode_launch(vp8gpu_encoder* enc, bool key, int qi, int sub, const vp8gpu_quant* reenc = nullptr) {
   Engine* e = enc->e;
   const vp8::Geom& g = e->geom();
   int pw, ph, cols, rows;
@@ -127,8 +133,10 @@ int encode_launch(vp8gpu_encoder* enc, bool key, int qi, int sub) {
   ej->tok_cap = enc->tok_cap;
   ej->progress = d_sync + 128;
   ej->tab = reinterpret_cast<const vp8::EncTables*>(enc->dev + enc->off_tab);
-  ej->q = make_quant(qi);
-  vp8::rd_multipliers(ej->q.y_ac, &ej->rate_mult, &ej->dist_mult);
+  ej->q = reenc ? *reenc : make_quant(qi);
+  if (!reenc) vp8::rd_multipliers(ej->q.y_ac, &enc->rd_rate, &enc->rd_dist);
+  ej->rate_mult = enc->rd_rate;
+  ej->dist_mult = enc->rd_dist;
   ej->cols = (uint16_t)cols;
   ej->rows = (uint16_t)rows;
   ej->sub = (uint8_t)sub;
@@ -136,8 +144,12 @@ int encode_launch(vp8gpu_encoder* enc, bool key, int qi, int sub) {
   ej->lf_level = 1;  // records carry "filtered"; the level itself is chosen afterwards (choose_loop_filter)
   ej->sad_per_bit = k_sad_per_bit16[clamp_q(qi)];
   ej->realtime = 1;  // REALTIME_QUALITY, what Salsify runs (salsify-sender.cc:287-288)
-  if (!key && sub == 1) enc->mv_costs_filled = true;  // encode_raster<InterFrame> fills the tables before it uses them
+  if (!key && sub == 1) {  // encode_raster<InterFrame> / reencode_as_interframe fill the tables before they use them
+    enc->mv_costs_filled = true;
+    if (!reenc) enc->mv_sad_filled = true;
+  }
   ej->mv_costs_zero = !key && !enc->mv_costs_filled;
+  ej->mv_sad_zero = !key && !enc->mv_sad_filled;
   auto fail = [&](int code) {
     e->frame_release(out);
     return code;
@@ -188,8 +200,8 @@ int encode_collect(vp8gpu_encoder* enc, int* out_frame) {
 
 // One encoding pass at quantiser index qi over the whole frame (sub = 1) or the 1/16 sample (sub = 4):
 // decisions, transforms, reconstruction on the device; records and tokens back on the host.
-int encode_core(vp8gpu_encoder* enc, bool key, int qi, int sub, int* out_frame) {
-  const int rc = encode_launch(enc, key, qi, sub);
+int encode_core(vp8gpu_encoder* enc, bool key, int qi, int sub, int* out_frame, const vp8gpu_quant* reenc = nullptr) {
+  const int rc = encode_launch(enc, key, qi, sub, reenc);
   return rc == VP8GPU_OK ? encode_collect(enc, out_frame) : rc;
 }
 
@@ -251,7 +263,7 @@ int filter_frame(vp8gpu_encoder* enc, int frame, bool key, int level) {
   dj->lf_progress = d_sync + 128 + g.mb_rows;
   dj->intra_progress = d_sync + 128;
   dj->key_frame = key;
-  dj->sharpness = 0;
+  dj->sharpness = (uint8_t)enc->lf_sharpness;
   dj->lf_enabled = 1;
   dj->lf_force = (uint8_t)level;
   int ids[1] = {frame};
@@ -401,6 +413,7 @@ int vp8gpu_encoder_clone(const vp8gpu_encoder* src, vp8gpu_encoder** out) {
   enc->last_qi = src->last_qi;
   enc->last_lf = src->last_lf;
   enc->mv_costs_filled = src->mv_costs_filled;  // costs_( encoder.costs_ ), encoder.cc:96
+  enc->mv_sad_filled = src->mv_sad_filled;
   enc->last_ssim = src->last_ssim;
   *enc->dec_state = *src->dec_state;
   for (int k = 0; k < 3; k++) {
@@ -904,6 +917,80 @@ int vp8gpu_encoder_update_residues(vp8gpu_encoder* enc, const uint8_t* y, size_t
   if (rc == VP8GPU_OK) {  // write_frame, REALTIME_QUALITY (encoder.cc:164-167)
     enc->last_qi = qi;
     enc->last_lf = vb.lf_level;
+  }
+  return rc;
+}
+
+// Encoder::reencode_as_interframe + write_frame (encoder/reencode.cc:39-129, 343-351): the chunk's initial key
+// frame is coded again as an inter frame predicted from this encoder's LAST -- the ordinary inter-frame decision loop
+// (k_enc_rd) at the key frame's quantiser indices with y_ac_qi replaced, without update_rd_multipliers and
+// fill_mv_sad_costs (the reference does not call them here), the key frame's sharpness, all references refreshed.
+int vp8gpu_encoder_reencode_as_interframe(vp8gpu_encoder* enc, const uint8_t* y, size_t y_stride, const uint8_t* u, const uint8_t* v,
+                                          size_t uv_stride, const vp8gpu_parsed* key_frame, int y_ac_qi, uint8_t* out, size_t cap,
+                                          size_t* size) {
+  const vp8::ParsedFrame* pf = vp8gpu_parsed_frame(key_frame);
+  if (!enc || !y || !u || !v || !pf || !size || y_ac_qi < 0 || y_ac_qi > 127) return VP8GPU_ERR_LOGIC;
+  Engine* e = enc->e;
+  const vp8::Verbatim& vb = pf->verbatim;
+  if (!pf->desc.key_frame) return e->fail(VP8GPU_ERR_LOGIC, "reencode_as_interframe: not a key frame");
+  if (vb.header_tape.empty()) return e->fail(VP8GPU_ERR_LOGIC, "reencode_as_interframe: the frame was parsed without vp8gpu_parsed_keep_labels");
+  if (pf->desc.width != e->width() || pf->desc.height != e->height()) return e->fail(VP8GPU_ERR_LOGIC, "reencode_as_interframe: raster size mismatch");
+  if (vb.seg_enabled) return e->fail(VP8GPU_ERR_UNSUPPORTED, "segmentation not supported");  // reencode.cc:49-51
+  if (!enc->has_state || enc->refs[0] < 0) return e->fail(VP8GPU_ERR_LOGIC, "reencode_as_interframe: the encoder has no references yet");
+  // Costs::fill_mv_component_costs( temp_tables.motion_vector_probs ) (reencode.cc:82-85): the rate tables on the
+  // device are those of the default motion-vector probabilities, which is what an Encoder that only ever saw its own
+  // frames (or the reference encoder's) has; another table would need its own upload
+  if (memcmp(enc->dec_state->mv_probs, k_mv_default_probs, 38) != 0)
+    return e->fail(VP8GPU_ERR_UNSUPPORTED, "reencode_as_interframe: the decoder state carries updated motion-vector probabilities");
+  cudaSetDevice(e->device());
+  int rc = upload_source(enc, y, y_stride, u, v, uv_stride);
+  if (rc != VP8GPU_OK) return rc;
+  vp8gpu_quant q;
+  q.y_ac = k_ac_q[clamp_q(y_ac_qi)];
+  q.y_dc = k_dc_q[clamp_q(y_ac_qi + vb.q_delta[0])];
+  q.y2_dc = static_cast<uint16_t>(k_dc_q[clamp_q(y_ac_qi + vb.q_delta[1])] * 2);
+  q.y2_ac = static_cast<uint16_t>(k_ac_q[clamp_q(y_ac_qi + vb.q_delta[2])] * 155 / 100);
+  q.uv_dc = k_dc_q[clamp_q(y_ac_qi + vb.q_delta[3])];
+  q.uv_ac = k_ac_q[clamp_q(y_ac_qi + vb.q_delta[4])];
+  if (q.y2_ac < 8) q.y2_ac = 8;
+  if (q.uv_dc > 132) q.uv_dc = 132;
+
+  int frame = -1, lf = 0;
+  double ssim = -1.0;
+  rc = encode_core(enc, false, y_ac_qi, 1, &frame, &q);
+  if (rc != VP8GPU_OK) return rc;
+  enc->lf_sharpness = pf->desc.sharpness;
+  rc = choose_loop_filter(enc, frame, false, &lf, &ssim);  // apply_best_loopfilter_settings (reencode.cc:126)
+  enc->lf_sharpness = 0;
+  e->frame_release(frame);  // write_frame decodes the frame it wrote (encoder.cc:153-158)
+  if (rc != VP8GPU_OK) return rc;
+
+  vp8::EncodeHeader h;
+  h.key_frame = false;
+  h.show_frame = true;
+  h.width = e->width();
+  h.height = e->height();
+  h.y_ac_qi = y_ac_qi;
+  h.loop_filter_level = lf;
+  h.sharpness = pf->desc.sharpness;
+  vp8::EncodeFeatures ft;
+  vp8::EncodeFeatures::RefWriterState fresh;  // a new InterFrame object
+  ft.ref_writer = &fresh;
+  ft.from_key = &vb;
+  ft.log2_partitions = 0;
+  ft.refresh_golden = ft.refresh_alternate = ft.refresh_last = true;
+  ft.refresh_entropy_probs = true;
+  uint8_t probs[1056];
+  memcpy(probs, enc->dec_state->coef_probs, 1056);
+  ft.saved_coef_probs = probs;
+  ft.mv_probs = enc->dec_state->mv_probs;  // the mode probabilities are the defaults the header itself sets
+  std::vector<uint8_t> bytes = vp8::serialize_frame(h, enc->h_mbs, enc->h_tokens, nullptr, &ft);
+  if (bytes.empty()) return e->fail(VP8GPU_ERR_LOGIC, "reencode_as_interframe: serializer rejected the device records");
+  rc = emit(enc, bytes, out, cap, size);
+  if (rc == VP8GPU_OK) {
+    enc->last_qi = y_ac_qi;
+    enc->last_lf = lf;
+    enc->last_ssim = ssim;
   }
   return rc;
 }

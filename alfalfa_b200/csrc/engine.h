@@ -78,7 +78,9 @@ struct EncJob {
   uint8_t mv_costs_zero;   // the reference fills its motion-vector cost tables (Costs::fill_mv_component_costs,
                            //   fill_mv_sad_costs) at the start of the first FULL inter-frame pass (encode_inter.cc:601-602);
                            //   the size estimates that precede it price every vector at 0
-  uint8_t pad[2];
+  uint8_t mv_sad_zero;     // the same for the diamond search's vector cost alone (Costs::fill_mv_sad_costs): Encoder::
+                           //   reencode_as_interframe fills the component costs but not these (reencode.cc:85)
+  uint8_t pad[1];
 };
 
 // Encoder::update_residues on the device (reencode.cuh): keep a coded frame's modes and vectors, recompute its

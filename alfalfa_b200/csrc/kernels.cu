@@ -1601,7 +1601,7 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __res
               const uint32_t sad = enc_sad(src, S.pcand[cur], lane);
               const int sx = max(min(cx >> 2, 255), -255), sy = max(min(cy >> 2, 255), -255);
               const uint32_t rate =
-                  J.mv_costs_zero ? 0u : ((uint32_t)(T.mv_sad_cost[abs(sy)] + T.mv_sad_cost[abs(sx)]) * J.sad_per_bit + 128u) / 256u;
+                  J.mv_sad_zero ? 0u : ((uint32_t)(T.mv_sad_cost[abs(sy)] + T.mv_sad_cost[abs(sx)]) * J.sad_per_bit + 128u) / 256u;
               const uint32_t c = ((128u + rate) / 256u) + sad;  // rdcost( rate, distortion, 1, 1 )
               if (c < bc) bc = c, bx2 = cx, by2 = cy;
             }

@@ -619,11 +619,17 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
     }
     bw.literal(x.log2_partitions, 2);
     bw.literal(h.y_ac_qi, 7);
-    put_flagged_signed(bw, x.y_dc_delta, 4);
-    put_flagged_signed(bw, x.y2_dc_delta, 4);
-    put_flagged_signed(bw, x.y2_ac_delta, 4);
-    put_flagged_signed(bw, x.uv_dc_delta, 4);
-    put_flagged_signed(bw, x.uv_ac_delta, 4);
+    if (x.from_key) {
+      if (!x.from_key->key || x.from_key->mark_qend > x.from_key->header_tape.size()) return {};
+      for (uint32_t i = x.from_key->mark_qdelta; i < x.from_key->mark_qend; i++)
+        bw.put(x.from_key->header_tape[i] & 1, x.from_key->header_tape[i] >> 1);
+    } else {
+      put_flagged_signed(bw, x.y_dc_delta, 4);
+      put_flagged_signed(bw, x.y2_dc_delta, 4);
+      put_flagged_signed(bw, x.y2_ac_delta, 4);
+      put_flagged_signed(bw, x.uv_dc_delta, 4);
+      put_flagged_signed(bw, x.uv_ac_delta, 4);
+    }
     // Without a saved table (stateless writer) refresh_entropy_probs = 0 whenever probabilities are
     // updated: the updates are then valid for this frame only and every frame is coded relative to
     // the default tables.
@@ -652,8 +658,15 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
       bw.literal(prob_inter, 8);
       bw.literal(prob_last, 8);
       bw.literal(prob_golden, 8);
-      bw.put(0);           // intra_16x16_prob unchanged
-      bw.put(0);           // intra_chroma_prob unchanged
+      if (x.from_key) {
+        bw.put(1);
+        for (int i = 0; i < 4; i++) bw.literal(k_ymode_default_probs[i], 8);
+        bw.put(1);
+        for (int i = 0; i < 3; i++) bw.literal(k_uvmode_default_probs[i], 8);
+      } else {
+        bw.put(0);           // intra_16x16_prob unchanged
+        bw.put(0);           // intra_chroma_prob unchanged
+      }
       for (int i = 0; i < 38; i++) bw.put(0, k_mv_update_probs[i]);  // motion vector probabilities unchanged
     }
   }

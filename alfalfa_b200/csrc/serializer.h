@@ -78,6 +78,11 @@ struct EncodeFeatures {
   // labels are the source frame's (the macroblock headers are copied, reencode.cc:141).
   const Verbatim* residue_of = nullptr;
   bool residue_refresh_all = false;
+  // A frame built by Encoder::reencode_as_interframe (encoder/reencode.cc:39-129) from the key frame `from_key`: the
+  // reference Encoder's inter-frame header (ref_writer, fresh) with the key frame's quantiser deltas (replayed from
+  // its tape) and sharpness (EncodeHeader), all three references refreshed, and intra_16x16_prob /
+  // intra_chroma_prob sent explicitly with their default values (reencode.cc:66-75)
+  const Verbatim* from_key = nullptr;
   // the stream's saved mode / motion-vector probabilities (DecoderState) that macroblock headers are coded with;
   // nullptr = the default tables (an Encoder that started from a key frame never changes them)
   const uint8_t* ymode_probs = nullptr;

@@ -540,8 +540,6 @@ class Encoder:
         """Encoder::reencode_as_interframe (encoder/reencode.cc:39-129)"""
         y, u, v = self._planes(y, u, v)
         size = C.c_size_t(0)
-        if not hasattr(self.L, "vp8gpu_encoder_reencode_as_interframe"):
-            raise capi.Unsupported(capi.ERR_UNSUPPORTED, "reencode_as_interframe is not built")
         check(self.L.vp8gpu_encoder_reencode_as_interframe(self.h, y.ctypes.data, y.shape[1], u.ctypes.data, v.ctypes.data, u.shape[1],
                                                            key_frame.h, int(y_ac_qi), self._out.ctypes.data, self._out.size,
                                                            C.byref(size)), self.ctx.h, "reencode_as_interframe")

@@ -109,6 +109,31 @@ def test_extra_frame_chunk_is_reencoded_byte_for_byte_like_the_reference(size, k
 
 
 @needs_ref
+@pytest.mark.parametrize("size", SIZES)
+@pytest.mark.parametrize("kf_q_weight", [1.0, 0.5])
+def test_whole_chunk_is_reencoded_byte_for_byte_like_the_reference(size, kf_q_weight):
+    """Encoder::reencode options 1 and 4 (reencode.cc:336-351, 366-372): the chunk's key frame becomes an inter frame
+    predicted from the receiver's LAST (reencode_as_interframe: the full decision loop, quantiser blended with the
+    next frame's), the other frames keep their decisions and get new residues"""
+    w, h = size
+    n = 4
+    targets, pred, state = make_case(w, h, n, qi_a=40, qi_b=64)
+    want = reference_reencode(w, h, targets, pred, state, kf_q_weight, False)
+    ctx, got, final = product_reencode(w, h, targets, pred, state, kf_q_weight, False)
+    assert len(got) == len(want) == n
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert a == b, "frame %d: %d vs %d bytes, first difference at %d" % (
+            i, len(a), len(b), next((k for k in range(min(len(a), len(b))) if a[k] != b[k]), -1))
+    assert got[0][0] & 1, "the chunk no longer starts with a key frame"
+    from alfalfa_b200 import Decoder
+    rx = Decoder.deserialize(ctx, state)
+    for c in got:
+        rx.get_frame_output(c)
+    assert rx == final
+    ctx.close()
+
+
+@needs_ref
 def test_reencoded_frames_differ_from_the_prediction_frames_but_keep_their_modes():
     """the point of update_residues: same decisions, new residues (the references are another reconstruction)"""
     w, h, n = 176, 144, 3
