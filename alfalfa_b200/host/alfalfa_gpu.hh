@@ -5,6 +5,7 @@
 // the include is switched.  Header-only; link with -lvp8gpu.
 #pragma once
 #include <cstdint>
+#include <cmath>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -134,6 +135,10 @@ class ParsedFrame {
     h_.reset(p, vp8gpu_parsed_destroy);
   }
   vp8gpu_parsed* get() const { return h_.get(); }
+  // the reference's Frame objects keep their header as coded and every label; the flat records keep them on request
+  // (needed by Encoder::reencode and by byte-exact re-serialisation)
+  void keep_labels(bool on = true) { check(vp8gpu_parsed_keep_labels(get(), on), nullptr, "parsed_keep_labels"); }
+  int y_ac_qi() const { return vp8gpu_parsed_y_ac_qi(get()); }  // header().quant_indices.y_ac_qi (needs keep_labels)
   bool show_frame() const { return vp8gpu_parsed_desc(get())->show_frame; }
   bool key_frame() const { return vp8gpu_parsed_desc(get())->key_frame; }
 };
@@ -173,8 +178,9 @@ class Decoder {
   const Context& context() const { return ctx_; }
 
   // parse_frame<KeyFrame|InterFrame>( decompress_frame( chunk ) ) (decoder.cc:83-98)
-  ParsedFrame parse_frame(const Chunk& compressed_frame) {
+  ParsedFrame parse_frame(const Chunk& compressed_frame, bool keep_labels = false) {
     ParsedFrame p;
+    if (keep_labels) p.keep_labels();
     check(vp8gpu_parse_frame(vp8gpu_decoder_state(h_), compressed_frame.buffer, compressed_frame.size, p.get()),
           ctx_.get(), "parse_frame");
     return p;
@@ -330,6 +336,65 @@ class Encoder {
           ctx_.get(), "encode_with_minimum_ssim");
     return take(n);
   }
+  // ---- re-encoding (encoder/reencode.cc; xc-enc --reencode, frontend/xc-enc.cc:262-327) ----
+  // update_residues + write_frame (reencode.cc:131-313): y_ac_qi < 0 keeps the prediction frame's own index
+  std::vector<uint8_t> update_residues(const SourceFrame& target, const ParsedFrame& prediction_frame, int y_ac_qi, bool last_frame) {
+    size_t n = 0;
+    check(vp8gpu_encoder_update_residues(h_, target.y, target.y_stride, target.u, target.v, target.uv_stride, prediction_frame.get(),
+                                         y_ac_qi, last_frame, buf_.data(), buf_.size(), &n),
+          ctx_.get(), "update_residues");
+    return take(n);
+  }
+  // reencode_as_interframe + write_frame (reencode.cc:39-129)
+  std::vector<uint8_t> reencode_as_interframe(const SourceFrame& target, const ParsedFrame& key_frame, uint8_t y_ac_qi) {
+    size_t n = 0;
+    check(vp8gpu_encoder_reencode_as_interframe(h_, target.y, target.y_stride, target.u, target.v, target.uv_stride, key_frame.get(),
+                                                y_ac_qi, buf_.data(), buf_.size(), &n),
+          ctx_.get(), "reencode_as_interframe");
+    return take(n);
+  }
+  // write_frame( KeyFrame ) (encoder.cc:146-176): a key frame that is kept
+  std::vector<uint8_t> write_frame(const ParsedFrame& key_frame) {
+    size_t n = 0;
+    check(vp8gpu_encoder_write_frame(h_, key_frame.get(), buf_.data(), buf_.size(), &n), ctx_.get(), "write_frame");
+    return take(n);
+  }
+  // Encoder::reencode (reencode.cc:315-381), statement for statement; the emitted frames are returned instead of
+  // appended to an IVFWriter.  prediction_frames were parsed with keep_labels by the prediction stream's decoder.
+  std::vector<std::vector<uint8_t>> reencode(const std::vector<SourceFrame>& original_rasters,
+                                             const std::vector<ParsedFrame>& prediction_frames, double kf_q_weight,
+                                             bool extra_frame_chunk) {
+    if (original_rasters.empty()) throw std::runtime_error("no rasters to re-encode");
+    if (original_rasters.size() != prediction_frames.size()) throw std::runtime_error("prediction/original_rasters mismatch");
+    std::vector<std::vector<uint8_t>> out;
+    const size_t start = extra_frame_chunk ? 1 : 0;
+    auto qi_of = [](const ParsedFrame& f) {
+      const int q = f.y_ac_qi();
+      if (q < 0) throw LogicError("reencode: prediction frames must be parsed with keep_labels");
+      return q;
+    };
+    for (size_t i = start; i < original_rasters.size(); i++) {
+      const SourceFrame& target = original_rasters[i];
+      const ParsedFrame& pred = prediction_frames[i];
+      const bool last = i == prediction_frames.size() - 1;
+      if (i == start && pred.key_frame()) {  // option 1: an initial key frame becomes an inter frame
+        int qi = qi_of(pred);
+        if (i + 1 < prediction_frames.size() && !prediction_frames[i + 1].key_frame())
+          qi = (int)lrint(kf_q_weight * qi_of(pred) + (1 - kf_q_weight) * qi_of(prediction_frames[i + 1]));
+        out.push_back(reencode_as_interframe(target, pred, (uint8_t)qi));
+      } else if (i == start && extra_frame_chunk) {  // option 2: first inter frame of an extra-frame chunk
+        if (!prediction_frames[0].key_frame()) throw std::runtime_error("extra-frame chunks must start with a keyframe.");
+        const int qi = (int)lrint(kf_q_weight * qi_of(prediction_frames[0]) + (1 - kf_q_weight) * qi_of(pred));
+        out.push_back(update_residues(target, pred, qi, last));
+      } else if (pred.key_frame()) {  // option 3: another key frame is preserved
+        out.push_back(write_frame(pred));
+      } else {  // option 4
+        out.push_back(update_residues(target, pred, -1, last));
+      }
+    }
+    return out;
+  }
+
   // EncoderStats::ssim of the last frame (encoder.hh:118-127)
   double last_ssim() const {
     double q = -1.0;

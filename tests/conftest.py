@@ -21,3 +21,13 @@ def golden_vectors():
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN_DIR
+
+
+def pytest_collection_modifyitems(config, items):
+    """The re-encoding path was written after this round's GPU minutes were spent: its kernels and host
+    code are checked bit-exactly under the SIMT emulator (tests/test_simt_emulation.py) but have not run on a B200 yet.
+    Its -m gpu tests therefore run LAST, so that under `pytest -x` a hardware-only failure there cannot keep the suites
+    that have a hardware record (parity, encoder, C++ callers, flatten, state format) from running."""
+    late = [it for it in items if "reencode" in it.nodeid]
+    if late:
+        items[:] = [it for it in items if "reencode" not in it.nodeid] + late

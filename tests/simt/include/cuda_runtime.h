@@ -31,7 +31,9 @@
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
 #define __constant__ static
-#define __shared__ static  // CTAs run one at a time
+// CTAs run one at a time, so a kernel's shared variables can be statics; they live in one section that the
+// emulator fills with a poison pattern before every CTA (shared memory is not zero on the device either)
+#define __shared__ static __attribute__((section("simt_shared")))
 
 struct uint3 { unsigned x, y, z; };
 struct dim3 {

@@ -30,6 +30,9 @@ asm(".text\n"
     "  ret\n"
     ".size simt_switch,.-simt_switch\n");
 
+extern "C" char __start_simt_shared[] __attribute__((weak));
+extern "C" char __stop_simt_shared[] __attribute__((weak));
+
 namespace simt {
 
 Fiber* cur = nullptr;
@@ -60,11 +63,20 @@ void switch_to(Fiber* next) {
   simt_switch(&prev->sp, next->sp);
 }
 
+// SIMT_ORDER=reverse schedules the threads of a CTA from the last to the first.  Between two barriers a thread runs
+// undisturbed, so with the default order a value written by lane a and read by lane b > a without a barrier in
+// between happens to be there, and with the reverse order the same holds for b < a: a missing __syncwarp fails in
+// at least one of the two orders (tests/test_simt_emulation.py runs both).
+const bool g_reverse = [] {
+  const char* v = getenv("SIMT_ORDER");
+  return v && strcmp(v, "reverse") == 0;
+}();
+
 Fiber* next_runnable(Fiber* from) {
   const size_t n = g_fibers.size();
   const size_t start = from - g_fibers.data();
   for (size_t k = 1; k <= n; k++) {
-    Fiber* f = &g_fibers[(start + k) % n];
+    Fiber* f = &g_fibers[g_reverse ? (start + n - k) % n : (start + k) % n];
     if (!f->done) return f;
   }
   return nullptr;
@@ -159,6 +171,9 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& b
     for (unsigned by = 0; by < grid.y; by++)
       for (unsigned bx = 0; bx < grid.x; bx++) {
         g_block = uint3{bx, by, bz};
+        if (__start_simt_shared && __stop_simt_shared > __start_simt_shared)
+          memset(__start_simt_shared, 0xCD, (size_t)(__stop_simt_shared - __start_simt_shared));
+        if (smem) memset(g_dyn.data(), 0xCD, smem);
         g_fibers.assign(nthreads, Fiber{});
         g_warps.assign(nwarps, Warp{});
         for (size_t i = 0; i < nthreads; i++) {
@@ -177,8 +192,8 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& b
         g_live = (int)nthreads;
         g_cta_arrived = 0;
         g_idle_switches = 0;
-        cur = &g_fibers[0];
-        simt_switch(&g_main_sp, g_fibers[0].sp);
+        cur = &g_fibers[g_reverse ? nthreads - 1 : 0];
+        simt_switch(&g_main_sp, cur->sp);
         cur = nullptr;
       }
   g_body = nullptr;

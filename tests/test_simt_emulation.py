@@ -79,3 +79,20 @@ def test_encoder_against_the_reference_encoder_emulated(simt_lib):
     """k_enc_rd + the encoder's host side: decisions equal to the unmodified reference encoder's, closed loop,
     target-size search, loop-filter choice, value semantics (the 1080p cases stay on the GPU: minutes here)"""
     run_gpu_tests_emulated(simt_lib, ["tests/test_gpu_encoder.py", "-k", "not rd_parity and not first_inter_frame and not size3"])
+
+
+def test_cxx_callers_on_the_host_mirror_emulated(simt_lib):
+    """C++ programs written against alfalfa_gpu.hh, linked with the emulated library: Salsify's concurrent Encoder
+    copies (two host threads launching kernels) and the xc-enc --reencode shape against the reference's output"""
+    run_gpu_tests_emulated(simt_lib, ["tests/test_gpu_cxx_host.py", "-k", "encoder_copies or reencode"])
+
+
+def test_reverse_thread_order_gives_the_same_results(simt_lib):
+    """SIMT_ORDER=reverse runs the threads of every CTA last to first: together with the default order this exposes a
+    shared-memory hand-over between lanes that lacks its barrier (one of the two orders reads before the write)"""
+    rev = {"SIMT_ORDER": "reverse"}
+    run_gpu_tests_emulated(simt_lib, ["tests/test_gpu_parity.py", "-k", "every_frame_matches_oracle or (fileplayer and not ff2941 and not 2a4c049c)"],
+                           env_extra=rev)
+    run_gpu_tests_emulated(simt_lib, ["tests/test_gpu_encoder.py", "-k", "decisions_equal and not size3"], env_extra=rev)
+    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_reencode")):
+        run_gpu_tests_emulated(simt_lib, ["tests/test_gpu_reencode.py"], env_extra=rev)
