@@ -243,6 +243,14 @@ int encode_bytes(vp8gpu_encoder* enc, bool key, int qi, int lf_level, int sub, b
     memcpy(scratch_probs, key ? k_coef_default_probs : probs, 1056);
     ft.saved_coef_probs = scratch_probs;
   }
+  if (!key) {
+    // macroblock headers of an inter frame are coded with the stream's saved mode / vector probabilities
+    // (Frame::serialize( probability_tables ), encoder.cc:169): the defaults unless this Encoder was built from a
+    // Decoder that had seen updates (a key frame resets them; estimate_size<KeyFrame> starts from a fresh state)
+    ft.ymode_probs = enc->dec_state->ymode_probs;
+    ft.uvmode_probs = enc->dec_state->uvmode_probs;
+    ft.mv_probs = enc->dec_state->mv_probs;
+  }
   bytes = vp8::serialize_frame(h, enc->h_mbs, enc->h_tokens, nullptr, &ft);
   if (bytes.empty()) return e->fail(VP8GPU_ERR_LOGIC, "serializer rejected the device records");
   return VP8GPU_OK;
@@ -476,6 +484,7 @@ void vp8gpu_encoder_destroy(vp8gpu_encoder* enc) {
   delete enc;
 }
 
+static int apply_emitted_frame(vp8gpu_encoder* enc, const uint8_t* data, size_t len);
 static int finish_frame(vp8gpu_encoder* enc, bool key, const std::vector<uint8_t>& bytes, int out_frame, int qi, int lf, double ssim,
                         uint8_t* out, size_t cap, size_t* size) {
   Engine* e = enc->e;
@@ -485,6 +494,19 @@ static int finish_frame(vp8gpu_encoder* enc, bool key, const std::vector<uint8_t
     return e->fail(VP8GPU_ERR_NOMEM, "output buffer too small");
   }
   memcpy(out, bytes.data(), bytes.size());
+  if (!key && enc->dec_state->seg_enabled) {
+    // An Encoder built from a Decoder whose stream uses segmentation: the frame carries no segmentation update, so
+    // a receiver keeps dequantising and filtering by segment while k_enc_rd reconstructed with the frame's one
+    // quantiser.  The reference is immune because write_frame always decodes what it wrote (encoder.cc:153-158);
+    // do the same here instead of keeping the kernel's reconstruction.
+    e->frame_release(out_frame);
+    const int rc = apply_emitted_frame(enc, bytes.data(), bytes.size());
+    if (rc != VP8GPU_OK) return rc;
+    enc->last_qi = qi;
+    enc->last_lf = lf;
+    enc->last_ssim = ssim;
+    return VP8GPU_OK;
+  }
   // Encoder::write_frame -> update_decoder_state (encoder.cc:146-151): the state a decoder is in after this
   // frame, obtained the way a decoder obtains it -- by parsing the frame (first partition only)
   const int prc = vp8::parse_frame(*enc->dec_state, bytes.data(), bytes.size(), *enc->scratch, true);

@@ -28,6 +28,8 @@ def pytest_collection_modifyitems(config, items):
     code are checked bit-exactly under the SIMT emulator (tests/test_simt_emulation.py) but have not run on a B200 yet.
     Its -m gpu tests therefore run LAST, so that under `pytest -x` a hardware-only failure there cannot keep the suites
     that have a hardware record (parity, encoder, C++ callers, flatten, state format) from running."""
-    late = [it for it in items if "reencode" in it.nodeid]
+    def is_late(it):  # (the Encoder-from-any-Decoder-state test came with the same change)
+        return "reencode" in it.nodeid or "built_from_a_decoder_in_any_state" in it.nodeid
+    late = [it for it in items if is_late(it)]
     if late:
-        items[:] = [it for it in items if "reencode" not in it.nodeid] + late
+        items[:] = [it for it in items if not is_late(it)] + late

@@ -393,3 +393,27 @@ def test_loop_filter_choice_and_minimum_ssim():
     src.release()
     del enc
     ctx.close()
+
+
+@pytest.mark.parametrize("name", ["04b68b0a642d8285303d2b8884fc374e09d28ae9", "07b5eb1e9741d90027c46166eaaff566c6bf934f",
+                                  "a4dace04a77fc9f969a8d7a645c99c0271f1f73e", "ced8ea7239e3c4ee32ed7ed6c9ff9cdfbaba3ae4",
+                                  "e3bc5f0c53d5efd6f2b1ea1a17ed1ee9bde5ea48"])
+def test_encoder_built_from_a_decoder_in_any_state_stays_in_step(name):
+    """Encoder( const Decoder & ) (encoder.hh:350-351) after a libvpx stream: the decoder's state carries updated mode /
+    motion-vector probabilities, loop-filter adjustments, segmentation.  The frames the Encoder then emits must be
+    coded against that state: a receiver that decodes them equals export_decoder() after every frame."""
+    from alfalfa_b200 import Context, Decoder, Encoder
+    from conftest import GOLDEN_DIR, golden_vectors
+    full = [n for n in golden_vectors() if n.startswith(name[:8])][0]
+    w, h, chunks = O.read_ivf(open(os.path.join(GOLDEN_DIR, full), "rb").read())
+    ctx = Context(w, h, max_frames=24)
+    rx = Decoder(ctx)
+    for c in chunks[:10]:
+        rx.get_frame_output(c)
+    enc = Encoder.from_decoder(ctx, rx)
+    for t in range(3):
+        frame = enc.encode_with_quantizer(*synth(w, h, t), 36 + 8 * t)
+        assert frame[0] & 1, "an Encoder built from a Decoder continues with inter frames"
+        rx.get_frame_output(frame)
+        assert rx == enc.export_decoder(), "frame %d" % t
+    ctx.close()
