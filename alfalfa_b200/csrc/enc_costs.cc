@@ -57,7 +57,8 @@ uint32_t mv_magnitude_cost(int num, const uint8_t* probs) {
 
 }  // namespace
 
-void build_enc_tables(EncTables& t) {
+void build_enc_tables(EncTables& t, const uint8_t* mv_probs) {
+  if (!mv_probs) mv_probs = k_mv_default_probs;
   memset(&t, 0, sizeof(t));
   for (int a = 0; a < 10; a++)
     for (int l = 0; l < 10; l++) tree_costs(t.bmode_cost[a][l], k_kf_bmode_probs + (a * 10 + l) * 9, kBModeTree, 0, 0);
@@ -68,10 +69,12 @@ void build_enc_tables(EncTables& t) {
       t.mvref_zero[k][c] = cost_zero(k_mv_count_probs[c * 4 + k]);
       t.mvref_one[k][c] = cost_one(k_mv_count_probs[c * 4 + k]);
     }
-  // the encoder never updates the motion-vector probabilities (optimize_mv_probs is not called from
-  // encode_raster, encode_inter.cc:578-653): the default table prices every frame
+  // Costs::fill_mv_component_costs( decoder_state_.probability_tables.motion_vector_probs ) (encode_inter.cc:601,
+  // reencode.cc:85).  The encoder never updates these probabilities itself (optimize_mv_probs is not called from
+  // encode_raster, encode_inter.cc:578-653): they are the defaults unless the Encoder was built from a Decoder that
+  // had seen updates.
   for (int comp = 0; comp < 2; comp++) {
-    const uint8_t* probs = k_mv_default_probs + comp * 19;
+    const uint8_t* probs = mv_probs + comp * 19;
     for (int i = 0; i < 1024; i++) t.mv_mag_cost[comp][i] = (uint16_t)mv_magnitude_cost(i, probs);
     t.mv_sign_cost[comp][0] = cost_zero(probs[SIGN]);
     t.mv_sign_cost[comp][1] = cost_one(probs[SIGN]);

@@ -16,7 +16,8 @@ struct EncTables {
   uint16_t pad[2];
 };
 
-void build_enc_tables(EncTables& t);
+// mv_probs: the stream's saved motion-vector probabilities ([2][19]); nullptr = the default table
+void build_enc_tables(EncTables& t, const uint8_t* mv_probs = nullptr);
 
 // Encoder::update_rd_multipliers (encoder.cc:179-194)
 inline void rd_multipliers(int y_ac, uint32_t* rate_mult, uint32_t* dist_mult) {

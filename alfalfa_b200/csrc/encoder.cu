@@ -45,6 +45,7 @@ struct vp8gpu_encoder {
   uint32_t rd_rate = 300, rd_dist = 1;  // RATE_MULTIPLIER / DISTORTION_MULTIPLIER (encoder.hh:152-153) as the last
                                         // update_rd_multipliers left them; a copy starts from the defaults again
   int lf_sharpness = 0;          // sharpness_level of the frame being built (0 for the Encoder's own frames)
+  uint8_t tab_mv_probs[38];      // the motion-vector probabilities the rate tables on the device were built from
   double last_ssim = -1.0;     // encode_stats_.ssim of the last frame
   vp8::State* dec_state = nullptr;  // DecoderState a decoder has after the frames emitted so far (export_decoder)
   // device scratch: EncJob | DevJob | sync ints | mbs | tokens | rate tables
@@ -120,6 +121,21 @@ int encode_launch(vp8gpu_encoder* enc, bool key, int qi, int sub, const vp8gpu_q
   if (rc != VP8GPU_OK) {
     e->frame_release(out);
     return rc;
+  }
+  if (!key && sub == 1 && memcmp(enc->tab_mv_probs, enc->dec_state->mv_probs, 38) != 0) {
+    // Costs::fill_mv_component_costs( the stream's probabilities ) at the start of a full inter-frame pass
+    // (encode_inter.cc:601, reencode.cc:85): only an Encoder built from a Decoder that had seen motion-vector
+    // probability updates ever gets here; sampled passes keep whatever the last full pass filled in
+    vp8::EncTables* t = new vp8::EncTables();
+    vp8::build_enc_tables(*t, &enc->dec_state->mv_probs[0][0]);
+    cudaError_t ce = cudaStreamSynchronize(s);  // nothing of this encoder may still be reading the tables
+    if (ce == cudaSuccess) ce = cudaMemcpy(enc->dev + enc->off_tab, t, sizeof(vp8::EncTables), cudaMemcpyHostToDevice);
+    delete t;
+    if (ce != cudaSuccess) {
+      e->frame_release(out);
+      return e->cuda_fail(ce, "rate tables upload");
+    }
+    memcpy(enc->tab_mv_probs, enc->dec_state->mv_probs, 38);
   }
   vp8::EncJob* ej = reinterpret_cast<vp8::EncJob*>(enc->h_hdr);
   memset(enc->h_hdr, 0, 512);
@@ -396,6 +412,7 @@ static int encoder_alloc(vp8gpu_ctx* ctx, vp8gpu_encoder** out) {
     vp8gpu_encoder_destroy(enc);
     return e->fail(VP8GPU_ERR_CUDA, "encoder rate tables upload failed");
   }
+  memcpy(enc->tab_mv_probs, k_mv_default_probs, 38);
   enc->dec_state = new vp8::State(e->width(), e->height());
   enc->scratch = new vp8::ParsedFrame();
   *out = enc;
@@ -959,11 +976,6 @@ int vp8gpu_encoder_reencode_as_interframe(vp8gpu_encoder* enc, const uint8_t* y,
   if (pf->desc.width != e->width() || pf->desc.height != e->height()) return e->fail(VP8GPU_ERR_LOGIC, "reencode_as_interframe: raster size mismatch");
   if (vb.seg_enabled) return e->fail(VP8GPU_ERR_UNSUPPORTED, "segmentation not supported");  // reencode.cc:49-51
   if (!enc->has_state || enc->refs[0] < 0) return e->fail(VP8GPU_ERR_LOGIC, "reencode_as_interframe: the encoder has no references yet");
-  // Costs::fill_mv_component_costs( temp_tables.motion_vector_probs ) (reencode.cc:82-85): the rate tables on the
-  // device are those of the default motion-vector probabilities, which is what an Encoder that only ever saw its own
-  // frames (or the reference encoder's) has; another table would need its own upload
-  if (memcmp(enc->dec_state->mv_probs, k_mv_default_probs, 38) != 0)
-    return e->fail(VP8GPU_ERR_UNSUPPORTED, "reencode_as_interframe: the decoder state carries updated motion-vector probabilities");
   cudaSetDevice(e->device());
   int rc = upload_source(enc, y, y_stride, u, v, uv_stride);
   if (rc != VP8GPU_OK) return rc;

@@ -456,8 +456,7 @@ int vp8gpu_encoder_update_residues(vp8gpu_encoder* enc, const uint8_t* y, size_t
 /* Encoder::reencode_as_interframe + write_frame (reencode.cc:39-129, 343-351): the chunk's initial key frame is coded
  * again as an inter frame predicted from this encoder's LAST (the reference's inter-frame decision loop on the
  * device), at the key frame's quantiser indices with y_ac_qi replaced, with its sharpness, refreshing all three
- * references.  VP8GPU_ERR_UNSUPPORTED for a key frame with segmentation (like the reference, reencode.cc:49-51) and
- * for a decoder state whose motion-vector probabilities are not the default ones. */
+ * references.  VP8GPU_ERR_UNSUPPORTED for a key frame with segmentation (like the reference, reencode.cc:49-51). */
 int vp8gpu_encoder_reencode_as_interframe(vp8gpu_encoder* enc, const uint8_t* y, size_t y_stride, const uint8_t* u,
                                           const uint8_t* v, size_t uv_stride, const vp8gpu_parsed* key_frame, int y_ac_qi,
                                           uint8_t* out, size_t cap, size_t* size);

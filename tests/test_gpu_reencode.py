@@ -250,3 +250,26 @@ def test_update_residues_on_libvpx_prediction_streams(prev, this, nframes):
         rx.get_frame_output(c)
     assert rx == final
     ctx.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("prev", ["07b5eb1e", "4fca93f3", "a4dace04", "ced8ea72", "d4e9f670", "df225756"])
+def test_whole_chunk_after_a_libvpx_stream(prev):
+    """options 1 + 4 when the receiver's state comes from a libvpx stream: updated motion-vector and mode
+    probabilities (the rate tables of the decision loop are rebuilt from them, Costs::fill_mv_component_costs
+    reencode.cc:82-85; macroblock headers are coded with them), loop-filter adjustments, golden / altref that differ
+    from LAST"""
+    w, h, prev_chunks = _golden(_full_name(prev))
+    n = 4
+    frames = [synth(w, h, t) for t in range(n)]
+    pred = reference_encode(frames, w, h, qi=60)
+    state = reference_state_after(w, h, prev_chunks, len(prev_chunks))
+    want = reference_reencode(w, h, frames, pred, state, 0.75, False)
+    ctx, got, final = product_reencode(w, h, frames, pred, state, 0.75, False)
+    assert got == want
+    from alfalfa_b200 import Decoder
+    rx = Decoder.deserialize(ctx, state)
+    for c in got:
+        rx.get_frame_output(c)
+    assert rx == final
+    ctx.close()
