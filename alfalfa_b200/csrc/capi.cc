@@ -895,29 +895,109 @@ struct IvfKnobs {
         parse_cache(getenv("VP8GPU_PARSE_CACHE") != nullptr) {}
 };
 
-int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threads, uint8_t* dst, size_t dst_size,
-                      uint32_t* n_decoded, uint32_t* n_shown) {
-  if (!ctx || !ivf) return VP8GPU_ERR_LOGIC;
-  Engine* e = ctx->engine;
-  const IvfKnobs knobs;
-  // IVF container (util/ivf.cc:36-82)
-  if (len < 32 || memcmp(ivf, "DKIF", 4) != 0) return e->fail(VP8GPU_ERR_INVALID, "missing IVF file header");
-  if ((ivf[4] | (ivf[5] << 8)) != 0) return e->fail(VP8GPU_ERR_UNSUPPORTED, "not an IVF version 0 file");
-  if ((ivf[6] | (ivf[7] << 8)) != 32) return e->fail(VP8GPU_ERR_UNSUPPORTED, "unsupported IVF header length");
-  if (memcmp(ivf + 8, "VP80", 4) != 0) return e->fail(VP8GPU_ERR_UNSUPPORTED, "not a VP8 file");
-  const int w = ivf[12] | (ivf[13] << 8), h = ivf[14] | (ivf[15] << 8);
-  if (w != e->width() || h != e->height()) return e->fail(VP8GPU_ERR_UNSUPPORTED, "IVF size does not match the context");
-  const uint32_t count = ivf[24] | (ivf[25] << 8) | (ivf[26] << 16) | ((uint32_t)ivf[27] << 24);
+// vp8gpu_decode_ivf as an object, one instance per call: parse_container() reads the IVF file into GOPs, plan() sizes
+// the pipeline (workers, token-ring slots, dispatchers), run() starts one thread per worker -- worker_host parses whole
+// frames, worker_device only first partitions and launches k_tokens for the rest -- and one per dispatcher, which
+// batches whatever the workers have queued (at most one frame per worker: consecutive frames of a GOP depend on each
+// other) onto the device.
+class IvfDecode {
+ public:
+  IvfDecode(vp8gpu_ctx* ctx_, const uint8_t* ivf_, size_t len_, int threads_, uint8_t* dst_, size_t dst_size_)
+      : ctx(ctx_), e(ctx_->engine), ivf(ivf_), len(len_), threads(threads_), dst(dst_), dst_size(dst_size_) {}
+  int parse_container();
+  void plan();
+  int run(uint32_t* n_decoded, uint32_t* n_shown);
+
+ private:
   struct Item {
     const uint8_t* p;
     uint32_t n;
     int64_t out_off;  // -1 = hidden
   };
+  static constexpr int kSlots = 4;  // parsed frames a host-token worker may have in flight
+  enum SlotState { kFree = 0, kQueued = 1 };
+  struct Pending {
+    vp8gpu_parsed* slot;
+    int refs[3];
+    int out;
+    int64_t out_off;
+    int* slot_state;
+    int tid = 0;  // the worker that queued it
+    // device-side tokens: the records live in ring slot `ring_slot` once `ready` has fired
+    const vp8::TokenRing* ring = nullptr;
+    int ring_slot = 0;
+    cudaEvent_t ready = nullptr;
+    cudaEvent_t* finished = nullptr;  // where submit() leaves the event that fires after the pixel kernels
+  };
+
+  vp8gpu_ctx* const ctx;
+  Engine* const e;
+  const IvfKnobs knobs;
+  const uint8_t* const ivf;
+  const size_t len;
+  int threads;
+  uint8_t* const dst;
+  const size_t dst_size;
+  // the container
+  int w = 0, h = 0;
   std::vector<Item> items;
   std::vector<uint32_t> gop_start;
+  uint32_t shown_total = 0, max_frame_bytes = 0;
+  int n_gops = 0;
+  // the plan
+  int tok_slots = 0, tok_chunk = 1, n_disp = 1, worker_nice = 5;
+  bool device_tokens = false;
+  // shared between workers and dispatchers
+  std::mutex mu;
+  // one condition variable per worker: a batch wakes exactly the workers whose slots it freed (a shared one
+  // woke every worker for every batch: hundreds of thousands of futile wake-ups per second of decoding)
+  std::vector<std::condition_variable> cv_worker, cv_disp;
+  std::vector<std::deque<Pending>> queues;
+  std::vector<int> running;  // workers each dispatcher still serves
+  std::atomic<int> next_gop{0};
+  std::atomic<int> first_error{VP8GPU_OK};
+  std::mutex stats_mu;
+  double st_parse = 0, st_wait_slot = 0, st_wait_dma = 0, st_submit = 0, st_download = 0, st_disp_idle = 0;
+  double st_batches = 0, st_jobs = 0;
+
+  void set_error(int rc) {
+    int ok = VP8GPU_OK;
+    first_error.compare_exchange_strong(ok, rc);
+  }
+  static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+  // Frame::copy_to (frame.cc:272-307) on the worker's three reference handles
+  static void advance_refs(Engine* e, int refs[3], const vp8gpu_frame_desc& desc, int out) {
+    if (desc.key_frame) {
+      set_ref(e, &refs[0], out);
+      set_ref(e, &refs[1], out);
+      set_ref(e, &refs[2], out);
+    } else {
+      if (desc.copy_to_alternate == 1) set_ref(e, &refs[2], refs[0]);
+      else if (desc.copy_to_alternate == 2) set_ref(e, &refs[2], refs[1]);
+      if (desc.copy_to_golden == 1) set_ref(e, &refs[1], refs[0]);
+      else if (desc.copy_to_golden == 2) set_ref(e, &refs[1], refs[2]);
+      if (desc.refresh_golden) set_ref(e, &refs[1], out);
+      if (desc.refresh_alternate) set_ref(e, &refs[2], out);
+      if (desc.refresh_last) set_ref(e, &refs[0], out);
+    }
+  }
+  void worker_host(int tid);
+  ivf_worker_kit* acquire_kit();
+  void worker_device(int tid);
+  void dispatcher(int di);
+};
+
+// IVF container (util/ivf.cc:36-82) -> items (frames from the first key frame on) and GOP boundaries
+int IvfDecode::parse_container() {
+  if (len < 32 || memcmp(ivf, "DKIF", 4) != 0) return e->fail(VP8GPU_ERR_INVALID, "missing IVF file header");
+  if ((ivf[4] | (ivf[5] << 8)) != 0) return e->fail(VP8GPU_ERR_UNSUPPORTED, "not an IVF version 0 file");
+  if ((ivf[6] | (ivf[7] << 8)) != 32) return e->fail(VP8GPU_ERR_UNSUPPORTED, "unsupported IVF header length");
+  if (memcmp(ivf + 8, "VP80", 4) != 0) return e->fail(VP8GPU_ERR_UNSUPPORTED, "not a VP8 file");
+  w = ivf[12] | (ivf[13] << 8), h = ivf[14] | (ivf[15] << 8);
+  if (w != e->width() || h != e->height()) return e->fail(VP8GPU_ERR_UNSUPPORTED, "IVF size does not match the context");
+  const uint32_t count = ivf[24] | (ivf[25] << 8) | (ivf[26] << 16) | ((uint32_t)ivf[27] << 24);
   const size_t frame_bytes = (size_t)w * h + 2 * (size_t)((w + 1) / 2) * ((h + 1) / 2);
   size_t pos = 32, out_off = 0;
-  uint32_t shown_total = 0;
   for (uint32_t i = 0; i < count; i++) {
     if (pos + 12 > len) return e->fail(VP8GPU_ERR_INVALID, "IVF file truncated");
     const uint32_t n = ivf[pos] | (ivf[pos + 1] << 8) | (ivf[pos + 2] << 16) | ((uint32_t)ivf[pos + 3] << 24);
@@ -937,14 +1017,17 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
   }
   if (dst && dst_size < out_off) return e->fail(VP8GPU_ERR_LOGIC, "decode_ivf: destination too small");
   gop_start.push_back((uint32_t)items.size());
-  const int n_gops = (int)gop_start.size() - 1;
+  n_gops = (int)gop_start.size() - 1;
+  for (const Item& it : items) max_frame_bytes = it.n > max_frame_bytes ? it.n : max_frame_bytes;
+  return VP8GPU_OK;
+}
+
+// how many workers, token-ring slots per worker, frames per k_tokens launch, dispatchers
+void IvfDecode::plan() {
   if (threads < 1) threads = 1;
   if (threads > 512) threads = 512;
   if (threads > n_gops) threads = n_gops > 0 ? n_gops : 1;
   // device-side token decoding needs rasters for the frames a worker keeps in flight
-  uint32_t max_frame_bytes = 0;
-  for (const Item& it : items) max_frame_bytes = it.n > max_frame_bytes ? it.n : max_frame_bytes;
-  int tok_slots = 0;
   if (ctx->device_tokens.load()) {
     tok_slots = e->frames_free() / threads - 4;
     // k_tokens needs tens of milliseconds per frame (one thread each), so a worker wants to run a
@@ -958,7 +1041,7 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     if (tok_slots > want) tok_slots = want;
     if (tok_slots < 4) tok_slots = 0;  // pool too small: the host workers parse everything
   }
-  const bool device_tokens = tok_slots > 0;
+  device_tokens = tok_slots > 0;
   if (!device_tokens) {
     // host-token path: a worker holds up to kSlots queued outputs plus its three references, and
     // Engine::frame_alloc fails rather than blocks, so the worker count is bounded by the raster pool
@@ -978,569 +1061,514 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
     ctx->tok_capacity = cap;
     ctx->tok_permits = cap;  // every earlier call has returned: all permits are back
   }
-  int tok_chunk = tok_slots / 3 > kTokChunk ? kTokChunk : (tok_slots / 3 > 0 ? tok_slots / 3 : 1);
+  tok_chunk = tok_slots / 3 > kTokChunk ? kTokChunk : (tok_slots / 3 > 0 ? tok_slots / 3 : 1);
   if (knobs.tok_chunk >= 0) {
     const int c = knobs.tok_chunk;
     if (c >= 1 && c <= tok_slots / 2) tok_chunk = c;
   }
-
-  // Host workers only parse (CPU entropy front end) and keep the per-GOP codec state; a single
-  // dispatcher gathers whatever they have produced -- at most one frame per worker, because
-  // consecutive frames of a GOP depend on each other -- into ONE batched decode per round, so the
-  // device sees a few large launches instead of three small ones per frame, and the wavefront
-  // kernels get rows of many frames to hide their latency with.
-  constexpr int kSlots = 4;      // parsed frames a worker may have in flight
-  enum SlotState { kFree = 0, kQueued = 1 };
-  struct Pending {
-    vp8gpu_parsed* slot;
-    int refs[3];
-    int out;
-    int64_t out_off;
-    int* slot_state;
-    int tid = 0;  // the worker that queued it
-    // device-side tokens: the records live in ring slot `ring_slot` once `ready` has fired
-    const vp8::TokenRing* ring = nullptr;
-    int ring_slot = 0;
-    cudaEvent_t ready = nullptr;
-    cudaEvent_t* finished = nullptr;  // where submit() leaves the event that fires after the pixel kernels
-  };
-  int n_disp = device_tokens ? (threads >= 32 ? 4 : (threads >= 8 ? 2 : 1)) : 1;
+  n_disp = device_tokens ? (threads >= 32 ? 4 : (threads >= 8 ? 2 : 1)) : 1;
   if (knobs.dispatchers >= 0) {
     const int n = knobs.dispatchers;
     if (n >= 1 && n <= 16 && n <= threads) n_disp = n;
   }
-  std::mutex mu;
-  // one condition variable per worker: a batch wakes exactly the workers whose slots it freed (a shared one
-  // woke every worker for every batch: hundreds of thousands of futile wake-ups per second of decoding)
-  std::vector<std::condition_variable> cv_worker(threads);
-  std::vector<std::condition_variable> cv_disp(n_disp);
-  std::vector<std::deque<Pending>> queues(threads);
-  std::vector<int> running(n_disp, 0);  // workers each dispatcher still serves
+  // The dispatchers feed the device and must not queue behind dozens of parsing workers for a CPU: the workers
+  // run at a lower priority (per-thread nice on Linux; VP8GPU_WORKER_NICE overrides, 0 = leave alone).
+  if (knobs.worker_nice >= 0) worker_nice = knobs.worker_nice;
+  cv_worker = std::vector<std::condition_variable>(threads);
+  cv_disp = std::vector<std::condition_variable>(n_disp);
+  queues.assign(threads, {});
+  running.assign(n_disp, 0);
   for (int t = 0; t < threads; t++) running[t % n_disp]++;
-  std::atomic<int> next_gop{0};
-  std::atomic<int> first_error{VP8GPU_OK};
-  auto set_error = [&](int rc) {
-    int ok = VP8GPU_OK;
-    first_error.compare_exchange_strong(ok, rc);
-  };
+}
 
-  std::mutex stats_mu;
-  double st_parse = 0, st_wait_slot = 0, st_wait_dma = 0, st_submit = 0, st_download = 0, st_disp_idle = 0;
-  double st_batches = 0, st_jobs = 0;
-  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-  auto worker = [&](int tid) {
-    cudaSetDevice(e->device());
-    double t_parse = 0, t_slot = 0, t_dma = 0;
-    State state(w, h);
-    int refs[3] = {-1, -1, -1};
-    vp8gpu_parsed* slots[kSlots] = {};
-    int slot_state[kSlots] = {};
-    int next_slot = 0;
-    int rc = VP8GPU_OK;
-    for (;;) {
-      const int g = next_gop.fetch_add(1);
-      if (g >= n_gops || first_error.load() != VP8GPU_OK) break;
-      for (uint32_t i = gop_start[g]; i < gop_start[g + 1] && rc == VP8GPU_OK; i++) {
-        const int si = next_slot;
-        next_slot = (next_slot + 1) % kSlots;
-        if (!slots[si]) {
-          {
-            std::lock_guard<std::mutex> lk(ctx->pool_mu);
-            if (!ctx->pinned_pool.empty()) {
-              slots[si] = ctx->pinned_pool.back();
-              ctx->pinned_pool.pop_back();
-            }
-          }
-          if (!slots[si]) {
-            slots[si] = new vp8gpu_parsed(kPinned);
-            cudaEventCreateWithFlags(&slots[si]->consumed, kWaitableEvent);
-            const size_t n_mbs = (size_t)e->geom().mb_cols * e->geom().mb_rows;
-            slots[si]->f.mbs.reserve(n_mbs, 0);
-            slots[si]->f.tokens.reserve(n_mbs * 32 + 1024, 0);
-            slots[si]->f.split.reserve(256, 0);
+// Host workers only parse (CPU entropy front end) and keep the per-GOP codec state; a dispatcher gathers
+// whatever they have produced -- at most one frame per worker, because consecutive frames of a GOP depend on
+// each other -- into ONE batched decode per round, so the device sees a few large launches instead of three small
+// ones per frame, and the wavefront kernels get rows of many frames to hide their latency with.
+void IvfDecode::worker_host(int tid) {
+  cudaSetDevice(e->device());
+  double t_parse = 0, t_slot = 0, t_dma = 0;
+  State state(w, h);
+  int refs[3] = {-1, -1, -1};
+  vp8gpu_parsed* slots[kSlots] = {};
+  int slot_state[kSlots] = {};
+  int next_slot = 0;
+  int rc = VP8GPU_OK;
+  for (;;) {
+    const int g = next_gop.fetch_add(1);
+    if (g >= n_gops || first_error.load() != VP8GPU_OK) break;
+    for (uint32_t i = gop_start[g]; i < gop_start[g + 1] && rc == VP8GPU_OK; i++) {
+      const int si = next_slot;
+      next_slot = (next_slot + 1) % kSlots;
+      if (!slots[si]) {
+        {
+          std::lock_guard<std::mutex> lk(ctx->pool_mu);
+          if (!ctx->pinned_pool.empty()) {
+            slots[si] = ctx->pinned_pool.back();
+            ctx->pinned_pool.pop_back();
           }
         }
-        vp8gpu_parsed* p = slots[si];
+        if (!slots[si]) {
+          slots[si] = new vp8gpu_parsed(kPinned);
+          cudaEventCreateWithFlags(&slots[si]->consumed, kWaitableEvent);
+          const size_t n_mbs = (size_t)e->geom().mb_cols * e->geom().mb_rows;
+          slots[si]->f.mbs.reserve(n_mbs, 0);
+          slots[si]->f.tokens.reserve(n_mbs * 32 + 1024, 0);
+          slots[si]->f.split.reserve(256, 0);
+        }
+      }
+      vp8gpu_parsed* p = slots[si];
+      const double t0 = now();
+      {  // the dispatcher must have picked the slot's previous frame up ...
+        std::unique_lock<std::mutex> lk(mu);
+        cv_worker[tid].wait(lk, [&] { return slot_state[si] == kFree; });
+      }
+      const double t1 = now();
+      if (p->busy) {  // ... and the DMA engine must have read it
+        cudaEventSynchronize(p->consumed);
+        p->busy = false;
+      }
+      const double t2 = now();
+      rc = vp8::parse_frame(state, items[i].p, items[i].n, p->f);
+      if (rc != VP8GPU_OK) break;
+      count_mbs(p);
+      t_slot += t1 - t0;
+      t_dma += t2 - t1;
+      t_parse += now() - t2;
+      const vp8gpu_frame_desc& desc = p->f.desc;
+      Pending job;
+      job.slot = p;
+      job.slot_state = &slot_state[si];
+      job.out_off = (dst && desc.show_frame) ? items[i].out_off : -1;
+      rc = e->frame_alloc(&job.out);
+      if (rc != VP8GPU_OK) break;
+      for (int k = 0; k < 3; k++) {
+        job.refs[k] = desc.key_frame ? -1 : refs[k];
+        if (job.refs[k] >= 0) e->frame_retain(job.refs[k]);  // keeps the raster alive until submitted
+      }
+      advance_refs(e, refs, desc, job.out);  // Frame::copy_to
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        slot_state[si] = kQueued;
+        job.tid = tid;
+        queues[tid].push_back(job);
+      }
+      cv_disp[tid % n_disp].notify_one();
+    }
+    if (rc != VP8GPU_OK) {
+      set_error(rc);
+      break;
+    }
+  }
+  {  // wait until everything this worker queued has been submitted, then retire
+    std::unique_lock<std::mutex> lk(mu);
+    cv_worker[tid].wait(lk, [&] {
+      for (int k = 0; k < kSlots; k++)
+        if (slot_state[k] != kFree) return false;  // the dispatcher still owns that slot
+      return true;
+    });
+    running[tid % n_disp]--;
+  }
+  cv_disp[tid % n_disp].notify_one();
+  {
+    std::lock_guard<std::mutex> lk(stats_mu);
+    st_parse += t_parse;
+    st_wait_slot += t_slot;
+    st_wait_dma += t_dma;
+  }
+  for (int k = 0; k < 3; k++)
+    if (refs[k] >= 0) e->frame_release(refs[k]);
+  for (auto* p : slots)
+    if (p) {
+      if (p->busy) {
+        cudaEventSynchronize(p->consumed);
+        p->busy = false;
+      }
+      std::lock_guard<std::mutex> lk(ctx->pool_mu);
+      ctx->pinned_pool.push_back(p);
+    }
+}
+
+// ---- workers with device-side token decoding: the host only walks the first partition; the DCT
+//      partitions of up to tok_chunk frames go to the device in one k_tokens launch on the worker's
+//      own stream, tok_slots frames may be in flight per worker, and the dispatcher picks a frame up
+//      once its `ready` event has fired ----
+ivf_worker_kit* IvfDecode::acquire_kit() {
+  ivf_worker_kit* k = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(ctx->pool_mu);
+    for (size_t i = 0; i < ctx->kit_pool.size(); i++)
+      if (ctx->kit_pool[i]->ring->bits_cap >= max_frame_bytes + 16 && ctx->kit_pool[i]->ring->nslots >= tok_slots) {
+        k = ctx->kit_pool[i];
+        ctx->kit_pool.erase(ctx->kit_pool.begin() + i);
+        break;
+      }
+  }
+  if (k) return k;
+  k = new ivf_worker_kit();
+  bool ok = e->token_ring_create(tok_slots, ring_bytes_for(max_frame_bytes), &k->ring) == VP8GPU_OK &&
+            cudaStreamCreateWithFlags(&k->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (cudaStream_t& st : k->kstream) ok = ok && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
+  if (!ok) {
+    if (k->ring) e->token_ring_free(k->ring);
+    if (k->copy_stream) cudaStreamDestroy(k->copy_stream);
+    for (cudaStream_t st : k->kstream)
+      if (st) cudaStreamDestroy(st);
+    delete k;
+    return nullptr;
+  }
+  const size_t n_mbs = (size_t)e->geom().mb_cols * e->geom().mb_rows;
+  for (int i = 0; i < tok_slots; i++) {
+    k->parsed[i] = new vp8gpu_parsed(kPinned);
+    k->parsed[i]->f.mbs.reserve(n_mbs, 0);
+    k->parsed[i]->f.split.reserve(256, 0);
+    cudaEventCreateWithFlags(&k->staged[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&k->ready[i], cudaEventDisableTiming);
+  }
+  return k;
+}
+
+void IvfDecode::worker_device(int tid) {
+  if (worker_nice > 0) setpriority(PRIO_PROCESS, (id_t)syscall(SYS_gettid), worker_nice);
+  cudaSetDevice(e->device());
+  double t_parse = 0, t_slot = 0, t_dma = 0;
+  State state(w, h);
+  int refs[3] = {-1, -1, -1};
+  int slot_state[kTokSlots] = {};
+  int next_slot = 0;
+  int launches_done = 0;
+  int rc = VP8GPU_OK;
+  ivf_worker_kit* kit = acquire_kit();
+  if (!kit) rc = e->fail(VP8GPU_ERR_NOMEM, "decode_ivf: token ring allocation failed");
+  while (rc == VP8GPU_OK) {
+    const int g = next_gop.fetch_add(1);
+    if (g >= n_gops || first_error.load() != VP8GPU_OK) break;
+    uint32_t i = gop_start[g];
+    while (i < gop_start[g + 1] && rc == VP8GPU_OK) {
+      const uint32_t left = gop_start[g + 1] - i;
+      // slow start: the first launches of a worker are small so that its pixel work can begin
+      // after one k_tokens latency instead of after a whole chunk's parse time on top of it
+      int want = tok_chunk;
+      if (launches_done < 3 && (2 << launches_done) < want) want = 2 << launches_done;
+      launches_done++;
+      const int n = (int)left < want ? (int)left : want;
+      const int first_slot = next_slot;
+      int staged = 0, permits_taken = 0;
+      for (int c = 0; c < n && rc == VP8GPU_OK; c++) {
+        const int si = (first_slot + c) % tok_slots;
         const double t0 = now();
-        {  // the dispatcher must have picked the slot's previous frame up ...
+        {  // the dispatcher must have submitted the slot's previous frame ...
           std::unique_lock<std::mutex> lk(mu);
           cv_worker[tid].wait(lk, [&] { return slot_state[si] == kFree; });
         }
         const double t1 = now();
-        if (p->busy) {  // ... and the DMA engine must have read it
-          cudaEventSynchronize(p->consumed);
-          p->busy = false;
+        if (kit->busy[si]) {  // ... and the pixel kernels must have read its records
+          if (kit->finished[si]) cudaEventSynchronize(kit->finished[si]);
+          kit->busy[si] = false;
         }
         const double t2 = now();
-        rc = vp8::parse_frame(state, items[i].p, items[i].n, p->f);
+        vp8gpu_parsed* p = kit->parsed[si];
+        rc = knobs.parse_cache ? parse_first_partition_cached(state, items[i + c].p, items[i + c].n, p->f)
+                               : vp8::parse_frame(state, items[i + c].p, items[i + c].n, p->f, true);
         if (rc != VP8GPU_OK) break;
         count_mbs(p);
+        rc = e->token_ring_stage(kit->ring, si, p->f, kit->copy_stream);
+        if (rc != VP8GPU_OK) break;
+        staged++;
         t_slot += t1 - t0;
         t_dma += t2 - t1;
         t_parse += now() - t2;
+      }
+      if (rc != VP8GPU_OK) break;
+      cudaStream_t ks = kit->kstream[kit->next_kstream];
+      kit->next_kstream = (kit->next_kstream + 1) % kTokStreams;
+      cudaEventRecord(kit->staged[first_slot], kit->copy_stream);
+      cudaStreamWaitEvent(ks, kit->staged[first_slot], 0);
+      if (ctx->tok_capacity > 0) {  // permits for the frames of this launch (returned by tok_release_cb when the kernel is done)
+        std::unique_lock<std::mutex> lk(ctx->tok_mu);
+        const int need = staged < ctx->tok_capacity ? staged : ctx->tok_capacity;
+        ctx->tok_cv.wait(lk, [&] { return ctx->tok_permits >= need; });
+        ctx->tok_permits -= need;
+        permits_taken = need;
+      }
+      // the ring is used modulo tok_slots (<= its real size): a chunk that wraps needs two launches
+      const int until_wrap = tok_slots - first_slot;
+      rc = e->token_ring_launch(kit->ring, first_slot, staged < until_wrap ? staged : until_wrap, ks);
+      if (rc == VP8GPU_OK && staged > until_wrap) rc = e->token_ring_launch(kit->ring, 0, staged - until_wrap, ks);
+      if (rc == VP8GPU_OK)
+        cudaEventRecord(kit->ready[first_slot], ks);  // one event per launch: its frames become ready together
+      // the permits come back when the stream gets here (also after a failed launch); queued after the
+      // `ready` events so that the host-function thread is not on the frames' critical path
+      if (permits_taken && cudaLaunchHostFunc(ks, tok_release_cb, new TokRelease{ctx, permits_taken}) != cudaSuccess) {
+        std::lock_guard<std::mutex> lk(ctx->tok_mu);
+        ctx->tok_permits += permits_taken;
+      }
+      if (rc != VP8GPU_OK) break;
+      for (int c = 0; c < staged && rc == VP8GPU_OK; c++) {
+        const int si = (first_slot + c) % tok_slots;
+        vp8gpu_parsed* p = kit->parsed[si];
         const vp8gpu_frame_desc& desc = p->f.desc;
         Pending job;
         job.slot = p;
         job.slot_state = &slot_state[si];
-        job.out_off = (dst && desc.show_frame) ? items[i].out_off : -1;
+        job.out_off = (dst && desc.show_frame) ? items[i + c].out_off : -1;
+        job.ring = kit->ring;
+        job.ring_slot = si;
+        job.ready = kit->ready[first_slot];
+        job.finished = &kit->finished[si];
         rc = e->frame_alloc(&job.out);
         if (rc != VP8GPU_OK) break;
         for (int k = 0; k < 3; k++) {
           job.refs[k] = desc.key_frame ? -1 : refs[k];
-          if (job.refs[k] >= 0) e->frame_retain(job.refs[k]);  // keeps the raster alive until submitted
+          if (job.refs[k] >= 0) e->frame_retain(job.refs[k]);
         }
-        // Frame::copy_to (frame.cc:272-307)
-        const int out = job.out;
-        if (desc.key_frame) {
-          set_ref(e, &refs[0], out);
-          set_ref(e, &refs[1], out);
-          set_ref(e, &refs[2], out);
-        } else {
-          if (desc.copy_to_alternate == 1) set_ref(e, &refs[2], refs[0]);
-          else if (desc.copy_to_alternate == 2) set_ref(e, &refs[2], refs[1]);
-          if (desc.copy_to_golden == 1) set_ref(e, &refs[1], refs[0]);
-          else if (desc.copy_to_golden == 2) set_ref(e, &refs[1], refs[2]);
-          if (desc.refresh_golden) set_ref(e, &refs[1], out);
-          if (desc.refresh_alternate) set_ref(e, &refs[2], out);
-          if (desc.refresh_last) set_ref(e, &refs[0], out);
-        }
+        advance_refs(e, refs, desc, job.out);  // Frame::copy_to
+        kit->busy[si] = true;
         {
           std::lock_guard<std::mutex> lk(mu);
           slot_state[si] = kQueued;
           job.tid = tid;
-          queues[tid].push_back(job);
+        queues[tid].push_back(job);
         }
         cv_disp[tid % n_disp].notify_one();
       }
-      if (rc != VP8GPU_OK) {
-        set_error(rc);
-        break;
+      next_slot = (first_slot + staged) % tok_slots;
+      i += (uint32_t)staged;
+    }
+    if (rc != VP8GPU_OK) break;
+  }
+  if (rc != VP8GPU_OK) set_error(rc);
+  {  // wait until everything this worker queued has been submitted, then retire
+    std::unique_lock<std::mutex> lk(mu);
+    cv_worker[tid].wait(lk, [&] {
+      for (int k = 0; k < kTokSlots; k++)
+        if (slot_state[k] != kFree) return false;
+      return true;
+    });
+    running[tid % n_disp]--;
+  }
+  cv_disp[tid % n_disp].notify_one();
+  {
+    std::lock_guard<std::mutex> lk(stats_mu);
+    st_parse += t_parse;
+    st_wait_slot += t_slot;
+    st_wait_dma += t_dma;
+  }
+  for (int k = 0; k < 3; k++)
+    if (refs[k] >= 0) e->frame_release(refs[k]);
+  if (kit) {
+    for (int k = 0; k < kTokSlots; k++)
+      if (kit->busy[k]) {
+        if (kit->finished[k]) cudaEventSynchronize(kit->finished[k]);
+        kit->busy[k] = false;
       }
+    cudaStreamSynchronize(kit->copy_stream);
+    for (cudaStream_t st : kit->kstream) cudaStreamSynchronize(st);
+    // k_tokens reports a token pool that was too small instead of writing out of bounds; the capacity
+    // rule (Engine::token_ring_layout) makes that impossible, so a set flag is an internal error
+    uint32_t res[kTokSlots][2];
+    if (cudaMemcpy2D(res, 8, kit->ring->dev + kit->ring->result_off, kit->ring->stride, 8, (size_t)kit->ring->nslots,
+                     cudaMemcpyDeviceToHost) == cudaSuccess) {
+      for (int k = 0; k < kit->ring->nslots && k < tok_slots; k++)
+        if (res[k][1]) set_error(e->fail(VP8GPU_ERR_LOGIC, "device token pool overflow"));
     }
-    {  // wait until everything this worker queued has been submitted, then retire
-      std::unique_lock<std::mutex> lk(mu);
-      cv_worker[tid].wait(lk, [&] {
-        for (int k = 0; k < kSlots; k++)
-          if (slot_state[k] != kFree) return false;  // the dispatcher still owns that slot
-        return true;
-      });
-      running[tid % n_disp]--;
-    }
-    cv_disp[tid % n_disp].notify_one();
-    {
-      std::lock_guard<std::mutex> lk(stats_mu);
-      st_parse += t_parse;
-      st_wait_slot += t_slot;
-      st_wait_dma += t_dma;
-    }
-    for (int k = 0; k < 3; k++)
-      if (refs[k] >= 0) e->frame_release(refs[k]);
-    for (auto* p : slots)
-      if (p) {
-        if (p->busy) {
-          cudaEventSynchronize(p->consumed);
-          p->busy = false;
-        }
-        std::lock_guard<std::mutex> lk(ctx->pool_mu);
-        ctx->pinned_pool.push_back(p);
-      }
-  };
+    std::lock_guard<std::mutex> lk(ctx->pool_mu);
+    ctx->kit_pool.push_back(kit);
+  }
+}
 
-  // ---- workers with device-side token decoding: the host only walks the first partition; the DCT
-  //      partitions of up to tok_chunk frames go to the device in one k_tokens launch on the worker's
-  //      own stream, tok_slots frames may be in flight per worker, and the dispatcher picks a frame up
-  //      once its `ready` event has fired ----
-  auto acquire_kit = [&]() -> ivf_worker_kit* {
-    ivf_worker_kit* k = nullptr;
+// Dispatchers: dispatcher d serves the workers with tid % D == d on its own two lanes.  Queueing a
+// frame costs a few dozen driver calls (stream ordering of its rasters, the launches, the download),
+// which one thread cannot do for more than ~10k frames/s.
+void IvfDecode::dispatcher(int di) {
+  cudaSetDevice(e->device());
+  std::vector<Pending> batch;
+  std::vector<HostJob> hj;
+  std::vector<int> dl_ids;
+  std::vector<uint8_t*> dl_dst;
+  int round = 0;
+  double t_idle = 0, t_submit = 0, t_download = 0, n_batches = 0, n_jobs = 0;
+  // VP8GPU_TRACE=1: device-side duration of every batch (diagnostic, printed to stderr)
+  struct Trace {
+    cudaEvent_t a, b;
+    int lane, n;
+    double host_t;
+    cudaEvent_t mid[4] = {nullptr, nullptr, nullptr, nullptr};  // -, after k_inter, after k_intra, before k_inter
+  };
+  std::vector<Trace> trace;
+  const bool tracing = knobs.trace;
+  for (;;) {
+    batch.clear();
+    const double ti = now();
     {
-      std::lock_guard<std::mutex> lk(ctx->pool_mu);
-      for (size_t i = 0; i < ctx->kit_pool.size(); i++)
-        if (ctx->kit_pool[i]->ring->bits_cap >= max_frame_bytes + 16 && ctx->kit_pool[i]->ring->nslots >= tok_slots) {
-          k = ctx->kit_pool[i];
-          ctx->kit_pool.erase(ctx->kit_pool.begin() + i);
+      std::unique_lock<std::mutex> lk(mu);
+      // a queue's front is eligible once its tokens are in HBM (device-side token decoding)
+      // The answer is remembered: once the event of a chunk has fired, every frame of that chunk at the head of
+      // the queue is marked (a query takes the driver's lock, and this runs for every queue on every poll --
+      // hundreds of thousands of queries per second next to the workers' own CUDA calls).
+      auto eligible = [&](std::deque<Pending>& q) {
+        if (q.empty()) return false;
+        Pending& f = q.front();
+        if (!f.ready) return true;
+        if (cudaEventQuery(f.ready) != cudaSuccess) return false;
+        const cudaEvent_t fired = f.ready;
+        for (Pending& p : q) {
+          if (p.ready != fired) break;
+          p.ready = nullptr;
+        }
+        return true;
+      };
+      auto ready = [&] {
+        int n = 0;
+        for (int t = di; t < threads; t += n_disp) n += eligible(queues[t]);
+        return n;
+      };
+      auto queued = [&] {
+        for (int t = di; t < threads; t += n_disp)
+          if (!queues[t].empty()) return true;
+        return false;
+      };
+      // nothing signals the condition variable when a CUDA event fires: poll while frames wait for one
+      while (!(running[di] == 0 && !queued()) && ready() == 0) {
+        if (queued()) cv_disp[di].wait_for(lk, std::chrono::microseconds(100));
+        else cv_disp[di].wait(lk);
+      }
+      // Device time per batch is almost flat in the number of frames (the wavefront kernels
+      // are latency bound), so give the other workers a moment to finish their current frame:
+      // go once most of them have something queued, or after a short grace period.
+      const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(1500);
+      while (running[di] > 0 && ready() < (running[di] * 3 + 3) / 4) {
+        if (device_tokens) {
+          if (std::chrono::steady_clock::now() >= deadline) break;
+          cv_disp[di].wait_for(lk, std::chrono::microseconds(100));
+        } else if (cv_disp[di].wait_until(lk, deadline) == std::cv_status::timeout) {
           break;
         }
-    }
-    if (k) return k;
-    k = new ivf_worker_kit();
-    bool ok = e->token_ring_create(tok_slots, ring_bytes_for(max_frame_bytes), &k->ring) == VP8GPU_OK &&
-              cudaStreamCreateWithFlags(&k->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
-    for (cudaStream_t& st : k->kstream) ok = ok && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
-    if (!ok) {
-      if (k->ring) e->token_ring_free(k->ring);
-      if (k->copy_stream) cudaStreamDestroy(k->copy_stream);
-      for (cudaStream_t st : k->kstream)
-        if (st) cudaStreamDestroy(st);
-      delete k;
-      return nullptr;
-    }
-    const size_t n_mbs = (size_t)e->geom().mb_cols * e->geom().mb_rows;
-    for (int i = 0; i < tok_slots; i++) {
-      k->parsed[i] = new vp8gpu_parsed(kPinned);
-      k->parsed[i]->f.mbs.reserve(n_mbs, 0);
-      k->parsed[i]->f.split.reserve(256, 0);
-      cudaEventCreateWithFlags(&k->staged[i], cudaEventDisableTiming);
-      cudaEventCreateWithFlags(&k->ready[i], cudaEventDisableTiming);
-    }
-    return k;
-  };
-  // The dispatchers feed the device and must not queue behind dozens of parsing workers for a CPU: the workers
-  // run at a lower priority (per-thread nice on Linux; VP8GPU_WORKER_NICE overrides, 0 = leave alone).
-  int worker_nice = 5;
-  if (knobs.worker_nice >= 0) worker_nice = knobs.worker_nice;
-  auto worker_dev = [&](int tid) {
-    if (worker_nice > 0) setpriority(PRIO_PROCESS, (id_t)syscall(SYS_gettid), worker_nice);
-    cudaSetDevice(e->device());
-    double t_parse = 0, t_slot = 0, t_dma = 0;
-    State state(w, h);
-    int refs[3] = {-1, -1, -1};
-    int slot_state[kTokSlots] = {};
-    int next_slot = 0;
-    int launches_done = 0;
-    int rc = VP8GPU_OK;
-    ivf_worker_kit* kit = acquire_kit();
-    if (!kit) rc = e->fail(VP8GPU_ERR_NOMEM, "decode_ivf: token ring allocation failed");
-    while (rc == VP8GPU_OK) {
-      const int g = next_gop.fetch_add(1);
-      if (g >= n_gops || first_error.load() != VP8GPU_OK) break;
-      uint32_t i = gop_start[g];
-      while (i < gop_start[g + 1] && rc == VP8GPU_OK) {
-        const uint32_t left = gop_start[g + 1] - i;
-        // slow start: the first launches of a worker are small so that its pixel work can begin
-        // after one k_tokens latency instead of after a whole chunk's parse time on top of it
-        int want = tok_chunk;
-        if (launches_done < 3 && (2 << launches_done) < want) want = 2 << launches_done;
-        launches_done++;
-        const int n = (int)left < want ? (int)left : want;
-        const int first_slot = next_slot;
-        int staged = 0, permits_taken = 0;
-        for (int c = 0; c < n && rc == VP8GPU_OK; c++) {
-          const int si = (first_slot + c) % tok_slots;
-          const double t0 = now();
-          {  // the dispatcher must have submitted the slot's previous frame ...
-            std::unique_lock<std::mutex> lk(mu);
-            cv_worker[tid].wait(lk, [&] { return slot_state[si] == kFree; });
-          }
-          const double t1 = now();
-          if (kit->busy[si]) {  // ... and the pixel kernels must have read its records
-            if (kit->finished[si]) cudaEventSynchronize(kit->finished[si]);
-            kit->busy[si] = false;
-          }
-          const double t2 = now();
-          vp8gpu_parsed* p = kit->parsed[si];
-          rc = knobs.parse_cache ? parse_first_partition_cached(state, items[i + c].p, items[i + c].n, p->f)
-                                 : vp8::parse_frame(state, items[i + c].p, items[i + c].n, p->f, true);
-          if (rc != VP8GPU_OK) break;
-          count_mbs(p);
-          rc = e->token_ring_stage(kit->ring, si, p->f, kit->copy_stream);
-          if (rc != VP8GPU_OK) break;
-          staged++;
-          t_slot += t1 - t0;
-          t_dma += t2 - t1;
-          t_parse += now() - t2;
-        }
-        if (rc != VP8GPU_OK) break;
-        cudaStream_t ks = kit->kstream[kit->next_kstream];
-        kit->next_kstream = (kit->next_kstream + 1) % kTokStreams;
-        cudaEventRecord(kit->staged[first_slot], kit->copy_stream);
-        cudaStreamWaitEvent(ks, kit->staged[first_slot], 0);
-        if (ctx->tok_capacity > 0) {  // permits for the frames of this launch (returned by tok_release_cb when the kernel is done)
-          std::unique_lock<std::mutex> lk(ctx->tok_mu);
-          const int need = staged < ctx->tok_capacity ? staged : ctx->tok_capacity;
-          ctx->tok_cv.wait(lk, [&] { return ctx->tok_permits >= need; });
-          ctx->tok_permits -= need;
-          permits_taken = need;
-        }
-        // the ring is used modulo tok_slots (<= its real size): a chunk that wraps needs two launches
-        const int until_wrap = tok_slots - first_slot;
-        rc = e->token_ring_launch(kit->ring, first_slot, staged < until_wrap ? staged : until_wrap, ks);
-        if (rc == VP8GPU_OK && staged > until_wrap) rc = e->token_ring_launch(kit->ring, 0, staged - until_wrap, ks);
-        if (rc == VP8GPU_OK)
-          cudaEventRecord(kit->ready[first_slot], ks);  // one event per launch: its frames become ready together
-        // the permits come back when the stream gets here (also after a failed launch); queued after the
-        // `ready` events so that the host-function thread is not on the frames' critical path
-        if (permits_taken && cudaLaunchHostFunc(ks, tok_release_cb, new TokRelease{ctx, permits_taken}) != cudaSuccess) {
-          std::lock_guard<std::mutex> lk(ctx->tok_mu);
-          ctx->tok_permits += permits_taken;
-        }
-        if (rc != VP8GPU_OK) break;
-        for (int c = 0; c < staged && rc == VP8GPU_OK; c++) {
-          const int si = (first_slot + c) % tok_slots;
-          vp8gpu_parsed* p = kit->parsed[si];
-          const vp8gpu_frame_desc& desc = p->f.desc;
-          Pending job;
-          job.slot = p;
-          job.slot_state = &slot_state[si];
-          job.out_off = (dst && desc.show_frame) ? items[i + c].out_off : -1;
-          job.ring = kit->ring;
-          job.ring_slot = si;
-          job.ready = kit->ready[first_slot];
-          job.finished = &kit->finished[si];
-          rc = e->frame_alloc(&job.out);
-          if (rc != VP8GPU_OK) break;
-          for (int k = 0; k < 3; k++) {
-            job.refs[k] = desc.key_frame ? -1 : refs[k];
-            if (job.refs[k] >= 0) e->frame_retain(job.refs[k]);
-          }
-          const int out = job.out;  // Frame::copy_to (frame.cc:272-307)
-          if (desc.key_frame) {
-            set_ref(e, &refs[0], out);
-            set_ref(e, &refs[1], out);
-            set_ref(e, &refs[2], out);
-          } else {
-            if (desc.copy_to_alternate == 1) set_ref(e, &refs[2], refs[0]);
-            else if (desc.copy_to_alternate == 2) set_ref(e, &refs[2], refs[1]);
-            if (desc.copy_to_golden == 1) set_ref(e, &refs[1], refs[0]);
-            else if (desc.copy_to_golden == 2) set_ref(e, &refs[1], refs[2]);
-            if (desc.refresh_golden) set_ref(e, &refs[1], out);
-            if (desc.refresh_alternate) set_ref(e, &refs[2], out);
-            if (desc.refresh_last) set_ref(e, &refs[0], out);
-          }
-          kit->busy[si] = true;
-          {
-            std::lock_guard<std::mutex> lk(mu);
-            slot_state[si] = kQueued;
-            job.tid = tid;
-          queues[tid].push_back(job);
-          }
-          cv_disp[tid % n_disp].notify_one();
-        }
-        next_slot = (first_slot + staged) % tok_slots;
-        i += (uint32_t)staged;
       }
-      if (rc != VP8GPU_OK) break;
+      for (int t = di; t < threads; t += n_disp)
+        if (eligible(queues[t])) {
+          batch.push_back(queues[t].front());
+          queues[t].pop_front();
+        }
+      if (batch.empty() && running[di] == 0 && !queued()) break;
+    }
+    if (batch.empty()) continue;
+    const double ts = now();
+    t_idle += ts - ti;
+    n_batches += 1;
+    n_jobs += batch.size();
+    const int lane = 2 * di + (round++ & 1);
+    hj.clear();
+    for (const Pending& b : batch) {
+      HostJob j;
+      j.desc = &b.slot->f.desc;
+      j.mbs = b.slot->f.mbs.data();
+      j.tokens = b.slot->f.tokens.data();
+      j.split = b.slot->f.split.data();
+      memcpy(j.refs, b.refs, sizeof(j.refs));
+      j.out = b.out;
+      j.n_intra = (int)b.slot->n_intra;
+      j.n_filtered = (int)b.slot->n_filtered;
+      j.consumed = b.slot->consumed;  // fires as soon as the records are in HBM, before the kernels
+      if (b.ring) {
+        j.ring = b.ring;
+        j.ring_slot = b.ring_slot;
+        j.ready = nullptr;  // already fired (eligible() checked it)
+        j.finished = b.finished;
+        j.consumed = nullptr;
+      }
+      hj.push_back(j);
+    }
+    Trace tr{nullptr, nullptr, lane, (int)batch.size(), ts};
+    if (tracing) {
+      e->ensure_lane(lane);
+      cudaEventCreate(&tr.a);
+      cudaEventCreate(&tr.b);
+      for (cudaEvent_t& m : tr.mid) cudaEventCreate(&m);
+      cudaEventRecord(tr.a, e->stream(lane));
+    }
+    int rc = e->submit(lane, hj.data(), (int)hj.size(), nullptr, tracing ? tr.mid + 1 : nullptr);
+    if (tracing) {
+      cudaEventRecord(tr.b, e->stream(lane));
+      trace.push_back(tr);
+    }
+    const double td = now();
+    t_submit += td - ts;
+    if (rc == VP8GPU_OK) {
+      dl_ids.clear();
+      dl_dst.clear();
+      for (const Pending& b : batch) {
+        if (!b.ring) b.slot->busy = true;
+        if (b.out_off >= 0) {
+          dl_ids.push_back(b.out);
+          dl_dst.push_back(dst + b.out_off);
+        }
+      }
+      if (!dl_ids.empty()) rc = e->frames_download_display(dl_ids.data(), dl_dst.data(), (int)dl_ids.size(), lane);
+    }
+    for (const Pending& b : batch) {
+      for (int k = 0; k < 3; k++)
+        if (b.refs[k] >= 0) e->frame_release(b.refs[k]);
+      e->frame_release(b.out);
     }
     if (rc != VP8GPU_OK) set_error(rc);
-    {  // wait until everything this worker queued has been submitted, then retire
-      std::unique_lock<std::mutex> lk(mu);
-      cv_worker[tid].wait(lk, [&] {
-        for (int k = 0; k < kTokSlots; k++)
-          if (slot_state[k] != kFree) return false;
-        return true;
-      });
-      running[tid % n_disp]--;
-    }
-    cv_disp[tid % n_disp].notify_one();
+    t_download += now() - td;
     {
-      std::lock_guard<std::mutex> lk(stats_mu);
-      st_parse += t_parse;
-      st_wait_slot += t_slot;
-      st_wait_dma += t_dma;
+      std::lock_guard<std::mutex> lk(mu);
+      for (const Pending& b : batch) *b.slot_state = kFree;
     }
-    for (int k = 0; k < 3; k++)
-      if (refs[k] >= 0) e->frame_release(refs[k]);
-    if (kit) {
-      for (int k = 0; k < kTokSlots; k++)
-        if (kit->busy[k]) {
-          if (kit->finished[k]) cudaEventSynchronize(kit->finished[k]);
-          kit->busy[k] = false;
-        }
-      cudaStreamSynchronize(kit->copy_stream);
-      for (cudaStream_t st : kit->kstream) cudaStreamSynchronize(st);
-      // k_tokens reports a token pool that was too small instead of writing out of bounds; the capacity
-      // rule (Engine::token_ring_layout) makes that impossible, so a set flag is an internal error
-      uint32_t res[kTokSlots][2];
-      if (cudaMemcpy2D(res, 8, kit->ring->dev + kit->ring->result_off, kit->ring->stride, 8, (size_t)kit->ring->nslots,
-                       cudaMemcpyDeviceToHost) == cudaSuccess) {
-        for (int k = 0; k < kit->ring->nslots && k < tok_slots; k++)
-          if (res[k][1]) set_error(e->fail(VP8GPU_ERR_LOGIC, "device token pool overflow"));
+    for (const Pending& b : batch) cv_worker[b.tid].notify_one();
+  }
+  e->sync_lane(2 * di);
+  e->sync_lane(2 * di + 1);
+  if (tracing && !trace.empty()) {
+    // per batch: device time from "stream reaches the batch" to "its kernels are done", and the
+    // device-side gap to the previous batch of this dispatcher
+    double sum_ms = 0, sum_gap = 0, first_host = trace.front().host_t, last_host = trace.back().host_t;
+    double sum_intra = 0, sum_lf = 0, sum_inter = 0, sum_pre = 0, sum_turn = 0;
+    float ms = 0;
+    for (size_t i = 0; i < trace.size(); i++) {
+      if (cudaEventElapsedTime(&ms, trace[i].mid[3], trace[i].mid[1]) == cudaSuccess) sum_inter += ms;
+      if (cudaEventElapsedTime(&ms, trace[i].a, trace[i].mid[3]) == cudaSuccess) sum_pre += ms;
+      if (cudaEventElapsedTime(&ms, trace[i].mid[1], trace[i].mid[2]) == cudaSuccess) sum_intra += ms;
+      if (cudaEventElapsedTime(&ms, trace[i].mid[2], trace[i].b) == cudaSuccess) sum_lf += ms;
+      cudaEventElapsedTime(&ms, trace[i].a, trace[i].b);
+      sum_ms += ms;
+      if (i) {
+        cudaEventElapsedTime(&ms, trace[i - 1].b, trace[i].b);
+        sum_gap += ms;
+        // device-side turn-around: end of the previous batch -> first kernel of this one (negative: overlapped)
+        if (cudaEventElapsedTime(&ms, trace[i - 1].b, trace[i].mid[3]) == cudaSuccess) sum_turn += ms;
       }
-      std::lock_guard<std::mutex> lk(ctx->pool_mu);
-      ctx->kit_pool.push_back(kit);
     }
-  };
+    fprintf(stderr, "[trace] dispatcher %d: %zu batches, avg %.2f frames, device %.3f ms per batch, end-to-end period %.3f ms, "
+            "host span %.1f ms; per batch: waits + upload %.3f ms, k_inter %.3f ms, k_intra %.3f ms, k_loopfilter %.3f ms, turn-around %.3f ms\n", di,
+            trace.size(), n_jobs / n_batches, sum_ms / trace.size(), trace.size() > 1 ? sum_gap / (trace.size() - 1) : 0.0,
+            (last_host - first_host) * 1e3, sum_pre / trace.size(), sum_inter / trace.size(), sum_intra / trace.size(),
+            sum_lf / trace.size(), trace.size() > 1 ? sum_turn / (trace.size() - 1) : 0.0);
+    for (Trace& t : trace) {
+      cudaEventDestroy(t.a);
+      cudaEventDestroy(t.b);
+      for (cudaEvent_t m : t.mid)
+        if (m) cudaEventDestroy(m);
+    }
+  }
+  std::lock_guard<std::mutex> lk(stats_mu);
+  st_disp_idle += t_idle;
+  st_submit += t_submit;
+  st_download += t_download;
+  st_batches += n_batches;
+  st_jobs += n_jobs;
+}
 
-  // Dispatchers: dispatcher d serves the workers with tid % D == d on its own two lanes.  Queueing a
-  // frame costs a few dozen driver calls (stream ordering of its rasters, the launches, the download),
-  // which one thread cannot do for more than ~10k frames/s.
-  auto dispatcher = [&](int di) {
-    cudaSetDevice(e->device());
-    std::vector<Pending> batch;
-    std::vector<HostJob> hj;
-    std::vector<int> dl_ids;
-    std::vector<uint8_t*> dl_dst;
-    int round = 0;
-    double t_idle = 0, t_submit = 0, t_download = 0, n_batches = 0, n_jobs = 0;
-    // VP8GPU_TRACE=1: device-side duration of every batch (diagnostic, printed to stderr)
-    struct Trace {
-      cudaEvent_t a, b;
-      int lane, n;
-      double host_t;
-      cudaEvent_t mid[4] = {nullptr, nullptr, nullptr, nullptr};  // -, after k_inter, after k_intra, before k_inter
-    };
-    std::vector<Trace> trace;
-    const bool tracing = knobs.trace;
-    for (;;) {
-      batch.clear();
-      const double ti = now();
-      {
-        std::unique_lock<std::mutex> lk(mu);
-        // a queue's front is eligible once its tokens are in HBM (device-side token decoding)
-        // The answer is remembered: once the event of a chunk has fired, every frame of that chunk at the head of
-        // the queue is marked (a query takes the driver's lock, and this runs for every queue on every poll --
-        // hundreds of thousands of queries per second next to the workers' own CUDA calls).
-        auto eligible = [&](std::deque<Pending>& q) {
-          if (q.empty()) return false;
-          Pending& f = q.front();
-          if (!f.ready) return true;
-          if (cudaEventQuery(f.ready) != cudaSuccess) return false;
-          const cudaEvent_t fired = f.ready;
-          for (Pending& p : q) {
-            if (p.ready != fired) break;
-            p.ready = nullptr;
-          }
-          return true;
-        };
-        auto ready = [&] {
-          int n = 0;
-          for (int t = di; t < threads; t += n_disp) n += eligible(queues[t]);
-          return n;
-        };
-        auto queued = [&] {
-          for (int t = di; t < threads; t += n_disp)
-            if (!queues[t].empty()) return true;
-          return false;
-        };
-        // nothing signals the condition variable when a CUDA event fires: poll while frames wait for one
-        while (!(running[di] == 0 && !queued()) && ready() == 0) {
-          if (queued()) cv_disp[di].wait_for(lk, std::chrono::microseconds(100));
-          else cv_disp[di].wait(lk);
-        }
-        // Device time per batch is almost flat in the number of frames (the wavefront kernels
-        // are latency bound), so give the other workers a moment to finish their current frame:
-        // go once most of them have something queued, or after a short grace period.
-        const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(1500);
-        while (running[di] > 0 && ready() < (running[di] * 3 + 3) / 4) {
-          if (device_tokens) {
-            if (std::chrono::steady_clock::now() >= deadline) break;
-            cv_disp[di].wait_for(lk, std::chrono::microseconds(100));
-          } else if (cv_disp[di].wait_until(lk, deadline) == std::cv_status::timeout) {
-            break;
-          }
-        }
-        for (int t = di; t < threads; t += n_disp)
-          if (eligible(queues[t])) {
-            batch.push_back(queues[t].front());
-            queues[t].pop_front();
-          }
-        if (batch.empty() && running[di] == 0 && !queued()) break;
-      }
-      if (batch.empty()) continue;
-      const double ts = now();
-      t_idle += ts - ti;
-      n_batches += 1;
-      n_jobs += batch.size();
-      const int lane = 2 * di + (round++ & 1);
-      hj.clear();
-      for (const Pending& b : batch) {
-        HostJob j;
-        j.desc = &b.slot->f.desc;
-        j.mbs = b.slot->f.mbs.data();
-        j.tokens = b.slot->f.tokens.data();
-        j.split = b.slot->f.split.data();
-        memcpy(j.refs, b.refs, sizeof(j.refs));
-        j.out = b.out;
-        j.n_intra = (int)b.slot->n_intra;
-        j.n_filtered = (int)b.slot->n_filtered;
-        j.consumed = b.slot->consumed;  // fires as soon as the records are in HBM, before the kernels
-        if (b.ring) {
-          j.ring = b.ring;
-          j.ring_slot = b.ring_slot;
-          j.ready = nullptr;  // already fired (eligible() checked it)
-          j.finished = b.finished;
-          j.consumed = nullptr;
-        }
-        hj.push_back(j);
-      }
-      Trace tr{nullptr, nullptr, lane, (int)batch.size(), ts};
-      if (tracing) {
-        e->ensure_lane(lane);
-        cudaEventCreate(&tr.a);
-        cudaEventCreate(&tr.b);
-        for (cudaEvent_t& m : tr.mid) cudaEventCreate(&m);
-        cudaEventRecord(tr.a, e->stream(lane));
-      }
-      int rc = e->submit(lane, hj.data(), (int)hj.size(), nullptr, tracing ? tr.mid + 1 : nullptr);
-      if (tracing) {
-        cudaEventRecord(tr.b, e->stream(lane));
-        trace.push_back(tr);
-      }
-      const double td = now();
-      t_submit += td - ts;
-      if (rc == VP8GPU_OK) {
-        dl_ids.clear();
-        dl_dst.clear();
-        for (const Pending& b : batch) {
-          if (!b.ring) b.slot->busy = true;
-          if (b.out_off >= 0) {
-            dl_ids.push_back(b.out);
-            dl_dst.push_back(dst + b.out_off);
-          }
-        }
-        if (!dl_ids.empty()) rc = e->frames_download_display(dl_ids.data(), dl_dst.data(), (int)dl_ids.size(), lane);
-      }
-      for (const Pending& b : batch) {
-        for (int k = 0; k < 3; k++)
-          if (b.refs[k] >= 0) e->frame_release(b.refs[k]);
-        e->frame_release(b.out);
-      }
-      if (rc != VP8GPU_OK) set_error(rc);
-      t_download += now() - td;
-      {
-        std::lock_guard<std::mutex> lk(mu);
-        for (const Pending& b : batch) *b.slot_state = kFree;
-      }
-      for (const Pending& b : batch) cv_worker[b.tid].notify_one();
-    }
-    e->sync_lane(2 * di);
-    e->sync_lane(2 * di + 1);
-    if (tracing && !trace.empty()) {
-      // per batch: device time from "stream reaches the batch" to "its kernels are done", and the
-      // device-side gap to the previous batch of this dispatcher
-      double sum_ms = 0, sum_gap = 0, first_host = trace.front().host_t, last_host = trace.back().host_t;
-      double sum_intra = 0, sum_lf = 0, sum_inter = 0, sum_pre = 0, sum_turn = 0;
-      float ms = 0;
-      for (size_t i = 0; i < trace.size(); i++) {
-        if (cudaEventElapsedTime(&ms, trace[i].mid[3], trace[i].mid[1]) == cudaSuccess) sum_inter += ms;
-        if (cudaEventElapsedTime(&ms, trace[i].a, trace[i].mid[3]) == cudaSuccess) sum_pre += ms;
-        if (cudaEventElapsedTime(&ms, trace[i].mid[1], trace[i].mid[2]) == cudaSuccess) sum_intra += ms;
-        if (cudaEventElapsedTime(&ms, trace[i].mid[2], trace[i].b) == cudaSuccess) sum_lf += ms;
-        cudaEventElapsedTime(&ms, trace[i].a, trace[i].b);
-        sum_ms += ms;
-        if (i) {
-          cudaEventElapsedTime(&ms, trace[i - 1].b, trace[i].b);
-          sum_gap += ms;
-          // device-side turn-around: end of the previous batch -> first kernel of this one (negative: overlapped)
-          if (cudaEventElapsedTime(&ms, trace[i - 1].b, trace[i].mid[3]) == cudaSuccess) sum_turn += ms;
-        }
-      }
-      fprintf(stderr, "[trace] dispatcher %d: %zu batches, avg %.2f frames, device %.3f ms per batch, end-to-end period %.3f ms, "
-              "host span %.1f ms; per batch: waits + upload %.3f ms, k_inter %.3f ms, k_intra %.3f ms, k_loopfilter %.3f ms, turn-around %.3f ms\n", di,
-              trace.size(), n_jobs / n_batches, sum_ms / trace.size(), trace.size() > 1 ? sum_gap / (trace.size() - 1) : 0.0,
-              (last_host - first_host) * 1e3, sum_pre / trace.size(), sum_inter / trace.size(), sum_intra / trace.size(),
-              sum_lf / trace.size(), trace.size() > 1 ? sum_turn / (trace.size() - 1) : 0.0);
-      for (Trace& t : trace) {
-        cudaEventDestroy(t.a);
-        cudaEventDestroy(t.b);
-        for (cudaEvent_t m : t.mid)
-          if (m) cudaEventDestroy(m);
-      }
-    }
-    std::lock_guard<std::mutex> lk(stats_mu);
-    st_disp_idle += t_idle;
-    st_submit += t_submit;
-    st_download += t_download;
-    st_batches += n_batches;
-    st_jobs += n_jobs;
-  };
-
+int IvfDecode::run(uint32_t* n_decoded, uint32_t* n_shown) {
   std::vector<std::thread> pool;
   for (int t = 0; t < threads; t++) {
-    if (device_tokens) pool.emplace_back(worker_dev, t);
-    else pool.emplace_back(worker, t);
+    if (device_tokens) pool.emplace_back(&IvfDecode::worker_device, this, t);
+    else pool.emplace_back(&IvfDecode::worker_host, this, t);
   }
   std::vector<std::thread> dispatchers;
-  for (int d = 1; d < n_disp; d++) dispatchers.emplace_back(dispatcher, d);
+  for (int d = 1; d < n_disp; d++) dispatchers.emplace_back(&IvfDecode::dispatcher, this, d);
   dispatcher(0);
   for (auto& t : dispatchers) t.join();
   for (auto& t : pool) t.join();
@@ -1555,6 +1583,16 @@ int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threa
   if (n_decoded) *n_decoded = (uint32_t)items.size();
   if (n_shown) *n_shown = shown_total;
   return first_error.load();
+}
+
+int vp8gpu_decode_ivf(vp8gpu_ctx* ctx, const uint8_t* ivf, size_t len, int threads, uint8_t* dst, size_t dst_size,
+                      uint32_t* n_decoded, uint32_t* n_shown) {
+  if (!ctx || !ivf) return VP8GPU_ERR_LOGIC;
+  IvfDecode job(ctx, ivf, len, threads, dst, dst_size);
+  const int rc = job.parse_container();
+  if (rc != VP8GPU_OK) return rc;
+  job.plan();
+  return job.run(n_decoded, n_shown);
 }
 
 }  // extern "C"
