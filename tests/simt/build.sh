@@ -5,15 +5,24 @@ set -e
 cd "$(dirname "$0")"
 SRC=../../alfalfa_b200/csrc
 mkdir -p _build
-CXX="g++ -O2 -g -std=c++17 -fPIC -pthread -DVP8GPU_SIMT_EMUL -Iinclude -Wall -Wno-unknown-pragmas -Wno-unused-function -Wno-unused-variable"
+# SIMT_SANITIZE=alignment (or address, undefined ...): the same build under a compiler sanitizer, into _build/san/ --
+# a misaligned uint4 / uint2 access passes unnoticed on x86 and faults on the GPU
+OUTDIR=_build
+SAN=""
+if [ -n "$SIMT_SANITIZE" ]; then
+  OUTDIR=_build/san
+  SAN="-fsanitize=$SIMT_SANITIZE -fno-sanitize-recover=all -fno-omit-frame-pointer"
+  mkdir -p $OUTDIR
+fi
+CXX="g++ -O2 -g -std=c++17 -fPIC -pthread -DVP8GPU_SIMT_EMUL -Iinclude -Wall -Wno-unknown-pragmas -Wno-unused-function -Wno-unused-variable $SAN"
 for f in kernels.cu tokens.cu engine.cu encoder.cu capi.cc comm.cc; do
-  $CXX -x c++ -c $SRC/$f -o _build/${f%.*}.o &
+  $CXX -x c++ -c $SRC/$f -o $OUTDIR/${f%.*}.o &
 done
 for f in parser.cc serializer.cc enc_costs.cc; do
-  $CXX -c $SRC/$f -o _build/${f%.*}.o &
+  $CXX -c $SRC/$f -o $OUTDIR/${f%.*}.o &
 done
-$CXX -c simt_runtime.cc -o _build/simt_runtime.o &
+$CXX -c simt_runtime.cc -o $OUTDIR/simt_runtime.o &
 wait
-g++ -shared -o _build/libvp8gpu_simt.so _build/kernels.o _build/tokens.o _build/engine.o _build/encoder.o _build/capi.o _build/comm.o \
-  _build/parser.o _build/serializer.o _build/enc_costs.o _build/simt_runtime.o -pthread -ldl
-echo "built $(pwd)/_build/libvp8gpu_simt.so"
+g++ -shared $SAN -o $OUTDIR/libvp8gpu_simt.so $OUTDIR/kernels.o $OUTDIR/tokens.o $OUTDIR/engine.o $OUTDIR/encoder.o $OUTDIR/capi.o $OUTDIR/comm.o \
+  $OUTDIR/parser.o $OUTDIR/serializer.o $OUTDIR/enc_costs.o $OUTDIR/simt_runtime.o -pthread -ldl
+echo "built $(pwd)/$OUTDIR/libvp8gpu_simt.so"

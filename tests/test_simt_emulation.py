@@ -96,3 +96,20 @@ def test_reverse_thread_order_gives_the_same_results(simt_lib):
     run_gpu_tests_emulated(simt_lib, ["tests/test_gpu_encoder.py", "-k", "decisions_equal and not size3"], env_extra=rev)
     if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_reencode")):
         run_gpu_tests_emulated(simt_lib, ["tests/test_gpu_reencode.py"], env_extra=rev)
+
+
+def test_no_misaligned_vector_access_in_the_kernels(simt_lib):
+    """x86 tolerates a misaligned uint4 / uint2 / uint32 access, the GPU faults on it: the emulated build once more
+    under -fsanitize=alignment (tests/simt/build.sh, SIMT_SANITIZE), over the re-encoding path (the kernels without a
+    hardware run) and a few decode vectors"""
+    ubsan = subprocess.run(["g++", "-print-file-name=libubsan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(ubsan) or not os.path.exists(ubsan):
+        pytest.skip("libubsan not available")
+    r = subprocess.run(["sh", os.path.join(SIMT_DIR, "build.sh")], env=dict(os.environ, SIMT_SANITIZE="alignment"), capture_output=True,
+                       text=True, timeout=900)
+    san = os.path.join(SIMT_DIR, "_build", "san", "libvp8gpu_simt.so")
+    assert r.returncode == 0 and os.path.exists(san), r.stderr[-2000:]
+    args = ["tests/test_gpu_parity.py", "-k", "fileplayer and (0b546dad or a4dace04 or e01c6f92 or 8bf4c5bb)"]
+    run_gpu_tests_emulated(san, args, env_extra={"LD_PRELOAD": ubsan})
+    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_reencode")):
+        run_gpu_tests_emulated(san, ["tests/test_gpu_reencode.py"], env_extra={"LD_PRELOAD": ubsan})
