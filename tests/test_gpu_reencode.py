@@ -68,19 +68,20 @@ def make_case(w, h, n, qi_a, qi_b):
     return frames[n:], pred, state
 
 
-def product_reencode(w, h, targets, pred_chunks, state_blob, kf_q_weight, extra_frame_chunk):
-    from alfalfa_b200 import Context, Decoder, Encoder
-    ctx = Context(w, h, max_frames=24)
-    pred_decoder = Decoder(ctx)  # the prediction stream's own decoder (xc-enc.cc:254, 284-300)
-    prediction_frames = []
-    for c in pred_chunks:
-        pf = pred_decoder.parse_frame(c, keep_labels=True)
-        pred_decoder.decode_frame(pf)
-        prediction_frames.append(pf)
-    enc = Encoder.from_decoder(ctx, Decoder.deserialize(ctx, state_blob))
-    out = enc.reencode(targets, prediction_frames, kf_q_weight, extra_frame_chunk)
-    final = enc.export_decoder()
-    return ctx, out, final
+def product_reencode(w, h, targets, pred_chunks, state_blob, kf_q_weight, extra_frame_chunk, timeout=300):
+    """the product's Encoder::reencode in a child process (tests/reencode_worker.py) under a timeout: returns
+    (emitted frames, receiver-in-step flag)"""
+    import pickle
+    import sys
+    with tempfile.TemporaryDirectory() as d:
+        fin, fout = os.path.join(d, "in.pickle"), os.path.join(d, "out.pickle")
+        pickle.dump(dict(w=w, h=h, targets=[tuple(np.ascontiguousarray(p) for p in t) for t in targets], pred=list(pred_chunks),
+                         state=bytes(state_blob), kf_q_weight=kf_q_weight, extra_frame_chunk=bool(extra_frame_chunk)), open(fin, "wb"))
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "reencode_worker.py"), fin, fout], capture_output=True, text=True,
+                           timeout=timeout)
+        assert r.returncode == 0, (r.stdout + r.stderr)[-1500:]
+        out = pickle.load(open(fout, "rb"))
+    return out["frames"], out["in_step"]
 
 
 @needs_ref
@@ -93,19 +94,14 @@ def test_extra_frame_chunk_is_reencoded_byte_for_byte_like_the_reference(size, k
     n = 4
     targets, pred, state = make_case(w, h, n, qi_a=40, qi_b=56)
     want = reference_reencode(w, h, targets, pred, state, kf_q_weight, True)
-    ctx, got, final = product_reencode(w, h, targets, pred, state, kf_q_weight, True)
+    got, in_step = product_reencode(w, h, targets, pred, state, kf_q_weight, True)
     assert len(got) == len(want) == n - 1
     for i, (a, b) in enumerate(zip(got, want)):
         assert a == b, "frame %d: %d vs %d bytes, first difference at %d" % (
             i + 1, len(a), len(b), next((k for k in range(min(len(a), len(b))) if a[k] != b[k]), -1))
     # and the Encoder moved the way a receiver moves: a decoder resumed from the blob that decodes the emitted
     # frames ends up equal to export_decoder()
-    from alfalfa_b200 import Decoder
-    rx = Decoder.deserialize(ctx, state)
-    for c in got:
-        rx.get_frame_output(c)
-    assert rx == final
-    ctx.close()
+    assert in_step
 
 
 @needs_ref
@@ -119,18 +115,13 @@ def test_whole_chunk_is_reencoded_byte_for_byte_like_the_reference(size, kf_q_we
     n = 4
     targets, pred, state = make_case(w, h, n, qi_a=40, qi_b=64)
     want = reference_reencode(w, h, targets, pred, state, kf_q_weight, False)
-    ctx, got, final = product_reencode(w, h, targets, pred, state, kf_q_weight, False)
+    got, in_step = product_reencode(w, h, targets, pred, state, kf_q_weight, False)
     assert len(got) == len(want) == n
     for i, (a, b) in enumerate(zip(got, want)):
         assert a == b, "frame %d: %d vs %d bytes, first difference at %d" % (
             i, len(a), len(b), next((k for k in range(min(len(a), len(b))) if a[k] != b[k]), -1))
     assert got[0][0] & 1, "the chunk no longer starts with a key frame"
-    from alfalfa_b200 import Decoder
-    rx = Decoder.deserialize(ctx, state)
-    for c in got:
-        rx.get_frame_output(c)
-    assert rx == final
-    ctx.close()
+    assert in_step
 
 
 @needs_ref
@@ -138,8 +129,9 @@ def test_reencoded_frames_differ_from_the_prediction_frames_but_keep_their_modes
     """the point of update_residues: same decisions, new residues (the references are another reconstruction)"""
     w, h, n = 176, 144, 3
     targets, pred, state = make_case(w, h, n, qi_a=30, qi_b=60)
-    ctx, got, _ = product_reencode(w, h, targets, pred, state, 1.0, True)
-    from alfalfa_b200 import Decoder
+    got, _ = product_reencode(w, h, targets, pred, state, 1.0, True)
+    from alfalfa_b200 import Context, Decoder
+    ctx = Context(w, h, max_frames=24)   # (the comparison below only decodes: kernels with a hardware record)
     a, b = Decoder(ctx), Decoder.deserialize(ctx, state)
     a.get_frame_output(pred[0])
     for new, old in zip(got, pred[1:]):
@@ -154,31 +146,12 @@ def test_reencoded_frames_differ_from_the_prediction_frames_but_keep_their_modes
 
 
 def test_update_residues_argument_errors():
-    from alfalfa_b200 import Context, Decoder, Encoder, capi
-    w, h = 64, 64
-    ctx = Context(w, h, max_frames=12)
-    enc = Encoder(ctx)
-    y, u, v = synth(w, h, 0)
-    key = enc.encode_with_quantizer(y, u, v, 40)
-    inter = enc.encode_with_quantizer(*synth(w, h, 1), 40)
-    d = Decoder(ctx)
-    pk = d.parse_frame(key, keep_labels=True)
-    d.decode_frame(pk)
-    plain = Decoder(ctx)
-    plain.decode_frame(plain.parse_frame(key))
-    p_nolabels = plain.parse_frame(inter)
-    pi = d.parse_frame(inter, keep_labels=True)
-    with pytest.raises(capi.LogicError):
-        enc.update_residues(y, u, v, pk)            # a key frame is not a prediction InterFrame
-    with pytest.raises(capi.LogicError):
-        enc.update_residues(y, u, v, p_nolabels)    # parsed without keep_labels
-    with pytest.raises(capi.LogicError):
-        Encoder(ctx).update_residues(y, u, v, pi)   # an Encoder without references
-    with pytest.raises(capi.Unsupported):
-        enc.write_frame(pi)                         # only key frames are written back unchanged
-    assert enc.write_frame(pk) == key               # Frame::serialize of the parsed key frame = its own bytes
-    assert len(enc.update_residues(y, u, v, pi)) > 0
-    ctx.close()
+    """LogicError / Unsupported where the reference throws or where the call cannot mean anything (child process, see
+    tests/reencode_worker.py)"""
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "reencode_worker.py"), "errors"], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, (r.stdout + r.stderr)[-1500:]
 
 
 def _decoded_targets(w, h, chunks):
@@ -240,16 +213,11 @@ def test_update_residues_on_libvpx_prediction_streams(prev, this, nframes):
     state = reference_state_after(w, h, prev_chunks, len(prev_chunks))
     targets = _decoded_targets(w, h, chunks)
     want = reference_reencode(w, h, targets, chunks, state, 0.75, True)
-    ctx, got, final = product_reencode(w, h, targets, chunks, state, 0.75, True)
+    got, in_step = product_reencode(w, h, targets, chunks, state, 0.75, True)
     assert len(got) == len(want) == len(chunks) - 1
     for i, (a, b) in enumerate(zip(got, want)):
         assert a == b, "frame %d: %d vs %d bytes" % (i + 1, len(a), len(b))
-    from alfalfa_b200 import Decoder
-    rx = Decoder.deserialize(ctx, state)
-    for c in got:
-        rx.get_frame_output(c)
-    assert rx == final
-    ctx.close()
+    assert in_step
 
 
 @needs_ref
@@ -265,11 +233,5 @@ def test_whole_chunk_after_a_libvpx_stream(prev):
     pred = reference_encode(frames, w, h, qi=60)
     state = reference_state_after(w, h, prev_chunks, len(prev_chunks))
     want = reference_reencode(w, h, frames, pred, state, 0.75, False)
-    ctx, got, final = product_reencode(w, h, frames, pred, state, 0.75, False)
-    assert got == want
-    from alfalfa_b200 import Decoder
-    rx = Decoder.deserialize(ctx, state)
-    for c in got:
-        rx.get_frame_output(c)
-    assert rx == final
-    ctx.close()
+    got, in_step = product_reencode(w, h, frames, pred, state, 0.75, False)
+    assert got == want and in_step
