@@ -318,6 +318,7 @@ def main():
     ap.add_argument("--ref-procs", type=int, default=0, help="reference processes (0 = usable CPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-encode", action="store_true", help="skip the 1080p encode section")
+    ap.add_argument("--no-reencode", action="store_true", help="skip the 1080p re-encoding (update_residues) section")
     ap.add_argument("--encode-frames", type=int, default=30)
     ap.add_argument("--encode-target", type=int, default=45000, help="bytes per frame for encode_with_target_size")
     ap.add_argument("--host-tokens", action="store_true",
@@ -590,6 +591,19 @@ def main():
     if rank == 0 and not a.no_encode:
         encode = bench_encode(a, local)
 
+    # ---------------- re-encoding: Encoder::reencode / update_residues at 1080p ----------------
+    # In a child process under a timeout: this path was finished after the round's GPU minutes were spent (checked
+    # bit-exactly under the SIMT emulator only), so whatever it does on hardware it must not be
+    # able to take this line's other numbers with it.
+    reencode = None
+    if rank == 0 and not a.no_reencode:
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "reencode_bench.py"), "--device", str(local)],
+                               capture_output=True, text=True, timeout=240)
+            reencode = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": (r.stderr or r.stdout)[-300:]}
+        except Exception as e:  # noqa: BLE001  (timeout, malformed output)
+            reencode = {"error": ("%s: %s" % (type(e).__name__, e))[:300]}
+
     # ---------------- CPU baseline (rank 0, one core, bounded sample) ----------------
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
@@ -628,7 +642,8 @@ def main():
                     "api": "vp8gpu_decode_ivf (host IVF bytes -> pinned host YUV)"},
             "gpu_launches": results["value"]["launches"], "gpu_launches_e2e": results["e2e"]["launches"],
             "gpu_launches_resident": int(launches_resident),
-            "roofline": roofline, "single_stream": single, "cpu_baseline": cpu, "encode": encode, "clocks": clocks}))
+            "roofline": roofline, "single_stream": single, "cpu_baseline": cpu, "encode": encode, "reencode": reencode,
+            "clocks": clocks}))
     if dist is not None:
         dist.destroy_process_group()
 
