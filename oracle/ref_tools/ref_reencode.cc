@@ -56,19 +56,24 @@ int main(int argc, char** argv) {
     }
     fclose(f);
 
-    Decoder pred_decoder(w, h);
-    vector<pair<Optional<KeyFrame>, Optional<InterFrame>>> prediction_frames;
-    for (unsigned i = 0; i < pred_ivf.frame_count(); i++) {
-      UncompressedChunk unch{pred_ivf.frame(i), pred_ivf.width(), pred_ivf.height(), false};
-      if (unch.key_frame()) {
-        KeyFrame frame = pred_decoder.parse_frame<KeyFrame>(unch);
-        pred_decoder.decode_frame(frame);
-        prediction_frames.emplace_back(move(frame), Optional<InterFrame>());
+    // the chunk as its own decoder sees it: every frame parsed into the reference's frame object and decoded, so that
+    // the next one parses against the right state (what xc-enc does before it calls Encoder::reencode)
+    typedef pair<Optional<KeyFrame>, Optional<InterFrame>> PredictionFrame;
+    vector<PredictionFrame> prediction_frames;
+    Decoder chunk_decoder(w, h);
+    const unsigned n_frames = pred_ivf.frame_count();
+    prediction_frames.reserve(n_frames);
+    for (unsigned idx = 0; idx < n_frames; idx++) {
+      const UncompressedChunk chunk(pred_ivf.frame(idx), w, h, false);
+      PredictionFrame slot;
+      if (chunk.key_frame()) {
+        slot.first.initialize(chunk_decoder.parse_frame<KeyFrame>(chunk));
+        chunk_decoder.decode_frame(slot.first.get());
       } else {
-        InterFrame frame = pred_decoder.parse_frame<InterFrame>(unch);
-        pred_decoder.decode_frame(frame);
-        prediction_frames.emplace_back(Optional<KeyFrame>(), move(frame));
+        slot.second.initialize(chunk_decoder.parse_frame<InterFrame>(chunk));
+        chunk_decoder.decode_frame(slot.second.get());
       }
+      prediction_frames.push_back(move(slot));
     }
 
     Encoder encoder(EncoderStateDeserializer::build<Decoder>(argv[6]), false, REALTIME_QUALITY);
