@@ -146,6 +146,7 @@ SYMBOLS = {
     "vp8gpu_encoder_create_from_decoder": (C.c_int, [_vp, _vp, _pp]),
     "vp8gpu_encoder_export_decoder": (C.c_int, [_vp, _pp]),
     "vp8gpu_encoder_minihash": (C.c_int, [_vp, C.POINTER(C.c_uint32)]),
+    "vp8gpu_encoder_set_two_pass": (C.c_int, [_vp, C.c_int]),
     "vp8gpu_encoder_update_residues": (C.c_int, [_vp, _u8p, C.c_size_t, _u8p, _u8p, C.c_size_t, _vp, C.c_int, C.c_int,
                                                  _u8p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "vp8gpu_encoder_reencode_as_interframe": (C.c_int, [_vp, _u8p, C.c_size_t, _u8p, _u8p, C.c_size_t, _vp, C.c_int,

@@ -86,4 +86,41 @@ void build_enc_tables(EncTables& t, const uint8_t* mv_probs) {
   }
 }
 
+// ---- two-pass key frames: token costs and the cost of a coefficient value beyond its token ----
+namespace {
+// tokens.hh:36-49: ZERO ONE TWO THREE FOUR CAT1..CAT6 EOB = 0..11; costs.cc:38-52
+const int8_t kCoefTree[22] = {-11, 2, 0, 4, -1, 6, 8, 12, -2, 10, -3, -4, 14, 16, -5, -6, 18, 20, -7, -8, -9, -10};
+// extra bits of DCT_VAL_CATEGORY1..6: first value, number of bits, their probabilities (tokens.hh:62-78)
+const int kCatBase[6] = {5, 7, 11, 19, 35, 67};
+const int kCatBits[6] = {1, 2, 3, 4, 5, 11};
+const uint8_t kCatProbs[6][11] = {{159}, {165, 145}, {173, 148, 140}, {176, 155, 140, 135}, {180, 157, 141, 134, 130},
+                                  {254, 254, 243, 230, 196, 177, 153, 140, 133, 130, 129}};
+}  // namespace
+
+void build_trellis_tables(TrellisTables& t) {
+  memset(&t, 0, sizeof(t));
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 8; j++)
+      for (int k = 0; k < 3; k++) {
+        const uint8_t* probs = k_coef_default_probs + ((i * 8 + j) * 3 + k) * 11;
+        // after a zero (context 0, beyond the first position of the block type) a block cannot end: the tree is
+        // entered below its end-of-block decision (costs.cc:180-185)
+        tree_costs(t.token_cost[i][j][k], probs, kCoefTree, (k == 0 && j > (i == 0 ? 1 : 0)) ? 2 : 0, 0);
+      }
+  // dct_value_cost (libvpx tokenize.c fill_value_tokens): the extra bits of the value's category, most significant
+  // first, each with its own probability, plus the sign at probability one half; nothing for 0
+  for (int v = -2048; v < 2048; v++) {
+    const int a = v < 0 ? -v : v;
+    if (a == 0) continue;
+    uint32_t cost = cost_bit(128, v < 0);
+    if (a > 4) {
+      int cat = 0;
+      while (cat + 1 < 6 && kCatBase[cat + 1] <= a) cat++;
+      const int extra = a - kCatBase[cat];
+      for (int b = 0; b < kCatBits[cat]; b++) cost += cost_bit(kCatProbs[cat][b], (extra >> (kCatBits[cat] - 1 - b)) & 1);
+    }
+    t.value_cost[v + 2048] = (uint16_t)cost;
+  }
+}
+
 }  // namespace vp8

@@ -16,6 +16,14 @@ struct EncTables {
   uint16_t pad[2];
 };
 
+// Tables of the second (trellis) pass of a two-pass key frame (encoder/encoder.cc:220-408)
+struct TrellisTables {
+  uint16_t token_cost[4][8][3][12];  // [block type][band][context][token]  Costs::fill_token_costs of the DEFAULT
+                                     // coefficient probabilities (encode_intra.cc:413-414: decoder_state_ is a fresh one)
+  uint16_t value_cost[4096];         // Costs::coeff_base_cost( v ) at [v + 2048]: extra bits + sign of the token of v
+};
+void build_trellis_tables(TrellisTables& t);
+
 // mv_probs: the stream's saved motion-vector probabilities ([2][19]); nullptr = the default table
 void build_enc_tables(EncTables& t, const uint8_t* mv_probs = nullptr);
 

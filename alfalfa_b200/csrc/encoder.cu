@@ -46,6 +46,8 @@ struct vp8gpu_encoder {
                                         // update_rd_multipliers left them; a copy starts from the defaults again
   int lf_sharpness = 0;          // sharpness_level of the frame being built (0 for the Encoder's own frames)
   uint8_t tab_mv_probs[38];      // the motion-vector probabilities the rate tables on the device were built from
+  bool two_pass = false;         // Encoder( ..., two_pass, ... ) (encoder.hh:347): key frames get a second, trellis pass
+  uint8_t* d_trellis = nullptr;  // TrellisTables | y2_prev[n_mbs] on the device (two-pass only)
   double last_ssim = -1.0;     // encode_stats_.ssim of the last frame
   vp8::State* dec_state = nullptr;  // DecoderState a decoder has after the frames emitted so far (export_decoder)
   // device scratch: EncJob | DevJob | sync ints | mbs | tokens | rate tables
@@ -104,7 +106,9 @@ void pass_dims(const vp8gpu_encoder* enc, int sub, int* w, int* h, int* cols, in
 // launch half of a pass: everything up to the asynchronous download of the token count and the records
 // reenc != nullptr: a pass of Encoder::reencode_as_interframe (reencode.cc:39-129) -- the quantiser comes with the
 // call (a key frame's indices with another y_ac_qi), update_rd_multipliers and fill_mv_sad_costs are NOT run
-int encode_launch(vp8gpu_encoder* enc, bool key, int qi, int sub, const vp8gpu_quant* reenc = nullptr) {
+// trellis: the second pass of a two-pass key frame (k_enc_rd<true>; enc->d_trellis holds the tables and the first
+// pass's Y2 flags)
+int encode_launch(vp8gpu_encoder* enc, bool key, int qi, int sub, const vp8gpu_quant* reenc = nullptr, bool trellis = false) {
   Engine* e = enc->e;
   const vp8::Geom& g = e->geom();
   int pw, ph, cols, rows;
@@ -166,6 +170,10 @@ int encode_launch(vp8gpu_encoder* enc, bool key, int qi, int sub, const vp8gpu_q
   }
   ej->mv_costs_zero = !key && !enc->mv_costs_filled;
   ej->mv_sad_zero = !key && !enc->mv_sad_filled;
+  if (trellis) {
+    ej->trellis = reinterpret_cast<const vp8::TrellisTables*>(enc->d_trellis);
+    ej->y2_prev = enc->d_trellis + align_up(sizeof(vp8::TrellisTables), 256);
+  }
   auto fail = [&](int code) {
     e->frame_release(out);
     return code;
@@ -178,7 +186,8 @@ int encode_launch(vp8gpu_encoder* enc, bool key, int qi, int sub, const vp8gpu_q
   CUF(cudaMemcpyAsync(enc->dev + enc->off_encjob, enc->h_hdr, 512, cudaMemcpyHostToDevice, s));
   CUF(cudaMemsetAsync(d_sync, 0, sizeof(int) * (128 + 2 * (size_t)g.mb_rows), s));
   const vp8::EncJob* d_ej = reinterpret_cast<const vp8::EncJob*>(enc->dev + enc->off_encjob);
-  if (int ce = vp8::launch_enc_rd(d_ej, rows, g, d_sync + 0, s)) return fail(e->cuda_fail((cudaError_t)ce, "k_enc_rd"));
+  if (int ce = trellis ? vp8::launch_enc_rd_trellis(d_ej, rows, g, d_sync + 0, s) : vp8::launch_enc_rd(d_ej, rows, g, d_sync + 0, s))
+    return fail(e->cuda_fail((cudaError_t)ce, "k_enc_rd"));
   e->count_launches(1);
   e->mark_frames(enc->lane, ids, key ? 2 : 3, 2u);
   // results back: token count first, then the records
@@ -216,8 +225,8 @@ int encode_collect(vp8gpu_encoder* enc, int* out_frame) {
 
 // One encoding pass at quantiser index qi over the whole frame (sub = 1) or the 1/16 sample (sub = 4):
 // decisions, transforms, reconstruction on the device; records and tokens back on the host.
-int encode_core(vp8gpu_encoder* enc, bool key, int qi, int sub, int* out_frame, const vp8gpu_quant* reenc = nullptr) {
-  const int rc = encode_launch(enc, key, qi, sub, reenc);
+int encode_core(vp8gpu_encoder* enc, bool key, int qi, int sub, int* out_frame, const vp8gpu_quant* reenc = nullptr, bool trellis = false) {
+  const int rc = encode_launch(enc, key, qi, sub, reenc, trellis);
   return rc == VP8GPU_OK ? encode_collect(enc, out_frame) : rc;
 }
 
@@ -434,6 +443,7 @@ int vp8gpu_encoder_clone(const vp8gpu_encoder* src, vp8gpu_encoder** out) {
   int rc = encoder_alloc(src->ctx, &enc);
   if (rc != VP8GPU_OK) return rc;
   enc->has_state = src->has_state;
+  enc->two_pass = src->two_pass;
   enc->writer = src->writer;  // (the copy's frame objects, i.e. the writer's header state, start fresh: encoder.cc:92-102)
   enc->last_qi = src->last_qi;
   enc->last_lf = src->last_lf;
@@ -491,6 +501,7 @@ void vp8gpu_encoder_destroy(vp8gpu_encoder* enc) {
   if (enc->src >= 0) enc->e->frame_release(enc->src);
   if (enc->dev) cudaFree(enc->dev);
   if (enc->d_split) cudaFree(enc->d_split);
+  if (enc->d_trellis) cudaFree(enc->d_trellis);
   if (enc->h_hdr) cudaFreeHost(enc->h_hdr);
   if (enc->h_mbs) cudaFreeHost(enc->h_mbs);
   if (enc->h_tokens) cudaFreeHost(enc->h_tokens);
@@ -546,11 +557,60 @@ static int finish_frame(vp8gpu_encoder* enc, bool key, const std::vector<uint8_t
   return VP8GPU_OK;
 }
 
+// The macroblock loop of encode_raster (encode_intra.cc:409-443): once, or -- key frame of a two-pass Encoder -- twice,
+// the second time with trellis quantisation.  Between the passes the reference keeps two things of the first one:
+// the token probability updates it derived from it (optimize_probability_tables runs after EACH pass on the same
+// frame header: the second pass adds to them) and every block's has_nonzero, of which the second pass reads only
+// those it does not recompute: the Y2 blocks of its B_PRED macroblocks.
+static int encode_passes(vp8gpu_encoder* enc, bool key, int qi, int* frame) {
+  if (!(key && enc->two_pass)) return encode_core(enc, key, qi, 1, frame);
+  Engine* e = enc->e;
+  const vp8::Geom& g = e->geom();
+  const size_t n_mbs = (size_t)g.mb_cols * g.mb_rows, y2_off = align_up(sizeof(vp8::TrellisTables), 256);
+  if (!enc->d_trellis) {
+    if (cudaMalloc(&enc->d_trellis, y2_off + align_up(n_mbs, 256)) != cudaSuccess) return e->fail(VP8GPU_ERR_NOMEM, "trellis tables");
+    vp8::TrellisTables* t = new vp8::TrellisTables();
+    vp8::build_trellis_tables(*t);
+    const cudaError_t ce = cudaMemcpy(enc->d_trellis, t, sizeof(*t), cudaMemcpyHostToDevice);
+    delete t;
+    if (ce != cudaSuccess) return e->cuda_fail(ce, "trellis tables upload");
+  }
+  int rc = encode_core(enc, true, qi, 1, frame);
+  if (rc != VP8GPU_OK) return rc;
+  e->frame_release(*frame);
+  *frame = -1;
+  if (enc->writer == 0) {  // optimize_probability_tables of the first pass: only its effect on the header state matters
+    std::vector<uint8_t> discard;
+    uint8_t probs[1056];
+    memcpy(probs, enc->dec_state->coef_probs, 1056);
+    rc = encode_bytes(enc, true, qi, 0, 1, true, probs, discard);
+    if (rc != VP8GPU_OK) return rc;
+  }
+  std::vector<uint8_t> y2(n_mbs, 0);
+  for (size_t i = 0; i < n_mbs; i++) {
+    const vp8gpu_mb& m = enc->h_mbs[i];
+    if (m.y_mode == VP8GPU_B_PRED) {  // Y2 untouched (a fresh key_frame_ object: false); Y blocks left as "Y without Y2"
+      y2[i] = 2;
+      continue;
+    }
+    for (unsigned t = 0; t < m.tok_cnt; t++) {
+      const uint32_t tk = enc->h_tokens[m.tok_off + t];
+      if (((tk >> 20) & 31) == 24 && (tk & 0xFFFF)) y2[i] = 1;
+    }
+  }
+  if (cudaMemcpy(enc->d_trellis + y2_off, y2.data(), n_mbs, cudaMemcpyHostToDevice) != cudaSuccess)
+    return e->fail(VP8GPU_ERR_CUDA, "two-pass: Y2 flags upload");
+  rc = encode_core(enc, true, qi, 1, frame, nullptr, true);
+  if (rc != VP8GPU_OK) return rc;
+  for (size_t i = 0; i < n_mbs; i++) enc->h_mbs[i].reserved = 0;  // the kernel's has_nonzero masks are not part of a record
+  return VP8GPU_OK;
+}
+
 // encode at qi, choose the loop filter, serialize: Encoder::encode_raster + write_frame (encoder.cc:140-178)
 static int encode_final(vp8gpu_encoder* enc, bool key, int qi, uint8_t* out, size_t cap, size_t* size) {
   int frame = -1, lf = 0;
   double ssim = -1.0;
-  int rc = encode_core(enc, key, qi, 1, &frame);
+  int rc = encode_passes(enc, key, qi, &frame);
   if (rc != VP8GPU_OK) return rc;
   rc = choose_loop_filter(enc, frame, key, &lf, &ssim);
   std::vector<uint8_t> bytes;
@@ -668,6 +728,14 @@ int vp8gpu_encoder_estimate_frame_size(vp8gpu_encoder* enc, const uint8_t* y, si
   int rc = upload_source(enc, y, y_stride, u, v, uv_stride);
   if (rc != VP8GPU_OK) return rc;
   return estimate_size(enc, !enc->has_state, y_ac_qi, size);
+}
+
+// Encoder( ..., two_pass, ... ) (encoder.hh:347-351): key frames are coded twice, the second time with trellis
+// quantisation (encoder.cc:220-408); inter frames are unaffected, as in the reference (encode_inter.cc codes FIRST_PASS)
+int vp8gpu_encoder_set_two_pass(vp8gpu_encoder* enc, int on) {
+  if (!enc) return VP8GPU_ERR_LOGIC;
+  enc->two_pass = on != 0;
+  return VP8GPU_OK;
 }
 
 // bitstream writer: 0 = byte-identical to the reference Encoder's output (default), 1 = compact / parallel

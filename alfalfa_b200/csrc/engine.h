@@ -57,6 +57,7 @@ struct DevJob {
 // decisions macroblock by macroblock (encoder/encode_intra.cc, encode_inter.cc), transforms, quantises,
 // emits tokens + macroblock records and reconstructs exactly what a decoder will reconstruct.
 struct EncTables;
+struct TrellisTables;
 struct EncJob {
   const uint8_t* src;      // source raster (same layout as every other raster)
   const uint8_t* ref;      // last reconstructed + loop-filtered frame; nullptr for key frames
@@ -81,6 +82,11 @@ struct EncJob {
   uint8_t mv_sad_zero;     // the same for the diamond search's vector cost alone (Costs::fill_mv_sad_costs): Encoder::
                            //   reencode_as_interframe fills the component costs but not these (reencode.cc:85)
   uint8_t pad[1];
+  // second pass of a two-pass key frame (k_enc_rd<true>, trellis quantisation encoder.cc:220-408)
+  const TrellisTables* trellis;  // token costs of the default probabilities, value costs
+  const uint8_t* y2_prev;        // [cols * rows] what the FIRST pass left in the frame object: bit 0 = Y2Block::has_nonzero()
+                                 //   (the flag a B_PRED macroblock of the second pass keeps: its Y2 block is not touched,
+                                 //   encode_intra.cc:181-184), bit 1 = the macroblock was B_PRED (its Y blocks' type)
 };
 
 // Encoder::update_residues on the device (reencode.cuh): keep a coded frame's modes and vectors, recompute its
@@ -115,6 +121,7 @@ struct TokJob {
 // Kernel launchers (kernels.cu, tokens.cu).  `stream` is a cudaStream_t passed as void* so this header
 // stays free of CUDA includes.  Return 0 or a cudaError_t value.
 int launch_inter(const DevJob* jobs, int njobs, const Geom& g, void* stream);
+int launch_enc_rd_trellis(const EncJob* job, int rows, const Geom& g, int* ticket, void* stream);
 int launch_reenc_inter(const ReencJob* job, int n_mbs, const Geom& g, void* stream);
 int launch_reenc_intra(const ReencJob* job, int rows, const Geom& g, int* ticket, void* stream);
 // `epoch`: a value no earlier launch on this context has used (Engine::next_epoch); it marks the hand-over

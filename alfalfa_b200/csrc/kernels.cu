@@ -1309,6 +1309,97 @@ __device__ __forceinline__ int implied_bmode(int y_mode) {
   return y_mode == VP8GPU_V_PRED ? VP8GPU_B_VE_PRED : (y_mode == VP8GPU_H_PRED ? VP8GPU_B_HE_PRED : (y_mode == VP8GPU_TM_PRED ? VP8GPU_B_TM_PRED : VP8GPU_B_DC_PRED));
 }
 
+// Encoder::trellis_quantize (encoder.cc:220-408) of one block by one lane.  c: the block's transform coefficients in
+// raster order (Y after Y2: DC already 0); on return the quantised values the trellis chose.  type: 0 Y after Y2,
+// 1 Y2, 2 U / V, 3 Y without Y2; ctx: has_nonzero of the block above + of the block to the left.  Returns whether
+// any value is non-zero.  Two candidate levels per position ({q, q - 1} towards zero), Viterbi from the last coded
+// position back to the first with the reference's integer rate / distortion arithmetic.
+__device__ __attribute__((noinline)) bool trellis_block(int16_t* c, int type, int dcq, int acq, int ctx, const TrellisTables& T, uint32_t RM, uint32_t DM) {
+  constexpr uint8_t kZig[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
+  constexpr uint8_t kBandOf[17] = {0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7, 0};
+  constexpr uint8_t kPrevClass[12] = {0, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 0};
+  constexpr int EOB = 11;
+  const int first = type == 0 ? 1 : 0;
+  int coded = 0;
+  for (int i = first; i < 16; i++)
+    if (c[kZig[i]]) coded = i + 1;
+  if (coded == 0) {
+    for (int i = 0; i < 16; i++) c[i] = 0;
+    return false;
+  }
+  uint32_t rate[17][2], dist[17][2], cost[17][2];
+  int16_t coeff[17][2];
+  uint8_t token[17][2], nxt[17][2];
+  for (int i = 0; i < 2; i++) {
+    rate[coded][i] = 0, dist[coded][i] = 0, cost[coded][i] = 0;
+    token[coded][i] = EOB, coeff[coded][i] = 0, nxt[coded][i] = 255;
+  }
+  for (int idx = coded - 1; idx >= first; idx--) {
+    const int factor = idx == 0 ? dcq : acq;
+    const int16_t orig = c[kZig[idx]];
+    const int16_t quantized = (int16_t)(orig / factor);
+    for (int qs = 0; qs < 2; qs++) {
+      int16_t cand = quantized;
+      if (cand < 0) {
+        cand = (int16_t)(cand + qs);
+        if (cand > 0) cand = 0;
+      } else if (cand > 0 || qs == 0) {
+        cand = (int16_t)(cand - qs);
+        if (cand < 0) cand = 0;
+      } else {  // cand == 0 and qs != 0: the same node as level 0
+        rate[idx][1] = rate[idx][0], dist[idx][1] = dist[idx][0], cost[idx][1] = cost[idx][0];
+        coeff[idx][1] = coeff[idx][0], token[idx][1] = token[idx][0], nxt[idx][1] = nxt[idx][0];
+        continue;
+      }
+      const int16_t diff = (int16_t)(orig - cand * factor);
+      const uint32_t sse = (uint32_t)((int)diff * (int)diff);
+      const int a = cand < 0 ? -cand : cand;
+      const int tok = a <= 4 ? a : (a <= 6 ? 5 : (a <= 10 ? 6 : (a <= 18 ? 7 : (a <= 34 ? 8 : (a <= 66 ? 9 : 10)))));  // Costs::token_for_coeff
+      uint32_t d2[2], r2[2], c2[2];
+      int best_next = 255;
+      uint32_t best_cost = 0xFFFFFFFFu;
+      for (int n = 0; n < 2; n++) {
+        d2[n] = dist[idx + 1][n] + sse;
+        r2[n] = rate[idx + 1][n];
+        if (idx < 15) r2[n] += T.token_cost[type][kBandOf[idx + 1]][kPrevClass[tok]][token[idx + 1][n]];
+        c2[n] = rdcost(r2[n], d2[n], RM, DM);
+        if (c2[n] < best_cost) best_cost = c2[n], best_next = n;
+      }
+      if (cand != 0 || token[idx + 1][best_next] != EOB) {
+        coeff[idx][qs] = cand, token[idx][qs] = (uint8_t)tok;
+        rate[idx][qs] = r2[best_next] + T.value_cost[cand + 2048];
+        dist[idx][qs] = d2[best_next];
+        cost[idx][qs] = c2[best_next];
+        nxt[idx][qs] = (uint8_t)best_next;
+      } else {  // a zero followed by the end of the block: the block ends here
+        coeff[idx][qs] = 0, token[idx][qs] = EOB;
+        rate[idx][qs] = 0;
+        dist[idx][qs] = sse;
+        cost[idx][qs] = rdcost(0, sse, RM, DM);
+        nxt[idx][qs] = 255;
+      }
+    }
+  }
+  uint32_t min_cost = 0xFFFFFFFFu;
+  int choice = 0;
+  for (int i = 0; i < 2; i++) {
+    rate[first][i] += T.token_cost[type][kBandOf[first]][ctx][token[first][i]];
+    cost[first][i] = rdcost(rate[first][i], dist[first][i], RM, DM);
+    if (cost[first][i] < min_cost) min_cost = cost[first][i], choice = i;
+  }
+  bool any = false;
+  int i = first;
+  for (; i < 16; i++) {
+    if (token[i][choice] == EOB) break;
+    c[kZig[i]] = coeff[i][choice];
+    any |= coeff[i][choice] != 0;
+    choice = nxt[i][choice];
+  }
+  for (; i < 16; i++) c[kZig[i]] = 0;
+  return any;
+}
+
+template <bool TRELLIS>
 __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __restrict__ jobp, Geom g, int* ticket) {
   __shared__ EncSmem s_all[WF_WARPS];
   __shared__ uint16_t s_lut[128];
@@ -1341,6 +1432,10 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __res
   bool left_inter = false;
   int left_mvx = 0, left_mvy = 0, left_ymode = VP8GPU_DC_PRED;
   unsigned long long left_bm = 0;
+  // second pass of a two-pass key frame: has_nonzero of the 25 blocks of the macroblock to the left (bits 0-15 Y,
+  // 16-19 U, 20-23 V, 24 Y2), the token contexts of the trellis (encoder.cc:362-363)
+  uint32_t left_nz = 0;
+  __shared__ uint8_t s_nz[TRELLIS ? WF_WARPS : 1][TRELLIS ? 32 : 1];
 
   for (int col = 0; col < cols; col++) {
     const int mbi = row * cols + col;
@@ -1396,6 +1491,11 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __res
       above_bm = __ldcg(reinterpret_cast<const unsigned long long*>(J.mbs + mbi - cols) + 3);
       if (col > 0) rec_al = __ldcg(reinterpret_cast<const uint4*>(J.mbs + mbi - cols - 1));
     }
+    uint32_t above_nz = 0;
+    if constexpr (TRELLIS) {
+      if (row > 0) above_nz = __ldcg(reinterpret_cast<const uint32_t*>(J.mbs + mbi - cols) + 5);  // vp8gpu_mb::reserved
+    }
+    uint32_t trial_nz = 0;  // B_PRED trial: has_nonzero of its sub-blocks
     __syncwarp();
 
     const uint8_t* A = W + 16;  // above[x]
@@ -1477,13 +1577,33 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __res
 #pragma unroll
           for (int k = 0; k < 16; k++) d[k] = S.tmp[k];
           vp8m::fdct16(d, o);
+          if constexpr (TRELLIS) {
+            // luma_sb_apply_intra_prediction( ..., SECOND_PASS ) (encode_intra.cc:58-63): contexts from the sub-blocks
+            // coded so far in this trial and from the neighbouring macroblocks
+            const int ca = by > 0 ? (int)((trial_nz >> (b - 4)) & 1) : (row > 0 ? (int)((above_nz >> (12 + bx)) & 1) : 0);
+            const int cl = bx > 0 ? (int)((trial_nz >> (b - 1)) & 1) : (col > 0 ? (int)((left_nz >> (4 * by + 3)) & 1) : 0);
+            // trellis_quantize runs BEFORE set_Y_without_Y2 (encode_intra.cc:58-66): the sub-block still has the type
+            // the FIRST pass left it with -- Y after Y2 unless that pass coded the macroblock as B_PRED -- and with
+            // that type the trellis starts at position 1 and leaves the DC as the transform produced it
+            const int ttype = (J.y2_prev[mbi] & 2) ? 3 : 0;
+            bool any = trellis_block(o, ttype, q.y_dc, q.y_ac, ca + cl, *J.trellis, RM, DM);
+            if (ttype == 0 && o[0] != 0) any = true;
+            if (any) trial_nz |= 1u << b;
 #pragma unroll
-          for (int k = 0; k < 16; k++) {
-            const int f = k ? q.y_ac : q.y_dc;
-            int qv = vp8m::quantize_trunc(o[k], f);
-            qv = qv > 2047 ? 2047 : (qv < -2047 ? -2047 : qv);
-            S.qb[b][k] = (int16_t)qv;
-            d[k] = (int16_t)(qv * f);
+            for (int k = 0; k < 16; k++) {
+              const int f = k ? q.y_ac : q.y_dc;
+              S.qb[b][k] = o[k];
+              d[k] = (int16_t)(o[k] * f);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+              const int f = k ? q.y_ac : q.y_dc;
+              int qv = vp8m::quantize_trunc(o[k], f);
+              qv = qv > 2047 ? 2047 : (qv < -2047 ? -2047 : qv);
+              S.qb[b][k] = (int16_t)qv;
+              d[k] = (int16_t)(qv * f);
+            }
           }
           vp8m::idct16(d, o);
 #pragma unroll
@@ -1495,6 +1615,7 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __res
       }
       best_cost = rdcost(rate, dist, RM, DM);
       best_mode = VP8GPU_B_PRED;
+      if constexpr (TRELLIS) trial_nz = __shfl_sync(0xffffffffu, trial_nz, 0);  // lane 0 coded the sub-blocks
     }
     // ---- 16x16 modes, in the reference's order TM, H, V, DC; distortion = variance of the prediction ----
     {
@@ -1745,7 +1866,77 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __res
     int cnt = 0;
     int16_t qv[16];
     const bool has_blk = lane < 24 || (lane == 24 && !bpred);
-    if (has_blk) {
+    uint32_t mb_nz = 0;
+    if constexpr (TRELLIS) {
+      // SECOND_PASS (encode_intra.cc:199-219, 305-330): every block through trellis_quantize, whose first token is
+      // priced in the context of the blocks above and to the left -- already requantised ones.  Blocks on the same
+      // anti-diagonal of their plane are independent: seven rounds; Y2 (check_reset_y2 first) in the first one.
+      uint8_t* const nz = s_nz[warp];
+      if (lane < 25) nz[lane] = (bpred && lane < 16) ? (uint8_t)((trial_nz >> lane) & 1) : 0;
+      __syncwarp();
+      const int gx = lane < 16 ? (lane & 3) : (lane & 1), gy = lane < 16 ? (lane >> 2) : ((lane >> 1) & 1);
+      const int diag = lane == 24 ? 0 : gx + gy;
+      for (int round = 0; round < 7; round++) {
+        if (has_blk && diag == round && !(bpred && lane < 16)) {
+          int ca, cl, type;
+          if (lane < 16) {
+            type = 0;
+            ca = gy > 0 ? nz[lane - 4] : (row > 0 ? (int)((above_nz >> (12 + gx)) & 1) : 0);
+            cl = gx > 0 ? nz[lane - 1] : (col > 0 ? (int)((left_nz >> (4 * gy + 3)) & 1) : 0);
+          } else if (lane < 24) {
+            type = 2;
+            const int base = lane & ~3;  // 16: U, 20: V
+            ca = gy > 0 ? nz[lane - 2] : (row > 0 ? (int)((above_nz >> (base + 2 + gx)) & 1) : 0);
+            cl = gx > 0 ? nz[lane - 1] : (col > 0 ? (int)((left_nz >> (base + 2 * gy + 1)) & 1) : 0);
+          } else {
+            type = 1;
+            ca = row > 0 ? (int)((above_nz >> 24) & 1) : 0;
+            cl = col > 0 ? (int)((left_nz >> 24) & 1) : 0;
+          }
+          const int dcq = lane < 16 ? q.y_dc : (lane < 24 ? q.uv_dc : q.y2_dc);
+          const int acq = lane < 16 ? q.y_ac : (lane < 24 ? q.uv_ac : q.y2_ac);
+          int16_t cc[16];
+#pragma unroll
+          for (int k = 0; k < 16; k++) cc[k] = coef[lane * CS + k];
+          if (lane < 16) cc[0] = 0;  // Y after Y2: the DC travels in Y2
+          if (lane == 24 && !(q.y2_dc >= 35 && q.y2_ac >= 35)) {  // Encoder::check_reset_y2 (encoder.cc:198-218)
+            int sum = 0;
+            bool keep = false;
+            for (int k = 0; k < 16; k++) {
+              sum += cc[k] < 0 ? -cc[k] : cc[k];
+              if (sum >= 35) {
+                keep = true;
+                break;
+              }
+            }
+            if (!keep)
+              for (int k = 0; k < 16; k++) cc[k] = 0;
+          }
+          nz[lane] = trellis_block(cc, type, dcq, acq, ca + cl, *J.trellis, RM, DM) ? 1 : 0;
+#pragma unroll
+          for (int k = 0; k < 16; k++) {
+            qv[k] = cc[k];
+            cnt += cc[k] != 0;
+            coef[lane * CS + k] = (int16_t)(cc[k] * (k ? acq : dcq));
+          }
+        }
+        __syncwarp();
+      }
+      if (bpred && lane < 16) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          const int v = S.qb[lane][k];
+          qv[k] = (int16_t)v;
+          cnt += v != 0;
+          coef[lane * CS + k] = (int16_t)(v * (k ? q.y_ac : q.y_dc));
+        }
+      }
+      // what the macroblocks to the right and below will see: a B_PRED macroblock leaves its Y2 block alone, so that
+      // block still says what the first pass left there
+      mb_nz = __ballot_sync(0xffffffffu, lane < 24 && nz[lane]);
+      const uint32_t y2_flag = bpred ? (uint32_t)(J.y2_prev[mbi] & 1) : (uint32_t)nz[24];
+      mb_nz = (mb_nz & 0x00FFFFFFu) | ((y2_flag & 1u) << 24);
+    } else if (has_blk) {
       const int dcq = lane < 16 ? q.y_dc : (lane < 24 ? q.uv_dc : q.y2_dc);
       const int acq = lane < 16 ? q.y_ac : (lane < 24 ? q.uv_ac : q.y2_ac);
 #pragma unroll
@@ -1838,7 +2029,7 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __res
       m.mv_x = (int16_t)(inter ? best_mvx : 0);
       m.mv_y = (int16_t)(inter ? best_mvy : 0);
       m.split_idx = 0;
-      m.reserved = 0;
+      m.reserved = TRELLIS ? mb_nz : 0;  // second pass: the blocks' has_nonzero for the row below (cleared by the host)
       m.b_modes = bpred ? bm : 0;
       J.mbs[mbi] = m;
     }
@@ -1847,6 +2038,7 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __res
     left_mvy = inter ? best_mvy : 0;
     left_ymode = best_mode;
     left_bm = bpred ? bm : 0;
+    if constexpr (TRELLIS) left_nz = mb_nz;
     publish_row(progress, col + 1, lane);
   }
 }
@@ -1973,7 +2165,11 @@ int launch_loopfilter(const DevJob* jobs, int njobs, const Geom& g, int* ticket,
 }
 
 int launch_enc_rd(const EncJob* job, int rows, const Geom& g, int* ticket, void* stream) {
-  VP8_LAUNCH(k_enc_rd, (rows + WF_WARPS - 1) / WF_WARPS, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream))(job, g, ticket);
+  VP8_LAUNCH(k_enc_rd<false>, (rows + WF_WARPS - 1) / WF_WARPS, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream))(job, g, ticket);
+  return (int)cudaGetLastError();
+}
+int launch_enc_rd_trellis(const EncJob* job, int rows, const Geom& g, int* ticket, void* stream) {
+  VP8_LAUNCH(k_enc_rd<true>, (rows + WF_WARPS - 1) / WF_WARPS, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream))(job, g, ticket);
   return (int)cudaGetLastError();
 }
 

@@ -423,6 +423,10 @@ class Encoder:
         check(self.L.vp8gpu_encoder_export_decoder(self.h, C.byref(h)), self.ctx.h, "encoder_export_decoder")
         return Decoder(self.ctx, _h=h)
 
+    def set_two_pass(self, on):
+        """Encoder( ..., two_pass, ... ): key frames get the trellis pass (encoder.cc:220-408)"""
+        check(self.L.vp8gpu_encoder_set_two_pass(self.h, int(bool(on))), self.ctx.h, "encoder_set_two_pass")
+
     def set_writer(self, mode):
         """0: bitstream byte-identical to the reference encoder's (default); 1: compact writer, 8 partitions"""
         check(self.L.vp8gpu_encoder_set_writer(self.h, int(mode)), self.ctx.h, "encoder_set_writer")

@@ -299,6 +299,8 @@ class Encoder {
     check(vp8gpu_encoder_export_decoder(h_, &d), ctx_.get(), "export_decoder");
     return Decoder(ctx_, d, width_, height_);
   }
+  // Encoder( ..., two_pass, ... ) (encoder.hh:347-351): key frames get the trellis pass (encoder.cc:220-408)
+  void set_two_pass(bool on) { check(vp8gpu_encoder_set_two_pass(h_, on), ctx_.get(), "set_two_pass"); }
   // minihash (encoder.hh:382)
   uint32_t minihash() const {
     uint32_t m = 0;

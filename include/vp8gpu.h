@@ -418,6 +418,10 @@ int vp8gpu_encoder_minihash(vp8gpu_encoder* enc, uint32_t* out);
  * are byte-identical to the reference encoder's.  1: compact -- only the probability updates that pay, eight
  * DCT partitions written on eight host threads (same decisions and reconstruction, fewer bytes, faster). */
 int vp8gpu_encoder_set_writer(vp8gpu_encoder* enc, int mode);
+/* Encoder( ..., two_pass, ... ) (encoder/encoder.hh:347-351): with on != 0 a key frame is coded twice, the second pass
+ * with trellis quantisation (Encoder::trellis_quantize, check_reset_y2, encoder/encoder.cc:198-408) priced by the token
+ * costs of the default tables; inter frames are coded once either way, as in the reference. */
+int vp8gpu_encoder_set_two_pass(vp8gpu_encoder* enc, int on);
 /* Encoder::encode_with_quantizer (encoder.cc:559-590) */
 int vp8gpu_encoder_encode_with_quantizer(vp8gpu_encoder* enc, const uint8_t* y, size_t y_stride, const uint8_t* u,
                                          const uint8_t* v, size_t uv_stride, int y_ac_qi, uint8_t* out, size_t cap,

@@ -37,6 +37,16 @@ int main() {
       for (unsigned i = 0; i < 1024; i++) printf(" %u", (unsigned)c.mv_component_costs.at(comp).at(sign).at(i));
   printf("\nmvsad");
   for (unsigned i = 0; i < 256; i++) printf(" %u", (unsigned)c.mv_sad_costs.at(0).at(0).at(i));
+  /* two-pass encoding (trellis quantisation, encoder.cc:220-408): token costs of the default probability tables
+   * (Costs::fill_token_costs, costs.cc:168-186) and the extra-bit + sign cost of every coefficient value */
+  c.fill_token_costs(ProbabilityTables());
+  printf("\ntokcost");
+  for (unsigned i = 0; i < BLOCK_TYPES; i++)
+    for (unsigned j = 0; j < COEF_BANDS; j++)
+      for (unsigned k = 0; k < PREV_COEF_CONTEXTS; k++)
+        for (unsigned t = 0; t < MAX_ENTROPY_TOKENS; t++) printf(" %u", (unsigned)c.token_costs.at(i).at(j).at(k).at(t));
+  printf("\nvalcost");
+  for (int v = -2048; v < 2048; v++) printf(" %u", (unsigned)Costs::coeff_base_cost((int16_t)v));
   printf("\n");
   return 0;
 }

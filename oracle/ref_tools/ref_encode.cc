@@ -6,6 +6,7 @@
  * usage: ref_encode OUT.ivf WIDTH HEIGHT FRAMES GOP QINDEX [SEED] [KIND]
  *   environment: REF_RAW=file.yuv  read planar YUV420 frames (display size) instead of synthesising;
  *                REF_TARGET=bytes  use Encoder::encode_with_target_size instead of a fixed quantiser;
+ *                REF_TWO_PASS=1    Encoder( ..., two_pass = true, ... ): key frames get the trellis pass (encoder.cc:220-408);
  *   prints one JSON line with encode seconds (source generation excluded), bytes and luma PSNR of
  *   the encoder's own reconstruction (Encoder::export_decoder, encoder.hh:378).
  *   KIND 0: smooth moving sinusoid + noise ("easy");  1: translating random-texture tiles ("hard");
@@ -98,7 +99,7 @@ int main(int argc, char** argv) {
     FILE* raw = raw_path ? fopen(raw_path, "rb") : nullptr;
     double enc_seconds = 0, sse = 0;
     for (int t = 0; t < frames; t++) {
-      if (t % gop == 0) { enc.clear(); enc.initialize(w, h, false, REALTIME_QUALITY); }
+      if (t % gop == 0) { enc.clear(); enc.initialize(w, h, getenv("REF_TWO_PASS") != nullptr, REALTIME_QUALITY); }
       MutableRasterHandle raster(w, h);
       if (raw) {
         VP8Raster& r = raster.get();

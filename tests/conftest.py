@@ -24,12 +24,12 @@ def golden_dir():
 
 
 def pytest_collection_modifyitems(config, items):
-    """The re-encoding path was written after this round's GPU minutes were spent: its kernels and host
+    """The re-encoding path and the two-pass (trellis) key frame were written after this round's GPU minutes were spent: its kernels and host
     code are checked bit-exactly under the SIMT emulator (tests/test_simt_emulation.py) but have not run on a B200 yet.
     Its -m gpu tests therefore run LAST, so that under `pytest -x` a hardware-only failure there cannot keep the suites
     that have a hardware record (parity, encoder, C++ callers, flatten, state format) from running."""
     def is_late(it):  # (the Encoder-from-any-Decoder-state test came with the same change)
-        return "reencode" in it.nodeid or "built_from_a_decoder_in_any_state" in it.nodeid
+        return "reencode" in it.nodeid or "built_from_a_decoder_in_any_state" in it.nodeid or "two_pass" in it.nodeid
     late = [it for it in items if is_late(it)]
     if late:
         items[:] = [it for it in items if not is_late(it)] + late

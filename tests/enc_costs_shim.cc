@@ -7,4 +7,6 @@ extern "C" {
 int ec_size() { return (int)sizeof(vp8::EncTables); }
 void ec_build(vp8::EncTables* t) { vp8::build_enc_tables(*t); }
 void ec_rd(int y_ac, unsigned* rm, unsigned* dm) { vp8::rd_multipliers(y_ac, rm, dm); }
+int ec_trellis_size() { return (int)sizeof(vp8::TrellisTables); }
+void ec_trellis(vp8::TrellisTables* t) { vp8::build_trellis_tables(*t); }
 }

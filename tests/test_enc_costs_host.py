@@ -76,3 +76,18 @@ def test_rd_multipliers(tables):
         want = int(q * q * 2.80)
         want_rm, want_dm = (want // 100, 1) if want > 1000 else (want, 100)
         assert (rm.value, dm.value) == (want_rm, want_dm), y_ac
+
+
+def test_trellis_tables_equal_the_reference(tables):
+    """two-pass key frames (encoder.cc:220-408): token costs of the default probabilities (Costs::fill_token_costs) and
+    Costs::coeff_base_cost of every coefficient value"""
+    L, _ = tables
+
+    class TrellisTables(C.Structure):
+        _fields_ = [("token_cost", C.c_uint16 * (4 * 8 * 3 * 12)), ("value_cost", C.c_uint16 * 4096)]
+    assert L.ec_trellis_size() == C.sizeof(TrellisTables)
+    t = TrellisTables()
+    L.ec_trellis(C.byref(t))
+    ref = {line.split()[0]: np.array(line.split()[1:], dtype=np.int64) for line in reference_dump().splitlines()}
+    assert np.array_equal(np.array(t.token_cost[:]), ref["tokcost"])
+    assert np.array_equal(np.array(t.value_cost[:]), ref["valcost"])

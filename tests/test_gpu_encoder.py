@@ -417,3 +417,38 @@ def test_encoder_built_from_a_decoder_in_any_state_stays_in_step(name):
         rx.get_frame_output(frame)
         assert rx == enc.export_decoder(), "frame %d" % t
     ctx.close()
+
+
+def _noisy(w, h, t, amp):
+    y, u, v = synth(w, h, t)
+    rng = np.random.default_rng(100 + t)
+    return tuple(np.clip(p.astype(np.int32) + rng.integers(-amp, amp + 1, p.shape), 0, 255).astype(np.uint8) for p in (y, u, v))
+
+
+@needs_ref
+@pytest.mark.parametrize("w,h,qi,amp,n", [(64, 64, 40, 20, 2), (176, 144, 70, 40, 2), (175, 143, 60, 35, 3), (320, 240, 110, 60, 2),
+                                        (640, 368, 40, 30, 2)])
+def test_two_pass_key_frames_equal_the_reference_encoder(w, h, qi, amp, n):
+    """Encoder( ..., two_pass = true, ... ): the key frame's second pass with trellis quantisation (k_enc_rd<true>:
+    Encoder::trellis_quantize, check_reset_y2, encoder.cc:198-408; token contexts from requantised neighbours; the block
+    types and Y2 flags the first pass left behind, encode_intra.cc:58-66, 181-184) -- frames byte-identical to the
+    unmodified reference's (REF_TWO_PASS), noisy sources so that the trellis has something to decide"""
+    from alfalfa_b200 import Context, Decoder, Encoder
+    frames = [_noisy(w, h, t, amp) for t in range(n)]
+    os.environ["REF_TWO_PASS"] = "1"
+    try:
+        want = reference_encode(frames, w, h, qi=qi)
+    finally:
+        del os.environ["REF_TWO_PASS"]
+    one_pass = reference_encode(frames[:1], w, h, qi=qi)
+    ctx = Context(w, h, max_frames=16)
+    enc = Encoder(ctx)
+    enc.set_two_pass(True)
+    got = [enc.encode_with_quantizer(*f, qi) for f in frames]
+    assert got == want
+    assert got[0] != one_pass[0], "the second pass changed nothing: the case does not exercise the trellis"
+    rx = Decoder(ctx)
+    for c in got:
+        rx.get_frame_output(c)
+    assert rx == enc.export_decoder()
+    ctx.close()
