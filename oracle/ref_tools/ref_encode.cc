@@ -6,6 +6,7 @@
  * usage: ref_encode OUT.ivf WIDTH HEIGHT FRAMES GOP QINDEX [SEED] [KIND]
  *   environment: REF_RAW=file.yuv  read planar YUV420 frames (display size) instead of synthesising;
  *                REF_TARGET=bytes  use Encoder::encode_with_target_size instead of a fixed quantiser;
+ *                REF_MIN_SSIM=x    use Encoder::encode_with_minimum_ssim;
  *                REF_TWO_PASS=1    Encoder( ..., two_pass = true, ... ): key frames get the trellis pass (encoder.cc:220-408);
  *   prints one JSON line with encode seconds (source generation excluded), bytes and luma PSNR of
  *   the encoder's own reconstruction (Encoder::export_decoder, encoder.hh:378).
@@ -132,8 +133,10 @@ int main(int argc, char** argv) {
         }
       }
       const auto t0 = chrono::steady_clock::now();
-      const vector<uint8_t> f = target_env ? enc.get().encode_with_target_size(raster.get(), atoi(target_env))
-                                           : enc.get().encode_with_quantizer(raster.get(), qi);
+      const char* ssim_env = getenv("REF_MIN_SSIM");
+      const vector<uint8_t> f = ssim_env ? enc.get().encode_with_minimum_ssim(raster.get(), atof(ssim_env))
+                                : target_env ? enc.get().encode_with_target_size(raster.get(), atoi(target_env))
+                                             : enc.get().encode_with_quantizer(raster.get(), qi);
       enc_seconds += chrono::duration<double>(chrono::steady_clock::now() - t0).count();
       out.append_frame(Chunk(&f.at(0), f.size()));
       total += f.size();
