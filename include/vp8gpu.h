@@ -434,7 +434,7 @@ int vp8gpu_encoder_encode_with_target_size(vp8gpu_encoder* enc, const uint8_t* y
 /* Encoder::encode_with_minimum_ssim (encoder.cc:510-557, 577-590) as it is meant: the coarsest quantiser index whose
  * reconstruction still reaches `minimum_ssim` (luma SSIM against the source after the loop filter).  NOT byte-compatible
  * with the reference here, on purpose: its search calls encode_raster( raster, quant_indices, true ) -- the `true` lands on
- * update_state, compute_ssim stays false (encoder.hh:257-258) -- so every candidate reports SSIM 0, the bisection walks
+ * update_state, compute_ssim stays false (encoder.hh:336-337) -- so every candidate reports SSIM 0, the bisection walks
  * down to index 0 and the frame is coded at the finest quantiser whatever was asked for (oracle/_ref/ref_encode with
  * REF_MIN_SSIM shows it). */
 int vp8gpu_encoder_encode_with_minimum_ssim(vp8gpu_encoder* enc, const uint8_t* y, size_t y_stride, const uint8_t* u,
