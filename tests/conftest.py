@@ -25,7 +25,8 @@ def golden_dir():
 
 def pytest_collection_modifyitems(config, items):
     """The re-encoding path and the two-pass (trellis) key frame were written after this round's GPU minutes were spent: its kernels and host
-    code are checked bit-exactly under the SIMT emulator (tests/test_simt_emulation.py) but have not run on a B200 yet.
+    code are checked bit-exactly under the SIMT emulator (tests/test_simt_emulation.py) and have had one short run on a B200
+    (profiles/r2z_new_kernels_b200.json), not the whole test files.
     Its -m gpu tests therefore run LAST, so that under `pytest -x` a hardware-only failure there cannot keep the suites
     that have a hardware record (parity, encoder, C++ callers, flatten, state format) from running."""
     def is_late(it):  # (the Encoder-from-any-Decoder-state test came with the same change)
