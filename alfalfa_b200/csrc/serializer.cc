@@ -192,18 +192,38 @@ inline uint8_t implied_bmode(int y_mode) {
 // One arithmetic-coded decision of the token partition, recorded first so that branch statistics can
 // choose the frame's probabilities before anything is written: (slot << 1) | bit, where slot < 1056
 // indexes the coefficient probability table and 1056 + p stands for the fixed probability p.
+// The statistics (how often each decision came out 0 / 1) are kept while recording: cnt[(slot << 1) | bit].
 struct TokenRecorder {
   std::vector<uint16_t> bits;
-  void coef(int slot, int bit) { bits.push_back(static_cast<uint16_t>((slot << 1) | bit)); }
-  void fixed(int prob, int bit) { bits.push_back(static_cast<uint16_t>(((1056 + prob) << 1) | bit)); }
+  uint32_t* cnt = nullptr;
+  void coef(int slot, int bit) {
+    const uint16_t d = static_cast<uint16_t>((slot << 1) | bit);
+    bits.push_back(d);
+    cnt[d]++;
+  }
+  void fixed(int prob, int bit) {
+    const uint16_t d = static_cast<uint16_t>(((1056 + prob) << 1) | bit);
+    bits.push_back(d);
+    cnt[d]++;
+  }
+};
+// When the frame's probabilities are known before its tokens are walked (a parsed frame written back, a size
+// estimate, a frame without probability optimisation) the decisions go straight into the arithmetic coder.
+struct DirectWriter {
+  BoolWriter& bw;
+  const uint8_t* probs;  // the frame's 1056 coefficient probabilities
+  void coef(int slot, int bit) { bw.put(bit, probs[slot]); }
+  void fixed(int prob, int bit) { bw.put(bit, prob); }
 };
 
-void put_extra(TokenRecorder& t, int v, const uint8_t* probs, int n) {
+template <class Sink>
+inline void put_extra(Sink& t, int v, const uint8_t* probs, int n) {
   for (int i = n - 1; i >= 0; i--) t.fixed(probs[n - 1 - i], (v >> i) & 1);
 }
 
 // inverse of Block::parse_tokens (tokens.cc:50-135); returns has_nonzero
-int record_block(TokenRecorder& t, const int16_t* coefs /* raster order */, int type, int ctx, int first) {
+template <class Sink>
+inline int record_block(Sink& t, const int16_t* coefs /* raster order */, int type, int ctx, int first) {
   static const uint8_t cat2[2] = {165, 145}, cat3[3] = {173, 148, 140}, cat4[4] = {176, 155, 140, 135},
                        cat5[5] = {180, 157, 141, 134, 130},
                        cat6[11] = {254, 254, 243, 230, 196, 177, 153, 140, 133, 130, 129};
@@ -339,6 +359,15 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
     }
   }
 
+  // ---- the frame's coefficient probabilities before any update of this frame ----
+  uint8_t coef_probs[1056];
+  if (x.saved_coef_probs && h.key_frame) memcpy(x.saved_coef_probs, k_coef_default_probs, 1056);
+  memcpy(coef_probs, x.saved_coef_probs ? x.saved_coef_probs : k_coef_default_probs, sizeof(coef_probs));
+  if (vb) memcpy(coef_probs, vb->coef, sizeof(coef_probs));
+  // they are final already when nothing will be derived from this frame's own statistics: a parsed frame written
+  // back, a size estimate, a frame without probability optimisation -- then the tokens are coded in one walk
+  const bool direct = vb || (x.ref_writer ? x.ref_estimate : !h.optimize_token_probs);
+
   // ---- pass 1: the decisions of the token partitions.  Row r belongs to partition r % n
   //      (frame.cc:131-136) and, given the above contexts, rows are independent: one recorder (and, with
   //      more than one partition, one thread) per partition ----
@@ -351,9 +380,9 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
   std::vector<PartWork> work(nparts);
   auto record_partition = [&](int p) {
     PartWork& W = work[p];
-    W.rec.bits.reserve(n_mbs * 160 / nparts + 1024);
     W.cnt.assign(2 * (1056 + 256), 0);
     W.ref_skip_eob.assign(1056, 0);
+    auto walk = [&](auto& sink) {
     int16_t c[25][16];  // coefficients of the current macroblock, raster order; all zero between macroblocks
     memset(c, 0, sizeof(c));
     for (int row = p; row < rows; row += nparts) {
@@ -390,8 +419,8 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
         auto block = [&](int blk, int type, int bx, int by, int first) {
           const int ctx = ((a >> bx) & 1) + ((left >> by) & 1);
           unsigned nz = 0;
-          if (m >> blk & 1) nz = static_cast<unsigned>(record_block(W.rec, c[blk], type, ctx, first));
-          else W.rec.coef(((type * 8 + kBand[first]) * 3 + ctx) * 11, 0);  // immediate end of block
+          if (m >> blk & 1) nz = static_cast<unsigned>(record_block(sink, c[blk], type, ctx, first));
+          else sink.coef(((type * 8 + kBand[first]) * 3 + ctx) * 11, 0);  // immediate end of block
           a = (a & ~(1u << bx)) | (nz << bx);
           left = (left & ~(1u << by)) | (nz << by);
         };
@@ -406,7 +435,18 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
         }
       }
     }
-    for (const uint16_t bit : W.rec.bits) W.cnt[bit]++;
+    };
+    if (direct) {
+      BoolWriter tw;
+      tw.reserve(n_mbs * 24 / nparts + 1024);
+      DirectWriter dw{tw, coef_probs};
+      walk(dw);
+      W.bytes = tw.finish();
+    } else {
+      W.rec.bits.reserve(n_mbs * 160 / nparts + 1024);
+      W.rec.cnt = W.cnt.data();
+      walk(W.rec);
+    }
   };
   const bool threaded = nparts > 1 && n_mbs >= 1024;
   {
@@ -418,10 +458,6 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
   }
 
   // ---- frame probabilities ----
-  uint8_t coef_probs[1056];
-  if (x.saved_coef_probs && h.key_frame) memcpy(x.saved_coef_probs, k_coef_default_probs, 1056);
-  memcpy(coef_probs, x.saved_coef_probs ? x.saved_coef_probs : k_coef_default_probs, sizeof(coef_probs));
-  if (vb) memcpy(coef_probs, vb->coef, sizeof(coef_probs));
   std::vector<uint8_t> updated(1056, 0);
   auto calc_prob = [](uint64_t falses, uint64_t total) -> int {  // Encoder::calc_prob (encoder.cc:48-55)
     if (falses == 0) return 0;
@@ -530,7 +566,7 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
     }
     ~Joiner() { join(); }
   } writers;
-  for (int p = 0; p < nparts; p++) {
+  for (int p = 0; p < nparts && !direct; p++) {
     if (threaded) writers.th.emplace_back(write_partition, p);
     else write_partition(p);
   }
