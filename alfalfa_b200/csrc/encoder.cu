@@ -1,12 +1,21 @@
 // encoder.cu -- host side of the encoder path: Encoder (encoder/encoder.hh:345-382) on the device.
 //
-// First slice of SURVEY.md 8a row a16: encode_with_quantizer / encode_with_target_size for a
-// key frame followed by inter frames predicted from LAST, 16x16 intra modes, SAD-driven decisions
-// (the reference's RD search, B_PRED / SPLITMV, trellis and SSIM-driven loop-filter search are not
-// reproduced yet).  What is exact: transform / quantiser arithmetic (dct.cc, quantization.cc) and
-// the closed loop -- the emitted frame decodes (reference decoder, oracle, this library) to exactly
-// the reconstruction the encoder keeps as its LAST reference, which is what Encoder::export_decoder
-// (encoder.hh:378) promises.
+// SURVEY.md 8a row a16 + 8 f3: encode_with_quantizer / encode_with_target_size / encode_with_minimum_ssim /
+// estimate_frame_size, the two-pass key frame, and re-encoding (update_residues, reencode_as_interframe,
+// write_frame).  The per-macroblock decisions are the reference's (k_enc_rd in kernels.cu: rdcost, B_PRED trial,
+// motion-vector census + diamond search, chroma by distortion, trellis in the second pass); this file is the
+// frame-level policy around them, statement for statement the reference's: the bisection over y_ac_qi on sampled
+// size estimates (encoder.cc:592-629, size_estimation.cc), the SSIM-driven loop-filter search (encoder.cc:460-508),
+// the writer's header rules (serializer.h RefWriterState) -- the emitted frames are byte-identical to the reference
+// encoder's (tests/test_gpu_encoder.py) -- and the closed loop: the emitted frame decodes (reference decoder,
+// oracle, this library) to exactly the reconstruction the encoder keeps as its LAST reference, which is what
+// Encoder::export_decoder (encoder.hh:378) promises.
+//
+// What differs from the reference is only the ORDER IN TIME of independent work: the candidates of the two
+// searches do not depend on each other (a size estimate is a function of the source, the references and y_ac_qi;
+// a loop-filter trial of the reconstruction and the level), and a wavefront kernel lasts as long for one frame as
+// for thirty, so the candidates a search can still visit are coded in ONE launch
+// (estimate_batch_launch, filter_batch) and the search then walks over finished results in the reference's order.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -69,11 +78,25 @@ struct vp8gpu_encoder {
   // (serializer.h RefWriterState) -- byte-identical output; 1: compact -- only token-probability updates that
   // pay, no zero loop-filter deltas, eight DCT partitions written on eight host threads.
   int writer = 0;
+  // speculative size estimates (estimate_batch_launch): EncJob[kEstMax] | ticket, token counters, row progress |
+  // records, token pools and reconstruction rasters of every candidate -- private to this Encoder, allocated on
+  // the first target-size search
+  uint8_t* d_est = nullptr;
+  uint8_t* h_est = nullptr;      // pinned: EncJob[kEstMax] | token counts
+  size_t est_off_sync = 0, est_off_mbs = 0, est_off_tokens = 0, est_off_out = 0, est_out_stride = 0;
+  uint32_t est_tok_cap = 0;      // tokens per candidate
+  int est_n = 0;                 // candidates of the batch whose results are on the device now (0: none)
+  int est_qi[33];
+  uint32_t est_rate[33], est_dist[33];
   // header state of the reference's four frame objects: key_frame_, inter_frame_, subsampled_*_ (encoder.hh:128-142)
   vp8::EncodeFeatures::RefWriterState ref_key, ref_inter, ref_sub_key, ref_sub_inter;
 };
 
 namespace {
+constexpr int kEstMax = 33;   // size estimates per launch: a whole search range of last_y_ac_qi +- 16 (encoder.cc:604-611)
+constexpr int kLfMax = 4;     // loop-filter trials per launch (the steady-state range is the last level +- 1, encoder.cc:466-471)
+constexpr size_t kHdrBytes = 512 + 512 * kLfMax;  // pinned / device header area: EncJob | DevJob[kLfMax]
+static_assert(sizeof(vp8::EncJob) <= 512 && sizeof(vp8::DevJob) <= 512, "header area slots");
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 int clamp_q(int q) { return q < 0 ? 0 : (q > 127 ? 127 : q); }
 vp8gpu_quant make_quant(int qi) {  // Quantizer::Quantizer, quantization.cc:83-93 (all deltas zero)
@@ -186,7 +209,7 @@ int encode_launch(vp8gpu_encoder* enc, bool key, int qi, int sub, const vp8gpu_q
   CUF(cudaMemcpyAsync(enc->dev + enc->off_encjob, enc->h_hdr, 512, cudaMemcpyHostToDevice, s));
   CUF(cudaMemsetAsync(d_sync, 0, sizeof(int) * (128 + 2 * (size_t)g.mb_rows), s));
   const vp8::EncJob* d_ej = reinterpret_cast<const vp8::EncJob*>(enc->dev + enc->off_encjob);
-  if (int ce = trellis ? vp8::launch_enc_rd_trellis(d_ej, rows, g, d_sync + 0, s) : vp8::launch_enc_rd(d_ej, rows, g, d_sync + 0, s))
+  if (int ce = trellis ? vp8::launch_enc_rd_trellis(d_ej, rows, g, d_sync + 0, s) : vp8::launch_enc_rd(d_ej, 1, rows, g, d_sync + 0, s))
     return fail(e->cuda_fail((cudaError_t)ce, "k_enc_rd"));
   e->count_launches(1);
   e->mark_frames(enc->lane, ids, key ? 2 : 3, 2u);
@@ -314,41 +337,120 @@ int filter_frame(vp8gpu_encoder* enc, int frame, bool key, int level) {
   return VP8GPU_OK;
 }
 
+// n loop-filter passes in ONE launch: frames[i] filtered in place with every macroblock at levels[i] (> 0).  The
+// trials of the loop-filter search are independent of each other and k_loopfilter takes a job array (ticket t ->
+// row t / n of job t % n), so n trials last about as long as one.
+int filter_batch(vp8gpu_encoder* enc, const int* frames, const int* levels, int n, bool key) {
+  Engine* e = enc->e;
+  const vp8::Geom& g = e->geom();
+  cudaStream_t s = e->stream(enc->lane);
+  if (n <= 0) return VP8GPU_OK;
+  if (n > kLfMax) return e->fail(VP8GPU_ERR_LOGIC, "filter_batch: too many trials");
+  vp8::DevJob* dj = reinterpret_cast<vp8::DevJob*>(enc->h_hdr + 512);
+  memset(dj, 0, sizeof(vp8::DevJob) * n);
+  int* d_sync = reinterpret_cast<int*>(enc->dev + enc->off_sync);
+  for (int i = 0; i < n; i++) {
+    dj[i].mbs = reinterpret_cast<const vp8gpu_mb*>(enc->dev + enc->off_mbs);
+    dj[i].tokens = reinterpret_cast<const vp8gpu_token*>(enc->dev + enc->off_tokens);
+    dj[i].out = e->frame_dev(frames[i]);
+    dj[i].lf_progress = d_sync + 128 + (size_t)(1 + i) * g.mb_rows;
+    dj[i].intra_progress = d_sync + 128;
+    dj[i].key_frame = key;
+    dj[i].sharpness = (uint8_t)enc->lf_sharpness;
+    dj[i].lf_enabled = 1;
+    dj[i].lf_force = (uint8_t)levels[i];
+  }
+  int rc = e->acquire_frames(enc->lane, frames, n);
+  if (rc != VP8GPU_OK) return rc;
+  CUE(cudaMemcpyAsync(enc->dev + enc->off_encjob + 512, dj, sizeof(vp8::DevJob) * n, cudaMemcpyHostToDevice, s));
+  CUE(cudaMemsetAsync(d_sync + 32, 0, sizeof(int), s));                                         // ticket
+  CUE(cudaMemsetAsync(d_sync + 128 + g.mb_rows, 0, sizeof(int) * (size_t)n * g.mb_rows, s));    // row progress
+  const vp8::DevJob* d_dj = reinterpret_cast<const vp8::DevJob*>(enc->dev + enc->off_encjob + 512);
+  if (int ce = vp8::launch_loopfilter(d_dj, n, g, d_sync + 32, e->next_epoch(2), s)) return e->cuda_fail((cudaError_t)ce, "k_loopfilter");
+  e->count_launches(1);
+  e->mark_frames(enc->lane, frames, n);
+  // the pinned descriptors are rewritten by the next call: wait until they have been read
+  CUE(cudaStreamSynchronize(s));
+  return VP8GPU_OK;
+}
+
+// VP8GPU_ENC_SPECULATE=0: the searches of the encoder run candidate by candidate (one launch each), as in round 1;
+// the results are the same either way (tests/test_gpu_encoder.py runs both)
+bool enc_speculate() {
+  static const bool on = [] {
+    const char* v = getenv("VP8GPU_ENC_SPECULATE");
+    return !(v && v[0] == '0');
+  }();
+  return on;
+}
+
 // Encoder::apply_best_loopfilter_settings (encoder.cc:460-508): try loop-filter levels in ascending
 // order -- all of 0..63 for the first frame, the previous level +-1 afterwards -- on a copy of the
 // reconstruction, keep going while the luma SSIM against the source improves, then filter the
-// reconstruction itself at the best level.
-int choose_loop_filter(vp8gpu_encoder* enc, int recon, bool key, int* level_out, double* ssim_out) {
+// reconstruction itself at the best level.  *recon may be replaced by another raster holding that result.
+//
+// The trials are independent, so up to kLfMax of them run in one k_loopfilter launch on copies; the walk over
+// their SSIMs is the reference's (ascending, stop at the first level that does not improve), and the copy
+// that was filtered at the best level IS the filtered reconstruction: it takes the place of *recon instead of a
+// further pass.  Steady state: one launch instead of three or four dependent ones.
+int choose_loop_filter(vp8gpu_encoder* enc, int* recon, bool key, int* level_out, double* ssim_out) {
   Engine* e = enc->e;
   int lo = 0, hi = 63;
   if (enc->last_lf >= 0) {
     lo = enc->last_lf > 0 ? enc->last_lf - 1 : 0;
     hi = enc->last_lf + 1 > 63 ? 63 : enc->last_lf + 1;
   }
-  int temp = -1;
-  int rc = e->frame_alloc(&temp);
-  if (rc != VP8GPU_OK) return rc;
-  int best = 0;
+  int temps[kLfMax], n_temps = 0;
+  const int want = enc_speculate() ? (hi - lo + 1 < kLfMax ? hi - lo + 1 : kLfMax) : 1;
+  for (; n_temps < want; n_temps++)
+    if (e->frame_alloc(&temps[n_temps]) != VP8GPU_OK) break;  // a small pool: fewer trials per launch
+  if (n_temps == 0) return e->fail(VP8GPU_ERR_NOMEM, "loop-filter search: no raster for a trial");
+  int best = 0, keep = -1;  // keep: the trial raster that holds the reconstruction filtered at `best`
   double best_ssim = -1.0;
-  for (int level = lo; level <= hi; level++) {
-    rc = e->frame_copy(temp, recon, enc->lane);
-    if (rc == VP8GPU_OK) rc = filter_frame(enc, temp, key, level);
-    double q = 0;
-    if (rc == VP8GPU_OK) rc = e->frames_ssim(temp, enc->src, enc->lane, &q);
-    if (rc != VP8GPU_OK) break;
-    if (q > best_ssim) {
-      best_ssim = q;
-      best = level;
-    } else {
-      break;
+  int rc = VP8GPU_OK;
+  bool stop = false, found = false;
+  for (int level = lo; level <= hi && !stop && rc == VP8GPU_OK;) {
+    int use[kLfMax], lv[kLfMax], n = 0, nf = 0, fr[kLfMax], fl[kLfMax];
+    for (int i = 0; i < n_temps && level + n <= hi; i++) {
+      if (temps[i] == keep && n_temps > 1) continue;  // holds the best result so far (a single trial raster is reused)
+      use[n] = temps[i];
+      lv[n] = level + n;
+      n++;
     }
+    if (n_temps == 1) keep = -1;
+    for (int i = 0; i < n && rc == VP8GPU_OK; i++) {
+      rc = e->frame_copy(use[i], *recon, enc->lane);
+      if (lv[i] > 0) fr[nf] = use[i], fl[nf] = lv[i], nf++;  // a frame-level 0 disables the filter (frame.cc:144)
+    }
+    if (rc == VP8GPU_OK) rc = filter_batch(enc, fr, fl, nf, key);
+    for (int i = 0; i < n && rc == VP8GPU_OK; i++) {
+      double q = 0;
+      rc = e->frames_ssim(use[i], enc->src, enc->lane, &q);
+      if (rc != VP8GPU_OK) break;
+      if (q > best_ssim) {
+        best_ssim = q;
+        best = lv[i];
+        keep = use[i];
+        found = true;
+      } else {
+        stop = true;
+        break;
+      }
+    }
+    level += n;
   }
-  e->frame_release(temp);
+  // a single trial raster is overwritten by the trial that ends the search: filter the reconstruction itself then
+  if (rc == VP8GPU_OK && keep < 0 && found) rc = filter_frame(enc, *recon, key, best);
+  for (int i = 0; i < n_temps; i++)
+    if (temps[i] != keep || rc != VP8GPU_OK) e->frame_release(temps[i]);
   if (rc != VP8GPU_OK) return rc;
-  rc = filter_frame(enc, recon, key, best);
+  if (keep >= 0) {
+    e->frame_release(*recon);
+    *recon = keep;
+  }
   *level_out = best;
   *ssim_out = best_ssim;
-  return rc;
+  return VP8GPU_OK;
 }
 
 // source planes (display size) -> MB-aligned raster on the device, edges replicated like the
@@ -393,9 +495,9 @@ static int encoder_alloc(vp8gpu_ctx* ctx, vp8gpu_encoder** out) {
   enc->tok_cap = (uint32_t)(n_mbs * 400);
   size_t off = 0;
   enc->off_encjob = off;
-  off = align_up(off + 1024, 256);
+  off = align_up(off + kHdrBytes, 256);
   enc->off_sync = off;
-  off = align_up(off + sizeof(int) * (128 + 2 * (size_t)g.mb_rows), 256);
+  off = align_up(off + sizeof(int) * (128 + (1 + (size_t)kLfMax) * g.mb_rows), 256);
   enc->off_mbs = off;
   off = align_up(off + n_mbs * sizeof(vp8gpu_mb), 256);
   enc->off_tab = off;
@@ -404,7 +506,7 @@ static int encoder_alloc(vp8gpu_ctx* ctx, vp8gpu_encoder** out) {
   off = align_up(off + (size_t)enc->tok_cap * sizeof(vp8gpu_token), 256);
   enc->dev_bytes = off;
   cudaSetDevice(e->device());
-  if (cudaMalloc(&enc->dev, enc->dev_bytes) != cudaSuccess || cudaHostAlloc(&enc->h_hdr, 1024, cudaHostAllocDefault) != cudaSuccess ||
+  if (cudaMalloc(&enc->dev, enc->dev_bytes) != cudaSuccess || cudaHostAlloc(&enc->h_hdr, kHdrBytes, cudaHostAllocDefault) != cudaSuccess ||
       cudaHostAlloc(&enc->h_mbs, n_mbs * sizeof(vp8gpu_mb), cudaHostAllocDefault) != cudaSuccess ||
       cudaHostAlloc(&enc->h_tokens, (size_t)enc->tok_cap * sizeof(vp8gpu_token), cudaHostAllocDefault) != cudaSuccess ||
       cudaHostAlloc(&enc->h_src, (size_t)g.W * g.H * 3 / 2, cudaHostAllocDefault) != cudaSuccess ||
@@ -502,6 +604,8 @@ void vp8gpu_encoder_destroy(vp8gpu_encoder* enc) {
   if (enc->dev) cudaFree(enc->dev);
   if (enc->d_split) cudaFree(enc->d_split);
   if (enc->d_trellis) cudaFree(enc->d_trellis);
+  if (enc->d_est) cudaFree(enc->d_est);
+  if (enc->h_est) cudaFreeHost(enc->h_est);
   if (enc->h_hdr) cudaFreeHost(enc->h_hdr);
   if (enc->h_mbs) cudaFreeHost(enc->h_mbs);
   if (enc->h_tokens) cudaFreeHost(enc->h_tokens);
@@ -612,7 +716,7 @@ static int encode_final(vp8gpu_encoder* enc, bool key, int qi, uint8_t* out, siz
   double ssim = -1.0;
   int rc = encode_passes(enc, key, qi, &frame);
   if (rc != VP8GPU_OK) return rc;
-  rc = choose_loop_filter(enc, frame, key, &lf, &ssim);
+  rc = choose_loop_filter(enc, &frame, key, &lf, &ssim);
   std::vector<uint8_t> bytes;
   uint8_t probs[1056];
   memcpy(probs, enc->dec_state->coef_probs, 1056);
@@ -626,13 +730,10 @@ static int encode_final(vp8gpu_encoder* enc, bool key, int qi, uint8_t* out, siz
 
 // Encoder::estimate_frame_size (size_estimation.cc:36-181): code the 1/16 sample at y_ac_qi, serialize it
 // with the current probability tables, multiply by 16
-static int estimate_size(vp8gpu_encoder* enc, bool key, int qi, size_t* size) {
-  int frame = -1;
-  int rc = encode_core(enc, key, qi, 4, &frame);
-  if (rc != VP8GPU_OK) return rc;
-  enc->e->frame_release(frame);
+// second half of an estimate: the sampled frame whose records and tokens are in h_mbs / h_tokens, serialised
+static int estimate_bytes(vp8gpu_encoder* enc, bool key, int qi, size_t* size) {
   std::vector<uint8_t> bytes;
-  rc = encode_bytes(enc, key, qi, 0, 4, false, enc->dec_state->coef_probs, bytes);
+  const int rc = encode_bytes(enc, key, qi, 0, 4, false, enc->dec_state->coef_probs, bytes);
   if (rc == VP8GPU_OK) *size = bytes.size() * 16;
   if (rc == VP8GPU_OK) {
     if (const char* path = getenv("VP8GPU_EST_DUMP")) {  // diagnostic (tools/enc_estimates.py): the sampled frame itself
@@ -643,6 +744,150 @@ static int estimate_size(vp8gpu_encoder* enc, bool key, int qi, size_t* size) {
     }
   }
   return rc;
+}
+static int estimate_size(vp8gpu_encoder* enc, bool key, int qi, size_t* size) {
+  int frame = -1;
+  int rc = encode_core(enc, key, qi, 4, &frame);
+  if (rc != VP8GPU_OK) return rc;
+  enc->e->frame_release(frame);
+  return estimate_bytes(enc, key, qi, size);
+}
+
+// ---- speculative size estimates -----------------------------------------------------------------------------
+// Encoder::encode_with_target_size bisects over y_ac_qi, and every probe is a sampled pass (estimate_size) that
+// depends on the source, the references and its quantiser only -- not on the probes before it.  A sampled pass is a
+// wavefront of (cols + 2 rows) dependent macroblock steps however many SMs there are, so the probes the search can
+// still reach are coded in ONE k_enc_rd launch (n jobs: own records, token pool, counters, reconstruction raster);
+// the bisection then reads results.  Five or six dependent launch / wait / download rounds per frame become one.
+// What the reference carries from probe to probe -- the header state of its subsampled frame objects, the rd
+// multipliers of the last probe -- is carried the same way, because serialisation (estimate_batch_size) still
+// happens probe by probe in the order of the search.
+static int estimate_batch_launch(vp8gpu_encoder* enc, bool key, const int* qis, int n) {
+  Engine* e = enc->e;
+  const vp8::Geom& g = e->geom();
+  enc->est_n = 0;
+  int pw, ph, cols, rows;
+  pass_dims(enc, 4, &pw, &ph, &cols, &rows);
+  if (cols < 1 || rows < 1) return e->fail(VP8GPU_ERR_UNSUPPORTED, "frame too small for the sampled size estimate");
+  if (n < 1 || n > kEstMax) return e->fail(VP8GPU_ERR_LOGIC, "estimate_batch_launch: bad candidate count");
+  const size_t n_mbs = (size_t)cols * rows;
+  if (!enc->d_est) {
+    enc->est_tok_cap = (uint32_t)(n_mbs * 400);
+    size_t off = align_up(sizeof(vp8::EncJob) * kEstMax, 256);
+    enc->est_off_sync = off;
+    off = align_up(off + sizeof(int) * (128 + (size_t)kEstMax * rows), 256);
+    enc->est_off_mbs = off;
+    off = align_up(off + (size_t)kEstMax * n_mbs * sizeof(vp8gpu_mb), 256);
+    enc->est_off_tokens = off;
+    off = align_up(off + (size_t)kEstMax * enc->est_tok_cap * sizeof(vp8gpu_token), 256);
+    enc->est_off_out = off;
+    enc->est_out_stride = align_up(g.frame_bytes, 256);
+    off += (size_t)kEstMax * enc->est_out_stride;
+    if (cudaMalloc(&enc->d_est, off) != cudaSuccess ||
+        cudaHostAlloc(&enc->h_est, align_up(sizeof(vp8::EncJob) * kEstMax, 256) + sizeof(uint32_t) * 64, cudaHostAllocDefault) != cudaSuccess) {
+      if (enc->d_est) cudaFree(enc->d_est);
+      enc->d_est = nullptr;
+      return e->fail(VP8GPU_ERR_NOMEM, "size estimates: scratch allocation failed");
+    }
+  }
+  if (int rc = e->ensure_lane(enc->lane)) return rc;
+  cudaStream_t s = e->stream(enc->lane);
+  int ids[2] = {enc->src, enc->refs[0]};
+  int rc = e->acquire_frames(enc->lane, ids, key ? 1 : 2, 0u);  // both only read
+  if (rc != VP8GPU_OK) return rc;
+  vp8::EncJob* ej = reinterpret_cast<vp8::EncJob*>(enc->h_est);
+  memset(ej, 0, sizeof(vp8::EncJob) * n);
+  int* d_sync = reinterpret_cast<int*>(enc->d_est + enc->est_off_sync);
+  for (int i = 0; i < n; i++) {
+    vp8::EncJob& j = ej[i];
+    uint32_t rate = enc->rd_rate, dist = enc->rd_dist;
+    j.src = e->frame_dev(enc->src);
+    j.ref = key ? nullptr : e->frame_dev(enc->refs[0]);
+    j.out = enc->d_est + enc->est_off_out + (size_t)i * enc->est_out_stride;
+    j.mbs = reinterpret_cast<vp8gpu_mb*>(enc->d_est + enc->est_off_mbs) + (size_t)i * n_mbs;
+    j.tokens = reinterpret_cast<vp8gpu_token*>(enc->d_est + enc->est_off_tokens) + (size_t)i * enc->est_tok_cap;
+    j.tok_counter = reinterpret_cast<uint32_t*>(d_sync + 32 + i);
+    j.tok_cap = enc->est_tok_cap;
+    j.progress = d_sync + 128 + (size_t)i * rows;
+    j.tab = reinterpret_cast<const vp8::EncTables*>(enc->dev + enc->off_tab);
+    j.q = make_quant(qis[i]);
+    vp8::rd_multipliers(j.q.y_ac, &rate, &dist);  // update_rd_multipliers( quantizer ) of this probe
+    j.rate_mult = rate;
+    j.dist_mult = dist;
+    j.cols = (uint16_t)cols;
+    j.rows = (uint16_t)rows;
+    j.sub = 4;
+    j.key_frame = key;
+    j.lf_level = 1;
+    j.sad_per_bit = k_sad_per_bit16[clamp_q(qis[i])];
+    j.realtime = 1;
+    j.mv_costs_zero = !key && !enc->mv_costs_filled;
+    j.mv_sad_zero = !key && !enc->mv_sad_filled;
+    enc->est_qi[i] = qis[i];
+    enc->est_rate[i] = rate;
+    enc->est_dist[i] = dist;
+  }
+  uint32_t* h_counts = reinterpret_cast<uint32_t*>(enc->h_est + align_up(sizeof(vp8::EncJob) * kEstMax, 256));
+  CUE(cudaMemcpyAsync(enc->d_est, ej, sizeof(vp8::EncJob) * n, cudaMemcpyHostToDevice, s));
+  CUE(cudaMemsetAsync(d_sync, 0, sizeof(int) * (128 + (size_t)n * rows), s));
+  if (int ce = vp8::launch_enc_rd(reinterpret_cast<const vp8::EncJob*>(enc->d_est), n, rows, g, d_sync + 0, s))
+    return e->cuda_fail((cudaError_t)ce, "k_enc_rd (size estimates)");
+  e->count_launches(1);
+  e->mark_frames(enc->lane, ids, key ? 1 : 2, 0u);
+  CUE(cudaMemcpyAsync(h_counts, d_sync + 32, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s));
+  CUE(cudaStreamSynchronize(s));
+  enc->est_n = n;
+  return VP8GPU_OK;
+}
+
+// the estimate of candidate idx of the current batch: its records and tokens to the host, then what estimate_size does
+static int estimate_batch_size(vp8gpu_encoder* enc, bool key, int idx, size_t* size) {
+  Engine* e = enc->e;
+  cudaStream_t s = e->stream(enc->lane);
+  int pw, ph, cols, rows;
+  pass_dims(enc, 4, &pw, &ph, &cols, &rows);
+  const size_t n_mbs = (size_t)cols * rows;
+  const uint32_t n_tok = reinterpret_cast<const uint32_t*>(enc->h_est + align_up(sizeof(vp8::EncJob) * kEstMax, 256))[idx];
+  if (n_tok > enc->est_tok_cap) return e->fail(VP8GPU_ERR_NOMEM, "encoder token pool overflow");
+  CUE(cudaMemcpyAsync(enc->h_mbs, reinterpret_cast<const vp8gpu_mb*>(enc->d_est + enc->est_off_mbs) + (size_t)idx * n_mbs,
+                      n_mbs * sizeof(vp8gpu_mb), cudaMemcpyDeviceToHost, s));
+  if (n_tok)
+    CUE(cudaMemcpyAsync(enc->h_tokens, reinterpret_cast<const vp8gpu_token*>(enc->d_est + enc->est_off_tokens) + (size_t)idx * enc->est_tok_cap,
+                        (size_t)n_tok * sizeof(vp8gpu_token), cudaMemcpyDeviceToHost, s));
+  CUE(cudaStreamSynchronize(s));
+  enc->rd_rate = enc->est_rate[idx];  // what update_rd_multipliers of this probe leaves behind
+  enc->rd_dist = enc->est_dist[idx];
+  return estimate_bytes(enc, key, enc->est_qi[idx], size);
+}
+
+// the candidates to code when the search stands at [lo, hi] and needs a probe that is not on the device: the whole
+// range if it fits one launch, else the nodes of the next three levels of the bisection tree
+static void bisection_nodes(int lo, int hi, int depth, int* out, int* n) {
+  if (lo > hi || depth == 0) return;
+  const int mid = (lo + hi) / 2;
+  out[(*n)++] = mid;
+  bisection_nodes(lo, mid - 1, depth - 1, out, n);
+  bisection_nodes(mid + 1, hi, depth - 1, out, n);
+}
+static int estimate_probe(vp8gpu_encoder* enc, bool key, int lo, int hi, int qi, size_t* size) {
+  if (!enc_speculate()) return estimate_size(enc, key, qi, size);
+  int idx = -1;
+  for (int i = 0; i < enc->est_n; i++)
+    if (enc->est_qi[i] == qi) idx = i;
+  if (idx < 0) {
+    int qis[kEstMax], n = 0;
+    if (hi - lo + 1 <= kEstMax) {
+      for (int q = lo; q <= hi; q++) qis[n++] = q;
+    } else {
+      bisection_nodes(lo, hi, 3, qis, &n);
+    }
+    const int rc = estimate_batch_launch(enc, key, qis, n);
+    if (rc != VP8GPU_OK) return rc;
+    for (int i = 0; i < enc->est_n; i++)
+      if (enc->est_qi[i] == qi) idx = i;
+    if (idx < 0) return enc->e->fail(VP8GPU_ERR_LOGIC, "size estimates: probe missing from its batch");
+  }
+  return estimate_batch_size(enc, key, idx, size);
 }
 
 int vp8gpu_encoder_encode_with_quantizer(vp8gpu_encoder* enc, const uint8_t* y, size_t y_stride, const uint8_t* u,
@@ -665,6 +910,7 @@ int vp8gpu_encoder_encode_with_target_size(vp8gpu_encoder* enc, const uint8_t* y
   // Encoder::encode_with_target_size (encoder.cc:592-629), statement for statement: bisection over y_ac_qi in
   // [4, 127] or within 16 of the last frame's index; a candidate's size is the sampled estimate
   const bool key = !enc->has_state;
+  enc->est_n = 0;  // estimates of an earlier source are not this frame's
   int lo = 4, hi = 127;
   if (enc->last_qi >= 0) {
     if (enc->last_qi - 16 >= lo) lo = enc->last_qi - 16;
@@ -674,7 +920,7 @@ int vp8gpu_encoder_encode_with_target_size(vp8gpu_encoder* enc, const uint8_t* y
   while (lo <= hi) {
     const int qi = (lo + hi) / 2;
     size_t est = 0;
-    rc = estimate_size(enc, key, qi, &est);
+    rc = estimate_probe(enc, key, lo, hi, qi, &est);
     if (rc != VP8GPU_OK) return rc;
     if (est <= target_size || (lo == hi && best == 255)) {
       best = qi;
@@ -706,7 +952,7 @@ int vp8gpu_encoder_encode_with_minimum_ssim(vp8gpu_encoder* enc, const uint8_t* 
     double ssim = -1.0;
     rc = encode_core(enc, key, qi, 1, &frame);
     if (rc != VP8GPU_OK) return rc;
-    rc = choose_loop_filter(enc, frame, key, &lf, &ssim);
+    rc = choose_loop_filter(enc, &frame, key, &lf, &ssim);
     enc->e->frame_release(frame);
     if (rc != VP8GPU_OK) return rc;
     if (ssim >= minimum_ssim || (lo == hi && !found)) {
@@ -1062,7 +1308,7 @@ int vp8gpu_encoder_reencode_as_interframe(vp8gpu_encoder* enc, const uint8_t* y,
   rc = encode_core(enc, false, y_ac_qi, 1, &frame, &q);
   if (rc != VP8GPU_OK) return rc;
   enc->lf_sharpness = pf->desc.sharpness;
-  rc = choose_loop_filter(enc, frame, false, &lf, &ssim);  // apply_best_loopfilter_settings (reencode.cc:126)
+  rc = choose_loop_filter(enc, &frame, false, &lf, &ssim);  // apply_best_loopfilter_settings (reencode.cc:126)
   enc->lf_sharpness = 0;
   e->frame_release(frame);  // write_frame decodes the frame it wrote (encoder.cc:153-158)
   if (rc != VP8GPU_OK) return rc;

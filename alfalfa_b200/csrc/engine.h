@@ -132,6 +132,6 @@ int launch_loopfilter(const DevJob* jobs, int njobs, const Geom& g, int* ticket,
 int launch_tokens(const uint8_t* ring, size_t stride, int first, int count, int nslots, const Geom& g, void* stream);
 int launch_fetch_header(void* dst, const void* src_host_devptr, size_t bytes, void* stream);  // bytes % 16 == 0
 int launch_ssim(const uint8_t* a, const uint8_t* b, const Geom& g, float* d_windows, void* stream);
-int launch_enc_rd(const EncJob* job, int rows, const Geom& g, int* ticket, void* stream);
+int launch_enc_rd(const EncJob* jobs, int njobs, int rows, const Geom& g, int* ticket, void* stream);
 
 }  // namespace vp8

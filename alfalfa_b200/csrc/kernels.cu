@@ -1400,10 +1400,9 @@ __device__ __attribute__((noinline)) bool trellis_block(int16_t* c, int type, in
 }
 
 template <bool TRELLIS>
-__global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __restrict__ jobp, Geom g, int* ticket) {
+__global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __restrict__ jobp, int njobs, Geom g, int* ticket) {
   __shared__ EncSmem s_all[WF_WARPS];
   __shared__ uint16_t s_lut[128];
-  const EncJob& J = *jobp;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < 128; i += blockDim.x) s_lut[i] = k_bpred_lut[i];
   __syncthreads();
@@ -1415,7 +1414,11 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __res
   int t = 0;
   if (lane == 0) t = atomicAdd(ticket, 1);
   t = __shfl_sync(0xffffffffu, t, 0);
-  const int row = t;
+  // ticket t -> row t / njobs of job t % njobs: the jobs of one launch are passes of the same shape (the size
+  // estimates of a target-size search at different quantisers, encoder.cu estimate_batch), each with its own
+  // output raster, records, token pool and progress counters; the row a warp waits for was claimed earlier
+  const EncJob& J = jobp[t % njobs];
+  const int row = t / njobs;
   const int cols = J.cols, rows = J.rows, sub = J.sub;
   if (row >= rows) return;
   int* progress = J.progress + row;
@@ -2164,12 +2167,12 @@ int launch_loopfilter(const DevJob* jobs, int njobs, const Geom& g, int* ticket,
   return (int)cudaGetLastError();
 }
 
-int launch_enc_rd(const EncJob* job, int rows, const Geom& g, int* ticket, void* stream) {
-  VP8_LAUNCH(k_enc_rd<false>, (rows + WF_WARPS - 1) / WF_WARPS, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream))(job, g, ticket);
+int launch_enc_rd(const EncJob* jobs, int njobs, int rows, const Geom& g, int* ticket, void* stream) {
+  VP8_LAUNCH(k_enc_rd<false>, (njobs * rows + WF_WARPS - 1) / WF_WARPS, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream))(jobs, njobs, g, ticket);
   return (int)cudaGetLastError();
 }
 int launch_enc_rd_trellis(const EncJob* job, int rows, const Geom& g, int* ticket, void* stream) {
-  VP8_LAUNCH(k_enc_rd<true>, (rows + WF_WARPS - 1) / WF_WARPS, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream))(job, g, ticket);
+  VP8_LAUNCH(k_enc_rd<true>, (rows + WF_WARPS - 1) / WF_WARPS, 32 * WF_WARPS, 0, static_cast<cudaStream_t>(stream))(job, 1, g, ticket);
   return (int)cudaGetLastError();
 }
 

@@ -306,6 +306,25 @@ def test_target_size_search_and_rate_monotonicity():
     ctx.close()
 
 
+@pytest.mark.parametrize("w,h,n,target", [(320, 240, 5, 2500), (176, 144, 4, 1200), (640, 368, 3, 8000)])
+def test_searches_in_one_launch_equal_candidate_by_candidate(w, h, n, target):
+    """The target-size search codes every probe it can still reach in one k_enc_rd launch (33 sampled passes, or the
+    next three levels of the bisection tree for the first frame's wider range), the loop-filter search its trials in
+    one k_loopfilter launch.  Same session with VP8GPU_ENC_SPECULATE=0 (one launch per candidate, the round-1 order):
+    same bytes, same quantisers, same loop-filter levels, same SSIM, same Decoder state -- and fewer launches."""
+    import json
+    import sys
+    worker = os.path.join(ROOT, "tests", "encoder_search_worker.py")
+    res = {}
+    for mode in ("1", "0"):
+        r = subprocess.run([sys.executable, worker, str(w), str(h), str(n), str(target)], env=dict(os.environ, VP8GPU_ENC_SPECULATE=mode),
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (r.stdout + r.stderr)[-1500:]
+        res[mode] = json.loads(r.stdout.strip().splitlines()[-1])
+    assert res["1"]["frames"] == res["0"]["frames"]
+    assert res["1"]["launches"] < res["0"]["launches"], (res["1"]["launches"], res["0"]["launches"])
+
+
 def ssim_x264(a, b):
     """util/ssim.cc -> x264 pixel_ssim_wxh / window count, restated with numpy: integer sums over every
     8x8 window at a 4-pixel step (oracle/ref_shim/ssim_stub.cc), float32 ratio, mean in float64"""
