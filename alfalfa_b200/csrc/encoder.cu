@@ -21,6 +21,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/vp8gpu.h"
@@ -257,7 +260,30 @@ int encode_core(vp8gpu_encoder* enc, bool key, int qi, int sub, int* out_frame, 
 // probabilities optimised and saved (refresh_entropy_probs, encode_intra.cc:402, encode_inter.cc:587) in
 // `probs`; otherwise a size estimate priced with the current tables, which are left alone
 // (size_estimation.cc:92,167: no optimize_probability_tables).
-int encode_bytes(vp8gpu_encoder* enc, bool key, int qi, int lf_level, int sub, bool final, uint8_t* probs, std::vector<uint8_t>& bytes) {
+// A loop-filter level that is still being searched for while the frame is written (EncodeFeatures::late_loop_filter_level)
+struct LateLevel {
+  std::mutex m;
+  std::condition_variable cv;
+  bool ready = false;
+  int level = 0;
+  void set(int v) {
+    {
+      std::lock_guard<std::mutex> lk(m);
+      level = v;
+      ready = true;
+    }
+    cv.notify_all();
+  }
+  static int wait(void* p) {
+    LateLevel* l = static_cast<LateLevel*>(p);
+    std::unique_lock<std::mutex> lk(l->m);
+    l->cv.wait(lk, [l] { return l->ready; });
+    return l->level;
+  }
+};
+
+int encode_bytes(vp8gpu_encoder* enc, bool key, int qi, int lf_level, int sub, bool final, uint8_t* probs, std::vector<uint8_t>& bytes,
+                 LateLevel* late = nullptr) {
   Engine* e = enc->e;
   int pw, ph, cols, rows;
   pass_dims(enc, sub, &pw, &ph, &cols, &rows);
@@ -298,6 +324,10 @@ int encode_bytes(vp8gpu_encoder* enc, bool key, int qi, int lf_level, int sub, b
     ft.ymode_probs = enc->dec_state->ymode_probs;
     ft.uvmode_probs = enc->dec_state->uvmode_probs;
     ft.mv_probs = enc->dec_state->mv_probs;
+  }
+  if (late) {
+    ft.late_loop_filter_level = &LateLevel::wait;
+    ft.late_ctx = late;
   }
   bytes = vp8::serialize_frame(h, enc->h_mbs, enc->h_tokens, nullptr, &ft);
   if (bytes.empty()) return e->fail(VP8GPU_ERR_LOGIC, "serializer rejected the device records");
@@ -716,11 +746,25 @@ static int encode_final(vp8gpu_encoder* enc, bool key, int qi, uint8_t* out, siz
   double ssim = -1.0;
   int rc = encode_passes(enc, key, qi, &frame);
   if (rc != VP8GPU_OK) return rc;
-  rc = choose_loop_filter(enc, &frame, key, &lf, &ssim);
   std::vector<uint8_t> bytes;
   uint8_t probs[1056];
   memcpy(probs, enc->dec_state->coef_probs, 1056);
-  if (rc == VP8GPU_OK) rc = encode_bytes(enc, key, qi, lf, 1, true, probs, bytes);
+  if (enc_speculate()) {
+    // The writer needs the loop-filter level only where the frame header spells it out, after the token partitions
+    // -- most of its work -- are done: it runs on a host thread of its own (host code only: records and tokens of the
+    // pass are in pinned memory) while this thread drives the loop-filter search on the device, and picks the level up
+    // when it gets there.
+    LateLevel late;
+    int wrc = VP8GPU_OK;
+    std::thread writer([&] { wrc = encode_bytes(enc, key, qi, 0, 1, true, probs, bytes, &late); });
+    rc = choose_loop_filter(enc, &frame, key, &lf, &ssim);
+    late.set(rc == VP8GPU_OK ? lf : 0);
+    writer.join();
+    if (rc == VP8GPU_OK) rc = wrc;
+  } else {
+    rc = choose_loop_filter(enc, &frame, key, &lf, &ssim);
+    if (rc == VP8GPU_OK) rc = encode_bytes(enc, key, qi, lf, 1, true, probs, bytes);
+  }
   if (rc != VP8GPU_OK) {
     enc->e->frame_release(frame);
     return rc;

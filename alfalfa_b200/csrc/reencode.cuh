@@ -179,13 +179,25 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_reenc_intra(const ReencJob
   uint8_t* const V = J.recon + g.v_off;
   const vp8gpu_quant q = J.q;
 
-  for (int col = 0; col < cols; col++) {
+  // Which macroblocks of this row are intra-coded: one mask word per lane (as in k_intra).  The inter-coded ones were
+  // reconstructed by step 3 and nothing of them depends on this frame, so the row only stops at its intra macroblocks
+  // and publishes "everything left of the next one is done" -- a row without any is finished at once instead of
+  // walking (and publishing) every macroblock.
+  const int nwords = (cols + 31) >> 5;
+  uint32_t my_word = 0;
+  for (int w = 0; w < nwords; w++) {
+    const int c = w * 32 + lane;
+    const bool intra = c < cols && (__ldg(reinterpret_cast<const uint32_t*>(J.mbs_in + row * cols + c) + 2) & 0xFF) == VP8GPU_REF_CURRENT;
+    const uint32_t bits = __ballot_sync(0xffffffffu, intra);
+    if (lane == w) my_word = bits;
+  }
+  int col = next_marked(my_word, 0, nwords);
+  // progress = P means: every macroblock of this row with column < P is reconstructed
+  publish_row(progress, col < 0 ? cols : col, lane);
+
+  while (col >= 0) {
     const int mbi = row * cols + col;
     const MbFields f = load_mb(J.mbs_in + mbi);
-    if (f.ref != VP8GPU_REF_CURRENT) {  // reconstructed by step 3; nothing of it depends on this frame
-      publish_row(progress, col + 1, lane);
-      continue;
-    }
     reenc_load_target(J, g, col, row, src, lane);
     __syncwarp();
     if (row > 0) wait_row(progress - 1, min(col + 2, cols), lane);
@@ -376,6 +388,8 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_reenc_intra(const ReencJob
       m.flags = bpred ? 0 : VP8GPU_MB_HAS_Y2;
       J.mbs_out[mbi] = m;
     }
-    publish_row(progress, col + 1, lane);
+    const int next = next_marked(my_word, col + 1, nwords);
+    publish_row(progress, next < 0 ? cols : next, lane);
+    col = next;
   }
 }

@@ -629,7 +629,7 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
         }
     }
     bw.put(0);  // filter_type: normal
-    bw.literal(h.loop_filter_level, 6);
+    bw.literal(x.late_loop_filter_level ? x.late_loop_filter_level(x.late_ctx) : h.loop_filter_level, 6);
     bw.literal(h.sharpness, 3);
     if (x.ref_writer && x.ref_estimate) {
       bw.put(0);  // the sampled frame of a size estimate never gets loop-filter settings (size_estimation.cc)

@@ -83,6 +83,11 @@ struct EncodeFeatures {
   // its tape) and sharpness (EncodeHeader), all three references refreshed, and intra_16x16_prob /
   // intra_chroma_prob sent explicitly with their default values (reencode.cc:66-75)
   const Verbatim* from_key = nullptr;
+  // EncodeHeader::loop_filter_level supplied late: called (once) where the header writes the level, i.e. after the
+  // token partitions have been recorded and coded -- nothing before that point depends on the level, so the encoder
+  // runs its loop-filter search (device) while this function works (host) and answers here (encoder.cu encode_final)
+  int (*late_loop_filter_level)(void* ctx) = nullptr;
+  void* late_ctx = nullptr;
   // the stream's saved mode / motion-vector probabilities (DecoderState) that macroblock headers are coded with;
   // nullptr = the default tables (an Encoder that started from a key frame never changes them)
   const uint8_t* ymode_probs = nullptr;
