@@ -23,12 +23,12 @@
 
 #include <condition_variable>
 #include <mutex>
-#include <thread>
 #include <vector>
 
 #include "../../include/vp8gpu.h"
 #include "enc_costs.h"
 #include "engine.hpp"
+#include "hostpool.h"
 #include "parser.h"
 #include "serializer.h"
 #include "vp8_enc_tables.h"
@@ -751,15 +751,16 @@ static int encode_final(vp8gpu_encoder* enc, bool key, int qi, uint8_t* out, siz
   memcpy(probs, enc->dec_state->coef_probs, 1056);
   if (enc_speculate()) {
     // The writer needs the loop-filter level only where the frame header spells it out, after the token partitions
-    // -- most of its work -- are done: it runs on a host thread of its own (host code only: records and tokens of the
+    // -- most of its work -- are done: it runs on a pool thread (hostpool.h; host code only: records and tokens of the
     // pass are in pinned memory) while this thread drives the loop-filter search on the device, and picks the level up
     // when it gets there.
     LateLevel late;
     int wrc = VP8GPU_OK;
-    std::thread writer([&] { wrc = encode_bytes(enc, key, qi, 0, 1, true, probs, bytes, &late); });
+    vp8::HostPool::Group writer;
+    writer.run([&] { wrc = encode_bytes(enc, key, qi, 0, 1, true, probs, bytes, &late); });
     rc = choose_loop_filter(enc, &frame, key, &lf, &ssim);
     late.set(rc == VP8GPU_OK ? lf : 0);
-    writer.join();
+    writer.wait();
     if (rc == VP8GPU_OK) rc = wrc;
   } else {
     rc = choose_loop_filter(enc, &frame, key, &lf, &ssim);

@@ -6,10 +6,14 @@
 // decoder will have when it reads it.
 #include "serializer.h"
 
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <thread>
+
+#include "hostpool.h"
 
 #include "vp8_tables.h"
 
@@ -22,32 +26,6 @@ void BoolWriter::add_one() {
   size_t i = out_.size();
   while (i > 0 && out_[i - 1] == 255) out_[--i] = 0;
   if (i > 0) ++out_[i - 1];
-}
-void BoolWriter::put(int bit, int prob) {
-  const uint32_t split = 1 + (((range_ - 1) * static_cast<uint32_t>(prob)) >> 8);
-  if (bit) {
-    bottom_ += split;
-    range_ -= split;
-  } else {
-    range_ = split;
-  }
-  // renormalise: same effect as shifting one bit at a time (RFC 6386 section 7.3), done in one step
-  int shift = __builtin_clz(range_) - 24;
-  range_ <<= shift;
-  while (shift > 0) {
-    const int n = shift < bit_count_ ? shift : bit_count_;  // bits until the next output byte
-    // bits leaving the top are carries into bytes already written
-    for (uint32_t carry = static_cast<uint32_t>((static_cast<uint64_t>(bottom_) << n) >> 32); carry; carry &= carry - 1)
-      add_one();
-    bottom_ <<= n;
-    bit_count_ -= n;
-    shift -= n;
-    if (!bit_count_) {
-      out_.push_back(static_cast<uint8_t>(bottom_ >> 24));
-      bottom_ &= (1u << 24) - 1;
-      bit_count_ = 8;
-    }
-  }
 }
 void BoolWriter::literal(int value, int width) {
   for (int i = width - 1; i >= 0; i--) put((value >> i) & 1, 128);
@@ -319,6 +297,10 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
   const int cols = (h.width + 15) / 16, rows = (h.height + 15) / 16;
   const size_t n_mbs = static_cast<size_t>(cols) * rows;
   std::vector<MbInfo> info(n_mbs);
+  static const bool ser_trace = getenv("VP8GPU_SER_TRACE") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double tt[8] = {0};
+  tt[0] = now();
 
   // ---- pass 0 (serial, cheap): which blocks of every macroblock hold a non-zero coefficient, and from
   //      that the "above" token contexts of every macroblock.  The Y2 context of a column / row is the
@@ -359,6 +341,7 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
     }
   }
 
+  tt[1] = now();
   // ---- the frame's coefficient probabilities before any update of this frame ----
   uint8_t coef_probs[1056];
   if (x.saved_coef_probs && h.key_frame) memcpy(x.saved_coef_probs, k_coef_default_probs, 1056);
@@ -377,15 +360,24 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
     std::vector<uint32_t> ref_skip_eob;  // reference writer policy: end-of-block counts of skipped macroblocks
     std::vector<uint8_t> bytes;
   };
-  std::vector<PartWork> work(nparts);
-  auto record_partition = [&](int p) {
-    PartWork& W = work[p];
+  // Recording (as opposed to coding) a partition needs nothing from the row before once the above contexts are known,
+  // so a partition's rows are recorded in `nsub` contiguous chunks on as many threads -- the reference's writer has
+  // ONE partition, which would otherwise leave this pass serial -- and replayed into the coder chunk after chunk.
+  // work[p * nsub + k]: chunk k of partition p; the partition's bytes end up in chunk 0.
+  const int nsub = (!direct && nparts == 1 && n_mbs >= 256) ? 4 : 1;  // (CIF and up: the small golden-vector sizes exercise it too)
+  std::vector<PartWork> work(static_cast<size_t>(nparts) * nsub);
+  auto record_partition = [&](int pk) {
+    const int p = pk / nsub, k = pk % nsub;
+    const int part_rows = (rows - p + nparts - 1) / nparts;  // rows p, p + nparts, ... of this partition
+    const int first = static_cast<int>(static_cast<int64_t>(part_rows) * k / nsub), last = static_cast<int>(static_cast<int64_t>(part_rows) * (k + 1) / nsub);
+    PartWork& W = work[pk];
+    const double t_begin = ser_trace ? now() : 0.0;
     W.cnt.assign(2 * (1056 + 256), 0);
     W.ref_skip_eob.assign(1056, 0);
     auto walk = [&](auto& sink) {
     int16_t c[25][16];  // coefficients of the current macroblock, raster order; all zero between macroblocks
     memset(c, 0, sizeof(c));
-    for (int row = p; row < rows; row += nparts) {
+    for (int row = p + first * nparts; row < p + last * nparts && row < rows; row += nparts) {
       unsigned left = 0;  // same bit layout as above_ctx
       for (int col = 0; col < cols; col++) {
         const size_t idx = static_cast<size_t>(row) * cols + col;
@@ -443,20 +435,22 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
       walk(dw);
       W.bytes = tw.finish();
     } else {
-      W.rec.bits.reserve(n_mbs * 160 / nparts + 1024);
+      W.rec.bits.reserve(n_mbs * 160 / (nparts * nsub) + 1024);
       W.rec.cnt = W.cnt.data();
       walk(W.rec);
     }
+    if (ser_trace) fprintf(stderr, "  chunk %d: rows %d..%d  %.2f ms (started at +%.2f)\n", pk, first, last, now() - t_begin, t_begin - tt[1]);
   };
-  const bool threaded = nparts > 1 && n_mbs >= 1024;
+  const bool threaded = nsub > 1 || (nparts > 1 && n_mbs >= 1024);
   {
-    std::vector<std::thread> th;
-    for (int p = 1; p < nparts && threaded; p++) th.emplace_back(record_partition, p);
+    HostPool::Group g;
+    for (int p = 1; p < nparts * nsub && threaded; p++) g.run([&record_partition, p] { record_partition(p); });
     record_partition(0);
-    for (int p = 1; p < nparts && !threaded; p++) record_partition(p);
-    for (auto& t : th) t.join();
+    for (int p = 1; p < nparts * nsub && !threaded; p++) record_partition(p);
+    g.wait();
   }
 
+  tt[2] = now();
   // ---- frame probabilities ----
   std::vector<uint8_t> updated(1056, 0);
   auto calc_prob = [](uint64_t falses, uint64_t total) -> int {  // Encoder::calc_prob (encoder.cc:48-55)
@@ -552,25 +546,21 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
   memcpy(prob_of_slot, coef_probs, 1056);
   for (int p = 0; p < 256; p++) prob_of_slot[1056 + p] = static_cast<uint8_t>(p);
   auto write_partition = [&](int p) {
-    PartWork& W = work[p];
     BoolWriter tw;
-    tw.reserve(W.rec.bits.size() / 4 + 64);
-    for (const uint16_t b : W.rec.bits) tw.put(b & 1, prob_of_slot[b >> 1]);
-    W.bytes = tw.finish();
+    size_t n_bits = 0;
+    for (int k = 0; k < nsub; k++) n_bits += work[p * nsub + k].rec.bits.size();
+    tw.reserve(n_bits / 4 + 64);
+    for (int k = 0; k < nsub; k++)
+      for (const uint16_t b : work[p * nsub + k].rec.bits) tw.put(b & 1, prob_of_slot[b >> 1]);
+    work[p * nsub].bytes = tw.finish();
   };
-  struct Joiner {  // every return path below waits for the writers
-    std::vector<std::thread> th;
-    void join() {
-      for (auto& t : th)
-        if (t.joinable()) t.join();
-    }
-    ~Joiner() { join(); }
-  } writers;
+  HostPool::Group writers;  // every return path below waits for the writers (the destructor does)
   for (int p = 0; p < nparts && !direct; p++) {
-    if (threaded) writers.th.emplace_back(write_partition, p);
+    if (threaded) writers.run([&write_partition, p] { write_partition(p); });
     else write_partition(p);
   }
 
+  tt[3] = now();
   // ---- first partition: frame header ----
   BoolWriter bw;
   const Verbatim* const ro = x.residue_of;
@@ -873,8 +863,10 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
   }
   const std::vector<uint8_t> first = bw.finish();
 
-  writers.join();
+  writers.wait();
 
+  tt[4] = now();
+  if (ser_trace) fprintf(stderr, "serialize_frame: pass0 %.2f record %.2f probs+write %.2f first partition %.2f ms\n", tt[1] - tt[0], tt[2] - tt[1], tt[3] - tt[2], tt[4] - tt[3]);
   // ---- frame tag (uncompressed_chunk.cc:49-77 inverted) ----
   std::vector<uint8_t> out;
   const uint32_t tag = (h.key_frame ? 0u : 1u) | (0u << 1) | (static_cast<uint32_t>(h.show_frame) << 4) |
@@ -893,11 +885,11 @@ std::vector<uint8_t> serialize_frame(const EncodeHeader& h, const vp8gpu_mb* mbs
   }
   out.insert(out.end(), first.begin(), first.end());
   for (int p = 0; p + 1 < nparts; p++) {  // partition sizes, all but the last (uncompressed_chunk.cc:132-155)
-    out.push_back(work[p].bytes.size() & 0xFF);
-    out.push_back((work[p].bytes.size() >> 8) & 0xFF);
-    out.push_back((work[p].bytes.size() >> 16) & 0xFF);
+    out.push_back(work[p * nsub].bytes.size() & 0xFF);
+    out.push_back((work[p * nsub].bytes.size() >> 8) & 0xFF);
+    out.push_back((work[p * nsub].bytes.size() >> 16) & 0xFF);
   }
-  for (int p = 0; p < nparts; p++) out.insert(out.end(), work[p].bytes.begin(), work[p].bytes.end());
+  for (int p = 0; p < nparts; p++) out.insert(out.end(), work[p * nsub].bytes.begin(), work[p * nsub].bytes.end());
   return out;
 }
 

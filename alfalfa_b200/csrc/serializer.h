@@ -98,7 +98,32 @@ struct EncodeFeatures {
 // RFC 6386 section 7 arithmetic encoder (same code stream as encoder/bool_encoder.hh)
 class BoolWriter {
  public:
-  void put(int bit, int prob = 128);
+  // RFC 6386 section 7.3.  `low_` holds the bits of the interval's lower end that may still change: 24 bits below
+  // the byte that goes out next; count_ counts the shifts until that byte is complete (from -24).  One
+  // renormalisation step per decision (count-leading-zeros), one branch when a byte leaves; a carry out of `low_`
+  // ripples through the bytes already written (at most once per output byte).
+  inline void put(int bit, int prob = 128) {
+    const uint32_t split = 1 + (((range_ - 1) * static_cast<uint32_t>(prob)) >> 8);
+    uint32_t range = split, low = low_;
+    if (bit) {
+      low += split;
+      range = range_ - split;
+    }
+    int shift = __builtin_clz(range) - 24;
+    range <<= shift;
+    count_ += shift;
+    if (count_ >= 0) {
+      const int offset = shift - count_;
+      if ((low << (offset - 1)) & 0x80000000u) add_one();
+      out_.push_back(static_cast<uint8_t>(low >> (24 - offset)));
+      low <<= offset;
+      shift = count_;
+      low &= 0xFFFFFFu;
+      count_ -= 8;
+    }
+    low_ = low << shift;
+    range_ = range;
+  }
   void literal(int value, int width);
   std::vector<uint8_t> finish();
   size_t size_estimate() const { return out_.size(); }
@@ -107,8 +132,8 @@ class BoolWriter {
  private:
   void add_one();
   std::vector<uint8_t> out_;
-  uint32_t range_ = 255, bottom_ = 0;
-  int bit_count_ = 24;
+  uint32_t range_ = 255, low_ = 0;
+  int count_ = -24;
 };
 
 // mbs: mb_cols*mb_rows records (y_mode, uv_mode, ref_frame, mv / split / b_modes, tok_off, tok_cnt);
