@@ -779,6 +779,40 @@ int vp8gpu_decoder_decode(vp8gpu_decoder* d, const uint8_t* data, size_t len, in
   return rc;
 }
 
+// Internal (encoder.cu, Encoder::write_frame's "decode what was written", encoder.cc:153-158): vp8gpu_decoder_decode
+// of a frame this library has just serialised from `enc_mbs` / `enc_tokens`.  The first partition is parsed like any
+// other frame's (state, modes, vectors, resolved loop-filter levels), but the DCT partitions are not decoded again:
+// their content is the token lists they were written from (tok_off / tok_cnt of the writer's records index
+// enc_tokens; the order inside a macroblock's list does not matter to the kernels).  Saves the serial half of the
+// parse, which is most of a frame's host time.
+int vp8gpu_decoder_decode_known_tokens(vp8gpu_decoder* d, const uint8_t* data, size_t len, const vp8gpu_mb* enc_mbs,
+                                       const vp8gpu_token* enc_tokens, uint32_t n_tok, int* shown, vp8gpu_frame_id* out) {
+  if (!d || !data || !enc_mbs || (n_tok && !enc_tokens)) return VP8GPU_ERR_LOGIC;
+  Engine* e = d->ctx->engine;
+  cudaSetDevice(e->device());
+  vp8gpu_parsed* p = next_ring_slot(d);
+  const int rc = vp8::parse_frame(d->state.s, data, len, p->f, true);
+  if (rc != VP8GPU_OK) return e->fail(rc, "parse_frame failed");
+  const size_t n = (size_t)p->f.desc.mb_cols * p->f.desc.mb_rows;
+  if (!p->f.tokens.reserve((size_t)n_tok + 1, 0)) return e->fail(VP8GPU_ERR_NOMEM, "token buffer");
+  if (n_tok) memcpy(p->f.tokens.data(), enc_tokens, (size_t)n_tok * sizeof(vp8gpu_token));
+  vp8gpu_mb* m = p->f.mbs.data();
+  for (size_t i = 0; i < n; i++) {
+    const vp8gpu_mb& w = enc_mbs[i];
+    // the frame must be the one written from these records: same decisions, a skipped macroblock has no tokens
+    if (m[i].y_mode != w.y_mode || m[i].ref_frame != w.ref_frame || ((m[i].flags & VP8GPU_MB_SKIP) && w.tok_cnt) ||
+        (size_t)w.tok_off + w.tok_cnt > n_tok)
+      return e->fail(VP8GPU_ERR_LOGIC, "decode_known_tokens: the records do not belong to this frame");
+    m[i].tok_off = w.tok_off;
+    m[i].tok_cnt = w.tok_cnt;
+    m[i].flags = static_cast<uint8_t>(m[i].flags & ~VP8GPU_MB_SKIP);
+  }
+  p->f.desc.n_tokens = n_tok;
+  p->f.tw.deferred = false;
+  count_mbs(p);
+  return decode_parsed_impl(d, p, true, shown, out);
+}
+
 int vp8gpu_decoder_decode_parsed(vp8gpu_decoder* d, const vp8gpu_parsed* parsed, int* shown, vp8gpu_frame_id* out) {
   if (!d || !parsed) return VP8GPU_ERR_LOGIC;
   cudaSetDevice(d->ctx->engine->device());

@@ -40,6 +40,8 @@ using vp8::Engine;
 extern "C" Engine* vp8gpu_ctx_engine(vp8gpu_ctx* ctx);
 extern "C" int vp8gpu_ctx_next_lane(vp8gpu_ctx* ctx);
 extern "C" const vp8::ParsedFrame* vp8gpu_parsed_frame(const vp8gpu_parsed* p);
+extern "C" int vp8gpu_decoder_decode_known_tokens(vp8gpu_decoder* d, const uint8_t* data, size_t len, const vp8gpu_mb* enc_mbs,
+                                                  const vp8gpu_token* enc_tokens, uint32_t n_tok, int* shown, vp8gpu_frame_id* out);
 
 struct vp8gpu_encoder {
   vp8gpu_ctx* ctx = nullptr;
@@ -646,7 +648,8 @@ void vp8gpu_encoder_destroy(vp8gpu_encoder* enc) {
   delete enc;
 }
 
-static int apply_emitted_frame(vp8gpu_encoder* enc, const uint8_t* data, size_t len);
+static int apply_emitted_frame(vp8gpu_encoder* enc, const uint8_t* data, size_t len, const vp8gpu_mb* mbs = nullptr,
+                               const vp8gpu_token* tokens = nullptr, uint32_t n_tok = 0);
 static int finish_frame(vp8gpu_encoder* enc, bool key, const std::vector<uint8_t>& bytes, int out_frame, int qi, int lf, double ssim,
                         uint8_t* out, size_t cap, size_t* size) {
   Engine* e = enc->e;
@@ -662,7 +665,7 @@ static int finish_frame(vp8gpu_encoder* enc, bool key, const std::vector<uint8_t
     // quantiser.  The reference is immune because write_frame always decodes what it wrote (encoder.cc:153-158);
     // do the same here instead of keeping the kernel's reconstruction.
     e->frame_release(out_frame);
-    const int rc = apply_emitted_frame(enc, bytes.data(), bytes.size());
+    const int rc = apply_emitted_frame(enc, bytes.data(), bytes.size(), enc->h_mbs, enc->h_tokens, *enc->h_count);
     if (rc != VP8GPU_OK) return rc;
     enc->last_qi = qi;
     enc->last_lf = lf;
@@ -1088,14 +1091,18 @@ int vp8gpu_encoder_minihash(vp8gpu_encoder* enc, uint32_t* out) {
 // Encoder::write_frame's state update (encoder.cc:146-170): decode the emitted frame like any receiver
 // (Frame::decode + loopfilter + copy_to on the device, through the library's own Decoder) and adopt the
 // DecoderState and References it ends with.
-static int apply_emitted_frame(vp8gpu_encoder* enc, const uint8_t* data, size_t len) {
+// mbs / tokens: the records and token lists the frame was serialised from (enc->h_mbs / h_tokens), when it was --
+// the decode then skips parsing the DCT partitions back (capi.cc vp8gpu_decoder_decode_known_tokens)
+static int apply_emitted_frame(vp8gpu_encoder* enc, const uint8_t* data, size_t len, const vp8gpu_mb* mbs, const vp8gpu_token* tokens,
+                               uint32_t n_tok) {
   Engine* e = enc->e;
   vp8gpu_decoder* d = nullptr;
   int rc = vp8gpu_encoder_export_decoder(enc, &d);
   if (rc != VP8GPU_OK) return rc;
   int shown = 0;
   vp8gpu_frame_id raster = -1;
-  rc = vp8gpu_decoder_decode(d, data, len, &shown, &raster);
+  if (mbs && enc_speculate()) rc = vp8gpu_decoder_decode_known_tokens(d, data, len, mbs, tokens, n_tok, &shown, &raster);
+  else rc = vp8gpu_decoder_decode(d, data, len, &shown, &raster);
   if (rc == VP8GPU_OK) {
     if (raster >= 0) e->frame_release(raster);
     const std::vector<uint8_t> blob = [&] {
@@ -1122,11 +1129,12 @@ static int apply_emitted_frame(vp8gpu_encoder* enc, const uint8_t* data, size_t 
   return rc;
 }
 
-static int emit(vp8gpu_encoder* enc, const std::vector<uint8_t>& bytes, uint8_t* out, size_t cap, size_t* size) {
+static int emit(vp8gpu_encoder* enc, const std::vector<uint8_t>& bytes, uint8_t* out, size_t cap, size_t* size, const vp8gpu_mb* mbs = nullptr,
+                const vp8gpu_token* tokens = nullptr, uint32_t n_tok = 0) {
   *size = bytes.size();
   if (!out || cap < bytes.size()) return enc->e->fail(VP8GPU_ERR_NOMEM, "output buffer too small");
   memcpy(out, bytes.data(), bytes.size());
-  return apply_emitted_frame(enc, bytes.data(), bytes.size());
+  return apply_emitted_frame(enc, bytes.data(), bytes.size(), mbs, tokens, n_tok);
 }
 
 // Encoder::write_frame( KeyFrame ) (encoder.cc:146-176) as Encoder::reencode uses it for a key frame that is kept
@@ -1311,7 +1319,7 @@ int vp8gpu_encoder_update_residues(vp8gpu_encoder* enc, const uint8_t* y, size_t
   ft.mv_probs = enc->dec_state->mv_probs;
   const std::vector<uint8_t> bytes = vp8::serialize_frame(h, enc->h_mbs, enc->h_tokens, pf->split.data(), &ft);
   if (bytes.empty()) return e->fail(VP8GPU_ERR_LOGIC, "update_residues: serializer rejected the records");
-  rc = emit(enc, bytes, out, cap, size);
+  rc = emit(enc, bytes, out, cap, size, enc->h_mbs, enc->h_tokens, n_tok);
   if (rc == VP8GPU_OK) {  // write_frame, REALTIME_QUALITY (encoder.cc:164-167)
     enc->last_qi = qi;
     enc->last_lf = vb.lf_level;
@@ -1379,7 +1387,7 @@ int vp8gpu_encoder_reencode_as_interframe(vp8gpu_encoder* enc, const uint8_t* y,
   ft.mv_probs = enc->dec_state->mv_probs;  // the mode probabilities are the defaults the header itself sets
   std::vector<uint8_t> bytes = vp8::serialize_frame(h, enc->h_mbs, enc->h_tokens, nullptr, &ft);
   if (bytes.empty()) return e->fail(VP8GPU_ERR_LOGIC, "reencode_as_interframe: serializer rejected the device records");
-  rc = emit(enc, bytes, out, cap, size);
+  rc = emit(enc, bytes, out, cap, size, enc->h_mbs, enc->h_tokens, *enc->h_count);
   if (rc == VP8GPU_OK) {
     enc->last_qi = y_ac_qi;
     enc->last_lf = lf;
