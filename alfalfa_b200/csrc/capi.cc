@@ -159,6 +159,7 @@ int vp8gpu_ctx_create(int device, int width, int height, int max_frames, vp8gpu_
   *out = c;
   return VP8GPU_OK;
 }
+extern "C" void vp8gpu_encoder_pool_purge(Engine* e);
 void vp8gpu_ctx_destroy(vp8gpu_ctx* ctx) {
   if (!ctx) return;
   for (vp8gpu_parsed* p : ctx->pinned_pool) vp8gpu_parsed_destroy(p);
@@ -176,6 +177,7 @@ void vp8gpu_ctx_destroy(vp8gpu_ctx* ctx) {
     }
     delete k;
   }
+  vp8gpu_encoder_pool_purge(ctx->engine);  // buffer sets of destroyed Encoders of this context (encoder.cu)
   delete ctx->engine;
   delete ctx;
 }

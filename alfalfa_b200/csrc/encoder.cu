@@ -23,6 +23,7 @@
 
 #include <condition_variable>
 #include <mutex>
+#include <utility>
 #include <vector>
 
 #include "../../include/vp8gpu.h"
@@ -515,6 +516,71 @@ int upload_source(vp8gpu_encoder* enc, const uint8_t* y, size_t ys, const uint8_
 
 }  // namespace
 
+// layout of the size-estimate scratch (estimate_batch_launch); returns its size
+static size_t est_layout(vp8gpu_encoder* enc) {
+  const vp8::Geom& g = enc->e->geom();
+  int pw, ph, cols, rows;
+  pass_dims(enc, 4, &pw, &ph, &cols, &rows);
+  const size_t n_mbs = (size_t)cols * rows;
+  enc->est_tok_cap = (uint32_t)(n_mbs * 400);
+  size_t off = align_up(sizeof(vp8::EncJob) * kEstMax, 256);
+  enc->est_off_sync = off;
+  off = align_up(off + sizeof(int) * (128 + (size_t)kEstMax * rows), 256);
+  enc->est_off_mbs = off;
+  off = align_up(off + (size_t)kEstMax * n_mbs * sizeof(vp8gpu_mb), 256);
+  enc->est_off_tokens = off;
+  off = align_up(off + (size_t)kEstMax * enc->est_tok_cap * sizeof(vp8gpu_token), 256);
+  enc->est_off_out = off;
+  enc->est_out_stride = align_up(g.frame_bytes, 256);
+  return off + (size_t)kEstMax * enc->est_out_stride;
+}
+
+// ---- buffer sets of destroyed Encoders, kept per context -----------------------------------------------------
+// Salsify copies its Encoder twice per frame and drops the copies again (salsify-sender.cc:492-518); an Encoder
+// here owns ~20 MB of pinned host memory and ~20 MB (+ the size-estimate scratch) of device memory at 1080p, and
+// cudaHostAlloc / cudaMalloc / cudaFree of those cost milliseconds and serialise on the driver.  A destroyed
+// Encoder therefore hands its buffers to its context, the next create / clone of that context takes them over.
+struct EncBufferSet {
+  uint8_t *dev, *d_split, *d_trellis, *d_est, *h_est, *h_hdr, *h_src;
+  vp8gpu_mb* h_mbs;
+  vp8gpu_token* h_tokens;
+  uint32_t* h_count;
+  size_t split_cap;
+  uint8_t tab_mv_probs[38];
+};
+static std::mutex g_enc_pool_mu;
+static std::vector<std::pair<Engine*, EncBufferSet>> g_enc_pool;
+constexpr size_t kEncPoolPerEngine = 4;
+
+static void enc_buffers_free(const EncBufferSet& b) {
+  if (b.dev) cudaFree(b.dev);
+  if (b.d_split) cudaFree(b.d_split);
+  if (b.d_trellis) cudaFree(b.d_trellis);
+  if (b.d_est) cudaFree(b.d_est);
+  if (b.h_est) cudaFreeHost(b.h_est);
+  if (b.h_hdr) cudaFreeHost(b.h_hdr);
+  if (b.h_mbs) cudaFreeHost(b.h_mbs);
+  if (b.h_tokens) cudaFreeHost(b.h_tokens);
+  if (b.h_src) cudaFreeHost(b.h_src);
+  if (b.h_count) cudaFreeHost(b.h_count);
+}
+// capi.cc vp8gpu_ctx_destroy: the context's buffer sets die with it
+extern "C" void vp8gpu_encoder_pool_purge(Engine* e) {
+  std::vector<EncBufferSet> dead;
+  {
+    std::lock_guard<std::mutex> lk(g_enc_pool_mu);
+    for (size_t i = 0; i < g_enc_pool.size();) {
+      if (g_enc_pool[i].first == e) {
+        dead.push_back(g_enc_pool[i].second);
+        g_enc_pool.erase(g_enc_pool.begin() + i);
+      } else {
+        i++;
+      }
+    }
+  }
+  for (const EncBufferSet& b : dead) enc_buffers_free(b);
+}
+
 // common part of create / clone / create_from: buffers on device and host, the rate tables
 static int encoder_alloc(vp8gpu_ctx* ctx, vp8gpu_encoder** out) {
   vp8gpu_encoder* enc = new vp8gpu_encoder();
@@ -538,7 +604,29 @@ static int encoder_alloc(vp8gpu_ctx* ctx, vp8gpu_encoder** out) {
   off = align_up(off + (size_t)enc->tok_cap * sizeof(vp8gpu_token), 256);
   enc->dev_bytes = off;
   cudaSetDevice(e->device());
-  if (cudaMalloc(&enc->dev, enc->dev_bytes) != cudaSuccess || cudaHostAlloc(&enc->h_hdr, kHdrBytes, cudaHostAllocDefault) != cudaSuccess ||
+  bool pooled = false;
+  {
+    std::lock_guard<std::mutex> lk(g_enc_pool_mu);
+    for (size_t i = g_enc_pool.size(); i-- > 0;)
+      if (g_enc_pool[i].first == e) {
+        const EncBufferSet b = g_enc_pool[i].second;
+        g_enc_pool.erase(g_enc_pool.begin() + i);
+        enc->dev = b.dev, enc->d_split = b.d_split, enc->d_trellis = b.d_trellis, enc->d_est = b.d_est, enc->h_est = b.h_est;
+        enc->h_hdr = b.h_hdr, enc->h_src = b.h_src, enc->h_mbs = b.h_mbs, enc->h_tokens = b.h_tokens, enc->h_count = b.h_count;
+        enc->split_cap = b.split_cap;
+        memcpy(enc->tab_mv_probs, b.tab_mv_probs, 38);
+        pooled = true;
+        break;
+      }
+  }
+  if (pooled) {
+    // same context = same geometry = same layout; what depends on the Encoder's history is only the rate tables
+    if (enc->d_est) est_layout(enc);
+    if (e->frame_alloc(&enc->src) != VP8GPU_OK) {
+      vp8gpu_encoder_destroy(enc);
+      return e->fail(VP8GPU_ERR_NOMEM, "encoder allocation failed");
+    }
+  } else if (cudaMalloc(&enc->dev, enc->dev_bytes) != cudaSuccess || cudaHostAlloc(&enc->h_hdr, kHdrBytes, cudaHostAllocDefault) != cudaSuccess ||
       cudaHostAlloc(&enc->h_mbs, n_mbs * sizeof(vp8gpu_mb), cudaHostAllocDefault) != cudaSuccess ||
       cudaHostAlloc(&enc->h_tokens, (size_t)enc->tok_cap * sizeof(vp8gpu_token), cudaHostAllocDefault) != cudaSuccess ||
       cudaHostAlloc(&enc->h_src, (size_t)g.W * g.H * 3 / 2, cudaHostAllocDefault) != cudaSuccess ||
@@ -551,7 +639,8 @@ static int encoder_alloc(vp8gpu_ctx* ctx, vp8gpu_encoder** out) {
     vp8::build_enc_tables(*t);
     return t;
   }();
-  if (cudaMemcpy(enc->dev + enc->off_tab, tables, sizeof(vp8::EncTables), cudaMemcpyHostToDevice) != cudaSuccess) {
+  if ((!pooled || memcmp(enc->tab_mv_probs, k_mv_default_probs, 38) != 0) &&
+      cudaMemcpy(enc->dev + enc->off_tab, tables, sizeof(vp8::EncTables), cudaMemcpyHostToDevice) != cudaSuccess) {
     vp8gpu_encoder_destroy(enc);
     return e->fail(VP8GPU_ERR_CUDA, "encoder rate tables upload failed");
   }
@@ -633,16 +722,22 @@ void vp8gpu_encoder_destroy(vp8gpu_encoder* enc) {
   for (int k = 0; k < 3; k++)
     if (enc->refs[k] >= 0) enc->e->frame_release(enc->refs[k]);
   if (enc->src >= 0) enc->e->frame_release(enc->src);
-  if (enc->dev) cudaFree(enc->dev);
-  if (enc->d_split) cudaFree(enc->d_split);
-  if (enc->d_trellis) cudaFree(enc->d_trellis);
-  if (enc->d_est) cudaFree(enc->d_est);
-  if (enc->h_est) cudaFreeHost(enc->h_est);
-  if (enc->h_hdr) cudaFreeHost(enc->h_hdr);
-  if (enc->h_mbs) cudaFreeHost(enc->h_mbs);
-  if (enc->h_tokens) cudaFreeHost(enc->h_tokens);
-  if (enc->h_src) cudaFreeHost(enc->h_src);
-  if (enc->h_count) cudaFreeHost(enc->h_count);
+  EncBufferSet b;
+  b.dev = enc->dev, b.d_split = enc->d_split, b.d_trellis = enc->d_trellis, b.d_est = enc->d_est, b.h_est = enc->h_est;
+  b.h_hdr = enc->h_hdr, b.h_src = enc->h_src, b.h_mbs = enc->h_mbs, b.h_tokens = enc->h_tokens, b.h_count = enc->h_count;
+  b.split_cap = enc->split_cap;
+  memcpy(b.tab_mv_probs, enc->tab_mv_probs, 38);
+  bool kept = false;
+  if (b.dev && b.h_hdr && b.h_mbs && b.h_tokens && b.h_src && b.h_count) {  // a complete set (not a failed allocation)
+    std::lock_guard<std::mutex> lk(g_enc_pool_mu);
+    size_t have = 0;
+    for (const auto& x : g_enc_pool) have += x.first == enc->e;
+    if (have < kEncPoolPerEngine) {
+      g_enc_pool.emplace_back(enc->e, b);
+      kept = true;
+    }
+  }
+  if (!kept) enc_buffers_free(b);
   delete enc->dec_state;
   delete enc->scratch;
   delete enc;
@@ -820,17 +915,7 @@ static int estimate_batch_launch(vp8gpu_encoder* enc, bool key, const int* qis, 
   if (n < 1 || n > kEstMax) return e->fail(VP8GPU_ERR_LOGIC, "estimate_batch_launch: bad candidate count");
   const size_t n_mbs = (size_t)cols * rows;
   if (!enc->d_est) {
-    enc->est_tok_cap = (uint32_t)(n_mbs * 400);
-    size_t off = align_up(sizeof(vp8::EncJob) * kEstMax, 256);
-    enc->est_off_sync = off;
-    off = align_up(off + sizeof(int) * (128 + (size_t)kEstMax * rows), 256);
-    enc->est_off_mbs = off;
-    off = align_up(off + (size_t)kEstMax * n_mbs * sizeof(vp8gpu_mb), 256);
-    enc->est_off_tokens = off;
-    off = align_up(off + (size_t)kEstMax * enc->est_tok_cap * sizeof(vp8gpu_token), 256);
-    enc->est_off_out = off;
-    enc->est_out_stride = align_up(g.frame_bytes, 256);
-    off += (size_t)kEstMax * enc->est_out_stride;
+    const size_t off = est_layout(enc);
     if (cudaMalloc(&enc->d_est, off) != cudaSuccess ||
         cudaHostAlloc(&enc->h_est, align_up(sizeof(vp8::EncJob) * kEstMax, 256) + sizeof(uint32_t) * 64, cudaHostAllocDefault) != cudaSuccess) {
       if (enc->d_est) cudaFree(enc->d_est);
