@@ -274,7 +274,11 @@ def bench_encode(a, local):
            "ssim_y": sum(ssims) / n, "gpu_launches": int(launches),
            "note": "the reference encoder's decisions on the device (k_enc_rd: rdcost, B_PRED trial, motion-vector census, diamond "
                    "search, chroma by distortion) and its writer policy: the frames are byte-identical to the reference encoder's "
-                   "(tests/test_gpu_encoder.py; `reference.identical_frames` below compares this very run)"}
+                   "(tests/test_gpu_encoder.py; `reference.identical_frames` below compares this very run)",
+           "searches": ("candidate by candidate (VP8GPU_ENC_SPECULATE=0)" if os.environ.get("VP8GPU_ENC_SPECULATE", "1")[:1] == "0" else
+                        "the probes of the target-size bisection in one k_enc_rd launch (<= 33 sampled passes), the trials of the "
+                        "loop-filter search in one k_loopfilter launch, the frame written on a host thread meanwhile "
+                        "(same bytes as candidate by candidate: tests/test_gpu_encoder.py)")}
     ref_enc = os.path.join(ROOT, "oracle", "_ref", "ref_encode")
     if os.path.exists(ref_enc):
         import tempfile
@@ -305,6 +309,29 @@ def bench_encode(a, local):
     return out
 
 
+def run_exchange(rank, world, local, timeout=240, tool_args=()):
+    """tools/split_gop_check.py on every rank's GPU, as child processes forming their own process group; rank 0 returns
+    the tool's JSON (mismatches, hand-over time, raster exchange time per 1080p raster), the others None"""
+    drop = ("TORCHELASTIC", "GROUP_", "ROLE_")  # torchrun's agent store must not be mistaken for the children's
+    env = {k: v for k, v in os.environ.items() if not k.startswith(drop)}
+    base = int(os.environ.get("MASTER_PORT", "29500"))
+    env.update(RANK=str(rank), LOCAL_RANK=str(local), WORLD_SIZE=str(world), LOCAL_WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+               MASTER_PORT=str(base + 211 if base + 211 < 65000 else base - 211))
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "split_gop_check.py")] + list(tool_args), env=env, capture_output=True, text=True,
+                           timeout=timeout)
+        if rank != 0:
+            return None
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if lines:
+            out = json.loads(lines[-1])
+            out["exit_code"] = r.returncode
+            return out
+        return {"error": (r.stderr or r.stdout)[-300:], "exit_code": r.returncode}
+    except Exception as e:  # noqa: BLE001  (timeout, malformed output)
+        return {"error": ("%s: %s" % (type(e).__name__, e))[:300]} if rank == 0 else None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -319,6 +346,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-encode", action="store_true", help="skip the 1080p encode section")
     ap.add_argument("--no-reencode", action="store_true", help="skip the 1080p re-encoding (update_residues) section")
+    ap.add_argument("--no-exchange", action="store_true", help="N > 1: skip the split-GOP hand-over over NCCL (exchange section)")
     ap.add_argument("--encode-frames", type=int, default=30)
     ap.add_argument("--encode-target", type=int, default=45000, help="bytes per frame for encode_with_target_size")
     ap.add_argument("--host-tokens", action="store_true",
@@ -604,6 +632,19 @@ def main():
         except Exception as e:  # noqa: BLE001  (timeout, malformed output)
             reencode = {"error": ("%s: %s" % (type(e).__name__, e))[:300]}
 
+    # ---------------- the exchange step (N > 1): a GOP that continues on other GPUs ----------------
+    # BASELINE.json config 4: rank 0 decodes the first half of a single-GOP 1080p stream with live golden / altref
+    # references and hands its Decoder over -- DecoderState record + the distinct reference rasters, ncclBroadcast
+    # straight between rasters on the lane stream (vp8gpu_comm_*, csrc/comm.cc) -- every other rank continues the decode
+    # and checks it bit for bit against decoding the whole stream alone.  Every rank runs tools/split_gop_check.py as a
+    # child (own process group on another port, own CUDA context on the rank's GPU) under a timeout: a communicator that
+    # does not come up costs this section, not the line.
+    exchange = None
+    if dist is not None and not a.no_exchange:
+        dist.barrier()  # rank 0 comes from its encode sections: the children start together
+        exchange = run_exchange(rank, world, local)
+        dist.barrier()
+
     # ---------------- CPU baseline (rank 0, one core, bounded sample) ----------------
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
@@ -643,7 +684,7 @@ def main():
             "gpu_launches": results["value"]["launches"], "gpu_launches_e2e": results["e2e"]["launches"],
             "gpu_launches_resident": int(launches_resident),
             "roofline": roofline, "single_stream": single, "cpu_baseline": cpu, "encode": encode, "reencode": reencode,
-            "clocks": clocks}))
+            "exchange": exchange, "clocks": clocks}))
     if dist is not None:
         dist.destroy_process_group()
 
