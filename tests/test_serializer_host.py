@@ -89,3 +89,24 @@ def test_reserialised_frames_parse_back_identically(name):
 def test_roundtrip_with_optimised_token_probabilities(name):
     done, _ = _roundtrip_vector(name, 40, optimize=True)
     assert done >= 1
+
+
+def test_writer_threads_under_thread_sanitizer(tmp_path):
+    """hostpool.h + the writer's parallel sections + the late loop-filter level (tests/serializer_threads.cc) under
+    -fsanitize=thread: no data race, same bytes as single-threaded"""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    clip = os.path.join(root, "bench_data", "synth1080p_medium_q90.ivf")
+    if shutil.which("g++") is None or not os.path.exists(clip):
+        pytest.skip("needs g++ and bench_data")
+    src = os.path.join(root, "alfalfa_b200", "csrc")
+    exe = str(tmp_path / "serializer_threads")
+    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-pthread", "-I", src, "-I", os.path.join(root, "include"),
+                        os.path.join(root, "tests", "serializer_threads.cc"), os.path.join(src, "parser.cc"), os.path.join(src, "serializer.cc"),
+                        "-o", exe], capture_output=True, text=True, timeout=600)
+    if r.returncode != 0 and "tsan" in (r.stderr or "").lower():
+        pytest.skip("ThreadSanitizer runtime not available")
+    assert r.returncode == 0, r.stderr[-1500:]
+    r = subprocess.run([exe, clip], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "bad 0" in r.stdout and "ThreadSanitizer" not in r.stderr, (r.stdout + r.stderr)[-2000:]
