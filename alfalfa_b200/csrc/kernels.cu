@@ -1454,7 +1454,12 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __res
       reinterpret_cast<uint32_t*>(src)[i] = __ldg(reinterpret_cast<const uint32_t*>(gp));
     }
     __syncwarp();
-    if (row > 0) wait_row(progress - 1, min(col + 2, cols), lane);
+    // The row above must have finished the macroblock above; the one above-right too, but only where its pixels can
+    // be used: by the sub-blocks of a B_PRED macroblock (prediction.cc:143-167).  Inter frames at REALTIME_QUALITY
+    // never try B_PRED (encode_inter.cc:281), so their rows follow each other one macroblock apart instead of two --
+    // (cols + rows) dependent steps per pass instead of (cols + 2 rows).  The above-right pixels are still fetched
+    // below, possibly before they are final, and then not looked at.
+    if (row > 0) wait_row(progress - 1, min(col + ((key || !J.realtime) ? 2 : 1), cols), lane);
 
     // ---- edges of the reconstruction so far (prediction.cc:99-167; same rules as k_intra) ----
     {

@@ -200,7 +200,8 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_reenc_intra(const ReencJob
     const MbFields f = load_mb(J.mbs_in + mbi);
     reenc_load_target(J, g, col, row, src, lane);
     __syncwarp();
-    if (row > 0) wait_row(progress - 1, min(col + 2, cols), lane);
+    // (the above-right macroblock only matters to the sub-blocks of a B_PRED macroblock, prediction.cc:143-167)
+    if (row > 0) wait_row(progress - 1, min(col + (f.y_mode == VP8GPU_B_PRED ? 2 : 1), cols), lane);
 
     // ---- edges of the reconstruction so far (prediction.cc:99-167; same rules as k_intra / k_enc_rd) ----
     {
