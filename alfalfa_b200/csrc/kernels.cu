@@ -1275,9 +1275,84 @@ struct __align__(16) EncSmem {  // per warp
 };
 
 // 16x16 luma prediction of `mv` from the reference into dst (stride 16): Block<16>::inter_predict on a SafeRaster
+// The window is staged like mc_block's (aligned words, or pixel by pixel with clamped coordinates when it leaves the
+// plane), the filters are k_inter's packed ones (rows: two dp4a per output on re-aligned words, columns: 32-bit
+// multiply-adds on pixel pairs) -- the motion search evaluates this a hundred times per searched macroblock.
 __device__ __forceinline__ void enc_mc16(const EncJob& J, const Geom& g, int px, int py, int mvx, int mvy, uint8_t* dst,
                                          EncSmem& S, int lane) {
-  mc_block<16>(J.ref, g.y_pitch, g.W, g.H, px, py, mvx, mvy, dst, 16, S.tile, S.mid, lane);
+  constexpr int TS = Mc<16>::TS, NW = Mc<16>::NW;
+  McPlan<16> p;
+  mc_plan<16>(p, J.ref, g.y_pitch, g.W, g.H, px, py, mvx, mvy, lane);
+  if (p.fast) {
+    uint32_t* tw = reinterpret_cast<uint32_t*>(S.tile);
+#pragma unroll
+    for (int k = 0; k < McPlan<16>::K; k++) {
+      const int i = lane + 32 * k;
+      if (i < p.wsize * NW) tw[i] = p.regs[k];
+    }
+  } else {
+    for (int i = lane; i < p.wsize * p.wsize; i += 32) {
+      const int r = i / p.wsize, c = i - r * p.wsize;
+      S.tile[r * TS + c] = __ldg(J.ref + (size_t)clampi(p.wy + r, 0, g.H - 1) * g.y_pitch + clampi(p.wx + c, 0, g.W - 1));
+    }
+  }
+  __syncwarp();
+  // window column / row 0 is pixel -2 of the block unless the vector is whole-pel (then it is the block itself)
+  if ((p.mx | p.my) == 0) {
+    hcopy<16, TS, 16>(S.tile, p.o, 16, dst, lane);
+  } else if (p.my == 0) {
+    hpass2<16, TS, 16>(S.tile + 2 * TS, p.o, 16, p.mx, dst, lane);
+  } else {
+    if (p.mx) hpass2<16, TS, 16>(S.tile, p.o, 21, p.mx, S.mid, lane);
+    else hcopy<16, TS, 16>(S.tile, p.o + 2, 21, S.mid, lane);
+    __syncwarp();
+    const int cp = lane & 7, rg = lane >> 3;
+    vitem<4>(S.mid + (4 * rg) * 16 + 2 * cp, 16, c_sixtap[p.my], dst + (4 * rg) * 16 + 2 * cp, 16);
+  }
+  __syncwarp();
+}
+// both 8x8 chroma predictions of a macroblock (same vector): dst = U 8x8, dst + 64 = V 8x8, stride 8.  The two windows
+// are requested together; staging and filtering as in enc_mc16.
+__device__ __forceinline__ void enc_mc8_pair(const EncJob& J, const Geom& g, int CW, int CH, int px, int py, int mvx, int mvy,
+                                             uint8_t* dst, EncSmem& S, int lane) {
+  constexpr int TS = Mc<8>::TS, NW = Mc<8>::NW;
+  McPlan<8> pl[2];
+  mc_plan<8>(pl[0], J.ref + g.u_off, g.c_pitch, CW, CH, px, py, mvx, mvy, lane);
+  mc_plan<8>(pl[1], J.ref + g.v_off, g.c_pitch, CW, CH, px, py, mvx, mvy, lane);
+#pragma unroll
+  for (int plane = 0; plane < 2; plane++) {
+    const McPlan<8>& p = pl[plane];
+    const uint8_t* ref = J.ref + (plane ? g.v_off : g.u_off);
+    uint8_t* d = dst + 64 * plane;
+    if (p.fast) {
+      uint32_t* tw = reinterpret_cast<uint32_t*>(S.tile);
+#pragma unroll
+      for (int k = 0; k < McPlan<8>::K; k++) {
+        const int i = lane + 32 * k;
+        if (i < p.wsize * NW) tw[i] = p.regs[k];
+      }
+    } else {
+      for (int i = lane; i < p.wsize * p.wsize; i += 32) {
+        const int r = i / p.wsize, c = i - r * p.wsize;
+        S.tile[r * TS + c] = __ldg(ref + (size_t)clampi(p.wy + r, 0, CH - 1) * g.c_pitch + clampi(p.wx + c, 0, CW - 1));
+      }
+    }
+    __syncwarp();
+    if ((p.mx | p.my) == 0) {
+      hcopy<8, TS, 8>(S.tile, p.o, 8, d, lane);
+    } else if (p.my == 0) {
+      hpass2<8, TS, 8>(S.tile + 2 * TS, p.o, 8, p.mx, d, lane);
+    } else {
+      if (p.mx) hpass2<8, TS, 8>(S.tile, p.o, 13, p.mx, S.mid, lane);
+      else hcopy<8, TS, 8>(S.tile, p.o + 2, 13, S.mid, lane);
+      __syncwarp();
+      if (lane < 16) {
+        const int cp = lane & 3, rg = lane >> 2;
+        vitem<2>(S.mid + (2 * rg) * 8 + 2 * cp, 8, c_sixtap[p.my], d + (2 * rg) * 8 + 2 * cp, 8);
+      }
+    }
+    __syncwarp();
+  }
 }
 __device__ __forceinline__ uint32_t enc_variance(const uint8_t* src, const uint8_t* pred, int lane) {
   const int o = (lane >> 1) * 16 + (lane & 1) * 8;
@@ -1759,8 +1834,7 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __res
     const int cplane = lane >> 4, cy = (lane >> 1) & 7, cx4 = (lane & 1) * 4;
     if (inter) {
       const int cmvx = chroma_component(4 * best_mvx), cmvy = chroma_component(4 * best_mvy);
-      mc_block<8>(J.ref + g.u_off, g.c_pitch, CW, CH, 8 * scol, 8 * srow, cmvx, cmvy, pixc, 8, S.tile, S.mid, lane);
-      mc_block<8>(J.ref + g.v_off, g.c_pitch, CW, CH, 8 * scol, 8 * srow, cmvx, cmvy, pixc + 64, 8, S.tile, S.mid, lane);
+      enc_mc8_pair(J, g, CW, CH, 8 * scol, 8 * srow, cmvx, cmvy, pixc, S, lane);
     } else {
       // chroma_mb_best_prediction_mode (encode_intra.cc:250-285): smallest sse( U ) + sse( V ), DC V H TM, first wins
       int cdc[2];
@@ -1992,8 +2066,7 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __res
         *reinterpret_cast<uint32_t*>(W + (y + 1) * WS + 16 + x4) = *reinterpret_cast<const uint32_t*>(S.pcand[0] + y * 16 + x4);
       }
       const int cmvx = chroma_component(4 * best_mvx), cmvy = chroma_component(4 * best_mvy);
-      mc_block<8>(J.ref + g.u_off, g.c_pitch, CW, CH, 8 * col, 8 * row, cmvx, cmvy, pixc, 8, S.tile, S.mid, lane);
-      mc_block<8>(J.ref + g.v_off, g.c_pitch, CW, CH, 8 * col, 8 * row, cmvx, cmvy, pixc + 64, 8, S.tile, S.mid, lane);
+      enc_mc8_pair(J, g, CW, CH, 8 * col, 8 * row, cmvx, cmvy, pixc, S, lane);
       __syncwarp();
     }
     // ---- reconstruct exactly like a decoder will ----
