@@ -113,3 +113,5 @@ def test_no_misaligned_vector_access_in_the_kernels(simt_lib):
     run_gpu_tests_emulated(san, args, env_extra={"LD_PRELOAD": ubsan})
     if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_reencode")):
         run_gpu_tests_emulated(san, ["tests/test_gpu_reencode.py"], env_extra={"LD_PRELOAD": ubsan})
+    # the encoder's predictor (packed filters on staged windows, word stores into the candidate buffers)
+    run_gpu_tests_emulated(san, ["tests/test_gpu_encoder.py", "-k", "(decisions_equal and not size3) or two_pass"], env_extra={"LD_PRELOAD": ubsan})
