@@ -1278,11 +1278,8 @@ struct __align__(16) EncSmem {  // per warp
 // The window is staged like mc_block's (aligned words, or pixel by pixel with clamped coordinates when it leaves the
 // plane), the filters are k_inter's packed ones (rows: two dp4a per output on re-aligned words, columns: 32-bit
 // multiply-adds on pixel pairs) -- the motion search evaluates this a hundred times per searched macroblock.
-__device__ __forceinline__ void enc_mc16(const EncJob& J, const Geom& g, int px, int py, int mvx, int mvy, uint8_t* dst,
-                                         EncSmem& S, int lane) {
+__device__ __forceinline__ void enc_mc16_finish(const McPlan<16>& p, const EncJob& J, const Geom& g, uint8_t* dst, EncSmem& S, int lane) {
   constexpr int TS = Mc<16>::TS, NW = Mc<16>::NW;
-  McPlan<16> p;
-  mc_plan<16>(p, J.ref, g.y_pitch, g.W, g.H, px, py, mvx, mvy, lane);
   if (p.fast) {
     uint32_t* tw = reinterpret_cast<uint32_t*>(S.tile);
 #pragma unroll
@@ -1310,6 +1307,12 @@ __device__ __forceinline__ void enc_mc16(const EncJob& J, const Geom& g, int px,
     vitem<4>(S.mid + (4 * rg) * 16 + 2 * cp, 16, c_sixtap[p.my], dst + (4 * rg) * 16 + 2 * cp, 16);
   }
   __syncwarp();
+}
+__device__ __forceinline__ void enc_mc16(const EncJob& J, const Geom& g, int px, int py, int mvx, int mvy, uint8_t* dst,
+                                         EncSmem& S, int lane) {
+  McPlan<16> p;
+  mc_plan<16>(p, J.ref, g.y_pitch, g.W, g.H, px, py, mvx, mvy, lane);
+  enc_mc16_finish(p, J, g, dst, S, lane);
 }
 // both 8x8 chroma predictions of a macroblock (same vector): dst = U 8x8, dst + 64 = V 8x8, stride 8.  The two windows
 // are requested together; staging and filtering as in enc_mc16.
@@ -1794,20 +1797,43 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __res
           for (int sz = step; sz > 1; sz >>= 1) {
             uint32_t bc = 0xFFFFFFFFu;
             int bx2 = 0, by2 = 0;  // MBPredictionData{}.mv: if every site is out of bounds the origin becomes (0, 0)
+            // one site ahead: the window of site i + 1 is requested (mc_plan: loads into registers) before site i is
+            // filtered and compared, so its latency hides behind that work
+            McPlan<16> pending;
+            int pcx = 0, pcy = 0;
+            bool have = false;
 #pragma unroll 1
-            for (int site = 0; site < 5; site++) {
-              const int dx = site == 0 ? -1 : (site == 4 ? 1 : 0), dy = site == 1 ? -1 : (site == 3 ? 1 : 0);
-              const int cx = ox + sz * dx, cy = oy + sz * dy;
-              if (cx > 1023 || cx < -1023 || cy > 1023 || cy < -1023) continue;
-              int tx = (int16_t)(cx + brx), ty = (int16_t)(cy + bry);
-              clamp_mv(tx, ty, col, row, cols, rows);
-              enc_mc16(J, g, px0, py0, tx, ty, S.pcand[cur], S, lane);
-              const uint32_t sad = enc_sad(src, S.pcand[cur], lane);
-              const int sx = max(min(cx >> 2, 255), -255), sy = max(min(cy >> 2, 255), -255);
-              const uint32_t rate =
-                  J.mv_sad_zero ? 0u : ((uint32_t)(T.mv_sad_cost[abs(sy)] + T.mv_sad_cost[abs(sx)]) * J.sad_per_bit + 128u) / 256u;
-              const uint32_t c = ((128u + rate) / 256u) + sad;  // rdcost( rate, distortion, 1, 1 )
-              if (c < bc) bc = c, bx2 = cx, by2 = cy;
+            for (int site = 0; site <= 5; site++) {
+              McPlan<16> next;
+              int ncx = 0, ncy = 0;
+              bool nvalid = false;
+              if (site < 5) {
+                const int dx = site == 0 ? -1 : (site == 4 ? 1 : 0), dy = site == 1 ? -1 : (site == 3 ? 1 : 0);
+                ncx = ox + sz * dx, ncy = oy + sz * dy;
+                nvalid = !(ncx > 1023 || ncx < -1023 || ncy > 1023 || ncy < -1023);
+                if (nvalid) {
+                  int tx = (int16_t)(ncx + brx), ty = (int16_t)(ncy + bry);
+                  clamp_mv(tx, ty, col, row, cols, rows);
+                  mc_plan<16>(next, J.ref, g.y_pitch, g.W, g.H, px0, py0, tx, ty, lane);
+                }
+              }
+              if (have) {
+                const int cx = pcx, cy = pcy;
+                enc_mc16_finish(pending, J, g, S.pcand[cur], S, lane);
+                const uint32_t sad = enc_sad(src, S.pcand[cur], lane);
+                const int sx = max(min(cx >> 2, 255), -255), sy = max(min(cy >> 2, 255), -255);
+                const uint32_t rate =
+                    J.mv_sad_zero ? 0u : ((uint32_t)(T.mv_sad_cost[abs(sy)] + T.mv_sad_cost[abs(sx)]) * J.sad_per_bit + 128u) / 256u;
+                const uint32_t c = ((128u + rate) / 256u) + sad;  // rdcost( rate, distortion, 1, 1 )
+                if (c < bc) bc = c, bx2 = cx, by2 = cy;
+              }
+              if (site < 5 && nvalid) {
+                pending = next;
+                pcx = ncx, pcy = ncy;
+                have = true;
+              } else if (site < 5) {
+                have = false;
+              }
             }
             if (bx2 == ox && by2 == oy) first_step = sz / 2;
             ox = bx2, oy = by2;
