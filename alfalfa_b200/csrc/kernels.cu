@@ -1792,6 +1792,12 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __res
       if (!J.realtime || ((col & 3) == 0 && (row & 3) == 0)) {
         // ---- NEWMV: repeated diamond searches around the census' best vector (encode_inter.cc:172-229, 279-293) ----
         int mvx = 0, mvy = 0;
+        // The centre of a diamond is the best site of the diamond before it (or its centre again), whose cost was
+        // computed then -- the cost of a site depends on its position only -- so it is remembered instead of predicted
+        // and compared a second time; the comparison itself still happens in its place (third of five, strict <).
+        uint32_t known_c = 0;
+        int known_x = 0, known_y = 0;
+        bool known = false;
         for (int step = 512; step > 1;) {
           int ox = mvx, oy = mvy, first_step = step / 2;
           for (int sz = step; sz > 1; sz >>= 1) {
@@ -1801,17 +1807,18 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __res
             // filtered and compared, so its latency hides behind that work
             McPlan<16> pending;
             int pcx = 0, pcy = 0;
-            bool have = false;
+            bool have = false, pcached = false;
 #pragma unroll 1
             for (int site = 0; site <= 5; site++) {
               McPlan<16> next;
               int ncx = 0, ncy = 0;
-              bool nvalid = false;
+              bool nvalid = false, ncached = false;
               if (site < 5) {
                 const int dx = site == 0 ? -1 : (site == 4 ? 1 : 0), dy = site == 1 ? -1 : (site == 3 ? 1 : 0);
                 ncx = ox + sz * dx, ncy = oy + sz * dy;
                 nvalid = !(ncx > 1023 || ncx < -1023 || ncy > 1023 || ncy < -1023);
-                if (nvalid) {
+                ncached = nvalid && known && ncx == known_x && ncy == known_y;
+                if (nvalid && !ncached) {
                   int tx = (int16_t)(ncx + brx), ty = (int16_t)(ncy + bry);
                   clamp_mv(tx, ty, col, row, cols, rows);
                   mc_plan<16>(next, J.ref, g.y_pitch, g.W, g.H, px0, py0, tx, ty, lane);
@@ -1819,22 +1826,28 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __res
               }
               if (have) {
                 const int cx = pcx, cy = pcy;
-                enc_mc16_finish(pending, J, g, S.pcand[cur], S, lane);
-                const uint32_t sad = enc_sad(src, S.pcand[cur], lane);
-                const int sx = max(min(cx >> 2, 255), -255), sy = max(min(cy >> 2, 255), -255);
-                const uint32_t rate =
-                    J.mv_sad_zero ? 0u : ((uint32_t)(T.mv_sad_cost[abs(sy)] + T.mv_sad_cost[abs(sx)]) * J.sad_per_bit + 128u) / 256u;
-                const uint32_t c = ((128u + rate) / 256u) + sad;  // rdcost( rate, distortion, 1, 1 )
+                uint32_t c = known_c;
+                if (!pcached) {
+                  enc_mc16_finish(pending, J, g, S.pcand[cur], S, lane);
+                  const uint32_t sad = enc_sad(src, S.pcand[cur], lane);
+                  const int sx = max(min(cx >> 2, 255), -255), sy = max(min(cy >> 2, 255), -255);
+                  const uint32_t rate =
+                      J.mv_sad_zero ? 0u : ((uint32_t)(T.mv_sad_cost[abs(sy)] + T.mv_sad_cost[abs(sx)]) * J.sad_per_bit + 128u) / 256u;
+                  c = ((128u + rate) / 256u) + sad;  // rdcost( rate, distortion, 1, 1 )
+                }
                 if (c < bc) bc = c, bx2 = cx, by2 = cy;
               }
               if (site < 5 && nvalid) {
                 pending = next;
                 pcx = ncx, pcy = ncy;
+                pcached = ncached;
                 have = true;
               } else if (site < 5) {
                 have = false;
               }
             }
+            known = bc != 0xFFFFFFFFu;
+            known_c = bc, known_x = bx2, known_y = by2;
             if (bx2 == ox && by2 == oy) first_step = sz / 2;
             ox = bx2, oy = by2;
           }
