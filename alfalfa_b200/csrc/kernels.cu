@@ -1777,8 +1777,9 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __res
       const uint32_t c_new = T.mvref_one[0][score[0]] + T.mvref_one[1][score[1]] + T.mvref_one[2][score[2]] + T.mvref_zero[3][0];
       const int px0 = 16 * scol, py0 = 16 * srow;
       int cur = 0;
-      auto consider = [&](int mode, int vx, int vy, uint32_t rate) {
-        enc_mc16(J, g, px0, py0, vx, vy, S.pcand[cur], S, lane);
+      // a candidate = its prediction (window requested by mc_plan, filtered by enc_mc16_finish) and rdcost of its variance
+      auto judge = [&](const McPlan<16>& pl, int mode, int vx, int vy, uint32_t rate) {
+        enc_mc16_finish(pl, J, g, S.pcand[cur], S, lane);
         const uint32_t c = rdcost(rate, enc_variance(src, S.pcand[cur], lane), RM, DM);
         if (c < best_cost) {
           best_cost = c, best_mode = mode, best_mvx = vx, best_mvy = vy;
@@ -1786,9 +1787,22 @@ __global__ void __launch_bounds__(32 * WF_WARPS, 8) k_enc_rd(const EncJob* __res
           cur ^= 1;
         }
       };
-      consider(VP8GPU_ZEROMV, 0, 0, c_zero);
-      if (nrx | nry) consider(VP8GPU_NEARESTMV, nrx, nry, c_nearest);
-      if (nex | ney) consider(VP8GPU_NEARMV, nex, ney, c_near);
+      auto consider = [&](int mode, int vx, int vy, uint32_t rate) {
+        McPlan<16> pl;
+        mc_plan<16>(pl, J.ref, g.y_pitch, g.W, g.H, px0, py0, vx, vy, lane);
+        judge(pl, mode, vx, vy, rate);
+      };
+      {
+        // ZEROMV, NEARESTMV, NEARMV in the reference's order, each window requested one candidate ahead
+        const bool has_nearest = (nrx | nry) != 0, has_near = (nex | ney) != 0;
+        McPlan<16> pa, pb;
+        mc_plan<16>(pa, J.ref, g.y_pitch, g.W, g.H, px0, py0, 0, 0, lane);
+        if (has_nearest) mc_plan<16>(pb, J.ref, g.y_pitch, g.W, g.H, px0, py0, nrx, nry, lane);
+        judge(pa, VP8GPU_ZEROMV, 0, 0, c_zero);
+        if (has_near) mc_plan<16>(pa, J.ref, g.y_pitch, g.W, g.H, px0, py0, nex, ney, lane);
+        if (has_nearest) judge(pb, VP8GPU_NEARESTMV, nrx, nry, c_nearest);
+        if (has_near) judge(pa, VP8GPU_NEARMV, nex, ney, c_near);
+      }
       if (!J.realtime || ((col & 3) == 0 && (row & 3) == 0)) {
         // ---- NEWMV: repeated diamond searches around the census' best vector (encode_inter.cc:172-229, 279-293) ----
         int mvx = 0, mvy = 0;
