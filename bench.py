@@ -309,7 +309,7 @@ def bench_encode(a, local):
     return out
 
 
-def run_exchange(rank, world, local, timeout=240, tool_args=()):
+def run_exchange(rank, world, local, timeout=150, tool_args=()):
     """tools/split_gop_check.py on every rank's GPU, as child processes forming their own process group; rank 0 returns
     the tool's JSON (mismatches, hand-over time, raster exchange time per 1080p raster), the others None"""
     drop = ("TORCHELASTIC", "GROUP_", "ROLE_")  # torchrun's agent store must not be mistaken for the children's
