@@ -427,7 +427,11 @@ int vp8gpu_encoder_encode_with_quantizer(vp8gpu_encoder* enc, const uint8_t* y, 
                                          const uint8_t* v, size_t uv_stride, int y_ac_qi, uint8_t* out, size_t cap,
                                          size_t* size);
 /* Encoder::encode_with_target_size (encoder.cc:592-629): smallest quantiser index in the searched
- * range whose frame fits `target_size` bytes; *chosen_qi (optional) receives it. */
+ * range whose frame fits `target_size` bytes; *chosen_qi (optional) receives it.  The probes of the bisection
+ * (Encoder::estimate_frame_size at up to 33 quantiser indices) are coded in one kernel launch and the search walks the
+ * finished results in the reference's order; likewise the trials of the loop-filter search of every encode_* call
+ * (encoder.cc:460-508).  The emitted bytes do not depend on that (VP8GPU_ENC_SPECULATE=0 in the environment, read once
+ * per process, runs both searches candidate by candidate). */
 int vp8gpu_encoder_encode_with_target_size(vp8gpu_encoder* enc, const uint8_t* y, size_t y_stride, const uint8_t* u,
                                            const uint8_t* v, size_t uv_stride, size_t target_size, uint8_t* out,
                                            size_t cap, size_t* size, int* chosen_qi);
