@@ -72,14 +72,30 @@ int main() {
       REQUIRE(encoder.export_decoder() == receiver);
       REQUIRE(encoder.minihash() == receiver.minihash());
     }
+    // the same pattern through the target-size search, which is what salsify-sender runs on its two copies: two
+    // bisections at once, each coding its probes in one launch on its own lane, both writers on the shared host pool
+    for (int t = frames; t < frames + 3; t++) {
+      const Picture pic2 = synth(w, h, t);
+      const SourceFrame src = pic2.view(w);
+      Encoder big(encoder), small(encoder);
+      auto fut_big = std::async(std::launch::async, [&] { return big.encode_with_target_size(src, 3000); });
+      auto fut_small = std::async(std::launch::async, [&] { return small.encode_with_target_size(src, 1000); });
+      const std::vector<uint8_t> frame_big = fut_big.get(), frame_small = fut_small.get();
+      REQUIRE(!frame_big.empty() && !frame_small.empty());
+      REQUIRE(Encoder(encoder).encode_with_target_size(src, 3000) == frame_big);
+      REQUIRE(Encoder(encoder).encode_with_target_size(src, 1000) == frame_small);
+      receiver.get_frame_output(Chunk(frame_big));
+      encoder = big;
+      REQUIRE(encoder.export_decoder() == receiver);
+    }
     // Encoder( const Decoder & ): continue the receiver's stream
     Encoder continued(receiver);
-    const Picture pic = synth(w, h, frames);
+    const Picture pic = synth(w, h, frames + 3);
     const std::vector<uint8_t> next = continued.encode_with_quantizer(pic.view(w), 60);
     REQUIRE(!next.empty() && (next[0] & 1) == 1);  // an inter frame
     receiver.get_frame_output(Chunk(next));
     REQUIRE(continued.export_decoder() == receiver);
-    std::printf("ok %d\n", frames + 1);
+    std::printf("ok %d\n", frames + 4);
   } catch (const std::exception& e) {
     std::fprintf(stderr, "exception: %s\n", e.what());
     return 1;
