@@ -167,6 +167,7 @@ SYMBOLS = {
     "vp8gpu_decoder_deserialize": (C.c_int, [_vp, C.c_char_p, C.c_size_t, _pp]),
     "vp8gpu_decoder_hash": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "vp8gpu_encoder_stats": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vp8gpu_encoder_timeline": (C.c_int, [_vp, C.POINTER(C.c_double), C.c_int]),
     "vp8gpu_frame_ssim": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
     "vp8gpu_serialize_frame": (C.c_int, [C.POINTER(EncodeHeader), _vp, _vp, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "vp8gpu_serialize_frame_ex": (C.c_int, [C.POINTER(EncodeHeader), C.POINTER(EncodeFeatures), _vp, _vp, _vp, _vp, C.c_size_t,

@@ -21,6 +21,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <utility>
@@ -84,6 +85,7 @@ struct vp8gpu_encoder {
   // (serializer.h RefWriterState) -- byte-identical output; 1: compact -- only token-probability updates that
   // pay, no zero loop-filter deltas, eight DCT partitions written on eight host threads.
   int writer = 0;
+  double tl[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // vp8gpu_encoder_timeline: milliseconds per phase of the last encode call
   // speculative size estimates (estimate_batch_launch): EncJob[kEstMax] | ticket, token counters, row progress |
   // records, token pools and reconstruction rasters of every candidate -- private to this Encoder, allocated on
   // the first target-size search
@@ -99,6 +101,13 @@ struct vp8gpu_encoder {
 };
 
 namespace {
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+struct Phase {  // adds the time between construction and destruction to one slot of the timeline
+  double* slot;
+  double t0;
+  explicit Phase(double* s) : slot(s), t0(now_ms()) {}
+  ~Phase() { *slot += now_ms() - t0; }
+};
 constexpr int kEstMax = 33;   // size estimates per launch: a whole search range of last_y_ac_qi +- 16 (encoder.cc:604-611)
 constexpr int kLfMax = 4;     // loop-filter trials per launch (the steady-state range is the last level +- 1, encoder.cc:466-471)
 constexpr size_t kHdrBytes = 512 + 512 * kLfMax;  // pinned / device header area: EncJob | DevJob[kLfMax]
@@ -269,6 +278,7 @@ struct LateLevel {
   std::condition_variable cv;
   bool ready = false;
   int level = 0;
+  double waited_ms = 0;  // how long the writer stood still for the level (timeline)
   void set(int v) {
     {
       std::lock_guard<std::mutex> lk(m);
@@ -279,8 +289,10 @@ struct LateLevel {
   }
   static int wait(void* p) {
     LateLevel* l = static_cast<LateLevel*>(p);
+    const double t0 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
     std::unique_lock<std::mutex> lk(l->m);
     l->cv.wait(lk, [l] { return l->ready; });
+    l->waited_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count() - t0;
     return l->level;
   }
 };
@@ -842,7 +854,11 @@ static int encode_passes(vp8gpu_encoder* enc, bool key, int qi, int* frame) {
 static int encode_final(vp8gpu_encoder* enc, bool key, int qi, uint8_t* out, size_t cap, size_t* size) {
   int frame = -1, lf = 0;
   double ssim = -1.0;
-  int rc = encode_passes(enc, key, qi, &frame);
+  int rc;
+  {
+    Phase ph(&enc->tl[3]);
+    rc = encode_passes(enc, key, qi, &frame);
+  }
   if (rc != VP8GPU_OK) return rc;
   std::vector<uint8_t> bytes;
   uint8_t probs[1056];
@@ -855,19 +871,31 @@ static int encode_final(vp8gpu_encoder* enc, bool key, int qi, uint8_t* out, siz
     LateLevel late;
     int wrc = VP8GPU_OK;
     vp8::HostPool::Group writer;
-    writer.run([&] { wrc = encode_bytes(enc, key, qi, 0, 1, true, probs, bytes, &late); });
-    rc = choose_loop_filter(enc, &frame, key, &lf, &ssim);
+    writer.run([&] {
+      Phase ph(&enc->tl[5]);
+      wrc = encode_bytes(enc, key, qi, 0, 1, true, probs, bytes, &late);
+    });
+    {
+      Phase ph(&enc->tl[4]);
+      rc = choose_loop_filter(enc, &frame, key, &lf, &ssim);
+    }
     late.set(rc == VP8GPU_OK ? lf : 0);
     writer.wait();
+    enc->tl[5] -= late.waited_ms;  // the writer's own work
     if (rc == VP8GPU_OK) rc = wrc;
   } else {
-    rc = choose_loop_filter(enc, &frame, key, &lf, &ssim);
+    {
+      Phase ph(&enc->tl[4]);
+      rc = choose_loop_filter(enc, &frame, key, &lf, &ssim);
+    }
+    Phase ph(&enc->tl[5]);
     if (rc == VP8GPU_OK) rc = encode_bytes(enc, key, qi, lf, 1, true, probs, bytes);
   }
   if (rc != VP8GPU_OK) {
     enc->e->frame_release(frame);
     return rc;
   }
+  Phase ph(&enc->tl[6]);
   return finish_frame(enc, key, bytes, frame, qi, lf, ssim, out, cap, size);
 }
 
@@ -1003,7 +1031,10 @@ static void bisection_nodes(int lo, int hi, int depth, int* out, int* n) {
   bisection_nodes(mid + 1, hi, depth - 1, out, n);
 }
 static int estimate_probe(vp8gpu_encoder* enc, bool key, int lo, int hi, int qi, size_t* size) {
-  if (!enc_speculate()) return estimate_size(enc, key, qi, size);
+  if (!enc_speculate()) {
+    Phase ph(&enc->tl[1]);  // candidate by candidate: launch, wait, download and serialise are one thing
+    return estimate_size(enc, key, qi, size);
+  }
   int idx = -1;
   for (int i = 0; i < enc->est_n; i++)
     if (enc->est_qi[i] == qi) idx = i;
@@ -1014,12 +1045,17 @@ static int estimate_probe(vp8gpu_encoder* enc, bool key, int lo, int hi, int qi,
     } else {
       bisection_nodes(lo, hi, 3, qis, &n);
     }
-    const int rc = estimate_batch_launch(enc, key, qis, n);
+    int rc;
+    {
+      Phase ph(&enc->tl[1]);
+      rc = estimate_batch_launch(enc, key, qis, n);
+    }
     if (rc != VP8GPU_OK) return rc;
     for (int i = 0; i < enc->est_n; i++)
       if (enc->est_qi[i] == qi) idx = i;
     if (idx < 0) return enc->e->fail(VP8GPU_ERR_LOGIC, "size estimates: probe missing from its batch");
   }
+  Phase ph(&enc->tl[2]);
   return estimate_batch_size(enc, key, idx, size);
 }
 
@@ -1028,7 +1064,13 @@ int vp8gpu_encoder_encode_with_quantizer(vp8gpu_encoder* enc, const uint8_t* y, 
                                          size_t* size) {
   if (!enc || !y || !u || !v || !size || y_ac_qi < 0 || y_ac_qi > 127) return VP8GPU_ERR_LOGIC;
   cudaSetDevice(enc->e->device());
-  int rc = upload_source(enc, y, y_stride, u, v, uv_stride);
+  memset(enc->tl, 0, sizeof(enc->tl));
+  Phase whole(&enc->tl[7]);
+  int rc;
+  {
+    Phase ph(&enc->tl[0]);
+    rc = upload_source(enc, y, y_stride, u, v, uv_stride);
+  }
   if (rc != VP8GPU_OK) return rc;
   return encode_final(enc, !enc->has_state, y_ac_qi, out, cap, size);
 }
@@ -1038,7 +1080,13 @@ int vp8gpu_encoder_encode_with_target_size(vp8gpu_encoder* enc, const uint8_t* y
                                            size_t cap, size_t* size, int* chosen_qi) {
   if (!enc || !y || !u || !v || !size) return VP8GPU_ERR_LOGIC;
   cudaSetDevice(enc->e->device());
-  int rc = upload_source(enc, y, y_stride, u, v, uv_stride);
+  memset(enc->tl, 0, sizeof(enc->tl));
+  Phase whole(&enc->tl[7]);
+  int rc;
+  {
+    Phase ph(&enc->tl[0]);
+    rc = upload_source(enc, y, y_stride, u, v, uv_stride);
+  }
   if (rc != VP8GPU_OK) return rc;
   // Encoder::encode_with_target_size (encoder.cc:592-629), statement for statement: bisection over y_ac_qi in
   // [4, 127] or within 16 of the last frame's index; a candidate's size is the sampled estimate
@@ -1131,6 +1179,12 @@ int vp8gpu_encoder_stats(const vp8gpu_encoder* enc, double* ssim, int* loop_filt
   if (ssim) *ssim = enc->last_ssim;
   if (loop_filter_level) *loop_filter_level = enc->last_lf;
   if (y_ac_qi) *y_ac_qi = enc->last_qi;
+  return VP8GPU_OK;
+}
+
+int vp8gpu_encoder_timeline(const vp8gpu_encoder* enc, double* ms, int n) {
+  if (!enc || !ms || n < 0) return VP8GPU_ERR_LOGIC;
+  for (int i = 0; i < n && i < 8; i++) ms[i] = enc->tl[i];
   return VP8GPU_OK;
 }
 

@@ -549,6 +549,14 @@ class Encoder:
                                                            C.byref(size)), self.ctx.h, "reencode_as_interframe")
         return self._out[:size.value].tobytes()
 
+    TIMELINE = ("upload", "estimates_launch", "estimates_walk", "full_pass", "loop_filter_search", "writer", "state_update", "total")
+
+    def timeline(self):
+        """vp8gpu_encoder_timeline: milliseconds per phase of the last encode call (diagnostic)"""
+        ms = (C.c_double * 8)()
+        check(self.L.vp8gpu_encoder_timeline(self.h, ms, 8), self.ctx.h, "encoder_timeline")
+        return dict(zip(self.TIMELINE, (float(x) for x in ms)))
+
     def stats(self):
         """EncoderStats of the last frame: dict(ssim, loop_filter_level, y_ac_qi)"""
         q, lf, qi = C.c_double(0), C.c_int(0), C.c_int(0)

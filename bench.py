@@ -248,7 +248,7 @@ def bench_encode(a, local):
     enc.encode_with_target_size(*src[0], a.encode_target)  # warm-up (key frame, allocations)
     del enc
     enc = Encoder(ctx)
-    sizes, qis, psnrs, times, ssims, lfs, blobs, sses = [], [], [], [], [], [], [], []
+    sizes, qis, psnrs, times, ssims, lfs, blobs, sses, phases = [], [], [], [], [], [], [], [], []
     for t in range(n):
         t0 = time.perf_counter()
         blob, qi = enc.encode_with_target_size(*src[t], a.encode_target)
@@ -256,6 +256,7 @@ def bench_encode(a, local):
         sizes.append(len(blob))
         blobs.append(bytes(blob))
         qis.append(qi)
+        phases.append(enc.timeline())
         st = enc.stats()
         ssims.append(st["ssim"])
         lfs.append(st["loop_filter_level"])
@@ -272,6 +273,10 @@ def bench_encode(a, local):
            "fps": (n - 1) / sum(times[1:]), "key_frame_ms": times[0] * 1e3, "inter_frame_ms": 1e3 * sum(times[1:]) / (n - 1),
            "bytes_per_frame": sum(sizes) / n, "qi": qis, "loop_filter_level": lfs, "psnr_y": sum(psnrs) / n,
            "ssim_y": sum(ssims) / n, "gpu_launches": int(launches),
+           # host wall clock per phase of a call (vp8gpu_encoder_timeline), mean over the inter frames; every phase ends with
+           # its device work finished; `writer` runs next to `loop_filter_search`, so the phases add up to more than `total`
+           "inter_frame_phases_ms": {k: round(sum(p[k] for p in phases[1:]) / max(1, n - 1), 3) for k in (phases[0] if phases else {})},
+           "key_frame_phases_ms": {k: round(v, 3) for k, v in (phases[0] if phases else {}).items()},
            "note": "the reference encoder's decisions on the device (k_enc_rd: rdcost, B_PRED trial, motion-vector census, diamond "
                    "search, chroma by distortion) and its writer policy: the frames are byte-identical to the reference encoder's "
                    "(tests/test_gpu_encoder.py; `reference.identical_frames` below compares this very run)",

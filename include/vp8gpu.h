@@ -481,6 +481,14 @@ int vp8gpu_parsed_y_ac_qi(const vp8gpu_parsed* p);
 
 /* EncoderStats (encoder.hh:118-127) of the last frame; any pointer may be NULL. */
 int vp8gpu_encoder_stats(const vp8gpu_encoder* enc, double* ssim, int* loop_filter_level, int* y_ac_qi);
+/* Diagnostic: where the host spent the last encode_with_quantizer / encode_with_target_size call, wall-clock
+ * milliseconds per phase (each phase ends with the device work it queued being finished, so device time is inside):
+ * [0] source upload, [1] size estimates: kernel launch(es) + wait, [2] size estimates: download + serialise the probes
+ * the search visited, [3] the full pass (decisions, transforms, reconstruction) incl. download of records and tokens,
+ * [4] loop-filter search (the frame writer runs next to it), [5] the frame writer's own work (host thread, next to [4]; its wait for
+ * the level is not counted), [6] state update (parse of the emitted frame's first partition, reference hand-over), [7] the whole
+ * call.  n <= 8 values are written. */
+int vp8gpu_encoder_timeline(const vp8gpu_encoder* enc, double* ms, int n);
 /* the reconstruction of the last encoded frame = the decoder's LAST reference after decoding it
  * (Encoder::export_decoder, encoder.hh:378); the caller releases the returned raster */
 int vp8gpu_encoder_reconstruction(vp8gpu_encoder* enc, vp8gpu_frame_id* out);
