@@ -10,6 +10,11 @@ timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_inter|k_intra|k_loopfilter" -c 9 -f -o $O/r2_final_full python bench.py --steps 1 --warmup 1 --no-encode --no-cpu-baseline --gop-instances 64 > $O/r2_final_ncu_full.log 2>&1
 timeout 300 compute-sanitizer --tool memcheck --launch-timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > $O/r2_final_memcheck.log 2>&1
 timeout 300 compute-sanitizer --tool racecheck --launch-timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > $O/r2_final_racecheck.log 2>&1
+# the encoder's timeline: both search modes, then a launch list of the batched one (what the round-2 changes need next)
+timeout 60 python tools/enc_search_ab.py 8 45000 > $O/r2_final_enc_ab_on.json 2> $O/r2_final_enc_ab_on.err
+VP8GPU_ENC_SPECULATE=0 timeout 60 python tools/enc_search_ab.py 8 45000 > $O/r2_final_enc_ab_off.json 2> $O/r2_final_enc_ab_off.err
+timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/r2_final_enc_launches.csv python tools/enc_search_ab.py 4 45000 > $O/r2_final_enc_ncu.log 2>&1
+timeout 120 python tools/reencode_bench.py --frames 8 > $O/r2_final_reencode_bench.json 2> $O/r2_final_reencode_bench.err
 for wl in 4k 720p features; do
   timeout 240 python bench.py --workload $wl --no-encode --no-cpu-baseline --steps 3 --warmup 1 > $O/r2_final_bench_$wl.json 2> $O/r2_final_bench_$wl.err
 done
