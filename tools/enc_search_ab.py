@@ -24,13 +24,14 @@ def main():
     ctx = Context(w, h, max_frames=32)
     enc = Encoder(ctx)
     l0 = ctx.launch_count()
-    ms, sha, qis = [], [], []
+    ms, sha, qis, phases = [], [], [], []
     for t in range(n):
         t0 = time.perf_counter()
         blob, qi = enc.encode_with_target_size(*frames[t], target)
         ms.append(round((time.perf_counter() - t0) * 1e3, 3))
         sha.append(hashlib.sha1(bytes(blob)).hexdigest()[:16])
         qis.append(qi)
+        phases.append(enc.timeline())
     t0 = time.perf_counter()
     copy = enc.copy()
     t_copy1 = (time.perf_counter() - t0) * 1e3
@@ -41,7 +42,8 @@ def main():
     del copy
     out = {"speculate": os.environ.get("VP8GPU_ENC_SPECULATE", "1"), "frames": n, "target": target, "ms": ms, "qi": qis, "sha1": sha,
            "inter_fps": round(1e3 * (n - 1) / sum(ms[1:]), 2) if n > 1 else None, "launches": int(ctx.launch_count() - l0),
-           "encoder_copy_ms": [round(t_copy1, 3), round(t_copy2, 3)]}
+           "encoder_copy_ms": [round(t_copy1, 3), round(t_copy2, 3)],
+           "inter_frame_phases_ms": {k: round(sum(p[k] for p in phases[1:]) / max(1, n - 1), 3) for k in phases[0]}}
     del enc
     ctx.close()
     print(json.dumps(out))
