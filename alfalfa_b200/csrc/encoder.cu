@@ -109,7 +109,7 @@ struct Phase {  // adds the time between construction and destruction to one slo
   ~Phase() { *slot += now_ms() - t0; }
 };
 constexpr int kEstMax = 33;   // size estimates per launch: a whole search range of last_y_ac_qi +- 16 (encoder.cc:604-611)
-constexpr int kLfMax = 4;     // loop-filter trials per launch (the steady-state range is the last level +- 1, encoder.cc:466-471)
+constexpr int kLfMax = 8;     // loop-filter trials per launch (steady state: the last level +- 1, encoder.cc:466-471; a first frame walks up from 0)
 constexpr size_t kHdrBytes = 512 + 512 * kLfMax;  // pinned / device header area: EncJob | DevJob[kLfMax]
 static_assert(sizeof(vp8::EncJob) <= 512 && sizeof(vp8::DevJob) <= 512, "header area slots");
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
