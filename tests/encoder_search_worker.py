@@ -24,13 +24,14 @@ def main():
     for t in range(n):
         blob, qi = enc.encode_with_target_size(*synth(w, h, t), target if t else 4 * target)
         out.append({"qi": qi, "bytes": len(blob), "sha1": hashlib.sha1(bytes(blob)).hexdigest(), "stats": repr(enc.stats())})
+    timeline = enc.timeline()  # of the last encode_with_target_size call
     blob, qi = enc.encode_with_minimum_ssim(*synth(w, h, n), 0.93)
     out.append({"qi": qi, "bytes": len(blob), "sha1": hashlib.sha1(bytes(blob)).hexdigest(), "stats": repr(enc.stats())})
     out.append({"minihash": enc.minihash()})
     launches = ctx.launch_count() - l0
     del enc
     ctx.close()
-    print(json.dumps({"frames": out, "launches": launches}))
+    print(json.dumps({"frames": out, "launches": launches, "timeline": timeline}))
 
 
 if __name__ == "__main__":

@@ -322,6 +322,10 @@ def test_searches_in_one_launch_equal_candidate_by_candidate(w, h, n, target):
         assert r.returncode == 0, (r.stdout + r.stderr)[-1500:]
         res[mode] = json.loads(r.stdout.strip().splitlines()[-1])
     assert res["1"]["frames"] == res["0"]["frames"]
+    for mode in ("1", "0"):  # vp8gpu_encoder_timeline: every phase a time, the parts that run one after the other within the whole
+        tl = res[mode]["timeline"]
+        assert all(v >= 0 for v in tl.values()) and tl["total"] > 0 and tl["full_pass"] > 0
+        assert tl["upload"] + tl["estimates_launch"] + tl["estimates_walk"] + tl["full_pass"] + tl["loop_filter_search"] + tl["state_update"] <= tl["total"] * 1.001 + 0.05
     assert res["1"]["launches"] < res["0"]["launches"], (res["1"]["launches"], res["0"]["launches"])
 
 
