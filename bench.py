@@ -284,6 +284,19 @@ def bench_encode(a, local):
                         "the probes of the target-size bisection in one k_enc_rd launch (<= 33 sampled passes), the trials of the "
                         "loop-filter search in one k_loopfilter launch, the frame written on a host thread meanwhile "
                         "(same bytes as candidate by candidate: tests/test_gpu_encoder.py)")}
+    # SURVEY 8(d), encode: the probe-free minimum of a frame is source P + reference P read, reconstruction P written
+    # (P = 384 B per macroblock) + its coefficients; over the time of the full pass (k_enc_rd, one launch, incl. the
+    # download of its records: `full_pass` of the timeline) that is the fraction of the HBM roofline the decision kernel
+    # reaches -- it is a latency chain of (cols + rows) macroblock steps on 68 warps, not a bandwidth consumer
+    if phases and n > 1:
+        peak, peak_src = measured_peaks()
+        mbs = ((w + 15) // 16) * ((h + 15) // 16)
+        alg = 3 * 384 * mbs + 4.0 * (sum(sizes[1:]) / (n - 1))  # (tokens ~ bytes of the frame: an upper bound of 4 B per coded byte)
+        fp_ms = out["inter_frame_phases_ms"].get("full_pass", 0.0)
+        if fp_ms > 0:
+            out["roofline"] = {"bound": "hbm", "kernel": "k_enc_rd (full pass of an inter frame)", "bytes_per_frame": alg,
+                               "full_pass_ms": fp_ms, "achieved": alg / (fp_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                               "frac": alg / (fp_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": None}
     ref_enc = os.path.join(ROOT, "oracle", "_ref", "ref_encode")
     if os.path.exists(ref_enc):
         import tempfile
