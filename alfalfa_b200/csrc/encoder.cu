@@ -507,21 +507,37 @@ int upload_source(vp8gpu_encoder* enc, const uint8_t* y, size_t ys, const uint8_
   uint8_t* py = enc->h_src;
   uint8_t* pu = py + (size_t)g.W * g.H;
   uint8_t* pv = pu + (size_t)(g.W / 2) * (g.H / 2);
-  for (int r = 0; r < g.H; r++) {
-    const uint8_t* srow = y + (size_t)(r < h ? r : h - 1) * ys;
-    uint8_t* drow = py + (size_t)r * g.W;
-    memcpy(drow, srow, w);
-    if (g.W > w) memset(drow + w, srow[w - 1], g.W - w);
-  }
-  for (int pl = 0; pl < 2; pl++) {
-    const uint8_t* sp = pl ? v : u;
-    uint8_t* dp = pl ? pv : pu;
-    for (int r = 0; r < g.H / 2; r++) {
-      const uint8_t* srow = sp + (size_t)(r < ch ? r : ch - 1) * cs;
-      uint8_t* drow = dp + (size_t)r * (g.W / 2);
-      memcpy(drow, srow, cw);
-      if (g.W / 2 > cw) memset(drow + cw, srow[cw - 1], g.W / 2 - cw);
+  // the copy into pinned memory is on every call's critical path: the luma rows in four slices on the host pool
+  auto luma_rows = [&](int r0, int r1) {
+    for (int r = r0; r < r1; r++) {
+      const uint8_t* srow = y + (size_t)(r < h ? r : h - 1) * ys;
+      uint8_t* drow = py + (size_t)r * g.W;
+      memcpy(drow, srow, w);
+      if (g.W > w) memset(drow + w, srow[w - 1], g.W - w);
     }
+  };
+  auto chroma_rows = [&]() {
+    for (int pl = 0; pl < 2; pl++) {
+      const uint8_t* sp = pl ? v : u;
+      uint8_t* dp = pl ? pv : pu;
+      for (int r = 0; r < g.H / 2; r++) {
+        const uint8_t* srow = sp + (size_t)(r < ch ? r : ch - 1) * cs;
+        uint8_t* drow = dp + (size_t)r * (g.W / 2);
+        memcpy(drow, srow, cw);
+        if (g.W / 2 > cw) memset(drow + cw, srow[cw - 1], g.W / 2 - cw);
+      }
+    }
+  };
+  if ((size_t)g.W * g.H >= (size_t)640 * 480) {
+    vp8::HostPool::Group grp;
+    const int q = g.H / 4;
+    for (int k = 1; k < 4; k++) grp.run([&luma_rows, k, q, &g] { luma_rows(k * q, k == 3 ? g.H : (k + 1) * q); });
+    grp.run(chroma_rows);
+    luma_rows(0, q);
+    grp.wait();
+  } else {
+    luma_rows(0, g.H);
+    chroma_rows();
   }
   return e->frame_upload(enc->src, py, g.W, pu, pv, g.W / 2);
 }
