@@ -68,7 +68,7 @@ def make_case(w, h, n, qi_a, qi_b):
     return frames[n:], pred, state
 
 
-def product_reencode(w, h, targets, pred_chunks, state_blob, kf_q_weight, extra_frame_chunk, timeout=300):
+def product_reencode(w, h, targets, pred_chunks, state_blob, kf_q_weight, extra_frame_chunk, timeout=300, env=None):
     """the product's Encoder::reencode in a child process (tests/reencode_worker.py) under a timeout: returns
     (emitted frames, receiver-in-step flag)"""
     import pickle
@@ -78,10 +78,22 @@ def product_reencode(w, h, targets, pred_chunks, state_blob, kf_q_weight, extra_
         pickle.dump(dict(w=w, h=h, targets=[tuple(np.ascontiguousarray(p) for p in t) for t in targets], pred=list(pred_chunks),
                          state=bytes(state_blob), kf_q_weight=kf_q_weight, extra_frame_chunk=bool(extra_frame_chunk)), open(fin, "wb"))
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "reencode_worker.py"), fin, fout], capture_output=True, text=True,
-                           timeout=timeout)
+                           timeout=timeout, env=dict(os.environ, **(env or {})))
         assert r.returncode == 0, (r.stdout + r.stderr)[-1500:]
         out = pickle.load(open(fout, "rb"))
     return out["frames"], out["in_step"]
+
+
+@needs_ref
+def test_whole_chunk_the_same_with_the_shortcuts_off():
+    """VP8GPU_ENC_SPECULATE=0: the loop-filter trials one by one and the decode of every written frame through the
+    full parse instead of the token lists it was written from -- the same bytes, the receiver still in step"""
+    w, h = SIZES[-1]
+    n = 4
+    targets, pred, state = make_case(w, h, n, qi_a=40, qi_b=64)
+    want = reference_reencode(w, h, targets, pred, state, 0.75, False)
+    got, in_step = product_reencode(w, h, targets, pred, state, 0.75, False, env={"VP8GPU_ENC_SPECULATE": "0"})
+    assert got == want and in_step
 
 
 @needs_ref
